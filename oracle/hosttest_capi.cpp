@@ -1,0 +1,49 @@
+// oracle/hosttest_capi.cpp - TEST-ONLY library entry points: the product's host orchestrator
+// (parsnp_b200/csrc/host/*.cpp) linked with the CPU search backends of oracle/ so that `-m "not gpu"` tests can
+// exercise the host logic (queue order, trim, LCB chaining) without a GPU.  Never linked into libparsnp_b200.so.
+#include "../parsnp_b200/csrc/host/result.h"
+#include <cstdlib>
+#include <cstring>
+
+namespace pb200_oracle {
+pb200::SearchBackend* make_spec_backend();
+pb200::SearchBackend* make_ref_backend();
+struct SpecCand { int32_t k, lon; std::vector<int32_t> sp; std::vector<uint8_t> fwd; };
+void spec_window(const uint8_t* R, int64_t n, int nq, const uint8_t* const* Q, const int64_t* m, int minsize, std::vector<SpecCand>& out);
+void spec_lrp(const uint8_t* R, int64_t n, std::vector<int32_t>& lrp);
+}
+
+extern "C" {
+// backend: 0 = brute-force specification (oracle/mumspec.cpp), 1 = real csgmum (oracle/ref_backend.cpp)
+int pbtest_align(int backend, int n, const uint8_t* const* seqs, const int64_t* lens, const pb200_params* prm, pb200_result** out) {
+    try {
+        pb200::SearchBackend* be = backend == 0 ? pb200_oracle::make_spec_backend() : pb200_oracle::make_ref_backend();
+        pb200::Aligner a(n, seqs, lens, pb200::to_align_params(prm), be);
+        a.enable_trace(prm->flags & PB200_FLAG_TRACE_WINDOWS);
+        a.set_speculate(!(prm->flags & PB200_FLAG_NO_SPECULATION));
+        bool ok = a.run();
+        *out = pb200::make_result(a);
+        delete be;
+        return ok ? 0 : PB200_ERR_NO_MUMS;
+    } catch (const std::exception& e) { pb200::g_last_error = e.what(); return PB200_ERR_INTERNAL; }
+}
+// one window through a CPU backend; outputs malloc'ed like pb200_search_windows
+int pbtest_search_windows(int backend, int n, const uint8_t* const* seqs, const int64_t* lens, int ntasks, const pb200_window* tasks,
+                          const int64_t* coords, int64_t** cand_off, int32_t** k, int32_t** lon, int32_t** sp, uint8_t** fwd) {
+    pb200::SearchBackend* be = backend == 0 ? pb200_oracle::make_spec_backend() : pb200_oracle::make_ref_backend();
+    be->set_genomes(n, seqs, lens);
+    pb200::CandBatch cb;
+    be->search((const pb200::WindowTask*)tasks, ntasks, coords, cb);
+    delete be;
+    auto dup = [](const void* p, size_t bytes) { void* q = malloc(bytes ? bytes : 1); if (bytes) memcpy(q, p, bytes); return q; };
+    *cand_off = (int64_t*)dup(cb.off.data(), cb.off.size() * 8);
+    *k = (int32_t*)dup(cb.k.data(), cb.k.size() * 4);
+    *lon = (int32_t*)dup(cb.lon.data(), cb.lon.size() * 4);
+    *sp = (int32_t*)dup(cb.sp.data(), cb.sp.size() * 4);
+    *fwd = (uint8_t*)dup(cb.fwd.data(), cb.fwd.size());
+    return 0;
+}
+int pbtest_lrp(const uint8_t* R, int64_t n, int32_t* out) {
+    std::vector<int32_t> v; pb200_oracle::spec_lrp(R, n, v); memcpy(out, v.data(), n * 4); return 0;
+}
+}

@@ -1,0 +1,105 @@
+"""Drive oracle/_ref/parsnp_core_ref (the REAL reference binary, built by oracle/build_ref.py).
+
+TEST INFRASTRUCTURE ONLY - see oracle/build_ref.py header.  Writes the minimal ini of
+SURVEY.md App. D (mirrors template.ini with the driver's defaults) and parses the hook dumps.
+"""
+import os
+import re
+import subprocess
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EXE = os.path.join(HERE, "_ref", "parsnp_core_ref")
+
+DEFAULTS = dict(anchors="1.1*(Log(S))", mums="1.1*(Log(S))", filter=1, factor="2.0", extendmums=0,
+                anchorsonly=0, calcmumi=0, recombfilter=0, cores=8, diagdiff="0.12", doalign=2,
+                c=21, d=300, q=30, p=15000000, unaligned=0)
+
+
+def write_ini(path, ref, queries, outdir, **kw):
+    o = dict(DEFAULTS)
+    o.update(kw)
+    L = ["[Reference]", "file=%s" % ref, "reverse=0", "[Query]"]
+    for i, q in enumerate(queries):
+        L += ["file%d=%s" % (i + 1, q), "reverse%d=0" % (i + 1)]
+    L += ["[MUM]", "anchors=%s" % o["anchors"], "anchorfile=", "anchorsonly=%d" % o["anchorsonly"],
+          "calcmumi=%d" % o["calcmumi"], "mums=%s" % o["mums"], "mumfile=", "filter=%d" % o["filter"],
+          "factor=%s" % o["factor"], "extendmums=%d" % o["extendmums"],
+          "[LCB]", "recombfilter=%d" % o["recombfilter"], "cores=%d" % o["cores"], "diagdiff=%s" % o["diagdiff"],
+          "doalign=%d" % o["doalign"], "c=%d" % o["c"], "d=%d" % o["d"], "q=%d" % o["q"], "p=%d" % o["p"],
+          "icr=0", "unaligned=%d" % o["unaligned"], "[Output]", "outdir=%s" % outdir, "prefix=parsnp", "showbps=1"]
+    with open(path, "w") as f:
+        f.write("\n".join(L) + "\n")
+    return path
+
+
+def parse_dump(path):
+    """-> dict(n, mums=[(length, slength, [(start,end,fwd)...])], clusters=[(type, nm, length, [(start,end)...])])"""
+    mums, clusters, n = [], [], 0
+    with open(path) as f:
+        for line in f:
+            t = line.split()
+            if not t:
+                continue
+            if t[0] == "N":
+                n = int(t[1])
+            elif t[0] == "M":
+                mums.append((int(t[1]), int(t[2]), [tuple(int(x) for x in s.split(":")) for s in t[3:]]))
+            elif t[0] == "C":
+                clusters.append((int(t[1]), int(t[2]), int(t[3]), [tuple(int(x) for x in s.split(":")) for s in t[4:]]))
+    return dict(n=n, mums=mums, clusters=clusters)
+
+
+def parse_cands(path):
+    """-> list of windows: dict(anchors, minsize, ini0, len0, region=[(start,len)..], cands=[(LON, [(dsp,fwd)..])])"""
+    wins = []
+    with open(path) as f:
+        for line in f:
+            t = line.split()
+            if not t:
+                continue
+            if t[0] == "W":
+                wins.append(dict(anchors=int(t[1]), minsize=int(t[2]), ini0=int(t[3]), len0=int(t[4]),
+                                 region=[tuple(int(x) for x in s.split(":")) for s in t[6:]], cands=[]))
+            elif t[0] == "K":
+                wins[-1]["cands"].append((int(t[1]), [tuple(int(x) for x in s.split(":")) for s in t[2:]]))
+    return wins
+
+
+def run_ref(ref, queries, workdir, dump=True, cands=False, dump_exit=True, timeout=None, **kw):
+    """run the reference binary; returns dict(dump=..., cands=..., mumlcb_seconds=..., wall=..., stdout=...)"""
+    if not os.path.exists(EXE):
+        raise RuntimeError("oracle/_ref/parsnp_core_ref missing: run python oracle/build_ref.py")
+    os.makedirs(workdir, exist_ok=True)
+    outdir = os.path.join(workdir, "out")
+    os.makedirs(outdir, exist_ok=True)
+    ini = write_ini(os.path.join(workdir, "ref.ini"), ref, queries, outdir, **kw)
+    env = dict(os.environ)
+    res = {}
+    if dump:
+        env["PARSNP_ORACLE_DUMP"] = os.path.join(workdir, "dump.txt")
+        if dump_exit:
+            env["PARSNP_ORACLE_DUMP_EXIT"] = "1"
+        if os.path.exists(env["PARSNP_ORACLE_DUMP"]):
+            os.remove(env["PARSNP_ORACLE_DUMP"])
+    if cands:
+        env["PARSNP_ORACLE_CANDS"] = os.path.join(workdir, "cands.txt")
+        if os.path.exists(env["PARSNP_ORACLE_CANDS"]):
+            os.remove(env["PARSNP_ORACLE_CANDS"])
+    t0 = time.time()
+    r = subprocess.run([EXE, ini], cwd=workdir, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       text=True, timeout=timeout)
+    res["wall"] = time.time() - t0
+    res["returncode"] = r.returncode
+    res["stdout"] = r.stdout
+    res["stderr"] = r.stderr
+    m = re.search(r"ORACLE_MUMLCB_SECONDS=([0-9.]+)", r.stderr)
+    res["mumlcb_seconds"] = float(m.group(1)) if m else None
+    res["outdir"] = outdir
+    if dump and os.path.exists(env["PARSNP_ORACLE_DUMP"]):
+        res["dump"] = parse_dump(env["PARSNP_ORACLE_DUMP"])
+    else:
+        res["dump"] = None
+    if cands and os.path.exists(env.get("PARSNP_ORACLE_CANDS", "")):
+        res["cands"] = parse_cands(env["PARSNP_ORACLE_CANDS"])
+    return res

@@ -1,0 +1,251 @@
+"""ctypes mirror of include/parsnp_b200.h - the Python host side above the C ABI.
+
+Mirrors the reference's operator surface for the MUM + LCB path: genomes in (after the ingest rules of
+src/parsnp.cpp:2999-3133), `this->mums` / `this->clusters` out (as at src/parsnp.cpp:505).  The product library is
+CUDA-only; importing works anywhere, computing without a B200-class GPU raises Pb200Error (no CPU fallback).
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libparsnp_b200.so")
+
+FLAG_TRACE_WINDOWS = 1
+FLAG_NO_SPECULATION = 2
+
+
+class Pb200Error(RuntimeError):
+    pass
+
+
+class CParams(C.Structure):
+    _fields_ = [("c", C.c_int32), ("d", C.c_int32), ("q", C.c_int32), ("p", C.c_int64), ("diagdiff", C.c_float),
+                ("filter", C.c_int32), ("anchors_only", C.c_int32), ("anchors", C.c_char_p), ("mums", C.c_char_p),
+                ("flags", C.c_int32), ("reserved", C.c_int32)]
+
+
+class CWindow(C.Structure):
+    _fields_ = [("ref_start", C.c_int64), ("ref_len", C.c_int64), ("coord_off", C.c_int64), ("minsize", C.c_int32),
+                ("pad", C.c_int32)]
+
+
+def make_params(c=21, d=300, q=30, p=15000000, diagdiff=0.12, filter=1, anchors_only=0,
+                anchors="1.1*(Log(S))", mums="1.1*(Log(S))", flags=0):
+    return CParams(c, d, q, p, diagdiff, filter, anchors_only, anchors.encode(), mums.encode(), flags, 0)
+
+
+def _decl_result_api(lib):
+    vp = C.c_void_p
+    lib.pb200_last_error.restype = C.c_char_p
+    lib.pb200_result_n.argtypes = [vp]
+    lib.pb200_result_num_mums.argtypes = [vp]
+    lib.pb200_result_num_mums.restype = C.c_int64
+    lib.pb200_result_mums.argtypes = [vp] + [vp] * 5
+    lib.pb200_result_num_clusters.argtypes = [vp]
+    lib.pb200_result_num_clusters.restype = C.c_int64
+    lib.pb200_result_clusters.argtypes = [vp] + [vp] * 5
+    lib.pb200_result_num_trace.argtypes = [vp]
+    lib.pb200_result_num_trace.restype = C.c_int64
+    lib.pb200_result_trace.argtypes = [vp, vp]
+    lib.pb200_result_stats.argtypes = [vp, vp, C.c_int]
+    lib.pb200_stats_names.restype = C.c_char_p
+    lib.pb200_result_free.argtypes = [vp]
+    lib.pb200_minsize.argtypes = [C.c_char_p, C.c_int64]
+    lib.pb200_free_buffer.argtypes = [vp]
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def unpack_result(lib, h):
+    """pb200_result* -> dict of numpy arrays; frees the handle"""
+    n = lib.pb200_result_n(h)
+    M = lib.pb200_result_num_mums(h)
+    length = np.zeros(M, np.int64); slength = np.zeros(M, np.int64)
+    start = np.zeros((M, n), np.int64); end = np.zeros((M, n), np.int64); fwd = np.zeros((M, n), np.uint8)
+    lib.pb200_result_mums(h, _ptr(length), _ptr(slength), _ptr(start), _ptr(end), _ptr(fwd))
+    K = lib.pb200_result_num_clusters(h)
+    ctype = np.zeros(K, np.int32); cn = np.zeros(K, np.int64); cl = np.zeros(K, np.int64)
+    cs = np.zeros((K, n), np.int64); ce = np.zeros((K, n), np.int64)
+    lib.pb200_result_clusters(h, _ptr(ctype), _ptr(cn), _ptr(cl), _ptr(cs), _ptr(ce))
+    T = lib.pb200_result_num_trace(h)
+    tr = np.zeros((T, 2), np.int64)
+    if T:
+        lib.pb200_result_trace(h, _ptr(tr))
+    names = lib.pb200_stats_names().decode().split(",")
+    sv = np.zeros(len(names), np.float64)
+    lib.pb200_result_stats(h, _ptr(sv), len(names))
+    lib.pb200_result_free(h)
+    return dict(n=n, mum_length=length, mum_slength=slength, mum_start=start, mum_end=end, mum_fwd=fwd,
+                cluster_type=ctype, cluster_nmums=cn, cluster_length=cl, cluster_start=cs, cluster_end=ce,
+                trace=tr, stats=dict(zip(names, sv.tolist())))
+
+
+def _seq_arrays(genomes):
+    """genomes: list of numpy uint8 ASCII arrays -> (keepalive list, uint8** array, int64 lens)"""
+    gs = [np.ascontiguousarray(g, dtype=np.uint8) for g in genomes]
+    n = len(gs)
+    ptrs = (C.c_void_p * n)(*[g.ctypes.data for g in gs])
+    lens = np.array([len(g) for g in gs], np.int64)
+    return gs, ptrs, lens
+
+
+_lib = None
+
+
+def load():
+    """load the product library (built by __graft_entry__.build()); fails loudly if it is missing"""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Pb200Error("parsnp_b200: %s not built - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "(the CUDA extension is required; there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    _decl_result_api(lib)
+    vp = C.c_void_p
+    lib.pb200_version.restype = C.c_char_p
+    lib.pb200_genomes_create.argtypes = [C.c_int, C.c_int, vp, vp, vp]
+    lib.pb200_genomes_free.argtypes = [vp]
+    lib.pb200_search_windows.argtypes = [vp, C.c_int, vp, vp, C.c_int64] + [vp] * 5
+    lib.pb200_align_resident.argtypes = [vp, vp, vp]
+    lib.pb200_align.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp]
+    lib.pb200_engine_timers.argtypes = [vp, vp, C.c_int]
+    lib.pb200_engine_timer_names.restype = C.c_char_p
+    lib.pb200_engine_reset_timers.argtypes = [vp]
+    lib.pb200_comm_unique_id.argtypes = [C.c_char_p, vp]
+    lib.pb200_comm_init.argtypes = [vp, C.c_char_p, vp, C.c_int, C.c_int]
+    lib.pb200_comm_destroy.argtypes = [vp]
+    _lib = lib
+    return lib
+
+
+def _check(lib, rc, allow=()):
+    if rc != 0 and rc not in allow:
+        raise Pb200Error("parsnp_b200 error %d: %s" % (rc, lib.pb200_last_error().decode()))
+    return rc
+
+
+def cuda_available():
+    return bool(load().pb200_cuda_available())
+
+
+def minsize(expr, slength):
+    return load().pb200_minsize(expr.encode(), int(slength))
+
+
+class Genomes:
+    """genome texts resident in HBM (pb200_genomes)"""
+
+    def __init__(self, genomes, device=0):
+        self.lib = load()
+        self._keep, self._ptrs, self._lens = _seq_arrays(genomes)
+        self.n = len(self._keep)
+        self.h = C.c_void_p()
+        _check(self.lib, self.lib.pb200_genomes_create(device, self.n, self._ptrs, _ptr(self._lens), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.lib.pb200_genomes_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def align(self, params=None):
+        prm = params or make_params()
+        out = C.c_void_p()
+        rc = _check(self.lib, self.lib.pb200_align_resident(self.h, C.byref(prm), C.byref(out)), allow=(-5,))
+        res = unpack_result(self.lib, out)
+        res["no_mums"] = rc == -5
+        return res
+
+    def search_windows(self, windows, coords):
+        """windows: list of (ref_start, ref_len, coord_off, minsize); coords: int64 array.
+        -> list per window of (k[], lon[], sp[c, n-1], fwd[c, n-1])"""
+        nt = len(windows)
+        arr = (CWindow * nt)(*[CWindow(int(a), int(b), int(c), int(d), 0) for a, b, c, d in windows])
+        coords = np.ascontiguousarray(coords, np.int64)
+        off = C.POINTER(C.c_int64)(); k = C.POINTER(C.c_int32)(); lon = C.POINTER(C.c_int32)()
+        sp = C.POINTER(C.c_int32)(); fwd = C.POINTER(C.c_uint8)()
+        _check(self.lib, self.lib.pb200_search_windows(self.h, nt, arr, _ptr(coords), len(coords), C.byref(off), C.byref(k),
+                                                       C.byref(lon), C.byref(sp), C.byref(fwd)))
+        res = _unpack_cands(off, k, lon, sp, fwd, nt, self.n - 1)
+        for p in (off, k, lon, sp, fwd):
+            self.lib.pb200_free_buffer(p)
+        return res
+
+    def engine_timers(self):
+        names = self.lib.pb200_engine_timer_names().decode().split(",")
+        v = np.zeros(len(names), np.float64)
+        self.lib.pb200_engine_timers(self.h, _ptr(v), len(names))
+        return dict(zip(names, v.tolist()))
+
+    def reset_timers(self):
+        self.lib.pb200_engine_reset_timers(self.h)
+
+
+def _unpack_cands(off, k, lon, sp, fwd, nt, nq):
+    o = np.ctypeslib.as_array(off, shape=(nt + 1,)).copy()
+    tot = int(o[-1])
+    kk = np.ctypeslib.as_array(k, shape=(max(tot, 1),))[:tot].copy()
+    ll = np.ctypeslib.as_array(lon, shape=(max(tot, 1),))[:tot].copy()
+    ss = np.ctypeslib.as_array(sp, shape=(max(tot * nq, 1),))[:tot * nq].copy().reshape(tot, nq)
+    ff = np.ctypeslib.as_array(fwd, shape=(max(tot * nq, 1),))[:tot * nq].copy().reshape(tot, nq)
+    return [(kk[o[t]:o[t + 1]], ll[o[t]:o[t + 1]], ss[o[t]:o[t + 1]], ff[o[t]:o[t + 1]]) for t in range(nt)]
+
+
+def align(genomes, params=None, device=0):
+    """end-to-end call with host buffers: upload + MUM/LCB path (pb200_align)"""
+    lib = load()
+    keep, ptrs, lens = _seq_arrays(genomes)
+    prm = params or make_params()
+    out = C.c_void_p()
+    rc = _check(lib, lib.pb200_align(device, len(keep), ptrs, _ptr(lens), C.byref(prm), C.byref(out)), allow=(-5,))
+    res = unpack_result(lib, out)
+    res["no_mums"] = rc == -5
+    return res
+
+
+# ---------------------------------------------------------------- ingest (host, mirrors src/parsnp.cpp:2973-3142)
+_INGEST = np.zeros(256, np.uint8)          # 0 = skipped character
+for _ch in b"ACGT":
+    _INGEST[_ch] = _ch
+    _INGEST[_ch + 32] = _ch
+for _ch in b"XYSWKHRMVDBN":
+    _INGEST[_ch] = ord("N")
+    _INGEST[_ch + 32] = ord("N")
+_INGEST[ord("U")] = ord("T"); _INGEST[ord("u")] = ord("T")
+_INGEST[ord("-")] = ord("N")
+
+
+def ingest_fasta(path, is_ref, d=300):
+    """FASTA -> uint8 ASCII genome exactly as parsnp_core builds `genomes[i]`: the first line is the header whatever
+    it contains; A,C,G,T kept (case folded); IUPAC codes, '-' -> N; U -> T; every other character skipped; each
+    further '>' line ends a contig and, in queries only, appends d+10 N's (src/parsnp.cpp:3106-3126)."""
+    with open(path, "rb") as f:
+        data = f.read()
+    nl = data.find(b"\n")
+    body = data[nl + 1:] if nl >= 0 else b""
+    parts = []
+    pos = 0
+    pad = np.full(d + 10, ord("N"), np.uint8)
+    while True:
+        gt = body.find(b">", pos)
+        chunk = body[pos:gt if gt >= 0 else len(body)]
+        a = _INGEST[np.frombuffer(chunk, np.uint8)]
+        parts.append(a[a != 0])
+        if gt < 0:
+            break
+        if not is_ref:
+            parts.append(pad)
+        e = body.find(b"\n", gt)
+        if e < 0:
+            break
+        pos = e + 1
+    return np.concatenate(parts) if parts else np.zeros(0, np.uint8)

@@ -1,0 +1,160 @@
+// Host orchestrator of the MUM + LCB path: anchors -> recursive inter-anchor search -> LCB chaining.
+//
+// This is a from-scratch C++ restatement of the *observable behaviour* of the reference's Aligner hot methods
+// (src/parsnp.cpp: setInitialClusters 2121-2174, setMums1 1484-1862 [loop D: validation/trim/accept],
+// trim 1399-1477, determineRegion 1199-1290, doWork 173-317, filterRandom1 327-425, setFinalClusters 2563-2719,
+// filterRandomClustersSimple1 433-497, setInterClusterRegions 2389-2460) with different data structures:
+//   * mumlayout is a packed 64-bit bitmap with word-level scans instead of vector<bool> bit loops;
+//   * MUMs / regions live in flat SoA pools instead of vector<vector<long>> objects;
+//   * the index build + scan + fold + emission of setMums1 (its calls into csgmum) is delegated to a
+//     SearchBackend (the CUDA engine), batched over many regions at once;
+//   * the recursion runs as  (1) a speculative, level-synchronous pass that only exists to discover which
+//     regions will be searched and to batch them onto the GPU, then (2) an exact sequential replay in the
+//     reference's own order (pop smallest start[0], push children, sort, drop adjacent duplicates) that looks
+//     the candidates up by region coordinates and asks the GPU for any region the speculation did not predict.
+//     The search is a pure function of the region coordinates, so pass (2) is exact by construction.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <unordered_map>
+#include <map>
+#include "../common.h"
+#include "minsize.h"
+
+namespace pb200 {
+
+struct AlignParams {                 // ini keys, src/parsnp.cpp:2866-2901
+    int c = 21;                      // [LCB] c
+    int d = 300;                     // [LCB] d
+    int q = 30;                      // [LCB] q
+    int64_t p = 15000000;            // [LCB] p
+    float diag_diff = 0.12f;         // [LCB] diagdiff
+    int random = 1;                  // [MUM] filter
+    bool anchors_only = false;       // [MUM] anchorsonly
+    std::string anchors = "1.1*(Log(S))";
+    std::string mums = "1.1*(Log(S))";
+};
+
+// packed mumlayout row (src/parsnp.cpp:3181-3186: len+1 bits, sentinel bit at len)
+class BitRow {
+public:
+    void init(int64_t nbits_with_sentinel);
+    inline bool get(int64_t i) const { return (w_[i >> 6] >> (i & 63)) & 1ull; }
+    void set_range(int64_t a, int64_t b);     // [a,b)
+    void clear_range(int64_t a, int64_t b);   // [a,b)
+    int64_t run_up(int64_t a, int64_t b) const;     // # consecutive set bits a, a+1, ... (< b)
+    int64_t run_down(int64_t a, int64_t b) const;   // # consecutive set bits b-1, b-2, ... (>= a)
+    int64_t prev_set(int64_t i) const;        // largest set index <= i, or -1
+    int64_t next_set(int64_t i, int64_t limit) const;   // smallest set index in [i,limit), or limit
+    int64_t nbits() const { return nbits_; }
+private:
+    std::vector<uint64_t> w_;
+    int64_t nbits_ = 0;
+};
+
+struct MumRec {
+    int64_t length;
+    int64_t slength;
+    int64_t off;       // offset into mum_start_/mum_fwd_ pools (n entries)
+    bool alive;
+};
+
+struct ClusterRec {
+    int type;                       // 1 = LCB, 0 = inter-cluster record
+    int64_t length;
+    std::vector<int> mums;          // indices into the (sorted) final MUM list; empty for type 0
+    std::vector<int64_t> start, end;
+};
+
+struct AlignStats {
+    int64_t anchors = 0, regions_searched = 0, spec_regions = 0, replay_misses = 0, spec_levels = 0,
+            windows_searched = 0, candidates = 0, slow_queue_iters = 0;
+    double t_anchor_search = 0, t_anchor_host = 0, t_spec_search = 0, t_spec_host = 0, t_replay = 0,
+           t_replay_search = 0, t_lcb = 0, t_total = 0;
+};
+
+class Aligner {
+public:
+    Aligner(int n, const uint8_t* const* seq, const int64_t* len, const AlignParams& prm, SearchBackend* be);
+    // returns false when no MUMs were found (reference: "NO MUMS FOUND", src/parsnp.cpp:3223-3229)
+    bool run();
+
+    // ---- results (valid after run()) ----
+    int n() const { return n_; }
+    // final MUM list in the order of this->mums at writeOutput time (sorted by start[0])
+    int64_t num_mums() const { return (int64_t)final_mums_.size(); }
+    const MumRec& mum(int64_t i) const { return mums_[final_mums_[i]]; }
+    const int64_t* mum_start(int64_t i) const { return &mum_start_[mums_[final_mums_[i]].off]; }
+    const uint8_t* mum_fwd(int64_t i) const { return &mum_fwd_[mums_[final_mums_[i]].off]; }
+    const std::vector<ClusterRec>& clusters() const { return clusters_; }
+    const AlignStats& stats() const { return stats_; }
+    // sequence of searched windows in exact reference order (ref_start, ref_len) - for order tests
+    const std::vector<std::pair<int64_t, int64_t>>& window_trace() const { return trace_; }
+    void enable_trace(bool on) { trace_on_ = on; }
+    void set_speculate(bool on) { speculate_ = on; }
+
+private:
+    // ---- region pool: 2n coords per region (start[n], end[n]) ----
+    int new_region(const int64_t* start, const int64_t* end);
+    inline const int64_t* rstart(int r) const { return &rcoord_[(size_t)r * 2 * n_]; }
+    inline const int64_t* rend(int r) const { return &rcoord_[(size_t)r * 2 * n_ + n_]; }
+    bool region_equal(int a, int b) const;
+    uint64_t region_hash(int r) const;
+
+    struct World {                     // one copy of the mutable alignment state
+        std::vector<BitRow> layout;
+    };
+
+    // search + cache
+    struct CacheEntry { int region; int64_t first_win; int nwin; };
+    int cache_lookup(int r) const;                    // -> index into cache_entries_ or -1
+    void search_regions(const std::vector<int>& regs, bool anchors);   // batched GPU search, fills the cache
+
+    // setMums1 loop D on cached candidates; appends accepted MUM ids to `found`
+    void accept_candidates(int r, int cache_idx, World& w, std::vector<int>& found);
+    int determine_region(const World& w, const int64_t* mstart, int64_t mlen, bool left);
+
+    void set_initial_clusters();     // anchors
+    void speculate(const std::vector<int>& initial, const World& truth);
+    void do_work_exact();
+    void filter_random1();
+    void set_final_clusters(std::vector<ClusterRec>& out);
+    void filter_clusters_simple(std::vector<ClusterRec>& cl);
+    void set_inter_cluster_regions(std::vector<ClusterRec>& cl);
+
+    int n_;
+    std::vector<const uint8_t*> seq_;
+    std::vector<int64_t> len_;
+    AlignParams prm_;
+    SearchBackend* be_;
+    MinSizeExpr anchor_expr_, mum_expr_;
+
+    std::vector<int64_t> rcoord_;
+    std::vector<int64_t> rslength_;
+
+    std::vector<MumRec> mums_;
+    std::vector<int64_t> mum_start_;
+    std::vector<uint8_t> mum_fwd_;
+    std::vector<int> all_mums_;       // this->mums in push order (ids into mums_)
+    std::vector<int> final_mums_;
+
+    World truth_;
+    std::vector<int> initial_regions_;
+
+    // candidate cache
+    struct WinRec { int64_t ref_start, ref_len; int64_t cand_off; int32_t ncand; int32_t minsize; };
+    std::vector<WinRec> wins_;
+    std::vector<int32_t> ck_, clon_, csp_;
+    std::vector<uint8_t> cfwd_;
+    std::vector<CacheEntry> cache_entries_;
+    std::unordered_multimap<uint64_t, int> cache_map_;
+
+    std::vector<ClusterRec> clusters_;
+    AlignStats stats_;
+    std::vector<std::pair<int64_t, int64_t>> trace_;
+    bool trace_on_ = false;
+    bool speculate_ = true;
+};
+
+}  // namespace pb200

@@ -1,0 +1,85 @@
+#include "result.h"
+#include <cstring>
+
+namespace pb200 {
+thread_local std::string g_last_error;
+
+pb200_result* make_result(const Aligner& a) {
+    pb200_result* r = new pb200_result;
+    const int n = a.n();
+    r->n = n;
+    const int64_t M = a.num_mums();
+    r->m_length.resize(M); r->m_slength.resize(M);
+    r->m_start.resize(M * n); r->m_end.resize(M * n); r->m_fwd.resize(M * n);
+    for (int64_t i = 0; i < M; ++i) {
+        const MumRec& m = a.mum(i);
+        r->m_length[i] = m.length; r->m_slength[i] = m.slength;
+        const int64_t* s = a.mum_start(i); const uint8_t* f = a.mum_fwd(i);
+        for (int k = 0; k < n; ++k) { r->m_start[i * n + k] = s[k]; r->m_end[i * n + k] = s[k] + m.length; r->m_fwd[i * n + k] = f[k]; }
+    }
+    for (const ClusterRec& c : a.clusters()) {
+        r->c_type.push_back(c.type); r->c_nmums.push_back(c.type == 1 ? (int64_t)c.mums.size() : 2); r->c_length.push_back(c.length);
+        r->c_start.insert(r->c_start.end(), c.start.begin(), c.start.end());
+        r->c_end.insert(r->c_end.end(), c.end.begin(), c.end.end());
+    }
+    for (auto& p : a.window_trace()) { r->trace.push_back(p.first); r->trace.push_back(p.second); }
+    const AlignStats& s = a.stats();
+    r->stats = { (double)s.anchors, (double)s.regions_searched, (double)s.spec_regions, (double)s.replay_misses,
+                 (double)s.spec_levels, (double)s.windows_searched, (double)s.candidates, (double)s.slow_queue_iters,
+                 s.t_anchor_search, s.t_anchor_host, s.t_spec_search, s.t_spec_host, s.t_replay, s.t_replay_search,
+                 s.t_lcb, s.t_total };
+    return r;
+}
+
+AlignParams to_align_params(const pb200_params* p) {
+    AlignParams a;
+    a.c = p->c; a.d = p->d; a.q = p->q; a.p = p->p; a.diag_diff = p->diagdiff;
+    if (a.diag_diff < 0.0 || a.diag_diff > 10000000) a.diag_diff = 1.0;      // src/parsnp.cpp:2873-2876
+    a.random = p->filter; a.anchors_only = p->anchors_only != 0;
+    if (p->anchors) a.anchors = p->anchors;
+    if (p->mums) a.mums = p->mums;
+    return a;
+}
+}  // namespace pb200
+
+extern "C" {
+void pb200_params_default(pb200_params* p) {
+    std::memset(p, 0, sizeof(*p));
+    p->c = 21; p->d = 300; p->q = 30; p->p = 15000000; p->diagdiff = 0.12f; p->filter = 1; p->anchors_only = 0;
+    p->anchors = "1.1*(Log(S))"; p->mums = "1.1*(Log(S))";
+}
+const char* pb200_last_error(void) { return pb200::g_last_error.c_str(); }
+int pb200_result_n(const pb200_result* r) { return r->n; }
+int64_t pb200_result_num_mums(const pb200_result* r) { return (int64_t)r->m_length.size(); }
+int pb200_result_mums(const pb200_result* r, int64_t* length, int64_t* slength, int64_t* start, int64_t* end, uint8_t* fwd) {
+    if (length) std::memcpy(length, r->m_length.data(), r->m_length.size() * 8);
+    if (slength) std::memcpy(slength, r->m_slength.data(), r->m_slength.size() * 8);
+    if (start) std::memcpy(start, r->m_start.data(), r->m_start.size() * 8);
+    if (end) std::memcpy(end, r->m_end.data(), r->m_end.size() * 8);
+    if (fwd) std::memcpy(fwd, r->m_fwd.data(), r->m_fwd.size());
+    return 0;
+}
+int64_t pb200_result_num_clusters(const pb200_result* r) { return (int64_t)r->c_type.size(); }
+int pb200_result_clusters(const pb200_result* r, int32_t* type, int64_t* nmums, int64_t* length, int64_t* start, int64_t* end) {
+    if (type) std::memcpy(type, r->c_type.data(), r->c_type.size() * 4);
+    if (nmums) std::memcpy(nmums, r->c_nmums.data(), r->c_nmums.size() * 8);
+    if (length) std::memcpy(length, r->c_length.data(), r->c_length.size() * 8);
+    if (start) std::memcpy(start, r->c_start.data(), r->c_start.size() * 8);
+    if (end) std::memcpy(end, r->c_end.data(), r->c_end.size() * 8);
+    return 0;
+}
+int64_t pb200_result_num_trace(const pb200_result* r) { return (int64_t)r->trace.size() / 2; }
+int pb200_result_trace(const pb200_result* r, int64_t* pairs) { std::memcpy(pairs, r->trace.data(), r->trace.size() * 8); return 0; }
+int pb200_result_stats(const pb200_result* r, double* values, int cap) {
+    int k = 0;
+    for (; k < cap && k < (int)r->stats.size(); ++k) values[k] = r->stats[k];
+    return k;
+}
+const char* pb200_stats_names(void) {
+    return "anchors,regions_searched,spec_regions,replay_misses,spec_levels,windows_searched,candidates,slow_queue_iters,"
+           "t_anchor_search,t_anchor_host,t_spec_search,t_spec_host,t_replay,t_replay_search,t_lcb,t_total";
+}
+void pb200_result_free(pb200_result* r) { delete r; }
+int pb200_minsize(const char* expr, int64_t slength) { return pb200::MinSizeExpr(expr)(slength); }
+void pb200_free_buffer(void* p) { free(p); }
+}

@@ -1,0 +1,23 @@
+// pb200_result: flat copy of the Aligner's final MUM/LCB lists behind the C ABI (include/parsnp_b200.h).
+#pragma once
+#include <vector>
+#include <string>
+#include <cstdint>
+#include "aligner.h"
+#include "../../../include/parsnp_b200.h"
+
+struct pb200_result {
+    int n = 0;
+    std::vector<int64_t> m_length, m_slength, m_start, m_end;
+    std::vector<uint8_t> m_fwd;
+    std::vector<int32_t> c_type;
+    std::vector<int64_t> c_nmums, c_length, c_start, c_end;
+    std::vector<int64_t> trace;
+    std::vector<double> stats;
+};
+
+namespace pb200 {
+extern thread_local std::string g_last_error;
+pb200_result* make_result(const Aligner& a);
+AlignParams to_align_params(const pb200_params* p);
+}

@@ -1,0 +1,36 @@
+"""helpers: compare an alignment result (api.unpack_result dict) with an oracle dump (oracle.runner.parse_dump)"""
+import numpy as np
+
+
+def result_to_dump(res):
+    mums = []
+    for i in range(len(res["mum_length"])):
+        mums.append((int(res["mum_length"][i]), int(res["mum_slength"][i]),
+                     [(int(s), int(e), int(f)) for s, e, f in zip(res["mum_start"][i], res["mum_end"][i], res["mum_fwd"][i])]))
+    cl = []
+    for i in range(len(res["cluster_type"])):
+        cl.append((int(res["cluster_type"][i]), int(res["cluster_nmums"][i]), int(res["cluster_length"][i]),
+                   [(int(s), int(e)) for s, e in zip(res["cluster_start"][i], res["cluster_end"][i])]))
+    return dict(n=res["n"], mums=mums, clusters=cl)
+
+
+def diff_dumps(a, b, limit=5):
+    """returns list of human-readable differences (empty = identical)"""
+    out = []
+    if a["n"] != b["n"]:
+        out.append("n: %s vs %s" % (a["n"], b["n"]))
+    if len(a["mums"]) != len(b["mums"]):
+        out.append("#mums: %d vs %d" % (len(a["mums"]), len(b["mums"])))
+    for i, (x, y) in enumerate(zip(a["mums"], b["mums"])):
+        if x != y:
+            out.append("mum %d: %s vs %s" % (i, x, y))
+            if len(out) > limit:
+                break
+    if len(a["clusters"]) != len(b["clusters"]):
+        out.append("#clusters: %d vs %d" % (len(a["clusters"]), len(b["clusters"])))
+    for i, (x, y) in enumerate(zip(a["clusters"], b["clusters"])):
+        if x != y:
+            out.append("cluster %d: %s vs %s" % (i, x, y))
+            if len(out) > 2 * limit:
+                break
+    return out
