@@ -1,0 +1,597 @@
+// Large-window search: suffix index of the reference window + seed-and-extend MEM scan of every query strand +
+// (floor, top1, top2) scan + ordered fold over queries + candidate emission.
+//
+// Replaces, for one reference window of Aligner::setMums1 (src/parsnp.cpp:1570-1695):
+//   build_CSG + find_leaves (src/csgmum/csg.c:448-575)   -> suffix array by packed 21-mer radix sort + prefix doubling,
+//                                                            adjacent LCP, lrp[l] = longest repeated prefix (u[l] = l + lrp[l])
+//   Find_UM + Test_UM (src/csgmum/mum.c:27-45,177-250)    -> sampled k-mer seeds (SA bucket table) + left/right extension
+//                                                            = maximal exact matches with L >= minsize and L > lrp[l]
+//   Intersect_UM (src/csgmum/mum.c:125-175)               -> associative scan of (fl, t1, t2, diag) over events sorted by l
+//   Master update + Merge_Master (mum.c:92-123)           -> per-position fold over queries in ini order (ties -> reverse)
+//   emission loop (src/parsnp.cpp:1633-1695)              -> flag + ordered compaction, then per-candidate SP/strand pass
+// Events shorter than minsize are pruned (exactness-preserving).
+#pragma once
+#include <algorithm>
+#include "util.cuh"
+#include "radix_sort.cuh"
+#include "scan_prims.cuh"
+
+namespace pb200 {
+namespace big {
+
+constexpr int KEY_BASES = 21;           // 3 bits per base (code+1; 0 = past the end of the window)
+constexpr int MAX_SEED_K = 12;
+
+struct StrandDesc { const uint8_t* q; int32_t m; int32_t pad; };
+
+__device__ __forceinline__ uint64_t load8u(const uint8_t* p) {
+    const uint64_t* a = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)7);
+    const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(p) & 7) * 8;
+    uint64_t lo = a[0];
+    if (sh == 0) return lo;
+    uint64_t hi = a[1];
+    return (lo >> sh) | (hi << (64 - sh));
+}
+// number of equal leading bytes of a[0..limit) and b[0..limit)
+__device__ __forceinline__ int match_len(const uint8_t* a, const uint8_t* b, int limit) {
+    int t = 0;
+    while (t < limit) {
+        uint64_t x = load8u(a + t) ^ load8u(b + t);
+        if (x) { t += (__ffsll((long long)x) - 1) >> 3; break; }
+        t += 8;
+    }
+    return t < limit ? t : limit;
+}
+
+// ------------------------------------------------------------------ index build
+__global__ void make_keys_kernel(const uint8_t* __restrict__ R, int n, uint64_t* __restrict__ keys, uint32_t* __restrict__ sa) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t key = 0;
+#pragma unroll
+    for (int t = 0; t < KEY_BASES; ++t) {
+        uint64_t c = (i + t < n) ? (uint64_t)(R[i + t] + 1) : 0ull;
+        key = (key << 3) | c;
+    }
+    keys[i] = key;
+    sa[i] = (uint32_t)i;
+}
+
+__device__ __forceinline__ bool kmer_of_key(uint64_t key, int k, uint32_t& code) {
+    code = 0;
+    for (int t = 0; t < k; ++t) {
+        uint32_t v = (uint32_t)(key >> (3 * (KEY_BASES - 1 - t))) & 7u;
+        if (v < 1u || v > 4u) return false;
+        code = (code << 2) | (v - 1u);
+    }
+    return true;
+}
+__global__ void kmer_table_kernel(const uint64_t* __restrict__ keys, int n, int k, uint32_t* __restrict__ tlo, uint32_t* __restrict__ thi) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    uint32_t c, cp = 0, cn = 0;
+    if (!kmer_of_key(keys[s], k, c)) return;
+    bool vp = s > 0 && kmer_of_key(keys[s - 1], k, cp);
+    bool vn = s + 1 < n && kmer_of_key(keys[s + 1], k, cn);
+    if (!vp || cp != c) tlo[c] = (uint32_t)s;
+    if (!vn || cn != c) thi[c] = (uint32_t)s + 1u;
+}
+__global__ void head_flags_kernel(const uint64_t* __restrict__ keys, int n, uint32_t* __restrict__ flag, uint32_t* __restrict__ hv) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    uint32_t f = (s == 0 || keys[s] != keys[s - 1]) ? 1u : 0u;
+    flag[s] = f;
+    hv[s] = f ? (uint32_t)s : 0u;
+}
+__global__ void rank_scatter_kernel(const uint32_t* __restrict__ sa, const uint32_t* __restrict__ head, int n, uint32_t* __restrict__ rank) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) rank[sa[s]] = head[s];
+}
+// u[s] = 1 when s belongs to a group of >= 2 equal keys
+__global__ void mark_unsorted_kernel(const uint32_t* __restrict__ flag, int n, uint32_t* __restrict__ u) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    bool single = flag[s] && (s == n - 1 || flag[s + 1]);
+    u[s] = single ? 0u : 1u;
+}
+// compaction: out[pos[s]] = src ? src[s] : s   for u[s] != 0
+__global__ void compact_kernel(const uint32_t* __restrict__ u, const uint32_t* __restrict__ pos, int n, const uint32_t* __restrict__ src,
+                               uint32_t* __restrict__ out) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n && u[s]) out[pos[s]] = src ? src[s] : (uint32_t)s;
+}
+__global__ void dbl_keys_kernel(const uint32_t* __restrict__ cs, int U, const uint32_t* __restrict__ sa, const uint32_t* __restrict__ rank,
+                                int n, int h, int nbits, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= U) return;
+    uint32_t i = sa[cs[c]];
+    uint64_t head = rank[i];
+    uint64_t r2 = ((int64_t)i + h < n) ? (uint64_t)rank[i + h] + 1ull : 0ull;
+    keys[c] = (head << nbits) | r2;
+    vals[c] = i;
+}
+__global__ void dbl_writeback_kernel(const uint32_t* __restrict__ cs, int U, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                     uint32_t* __restrict__ sa, uint32_t* __restrict__ cflag, uint32_t* __restrict__ hv) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= U) return;
+    uint32_t s = cs[c];
+    sa[s] = vals[c];
+    uint32_t f = (c == 0 || keys[c] != keys[c - 1]) ? 1u : 0u;
+    cflag[c] = f;
+    hv[c] = f ? s : 0u;
+}
+__global__ void dbl_rank_kernel(const uint32_t* __restrict__ vals, const uint32_t* __restrict__ head, int U, uint32_t* __restrict__ rank) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < U) rank[vals[c]] = head[c];
+}
+__global__ void lcp_kernel(const uint8_t* __restrict__ R, int n, const uint32_t* __restrict__ sa, int32_t* __restrict__ lcp) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n) return;
+    if (s == 0 || s == n) { lcp[s] = 0; return; }
+    int a = (int)sa[s - 1], b = (int)sa[s];
+    int limit = n - max(a, b);
+    lcp[s] = match_len(R + a, R + b, limit);
+}
+__global__ void lrp_kernel(const uint32_t* __restrict__ sa, const int32_t* __restrict__ lcp, int n, int32_t* __restrict__ lrp) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) lrp[sa[s]] = max(lcp[s], lcp[s + 1]);
+}
+
+// ------------------------------------------------------------------ MEM scan (seed and extend)
+// compare the k bases at q with the suffix of R starting at l (window end sorts first): <0, 0, >0
+__device__ __forceinline__ int cmp_kmer(const uint8_t* __restrict__ R, int n, int l, const uint8_t* __restrict__ q, int k) {
+    for (int t = 0; t < k; ++t) {
+        int a = (l + t < n) ? (int)R[l + t] + 1 : 0;
+        int b = (int)q[t] + 1;
+        if (a != b) return a - b;
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(128) seed_extend_kernel(const uint8_t* __restrict__ R, int n, const uint32_t* __restrict__ sa,
+                                                          const int32_t* __restrict__ lrp, const uint32_t* __restrict__ tlo,
+                                                          const uint32_t* __restrict__ thi, int k, int step, int minsize,
+                                                          const StrandDesc* __restrict__ strands, uint64_t* __restrict__ ev_key,
+                                                          uint64_t* __restrict__ ev_val, unsigned long long* __restrict__ ev_count,
+                                                          unsigned long long ev_cap) {
+    const int strand = blockIdx.y;
+    const uint8_t* __restrict__ Q = strands[strand].q;
+    const int m = strands[strand].m;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long jl = idx * step;
+    if (jl + k > m) return;
+    const int j = (int)jl;
+    uint32_t code = 0;
+    bool plain = true;
+    for (int t = 0; t < k; ++t) {
+        uint32_t c = Q[j + t];
+        if (c > 3u) plain = false;
+        code = (code << 2) | (c & 3u);
+    }
+    int lo, hi;
+    if (plain) { lo = (int)tlo[code]; hi = (int)thi[code]; }
+    else {
+        // k-mer with N: binary search the suffix array (rare)
+        int a = 0, b = n;
+        while (a < b) { int mid = (a + b) >> 1; if (cmp_kmer(R, n, (int)sa[mid], Q + j, k) < 0) a = mid + 1; else b = mid; }
+        lo = a;
+        b = n;
+        while (a < b) { int mid = (a + b) >> 1; if (cmp_kmer(R, n, (int)sa[mid], Q + j, k) <= 0) a = mid + 1; else b = mid; }
+        hi = a;
+    }
+    for (int sidx = lo; sidx < hi; ++sidx) {
+        const int l = (int)sa[sidx];
+        int c = 0;
+        const int cmax = min(step, min(j, l));
+        while (c < cmax && Q[j - 1 - c] == R[l - 1 - c]) ++c;
+        if (c >= step) continue;                      // an earlier sampled seed lies inside the same match
+        const int lim = min(m - (j + k), n - (l + k));
+        const int e = match_len(Q + j + k, R + l + k, lim);
+        const int L = c + k + e;
+        const int l0 = l - c;
+        if (L >= minsize && L > lrp[l0]) {
+            unsigned long long slot = atomicAdd(ev_count, 1ull);
+            if (slot < ev_cap) {
+                ev_key[slot] = ((uint64_t)(uint32_t)strand << 32) | (uint32_t)l0;
+                ev_val[slot] = ((uint64_t)(uint32_t)(l0 + L) << 32) | (uint32_t)(j - c);
+            }
+        }
+    }
+}
+
+// segment bounds of each strand inside the sorted event array; also splits off the l column
+__global__ void strand_segments_kernel(const uint64_t* __restrict__ ev_key, int E, uint32_t* __restrict__ seg_lo, uint32_t* __restrict__ seg_hi,
+                                       uint32_t* __restrict__ evl) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E) return;
+    uint64_t kx = ev_key[i];
+    uint32_t st = (uint32_t)(kx >> 32);
+    evl[i] = (uint32_t)kx;
+    if (i == 0 || (uint32_t)(ev_key[i - 1] >> 32) != st) seg_lo[st] = (uint32_t)i;
+    if (i == E - 1 || (uint32_t)(ev_key[i + 1] >> 32) != st) seg_hi[st] = (uint32_t)i + 1u;
+}
+
+// scan state: fl = max floor u[l], (t1, t2) = two largest ends, d1 = (query start - ref start) of the event holding t1
+struct St { int fl, t1, t2, d1; };
+__device__ __forceinline__ St st_combine(const St& a, const St& b) {     // a = earlier (smaller l)
+    St r;
+    r.fl = max(a.fl, b.fl);
+    if (b.t1 >= a.t1) { r.t1 = b.t1; r.d1 = b.d1; r.t2 = max(a.t1, b.t2); }
+    else { r.t1 = a.t1; r.d1 = a.d1; r.t2 = max(a.t2, b.t1); }
+    return r;
+}
+__device__ __forceinline__ St st_shfl_up(const St& s, int o) {
+    St r;
+    r.fl = __shfl_up_sync(0xffffffffu, s.fl, o);
+    r.t1 = __shfl_up_sync(0xffffffffu, s.t1, o);
+    r.t2 = __shfl_up_sync(0xffffffffu, s.t2, o);
+    r.d1 = __shfl_up_sync(0xffffffffu, s.d1, o);
+    return r;
+}
+// one block per strand: inclusive scan of the strand's events (sorted by l)
+__global__ void __launch_bounds__(256) event_scan_kernel(const uint32_t* __restrict__ evl, const uint64_t* __restrict__ ev_val,
+                                                         const int32_t* __restrict__ lrp, const uint32_t* __restrict__ seg_lo,
+                                                         const uint32_t* __restrict__ seg_hi, int4* __restrict__ states) {
+    __shared__ St s_w[8];
+    const int strand = blockIdx.x;
+    const int lo = (int)seg_lo[strand], hi = (int)seg_hi[strand];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    St carry = {0, 0, 0, 0};
+    for (int base = lo; base < hi; base += 256) {
+        int i = base + threadIdx.x;
+        St x = {0, 0, 0, 0};
+        if (i < hi) {
+            int l = (int)evl[i];
+            uint64_t v = ev_val[i];
+            x.fl = l + lrp[l];
+            x.t1 = (int)(uint32_t)(v >> 32);
+            x.t2 = 0;
+            x.d1 = (int)(uint32_t)v - l;
+        }
+        for (int o = 1; o < 32; o <<= 1) { St y = st_shfl_up(x, o); if (lane >= o) x = st_combine(y, x); }
+        if (lane == 31) s_w[w] = x;
+        __syncthreads();
+        St pre = carry;
+        for (int q = 0; q < w; ++q) pre = st_combine(pre, s_w[q]);
+        St tot = carry;
+        for (int q = 0; q < 8; ++q) tot = st_combine(tot, s_w[q]);
+        x = st_combine(pre, x);
+        if (i < hi) states[i] = make_int4(x.fl, x.t1, x.t2, x.d1);
+        carry = tot;
+        __syncthreads();
+    }
+}
+
+// last event index in [a,b) with l <= k, or a-1
+__device__ __forceinline__ int last_le(const uint32_t* __restrict__ evl, int a, int b, uint32_t k) {
+    int lo = a, hi = b;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (evl[mid] <= k) lo = mid + 1; else hi = mid; }
+    return lo - 1;
+}
+__device__ __forceinline__ void strand_at(const uint32_t* __restrict__ evl, const int4* __restrict__ states, int seg_lo, int a, int b,
+                                          uint32_t k, int& UP, int& EP, int& d1) {
+    int t = last_le(evl, a, b, k);
+    if (t < seg_lo) { UP = 0; EP = 0; d1 = 0; return; }
+    int4 s = states[t];
+    UP = max(s.x, s.z);
+    EP = max(s.y, s.x);
+    d1 = s.w;
+}
+
+constexpr int FOLD_THREADS = 256;
+constexpr int FOLD_ITEMS = 4;
+constexpr int FOLD_TILE = FOLD_THREADS * FOLD_ITEMS;
+// fold over queries q0..q1 (ini order) for a tile of reference positions; master_in may be null (= initial (0, n))
+__global__ void __launch_bounds__(FOLD_THREADS) fold_kernel(const uint32_t* __restrict__ evl, const int4* __restrict__ states,
+                                                            const uint32_t* __restrict__ seg_lo, const uint32_t* __restrict__ seg_hi,
+                                                            int nq, int n, int32_t* __restrict__ MUP, int32_t* __restrict__ MEP,
+                                                            int init_master) {
+    __shared__ int s_a[2], s_b[2], s_lo[2];
+    const int tile0 = blockIdx.x * FOLD_TILE;
+    const int tile1 = min(n, tile0 + FOLD_TILE);
+    int up[FOLD_ITEMS], ep[FOLD_ITEMS];
+#pragma unroll
+    for (int r = 0; r < FOLD_ITEMS; ++r) {
+        int k = tile0 + r * FOLD_THREADS + threadIdx.x;
+        if (init_master || k >= n) { up[r] = 0; ep[r] = n; }
+        else { up[r] = MUP[k]; ep[r] = MEP[k]; }
+    }
+    for (int q = 0; q < nq; ++q) {
+        if (threadIdx.x < 2) {
+            int st = 2 * q + threadIdx.x;
+            int lo = (int)seg_lo[st], hi = (int)seg_hi[st];
+            int a = lo, b = hi;
+            while (a < b) { int mid = (a + b) >> 1; if (evl[mid] < (uint32_t)tile0) a = mid + 1; else b = mid; }
+            int first = a;
+            b = hi;
+            while (a < b) { int mid = (a + b) >> 1; if (evl[mid] < (uint32_t)tile1) a = mid + 1; else b = mid; }
+            s_a[threadIdx.x] = first; s_b[threadIdx.x] = a; s_lo[threadIdx.x] = lo;
+        }
+        __syncthreads();
+        const int fa = s_a[0], fb = s_b[0], flo = s_lo[0], ca = s_a[1], cb = s_b[1], clo = s_lo[1];
+#pragma unroll
+        for (int r = 0; r < FOLD_ITEMS; ++r) {
+            int k = tile0 + r * FOLD_THREADS + threadIdx.x;
+            if (k < n) {
+                int UPf, EPf, df, UPc, EPc, dc;
+                strand_at(evl, states, flo, fa, fb, (uint32_t)k, UPf, EPf, df);
+                strand_at(evl, states, clo, ca, cb, (uint32_t)k, UPc, EPc, dc);
+                int fe = min(ep[r], EPf), ce = min(ep[r], EPc);
+                if (fe > ce) { up[r] = max(up[r], UPf); ep[r] = fe; }
+                else { up[r] = max(up[r], UPc); ep[r] = ce; }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < FOLD_ITEMS; ++r) {
+        int k = tile0 + r * FOLD_THREADS + threadIdx.x;
+        if (k < n) { MUP[k] = up[r]; MEP[k] = ep[r]; }
+    }
+}
+
+__global__ void emit_flags_kernel(const int32_t* __restrict__ MUP, const int32_t* __restrict__ MEP, int n, int minsize,
+                                  uint32_t* __restrict__ flag) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int prev = k ? MEP[k - 1] : 0;
+    int ep = MEP[k];
+    flag[k] = (ep > prev && MUP[k] < ep && ep - k >= minsize) ? 1u : 0u;
+}
+
+// per candidate: replay the fold at position k to recover every query's strand and start (SP)
+__global__ void pass2_kernel(const uint32_t* __restrict__ ck, int ncand, const uint32_t* __restrict__ evl, const int4* __restrict__ states,
+                             const uint32_t* __restrict__ seg_lo, const uint32_t* __restrict__ seg_hi, int nq, int n,
+                             const int32_t* __restrict__ MEP, int32_t* __restrict__ out_lon, int32_t* __restrict__ out_sp,
+                             uint8_t* __restrict__ out_fwd) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncand) return;
+    const uint32_t k = ck[c];
+    int M = n;
+    for (int q = 0; q < nq; ++q) {
+        int UPf, EPf, df, UPc, EPc, dc;
+        int lo = (int)seg_lo[2 * q], hi = (int)seg_hi[2 * q];
+        strand_at(evl, states, lo, lo, hi, k, UPf, EPf, df);
+        lo = (int)seg_lo[2 * q + 1]; hi = (int)seg_hi[2 * q + 1];
+        strand_at(evl, states, lo, lo, hi, k, UPc, EPc, dc);
+        int fe = min(M, EPf), ce = min(M, EPc);
+        if (fe > ce) { out_sp[(size_t)c * nq + q] = (int)k + df; out_fwd[(size_t)c * nq + q] = 1; M = fe; }
+        else { out_sp[(size_t)c * nq + q] = (int)k + dc; out_fwd[(size_t)c * nq + q] = 0; M = ce; }
+    }
+    out_lon[c] = MEP[k] - (int)k;
+}
+
+// ------------------------------------------------------------------ host driver
+struct WindowIndexInfo { int rounds = 0; int64_t unsorted_after_sort = 0; };
+
+class BigPath {
+public:
+    GpuTimers* tm = nullptr;
+    WindowIndexInfo last_index;
+
+    // R: device text of the window (codes 0..4), n bases. strands: host array of 2*nq descriptors (device text pointers):
+    // strand 2q = forward string of query q's region, 2q+1 = its reverse complement.
+    void search(const uint8_t* R, int n, int nq, const std::vector<StrandDesc>& strands, int minsize, cudaStream_t st,
+                std::vector<int32_t>& out_k, std::vector<int32_t>& out_lon, std::vector<int32_t>& out_sp, std::vector<uint8_t>& out_fwd) {
+        build_index(R, n, minsize, st);
+        scan(R, n, nq, strands, minsize, st, out_k, out_lon, out_sp, out_fwd);
+    }
+
+    // debug/test access (device pointers valid until the next build_index)
+    const uint32_t* d_sa() const { return sa_.get(); }
+    const int32_t* d_lrp() const { return lrp_.get(); }
+
+    void build_index(const uint8_t* R, int n, int minsize, cudaStream_t st) {
+        const int TB = 256;
+        const unsigned nb = (unsigned)((n + TB - 1) / TB);
+        uint64_t* k0 = keys0_.ensure((size_t)n, false, st);
+        uint64_t* k1 = keys1_.ensure((size_t)n, false, st);
+        uint32_t* v0 = vals0_.ensure((size_t)n, false, st);
+        uint32_t* v1 = vals1_.ensure((size_t)n, false, st);
+        uint32_t* sa = sa_.ensure((size_t)n, false, st);
+        uint32_t* rank = rank_.ensure((size_t)n, false, st);
+        uint32_t* tA = tmpA_.ensure((size_t)n + 1, false, st);
+        uint32_t* tB = tmpB_.ensure((size_t)n + 1, false, st);
+        uint32_t* tC = tmpC_.ensure((size_t)n + 1, false, st);
+        int32_t* lcp = lcp_.ensure((size_t)n + 1, false, st);
+        int32_t* lrp = lrp_.ensure((size_t)n, false, st);
+        uint32_t* d_tot = total_.ensure(4, false, st);
+
+        if (tm) tm->start(GpuTimers::T_INDEX_KEYS, st);
+        make_keys_kernel<<<nb, TB, 0, st>>>(R, n, k0, v0);
+        if (tm) tm->stop(GpuTimers::T_INDEX_KEYS, st);
+
+        if (tm) tm->start(GpuTimers::T_INDEX_SORT, st);
+        int res = sorter_.sort<uint64_t, uint32_t>(k0, k1, v0, v1, n, 0, 3 * KEY_BASES, st);
+        const uint64_t* ks = res ? k1 : k0;
+        const uint32_t* vs = res ? v1 : v0;
+        PB_CUDA(cudaMemcpyAsync(sa, vs, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        if (tm) tm->stop(GpuTimers::T_INDEX_SORT, st);
+
+        // seed table over the sorted 21-mer keys (buckets are unaffected by the refinement of tied groups)
+        if (tm) tm->start(GpuTimers::T_INDEX_TABLE, st);
+        seed_k_ = std::min(MAX_SEED_K, std::max(1, minsize));
+        const size_t tsize = (size_t)1 << (2 * seed_k_);
+        uint32_t* tlo = tlo_.ensure(tsize, false, st);
+        uint32_t* thi = thi_.ensure(tsize, false, st);
+        PB_CUDA(cudaMemsetAsync(tlo, 0, tsize * 4, st));
+        PB_CUDA(cudaMemsetAsync(thi, 0, tsize * 4, st));
+        kmer_table_kernel<<<nb, TB, 0, st>>>(ks, n, seed_k_, tlo, thi);
+        if (tm) tm->stop(GpuTimers::T_INDEX_TABLE, st);
+
+        // prefix doubling on the groups the 21-mer sort left tied
+        if (tm) tm->start(GpuTimers::T_INDEX_DOUBLING, st);
+        head_flags_kernel<<<nb, TB, 0, st>>>(ks, n, tA /*flag*/, tB /*hv*/);
+        scanner_.scan<prim::OpMax, false>(tB, tB, n, nullptr, st);                 // tB = head index per SA slot
+        rank_scatter_kernel<<<nb, TB, 0, st>>>(sa, tB, n, rank);
+        mark_unsorted_kernel<<<nb, TB, 0, st>>>(tA, n, tC /*u*/);
+        scanner_.scan<prim::OpSum, true>(tC, tB, n, d_tot, st);                    // tB = compact position
+        uint32_t U = 0;
+        PB_CUDA(cudaMemcpyAsync(&U, d_tot, 4, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaStreamSynchronize(st));
+        last_index.unsorted_after_sort = U;
+        last_index.rounds = 0;
+        if (U > 0) {
+            uint32_t* cs = cs0_.ensure((size_t)U, false, st);
+            uint32_t* cs2 = cs1_.ensure((size_t)U, false, st);
+            compact_kernel<<<nb, TB, 0, st>>>(tC, tB, n, nullptr, cs);
+            int nbits = 1;
+            while (((int64_t)1 << nbits) < (int64_t)n + 1) ++nbits;
+            int64_t h = KEY_BASES;
+            while (U > 0) {
+                const unsigned ub = (unsigned)((U + TB - 1) / TB);
+                dbl_keys_kernel<<<ub, TB, 0, st>>>(cs, (int)U, sa, rank, n, (int)std::min<int64_t>(h, n), nbits, k0, v0);
+                int r2 = sorter_.sort<uint64_t, uint32_t>(k0, k1, v0, v1, U, 0, 2 * nbits, st);
+                const uint64_t* k2 = r2 ? k1 : k0;
+                const uint32_t* v2 = r2 ? v1 : v0;
+                dbl_writeback_kernel<<<ub, TB, 0, st>>>(cs, (int)U, k2, v2, sa, tA /*cflag*/, tB /*hv*/);
+                scanner_.scan<prim::OpMax, false>(tB, tB, U, nullptr, st);         // head per compact slot
+                dbl_rank_kernel<<<ub, TB, 0, st>>>(v2, tB, (int)U, rank);
+                mark_unsorted_kernel<<<ub, TB, 0, st>>>(tA, (int)U, tC);
+                scanner_.scan<prim::OpSum, true>(tC, tB, U, d_tot, st);
+                uint32_t U2 = 0;
+                PB_CUDA(cudaMemcpyAsync(&U2, d_tot, 4, cudaMemcpyDeviceToHost, st));
+                PB_CUDA(cudaStreamSynchronize(st));
+                if (U2 > 0) compact_kernel<<<ub, TB, 0, st>>>(tC, tB, (int)U, cs, cs2);
+                std::swap(cs, cs2);
+                U = U2;
+                h *= 2;
+                last_index.rounds++;
+                if (last_index.rounds > 40) throw CudaError("prefix doubling did not converge");
+            }
+        }
+        if (tm) tm->stop(GpuTimers::T_INDEX_DOUBLING, st);
+
+        if (tm) tm->start(GpuTimers::T_INDEX_LCP, st);
+        lcp_kernel<<<(unsigned)((n + 1 + TB - 1) / TB), TB, 0, st>>>(R, n, sa, lcp);
+        lrp_kernel<<<nb, TB, 0, st>>>(sa, lcp, n, lrp);
+        if (tm) tm->stop(GpuTimers::T_INDEX_LCP, st);
+        PB_CUDA(cudaGetLastError());
+    }
+
+    void scan(const uint8_t* R, int n, int nq, const std::vector<StrandDesc>& strands, int minsize, cudaStream_t st,
+              std::vector<int32_t>& out_k, std::vector<int32_t>& out_lon, std::vector<int32_t>& out_sp, std::vector<uint8_t>& out_fwd) {
+        const int TB = 256;
+        const int ns = 2 * nq;
+        const int k = seed_k_;
+        const int step = std::max(1, minsize - k + 1);
+        StrandDesc* d_str = strands_.ensure((size_t)ns, false, st);
+        PB_CUDA(cudaMemcpyAsync(d_str, strands.data(), sizeof(StrandDesc) * ns, cudaMemcpyHostToDevice, st));
+        int64_t tot_m = 0;
+        int max_m = 0;
+        for (int s = 0; s < ns; ++s) { tot_m += strands[s].m; max_m = std::max(max_m, strands[s].m); }
+        size_t cap = std::max<size_t>(ev_cap_hint_, (size_t)(tot_m / 16) + 65536);
+        unsigned long long* d_cnt = evcount_.ensure(1, false, st);
+        unsigned long long E = 0;
+        if (tm) tm->start(GpuTimers::T_SCAN_SEED, st);
+        for (;;) {
+            uint64_t* ek = evk0_.ensure(cap, false, st);
+            uint64_t* ev = evv0_.ensure(cap, false, st);
+            PB_CUDA(cudaMemsetAsync(d_cnt, 0, 8, st));
+            long long samples = ((long long)max_m + step - 1) / step;
+            dim3 grid((unsigned)((samples + 127) / 128), (unsigned)ns);
+            if (samples > 0 && ns > 0)
+                seed_extend_kernel<<<grid, 128, 0, st>>>(R, n, sa_.get(), lrp_.get(), tlo_.get(), thi_.get(), k, step, minsize, d_str, ek, ev,
+                                                         d_cnt, (unsigned long long)cap);
+            PB_CUDA(cudaMemcpyAsync(&E, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+            PB_CUDA(cudaStreamSynchronize(st));
+            if (E <= cap) break;
+            cap = (size_t)E + (size_t)E / 8 + 1024;
+            ev_cap_hint_ = cap;
+        }
+        if (tm) tm->stop(GpuTimers::T_SCAN_SEED, st);
+
+        // order events by (strand, l)
+        if (tm) tm->start(GpuTimers::T_SCAN_EVSORT, st);
+        uint64_t* ek1 = evk1_.ensure(std::max<size_t>(cap, 1), false, st);
+        uint64_t* ev1 = evv1_.ensure(std::max<size_t>(cap, 1), false, st);
+        int sbits = 1;
+        while ((1 << sbits) < ns) ++sbits;
+        int lbits = 1;
+        while (((int64_t)1 << lbits) < (int64_t)n) ++lbits;
+        const uint64_t* eks = evk0_.get();
+        const uint64_t* evs = evv0_.get();
+        if (E > 1) {
+            // two key fields: l in bits [0,lbits), strand in bits [32, 32+sbits): sort the low field, then the high one (LSD, stable)
+            int r1 = sorter_.sort<uint64_t, uint64_t>(evk0_.get(), ek1, evv0_.get(), ev1, (int64_t)E, 0, lbits, st);
+            uint64_t* a_k = r1 ? ek1 : evk0_.get(); uint64_t* b_k = r1 ? evk0_.get() : ek1;
+            uint64_t* a_v = r1 ? ev1 : evv0_.get(); uint64_t* b_v = r1 ? evv0_.get() : ev1;
+            int r2 = sorter_.sort<uint64_t, uint64_t>(a_k, b_k, a_v, b_v, (int64_t)E, 32, 32 + sbits, st);
+            eks = r2 ? b_k : a_k;
+            evs = r2 ? b_v : a_v;
+        }
+        uint32_t* seg_lo = seglo_.ensure((size_t)ns, false, st);
+        uint32_t* seg_hi = seghi_.ensure((size_t)ns, false, st);
+        PB_CUDA(cudaMemsetAsync(seg_lo, 0, (size_t)ns * 4, st));
+        PB_CUDA(cudaMemsetAsync(seg_hi, 0, (size_t)ns * 4, st));
+        uint32_t* evl = evl_.ensure(std::max<size_t>((size_t)E, 1), false, st);
+        int4* states = states_.ensure(std::max<size_t>((size_t)E, 1), false, st);
+        if (E > 0) strand_segments_kernel<<<(unsigned)((E + TB - 1) / TB), TB, 0, st>>>(eks, (int)E, seg_lo, seg_hi, evl);
+        if (tm) tm->stop(GpuTimers::T_SCAN_EVSORT, st);
+
+        if (tm) tm->start(GpuTimers::T_SCAN_EVSCAN, st);
+        if (ns > 0) event_scan_kernel<<<(unsigned)ns, 256, 0, st>>>(evl, evs, lrp_.get(), seg_lo, seg_hi, states);
+        if (tm) tm->stop(GpuTimers::T_SCAN_EVSCAN, st);
+
+        if (tm) tm->start(GpuTimers::T_SCAN_FOLD, st);
+        int32_t* MUP = mup_.ensure((size_t)n, false, st);
+        int32_t* MEP = mep_.ensure((size_t)n, false, st);
+        fold_kernel<<<(unsigned)((n + FOLD_TILE - 1) / FOLD_TILE), FOLD_THREADS, 0, st>>>(evl, states, seg_lo, seg_hi, nq, n, MUP, MEP, 1);
+        if (tm) tm->stop(GpuTimers::T_SCAN_FOLD, st);
+
+        if (tm) tm->start(GpuTimers::T_SCAN_EMIT, st);
+        uint32_t* flag = tmpA_.ensure((size_t)n + 1, false, st);
+        uint32_t* pos = tmpB_.ensure((size_t)n + 1, false, st);
+        uint32_t* d_tot = total_.ensure(4, false, st);
+        const unsigned nb = (unsigned)((n + TB - 1) / TB);
+        emit_flags_kernel<<<nb, TB, 0, st>>>(MUP, MEP, n, minsize, flag);
+        scanner_.scan<prim::OpSum, true>(flag, pos, n, d_tot, st);
+        uint32_t ncand = 0;
+        PB_CUDA(cudaMemcpyAsync(&ncand, d_tot, 4, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaStreamSynchronize(st));
+        uint32_t* ck = ck_.ensure(std::max<size_t>(ncand, 1), false, st);
+        if (ncand) compact_kernel<<<nb, TB, 0, st>>>(flag, pos, n, nullptr, ck);
+        if (tm) tm->stop(GpuTimers::T_SCAN_EMIT, st);
+
+        if (tm) tm->start(GpuTimers::T_SCAN_PASS2, st);
+        const size_t base = out_k.size();
+        out_k.resize(base + ncand);
+        out_lon.resize(base + ncand);
+        const size_t bsp = out_sp.size();
+        out_sp.resize(bsp + (size_t)ncand * nq);
+        out_fwd.resize(bsp + (size_t)ncand * nq);
+        if (ncand) {
+            int32_t* d_lon = olon_.ensure(ncand, false, st);
+            int32_t* d_sp = osp_.ensure((size_t)ncand * std::max(nq, 1), false, st);
+            uint8_t* d_fwd = ofwd_.ensure((size_t)ncand * std::max(nq, 1), false, st);
+            pass2_kernel<<<(ncand + 127) / 128, 128, 0, st>>>(ck, (int)ncand, evl, states, seg_lo, seg_hi, nq, n, MEP, d_lon, d_sp, d_fwd);
+            PB_CUDA(cudaMemcpyAsync(out_k.data() + base, ck, (size_t)ncand * 4, cudaMemcpyDeviceToHost, st));
+            PB_CUDA(cudaMemcpyAsync(out_lon.data() + base, d_lon, (size_t)ncand * 4, cudaMemcpyDeviceToHost, st));
+            if (nq) {
+                PB_CUDA(cudaMemcpyAsync(out_sp.data() + bsp, d_sp, (size_t)ncand * nq * 4, cudaMemcpyDeviceToHost, st));
+                PB_CUDA(cudaMemcpyAsync(out_fwd.data() + bsp, d_fwd, (size_t)ncand * nq, cudaMemcpyDeviceToHost, st));
+            }
+            PB_CUDA(cudaStreamSynchronize(st));
+        }
+        if (tm) tm->stop(GpuTimers::T_SCAN_PASS2, st);
+        PB_CUDA(cudaGetLastError());
+        last_events = (int64_t)E;
+    }
+    int64_t last_events = 0;
+
+private:
+    rsort::RadixSorter sorter_;
+    prim::Scanner scanner_;
+    DevBuf<uint64_t> keys0_, keys1_, evk0_, evk1_, evv0_, evv1_;
+    DevBuf<uint32_t> vals0_, vals1_, sa_, rank_, tmpA_, tmpB_, tmpC_, cs0_, cs1_, tlo_, thi_, total_, seglo_, seghi_, evl_, ck_;
+    DevBuf<int32_t> lcp_, lrp_, mup_, mep_, olon_, osp_;
+    DevBuf<uint8_t> ofwd_;
+    DevBuf<int4> states_;
+    DevBuf<StrandDesc> strands_;
+    DevBuf<unsigned long long> evcount_;
+    size_t ev_cap_hint_ = 0;
+    int seed_k_ = MAX_SEED_K;
+};
+
+}  // namespace big
+}  // namespace pb200

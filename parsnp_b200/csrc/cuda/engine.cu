@@ -1,0 +1,415 @@
+// CUDA search engine + C ABI of libparsnp_b200.so (see include/parsnp_b200.h).  sm_100a only, no CPU path.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstring>
+#include <cstdlib>
+#include <string>
+#include <memory>
+#include <mutex>
+#include <numeric>
+#include "../../../include/parsnp_b200.h"
+#include "../common.h"
+#include "../host/aligner.h"
+#include "../host/result.h"
+#include "util.cuh"
+#include "bigpath.cuh"
+#include "smallpath.cuh"
+
+namespace pb200 {
+
+// ASCII (A,C,G,T,N) -> forward codes and reverse-complement codes (A0 C1 G2 T3 N4; complement = 3-c, N stays N)
+__global__ void encode_kernel(const uint8_t* __restrict__ ascii, int64_t len, uint8_t* __restrict__ fwd, uint8_t* __restrict__ rc) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    uint8_t a = ascii[i], c;
+    switch (a) { case 'A': c = 0; break; case 'C': c = 1; break; case 'G': c = 2; break; case 'T': c = 3; break; default: c = 4; }
+    fwd[i] = c;
+    if (rc) rc[len - 1 - i] = c < 4 ? (uint8_t)(3 - c) : (uint8_t)4;
+}
+
+class CudaEngine : public SearchBackend {
+public:
+    explicit CudaEngine(int device) : device_(device) {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) throw CudaError("parsnp_b200 requires a CUDA device (none found); there is no CPU fallback");
+        if (device < 0 || device >= count) throw CudaError("parsnp_b200: bad device ordinal");
+        PB_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        PB_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) throw CudaError("parsnp_b200 kernels are built for sm_100a (Blackwell) only");
+        sm_count_ = prop.multiProcessorCount;
+        PB_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+        big_.tm = &timers;
+        const char* fp = getenv("PB200_FORCE_PATH");      // tests: "big" routes every window through the large-window path
+        force_big_ = (fp && std::string(fp) == "big") ? 1 : 0;
+        classes_[0] = small::ClassCfg{256, 512, 32, 32};
+        classes_[1] = small::ClassCfg{1024, 2048, 128, 128};
+        classes_[2] = small::ClassCfg{4096, 8192, 512, 512};
+        for (int c = 0; c < 3; ++c)
+            if (classes_[c].smem_bytes() > 48 * 1024)
+                max_smem_ = std::max(max_smem_, classes_[c].smem_bytes());
+        if (max_smem_)
+            PB_CUDA(cudaFuncSetAttribute(small::small_region_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem_));
+    }
+    ~CudaEngine() override {
+        cudaSetDevice(device_);
+        if (st_) cudaStreamDestroy(st_);
+    }
+
+    void set_genomes(int n, const uint8_t* const* seq, const int64_t* len) override {
+        PB_CUDA(cudaSetDevice(device_));
+        n_ = n;
+        len_.assign(len, len + n);
+        gfwd_.assign(n, 0);
+        grc_.assign(n, 0);
+        int64_t tot = 0, maxlen = 0;
+        auto pad = [](int64_t x) { return (x + 63) & ~(int64_t)63; };
+        for (int i = 0; i < n; ++i) {
+            if (len[i] >= ((int64_t)1 << 31) - 64) throw CudaError("parsnp_b200: genome longer than 2^31 bases");
+            gfwd_[i] = tot; tot += pad(len[i] + 16);
+            if (i > 0) { grc_[i] = tot; tot += pad(len[i] + 16); }
+            maxlen = std::max(maxlen, len[i]);
+        }
+        uint8_t* text = text_.ensure((size_t)tot + 256, false, st_);
+        PB_CUDA(cudaMemsetAsync(text, 7, (size_t)tot + 256, st_));         // 7 never matches a base code
+        uint8_t* stage = stage_.ensure((size_t)maxlen + 64, false, st_);
+        for (int i = 0; i < n; ++i) {
+            if (len[i] == 0) continue;
+            PB_CUDA(cudaMemcpyAsync(stage, seq[i], (size_t)len[i], cudaMemcpyHostToDevice, st_));
+            encode_kernel<<<(unsigned)((len[i] + 255) / 256), 256, 0, st_>>>(stage, len[i], text + gfwd_[i], i > 0 ? text + grc_[i] : nullptr);
+            PB_CUDA(cudaStreamSynchronize(st_));                             // stage is reused
+        }
+        h2d_bytes_ = 0;
+        for (int i = 0; i < n; ++i) h2d_bytes_ += len[i];
+        int64_t* d = gmeta_.ensure((size_t)3 * n, false, st_);
+        std::vector<int64_t> meta(3 * (size_t)n);
+        for (int i = 0; i < n; ++i) { meta[i] = gfwd_[i]; meta[n + i] = grc_[i]; meta[2 * n + i] = len_[i]; }
+        PB_CUDA(cudaMemcpyAsync(d, meta.data(), meta.size() * 8, cudaMemcpyHostToDevice, st_));
+        PB_CUDA(cudaStreamSynchronize(st_));
+    }
+
+    void search(const WindowTask* tasks, int ntasks, const int64_t* coords, CandBatch& out) override {
+        PB_CUDA(cudaSetDevice(device_));
+        const int nq = n_ - 1;
+        out.clear();
+        out.nq = nq;
+        // find the extent of the coordinate pool
+        int64_t ncoords = 0;
+        for (int t = 0; t < ntasks; ++t) ncoords = std::max(ncoords, tasks[t].coord_off + 2 * (int64_t)nq);
+        // classify
+        std::vector<int> cls(ntasks, 3);
+        std::vector<std::vector<int>> by_class(4);
+        for (int t = 0; t < ntasks; ++t) {
+            const int64_t* ql = coords + tasks[t].coord_off + nq;
+            int64_t maxm = 0;
+            for (int q = 0; q < nq; ++q) maxm = std::max(maxm, ql[q]);
+            int c = 3;
+            for (int k = 0; k < 3; ++k)
+                if (tasks[t].ref_len <= classes_[k].n_cap && maxm <= classes_[k].m_cap) { c = k; break; }
+            if (tasks[t].minsize < 1) c = 3;
+            if (force_big_) c = 3;
+            cls[t] = c;
+            by_class[c].push_back(t);
+        }
+        // per-task results
+        std::vector<int64_t> t_base(ntasks, 0);
+        std::vector<int32_t> t_cnt(ntasks, 0);
+        std::vector<int8_t> t_src(ntasks, 0);              // 0 = small arrays, 1 = big arrays
+        sm_k_.clear(); sm_lon_.clear(); sm_sp_.clear(); sm_fwd_.clear();
+        bg_k_.clear(); bg_lon_.clear(); bg_sp_.clear(); bg_fwd_.clear();
+        const bool any_small = !by_class[0].empty() || !by_class[1].empty() || !by_class[2].empty();
+        if (any_small) upload_small_tasks(tasks, ntasks, coords, ncoords);
+        for (int c = 0; c < 3; ++c) {
+            if (by_class[c].empty()) continue;
+            std::vector<int> retry;
+            run_small(c, by_class[c], nq, t_base, t_cnt, retry);
+            for (int t : retry) by_class[c + 1].push_back(t);
+        }
+        for (int t : by_class[3]) {
+            t_src[t] = 1;
+            t_base[t] = (int64_t)bg_k_.size();
+            run_big(tasks[t], coords, nq);
+            t_cnt[t] = (int32_t)((int64_t)bg_k_.size() - t_base[t]);
+        }
+        // assemble in task order
+        out.off.resize(ntasks + 1);
+        int64_t tot = 0;
+        for (int t = 0; t < ntasks; ++t) { out.off[t] = tot; tot += t_cnt[t]; }
+        out.off[ntasks] = tot;
+        out.k.resize(tot); out.lon.resize(tot); out.sp.resize((size_t)tot * nq); out.fwd.resize((size_t)tot * nq);
+        for (int t = 0; t < ntasks; ++t) {
+            const int32_t cnt = t_cnt[t];
+            if (!cnt) continue;
+            const std::vector<int32_t>& sk = t_src[t] ? bg_k_ : sm_k_;
+            const std::vector<int32_t>& sl = t_src[t] ? bg_lon_ : sm_lon_;
+            const std::vector<int32_t>& ss = t_src[t] ? bg_sp_ : sm_sp_;
+            const std::vector<uint8_t>& sf = t_src[t] ? bg_fwd_ : sm_fwd_;
+            std::memcpy(&out.k[out.off[t]], &sk[t_base[t]], (size_t)cnt * 4);
+            std::memcpy(&out.lon[out.off[t]], &sl[t_base[t]], (size_t)cnt * 4);
+            if (nq) {
+                std::memcpy(&out.sp[(size_t)out.off[t] * nq], &ss[(size_t)t_base[t] * nq], (size_t)cnt * nq * 4);
+                std::memcpy(&out.fwd[(size_t)out.off[t] * nq], &sf[(size_t)t_base[t] * nq], (size_t)cnt * nq);
+            }
+        }
+    }
+
+    // test hooks: suffix array + lrp of a window of genome 0
+    void debug_index(int64_t ref_start, int n, int minsize, uint32_t* sa, int32_t* lrp) {
+        PB_CUDA(cudaSetDevice(device_));
+        big_.build_index(text_.get() + gfwd_[0] + ref_start, n, minsize, st_);
+        PB_CUDA(cudaMemcpyAsync(sa, big_.d_sa(), (size_t)n * 4, cudaMemcpyDeviceToHost, st_));
+        PB_CUDA(cudaMemcpyAsync(lrp, big_.d_lrp(), (size_t)n * 4, cudaMemcpyDeviceToHost, st_));
+        PB_CUDA(cudaStreamSynchronize(st_));
+    }
+    void set_force_class(int c) { force_big_ = c; }
+    int n() const { return n_; }
+    int device() const { return device_; }
+    int64_t h2d_bytes() const { return h2d_bytes_; }
+    GpuTimers timers;
+    int64_t big_windows = 0, small_windows = 0, small_retries = 0, big_events = 0, index_rounds = 0;
+
+private:
+    void upload_small_tasks(const WindowTask* tasks, int ntasks, const int64_t* coords, int64_t ncoords) {
+        std::vector<small::TaskDev> td(ntasks);
+        for (int t = 0; t < ntasks; ++t) {
+            td[t].ref_off = gfwd_[0] + tasks[t].ref_start;
+            td[t].n = (int32_t)tasks[t].ref_len;
+            td[t].minsize = tasks[t].minsize;
+            td[t].qcoord_off = tasks[t].coord_off;
+        }
+        std::vector<int32_t> qc((size_t)ncoords);
+        for (int64_t i = 0; i < ncoords; ++i) qc[i] = (int32_t)coords[i];
+        small::TaskDev* d_t = d_tasks_.ensure((size_t)ntasks, false, st_);
+        int32_t* d_q = d_qcoords_.ensure((size_t)std::max<int64_t>(ncoords, 1), false, st_);
+        d_outs_.ensure((size_t)ntasks, false, st_);
+        PB_CUDA(cudaMemcpyAsync(d_t, td.data(), sizeof(small::TaskDev) * ntasks, cudaMemcpyHostToDevice, st_));
+        if (ncoords) PB_CUDA(cudaMemcpyAsync(d_q, qc.data(), (size_t)ncoords * 4, cudaMemcpyHostToDevice, st_));
+        PB_CUDA(cudaStreamSynchronize(st_));
+    }
+
+    void run_small(int c, const std::vector<int>& ids_in, int nq, std::vector<int64_t>& t_base, std::vector<int32_t>& t_cnt,
+                   std::vector<int>& retry) {
+        std::vector<int> ids = ids_in;
+        const small::ClassCfg cfg = classes_[c];
+        size_t cand_cap = std::max<size_t>(cand_cap_hint_, (size_t)ids.size() * 2 + 4096);
+        while (!ids.empty()) {
+            const int nt = (int)ids.size();
+            int32_t* d_ids = d_ids_.ensure((size_t)nt, false, st_);
+            PB_CUDA(cudaMemcpyAsync(d_ids, ids.data(), (size_t)nt * 4, cudaMemcpyHostToDevice, st_));
+            unsigned long long* d_cnt = d_candcnt_.ensure(1, false, st_);
+            PB_CUDA(cudaMemsetAsync(d_cnt, 0, 8, st_));
+            int32_t* d_k = d_ck_.ensure(cand_cap, false, st_);
+            int32_t* d_lon = d_clon_.ensure(cand_cap, false, st_);
+            int32_t* d_sp = d_csp_.ensure(cand_cap * std::max(nq, 1), false, st_);
+            uint8_t* d_fw = d_cfwd_.ensure(cand_cap * std::max(nq, 1), false, st_);
+            timers.start(GpuTimers::T_SMALL, st_);
+            small::small_region_kernel<<<nt, small::SM_THREADS, cfg.smem_bytes(), st_>>>(
+                text_.get(), gmeta_.get(), gmeta_.get() + n_, gmeta_.get() + 2 * n_, nq, d_tasks_.get(), d_qcoords_.get(), d_ids, nt, cfg,
+                d_outs_.get(), d_cnt, (unsigned long long)cand_cap, d_k, d_lon, d_sp, d_fw);
+            PB_CUDA(cudaGetLastError());
+            timers.stop(GpuTimers::T_SMALL, st_);
+            unsigned long long used = 0;
+            PB_CUDA(cudaMemcpyAsync(&used, d_cnt, 8, cudaMemcpyDeviceToHost, st_));
+            h_outs_.resize(nt);
+            // outs are indexed by task id; fetch the ones of this launch
+            std::vector<small::TaskOut>& ho = h_outs_;
+            int maxid = *std::max_element(ids.begin(), ids.end());
+            h_outs_all_.resize((size_t)maxid + 1);
+            PB_CUDA(cudaMemcpyAsync(h_outs_all_.data(), d_outs_.get(), sizeof(small::TaskOut) * ((size_t)maxid + 1), cudaMemcpyDeviceToHost, st_));
+            PB_CUDA(cudaStreamSynchronize(st_));
+            (void)ho;
+            const size_t got = (size_t)std::min<unsigned long long>(used, cand_cap);
+            const size_t hb = sm_k_.size();
+            sm_k_.resize(hb + got); sm_lon_.resize(hb + got);
+            sm_sp_.resize((hb + got) * nq); sm_fwd_.resize((hb + got) * nq);
+            if (got) {
+                PB_CUDA(cudaMemcpyAsync(sm_k_.data() + hb, d_k, got * 4, cudaMemcpyDeviceToHost, st_));
+                PB_CUDA(cudaMemcpyAsync(sm_lon_.data() + hb, d_lon, got * 4, cudaMemcpyDeviceToHost, st_));
+                if (nq) {
+                    PB_CUDA(cudaMemcpyAsync(sm_sp_.data() + hb * nq, d_sp, got * nq * 4, cudaMemcpyDeviceToHost, st_));
+                    PB_CUDA(cudaMemcpyAsync(sm_fwd_.data() + hb * nq, d_fw, got * nq, cudaMemcpyDeviceToHost, st_));
+                }
+                PB_CUDA(cudaStreamSynchronize(st_));
+            }
+            std::vector<int> again;
+            for (int t : ids) {
+                const small::TaskOut& o = h_outs_all_[t];
+                if (o.ncand >= 0) { t_cnt[t] = o.ncand; t_base[t] = (int64_t)hb + o.cand_base; small_windows++; }
+                else if (o.ncand == -2) again.push_back(t);      // global candidate buffer full: same class, bigger buffer
+                else { retry.push_back(t); small_retries++; }     // per-CTA event/candidate capacity: next class
+            }
+            ids.swap(again);
+            if (!ids.empty()) { cand_cap = cand_cap * 2 + 4096; cand_cap_hint_ = cand_cap; }
+        }
+    }
+
+    void run_big(const WindowTask& t, const int64_t* coords, int nq) {
+        if (t.ref_len >= ((int64_t)1 << 31) - 64) throw CudaError("window longer than 2^31");
+        const int64_t* qs = coords + t.coord_off;
+        const int64_t* ql = qs + nq;
+        std::vector<big::StrandDesc> sd((size_t)2 * nq);
+        for (int q = 0; q < nq; ++q) {
+            const int g = q + 1;
+            sd[2 * q].q = text_.get() + gfwd_[g] + qs[q];
+            sd[2 * q].m = (int32_t)ql[q];
+            sd[2 * q].pad = 0;
+            sd[2 * q + 1].q = text_.get() + grc_[g] + (len_[g] - qs[q] - ql[q]);
+            sd[2 * q + 1].m = (int32_t)ql[q];
+            sd[2 * q + 1].pad = 0;
+        }
+        big_.search(text_.get() + gfwd_[0] + t.ref_start, (int)t.ref_len, nq, sd, t.minsize, st_, bg_k_, bg_lon_, bg_sp_, bg_fwd_);
+        big_windows++;
+        big_events += big_.last_events;
+        index_rounds += big_.last_index.rounds;
+    }
+
+    int device_ = 0, n_ = 0, sm_count_ = 148, force_big_ = 0;
+    cudaStream_t st_ = nullptr;
+    std::vector<int64_t> len_, gfwd_, grc_;
+    int64_t h2d_bytes_ = 0;
+    DevBuf<uint8_t> text_, stage_, d_cfwd_;
+    DevBuf<int64_t> gmeta_;
+    DevBuf<small::TaskDev> d_tasks_;
+    DevBuf<small::TaskOut> d_outs_;
+    DevBuf<int32_t> d_qcoords_, d_ids_, d_ck_, d_clon_, d_csp_;
+    DevBuf<unsigned long long> d_candcnt_;
+    std::vector<small::TaskOut> h_outs_, h_outs_all_;
+    small::ClassCfg classes_[3];
+    size_t max_smem_ = 0, cand_cap_hint_ = 0;
+    big::BigPath big_;
+    std::vector<int32_t> sm_k_, sm_lon_, sm_sp_, bg_k_, bg_lon_, bg_sp_;
+    std::vector<uint8_t> sm_fwd_, bg_fwd_;
+};
+
+}  // namespace pb200
+
+// =====================================================================================================  C ABI
+struct pb200_genomes {
+    std::unique_ptr<pb200::CudaEngine> eng;
+    int n = 0;
+    std::vector<const uint8_t*> seq;
+    std::vector<int64_t> len;
+};
+
+namespace {
+template <class F>
+int guarded(F&& f) {
+    try { return f(); }
+    catch (const pb200::CudaError& e) {
+        pb200::g_last_error = e.what();
+        std::string s = e.what();
+        return (s.find("requires a CUDA device") != std::string::npos || s.find("sm_100a") != std::string::npos) ? PB200_ERR_NO_CUDA : PB200_ERR_CUDA;
+    }
+    catch (const std::exception& e) { pb200::g_last_error = e.what(); return PB200_ERR_INTERNAL; }
+}
+}  // namespace
+
+extern "C" {
+
+const char* pb200_version(void) { return "parsnp_b200 0.1 (sm_100a)"; }
+
+int pb200_cuda_available(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); return 0; }
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, 0) != cudaSuccess) return 0;
+    return p.major >= 10 ? 1 : 0;
+}
+
+int pb200_genomes_create(int device, int n, const uint8_t* const* seqs, const int64_t* lens, pb200_genomes** out) {
+    return guarded([&]() {
+        if (n < 1 || !seqs || !lens || !out) { pb200::g_last_error = "bad arguments"; return (int)PB200_ERR_ARG; }
+        std::unique_ptr<pb200_genomes> g(new pb200_genomes);
+        g->eng.reset(new pb200::CudaEngine(device));
+        g->n = n;
+        g->seq.assign(seqs, seqs + n);
+        g->len.assign(lens, lens + n);
+        g->eng->set_genomes(n, seqs, lens);
+        *out = g.release();
+        return (int)PB200_OK;
+    });
+}
+void pb200_genomes_free(pb200_genomes* g) { delete g; }
+
+int pb200_search_windows(pb200_genomes* g, int ntasks, const pb200_window* tasks, const int64_t* coords, int64_t ncoords,
+                         int64_t** cand_off, int32_t** k, int32_t** lon, int32_t** sp, uint8_t** fwd) {
+    return guarded([&]() {
+        (void)ncoords;
+        static_assert(sizeof(pb200_window) == sizeof(pb200::WindowTask), "window layout");
+        pb200::CandBatch cb;
+        g->eng->search(reinterpret_cast<const pb200::WindowTask*>(tasks), ntasks, coords, cb);
+        auto dup = [](const void* p, size_t bytes) { void* q = malloc(bytes ? bytes : 1); if (bytes) memcpy(q, p, bytes); return q; };
+        *cand_off = (int64_t*)dup(cb.off.data(), cb.off.size() * 8);
+        *k = (int32_t*)dup(cb.k.data(), cb.k.size() * 4);
+        *lon = (int32_t*)dup(cb.lon.data(), cb.lon.size() * 4);
+        *sp = (int32_t*)dup(cb.sp.data(), cb.sp.size() * 4);
+        *fwd = (uint8_t*)dup(cb.fwd.data(), cb.fwd.size());
+        return (int)PB200_OK;
+    });
+}
+
+// the engine re-uses the resident genomes; the Aligner's set_genomes call is a no-op for it
+namespace {
+class ResidentBackend : public pb200::SearchBackend {
+public:
+    explicit ResidentBackend(pb200::CudaEngine* e) : e_(e) {}
+    void set_genomes(int, const uint8_t* const*, const int64_t*) override {}
+    void search(const pb200::WindowTask* t, int nt, const int64_t* c, pb200::CandBatch& out) override { e_->search(t, nt, c, out); }
+private:
+    pb200::CudaEngine* e_;
+};
+}  // namespace
+
+int pb200_align_resident(pb200_genomes* g, const pb200_params* prm, pb200_result** out) {
+    return guarded([&]() {
+        if (!g || !prm || !out) { pb200::g_last_error = "bad arguments"; return (int)PB200_ERR_ARG; }
+        ResidentBackend be(g->eng.get());
+        pb200::Aligner a(g->n, g->seq.data(), g->len.data(), pb200::to_align_params(prm), &be);
+        a.enable_trace(prm->flags & PB200_FLAG_TRACE_WINDOWS);
+        a.set_speculate(!(prm->flags & PB200_FLAG_NO_SPECULATION));
+        bool ok = a.run();
+        *out = pb200::make_result(a);
+        return ok ? (int)PB200_OK : (int)PB200_ERR_NO_MUMS;
+    });
+}
+
+int pb200_align(int device, int n, const uint8_t* const* seqs, const int64_t* lens, const pb200_params* prm, pb200_result** out) {
+    pb200_genomes* g = nullptr;
+    int rc = pb200_genomes_create(device, n, seqs, lens, &g);
+    if (rc != 0) return rc;
+    rc = pb200_align_resident(g, prm, out);
+    pb200_genomes_free(g);
+    return rc;
+}
+
+int pb200_engine_timers(pb200_genomes* g, double* values, int cap) {
+    int k = 0;
+    const int T = pb200::GpuTimers::T_COUNT;
+    for (int i = 0; i < T && k < cap; ++i) values[k++] = g->eng->timers.ms[i];
+    for (int i = 0; i < T && k < cap; ++i) values[k++] = g->eng->timers.cnt[i];
+    const double extra[5] = {(double)g->eng->big_windows, (double)g->eng->small_windows, (double)g->eng->small_retries,
+                             (double)g->eng->big_events, (double)g->eng->index_rounds};
+    for (int i = 0; i < 5 && k < cap; ++i) values[k++] = extra[i];
+    return k;
+}
+const char* pb200_engine_timer_names(void) {
+    static std::string s = std::string(pb200::GpuTimers::names()) + ",big_windows,small_windows,small_retries,big_events,index_rounds";
+    return s.c_str();
+}
+void pb200_engine_reset_timers(pb200_genomes* g) {
+    g->eng->timers.reset();
+    g->eng->timers.enabled = true;
+    g->eng->big_windows = g->eng->small_windows = g->eng->small_retries = g->eng->big_events = g->eng->index_rounds = 0;
+}
+
+// test hook (not in the public header): suffix array + longest-repeated-prefix of a window of genome 0
+int pb200_debug_index(pb200_genomes* g, int64_t ref_start, int32_t n, int32_t minsize, uint32_t* sa, int32_t* lrp) {
+    return guarded([&]() { g->eng->debug_index(ref_start, n, minsize, sa, lrp); return (int)PB200_OK; });
+}
+
+int pb200_comm_unique_id(const char*, uint8_t*) { pb200::g_last_error = "multi-GPU exchange not built yet"; return PB200_ERR_INTERNAL; }
+int pb200_comm_init(pb200_genomes*, const char*, const uint8_t*, int, int) { pb200::g_last_error = "multi-GPU exchange not built yet"; return PB200_ERR_INTERNAL; }
+void pb200_comm_destroy(pb200_genomes*) {}
+
+}  // extern "C"

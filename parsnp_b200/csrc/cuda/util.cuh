@@ -1,0 +1,106 @@
+// Small CUDA utilities: error checking, RAII device buffers, event timers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace pb200 {
+
+struct CudaError : public std::runtime_error {
+    explicit CudaError(const std::string& s) : std::runtime_error(s) {}
+};
+
+#define PB_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (call);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            throw pb200::CudaError(std::string(#call) + " failed: " + cudaGetErrorString(_e) + " at " + \
+                                   __FILE__ + ":" + std::to_string(__LINE__));                          \
+    } while (0)
+
+// growable device buffer (never shrinks); contents are NOT preserved on growth unless keep=true
+template <class T>
+class DevBuf {
+public:
+    DevBuf() {}
+    ~DevBuf() { if (p_) cudaFree(p_); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    T* get() const { return p_; }
+    size_t capacity() const { return cap_; }
+    T* ensure(size_t n, bool keep = false, cudaStream_t st = 0) {
+        if (n <= cap_) return p_;
+        size_t ncap = n + n / 4 + 64;
+        T* q = nullptr;
+        PB_CUDA(cudaMalloc(&q, ncap * sizeof(T)));
+        if (keep && p_ && cap_) PB_CUDA(cudaMemcpyAsync(q, p_, cap_ * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        if (p_) { PB_CUDA(cudaStreamSynchronize(st)); cudaFree(p_); }
+        p_ = q;
+        cap_ = ncap;
+        return p_;
+    }
+private:
+    T* p_ = nullptr;
+    size_t cap_ = 0;
+};
+
+// pinned host buffer
+template <class T>
+class PinBuf {
+public:
+    ~PinBuf() { if (p_) cudaFreeHost(p_); }
+    T* ensure(size_t n) {
+        if (n <= cap_) return p_;
+        if (p_) cudaFreeHost(p_);
+        cap_ = n + n / 4 + 64;
+        PB_CUDA(cudaMallocHost(&p_, cap_ * sizeof(T)));
+        return p_;
+    }
+    T* get() const { return p_; }
+private:
+    T* p_ = nullptr;
+    size_t cap_ = 0;
+};
+
+// accumulating named GPU timers (CUDA events on the engine stream)
+class GpuTimers {
+public:
+    enum { T_INDEX_KEYS = 0, T_INDEX_SORT, T_INDEX_DOUBLING, T_INDEX_LCP, T_INDEX_TABLE, T_SCAN_SEED, T_SCAN_EVSORT, T_SCAN_EVSCAN,
+           T_SCAN_FOLD, T_SCAN_EMIT, T_SCAN_PASS2, T_SMALL, T_COUNT };
+    static const char* names() {
+        return "index_keys_ms,index_sort_ms,index_doubling_ms,index_lcp_ms,index_table_ms,scan_seed_ms,scan_evsort_ms,scan_evscan_ms,"
+               "scan_fold_ms,scan_emit_ms,scan_pass2_ms,small_regions_ms,"
+               "n_index_keys,n_index_sort,n_index_doubling,n_index_lcp,n_index_table,n_scan_seed,n_scan_evsort,n_scan_evscan,"
+               "n_scan_fold,n_scan_emit,n_scan_pass2,n_small_regions";
+    }
+    GpuTimers() { for (int i = 0; i < T_COUNT; ++i) { ms[i] = 0; cnt[i] = 0; } }
+    void init() {
+        if (ready) return;
+        for (int i = 0; i < 2 * T_COUNT; ++i) cudaEventCreate(&ev[i]);
+        ready = true;
+    }
+    bool enabled = false;
+    void start(int id, cudaStream_t s) { if (enabled) { init(); cudaEventRecord(ev[2 * id], s); } }
+    void stop(int id, cudaStream_t s) {
+        if (!enabled) return;
+        cudaEventRecord(ev[2 * id + 1], s);
+        cudaEventSynchronize(ev[2 * id + 1]);
+        float t = 0;
+        cudaEventElapsedTime(&t, ev[2 * id], ev[2 * id + 1]);
+        ms[id] += t;
+        cnt[id] += 1;
+    }
+    void reset() { for (int i = 0; i < T_COUNT; ++i) { ms[i] = 0; cnt[i] = 0; } }
+    double ms[T_COUNT];
+    double cnt[T_COUNT];
+private:
+    cudaEvent_t ev[2 * T_COUNT];
+    bool ready = false;
+};
+
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace pb200

@@ -1,0 +1,140 @@
+"""CPU tests (no GPU): the oracle restatement against the real reference (golden vectors + csgmum), and the
+product's host orchestrator (parsnp_b200/csrc/host) driven by the reference's own csgmum search."""
+import ctypes as C
+import hashlib
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from tests.conftest import ROOT, GOLDEN, golden_case, load_golden, random_case, whole_window_task, C1A
+from tests.refcmp import result_to_dump, diff_dumps
+from parsnp_b200 import api
+
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+have_ref = os.path.exists(os.path.join(REFDIR, "libpb200_hosttest.so"))
+pytestmark = pytest.mark.skipif(not have_ref, reason="oracle/_ref not built (python oracle/build_ref.py && make -C oracle)")
+
+
+def test_reference_binary_reproduces_golden_c1a():
+    """pins the goldens to the reference itself: XMFA md5 of SURVEY.md App. C + the committed MUM/LCB dump"""
+    from oracle import runner
+    with tempfile.TemporaryDirectory() as td:
+        r = runner.run_ref(os.path.join(GOLDEN, "mers", "England1.fna"), [os.path.join(GOLDEN, "mers", q + ".fna") for q in C1A],
+                           td, dump_exit=False)
+        md5 = hashlib.md5(open(os.path.join(r["outdir"], "parsnpAligner.xmfa"), "rb").read()).hexdigest()
+    assert md5 == "5b59e50c5b8c1f79165fc41cfd2a6ac4"
+    assert diff_dumps(r["dump"], load_golden("c1a")) == []
+    assert len(r["dump"]["mums"]) == 149
+
+
+def test_known_answer_csgmum():
+    """SURVEY.md App. A known-answer vector, straight through the real csg.c/mum.c"""
+    lib = C.CDLL(os.path.join(REFDIR, "libcsgmum_ref.so"))
+    lib.ref_index_build.restype = C.c_void_p
+    lib.ref_index_build.argtypes = [C.c_char_p, C.c_long, C.c_double]
+    lib.ref_find_um.argtypes = [C.c_void_p, C.c_char_p, C.c_long, C.c_void_p, C.c_void_p]
+    lib.ref_intersect_um.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.ref_index_stats.argtypes = [C.c_void_p] + [C.c_void_p] * 3
+    R = b"ACGTACGGTTACGTAACCGGTAC"
+    Q = b"GGTTACGTAACCACGTACGG"
+    n = len(R)
+    ix = lib.ref_index_build(R, n, 2.0)
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    lib.ref_index_stats(ix, C.byref(a), C.byref(b), C.byref(c))
+    assert (a.value, b.value, c.value) == (25, 17, 8)
+    pair = np.zeros(2 * n, np.int32)
+    sp = np.zeros(n, np.uint64)
+    lib.ref_find_um(ix, Q, len(Q), sp.ctypes.data, pair.ctypes.data)
+    assert tuple(pair[0:2]) == (5, 8) and sp[0] == 12
+    assert tuple(pair[12:14]) == (9, 18) and sp[6] == 0
+    assert pair.reshape(-1, 2)[[i for i in range(n) if i not in (0, 6)]].sum() == 0
+    master = np.zeros(2 * n, np.int32)
+    master[1::2] = n
+    lib.ref_intersect_um(ix, master.ctypes.data, pair.ctypes.data, n, sp.ctypes.data)
+    m = master.reshape(-1, 2)
+    assert all(tuple(m[k]) == (5, 8) and sp[k] == 12 + k for k in range(6))
+    assert all(tuple(m[k]) == (9, 18) and sp[k] == k - 6 for k in range(6, n))
+    # and the specification's uniqueness floor agrees: u[6] = 9, u[0] = 5
+    from oracle import hosttest
+    lrp = hosttest.lrp(np.frombuffer(R, np.uint8))
+    assert 6 + lrp[6] == 9 and 0 + lrp[0] == 5
+
+
+@pytest.mark.parametrize("alphabet,with_n", [(b"AT", False), (b"ACGT", False), (b"ACGT", True), (b"AACGGT", True)])
+def test_spec_matches_real_csgmum(alphabet, with_n):
+    """brute-force specification (oracle/mumspec.cpp) == real csgmum on random windows: candidates, SP, strand flags"""
+    from oracle import hosttest
+    rng = np.random.default_rng(len(alphabet) * 10 + with_n)
+    total = 0
+    for it in range(150):
+        g = random_case(rng, 30, 160, 4, alphabet, with_n)
+        minsize = int(rng.integers(4, 12))
+        w, coords = whole_window_task(g, minsize)
+        a = hosttest.search_windows(g, w, coords, backend=0)[0]
+        b = hosttest.search_windows(g, w, coords, backend=1)[0]
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y), (it, a, b)
+        total += len(a[0])
+    assert total > 50
+
+
+def test_minsize_matches_reference_calculator():
+    lib = C.CDLL(os.path.join(REFDIR, "libcsgmum_ref.so"))
+    lib.ref_minsize.argtypes = [C.c_char_p, C.c_long]
+    lib.ref_postfix.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+    ht = C.CDLL(os.path.join(REFDIR, "libpb200_hosttest.so"))
+    ht.pb200_minsize.argtypes = [C.c_char_p, C.c_int64]
+    # (expressions such as "1.1*Log(S)" - Log after an operator without parentheses - make the reference's own Converter
+    #  pop an empty stack and exit, so only forms the reference survives are compared)
+    exprs = [b"1.1*(Log(S))", b"1.2*(Log(S))", b"25", b"Log(S)", b"2*(Log(S))-4", b"(Log(S))/2+10", b"1.5*(Log(S))+2",
+             b"(Log(S))*(Log(S))/10"]
+    rng = np.random.default_rng(1)
+    for e in exprs:
+        vals = list(range(1, 3000)) + [int(x) for x in rng.integers(3000, 60_000_000, 4000)] + [2 ** k for k in range(1, 30)] + \
+               [2 ** k + d for k in range(4, 28) for d in (-1, 1)]
+        for s in vals:
+            assert ht.pb200_minsize(e, s) == lib.ref_minsize(e, s), (e, s)
+    # SURVEY.md a18 examples
+    for s, want in ((31, 6), (100, 8), (30030, 17), (5000000, 25), (15000000, 27)):
+        assert ht.pb200_minsize(b"1.1*(Log(S))", s) == want
+
+
+@pytest.mark.parametrize("name", ["c1a", "c1b", "indep_20k", "rearr_60k", "windows_50k", "pop_30k_x12", "c1c"])
+def test_host_orchestrator_reproduces_reference(name):
+    """the product's host logic (queue order, trim, accept, LCB chaining) fed by the reference's own search == golden"""
+    from oracle import hosttest
+    g, kw, gold = golden_case(name)
+    res = hosttest.align(g, api.make_params(**kw), backend=1)
+    assert diff_dumps(result_to_dump(res), gold) == []
+    # speculation off must give the same answer (every region searched on demand in reference order)
+    if name in ("indep_20k", "rearr_60k"):
+        res2 = hosttest.align(g, api.make_params(flags=api.FLAG_NO_SPECULATION, **kw), backend=1)
+        assert diff_dumps(result_to_dump(res2), gold) == []
+
+
+def test_window_order_matches_reference_trace():
+    """sequence of (window start, length) searched by the exact replay == the reference's setMums1 call sequence"""
+    from oracle import hosttest, runner
+    from parsnp_b200 import synth
+    g = synth.g_indep(30000, 3, 0.03, 13)
+    with tempfile.TemporaryDirectory() as td:
+        ref, qs = synth.write_dataset(os.path.join(td, "d"), g)
+        r = runner.run_ref(ref, qs, os.path.join(td, "r"), cands=True)
+    res = hosttest.align(g, api.make_params(flags=api.FLAG_TRACE_WINDOWS), backend=1)
+    want = [(w["ini0"], w["len0"]) for w in r["cands"]]
+    assert [tuple(x) for x in res["trace"].tolist()] == want
+    assert diff_dumps(result_to_dump(res), r["dump"]) == []
+
+
+def test_spec_backend_end_to_end_small():
+    """host orchestrator + brute-force specification on a tiny set == reference binary"""
+    from oracle import hosttest, runner
+    from parsnp_b200 import synth
+    g = synth.g_indep(3000, 2, 0.04, 3)
+    with tempfile.TemporaryDirectory() as td:
+        ref, qs = synth.write_dataset(os.path.join(td, "d"), g)
+        r = runner.run_ref(ref, qs, os.path.join(td, "r"))
+    res = hosttest.align(g, api.make_params(), backend=0)
+    assert diff_dumps(result_to_dump(res), r["dump"]) == []
