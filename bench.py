@@ -1,0 +1,277 @@
+#!/usr/bin/env python3
+"""bench.py - genome-bases/s through the MUM+LCB path (BASELINE.json metric).
+
+One "step" = one complete pass of the hot path (anchor search over the reference window(s), recursive inter-anchor
+search, LCB chaining; reference src/parsnp.cpp:3187-3273) over one synthetic genome set.
+
+  N = 1 : BASELINE.json configs[1] = G_indep(5 Mbp reference + 8 queries, 1 % independent divergence, seed 1)
+  N > 1 : weak scaling - every rank runs the same-shaped workload on its own genome set (seed = 1 + rank), i.e. N
+          independent partitions as in the reference's partition mode (parsnp:1553-1615); no data-path collective.
+
+`value`  : sum of genome bases / time, genomes already resident in HBM (pb200_align_resident)
+`e2e`    : same metric through the user-facing call with HOST buffers (pb200_align: H2D of the genomes + result D2H)
+`--impl reference` : the reference's own CPU implementation (oracle/_ref/parsnp_core_ref = unmodified marbl/parsnp
+                     built by oracle/build_ref.py) on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L_FULL, NQ, DIV, SEED = 5_000_000, 8, 0.01, 1
+L_CPU_SAMPLE = 1_000_000          # cpu_baseline leg: ~20 s of single-thread CPU work
+L_REF_STEP = 500_000              # --impl reference: ~7 s per step
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    def __init__(self, gpu_index=0):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(L, workdir, nq=NQ, seed=SEED):
+    """the reference binary on G_indep(L, nq): returns (bases, mum+lcb seconds, #mums)"""
+    from parsnp_b200 import synth
+    from oracle import runner
+    g = synth.g_indep(L, nq, DIV, seed)
+    ref, qs = synth.write_dataset(os.path.join(workdir, "data"), g)
+    r = runner.run_ref(ref, qs, os.path.join(workdir, "run"), cores=os.cpu_count() or 1)
+    bases = sum(len(x) for x in g)
+    return bases, r["mumlcb_seconds"], len(r["dump"]["mums"]) if r["dump"] else 0
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps = []
+    with tempfile.TemporaryDirectory() as td:
+        for i in range(args.warmup + args.steps):
+            bases, sec, nm = cpu_reference_run(L_REF_STEP, os.path.join(td, "s%d" % i))
+            if i >= args.warmup:
+                steps.append(sec)
+    ms = 1000.0 * sum(steps) / len(steps)
+    val = bases / (ms / 1000.0)
+    line = {"impl": "reference", "metric": "genome_bases_per_sec_mum_lcb", "value": val, "unit": "bases/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "bounded sample of configs[1]: G_indep(%d bp reference + %d queries, 1%% divergence, seed 1); "
+                                   "full configs[1] is 5 Mbp (the reference needs ~530 s per step there: 86 kbp/s, BASELINE.md)" % (L_REF_STEP, NQ)},
+            "cpu_baseline": {"value": val, "unit": "bases/s", "cores": 1, "kind": "reference",
+                             "sample": "G_indep(%d,8,0.01,1); MUM+LCB path of parsnp_core is single-threaded (ini cores=%d only affects MUSCLE)"
+                                       % (L_REF_STEP, os.cpu_count() or 1)},
+            "e2e": {"value": val, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--length", type=int, default=L_FULL, help="reference length (default = configs[1])")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return 0
+
+    import torch
+    from parsnp_b200 import api, synth
+    if not torch.cuda.is_available() or not api.cuda_available():
+        raise SystemExit("bench.py: no CUDA device - parsnp_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    L = args.length
+    genomes = synth.g_indep(L, NQ, DIV, SEED + rank)
+    bases = sum(len(g) for g in genomes)
+    # pinned host copies for the end-to-end leg
+    pinned = []
+    for g in genomes:
+        t = torch.empty(len(g), dtype=torch.uint8, pin_memory=True)
+        t.numpy()[:] = g
+        pinned.append(t)
+    host_g = [t.numpy() for t in pinned]
+    prm = api.make_params()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    G = api.Genomes(host_g, device=local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    res = None
+    for _ in range(args.warmup):
+        res = G.align(prm)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    G.reset_timers()
+    step_ms = []
+    for _ in range(args.steps):
+        flush.zero_()                      # evict L2 between timed iterations
+        barrier()
+        e0.record()
+        res = G.align(prm)
+        e1.record()
+        barrier()
+        step_ms.append(e0.elapsed_time(e1))
+    timers = G.engine_timers()
+    clocks = sampler.stop()
+    # end-to-end: host buffers in, results out, through the user-facing call
+    e2e_ms = []
+    for _ in range(max(1, min(args.steps, 3))):
+        flush.zero_()
+        barrier()
+        e0.record()
+        res_e = api.align(host_g, prm, device=local_rank)
+        e1.record()
+        barrier()
+        e2e_ms.append(e0.elapsed_time(e1))
+    t_sum = torch.tensor([sum(step_ms), sum(e2e_ms) / len(e2e_ms) * args.steps], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_sum, op=dist.ReduceOp.MAX)
+    tot_ms, tot_e2e_ms = t_sum.tolist()
+    ms_per_step = tot_ms / args.steps
+    value = bases * world / (ms_per_step / 1000.0)
+    e2e_value = bases * world / (tot_e2e_ms / args.steps / 1000.0)
+
+    peak, peak_src = read_peaks()
+    nsteps = args.steps
+    # dominant kernel by device time: choose the largest kernel group; algorithmic bytes per SURVEY.md 8(d)
+    groups = {k[:-3]: v for k, v in timers.items() if k.endswith("_ms")}
+    counts = {k[2:]: v for k, v in timers.items() if k.startswith("n_")}
+    gpu_ms_total = sum(groups.values())
+    nq = len(genomes) - 1
+    # SA build = radix-sort passes of the 21-mer keys: A_sa(r) = 13 + 208 r per window base -> the sort itself moves 8 passes x 24 B
+    # MUM scan (seed_extend): A_scan = 20 B per query base (both strands)
+    st = res["stats"]
+    def per_launch(name):
+        c = max(1.0, counts.get(name, 1.0))
+        return groups.get(name, 0.0) / c, c
+    sort_ms, sort_n = per_launch("index_sort")
+    seed_ms, seed_n = per_launch("scan_seed")
+    small_ms, small_n = per_launch("small_regions")
+    rounds = 1.0 + timers.get("index_rounds", 0.0) / max(1.0, timers.get("big_windows", 1.0))
+    roof_kernels = {
+        # one launch group = the 8 one-sweep passes over (8 B key + 4 B value) of one window: 8 x (12 read + 12 write) B per base
+        "sa_build_radix_sort(onesweep_kernel x8)": {"bytes": 192.0 * timers.get("big_ref_bases", 0.0) / sort_n, "ms": sort_ms},
+        # A_scan = 20 B per query base (both strands)
+        "mum_scan(seed_extend_kernel)": {"bytes": 20.0 * timers.get("big_query_bases", 0.0) / seed_n, "ms": seed_ms},
+        # SURVEY 8(d) "recursion: same formulas applied to the sum of region lengths": A_sa(r=1) = 221 B per window base + 20 B per query base
+        "recursion(small_region_kernel)": {"bytes": (221.0 * timers.get("small_ref_bases", 0.0) + 20.0 * timers.get("small_query_bases", 0.0)) / small_n,
+                                           "ms": small_ms},
+    }
+    dom_total = {"sa_build_radix_sort(onesweep_kernel x8)": groups.get("index_sort", 0.0), "mum_scan(seed_extend_kernel)": groups.get("scan_seed", 0.0),
+                 "recursion(small_region_kernel)": groups.get("small_regions", 0.0)}
+    dom = max(dom_total, key=lambda k: dom_total[k])
+    rk = roof_kernels[dom]
+    ach = rk["bytes"] / (rk["ms"] / 1000.0) / 1e9 if rk["ms"] > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": rk["bytes"], "ms_per_launch": rk["ms"],
+                "share_of_gpu_time": dom_total[dom] / gpu_ms_total if gpu_ms_total else 0.0,
+                "other": {k: {"GBps": (v["bytes"] / (v["ms"] / 1000.0) / 1e9 if v["ms"] > 0 else 0.0), "ms": v["ms"]}
+                          for k, v in roof_kernels.items()},
+                "gpu_ms_per_step_by_group": {k: v / nsteps for k, v in groups.items()},
+                "gpu_ms_per_step": gpu_ms_total / nsteps}
+    line = {"metric": "genome_bases_per_sec_mum_lcb", "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "configs[1]: G_indep(%d bp reference + %d queries, 1%% independent divergence, seed 1+rank), "
+                                   "ini = template defaults (c=21 d=300 q=30 p=15000000 diagdiff=0.12)" % (L, NQ),
+                       "bases_per_step_per_gpu": bases, "l2": "flushed between timed steps (256 MiB write)",
+                       "parallelism": "1 partition per GPU" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": int(bases),
+                    "d2h_bytes_per_step": int(st["candidates"] * (8 + 5 * nq))},
+            "gpu_launches": int(timers.get("kernel_launches", 0)),
+            "clocks": clocks, "roofline": roofline,
+            "result": {"mums": int(len(res["mum_length"])), "lcbs": int((res["cluster_type"] == 1).sum()),
+                       "anchors": int(st["anchors"]), "regions_searched": int(st["regions_searched"]),
+                       "replay_misses": int(st["replay_misses"]), "spec_levels": int(st["spec_levels"])},
+            "host_seconds": {k: st[k] for k in st if k.startswith("t_")}}
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        try:
+            with tempfile.TemporaryDirectory() as td:
+                b, sec, nm = cpu_reference_run(L_CPU_SAMPLE, td)
+            line["cpu_baseline"] = {"value": b / sec, "unit": "bases/s", "cores": 1, "kind": "reference",
+                                    "sample": "oracle/_ref/parsnp_core_ref on G_indep(%d,8,0.01,1): %.1f s for %d bases; the reference's MUM+LCB "
+                                              "path is single-threaded (host has %d cores). Full configs[1] on the reference: ~526 s "
+                                              "(86 kbp/s, BASELINE.md) - its recursion is super-linear" % (L_CPU_SAMPLE, sec, b, os.cpu_count() or 1)}
+        except Exception as ex:  # the oracle binary is test infrastructure; absence must not break the bench
+            line["cpu_baseline"] = {"value": None, "unit": "bases/s", "cores": 1, "kind": "reference", "sample": "unavailable: %s" % ex}
+    if rank == 0:
+        print(json.dumps(line))
+    G.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

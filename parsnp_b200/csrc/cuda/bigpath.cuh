@@ -398,7 +398,7 @@ public:
         uint32_t* d_tot = total_.ensure(4, false, st);
 
         if (tm) tm->start(GpuTimers::T_INDEX_KEYS, st);
-        make_keys_kernel<<<nb, TB, 0, st>>>(R, n, k0, v0);
+        pb200::launch(make_keys_kernel, nb, TB, 0, st, R, n, k0, v0);
         if (tm) tm->stop(GpuTimers::T_INDEX_KEYS, st);
 
         if (tm) tm->start(GpuTimers::T_INDEX_SORT, st);
@@ -416,15 +416,15 @@ public:
         uint32_t* thi = thi_.ensure(tsize, false, st);
         PB_CUDA(cudaMemsetAsync(tlo, 0, tsize * 4, st));
         PB_CUDA(cudaMemsetAsync(thi, 0, tsize * 4, st));
-        kmer_table_kernel<<<nb, TB, 0, st>>>(ks, n, seed_k_, tlo, thi);
+        pb200::launch(kmer_table_kernel, nb, TB, 0, st, ks, n, seed_k_, tlo, thi);
         if (tm) tm->stop(GpuTimers::T_INDEX_TABLE, st);
 
         // prefix doubling on the groups the 21-mer sort left tied
         if (tm) tm->start(GpuTimers::T_INDEX_DOUBLING, st);
-        head_flags_kernel<<<nb, TB, 0, st>>>(ks, n, tA /*flag*/, tB /*hv*/);
+        pb200::launch(head_flags_kernel, nb, TB, 0, st, ks, n, tA /*flag*/, tB /*hv*/);
         scanner_.scan<prim::OpMax, false>(tB, tB, n, nullptr, st);                 // tB = head index per SA slot
-        rank_scatter_kernel<<<nb, TB, 0, st>>>(sa, tB, n, rank);
-        mark_unsorted_kernel<<<nb, TB, 0, st>>>(tA, n, tC /*u*/);
+        pb200::launch(rank_scatter_kernel, nb, TB, 0, st, sa, tB, n, rank);
+        pb200::launch(mark_unsorted_kernel, nb, TB, 0, st, tA, n, tC /*u*/);
         scanner_.scan<prim::OpSum, true>(tC, tB, n, d_tot, st);                    // tB = compact position
         uint32_t U = 0;
         PB_CUDA(cudaMemcpyAsync(&U, d_tot, 4, cudaMemcpyDeviceToHost, st));
@@ -434,25 +434,25 @@ public:
         if (U > 0) {
             uint32_t* cs = cs0_.ensure((size_t)U, false, st);
             uint32_t* cs2 = cs1_.ensure((size_t)U, false, st);
-            compact_kernel<<<nb, TB, 0, st>>>(tC, tB, n, nullptr, cs);
+            pb200::launch(compact_kernel, nb, TB, 0, st, tC, tB, n, nullptr, cs);
             int nbits = 1;
             while (((int64_t)1 << nbits) < (int64_t)n + 1) ++nbits;
             int64_t h = KEY_BASES;
             while (U > 0) {
                 const unsigned ub = (unsigned)((U + TB - 1) / TB);
-                dbl_keys_kernel<<<ub, TB, 0, st>>>(cs, (int)U, sa, rank, n, (int)std::min<int64_t>(h, n), nbits, k0, v0);
+                pb200::launch(dbl_keys_kernel, ub, TB, 0, st, cs, (int)U, sa, rank, n, (int)std::min<int64_t>(h, n), nbits, k0, v0);
                 int r2 = sorter_.sort<uint64_t, uint32_t>(k0, k1, v0, v1, U, 0, 2 * nbits, st);
                 const uint64_t* k2 = r2 ? k1 : k0;
                 const uint32_t* v2 = r2 ? v1 : v0;
-                dbl_writeback_kernel<<<ub, TB, 0, st>>>(cs, (int)U, k2, v2, sa, tA /*cflag*/, tB /*hv*/);
+                pb200::launch(dbl_writeback_kernel, ub, TB, 0, st, cs, (int)U, k2, v2, sa, tA /*cflag*/, tB /*hv*/);
                 scanner_.scan<prim::OpMax, false>(tB, tB, U, nullptr, st);         // head per compact slot
-                dbl_rank_kernel<<<ub, TB, 0, st>>>(v2, tB, (int)U, rank);
-                mark_unsorted_kernel<<<ub, TB, 0, st>>>(tA, (int)U, tC);
+                pb200::launch(dbl_rank_kernel, ub, TB, 0, st, v2, tB, (int)U, rank);
+                pb200::launch(mark_unsorted_kernel, ub, TB, 0, st, tA, (int)U, tC);
                 scanner_.scan<prim::OpSum, true>(tC, tB, U, d_tot, st);
                 uint32_t U2 = 0;
                 PB_CUDA(cudaMemcpyAsync(&U2, d_tot, 4, cudaMemcpyDeviceToHost, st));
                 PB_CUDA(cudaStreamSynchronize(st));
-                if (U2 > 0) compact_kernel<<<ub, TB, 0, st>>>(tC, tB, (int)U, cs, cs2);
+                if (U2 > 0) pb200::launch(compact_kernel, ub, TB, 0, st, tC, tB, (int)U, cs, cs2);
                 std::swap(cs, cs2);
                 U = U2;
                 h *= 2;
@@ -463,8 +463,8 @@ public:
         if (tm) tm->stop(GpuTimers::T_INDEX_DOUBLING, st);
 
         if (tm) tm->start(GpuTimers::T_INDEX_LCP, st);
-        lcp_kernel<<<(unsigned)((n + 1 + TB - 1) / TB), TB, 0, st>>>(R, n, sa, lcp);
-        lrp_kernel<<<nb, TB, 0, st>>>(sa, lcp, n, lrp);
+        pb200::launch(lcp_kernel, (unsigned)((n + 1 + TB - 1) / TB), TB, 0, st, R, n, sa, lcp);
+        pb200::launch(lrp_kernel, nb, TB, 0, st, sa, lcp, n, lrp);
         if (tm) tm->stop(GpuTimers::T_INDEX_LCP, st);
         PB_CUDA(cudaGetLastError());
     }
@@ -491,7 +491,7 @@ public:
             long long samples = ((long long)max_m + step - 1) / step;
             dim3 grid((unsigned)((samples + 127) / 128), (unsigned)ns);
             if (samples > 0 && ns > 0)
-                seed_extend_kernel<<<grid, 128, 0, st>>>(R, n, sa_.get(), lrp_.get(), tlo_.get(), thi_.get(), k, step, minsize, d_str, ek, ev,
+                pb200::launch(seed_extend_kernel, grid, 128, 0, st, R, n, sa_.get(), lrp_.get(), tlo_.get(), thi_.get(), k, step, minsize, d_str, ek, ev,
                                                          d_cnt, (unsigned long long)cap);
             PB_CUDA(cudaMemcpyAsync(&E, d_cnt, 8, cudaMemcpyDeviceToHost, st));
             PB_CUDA(cudaStreamSynchronize(st));
@@ -526,17 +526,17 @@ public:
         PB_CUDA(cudaMemsetAsync(seg_hi, 0, (size_t)ns * 4, st));
         uint32_t* evl = evl_.ensure(std::max<size_t>((size_t)E, 1), false, st);
         int4* states = states_.ensure(std::max<size_t>((size_t)E, 1), false, st);
-        if (E > 0) strand_segments_kernel<<<(unsigned)((E + TB - 1) / TB), TB, 0, st>>>(eks, (int)E, seg_lo, seg_hi, evl);
+        if (E > 0) pb200::launch(strand_segments_kernel, (unsigned)((E + TB - 1) / TB), TB, 0, st, eks, (int)E, seg_lo, seg_hi, evl);
         if (tm) tm->stop(GpuTimers::T_SCAN_EVSORT, st);
 
         if (tm) tm->start(GpuTimers::T_SCAN_EVSCAN, st);
-        if (ns > 0) event_scan_kernel<<<(unsigned)ns, 256, 0, st>>>(evl, evs, lrp_.get(), seg_lo, seg_hi, states);
+        if (ns > 0) pb200::launch(event_scan_kernel, (unsigned)ns, 256, 0, st, evl, evs, lrp_.get(), seg_lo, seg_hi, states);
         if (tm) tm->stop(GpuTimers::T_SCAN_EVSCAN, st);
 
         if (tm) tm->start(GpuTimers::T_SCAN_FOLD, st);
         int32_t* MUP = mup_.ensure((size_t)n, false, st);
         int32_t* MEP = mep_.ensure((size_t)n, false, st);
-        fold_kernel<<<(unsigned)((n + FOLD_TILE - 1) / FOLD_TILE), FOLD_THREADS, 0, st>>>(evl, states, seg_lo, seg_hi, nq, n, MUP, MEP, 1);
+        pb200::launch(fold_kernel, (unsigned)((n + FOLD_TILE - 1) / FOLD_TILE), FOLD_THREADS, 0, st, evl, states, seg_lo, seg_hi, nq, n, MUP, MEP, 1);
         if (tm) tm->stop(GpuTimers::T_SCAN_FOLD, st);
 
         if (tm) tm->start(GpuTimers::T_SCAN_EMIT, st);
@@ -544,13 +544,13 @@ public:
         uint32_t* pos = tmpB_.ensure((size_t)n + 1, false, st);
         uint32_t* d_tot = total_.ensure(4, false, st);
         const unsigned nb = (unsigned)((n + TB - 1) / TB);
-        emit_flags_kernel<<<nb, TB, 0, st>>>(MUP, MEP, n, minsize, flag);
+        pb200::launch(emit_flags_kernel, nb, TB, 0, st, MUP, MEP, n, minsize, flag);
         scanner_.scan<prim::OpSum, true>(flag, pos, n, d_tot, st);
         uint32_t ncand = 0;
         PB_CUDA(cudaMemcpyAsync(&ncand, d_tot, 4, cudaMemcpyDeviceToHost, st));
         PB_CUDA(cudaStreamSynchronize(st));
         uint32_t* ck = ck_.ensure(std::max<size_t>(ncand, 1), false, st);
-        if (ncand) compact_kernel<<<nb, TB, 0, st>>>(flag, pos, n, nullptr, ck);
+        if (ncand) pb200::launch(compact_kernel, nb, TB, 0, st, flag, pos, n, nullptr, ck);
         if (tm) tm->stop(GpuTimers::T_SCAN_EMIT, st);
 
         if (tm) tm->start(GpuTimers::T_SCAN_PASS2, st);
@@ -564,7 +564,7 @@ public:
             int32_t* d_lon = olon_.ensure(ncand, false, st);
             int32_t* d_sp = osp_.ensure((size_t)ncand * std::max(nq, 1), false, st);
             uint8_t* d_fwd = ofwd_.ensure((size_t)ncand * std::max(nq, 1), false, st);
-            pass2_kernel<<<(ncand + 127) / 128, 128, 0, st>>>(ck, (int)ncand, evl, states, seg_lo, seg_hi, nq, n, MEP, d_lon, d_sp, d_fwd);
+            pb200::launch(pass2_kernel, (ncand + 127) / 128, 128, 0, st, ck, (int)ncand, evl, states, seg_lo, seg_hi, nq, n, MEP, d_lon, d_sp, d_fwd);
             PB_CUDA(cudaMemcpyAsync(out_k.data() + base, ck, (size_t)ncand * 4, cudaMemcpyDeviceToHost, st));
             PB_CUDA(cudaMemcpyAsync(out_lon.data() + base, d_lon, (size_t)ncand * 4, cudaMemcpyDeviceToHost, st));
             if (nq) {

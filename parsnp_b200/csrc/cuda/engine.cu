@@ -17,6 +17,8 @@
 
 namespace pb200 {
 
+int64_t g_kernel_launches = 0;
+
 // ASCII (A,C,G,T,N) -> forward codes and reverse-complement codes (A0 C1 G2 T3 N4; complement = 3-c, N stays N)
 __global__ void encode_kernel(const uint8_t* __restrict__ ascii, int64_t len, uint8_t* __restrict__ fwd, uint8_t* __restrict__ rc) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -77,7 +79,7 @@ public:
         for (int i = 0; i < n; ++i) {
             if (len[i] == 0) continue;
             PB_CUDA(cudaMemcpyAsync(stage, seq[i], (size_t)len[i], cudaMemcpyHostToDevice, st_));
-            encode_kernel<<<(unsigned)((len[i] + 255) / 256), 256, 0, st_>>>(stage, len[i], text + gfwd_[i], i > 0 ? text + grc_[i] : nullptr);
+            pb200::launch(encode_kernel, (unsigned)((len[i] + 255) / 256), 256, 0, st_, stage, len[i], text + gfwd_[i], i > 0 ? text + grc_[i] : nullptr);
             PB_CUDA(cudaStreamSynchronize(st_));                             // stage is reused
         }
         h2d_bytes_ = 0;
@@ -163,16 +165,24 @@ public:
         PB_CUDA(cudaStreamSynchronize(st_));
     }
     void set_force_class(int c) { force_big_ = c; }
+    void collect_timers() { cudaSetDevice(device_); timers.collect(st_); }
     int n() const { return n_; }
     int device() const { return device_; }
     int64_t h2d_bytes() const { return h2d_bytes_; }
     GpuTimers timers;
     int64_t big_windows = 0, small_windows = 0, small_retries = 0, big_events = 0, index_rounds = 0;
+    int64_t small_ref_bases = 0, small_query_bases = 0, big_ref_bases = 0, big_query_bases = 0;
 
 private:
     void upload_small_tasks(const WindowTask* tasks, int ntasks, const int64_t* coords, int64_t ncoords) {
         std::vector<small::TaskDev> td(ntasks);
+        h_task_n_.assign(ntasks, 0);
+        h_task_m_.assign(ntasks, 0);
+        const int nq_ = n_ - 1;
         for (int t = 0; t < ntasks; ++t) {
+            h_task_n_[t] = tasks[t].ref_len;
+            const int64_t* ql = coords + tasks[t].coord_off + nq_;
+            for (int q = 0; q < nq_; ++q) h_task_m_[t] += ql[q];
             td[t].ref_off = gfwd_[0] + tasks[t].ref_start;
             td[t].n = (int32_t)tasks[t].ref_len;
             td[t].minsize = tasks[t].minsize;
@@ -192,6 +202,7 @@ private:
                    std::vector<int>& retry) {
         std::vector<int> ids = ids_in;
         const small::ClassCfg cfg = classes_[c];
+        for (int t : ids_in) { small_ref_bases += h_task_n_[t]; small_query_bases += h_task_m_[t]; }
         size_t cand_cap = std::max<size_t>(cand_cap_hint_, (size_t)ids.size() * 2 + 4096);
         while (!ids.empty()) {
             const int nt = (int)ids.size();
@@ -204,7 +215,7 @@ private:
             int32_t* d_sp = d_csp_.ensure(cand_cap * std::max(nq, 1), false, st_);
             uint8_t* d_fw = d_cfwd_.ensure(cand_cap * std::max(nq, 1), false, st_);
             timers.start(GpuTimers::T_SMALL, st_);
-            small::small_region_kernel<<<nt, small::SM_THREADS, cfg.smem_bytes(), st_>>>(
+            pb200::launch(small::small_region_kernel, nt, small::SM_THREADS, cfg.smem_bytes(), st_, 
                 text_.get(), gmeta_.get(), gmeta_.get() + n_, gmeta_.get() + 2 * n_, nq, d_tasks_.get(), d_qcoords_.get(), d_ids, nt, cfg,
                 d_outs_.get(), d_cnt, (unsigned long long)cand_cap, d_k, d_lon, d_sp, d_fw);
             PB_CUDA(cudaGetLastError());
@@ -260,6 +271,8 @@ private:
         }
         big_.search(text_.get() + gfwd_[0] + t.ref_start, (int)t.ref_len, nq, sd, t.minsize, st_, bg_k_, bg_lon_, bg_sp_, bg_fwd_);
         big_windows++;
+        big_ref_bases += t.ref_len;
+        for (int q = 0; q < nq; ++q) big_query_bases += ql[q];
         big_events += big_.last_events;
         index_rounds += big_.last_index.rounds;
     }
@@ -275,6 +288,7 @@ private:
     DevBuf<int32_t> d_qcoords_, d_ids_, d_ck_, d_clon_, d_csp_;
     DevBuf<unsigned long long> d_candcnt_;
     std::vector<small::TaskOut> h_outs_, h_outs_all_;
+    std::vector<int64_t> h_task_n_, h_task_m_;
     small::ClassCfg classes_[3];
     size_t max_smem_ = 0, cand_cap_hint_ = 0;
     big::BigPath big_;
@@ -385,22 +399,27 @@ int pb200_align(int device, int n, const uint8_t* const* seqs, const int64_t* le
 
 int pb200_engine_timers(pb200_genomes* g, double* values, int cap) {
     int k = 0;
+    g->eng->collect_timers();
     const int T = pb200::GpuTimers::T_COUNT;
     for (int i = 0; i < T && k < cap; ++i) values[k++] = g->eng->timers.ms[i];
     for (int i = 0; i < T && k < cap; ++i) values[k++] = g->eng->timers.cnt[i];
-    const double extra[5] = {(double)g->eng->big_windows, (double)g->eng->small_windows, (double)g->eng->small_retries,
-                             (double)g->eng->big_events, (double)g->eng->index_rounds};
-    for (int i = 0; i < 5 && k < cap; ++i) values[k++] = extra[i];
+    const double extra[10] = {(double)g->eng->big_windows, (double)g->eng->small_windows, (double)g->eng->small_retries,
+                              (double)g->eng->big_events, (double)g->eng->index_rounds, (double)pb200::g_kernel_launches,
+                              (double)g->eng->small_ref_bases, (double)g->eng->small_query_bases, (double)g->eng->big_ref_bases,
+                              (double)g->eng->big_query_bases};
+    for (int i = 0; i < 10 && k < cap; ++i) values[k++] = extra[i];
     return k;
 }
 const char* pb200_engine_timer_names(void) {
-    static std::string s = std::string(pb200::GpuTimers::names()) + ",big_windows,small_windows,small_retries,big_events,index_rounds";
+    static std::string s = std::string(pb200::GpuTimers::names()) + ",big_windows,small_windows,small_retries,big_events,index_rounds,kernel_launches,small_ref_bases,small_query_bases,big_ref_bases,big_query_bases";
     return s.c_str();
 }
 void pb200_engine_reset_timers(pb200_genomes* g) {
+    g->eng->collect_timers();
     g->eng->timers.reset();
-    g->eng->timers.enabled = true;
     g->eng->big_windows = g->eng->small_windows = g->eng->small_retries = g->eng->big_events = g->eng->index_rounds = 0;
+    pb200::g_kernel_launches = 0;
+    g->eng->small_ref_bases = g->eng->small_query_bases = g->eng->big_ref_bases = g->eng->big_query_bases = 0;
 }
 
 // test hook (not in the public header): suffix array + longest-repeated-prefix of a window of genome 0

@@ -174,8 +174,8 @@ public:
         uint32_t* counters = gofs + (size_t)npass * 256;
         uint32_t* status = counters + npass;
         int hb = (int)std::min<int64_t>((n + 256 * 16 - 1) / (256 * 16), 148 * 8);
-        hist_kernel<K><<<hb, 256, 0, st>>>(k0, n, begin_bit, end_bit, npass, ghist);
-        scan_hist_kernel<<<npass, 256, 0, st>>>(ghist, gofs);
+        pb200::launch(hist_kernel<K>, hb, 256, 0, st, k0, n, begin_bit, end_bit, npass, ghist);
+        pb200::launch(scan_hist_kernel, npass, 256, 0, st, ghist, gofs);
         const size_t smem = (sizeof(K) + sizeof(V)) * RS_TILE + (RS_WARPS * 256 + 512) * sizeof(uint32_t);
         static bool attr_set[2][2] = {{false, false}, {false, false}};
         bool& a = attr_set[sizeof(K) == 8][sizeof(V) == 8];
@@ -188,7 +188,7 @@ public:
         for (int p = 0; p < npass; ++p) {
             int shift = begin_bit + 8 * p;
             int bits = std::min(8, end_bit - shift);
-            onesweep_kernel<K, V><<<(unsigned)tiles, RS_THREADS, smem, st>>>(kin, kout, vin, vout, n, shift, bits, gofs + (size_t)p * 256,
+            pb200::launch(onesweep_kernel<K, V>, (unsigned)tiles, RS_THREADS, smem, st, kin, kout, vin, vout, n, shift, bits, gofs + (size_t)p * 256,
                                                                             status + (size_t)p * tiles * 256, counters + p);
             std::swap(kin, kout);
             std::swap(vin, vout);

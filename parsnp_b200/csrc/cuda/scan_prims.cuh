@@ -98,9 +98,9 @@ public:
         if (n <= 0) { if (d_total) PB_CUDA(cudaMemsetAsync(d_total, 0, 4, st)); return; }
         int64_t tiles = (n + SC_TILE - 1) / SC_TILE;
         uint32_t* partial = part_.ensure((size_t)tiles, false, st);
-        tile_reduce_kernel<Op><<<(unsigned)tiles, SC_THREADS, 0, st>>>(in, n, partial);
-        partial_scan_kernel<Op><<<1, SC_THREADS, 0, st>>>(partial, tiles, d_total);
-        tile_scan_kernel<Op, EXCLUSIVE><<<(unsigned)tiles, SC_THREADS, 0, st>>>(in, out, n, partial);
+        pb200::launch(tile_reduce_kernel<Op>, (unsigned)tiles, SC_THREADS, 0, st, in, n, partial);
+        pb200::launch(partial_scan_kernel<Op>, 1, SC_THREADS, 0, st, partial, tiles, d_total);
+        pb200::launch(tile_scan_kernel<Op, EXCLUSIVE>, (unsigned)tiles, SC_THREADS, 0, st, in, out, n, partial);
         PB_CUDA(cudaGetLastError());
     }
 private:

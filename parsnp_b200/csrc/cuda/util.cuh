@@ -65,7 +65,8 @@ private:
     size_t cap_ = 0;
 };
 
-// accumulating named GPU timers (CUDA events on the engine stream)
+// Named GPU timers: CUDA event pairs recorded on the engine stream WITHOUT synchronising; collect() (called once
+// the stream is idle) folds the elapsed times into per-group accumulators.  Always on; ~2 event records per group.
 class GpuTimers {
 public:
     enum { T_INDEX_KEYS = 0, T_INDEX_SORT, T_INDEX_DOUBLING, T_INDEX_LCP, T_INDEX_TABLE, T_SCAN_SEED, T_SCAN_EVSORT, T_SCAN_EVSCAN,
@@ -76,30 +77,52 @@ public:
                "n_index_keys,n_index_sort,n_index_doubling,n_index_lcp,n_index_table,n_scan_seed,n_scan_evsort,n_scan_evscan,"
                "n_scan_fold,n_scan_emit,n_scan_pass2,n_small_regions";
     }
-    GpuTimers() { for (int i = 0; i < T_COUNT; ++i) { ms[i] = 0; cnt[i] = 0; } }
-    void init() {
-        if (ready) return;
-        for (int i = 0; i < 2 * T_COUNT; ++i) cudaEventCreate(&ev[i]);
-        ready = true;
+    GpuTimers() { reset(); }
+    ~GpuTimers() { for (auto& e : pool_) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); } }
+    bool enabled = true;
+    void start(int id, cudaStream_t s) {
+        if (!enabled) return;
+        if (used_ == pool_.size()) {
+            Pair p; p.id = 0;
+            cudaEventCreate(&p.a); cudaEventCreate(&p.b);
+            pool_.push_back(p);
+        }
+        cur_ = used_++;
+        pool_[cur_].id = id;
+        cudaEventRecord(pool_[cur_].a, s);
     }
-    bool enabled = false;
-    void start(int id, cudaStream_t s) { if (enabled) { init(); cudaEventRecord(ev[2 * id], s); } }
     void stop(int id, cudaStream_t s) {
         if (!enabled) return;
-        cudaEventRecord(ev[2 * id + 1], s);
-        cudaEventSynchronize(ev[2 * id + 1]);
-        float t = 0;
-        cudaEventElapsedTime(&t, ev[2 * id], ev[2 * id + 1]);
-        ms[id] += t;
-        cnt[id] += 1;
+        (void)id;
+        cudaEventRecord(pool_[cur_].b, s);
+        if (used_ >= 4096) collect(s);
     }
-    void reset() { for (int i = 0; i < T_COUNT; ++i) { ms[i] = 0; cnt[i] = 0; } }
+    // requires all recorded work to have completed (or completes it)
+    void collect(cudaStream_t s) {
+        if (!used_) return;
+        cudaStreamSynchronize(s);
+        for (size_t i = 0; i < used_; ++i) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, pool_[i].a, pool_[i].b) == cudaSuccess) { ms[pool_[i].id] += t; cnt[pool_[i].id] += 1; }
+        }
+        used_ = 0;
+    }
+    void reset() { for (int i = 0; i < T_COUNT; ++i) { ms[i] = 0; cnt[i] = 0; } used_ = 0; }
     double ms[T_COUNT];
     double cnt[T_COUNT];
 private:
-    cudaEvent_t ev[2 * T_COUNT];
-    bool ready = false;
+    struct Pair { cudaEvent_t a, b; int id; };
+    std::vector<Pair> pool_;
+    size_t used_ = 0, cur_ = 0;
 };
+
+// every kernel launch of the library goes through here so that the engine can report how many kernels it launched
+extern int64_t g_kernel_launches;
+template <class... KArgs, class... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    ++g_kernel_launches;
+    kernel<<<grid, block, smem, st>>>(static_cast<KArgs>(args)...);
+}
 
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
