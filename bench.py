@@ -216,6 +216,8 @@ def main():
         return groups.get(name, 0.0) / c, c
     sort_ms, sort_n = per_launch("index_sort")
     seed_ms, seed_n = per_launch("scan_seed")
+    groups["small_regions"] = groups.get("small_regions", 0.0) + groups.pop("small_b", 0.0) + groups.pop("small_c", 0.0)
+    counts["small_regions"] = counts.get("small_regions", 0.0) + counts.pop("small_b", 0.0) + counts.pop("small_c", 0.0)
     small_ms, small_n = per_launch("small_regions")
     rounds = 1.0 + timers.get("index_rounds", 0.0) / max(1.0, timers.get("big_windows", 1.0))
     roof_kernels = {
@@ -254,7 +256,10 @@ def main():
             "result": {"mums": int(len(res["mum_length"])), "lcbs": int((res["cluster_type"] == 1).sum()),
                        "anchors": int(st["anchors"]), "regions_searched": int(st["regions_searched"]),
                        "replay_misses": int(st["replay_misses"]), "spec_levels": int(st["spec_levels"])},
-            "host_seconds": {k: st[k] for k in st if k.startswith("t_")}}
+            "host_seconds": {k: st[k] for k in st if k.startswith("t_")},
+            "engine": {k: timers[k] for k in timers if not k.endswith("_ms") and not k.startswith("n_")},
+            "small_class_ms": {"a": timers.get("small_regions_ms", 0.0) / nsteps, "b": timers.get("small_b_ms", 0.0) / nsteps,
+                               "c": timers.get("small_c_ms", 0.0) / nsteps}}
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         try:
             with tempfile.TemporaryDirectory() as td:

@@ -42,17 +42,20 @@ public:
         if (prop.major < 10) throw CudaError("parsnp_b200 kernels are built for sm_100a (Blackwell) only");
         sm_count_ = prop.multiProcessorCount;
         PB_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+        {   // keep freed blocks in the pool: later engines (one per pb200_align call) re-use them without cudaMalloc
+            cudaMemPool_t pool;
+            PB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+            uint64_t thr = UINT64_MAX;
+            PB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        }
         big_.tm = &timers;
         const char* fp = getenv("PB200_FORCE_PATH");      // tests: "big" routes every window through the large-window path
         force_big_ = (fp && std::string(fp) == "big") ? 1 : 0;
-        classes_[0] = small::ClassCfg{256, 512, 32, 32};
-        classes_[1] = small::ClassCfg{1024, 2048, 128, 128};
-        classes_[2] = small::ClassCfg{4096, 8192, 512, 512};
-        for (int c = 0; c < 3; ++c)
-            if (classes_[c].smem_bytes() > 48 * 1024)
-                max_smem_ = std::max(max_smem_, classes_[c].smem_bytes());
-        if (max_smem_)
-            PB_CUDA(cudaFuncSetAttribute(small::small_region_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem_));
+        // {n_cap, m_cap, event store capacity (all strands), candidate capacity, threads}
+        classes_[0] = small::ClassCfg{256, 512, 512, 64, 128};
+        classes_[1] = small::ClassCfg{1024, 2048, 2048, 256, 256};
+        classes_[2] = small::ClassCfg{4096, 8192, 4096, 512, 256};
+        PB_CUDA(cudaFuncSetAttribute(small::small_region_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
     ~CudaEngine() override {
         cudaSetDevice(device_);
@@ -109,7 +112,7 @@ public:
             int c = 3;
             for (int k = 0; k < 3; ++k)
                 if (tasks[t].ref_len <= classes_[k].n_cap && maxm <= classes_[k].m_cap) { c = k; break; }
-            if (tasks[t].minsize < 1) c = 3;
+            if (tasks[t].minsize < 2) c = 3;
             if (force_big_) c = 3;
             cls[t] = c;
             by_class[c].push_back(t);
@@ -171,6 +174,7 @@ public:
     int64_t h2d_bytes() const { return h2d_bytes_; }
     GpuTimers timers;
     int64_t big_windows = 0, small_windows = 0, small_retries = 0, big_events = 0, index_rounds = 0;
+    int64_t small_class_tasks[3] = {0, 0, 0};
     int64_t small_ref_bases = 0, small_query_bases = 0, big_ref_bases = 0, big_query_bases = 0;
 
 private:
@@ -201,7 +205,9 @@ private:
     void run_small(int c, const std::vector<int>& ids_in, int nq, std::vector<int64_t>& t_base, std::vector<int32_t>& t_cnt,
                    std::vector<int>& retry) {
         std::vector<int> ids = ids_in;
-        const small::ClassCfg cfg = classes_[c];
+        small::ClassCfg cfg = classes_[c];
+        cfg.ev_cap += 4 * nq;            // the event store holds all strands of all queries of a window
+        if (cfg.ev_cap > 60000) cfg.ev_cap = 60000;
         for (int t : ids_in) { small_ref_bases += h_task_n_[t]; small_query_bases += h_task_m_[t]; }
         size_t cand_cap = std::max<size_t>(cand_cap_hint_, (size_t)ids.size() * 2 + 4096);
         while (!ids.empty()) {
@@ -214,12 +220,13 @@ private:
             int32_t* d_lon = d_clon_.ensure(cand_cap, false, st_);
             int32_t* d_sp = d_csp_.ensure(cand_cap * std::max(nq, 1), false, st_);
             uint8_t* d_fw = d_cfwd_.ensure(cand_cap * std::max(nq, 1), false, st_);
-            timers.start(GpuTimers::T_SMALL, st_);
-            pb200::launch(small::small_region_kernel, nt, small::SM_THREADS, cfg.smem_bytes(), st_, 
+            timers.start(GpuTimers::T_SMALL + c, st_);
+            pb200::launch(small::small_region_kernel, nt, cfg.threads, cfg.smem_bytes(nq), st_, 
                 text_.get(), gmeta_.get(), gmeta_.get() + n_, gmeta_.get() + 2 * n_, nq, d_tasks_.get(), d_qcoords_.get(), d_ids, nt, cfg,
                 d_outs_.get(), d_cnt, (unsigned long long)cand_cap, d_k, d_lon, d_sp, d_fw);
             PB_CUDA(cudaGetLastError());
-            timers.stop(GpuTimers::T_SMALL, st_);
+            timers.stop(GpuTimers::T_SMALL + c, st_);
+            small_class_tasks[c] += nt;
             unsigned long long used = 0;
             PB_CUDA(cudaMemcpyAsync(&used, d_cnt, 8, cudaMemcpyDeviceToHost, st_));
             h_outs_.resize(nt);
@@ -403,15 +410,15 @@ int pb200_engine_timers(pb200_genomes* g, double* values, int cap) {
     const int T = pb200::GpuTimers::T_COUNT;
     for (int i = 0; i < T && k < cap; ++i) values[k++] = g->eng->timers.ms[i];
     for (int i = 0; i < T && k < cap; ++i) values[k++] = g->eng->timers.cnt[i];
-    const double extra[10] = {(double)g->eng->big_windows, (double)g->eng->small_windows, (double)g->eng->small_retries,
+    const double extra[13] = {(double)g->eng->small_class_tasks[0], (double)g->eng->small_class_tasks[1], (double)g->eng->small_class_tasks[2],(double)g->eng->big_windows, (double)g->eng->small_windows, (double)g->eng->small_retries,
                               (double)g->eng->big_events, (double)g->eng->index_rounds, (double)pb200::g_kernel_launches,
                               (double)g->eng->small_ref_bases, (double)g->eng->small_query_bases, (double)g->eng->big_ref_bases,
                               (double)g->eng->big_query_bases};
-    for (int i = 0; i < 10 && k < cap; ++i) values[k++] = extra[i];
+    for (int i = 0; i < 13 && k < cap; ++i) values[k++] = extra[i];
     return k;
 }
 const char* pb200_engine_timer_names(void) {
-    static std::string s = std::string(pb200::GpuTimers::names()) + ",big_windows,small_windows,small_retries,big_events,index_rounds,kernel_launches,small_ref_bases,small_query_bases,big_ref_bases,big_query_bases";
+    static std::string s = std::string(pb200::GpuTimers::names()) + ",tasks_class_a,tasks_class_b,tasks_class_c,big_windows,small_windows,small_retries,big_events,index_rounds,kernel_launches,small_ref_bases,small_query_bases,big_ref_bases,big_query_bases";
     return s.c_str();
 }
 void pb200_engine_reset_timers(pb200_genomes* g) {
@@ -420,6 +427,7 @@ void pb200_engine_reset_timers(pb200_genomes* g) {
     g->eng->big_windows = g->eng->small_windows = g->eng->small_retries = g->eng->big_events = g->eng->index_rounds = 0;
     pb200::g_kernel_launches = 0;
     g->eng->small_ref_bases = g->eng->small_query_bases = g->eng->big_ref_bases = g->eng->big_query_bases = 0;
+    g->eng->small_class_tasks[0] = g->eng->small_class_tasks[1] = g->eng->small_class_tasks[2] = 0;
 }
 
 // test hook (not in the public header): suffix array + longest-repeated-prefix of a window of genome 0

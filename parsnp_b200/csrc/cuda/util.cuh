@@ -35,9 +35,10 @@ public:
         if (n <= cap_) return p_;
         size_t ncap = n + n / 4 + 64;
         T* q = nullptr;
-        PB_CUDA(cudaMalloc(&q, ncap * sizeof(T)));
+        // stream-ordered allocation from the device's default pool (kept warm across engines: see CudaEngine ctor)
+        PB_CUDA(cudaMallocAsync((void**)&q, ncap * sizeof(T), st));
         if (keep && p_ && cap_) PB_CUDA(cudaMemcpyAsync(q, p_, cap_ * sizeof(T), cudaMemcpyDeviceToDevice, st));
-        if (p_) { PB_CUDA(cudaStreamSynchronize(st)); cudaFree(p_); }
+        if (p_) PB_CUDA(cudaFreeAsync(p_, st));
         p_ = q;
         cap_ = ncap;
         return p_;
@@ -70,12 +71,12 @@ private:
 class GpuTimers {
 public:
     enum { T_INDEX_KEYS = 0, T_INDEX_SORT, T_INDEX_DOUBLING, T_INDEX_LCP, T_INDEX_TABLE, T_SCAN_SEED, T_SCAN_EVSORT, T_SCAN_EVSCAN,
-           T_SCAN_FOLD, T_SCAN_EMIT, T_SCAN_PASS2, T_SMALL, T_COUNT };
+           T_SCAN_FOLD, T_SCAN_EMIT, T_SCAN_PASS2, T_SMALL, T_SMALL_B, T_SMALL_C, T_COUNT };
     static const char* names() {
         return "index_keys_ms,index_sort_ms,index_doubling_ms,index_lcp_ms,index_table_ms,scan_seed_ms,scan_evsort_ms,scan_evscan_ms,"
-               "scan_fold_ms,scan_emit_ms,scan_pass2_ms,small_regions_ms,"
+               "scan_fold_ms,scan_emit_ms,scan_pass2_ms,small_regions_ms,small_b_ms,small_c_ms,"
                "n_index_keys,n_index_sort,n_index_doubling,n_index_lcp,n_index_table,n_scan_seed,n_scan_evsort,n_scan_evscan,"
-               "n_scan_fold,n_scan_emit,n_scan_pass2,n_small_regions";
+               "n_scan_fold,n_scan_emit,n_scan_pass2,n_small_regions,n_small_b,n_small_c";
     }
     GpuTimers() { reset(); }
     ~GpuTimers() { for (auto& e : pool_) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); } }

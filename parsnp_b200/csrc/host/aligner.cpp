@@ -2,6 +2,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <climits>
+#include <cstdint>
 #include <cstdio>
 #include <stdexcept>
 #include <unordered_set>
@@ -135,6 +137,15 @@ int Aligner::cache_lookup(int r) const {
     return -1;
 }
 
+int Aligner::minsize_cached(bool anchors, int64_t slength) {
+    std::unordered_map<int64_t, int>& c = minsize_cache_[anchors ? 1 : 0];
+    auto it = c.find(slength);
+    if (it != c.end()) return it->second;
+    int v = anchors ? anchor_expr_(slength) : mum_expr_(slength);
+    c.emplace(slength, v);
+    return v;
+}
+
 // ------------------------------------------------------------------ batched search (setMums1 up to the emission loop)
 void Aligner::search_regions(const std::vector<int>& regs, bool anchors) {
     if (regs.empty()) return;
@@ -147,7 +158,7 @@ void Aligner::search_regions(const std::vector<int>& regs, bool anchors) {
         const int64_t* rs = rstart(r);
         const int64_t* re = rend(r);
         first_task[ri] = (int)tasks.size();
-        const int minsize = anchors ? anchor_expr_(rslength_[r]) : mum_expr_(rslength_[r]);
+        const int minsize = minsize_cached(anchors, rslength_[r]);
         const int64_t coff = (int64_t)coords.size();
         for (int j = 1; j < n_; ++j) coords.push_back(rs[j]);
         for (int j = 1; j < n_; ++j) coords.push_back(re[j] - rs[j]);
@@ -211,8 +222,10 @@ void Aligner::accept_candidates(int r, int cache_idx, World& w, std::vector<int>
     const int64_t* rs = rstart(r);
     const int64_t* re = rend(r);
     const int nq = n_ - 1;
-    std::vector<int64_t> st(n_);
-    std::vector<uint8_t> fw(n_);
+    scratch_st_.resize(n_);
+    scratch_fw_.resize(n_);
+    std::vector<int64_t>& st = scratch_st_;
+    std::vector<uint8_t>& fw = scratch_fw_;
     for (int wi = 0; wi < ce.nwin; ++wi) {
         const WinRec& win = wins_[ce.first_win + wi];
         if (trace_on_ && &w == &truth_) trace_.emplace_back(win.ref_start, win.ref_len);
@@ -471,11 +484,29 @@ void Aligner::do_work_exact() {
     stats_.t_replay = now_s() - t0;
 }
 
+// sort(this->mums) by start[0] (operator<, src/TMum.cpp:151); starts are distinct (accepted MUMs are disjoint on the
+// reference), so the order is unique.  Sorts compact (start0,id) pairs and skips the work when already sorted.
+void Aligner::sort_final_mums() {
+    const size_t M = final_mums_.size();
+    bool sorted = true;
+    int64_t prev = INT64_MIN;
+    for (size_t i = 0; i < M; ++i) {
+        int64_t s0 = mum_start_[mums_[final_mums_[i]].off];
+        if (s0 < prev) { sorted = false; break; }
+        prev = s0;
+    }
+    if (sorted) return;
+    std::vector<std::pair<int64_t, int>> kv(M);
+    for (size_t i = 0; i < M; ++i) kv[i] = std::make_pair(mum_start_[mums_[final_mums_[i]].off], final_mums_[i]);
+    std::sort(kv.begin(), kv.end());
+    for (size_t i = 0; i < M; ++i) final_mums_[i] = kv[i].second;
+}
+
 // ------------------------------------------------------------------ filterRandom1 (src/parsnp.cpp:327-425)
 void Aligner::filter_random1() {
     // with the ini's filter=1 (`rvalue` = 1) no MUM has length <= 1, so only the sort has an effect;
     // larger values are restated literally below.
-    std::sort(final_mums_.begin(), final_mums_.end(), [&](int a, int b) { return mum_start_[mums_[a].off] < mum_start_[mums_[b].off]; });
+    sort_final_mums();
     const int rvalue = prm_.random;
     size_t numums = final_mums_.size();
     if (numums == 0) return;
@@ -512,7 +543,7 @@ void Aligner::filter_random1() {
 // ------------------------------------------------------------------ setFinalClusters (src/parsnp.cpp:2563-2719)
 void Aligner::set_final_clusters(std::vector<ClusterRec>& out) {
     out.clear();
-    std::sort(final_mums_.begin(), final_mums_.end(), [&](int a, int b) { return mum_start_[mums_[a].off] < mum_start_[mums_[b].off]; });
+    sort_final_mums();
     const int64_t M = (int64_t)final_mums_.size();
     if (M == 0) return;
     auto S = [&](int64_t i, int k) { return mum_start_[mums_[final_mums_[i]].off + k]; };

@@ -119,6 +119,8 @@ private:
     void speculate(const std::vector<int>& initial, const World& truth);
     void do_work_exact();
     void filter_random1();
+    void sort_final_mums();
+    int minsize_cached(bool anchors, int64_t slength);
     void set_final_clusters(std::vector<ClusterRec>& out);
     void filter_clusters_simple(std::vector<ClusterRec>& cl);
     void set_inter_cluster_regions(std::vector<ClusterRec>& cl);
@@ -151,6 +153,9 @@ private:
     std::unordered_multimap<uint64_t, int> cache_map_;
 
     std::vector<ClusterRec> clusters_;
+    std::unordered_map<int64_t, int> minsize_cache_[2];
+    std::vector<int64_t> scratch_st_;
+    std::vector<uint8_t> scratch_fw_;
     AlignStats stats_;
     std::vector<std::pair<int64_t, int64_t>> trace_;
     bool trace_on_ = false;
