@@ -66,15 +66,27 @@ __device__ __forceinline__ bool kmer_of_key(uint64_t key, int k, uint32_t& code)
     }
     return true;
 }
-__global__ void kmer_table_kernel(const uint64_t* __restrict__ keys, int n, int k, uint32_t* __restrict__ tlo, uint32_t* __restrict__ thi) {
+// seed table entry: .x = first SA slot of the k-mer's bucket, .y = number of suffixes in it (0 = k-mer absent)
+__global__ void kmer_table_kernel(const uint64_t* __restrict__ keys, int n, int k, uint2* __restrict__ table) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     uint32_t c, cp = 0, cn = 0;
     if (!kmer_of_key(keys[s], k, c)) return;
     bool vp = s > 0 && kmer_of_key(keys[s - 1], k, cp);
     bool vn = s + 1 < n && kmer_of_key(keys[s + 1], k, cn);
-    if (!vp || cp != c) tlo[c] = (uint32_t)s;
-    if (!vn || cn != c) thi[c] = (uint32_t)s + 1u;
+    if (!vp || cp != c) table[c].x = (uint32_t)s;
+    if (!vn || cn != c) table[c].y = (uint32_t)s + 1u;       // end slot for now; turned into a count by kmer_table_fix_kernel
+}
+// .y = end - start; buckets of one suffix store the text position itself in .x (saves the SA read in the scan)
+__global__ void kmer_table_fix_kernel(uint2* __restrict__ table, size_t size, const uint32_t* __restrict__ sa_sorted) {
+    size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= size) return;
+    uint2 e = table[c];
+    if (e.y == 0) return;
+    uint32_t cnt = e.y - e.x;
+    if (cnt == 1) e.x = sa_sorted[e.x];
+    e.y = cnt;
+    table[c] = e;
 }
 __global__ void head_flags_kernel(const uint64_t* __restrict__ keys, int n, uint32_t* __restrict__ flag, uint32_t* __restrict__ hv) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -149,8 +161,8 @@ __device__ __forceinline__ int cmp_kmer(const uint8_t* __restrict__ R, int n, in
 }
 
 __global__ void __launch_bounds__(128) seed_extend_kernel(const uint8_t* __restrict__ R, int n, const uint32_t* __restrict__ sa,
-                                                          const int32_t* __restrict__ lrp, const uint32_t* __restrict__ tlo,
-                                                          const uint32_t* __restrict__ thi, int k, int step, int minsize,
+                                                          const int32_t* __restrict__ lrp, const uint2* __restrict__ table,
+                                                          int k, int step, int minsize,
                                                           const StrandDesc* __restrict__ strands, uint64_t* __restrict__ ev_key,
                                                           uint64_t* __restrict__ ev_val, unsigned long long* __restrict__ ev_count,
                                                           unsigned long long ev_cap) {
@@ -161,16 +173,27 @@ __global__ void __launch_bounds__(128) seed_extend_kernel(const uint8_t* __restr
     const long long jl = idx * step;
     if (jl + k > m) return;
     const int j = (int)jl;
+    // k <= 12 bases = the low 2 bits of 12 consecutive bytes: two 8-byte loads instead of k byte loads
     uint32_t code = 0;
     bool plain = true;
-    for (int t = 0; t < k; ++t) {
-        uint32_t c = Q[j + t];
-        if (c > 3u) plain = false;
-        code = (code << 2) | (c & 3u);
+    {
+        uint64_t w0 = load8u(Q + j), w1 = load8u(Q + j + 8);
+#pragma unroll
+        for (int t = 0; t < MAX_SEED_K; ++t) {
+            if (t < k) {
+                uint32_t c = (uint32_t)((t < 8 ? (w0 >> (8 * t)) : (w1 >> (8 * (t - 8)))) & 0xffu);
+                if (c > 3u) plain = false;
+                code = (code << 2) | (c & 3u);
+            }
+        }
     }
     int lo, hi;
-    if (plain) { lo = (int)tlo[code]; hi = (int)thi[code]; }
-    else {
+    int single = -1;                                  // text position when the bucket holds exactly one suffix
+    if (plain) {
+        const uint2 e = table[code];
+        if (e.y == 1u) { single = (int)e.x; lo = 0; hi = 1; }
+        else { lo = (int)e.x; hi = lo + (int)e.y; }
+    } else {
         // k-mer with N: binary search the suffix array (rare)
         int a = 0, b = n;
         while (a < b) { int mid = (a + b) >> 1; if (cmp_kmer(R, n, (int)sa[mid], Q + j, k) < 0) a = mid + 1; else b = mid; }
@@ -180,10 +203,17 @@ __global__ void __launch_bounds__(128) seed_extend_kernel(const uint8_t* __restr
         hi = a;
     }
     for (int sidx = lo; sidx < hi; ++sidx) {
-        const int l = (int)sa[sidx];
+        const int l = single >= 0 ? single : (int)sa[sidx];
         int c = 0;
         const int cmax = min(step, min(j, l));
+        // left extension, 8 bytes per compare (the byte just left of the seed is the top byte of the word)
+        while (c + 8 <= cmax) {
+            uint64_t x = load8u(Q + j - c - 8) ^ load8u(R + l - c - 8);
+            if (x) { c += __clzll((long long)x) >> 3; goto left_done; }
+            c += 8;
+        }
         while (c < cmax && Q[j - 1 - c] == R[l - 1 - c]) ++c;
+    left_done:
         if (c >= step) continue;                      // an earlier sampled seed lies inside the same match
         const int lim = min(m - (j + k), n - (l + k));
         const int e = match_len(Q + j + k, R + l + k, lim);
@@ -412,11 +442,10 @@ public:
         if (tm) tm->start(GpuTimers::T_INDEX_TABLE, st);
         seed_k_ = std::min(MAX_SEED_K, std::max(1, minsize));
         const size_t tsize = (size_t)1 << (2 * seed_k_);
-        uint32_t* tlo = tlo_.ensure(tsize, false, st);
-        uint32_t* thi = thi_.ensure(tsize, false, st);
-        PB_CUDA(cudaMemsetAsync(tlo, 0, tsize * 4, st));
-        PB_CUDA(cudaMemsetAsync(thi, 0, tsize * 4, st));
-        pb200::launch(kmer_table_kernel, nb, TB, 0, st, ks, n, seed_k_, tlo, thi);
+        uint2* table = table_.ensure(tsize, false, st);
+        PB_CUDA(cudaMemsetAsync(table, 0, tsize * sizeof(uint2), st));
+        pb200::launch(kmer_table_kernel, nb, TB, 0, st, ks, n, seed_k_, table);
+        pb200::launch(kmer_table_fix_kernel, (unsigned)((tsize + 255) / 256), 256, 0, st, table, tsize, vs);
         if (tm) tm->stop(GpuTimers::T_INDEX_TABLE, st);
 
         // prefix doubling on the groups the 21-mer sort left tied
@@ -491,7 +520,7 @@ public:
             long long samples = ((long long)max_m + step - 1) / step;
             dim3 grid((unsigned)((samples + 127) / 128), (unsigned)ns);
             if (samples > 0 && ns > 0)
-                pb200::launch(seed_extend_kernel, grid, 128, 0, st, R, n, sa_.get(), lrp_.get(), tlo_.get(), thi_.get(), k, step, minsize, d_str, ek, ev,
+                pb200::launch(seed_extend_kernel, grid, 128, 0, st, R, n, sa_.get(), lrp_.get(), table_.get(), k, step, minsize, d_str, ek, ev,
                                                          d_cnt, (unsigned long long)cap);
             PB_CUDA(cudaMemcpyAsync(&E, d_cnt, 8, cudaMemcpyDeviceToHost, st));
             PB_CUDA(cudaStreamSynchronize(st));
@@ -583,10 +612,11 @@ private:
     rsort::RadixSorter sorter_;
     prim::Scanner scanner_;
     DevBuf<uint64_t> keys0_, keys1_, evk0_, evk1_, evv0_, evv1_;
-    DevBuf<uint32_t> vals0_, vals1_, sa_, rank_, tmpA_, tmpB_, tmpC_, cs0_, cs1_, tlo_, thi_, total_, seglo_, seghi_, evl_, ck_;
+    DevBuf<uint32_t> vals0_, vals1_, sa_, rank_, tmpA_, tmpB_, tmpC_, cs0_, cs1_, total_, seglo_, seghi_, evl_, ck_;
     DevBuf<int32_t> lcp_, lrp_, mup_, mep_, olon_, osp_;
     DevBuf<uint8_t> ofwd_;
     DevBuf<int4> states_;
+    DevBuf<uint2> table_;
     DevBuf<StrandDesc> strands_;
     DevBuf<unsigned long long> evcount_;
     size_t ev_cap_hint_ = 0;

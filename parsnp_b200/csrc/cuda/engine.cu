@@ -112,7 +112,7 @@ public:
             int c = 3;
             for (int k = 0; k < 3; ++k)
                 if (tasks[t].ref_len <= classes_[k].n_cap && maxm <= classes_[k].m_cap) { c = k; break; }
-            if (tasks[t].minsize < 2) c = 3;
+            if (tasks[t].minsize < 4) c = 3;          // the shared-memory path seeds with 4-base matches
             if (force_big_) c = 3;
             cls[t] = c;
             by_class[c].push_back(t);

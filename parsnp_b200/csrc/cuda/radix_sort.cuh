@@ -1,5 +1,5 @@
 // LSD radix sort (8-bit digits) of (key, value) pairs, one-sweep style: one global histogram kernel for all passes,
-// then per pass ONE kernel that ranks a 4096-key tile in shared memory (warp match_any multisplit), resolves the
+// then per pass ONE kernel that ranks a 2048-key tile in shared memory (warp match_any multisplit), resolves the
 // tile's global digit offsets with a decoupled look-back over single-word (flag|count) tile states, stages the tile
 // sorted by digit in shared memory and writes each digit run out contiguously (coalesced).
 // Algorithmic HBM traffic per pass: read key+value, write key+value (+ one extra key read for the histograms).
@@ -14,8 +14,8 @@ namespace rsort {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;   // 4096
+constexpr int RS_ITEMS = 8;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;   // 2048 keys per tile: ~64 registers, 32 KB smem -> 5-6 CTAs per SM
 constexpr uint32_t ST_AGG = 1u << 30;
 constexpr uint32_t ST_INCL = 2u << 30;
 constexpr uint32_t ST_MASK = (1u << 30) - 1;
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) scan_hist_kernel(const uint32_t* __restri
 }
 
 template <class K, class V>
-__global__ void __launch_bounds__(RS_THREADS) onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout,
+__global__ void __launch_bounds__(RS_THREADS, 4) onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout,
                                                               const V* __restrict__ vin, V* __restrict__ vout, int64_t n, int shift,
                                                               int bits, const uint32_t* __restrict__ gofs,
                                                               volatile uint32_t* status, uint32_t* tile_counter) {
@@ -116,14 +116,23 @@ __global__ void __launch_bounds__(RS_THREADS) onesweep_kernel(const K* __restric
             status[(int64_t)tile * 256 + d] = tot | ST_INCL;
         } else {
             status[(int64_t)tile * 256 + d] = tot | ST_AGG;
+            // look back over the predecessor tiles, 8 status words in flight per step (the first wave of resident tiles has
+            // to walk back hundreds of tiles; one dependent L2 round trip per tile would serialise the whole pass)
             int t = tile - 1;
-            while (true) {
-                uint32_t v = status[(int64_t)t * 256 + d];
-                uint32_t f = v & ~ST_MASK;
-                if (f == 0) continue;
-                excl += v & ST_MASK;
-                if (f == ST_INCL) break;
-                --t;
+            bool done = false;
+            while (!done) {
+                uint32_t v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { v[u] = 2u << 30; if (t - u >= 0) v[u] = status[(int64_t)(t - u) * 256 + d]; }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (done) break;
+                    const uint32_t f = v[u] & ~ST_MASK;
+                    if (f == 0) break;                   // predecessor not published yet: re-read from here
+                    excl += v[u] & ST_MASK;
+                    --t;
+                    if (f == ST_INCL) done = true;
+                }
             }
             status[(int64_t)tile * 256 + d] = (excl + tot) | ST_INCL;
         }

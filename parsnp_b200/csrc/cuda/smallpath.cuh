@@ -32,7 +32,7 @@ struct ClassCfg {
     __host__ __device__ static size_t al(size_t x) { return (x + 15) & ~(size_t)15; }
     // ev_cap = capacity of the event store for ALL strands of ALL queries of the window
     __host__ __device__ size_t smem_bytes(int nq) const {
-        return al(n_cap) + 2 * al(m_cap) + 3 * al(2 * (size_t)n_cap) + al((size_t)ev_cap * sizeof(Ev)) + al(2 * (size_t)(2 * nq + 2)) +
+        return al(n_cap) + 2 * al(m_cap) + 4 * al(2 * (size_t)n_cap) + al((size_t)ev_cap * sizeof(Ev)) + al(2 * (size_t)(2 * nq + 2)) +
                2 * al(2 * (size_t)cand_cap) + 64;
     }
 };
@@ -40,74 +40,124 @@ struct ClassCfg {
 constexpr int SM_MAX_THREADS = 256;
 constexpr uint16_t LRP_UNKNOWN = 0xFFFFu;
 
-// longest prefix of R[l..) that occurs at another position of R (A1), computed on demand and cached
-__device__ __forceinline__ int lazy_lrp(const uint8_t* __restrict__ R, int n, uint16_t* __restrict__ lrp, int l) {
-    uint16_t v = lrp[l];
-    if (v != LRP_UNKNOWN) return v;
-    int best = 0;
-    const uint8_t c0 = R[l];
-    for (int l2 = 0; l2 < n; ++l2) {
-        if (R[l2] != c0 || l2 == l) continue;
-        int t = 1;
-        const int lim = n - max(l, l2);
-        while (t < lim && R[l + t] == R[l2 + t]) ++t;
-        best = max(best, t);
+// ---- shared-memory string compares, 8 bytes per step (arrays are 16-byte aligned and padded, over-reads are clamped by `limit`)
+__device__ __forceinline__ uint64_t sld8u(const uint8_t* p) {
+    const uint64_t* a = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)7);
+    const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(p) & 7) * 8;
+    uint64_t lo = a[0];
+    if (sh == 0) return lo;
+    return (lo >> sh) | (a[1] << (64 - sh));
+}
+// equal leading bytes of a[0..limit) and b[0..limit)
+__device__ __forceinline__ int smatch_fwd(const uint8_t* a, const uint8_t* b, int limit) {
+    int t = 0;
+    while (t < limit) {
+        uint64_t x = sld8u(a + t) ^ sld8u(b + t);
+        if (x) { t += (__ffsll((long long)x) - 1) >> 3; break; }
+        t += 8;
     }
-    lrp[l] = (uint16_t)best;         // racing writers store the same value
-    return best;
+    return t < limit ? t : limit;
+}
+// equal bytes going left: a[-1]==b[-1], a[-2]==b[-2], ... at most `limit` (the caller guarantees a-limit, b-limit are inside the arrays)
+__device__ __forceinline__ int smatch_bwd(const uint8_t* a, const uint8_t* b, int limit) {
+    int c = 0;
+    while (c + 8 <= limit) {
+        uint64_t x = sld8u(a - c - 8) ^ sld8u(b - c - 8);
+        if (x) return c + (__clzll((long long)x) >> 3);
+        c += 8;
+    }
+    while (c < limit && a[-1 - c] == b[-1 - c]) ++c;
+    return c;
 }
 
-// MEM events of one strand: Q (m bases in smem) against R (n bases in smem).  Seeds = 2-base matches at every
-// (minsize-1)-th query position against every reference position (a dense rows x n grid, no divergence in the
-// enumeration); a match of >= minsize bases contains exactly one seed whose left extension is shorter than the
-// seed spacing, which reports it.
-__device__ inline void find_events(const uint8_t* __restrict__ R, int n, const uint8_t* __restrict__ Q, int m,
-                                   uint16_t* __restrict__ lrp, int minsize, Ev* __restrict__ ev, int* __restrict__ ev_n, int ev_cap,
-                                   int nthreads) {
-    const int step = max(1, minsize - 1);
-    for (int j = 0; j + 1 < m; j += step) {
-        const uint8_t q0 = Q[j], q1 = Q[j + 1];
-        for (int l = threadIdx.x; l + 1 < n; l += nthreads) {
-            if (R[l] != q0 || R[l + 1] != q1) continue;
-            int c = 0;
-            const int cmax = min(step, min(j, l));
-            while (c < cmax && Q[j - 1 - c] == R[l - 1 - c]) ++c;
-            if (c >= step) continue;                  // the previous seed row lies in the same match
-            int e = 2;
-            const int emax = min(m - j, n - l);
-            while (e < emax && Q[j + e] == R[l + e]) ++e;
-            const int L = c + e, l0 = l - c;
-            if (L < minsize) continue;
-            const int lr = lazy_lrp(R, n, lrp, l0);
-            if (L > lr) {
+// MEM events of one query (both strands) against R.  Seeds = SEED_K-base matches (packed 3 bits per base in R4[l]) at every
+// (minsize-SEED_K+1)-th query position against every reference position: a dense rows x n grid without divergence in
+// the enumeration, ~1/256 random hits.  A match of >= minsize bases contains exactly one seed whose left extension is
+// shorter than the seed spacing, and that seed reports it.  Events are stored unconditionally (strand in pad bit 1);
+// uniqueness is decided afterwards by resolve_unique().
+constexpr int SEED_K = 4;
+__device__ __forceinline__ uint32_t pack4(const uint8_t* p) {
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 3) | ((uint32_t)p[2] << 6) | ((uint32_t)p[3] << 9);
+}
+__device__ inline void find_events(const uint8_t* __restrict__ R, const uint16_t* __restrict__ R4, int n,
+                                   const uint8_t* __restrict__ Qf, const uint8_t* __restrict__ Qc, int m,
+                                   int minsize, Ev* __restrict__ ev, int* __restrict__ ev_n, int ev_cap, int nthreads) {
+    const int step = max(1, minsize - SEED_K + 1);
+    for (int j = 0; j + SEED_K <= m; j += step) {
+        const uint32_t qf = pack4(Qf + j), qc = pack4(Qc + j);
+        for (int l = threadIdx.x; l + SEED_K <= n; l += nthreads) {
+            const uint32_t r4 = R4[l];
+            if (r4 != qf && r4 != qc) continue;
+#pragma unroll 1
+            for (int strand = 0; strand < 2; ++strand) {
+                if (r4 != (strand ? qc : qf)) continue;
+                const uint8_t* __restrict__ Q = strand ? Qc : Qf;
+                const int cmax = min(step, min(j, l));
+                int c = 0;
+                while (c < cmax && Q[j - 1 - c] == R[l - 1 - c]) ++c;
+                if (c >= step) continue;              // the previous seed row lies in the same match
+                const int emax = min(m - j, n - l);
+                const int e = SEED_K + smatch_fwd(Q + j + SEED_K, R + l + SEED_K, emax - SEED_K);
+                const int L = c + e, l0 = l - c;
+                if (L < minsize) continue;
                 int slot = atomicAdd(ev_n, 1);
                 if (slot < ev_cap) {
-                    ev[slot].l = (uint16_t)l0; ev[slot].e = (uint16_t)(l0 + L); ev[slot].u = (uint16_t)(l0 + lr); ev[slot].pad = 0;
+                    ev[slot].l = (uint16_t)l0; ev[slot].e = (uint16_t)(l0 + L); ev[slot].u = 0; ev[slot].pad = (uint16_t)(strand << 1);
                     ev[slot].d1 = (j - c) - l0;
                 }
             }
         }
     }
-    // a window shorter than 2 bases cannot seed; minsize >= 2 always holds for the callers (q = 30 -> minsize >= 6)
 }
-// (UP', EP', d1) of a strand at reference position k  (Intersect_UM closed form over the strand's events)
-__device__ __forceinline__ void eval_at(const Ev* __restrict__ ev, int ne, int k, int& UP, int& EP, int& d1) {
-    int fl = 0, t1 = 0, t2 = 0, dd = 0;
-    for (int i = 0; i < ne; ++i) {
-        int l = ev[i].l;
-        if (l > k) continue;
-        int e = ev[i].e;
-        fl = max(fl, (int)ev[i].u);
-        if (e > t1) { t2 = t1; t1 = e; dd = ev[i].d1; }
-        else if (e == t1) { t2 = t1; }
-        else if (e > t2) t2 = e;
+// A1 on demand: for every new event, lrp[l] = longest prefix of R[l..) occurring at another position of R (one warp per
+// event, lanes stride over the other positions; cached per reference position), then u = l + lrp and validity L > lrp.
+__device__ inline void resolve_unique(const uint8_t* __restrict__ R, int n, uint16_t* __restrict__ lrp, Ev* __restrict__ ev, int e_begin,
+                                      int e_end, int nthreads) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = nthreads >> 5;
+    for (int i = e_begin + warp; i < e_end; i += nwarps) {
+        const int l = ev[i].l;
+        int v = lrp[l];
+        if (v == LRP_UNKNOWN) {
+            int best = 0;
+            const uint8_t c0 = R[l];
+            for (int l2 = lane; l2 < n; l2 += 32) {
+                if (l2 == l || R[l2] != c0) continue;
+                best = max(best, 1 + smatch_fwd(R + l + 1, R + l2 + 1, n - max(l, l2) - 1));
+            }
+            for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+            v = best;
+            if (lane == 0) lrp[l] = (uint16_t)v;      // racing warps store the same value
+        }
+        if (lane == 0) {
+            const int L = (int)ev[i].e - l;
+            ev[i].u = (uint16_t)(l + v);
+            ev[i].pad = (uint16_t)((ev[i].pad & 2) | ((L > v) ? 1 : 0));   // bit0: unique in R (an event of Find_UM); bit1: reverse strand
+        }
     }
-    UP = max(fl, t2);
-    EP = max(t1, fl);
-    d1 = dd;
+}
+// (UP', EP', d1) of both strands of one query at reference position k (Intersect_UM closed form over the query's events)
+struct StrandVal { int UP, EP, d1; };
+struct Acc { int fl, t1, t2, dd; };
+__device__ __forceinline__ void acc_add(Acc& a, int u, int e, int d1) {
+    a.fl = max(a.fl, u);
+    if (e > a.t1) { a.t2 = a.t1; a.t1 = e; a.dd = d1; }
+    else if (e == a.t1) { a.t2 = a.t1; }
+    else if (e > a.t2) a.t2 = e;
+}
+__device__ __forceinline__ void eval_at(const Ev* __restrict__ ev, int ne, int k, StrandVal& F, StrandVal& C) {
+    Acc af = {0, 0, 0, 0}, ac = {0, 0, 0, 0};
+    for (int i = 0; i < ne; ++i) {
+        const int l = ev[i].l;
+        const int tag = ev[i].pad;
+        if (l > k || !(tag & 1)) continue;
+        if (tag & 2) acc_add(ac, (int)ev[i].u, (int)ev[i].e, ev[i].d1);
+        else acc_add(af, (int)ev[i].u, (int)ev[i].e, ev[i].d1);
+    }
+    F.UP = max(af.fl, af.t2); F.EP = max(af.t1, af.fl); F.d1 = af.dd;
+    C.UP = max(ac.fl, ac.t2); C.EP = max(ac.t1, ac.fl); C.d1 = ac.dd;
 }
 
-__global__ void __launch_bounds__(SM_MAX_THREADS) small_region_kernel(
+__global__ void __launch_bounds__(SM_MAX_THREADS, 6) small_region_kernel(
     const uint8_t* __restrict__ text, const int64_t* __restrict__ gbase_fwd, const int64_t* __restrict__ gbase_rc,
     const int64_t* __restrict__ glen, int nq, const TaskDev* __restrict__ tasks, const int32_t* __restrict__ qcoords,
     const int32_t* __restrict__ task_ids, int ntasks, ClassCfg cfg, TaskOut* __restrict__ outs,
@@ -125,6 +175,7 @@ __global__ void __launch_bounds__(SM_MAX_THREADS) small_region_kernel(
     uint8_t* Qf = smem + off; off += ClassCfg::al(cfg.m_cap);
     uint8_t* Qc = smem + off; off += ClassCfg::al(cfg.m_cap);
     uint16_t* lrp = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
+    uint16_t* R4 = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
     uint16_t* MUP = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
     uint16_t* MEP = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
     Ev* evs = reinterpret_cast<Ev*>(smem + off); off += ClassCfg::al((size_t)cfg.ev_cap * sizeof(Ev));
@@ -139,8 +190,11 @@ __global__ void __launch_bounds__(SM_MAX_THREADS) small_region_kernel(
     for (int i = tid; i < n; i += T) { R[i] = text[tk.ref_off + i]; MUP[i] = 0; MEP[i] = (uint16_t)n; lrp[i] = LRP_UNKNOWN; }
     if (tid < 8) s_int[tid] = 0;
     __syncthreads();
+    for (int i = tid; i + SEED_K <= n; i += T) R4[i] = (uint16_t)pack4(R + i);
+    __syncthreads();
 
-    // pass 0: fold all queries (ini order) into Master, keeping every strand's events in shared memory
+    // pass 0: fold all queries (ini order) into Master, keeping every query's events in shared memory
+    int e0 = 0;
     for (int q = 0; q < nq; ++q) {
         const int m = ql[q];
         const int64_t g = q + 1;
@@ -148,27 +202,23 @@ __global__ void __launch_bounds__(SM_MAX_THREADS) small_region_kernel(
         const int64_t c_off = gbase_rc[g] + (glen[g] - qs[q] - m);
         for (int i = tid; i < m; i += T) { Qf[i] = text[f_off + i]; Qc[i] = text[c_off + i]; }
         __syncthreads();
-        const int e0 = min(s_int[0], cfg.ev_cap);
-        __syncthreads();
-        find_events(R, n, Qf, m, lrp, minsize, evs, &s_int[0], cfg.ev_cap, T);
-        __syncthreads();
-        const int e1 = min(s_int[0], cfg.ev_cap);
-        __syncthreads();
-        find_events(R, n, Qc, m, lrp, minsize, evs, &s_int[0], cfg.ev_cap, T);
+        find_events(R, R4, n, Qf, Qc, m, minsize, evs, &s_int[0], cfg.ev_cap, T);
         __syncthreads();
         const int e2 = s_int[0];
         if (e2 > cfg.ev_cap) { if (tid == 0) s_int[3] = 1; __syncthreads(); break; }
-        if (tid == 0) { evoff[2 * q] = (uint16_t)e0; evoff[2 * q + 1] = (uint16_t)e1; evoff[2 * q + 2] = (uint16_t)e2; }
+        resolve_unique(R, n, lrp, evs, e0, e2, T);
+        if (tid == 0) { evoff[q] = (uint16_t)e0; evoff[q + 1] = (uint16_t)e2; }
+        __syncthreads();
         for (int k = tid; k < n; k += T) {
-            int UPf, EPf, df, UPc, EPc, dc;
-            eval_at(evs + e0, e1 - e0, k, UPf, EPf, df);
-            eval_at(evs + e1, e2 - e1, k, UPc, EPc, dc);
+            StrandVal F, C;
+            eval_at(evs + e0, e2 - e0, k, F, C);
             int mep = MEP[k], mup = MUP[k];
-            int fe = min(mep, EPf), ce = min(mep, EPc);
-            if (fe > ce) { mup = max(mup, UPf); mep = fe; }
-            else { mup = max(mup, UPc); mep = ce; }
+            int fe = min(mep, F.EP), ce = min(mep, C.EP);
+            if (fe > ce) { mup = max(mup, F.UP); mep = fe; }
+            else { mup = max(mup, C.UP); mep = ce; }
             MUP[k] = (uint16_t)mup; MEP[k] = (uint16_t)mep;
         }
+        e0 = e2;
         __syncthreads();
     }
     __syncthreads();
@@ -211,14 +261,13 @@ __global__ void __launch_bounds__(SM_MAX_THREADS) small_region_kernel(
         const int k = candK[c];
         int M = n;
         for (int q = 0; q < nq; ++q) {
-            const int e0 = evoff[2 * q], e1 = evoff[2 * q + 1], e2 = evoff[2 * q + 2];
-            int UPf, EPf, df, UPc, EPc, dc;
-            eval_at(evs + e0, e1 - e0, k, UPf, EPf, df);
-            eval_at(evs + e1, e2 - e1, k, UPc, EPc, dc);
-            int fe = min(M, EPf), ce = min(M, EPc);
+            const int a0 = evoff[q], a1 = evoff[q + 1];
+            StrandVal F, C;
+            eval_at(evs + a0, a1 - a0, k, F, C);
+            int fe = min(M, F.EP), ce = min(M, C.EP);
             const size_t o = (size_t)(base + c) * nq + q;
-            if (fe > ce) { out_sp[o] = k + df; out_fwd[o] = 1; M = fe; }
-            else { out_sp[o] = k + dc; out_fwd[o] = 0; M = ce; }
+            if (fe > ce) { out_sp[o] = k + F.d1; out_fwd[o] = 1; M = fe; }
+            else { out_sp[o] = k + C.d1; out_fwd[o] = 0; M = ce; }
         }
         out_k[base + c] = k;
         out_lon[base + c] = (int)MEP[k] - k;
