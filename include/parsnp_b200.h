@@ -25,9 +25,9 @@
  *   pb200_minsize
  *       Converter()+Calculator() as used at src/parsnp.cpp:1502-1514.
  *
- *   pb200_comm_*  (multi-GPU; one process per GPU)
+ *   pb200_comm_set / pb200_comm_clear  (multi-GPU; one process per GPU)
  *       no reference counterpart (the reference has no distributed backend): query genomes are sharded over
- *       ranks for the anchor scan, regions are sharded for the recursion; NCCL carries the exchange.
+ *       ranks for the anchor scan, windows are sharded for the recursion; the caller's collectives carry the exchange.
  */
 #ifndef PARSNP_B200_H
 #define PARSNP_B200_H
@@ -126,12 +126,19 @@ int pb200_engine_timers(pb200_genomes* g, double* values, int cap);
 const char* pb200_engine_timer_names(void);
 void pb200_engine_reset_timers(pb200_genomes* g);
 
-/* ---- multi-GPU ---- */
-#define PB200_NCCL_ID_BYTES 128
-/* nccl_lib: path of the libnccl.so to dlopen (the one torch already loaded) */
-int pb200_comm_unique_id(const char* nccl_lib, uint8_t id[PB200_NCCL_ID_BYTES]);
-int pb200_comm_init(pb200_genomes* g, const char* nccl_lib, const uint8_t id[PB200_NCCL_ID_BYTES], int rank, int world);
-void pb200_comm_destroy(pb200_genomes* g);
+/* ---- multi-GPU (one process per GPU; every rank calls pb200_align_resident with the same genomes and parameters) ----
+ * The library shards the search (queries for large windows, windows for the recursion batches)
+ * and calls back for the collectives, which the host side implements with torch.distributed (NCCL over NVLink on the
+ * GPUs, gloo in the CPU tests).  Callbacks return 0 on success.  `on_device` = the pointers are device memory of this
+ * rank's GPU (the library has synchronised its stream before the call; the callback must complete the collective
+ * before returning). */
+typedef int (*pb200_allgather_cb)(void* user, const void* send, void* recv, int64_t bytes_per_rank, int on_device);
+typedef int (*pb200_allreduce_cb)(void* user, void* buf_i32, int64_t count, int is_max, int on_device);   /* int32 min / max */
+typedef int (*pb200_bcast_cb)(void* user, void* buf, int64_t bytes, int root, int on_device);
+/* bcast_index != 0: the window index is built on rank 0 and broadcast; 0: every rank rebuilds it */
+int pb200_comm_set(pb200_genomes* g, int rank, int world, pb200_allgather_cb ag, pb200_allreduce_cb ar, pb200_bcast_cb bc,
+                   void* user, int bcast_index);
+void pb200_comm_clear(pb200_genomes* g);
 
 #ifdef __cplusplus
 }

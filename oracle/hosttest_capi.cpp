@@ -2,12 +2,16 @@
 // (parsnp_b200/csrc/host/*.cpp) linked with the CPU search backends of oracle/ so that `-m "not gpu"` tests can
 // exercise the host logic (queue order, trim, LCB chaining) without a GPU.  Never linked into libparsnp_b200.so.
 #include "../parsnp_b200/csrc/host/result.h"
+#include "../parsnp_b200/csrc/host/sharded.h"
+#include <memory>
+#include <stdexcept>
 #include <cstdlib>
 #include <cstring>
 
 namespace pb200_oracle {
 pb200::SearchBackend* make_spec_backend();
 pb200::SearchBackend* make_ref_backend();
+pb200::StagedWindowEngine* as_staged(pb200::SearchBackend* b);
 struct SpecCand { int32_t k, lon; std::vector<int32_t> sp; std::vector<uint8_t> fwd; };
 void spec_window(const uint8_t* R, int64_t n, int nq, const uint8_t* const* Q, const int64_t* m, int minsize, std::vector<SpecCand>& out);
 void spec_lrp(const uint8_t* R, int64_t n, std::vector<int32_t>& lrp);
@@ -24,6 +28,29 @@ int pbtest_align(int backend, int n, const uint8_t* const* seqs, const int64_t* 
         bool ok = a.run();
         *out = pb200::make_result(a);
         delete be;
+        return ok ? 0 : PB200_ERR_NO_MUMS;
+    } catch (const std::exception& e) { pb200::g_last_error = e.what(); return PB200_ERR_INTERNAL; }
+}
+// the N>1 path on CPU: host orchestrator replicated on every rank, search sharded over ranks (queries for large windows,
+// windows for the recursion batches, host/sharded.cpp) on the csgmum backend; collectives = caller callbacks (gloo)
+namespace {
+struct CbComm : public pb200::Comm {
+    pb200_allgather_cb ag; pb200_allreduce_cb ar; pb200_bcast_cb bc; void* user;
+    void allgather(const void* s, void* r, size_t b, bool d) override { if (ag(user, s, r, (int64_t)b, d) != 0) throw std::runtime_error("allgather failed"); }
+    void allreduce_i32(int32_t* p, size_t c, bool mx, bool d) override { if (ar(user, p, (int64_t)c, mx, d) != 0) throw std::runtime_error("allreduce failed"); }
+    void bcast(void* p, size_t b, int root, bool d) override { if (bc(user, p, (int64_t)b, root, d) != 0) throw std::runtime_error("bcast failed"); }
+};
+}
+int pbtest_align_sharded(int rank, int world, pb200_allgather_cb ag, pb200_allreduce_cb ar, pb200_bcast_cb bc, int n,
+                         const uint8_t* const* seqs, const int64_t* lens, const pb200_params* prm, pb200_result** out, int64_t* counters) {
+    try {
+        std::unique_ptr<pb200::SearchBackend> local(pb200_oracle::make_ref_backend());
+        CbComm comm; comm.rank = rank; comm.world = world; comm.ag = ag; comm.ar = ar; comm.bc = bc; comm.user = nullptr;
+        pb200::ShardedBackend sb(local.get(), pb200_oracle::as_staged(local.get()), &comm, true);
+        pb200::Aligner a(n, seqs, lens, pb200::to_align_params(prm), &sb);
+        bool ok = a.run();
+        *out = pb200::make_result(a);
+        if (counters) { counters[0] = sb.staged_windows; counters[1] = sb.sharded_small_windows; }
         return ok ? 0 : PB200_ERR_NO_MUMS;
     } catch (const std::exception& e) { pb200::g_last_error = e.what(); return PB200_ERR_INTERNAL; }
 }

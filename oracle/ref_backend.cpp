@@ -6,7 +6,9 @@
 #include <cstring>
 #include <cstdlib>
 #include <vector>
+#include <algorithm>
 #include "../parsnp_b200/csrc/common.h"
+#include "../parsnp_b200/csrc/host/sharded.h"
 
 extern "C" {
 void* ref_index_build(const char* text, long n, double factor);
@@ -22,7 +24,7 @@ static inline char comp(char c) {
     switch (c) { case 'A': return 'T'; case 'T': return 'A'; case 'C': return 'G'; case 'G': return 'C'; default: return 'N'; }
 }
 
-class RefBackend : public pb200::SearchBackend {
+class RefBackend : public pb200::SearchBackend, public pb200::StagedWindowEngine {
 public:
     void set_genomes(int n, const uint8_t* const* seq, const int64_t* len) override {
         n_ = n; seq_.assign(seq, seq + n); len_.assign(len, len + n);
@@ -64,10 +66,73 @@ public:
             ref_index_free(ix);
         }
     }
+    // ---- StagedWindowEngine on host buffers: the same csgmum calls, restricted to a block of queries and started from a
+    //      given Master (the reference's Master/MasterRC arrays are in/out, src/csgmum/mum.c:125-175)
+    int64_t staged_threshold = 5000;
+    bool wants_staged(const pb200::WindowTask& t, const int64_t*) override { return t.ref_len > staged_threshold; }
+    bool buffers_on_device() const override { return false; }
+    void window_begin(const pb200::WindowTask& t, const int64_t* coords, bool) override {
+        w_ = t; wcoords_ = coords;
+        if (ix_) ref_index_free(ix_);
+        ix_ = ref_index_build((const char*)seq_[0] + t.ref_start, (long)t.ref_len, 2.0);
+        up_.assign(t.ref_len, 0); ep_.assign(t.ref_len, (int32_t)t.ref_len); init_.clear();
+    }
+    void window_index_buffers(std::vector<std::pair<void*, size_t>>&) override {}     // every rank builds its own CSG
+    int window_n() const override { return (int)w_.ref_len; }
+    void window_scan(int q0, int q1) override { q0_ = q0; q1_ = q1; }
+    void window_fold(bool init) override {
+        const int64_t n = w_.ref_len; const int nq = n_ - 1;
+        const int64_t* qs = wcoords_ + w_.coord_off; const int64_t* ql = qs + nq;
+        if (init) { up_.assign(n, 0); ep_.assign(n, (int32_t)n); }
+        std::vector<int> Master(2 * n), MasterRC(2 * n), Pair(2 * n, 0), PairRC(2 * n, 0);
+        for (int64_t i = 0; i < n; ++i) { Master[2 * i] = MasterRC[2 * i] = up_[i]; Master[2 * i + 1] = MasterRC[2 * i + 1] = ep_[i]; }
+        msp_.assign(q1_ - q0_, std::vector<unsigned long>(n, 0)); fw_.assign(q1_ - q0_, std::vector<char>(n, 1));
+        std::vector<unsigned long> tmp(n); std::vector<char> rc;
+        for (int q = q0_; q < q1_; ++q) {
+            std::fill(tmp.begin(), tmp.end(), 0ul);
+            const char* Q = (const char*)seq_[q + 1] + qs[q];
+            rc.resize(ql[q]);
+            for (int64_t i = 0; i < ql[q]; ++i) rc[i] = comp(Q[ql[q] - 1 - i]);
+            ref_find_um(ix_, Q, (long)ql[q], msp_[q - q0_].data(), Pair.data());
+            ref_find_um(ix_, rc.data(), (long)ql[q], tmp.data(), PairRC.data());
+            ref_intersect_um(ix_, Master.data(), Pair.data(), (int)n, msp_[q - q0_].data());
+            ref_intersect_um(ix_, MasterRC.data(), PairRC.data(), (int)n, tmp.data());
+            ref_merge_master(Master.data(), MasterRC.data(), (int)n, msp_[q - q0_].data(), fw_[q - q0_].data(), tmp.data());
+        }
+        for (int64_t i = 0; i < n; ++i) { up_[i] = Master[2 * i]; ep_[i] = Master[2 * i + 1]; }
+    }
+    int32_t* window_master_up() override { return up_.data(); }
+    int32_t* window_master_ep() override { return ep_.data(); }
+    int32_t* window_gather_buffer(size_t ints) override { gather_.resize(ints); return gather_.data(); }
+    void window_apply_prefix(const int32_t* g, int, int rank) override {
+        const int64_t n = w_.ref_len;
+        init_.assign(n, (int32_t)n);
+        for (int r = 0; r < rank; ++r) for (int64_t k = 0; k < n; ++k) init_[k] = std::min(init_[k], g[(size_t)r * n + k]);
+        up_.assign(n, 0); ep_ = init_;
+    }
+    uint32_t window_emit() override {
+        cand_.clear();
+        int prev = 0;
+        for (int64_t k = 0; k < w_.ref_len; ++k) {
+            if (ep_[k] > prev && up_[k] < ep_[k] && ep_[k] - k >= w_.minsize) cand_.push_back((int32_t)k);
+            prev = ep_[k];
+        }
+        return (uint32_t)cand_.size();
+    }
+    void window_pass2(std::vector<int32_t>& k, std::vector<int32_t>& lon, std::vector<int32_t>& sp, std::vector<uint8_t>& fwd) override {
+        for (int32_t c : cand_) {
+            k.push_back(c); lon.push_back(ep_[c] - c);
+            for (int q = q0_; q < q1_; ++q) { sp.push_back((int32_t)msp_[q - q0_][c]); fwd.push_back((uint8_t)fw_[q - q0_][c]); }
+        }
+    }
 private:
     int n_ = 0; std::vector<const uint8_t*> seq_; std::vector<int64_t> len_;
+    pb200::WindowTask w_{}; const int64_t* wcoords_ = nullptr; void* ix_ = nullptr; int q0_ = 0, q1_ = 0;
+    std::vector<int32_t> up_, ep_, init_, gather_, cand_;
+    std::vector<std::vector<unsigned long>> msp_; std::vector<std::vector<char>> fw_;
 };
 
 pb200::SearchBackend* make_ref_backend() { return new RefBackend(); }
+pb200::StagedWindowEngine* as_staged(pb200::SearchBackend* b) { return dynamic_cast<RefBackend*>(b); }
 
 }  // namespace pb200_oracle

@@ -30,6 +30,97 @@ class CWindow(C.Structure):
                 ("pad", C.c_int32)]
 
 
+AG_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int)
+AR_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int)
+BC_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int)
+
+
+class _DevPtr:
+    """raw device pointer -> zero-copy torch tensor via __cuda_array_interface__"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class TorchComm:
+    """The collectives the library calls back for (include/parsnp_b200.h, pb200_comm_set), implemented with
+    torch.distributed: NCCL over NVLink when the process group is NCCL (device pointers are wrapped zero-copy, host
+    buffers are staged through a CUDA tensor), gloo on CPU (tests)."""
+
+    def __init__(self, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.nccl = dist.get_backend(group) == "nccl"
+        self.ag = AG_CB(self._allgather)
+        self.ar = AR_CB(self._allreduce)
+        self.bc = BC_CB(self._bcast)
+        self.calls = {"allgather": 0, "allreduce": 0, "bcast": 0, "bytes": 0}
+
+    def _tensor(self, ptr, nbytes, on_device):
+        torch = self.torch
+        if on_device:
+            return torch.as_tensor(_DevPtr(ptr, nbytes), device="cuda"), None
+        host = torch.frombuffer((C.c_uint8 * nbytes).from_address(ptr), dtype=torch.uint8)
+        if self.nccl:
+            return host.cuda(), host
+        return host, None
+
+    def _finish(self, t, host):
+        if host is not None:
+            host.copy_(t.cpu())
+        if self.nccl:
+            self.torch.cuda.synchronize()
+
+    def _allgather(self, user, send, recv, nbytes, on_device):
+        try:
+            if nbytes == 0:
+                return 0
+            st, _ = self._tensor(send, nbytes, on_device)
+            rt, rhost = self._tensor(recv, nbytes * self.world, on_device)
+            self.dist.all_gather_into_tensor(rt, st, group=self.group)
+            self._finish(rt, rhost)
+            self.calls["allgather"] += 1
+            self.calls["bytes"] += nbytes * self.world
+            return 0
+        except Exception as e:  # noqa: BLE001 - reported through the C ABI
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    def _allreduce(self, user, buf, count, is_max, on_device):
+        try:
+            if count == 0:
+                return 0
+            t, host = self._tensor(buf, count * 4, on_device)
+            v = t.view(self.torch.int32)
+            self.dist.all_reduce(v, op=self.dist.ReduceOp.MAX if is_max else self.dist.ReduceOp.MIN, group=self.group)
+            self._finish(t, host)
+            self.calls["allreduce"] += 1
+            self.calls["bytes"] += count * 4
+            return 0
+        except Exception:  # noqa: BLE001
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    def _bcast(self, user, buf, nbytes, root, on_device):
+        try:
+            if nbytes == 0:
+                return 0
+            t, host = self._tensor(buf, nbytes, on_device)
+            self.dist.broadcast(t, src=self.dist.get_global_rank(self.group, root) if self.group is not None else root, group=self.group)
+            self._finish(t, host)
+            self.calls["bcast"] += 1
+            self.calls["bytes"] += nbytes
+            return 0
+        except Exception:  # noqa: BLE001
+            import traceback
+            traceback.print_exc()
+            return 1
+
+
 def make_params(c=21, d=300, q=30, p=15000000, diagdiff=0.12, filter=1, anchors_only=0,
                 anchors="1.1*(Log(S))", mums="1.1*(Log(S))", flags=0):
     return CParams(c, d, q, p, diagdiff, filter, anchors_only, anchors.encode(), mums.encode(), flags, 0)
@@ -115,9 +206,8 @@ def load():
     lib.pb200_engine_timers.argtypes = [vp, vp, C.c_int]
     lib.pb200_engine_timer_names.restype = C.c_char_p
     lib.pb200_engine_reset_timers.argtypes = [vp]
-    lib.pb200_comm_unique_id.argtypes = [C.c_char_p, vp]
-    lib.pb200_comm_init.argtypes = [vp, C.c_char_p, vp, C.c_int, C.c_int]
-    lib.pb200_comm_destroy.argtypes = [vp]
+    lib.pb200_comm_set.argtypes = [vp, C.c_int, C.c_int, AG_CB, AR_CB, BC_CB, vp, C.c_int]
+    lib.pb200_comm_clear.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -179,6 +269,15 @@ class Genomes:
         for p in (off, k, lon, sp, fwd):
             self.lib.pb200_free_buffer(p)
         return res
+
+    def set_comm(self, comm, bcast_index=True):
+        """shard the search of align() over the ranks of `comm` (a TorchComm); every rank must hold the same genomes"""
+        self._comm = comm           # keep the callbacks alive
+        _check(self.lib, self.lib.pb200_comm_set(self.h, comm.rank, comm.world, comm.ag, comm.ar, comm.bc, None, 1 if bcast_index else 0))
+
+    def clear_comm(self):
+        self.lib.pb200_comm_clear(self.h)
+        self._comm = None
 
     def engine_timers(self):
         names = self.lib.pb200_engine_timer_names().decode().split(",")

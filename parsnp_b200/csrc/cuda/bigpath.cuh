@@ -372,12 +372,12 @@ __global__ void emit_flags_kernel(const int32_t* __restrict__ MUP, const int32_t
 // per candidate: replay the fold at position k to recover every query's strand and start (SP)
 __global__ void pass2_kernel(const uint32_t* __restrict__ ck, int ncand, const uint32_t* __restrict__ evl, const int4* __restrict__ states,
                              const uint32_t* __restrict__ seg_lo, const uint32_t* __restrict__ seg_hi, int nq, int n,
-                             const int32_t* __restrict__ MEP, int32_t* __restrict__ out_lon, int32_t* __restrict__ out_sp,
-                             uint8_t* __restrict__ out_fwd) {
+                             const int32_t* __restrict__ MEP, const int32_t* __restrict__ initEP, int32_t* __restrict__ out_lon,
+                             int32_t* __restrict__ out_sp, uint8_t* __restrict__ out_fwd) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncand) return;
     const uint32_t k = ck[c];
-    int M = n;
+    int M = initEP ? initEP[k] : n;        // Master.EP[k] before this rank's first query (multi-GPU: prefix over earlier ranks)
     for (int q = 0; q < nq; ++q) {
         int UPf, EPf, df, UPc, EPc, dc;
         int lo = (int)seg_lo[2 * q], hi = (int)seg_hi[2 * q];
@@ -498,14 +498,16 @@ public:
         PB_CUDA(cudaGetLastError());
     }
 
-    void scan(const uint8_t* R, int n, int nq, const std::vector<StrandDesc>& strands, int minsize, cudaStream_t st,
-              std::vector<int32_t>& out_k, std::vector<int32_t>& out_lon, std::vector<int32_t>& out_sp, std::vector<uint8_t>& out_fwd) {
+    // ---- staged scan (the single-GPU path runs the stages back to back; the sharded path exchanges between them) ----
+    // stage 1: MEM events of the given strands (2 per local query), ordered by (strand, l) and scanned
+    void scan_events(const uint8_t* R, int n, int nq, const std::vector<StrandDesc>& strands, int minsize, cudaStream_t st) {
         const int TB = 256;
         const int ns = 2 * nq;
         const int k = seed_k_;
         const int step = std::max(1, minsize - k + 1);
-        StrandDesc* d_str = strands_.ensure((size_t)ns, false, st);
-        PB_CUDA(cudaMemcpyAsync(d_str, strands.data(), sizeof(StrandDesc) * ns, cudaMemcpyHostToDevice, st));
+        cur_n_ = n; cur_nq_ = nq; cur_minsize_ = minsize;
+        StrandDesc* d_str = strands_.ensure((size_t)std::max(ns, 1), false, st);
+        if (ns) PB_CUDA(cudaMemcpyAsync(d_str, strands.data(), sizeof(StrandDesc) * ns, cudaMemcpyHostToDevice, st));
         int64_t tot_m = 0;
         int max_m = 0;
         for (int s = 0; s < ns; ++s) { tot_m += strands[s].m; max_m = std::max(max_m, strands[s].m); }
@@ -518,10 +520,10 @@ public:
             uint64_t* ev = evv0_.ensure(cap, false, st);
             PB_CUDA(cudaMemsetAsync(d_cnt, 0, 8, st));
             long long samples = ((long long)max_m + step - 1) / step;
-            dim3 grid((unsigned)((samples + 127) / 128), (unsigned)ns);
+            dim3 grid((unsigned)((samples + 127) / 128), (unsigned)std::max(ns, 1));
             if (samples > 0 && ns > 0)
                 pb200::launch(seed_extend_kernel, grid, 128, 0, st, R, n, sa_.get(), lrp_.get(), table_.get(), k, step, minsize, d_str, ek, ev,
-                                                         d_cnt, (unsigned long long)cap);
+                              d_cnt, (unsigned long long)cap);
             PB_CUDA(cudaMemcpyAsync(&E, d_cnt, 8, cudaMemcpyDeviceToHost, st));
             PB_CUDA(cudaStreamSynchronize(st));
             if (E <= cap) break;
@@ -549,10 +551,10 @@ public:
             eks = r2 ? b_k : a_k;
             evs = r2 ? b_v : a_v;
         }
-        uint32_t* seg_lo = seglo_.ensure((size_t)ns, false, st);
-        uint32_t* seg_hi = seghi_.ensure((size_t)ns, false, st);
-        PB_CUDA(cudaMemsetAsync(seg_lo, 0, (size_t)ns * 4, st));
-        PB_CUDA(cudaMemsetAsync(seg_hi, 0, (size_t)ns * 4, st));
+        uint32_t* seg_lo = seglo_.ensure((size_t)std::max(ns, 1), false, st);
+        uint32_t* seg_hi = seghi_.ensure((size_t)std::max(ns, 1), false, st);
+        PB_CUDA(cudaMemsetAsync(seg_lo, 0, (size_t)std::max(ns, 1) * 4, st));
+        PB_CUDA(cudaMemsetAsync(seg_hi, 0, (size_t)std::max(ns, 1) * 4, st));
         uint32_t* evl = evl_.ensure(std::max<size_t>((size_t)E, 1), false, st);
         int4* states = states_.ensure(std::max<size_t>((size_t)E, 1), false, st);
         if (E > 0) pb200::launch(strand_segments_kernel, (unsigned)((E + TB - 1) / TB), TB, 0, st, eks, (int)E, seg_lo, seg_hi, evl);
@@ -561,19 +563,31 @@ public:
         if (tm) tm->start(GpuTimers::T_SCAN_EVSCAN, st);
         if (ns > 0) pb200::launch(event_scan_kernel, (unsigned)ns, 256, 0, st, evl, evs, lrp_.get(), seg_lo, seg_hi, states);
         if (tm) tm->stop(GpuTimers::T_SCAN_EVSCAN, st);
-
+        last_events = (int64_t)E;
+    }
+    // stage 2: fold the local queries (ini order) into Master; init = true starts from (UP 0, EP n), else from the
+    // current contents of master_up()/master_ep() (multi-GPU: EP preset to the prefix over earlier ranks, UP = 0)
+    void fold(bool init, cudaStream_t st) {
+        const int n = cur_n_;
         if (tm) tm->start(GpuTimers::T_SCAN_FOLD, st);
-        int32_t* MUP = mup_.ensure((size_t)n, false, st);
-        int32_t* MEP = mep_.ensure((size_t)n, false, st);
-        pb200::launch(fold_kernel, (unsigned)((n + FOLD_TILE - 1) / FOLD_TILE), FOLD_THREADS, 0, st, evl, states, seg_lo, seg_hi, nq, n, MUP, MEP, 1);
+        int32_t* MUP = mup_.ensure((size_t)n, true, st);
+        int32_t* MEP = mep_.ensure((size_t)n, true, st);
+        pb200::launch(fold_kernel, (unsigned)((n + FOLD_TILE - 1) / FOLD_TILE), FOLD_THREADS, 0, st, evl_.get(), states_.get(), seglo_.get(),
+                      seghi_.get(), cur_nq_, n, MUP, MEP, init ? 1 : 0);
         if (tm) tm->stop(GpuTimers::T_SCAN_FOLD, st);
-
+    }
+    int32_t* master_up(cudaStream_t st) { return mup_.ensure((size_t)cur_n_, true, st); }
+    int32_t* master_ep(cudaStream_t st) { return mep_.ensure((size_t)cur_n_, true, st); }
+    // stage 3: candidate positions from the (global) Master -> device list, returns the count
+    uint32_t emit(cudaStream_t st) {
+        const int TB = 256;
+        const int n = cur_n_;
         if (tm) tm->start(GpuTimers::T_SCAN_EMIT, st);
         uint32_t* flag = tmpA_.ensure((size_t)n + 1, false, st);
         uint32_t* pos = tmpB_.ensure((size_t)n + 1, false, st);
         uint32_t* d_tot = total_.ensure(4, false, st);
         const unsigned nb = (unsigned)((n + TB - 1) / TB);
-        pb200::launch(emit_flags_kernel, nb, TB, 0, st, MUP, MEP, n, minsize, flag);
+        pb200::launch(emit_flags_kernel, nb, TB, 0, st, mup_.get(), mep_.get(), n, cur_minsize_, flag);
         scanner_.scan<prim::OpSum, true>(flag, pos, n, d_tot, st);
         uint32_t ncand = 0;
         PB_CUDA(cudaMemcpyAsync(&ncand, d_tot, 4, cudaMemcpyDeviceToHost, st));
@@ -581,7 +595,15 @@ public:
         uint32_t* ck = ck_.ensure(std::max<size_t>(ncand, 1), false, st);
         if (ncand) pb200::launch(compact_kernel, nb, TB, 0, st, flag, pos, n, nullptr, ck);
         if (tm) tm->stop(GpuTimers::T_SCAN_EMIT, st);
-
+        cur_ncand_ = ncand;
+        return ncand;
+    }
+    // stage 4: per candidate, strand flag and start of every LOCAL query; initEP (device, n ints) = Master.EP before the
+    // first local query, or null.  Appends to the host vectors.
+    void pass2(const int32_t* initEP, cudaStream_t st, std::vector<int32_t>& out_k, std::vector<int32_t>& out_lon,
+               std::vector<int32_t>& out_sp, std::vector<uint8_t>& out_fwd) {
+        const uint32_t ncand = cur_ncand_;
+        const int nq = cur_nq_, n = cur_n_;
         if (tm) tm->start(GpuTimers::T_SCAN_PASS2, st);
         const size_t base = out_k.size();
         out_k.resize(base + ncand);
@@ -593,8 +615,9 @@ public:
             int32_t* d_lon = olon_.ensure(ncand, false, st);
             int32_t* d_sp = osp_.ensure((size_t)ncand * std::max(nq, 1), false, st);
             uint8_t* d_fwd = ofwd_.ensure((size_t)ncand * std::max(nq, 1), false, st);
-            pb200::launch(pass2_kernel, (ncand + 127) / 128, 128, 0, st, ck, (int)ncand, evl, states, seg_lo, seg_hi, nq, n, MEP, d_lon, d_sp, d_fwd);
-            PB_CUDA(cudaMemcpyAsync(out_k.data() + base, ck, (size_t)ncand * 4, cudaMemcpyDeviceToHost, st));
+            pb200::launch(pass2_kernel, (ncand + 127) / 128, 128, 0, st, ck_.get(), (int)ncand, evl_.get(), states_.get(), seglo_.get(),
+                          seghi_.get(), nq, n, mep_.get(), initEP, d_lon, d_sp, d_fwd);
+            PB_CUDA(cudaMemcpyAsync(out_k.data() + base, ck_.get(), (size_t)ncand * 4, cudaMemcpyDeviceToHost, st));
             PB_CUDA(cudaMemcpyAsync(out_lon.data() + base, d_lon, (size_t)ncand * 4, cudaMemcpyDeviceToHost, st));
             if (nq) {
                 PB_CUDA(cudaMemcpyAsync(out_sp.data() + bsp, d_sp, (size_t)ncand * nq * 4, cudaMemcpyDeviceToHost, st));
@@ -604,7 +627,24 @@ public:
         }
         if (tm) tm->stop(GpuTimers::T_SCAN_PASS2, st);
         PB_CUDA(cudaGetLastError());
-        last_events = (int64_t)E;
+    }
+    void scan(const uint8_t* R, int n, int nq, const std::vector<StrandDesc>& strands, int minsize, cudaStream_t st,
+              std::vector<int32_t>& out_k, std::vector<int32_t>& out_lon, std::vector<int32_t>& out_sp, std::vector<uint8_t>& out_fwd) {
+        scan_events(R, n, nq, strands, minsize, st);
+        fold(true, st);
+        emit(st);
+        pass2(nullptr, st, out_k, out_lon, out_sp, out_fwd);
+    }
+    // multi-GPU: device pointers of the window index (for the broadcast from the building rank)
+    uint32_t* index_sa() { return sa_.get(); }
+    int32_t* index_lrp() { return lrp_.get(); }
+    uint2* index_table() { return table_.get(); }
+    size_t index_table_entries() const { return (size_t)1 << (2 * seed_k_); }
+    void alloc_index(int n, int minsize, cudaStream_t st) {      // receiving side of the broadcast
+        seed_k_ = std::min(MAX_SEED_K, std::max(1, minsize));
+        sa_.ensure((size_t)n, false, st);
+        lrp_.ensure((size_t)n, false, st);
+        table_.ensure(index_table_entries(), false, st);
     }
     int64_t last_events = 0;
 
@@ -621,6 +661,8 @@ private:
     DevBuf<unsigned long long> evcount_;
     size_t ev_cap_hint_ = 0;
     int seed_k_ = MAX_SEED_K;
+    int cur_n_ = 0, cur_nq_ = 0, cur_minsize_ = 0;
+    uint32_t cur_ncand_ = 0;
 };
 
 }  // namespace big

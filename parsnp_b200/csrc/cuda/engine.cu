@@ -11,6 +11,7 @@
 #include "../common.h"
 #include "../host/aligner.h"
 #include "../host/result.h"
+#include "../host/sharded.h"
 #include "util.cuh"
 #include "bigpath.cuh"
 #include "smallpath.cuh"
@@ -29,7 +30,19 @@ __global__ void encode_kernel(const uint8_t* __restrict__ ascii, int64_t len, ui
     if (rc) rc[len - 1 - i] = c < 4 ? (uint8_t)(3 - c) : (uint8_t)4;
 }
 
-class CudaEngine : public SearchBackend {
+// initEP[k] = min(n, block minima of the ranks before `rank`); Master = (UP 0, EP initEP)
+__global__ void prefix_min_kernel(const int32_t* __restrict__ gathered, int world, int rank, int n, int32_t* __restrict__ initEP,
+                                  int32_t* __restrict__ MUP, int32_t* __restrict__ MEP) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int m = n;
+    for (int r = 0; r < rank; ++r) m = min(m, gathered[(size_t)r * n + k]);
+    initEP[k] = m;
+    MUP[k] = 0;
+    MEP[k] = m;
+}
+
+class CudaEngine : public SearchBackend, public StagedWindowEngine {
 public:
     explicit CudaEngine(int device) : device_(device) {
         int count = 0;
@@ -106,14 +119,7 @@ public:
         std::vector<int> cls(ntasks, 3);
         std::vector<std::vector<int>> by_class(4);
         for (int t = 0; t < ntasks; ++t) {
-            const int64_t* ql = coords + tasks[t].coord_off + nq;
-            int64_t maxm = 0;
-            for (int q = 0; q < nq; ++q) maxm = std::max(maxm, ql[q]);
-            int c = 3;
-            for (int k = 0; k < 3; ++k)
-                if (tasks[t].ref_len <= classes_[k].n_cap && maxm <= classes_[k].m_cap) { c = k; break; }
-            if (tasks[t].minsize < 4) c = 3;          // the shared-memory path seeds with 4-base matches
-            if (force_big_) c = 3;
+            const int c = classify(tasks[t], coords);
             cls[t] = c;
             by_class[c].push_back(t);
         }
@@ -158,6 +164,66 @@ public:
             }
         }
     }
+
+    // ---- StagedWindowEngine (query-sharded large windows, see host/sharded.h) ----
+    int classify(const WindowTask& t, const int64_t* coords) const {
+        const int nq = n_ - 1;
+        const int64_t* ql = coords + t.coord_off + nq;
+        int64_t maxm = 0;
+        for (int q = 0; q < nq; ++q) maxm = std::max(maxm, ql[q]);
+        int c = 3;
+        for (int k = 0; k < 3; ++k)
+            if (t.ref_len <= classes_[k].n_cap && maxm <= classes_[k].m_cap) { c = k; break; }
+        if (t.minsize < 4) c = 3;          // the shared-memory path seeds with 4-base matches
+        if (force_big_) c = 3;
+        return c;
+    }
+    bool wants_staged(const WindowTask& t, const int64_t* coords) override { return classify(t, coords) == 3; }
+    bool buffers_on_device() const override { return true; }
+    void window_begin(const WindowTask& t, const int64_t* coords, bool build_index) override {
+        PB_CUDA(cudaSetDevice(device_));
+        const int nq = n_ - 1;
+        w_task_ = t;
+        w_R_ = text_.get() + gfwd_[0] + t.ref_start;
+        const int64_t* qs = coords + t.coord_off;
+        const int64_t* ql = qs + nq;
+        w_strands_.resize((size_t)2 * nq);
+        for (int q = 0; q < nq; ++q) {
+            const int g = q + 1;
+            w_strands_[2 * q] = big::StrandDesc{text_.get() + gfwd_[g] + qs[q], (int32_t)ql[q], 0};
+            w_strands_[2 * q + 1] = big::StrandDesc{text_.get() + grc_[g] + (len_[g] - qs[q] - ql[q]), (int32_t)ql[q], 0};
+        }
+        if (build_index) big_.build_index(w_R_, (int)t.ref_len, t.minsize, st_);
+        else big_.alloc_index((int)t.ref_len, t.minsize, st_);
+        PB_CUDA(cudaStreamSynchronize(st_));
+        big_windows++;
+    }
+    void window_index_buffers(std::vector<std::pair<void*, size_t>>& bufs) override {
+        const size_t n = (size_t)w_task_.ref_len;
+        bufs.emplace_back((void*)big_.index_sa(), n * 4);
+        bufs.emplace_back((void*)big_.index_lrp(), n * 4);
+        bufs.emplace_back((void*)big_.index_table(), big_.index_table_entries() * sizeof(uint2));
+    }
+    int window_n() const override { return (int)w_task_.ref_len; }
+    void window_scan(int q0, int q1) override {
+        w_q0_ = q0; w_q1_ = q1;
+        std::vector<big::StrandDesc> sd(w_strands_.begin() + 2 * q0, w_strands_.begin() + 2 * q1);
+        big_.scan_events(w_R_, (int)w_task_.ref_len, q1 - q0, sd, w_task_.minsize, st_);
+    }
+    void window_fold(bool init) override { big_.fold(init, st_); PB_CUDA(cudaStreamSynchronize(st_)); }
+    int32_t* window_master_up() override { return big_.master_up(st_); }
+    int32_t* window_master_ep() override { return big_.master_ep(st_); }
+    int32_t* window_gather_buffer(size_t ints) override { int32_t* p = w_gather_.ensure(ints, false, st_); PB_CUDA(cudaStreamSynchronize(st_)); return p; }
+    void window_apply_prefix(const int32_t* gathered, int world, int rank) override {
+        const int n = (int)w_task_.ref_len;
+        int32_t* init = w_init_.ensure((size_t)n, false, st_);
+        pb200::launch(prefix_min_kernel, (unsigned)((n + 255) / 256), 256, 0, st_, gathered, world, rank, n, init, big_.master_up(st_), big_.master_ep(st_));
+    }
+    uint32_t window_emit() override { return big_.emit(st_); }
+    void window_pass2(std::vector<int32_t>& k, std::vector<int32_t>& lon, std::vector<int32_t>& sp, std::vector<uint8_t>& fwd) override {
+        big_.pass2(w_init_.get(), st_, k, lon, sp, fwd);
+    }
+    cudaStream_t stream() const { return st_; }
 
     // test hooks: suffix array + lrp of a window of genome 0
     void debug_index(int64_t ref_start, int n, int minsize, uint32_t* sa, int32_t* lrp) {
@@ -294,6 +360,11 @@ private:
     DevBuf<small::TaskOut> d_outs_;
     DevBuf<int32_t> d_qcoords_, d_ids_, d_ck_, d_clon_, d_csp_;
     DevBuf<unsigned long long> d_candcnt_;
+    DevBuf<int32_t> w_gather_, w_init_;
+    WindowTask w_task_{};
+    const uint8_t* w_R_ = nullptr;
+    std::vector<big::StrandDesc> w_strands_;
+    int w_q0_ = 0, w_q1_ = 0;
     std::vector<small::TaskOut> h_outs_, h_outs_all_;
     std::vector<int64_t> h_task_n_, h_task_m_;
     small::ClassCfg classes_[3];
@@ -306,8 +377,31 @@ private:
 }  // namespace pb200
 
 // =====================================================================================================  C ABI
+namespace {
+// Comm over caller-supplied collectives; synchronises the engine stream before handing device pointers out
+struct CallbackComm : public pb200::Comm {
+    pb200_allgather_cb ag = nullptr; pb200_allreduce_cb ar = nullptr; pb200_bcast_cb bc = nullptr; void* user = nullptr;
+    pb200::CudaEngine* eng = nullptr;
+    void pre(bool device) { if (device && eng) { cudaSetDevice(eng->device()); cudaStreamSynchronize(eng->stream()); } }
+    void allgather(const void* send, void* recv, size_t bytes, bool device) override {
+        pre(device);
+        if (ag(user, send, recv, (int64_t)bytes, device ? 1 : 0) != 0) throw std::runtime_error("allgather callback failed");
+    }
+    void allreduce_i32(int32_t* buf, size_t count, bool is_max, bool device) override {
+        pre(device);
+        if (ar(user, buf, (int64_t)count, is_max ? 1 : 0, device ? 1 : 0) != 0) throw std::runtime_error("allreduce callback failed");
+    }
+    void bcast(void* buf, size_t bytes, int root, bool device) override {
+        pre(device);
+        if (bc(user, buf, (int64_t)bytes, root, device ? 1 : 0) != 0) throw std::runtime_error("bcast callback failed");
+    }
+};
+}  // namespace
+
 struct pb200_genomes {
     std::unique_ptr<pb200::CudaEngine> eng;
+    std::unique_ptr<CallbackComm> comm;
+    bool bcast_index = true;
     int n = 0;
     std::vector<const uint8_t*> seq;
     std::vector<int64_t> len;
@@ -385,7 +479,15 @@ private:
 int pb200_align_resident(pb200_genomes* g, const pb200_params* prm, pb200_result** out) {
     return guarded([&]() {
         if (!g || !prm || !out) { pb200::g_last_error = "bad arguments"; return (int)PB200_ERR_ARG; }
-        ResidentBackend be(g->eng.get());
+        ResidentBackend local(g->eng.get());
+        std::unique_ptr<pb200::ShardedBackend> sharded;
+        pb200::SearchBackend* bep = &local;
+        if (g->comm && g->comm->world > 1) {
+            sharded.reset(new pb200::ShardedBackend(&local, g->eng.get(), g->comm.get(), g->bcast_index));
+            sharded->set_n(g->n);
+            bep = sharded.get();
+        }
+        pb200::SearchBackend& be = *bep;
         pb200::Aligner a(g->n, g->seq.data(), g->len.data(), pb200::to_align_params(prm), &be);
         a.enable_trace(prm->flags & PB200_FLAG_TRACE_WINDOWS);
         a.set_speculate(!(prm->flags & PB200_FLAG_NO_SPECULATION));
@@ -435,8 +537,15 @@ int pb200_debug_index(pb200_genomes* g, int64_t ref_start, int32_t n, int32_t mi
     return guarded([&]() { g->eng->debug_index(ref_start, n, minsize, sa, lrp); return (int)PB200_OK; });
 }
 
-int pb200_comm_unique_id(const char*, uint8_t*) { pb200::g_last_error = "multi-GPU exchange not built yet"; return PB200_ERR_INTERNAL; }
-int pb200_comm_init(pb200_genomes*, const char*, const uint8_t*, int, int) { pb200::g_last_error = "multi-GPU exchange not built yet"; return PB200_ERR_INTERNAL; }
-void pb200_comm_destroy(pb200_genomes*) {}
+int pb200_comm_set(pb200_genomes* g, int rank, int world, pb200_allgather_cb ag, pb200_allreduce_cb ar, pb200_bcast_cb bc, void* user,
+                   int bcast_index) {
+    if (!g || world < 1 || rank < 0 || rank >= world || !ag || !ar || !bc) { pb200::g_last_error = "bad arguments"; return PB200_ERR_ARG; }
+    g->comm.reset(new CallbackComm);
+    g->comm->rank = rank; g->comm->world = world; g->comm->ag = ag; g->comm->ar = ar; g->comm->bc = bc; g->comm->user = user;
+    g->comm->eng = g->eng.get();
+    g->bcast_index = bcast_index != 0;
+    return PB200_OK;
+}
+void pb200_comm_clear(pb200_genomes* g) { if (g) g->comm.reset(); }
 
 }  // extern "C"
