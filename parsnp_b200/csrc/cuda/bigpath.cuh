@@ -57,6 +57,39 @@ __global__ void make_keys_kernel(const uint8_t* __restrict__ R, int n, uint64_t*
     sa[i] = (uint32_t)i;
 }
 
+// N-free windows: 16 bases at 2 bits per base in a 32-bit key (past the end = 0; the prefix doubling orders the few suffixes
+// shorter than 16 correctly because their second key is 0 = "before everything")
+constexpr int KEY2_BASES = 16;
+__global__ void make_keys2_kernel(const uint8_t* __restrict__ R, int n, uint32_t* __restrict__ keys, uint32_t* __restrict__ sa) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t w0 = load8u(R + i), w1 = load8u(R + i + 8);
+    uint32_t key = 0;
+#pragma unroll
+    for (int t = 0; t < KEY2_BASES; ++t) {
+        uint32_t c = (uint32_t)((t < 8 ? (w0 >> (8 * t)) : (w1 >> (8 * (t - 8)))) & 3u);
+        if (i + t >= n) c = 0;
+        key = (key << 2) | c;
+    }
+    keys[i] = key;
+    sa[i] = (uint32_t)i;
+}
+__global__ void kmer_table2_kernel(const uint32_t* __restrict__ keys, int n, int k, uint2* __restrict__ table) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int sh = 2 * (KEY2_BASES - k);
+    uint32_t c = keys[s] >> sh;
+    if (s == 0 || (keys[s - 1] >> sh) != c) table[c].x = (uint32_t)s;
+    if (s == n - 1 || (keys[s + 1] >> sh) != c) table[c].y = (uint32_t)s + 1u;
+}
+__global__ void head_flags2_kernel(const uint32_t* __restrict__ keys, int n, uint32_t* __restrict__ flag, uint32_t* __restrict__ hv) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    uint32_t f = (s == 0 || keys[s] != keys[s - 1]) ? 1u : 0u;
+    flag[s] = f;
+    hv[s] = f ? (uint32_t)s : 0u;
+}
+
 __device__ __forceinline__ bool kmer_of_key(uint64_t key, int k, uint32_t& code) {
     code = 0;
     for (int t = 0; t < k; ++t) {
@@ -77,15 +110,35 @@ __global__ void kmer_table_kernel(const uint64_t* __restrict__ keys, int n, int 
     if (!vp || cp != c) table[c].x = (uint32_t)s;
     if (!vn || cn != c) table[c].y = (uint32_t)s + 1u;       // end slot for now; turned into a count by kmer_table_fix_kernel
 }
-// .y = end - start; buckets of one suffix store the text position itself in .x (saves the SA read in the scan)
-__global__ void kmer_table_fix_kernel(uint2* __restrict__ table, size_t size, const uint32_t* __restrict__ sa_sorted) {
+// .y = end - start.  Buckets of ONE suffix (the common case) store the text position itself in .x (saves the SA read in
+// the scan) and, in .y, bit 31 + a 24-bit signature = the 4 bases before and the 4 bases after the k-mer (3 bits each,
+// 7 = outside the window): a match of >= k+7 bases around the seed must agree with the reference on one of the two
+// sides, so the scan can discard almost every chance k-mer hit without touching the reference text.
+constexpr uint32_t SIG_FLAG = 0x80000000u;
+__device__ __forceinline__ uint32_t side_sig(const uint8_t* __restrict__ T, int len, int pos) {   // 4 bases at pos..pos+3, 7 if outside
+    uint32_t s = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        int p = pos + t;
+        uint32_t c = (p >= 0 && p < len) ? (uint32_t)T[p] : 7u;
+        s = (s << 3) | c;
+    }
+    return s;
+}
+__global__ void kmer_table_fix_kernel(uint2* __restrict__ table, size_t size, const uint32_t* __restrict__ sa_sorted,
+                                      const uint8_t* __restrict__ R, int n, int k) {
     size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= size) return;
     uint2 e = table[c];
     if (e.y == 0) return;
     uint32_t cnt = e.y - e.x;
-    if (cnt == 1) e.x = sa_sorted[e.x];
-    e.y = cnt;
+    if (cnt == 1) {
+        const int l = (int)sa_sorted[e.x];
+        e.x = (uint32_t)l;
+        e.y = SIG_FLAG | (side_sig(R, n, l - 4) << 12) | side_sig(R, n, l + k);
+    } else {
+        e.y = cnt;
+    }
     table[c] = e;
 }
 __global__ void head_flags_kernel(const uint64_t* __restrict__ keys, int n, uint32_t* __restrict__ flag, uint32_t* __restrict__ hv) {
@@ -118,8 +171,9 @@ __global__ void dbl_keys_kernel(const uint32_t* __restrict__ cs, int U, const ui
     if (c >= U) return;
     uint32_t i = sa[cs[c]];
     uint64_t head = rank[i];
-    uint64_t r2 = ((int64_t)i + h < n) ? (uint64_t)rank[i + h] + 1ull : 0ull;
-    keys[c] = (head << nbits) | r2;
+    // second key: rank of the suffix h further on; suffixes that end before that sort first, the shorter one first
+    uint64_t r2 = ((int64_t)i + h < n) ? (uint64_t)rank[i + h] + (uint64_t)n : (uint64_t)(n - 1 - (int64_t)i);
+    keys[c] = (head << (nbits + 1)) | r2;
     vals[c] = i;
 }
 __global__ void dbl_writeback_kernel(const uint32_t* __restrict__ cs, int U, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
@@ -191,8 +245,15 @@ __global__ void __launch_bounds__(128) seed_extend_kernel(const uint8_t* __restr
     int single = -1;                                  // text position when the bucket holds exactly one suffix
     if (plain) {
         const uint2 e = table[code];
-        if (e.y == 1u) { single = (int)e.x; lo = 0; hi = 1; }
-        else { lo = (int)e.x; hi = lo + (int)e.y; }
+        if (e.y & SIG_FLAG) {
+            single = (int)e.x; lo = 0; hi = 1;
+            if (minsize >= k + 7) {
+                // one of the two 4-base flanks must agree (see kmer_table_fix_kernel); flanks outside the query never agree
+                const uint32_t ql = side_sig(Q, m, j - 4), qr = side_sig(Q, m, j + k);
+                const uint32_t rl = (e.y >> 12) & 0xfffu, rr = e.y & 0xfffu;
+                if (ql != rl && qr != rr) return;
+            }
+        } else { lo = (int)e.x; hi = lo + (int)e.y; }
     } else {
         // k-mer with N: binary search the suffix array (rare)
         int a = 0, b = n;
@@ -204,6 +265,7 @@ __global__ void __launch_bounds__(128) seed_extend_kernel(const uint8_t* __restr
     }
     for (int sidx = lo; sidx < hi; ++sidx) {
         const int l = single >= 0 ? single : (int)sa[sidx];
+        if (l + k > n) continue;                      // (2-bit keys: suffixes shorter than k sit in the bucket of their padded key)
         int c = 0;
         const int cmax = min(step, min(j, l));
         // left extension, 8 bytes per compare (the byte just left of the seed is the top byte of the word)
@@ -392,7 +454,7 @@ __global__ void pass2_kernel(const uint32_t* __restrict__ ck, int ncand, const u
 }
 
 // ------------------------------------------------------------------ host driver
-struct WindowIndexInfo { int rounds = 0; int64_t unsorted_after_sort = 0; };
+struct WindowIndexInfo { int rounds = 0; int64_t unsorted_after_sort = 0; bool two_bit = false; };
 
 class BigPath {
 public:
@@ -402,8 +464,9 @@ public:
     // R: device text of the window (codes 0..4), n bases. strands: host array of 2*nq descriptors (device text pointers):
     // strand 2q = forward string of query q's region, 2q+1 = its reverse complement.
     void search(const uint8_t* R, int n, int nq, const std::vector<StrandDesc>& strands, int minsize, cudaStream_t st,
-                std::vector<int32_t>& out_k, std::vector<int32_t>& out_lon, std::vector<int32_t>& out_sp, std::vector<uint8_t>& out_fwd) {
-        build_index(R, n, minsize, st);
+                std::vector<int32_t>& out_k, std::vector<int32_t>& out_lon, std::vector<int32_t>& out_sp, std::vector<uint8_t>& out_fwd,
+                bool two_bit = false) {
+        build_index(R, n, minsize, st, two_bit);
         scan(R, n, nq, strands, minsize, st, out_k, out_lon, out_sp, out_fwd);
     }
 
@@ -411,7 +474,7 @@ public:
     const uint32_t* d_sa() const { return sa_.get(); }
     const int32_t* d_lrp() const { return lrp_.get(); }
 
-    void build_index(const uint8_t* R, int n, int minsize, cudaStream_t st) {
+    void build_index(const uint8_t* R, int n, int minsize, cudaStream_t st, bool two_bit = false) {
         const int TB = 256;
         const unsigned nb = (unsigned)((n + TB - 1) / TB);
         uint64_t* k0 = keys0_.ensure((size_t)n, false, st);
@@ -427,30 +490,53 @@ public:
         int32_t* lrp = lrp_.ensure((size_t)n, false, st);
         uint32_t* d_tot = total_.ensure(4, false, st);
 
-        if (tm) tm->start(GpuTimers::T_INDEX_KEYS, st);
-        pb200::launch(make_keys_kernel, nb, TB, 0, st, R, n, k0, v0);
-        if (tm) tm->stop(GpuTimers::T_INDEX_KEYS, st);
-
-        if (tm) tm->start(GpuTimers::T_INDEX_SORT, st);
-        int res = sorter_.sort<uint64_t, uint32_t>(k0, k1, v0, v1, n, 0, 3 * KEY_BASES, st);
-        const uint64_t* ks = res ? k1 : k0;
-        const uint32_t* vs = res ? v1 : v0;
-        PB_CUDA(cudaMemcpyAsync(sa, vs, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
-        if (tm) tm->stop(GpuTimers::T_INDEX_SORT, st);
-
-        // seed table over the sorted 21-mer keys (buckets are unaffected by the refinement of tied groups)
-        if (tm) tm->start(GpuTimers::T_INDEX_TABLE, st);
         seed_k_ = std::min(MAX_SEED_K, std::max(1, minsize));
         const size_t tsize = (size_t)1 << (2 * seed_k_);
         uint2* table = table_.ensure(tsize, false, st);
-        PB_CUDA(cudaMemsetAsync(table, 0, tsize * sizeof(uint2), st));
-        pb200::launch(kmer_table_kernel, nb, TB, 0, st, ks, n, seed_k_, table);
-        pb200::launch(kmer_table_fix_kernel, (unsigned)((tsize + 255) / 256), 256, 0, st, table, tsize, vs);
-        if (tm) tm->stop(GpuTimers::T_INDEX_TABLE, st);
-
-        // prefix doubling on the groups the 21-mer sort left tied
-        if (tm) tm->start(GpuTimers::T_INDEX_DOUBLING, st);
-        pb200::launch(head_flags_kernel, nb, TB, 0, st, ks, n, tA /*flag*/, tB /*hv*/);
+        int64_t h0;
+        last_index.two_bit = two_bit;
+        if (two_bit) {
+            // N-free window: 32-bit keys of 16 bases, 4 one-sweep passes over (4 B key + 4 B value)
+            uint32_t* q0 = reinterpret_cast<uint32_t*>(k0);
+            uint32_t* q1 = reinterpret_cast<uint32_t*>(k1);
+            if (tm) tm->start(GpuTimers::T_INDEX_KEYS, st);
+            pb200::launch(make_keys2_kernel, nb, TB, 0, st, R, n, q0, v0);
+            if (tm) tm->stop(GpuTimers::T_INDEX_KEYS, st);
+            if (tm) tm->start(GpuTimers::T_INDEX_SORT, st);
+            int res = sorter_.sort<uint32_t, uint32_t>(q0, q1, v0, v1, n, 0, 2 * KEY2_BASES, st);
+            const uint32_t* ks = res ? q1 : q0;
+            const uint32_t* vs = res ? v1 : v0;
+            PB_CUDA(cudaMemcpyAsync(sa, vs, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+            if (tm) tm->stop(GpuTimers::T_INDEX_SORT, st);
+            if (tm) tm->start(GpuTimers::T_INDEX_TABLE, st);
+            PB_CUDA(cudaMemsetAsync(table, 0, tsize * sizeof(uint2), st));
+            pb200::launch(kmer_table2_kernel, nb, TB, 0, st, ks, n, seed_k_, table);
+            pb200::launch(kmer_table_fix_kernel, (unsigned)((tsize + 255) / 256), 256, 0, st, table, tsize, vs, R, n, seed_k_);
+            if (tm) tm->stop(GpuTimers::T_INDEX_TABLE, st);
+            if (tm) tm->start(GpuTimers::T_INDEX_DOUBLING, st);
+            pb200::launch(head_flags2_kernel, nb, TB, 0, st, ks, n, tA /*flag*/, tB /*hv*/);
+            h0 = KEY2_BASES;
+        } else {
+            if (tm) tm->start(GpuTimers::T_INDEX_KEYS, st);
+            pb200::launch(make_keys_kernel, nb, TB, 0, st, R, n, k0, v0);
+            if (tm) tm->stop(GpuTimers::T_INDEX_KEYS, st);
+            if (tm) tm->start(GpuTimers::T_INDEX_SORT, st);
+            int res = sorter_.sort<uint64_t, uint32_t>(k0, k1, v0, v1, n, 0, 3 * KEY_BASES, st);
+            const uint64_t* ks = res ? k1 : k0;
+            const uint32_t* vs = res ? v1 : v0;
+            PB_CUDA(cudaMemcpyAsync(sa, vs, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+            if (tm) tm->stop(GpuTimers::T_INDEX_SORT, st);
+            // seed table over the sorted 21-mer keys (buckets are unaffected by the refinement of tied groups)
+            if (tm) tm->start(GpuTimers::T_INDEX_TABLE, st);
+            PB_CUDA(cudaMemsetAsync(table, 0, tsize * sizeof(uint2), st));
+            pb200::launch(kmer_table_kernel, nb, TB, 0, st, ks, n, seed_k_, table);
+            pb200::launch(kmer_table_fix_kernel, (unsigned)((tsize + 255) / 256), 256, 0, st, table, tsize, vs, R, n, seed_k_);
+            if (tm) tm->stop(GpuTimers::T_INDEX_TABLE, st);
+            // prefix doubling on the groups the 21-mer sort left tied
+            if (tm) tm->start(GpuTimers::T_INDEX_DOUBLING, st);
+            pb200::launch(head_flags_kernel, nb, TB, 0, st, ks, n, tA /*flag*/, tB /*hv*/);
+            h0 = KEY_BASES;
+        }
         scanner_.scan<prim::OpMax, false>(tB, tB, n, nullptr, st);                 // tB = head index per SA slot
         pb200::launch(rank_scatter_kernel, nb, TB, 0, st, sa, tB, n, rank);
         pb200::launch(mark_unsorted_kernel, nb, TB, 0, st, tA, n, tC /*u*/);
@@ -466,11 +552,11 @@ public:
             pb200::launch(compact_kernel, nb, TB, 0, st, tC, tB, n, nullptr, cs);
             int nbits = 1;
             while (((int64_t)1 << nbits) < (int64_t)n + 1) ++nbits;
-            int64_t h = KEY_BASES;
+            int64_t h = h0;
             while (U > 0) {
                 const unsigned ub = (unsigned)((U + TB - 1) / TB);
                 pb200::launch(dbl_keys_kernel, ub, TB, 0, st, cs, (int)U, sa, rank, n, (int)std::min<int64_t>(h, n), nbits, k0, v0);
-                int r2 = sorter_.sort<uint64_t, uint32_t>(k0, k1, v0, v1, U, 0, 2 * nbits, st);
+                int r2 = sorter_.sort<uint64_t, uint32_t>(k0, k1, v0, v1, U, 0, 2 * nbits + 1, st);
                 const uint64_t* k2 = r2 ? k1 : k0;
                 const uint32_t* v2 = r2 ? v1 : v0;
                 pb200::launch(dbl_writeback_kernel, ub, TB, 0, st, cs, (int)U, k2, v2, sa, tA /*cflag*/, tB /*hv*/);

@@ -64,6 +64,8 @@ public:
         big_.tm = &timers;
         const char* fp = getenv("PB200_FORCE_PATH");      // tests: "big" routes every window through the large-window path
         force_big_ = (fp && std::string(fp) == "big") ? 1 : 0;
+        const char* fk = getenv("PB200_FORCE_3BIT_KEYS");  // tests: always use the 21-mer 3-bit key path
+        force_3bit_ = fk && fk[0] == '1';
         // {n_cap, m_cap, event store capacity (all strands), candidate capacity, threads}
         classes_[0] = small::ClassCfg{256, 512, 512, 64, 128};
         classes_[1] = small::ClassCfg{1024, 2048, 2048, 256, 256};
@@ -100,6 +102,12 @@ public:
         }
         h2d_bytes_ = 0;
         for (int i = 0; i < n; ++i) h2d_bytes_ += len[i];
+        // positions of non-ACGT symbols in the reference (N is an ordinary symbol; windows without any take the 2-bit key path)
+        ref_n_pos_.clear();
+        for (int64_t i = 0; i < len[0]; ++i) {
+            const uint8_t c = seq[0][i];
+            if (c != 'A' && c != 'C' && c != 'G' && c != 'T') ref_n_pos_.push_back(i);
+        }
         int64_t* d = gmeta_.ensure((size_t)3 * n, false, st_);
         std::vector<int64_t> meta(3 * (size_t)n);
         for (int i = 0; i < n; ++i) { meta[i] = gfwd_[i]; meta[n + i] = grc_[i]; meta[2 * n + i] = len_[i]; }
@@ -193,7 +201,7 @@ public:
             w_strands_[2 * q] = big::StrandDesc{text_.get() + gfwd_[g] + qs[q], (int32_t)ql[q], 0};
             w_strands_[2 * q + 1] = big::StrandDesc{text_.get() + grc_[g] + (len_[g] - qs[q] - ql[q]), (int32_t)ql[q], 0};
         }
-        if (build_index) big_.build_index(w_R_, (int)t.ref_len, t.minsize, st_);
+        if (build_index) big_.build_index(w_R_, (int)t.ref_len, t.minsize, st_, window_is_n_free(t.ref_start, t.ref_len));
         else big_.alloc_index((int)t.ref_len, t.minsize, st_);
         PB_CUDA(cudaStreamSynchronize(st_));
         big_windows++;
@@ -228,13 +236,17 @@ public:
     // test hooks: suffix array + lrp of a window of genome 0
     void debug_index(int64_t ref_start, int n, int minsize, uint32_t* sa, int32_t* lrp) {
         PB_CUDA(cudaSetDevice(device_));
-        big_.build_index(text_.get() + gfwd_[0] + ref_start, n, minsize, st_);
+        big_.build_index(text_.get() + gfwd_[0] + ref_start, n, minsize, st_, window_is_n_free(ref_start, n));
         PB_CUDA(cudaMemcpyAsync(sa, big_.d_sa(), (size_t)n * 4, cudaMemcpyDeviceToHost, st_));
         PB_CUDA(cudaMemcpyAsync(lrp, big_.d_lrp(), (size_t)n * 4, cudaMemcpyDeviceToHost, st_));
         PB_CUDA(cudaStreamSynchronize(st_));
     }
     void set_force_class(int c) { force_big_ = c; }
     void collect_timers() { cudaSetDevice(device_); timers.collect(st_); }
+    bool window_is_n_free(int64_t start, int64_t len) const {
+        auto it = std::lower_bound(ref_n_pos_.begin(), ref_n_pos_.end(), start);
+        return (it == ref_n_pos_.end() || *it >= start + len) && !force_3bit_;
+    }
     int n() const { return n_; }
     int device() const { return device_; }
     int64_t h2d_bytes() const { return h2d_bytes_; }
@@ -342,7 +354,8 @@ private:
             sd[2 * q + 1].m = (int32_t)ql[q];
             sd[2 * q + 1].pad = 0;
         }
-        big_.search(text_.get() + gfwd_[0] + t.ref_start, (int)t.ref_len, nq, sd, t.minsize, st_, bg_k_, bg_lon_, bg_sp_, bg_fwd_);
+        big_.search(text_.get() + gfwd_[0] + t.ref_start, (int)t.ref_len, nq, sd, t.minsize, st_, bg_k_, bg_lon_, bg_sp_, bg_fwd_,
+                    window_is_n_free(t.ref_start, t.ref_len));
         big_windows++;
         big_ref_bases += t.ref_len;
         for (int q = 0; q < nq; ++q) big_query_bases += ql[q];
@@ -351,6 +364,8 @@ private:
     }
 
     int device_ = 0, n_ = 0, sm_count_ = 148, force_big_ = 0;
+    bool force_3bit_ = false;
+    std::vector<int64_t> ref_n_pos_;
     cudaStream_t st_ = nullptr;
     std::vector<int64_t> len_, gfwd_, grc_;
     int64_t h2d_bytes_ = 0;

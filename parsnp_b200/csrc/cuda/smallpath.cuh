@@ -32,7 +32,7 @@ struct ClassCfg {
     __host__ __device__ static size_t al(size_t x) { return (x + 15) & ~(size_t)15; }
     // ev_cap = capacity of the event store for ALL strands of ALL queries of the window
     __host__ __device__ size_t smem_bytes(int nq) const {
-        return al(n_cap) + 2 * al(m_cap) + 4 * al(2 * (size_t)n_cap) + al((size_t)ev_cap * sizeof(Ev)) + al(2 * (size_t)(2 * nq + 2)) +
+        return al(n_cap) + 2 * al(m_cap) + 2 * al(2 * (size_t)m_cap) + 4 * al(2 * (size_t)n_cap) + al((size_t)ev_cap * sizeof(Ev)) + al(2 * (size_t)(2 * nq + 2)) +
                2 * al(2 * (size_t)cand_cap) + 64;
     }
 };
@@ -79,33 +79,33 @@ constexpr int SEED_K = 4;
 __device__ __forceinline__ uint32_t pack4(const uint8_t* p) {
     return (uint32_t)p[0] | ((uint32_t)p[1] << 3) | ((uint32_t)p[2] << 6) | ((uint32_t)p[3] << 9);
 }
+__device__ __forceinline__ void seed_hit(const uint8_t* __restrict__ R, int n, const uint8_t* __restrict__ Q, int m, int j, int l, int step,
+                                         int minsize, int strand, Ev* __restrict__ ev, int* __restrict__ ev_n, int ev_cap) {
+    const int cmax = min(step, min(j, l));
+    int c = 0;
+    while (c < cmax && Q[j - 1 - c] == R[l - 1 - c]) ++c;
+    if (c >= step) return;                        // the previous seed row lies in the same match
+    const int emax = min(m - j, n - l);
+    const int e = SEED_K + smatch_fwd(Q + j + SEED_K, R + l + SEED_K, emax - SEED_K);
+    const int L = c + e, l0 = l - c;
+    if (L < minsize) return;
+    int slot = atomicAdd(ev_n, 1);
+    if (slot < ev_cap) {
+        ev[slot].l = (uint16_t)l0; ev[slot].e = (uint16_t)(l0 + L); ev[slot].u = 0; ev[slot].pad = (uint16_t)(strand << 1);
+        ev[slot].d1 = (j - c) - l0;
+    }
+}
+// Q4f/Q4c: packed seed codes of the sampled query rows (filled by the caller, one row per thread)
 __device__ inline void find_events(const uint8_t* __restrict__ R, const uint16_t* __restrict__ R4, int n,
                                    const uint8_t* __restrict__ Qf, const uint8_t* __restrict__ Qc, int m,
+                                   const uint16_t* __restrict__ Q4f, const uint16_t* __restrict__ Q4c, int nrows, int step,
                                    int minsize, Ev* __restrict__ ev, int* __restrict__ ev_n, int ev_cap, int nthreads) {
-    const int step = max(1, minsize - SEED_K + 1);
-    for (int j = 0; j + SEED_K <= m; j += step) {
-        const uint32_t qf = pack4(Qf + j), qc = pack4(Qc + j);
-        for (int l = threadIdx.x; l + SEED_K <= n; l += nthreads) {
-            const uint32_t r4 = R4[l];
-            if (r4 != qf && r4 != qc) continue;
-#pragma unroll 1
-            for (int strand = 0; strand < 2; ++strand) {
-                if (r4 != (strand ? qc : qf)) continue;
-                const uint8_t* __restrict__ Q = strand ? Qc : Qf;
-                const int cmax = min(step, min(j, l));
-                int c = 0;
-                while (c < cmax && Q[j - 1 - c] == R[l - 1 - c]) ++c;
-                if (c >= step) continue;              // the previous seed row lies in the same match
-                const int emax = min(m - j, n - l);
-                const int e = SEED_K + smatch_fwd(Q + j + SEED_K, R + l + SEED_K, emax - SEED_K);
-                const int L = c + e, l0 = l - c;
-                if (L < minsize) continue;
-                int slot = atomicAdd(ev_n, 1);
-                if (slot < ev_cap) {
-                    ev[slot].l = (uint16_t)l0; ev[slot].e = (uint16_t)(l0 + L); ev[slot].u = 0; ev[slot].pad = (uint16_t)(strand << 1);
-                    ev[slot].d1 = (j - c) - l0;
-                }
-            }
+    for (int l = threadIdx.x; l + SEED_K <= n; l += nthreads) {
+        const uint32_t r4 = R4[l];
+        for (int row = 0; row < nrows; ++row) {
+            const uint32_t qf = Q4f[row], qc = Q4c[row];       // same address for the whole warp: broadcast
+            if (r4 == qf) seed_hit(R, n, Qf, m, row * step, l, step, minsize, 0, ev, ev_n, ev_cap);
+            if (r4 == qc) seed_hit(R, n, Qc, m, row * step, l, step, minsize, 1, ev, ev_n, ev_cap);
         }
     }
 }
@@ -176,6 +176,8 @@ __global__ void __launch_bounds__(SM_MAX_THREADS, 6) small_region_kernel(
     uint8_t* Qc = smem + off; off += ClassCfg::al(cfg.m_cap);
     uint16_t* lrp = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
     uint16_t* R4 = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
+    uint16_t* Q4f = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.m_cap);
+    uint16_t* Q4c = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.m_cap);
     uint16_t* MUP = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
     uint16_t* MEP = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
     Ev* evs = reinterpret_cast<Ev*>(smem + off); off += ClassCfg::al((size_t)cfg.ev_cap * sizeof(Ev));
@@ -195,6 +197,7 @@ __global__ void __launch_bounds__(SM_MAX_THREADS, 6) small_region_kernel(
 
     // pass 0: fold all queries (ini order) into Master, keeping every query's events in shared memory
     int e0 = 0;
+    const int step = max(1, minsize - SEED_K + 1);
     for (int q = 0; q < nq; ++q) {
         const int m = ql[q];
         const int64_t g = q + 1;
@@ -202,7 +205,10 @@ __global__ void __launch_bounds__(SM_MAX_THREADS, 6) small_region_kernel(
         const int64_t c_off = gbase_rc[g] + (glen[g] - qs[q] - m);
         for (int i = tid; i < m; i += T) { Qf[i] = text[f_off + i]; Qc[i] = text[c_off + i]; }
         __syncthreads();
-        find_events(R, R4, n, Qf, Qc, m, minsize, evs, &s_int[0], cfg.ev_cap, T);
+        const int nrows = m >= SEED_K ? (m - SEED_K) / step + 1 : 0;
+        for (int row = tid; row < nrows; row += T) { Q4f[row] = (uint16_t)pack4(Qf + row * step); Q4c[row] = (uint16_t)pack4(Qc + row * step); }
+        __syncthreads();
+        find_events(R, R4, n, Qf, Qc, m, Q4f, Q4c, nrows, step, minsize, evs, &s_int[0], cfg.ev_cap, T);
         __syncthreads();
         const int e2 = s_int[0];
         if (e2 > cfg.ev_cap) { if (tid == 0) s_int[3] = 1; __syncthreads(); break; }

@@ -83,13 +83,24 @@ def _texts():
     out["tiny"] = np.frombuffer(b"ACGTACGGTTACGTAACCGGTAC", np.uint8)
     out["tandem"] = np.tile(np.frombuffer(b"ACGTTGCA", np.uint8), 700)
     out["random_200k"] = A[rng.integers(0, 4, 200000)]
+    out["ends_in_A"] = np.concatenate([A[rng.integers(0, 4, 3000)], np.full(23, ord("A"), np.uint8)])
+    out["all_A"] = np.full(700, ord("A"), np.uint8)
+    out["short"] = np.frombuffer(b"ACGTA", np.uint8)
     return out
 
 
-@pytest.mark.parametrize("name", ["tiny", "random_5k", "repeats_30k", "tandem", "random_200k"])
-def test_suffix_index_matches_cpu(name):
+@pytest.mark.parametrize("three_bit", [False, True])
+@pytest.mark.parametrize("name", ["tiny", "random_5k", "repeats_30k", "tandem", "random_200k", "ends_in_A", "all_A", "short"])
+def test_suffix_index_matches_cpu(name, three_bit):
+    """suffix array + longest-repeated-prefix; N-free windows take the 16-mer 2-bit key path unless forced to the 21-mer
+    3-bit one - both must give the true suffix order (window end sorts first)"""
     text = np.ascontiguousarray(_texts()[name])
-    G = api.Genomes([text, text[: max(10, len(text) // 2)].copy()])
+    if three_bit:
+        os.environ["PB200_FORCE_3BIT_KEYS"] = "1"
+    try:
+        G = api.Genomes([text, text[: max(3, len(text) // 2)].copy()])
+    finally:
+        os.environ.pop("PB200_FORCE_3BIT_KEYS", None)
     sa, lrp = _debug_index(G, len(text))
     wsa, wlrp = cpu_sa_lrp(text)
     assert np.array_equal(sa, wsa)
