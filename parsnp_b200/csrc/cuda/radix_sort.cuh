@@ -1,10 +1,15 @@
-// LSD radix sort (8-bit digits) of (key, value) pairs, one-sweep style: one global histogram kernel for all passes,
-// then per pass ONE kernel that ranks a 2048-key tile in shared memory (warp match_any multisplit), resolves the
-// tile's global digit offsets with a decoupled look-back over single-word (flag|count) tile states, stages the tile
-// sorted by digit in shared memory and writes each digit run out contiguously (coalesced).
-// Algorithmic HBM traffic per pass: read key+value, write key+value (+ one extra key read for the histograms).
+// LSD radix sort (8-bit digits) of (key, value) pairs.  Per pass three kernels, none of which waits on another block:
+//   tile_hist_kernel   per-tile digit histogram (reads the keys once)                      -> counts[digit][tile]
+//   digit_scan_kernel  one block per digit: exclusive scan over the tiles + global digit offset (in place)
+//   scatter_kernel     ranks a 2048-key tile in shared memory (warp match_any multisplit), stages the tile sorted by
+//                      digit in shared memory and writes each digit run out contiguously (coalesced)
+// plus one hist_kernel/scan_hist_kernel pair up front for the global digit offsets of all passes.
+// (A one-sweep variant with decoupled look-back was measured first: with ~600 resident tiles every tile walks hundreds of
+//  predecessor states and the pass time stayed at ~75 us whatever the record size - profiles/r01_*; the split form moves
+//  8 (4) more bytes per key and pass but has no cross-block dependency.)
+// HBM traffic per pass: keys read twice, values once, both written once.
 //
-// Used for: the suffix-array build (64-bit packed 21-mer keys, prefix-doubling keys) and the (strand, ref start)
+// Used for: the suffix-array build (packed 16-mer / 21-mer keys, prefix-doubling keys) and the (strand, ref start)
 // ordering of MEM events.  No reference counterpart (the reference builds a suffix graph online, src/csgmum/csg.c).
 #pragma once
 #include "util.cuh"
@@ -16,8 +21,6 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ITEMS = 8;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;   // 2048 keys per tile: ~64 registers, 32 KB smem -> 5-6 CTAs per SM
-constexpr uint32_t ST_AGG = 1u << 30;
-constexpr uint32_t ST_INCL = 2u << 30;
 constexpr uint32_t ST_MASK = (1u << 30) - 1;
 
 template <class K>
@@ -54,26 +57,61 @@ __global__ void __launch_bounds__(256) scan_hist_kernel(const uint32_t* __restri
     gofs[p * 256 + d] = base + x - v;
 }
 
+template <class K>
+__global__ void __launch_bounds__(RS_THREADS) tile_hist_kernel(const K* __restrict__ kin, int64_t n, int shift, int bits,
+                                                               uint32_t* __restrict__ counts, int64_t tiles) {
+    __shared__ uint32_t h[256];
+    const int tid = threadIdx.x;
+    h[tid] = 0;
+    __syncthreads();
+    const int64_t tile_base = (int64_t)blockIdx.x * RS_TILE;
+    const uint32_t mask = (1u << bits) - 1;
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        int64_t i = tile_base + r * RS_THREADS + tid;
+        if (i < n) atomicAdd(&h[(uint32_t)(kin[i] >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    counts[(int64_t)tid * tiles + blockIdx.x] = h[tid];
+}
+
+// block d: counts[d][0..tiles) -> exclusive prefix + gofs[d]
+__global__ void __launch_bounds__(256) digit_scan_kernel(uint32_t* __restrict__ counts, int64_t tiles, const uint32_t* __restrict__ gofs) {
+    __shared__ uint32_t s_w[8];
+    uint32_t* row = counts + (int64_t)blockIdx.x * tiles;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t carry = gofs[blockIdx.x];
+    for (int64_t b = 0; b < tiles; b += 256) {
+        int64_t i = b + threadIdx.x;
+        uint32_t v = i < tiles ? row[i] : 0u;
+        uint32_t x = v;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_w[w] = x;
+        __syncthreads();
+        uint32_t base = 0, tot = 0;
+        for (int q = 0; q < 8; ++q) { if (q < w) base += s_w[q]; tot += s_w[q]; }
+        if (i < tiles) row[i] = carry + base + x - v;
+        carry += tot;
+        __syncthreads();
+    }
+}
+
 template <class K, class V>
-__global__ void __launch_bounds__(RS_THREADS, 4) onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout,
-                                                              const V* __restrict__ vin, V* __restrict__ vout, int64_t n, int shift,
-                                                              int bits, const uint32_t* __restrict__ gofs,
-                                                              volatile uint32_t* status, uint32_t* tile_counter) {
+__global__ void __launch_bounds__(RS_THREADS, 4) scatter_kernel(const K* __restrict__ kin, K* __restrict__ kout,
+                                                                const V* __restrict__ vin, V* __restrict__ vout, int64_t n, int shift,
+                                                                int bits, const uint32_t* __restrict__ offsets, int64_t tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     K* s_keys = reinterpret_cast<K*>(smem_raw);                                  // RS_TILE
     V* s_vals = reinterpret_cast<V*>(smem_raw + sizeof(K) * RS_TILE);            // RS_TILE
     uint32_t* s_whist = reinterpret_cast<uint32_t*>(smem_raw + (sizeof(K) + sizeof(V)) * RS_TILE);   // [RS_WARPS][256]
     uint32_t* s_base = s_whist + RS_WARPS * 256;                                  // [256] global base - local start
     uint32_t* s_dstart = s_base + 256;                                            // [256] local start of digit run
-    __shared__ int s_tile;
     __shared__ uint32_t s_wsum[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t mask = (1u << bits) - 1;
-    if (tid == 0) s_tile = (int)atomicAdd(tile_counter, 1u);
     for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) s_whist[i] = 0;
-    __syncthreads();
-    const int tile = s_tile;
-    const int64_t tile_base = (int64_t)tile * RS_TILE;
+    const int64_t tile = blockIdx.x;
+    const int64_t tile_base = tile * RS_TILE;
     const int64_t wbase = tile_base + (int64_t)warp * (RS_ITEMS * 32);
     K key[RS_ITEMS];
     V val[RS_ITEMS];
@@ -84,6 +122,8 @@ __global__ void __launch_bounds__(RS_THREADS, 4) onesweep_kernel(const K* __rest
         if (i < n) { key[r] = kin[i]; val[r] = vin[i]; }
         else { key[r] = (K)0; val[r] = (V)0; }
     }
+    const uint32_t my_off = offsets[(int64_t)tid * tiles + tile];      // global start of digit `tid` for this tile
+    __syncthreads();
     uint32_t* mywh = s_whist + warp * 256;
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
@@ -100,48 +140,20 @@ __global__ void __launch_bounds__(RS_THREADS, 4) onesweep_kernel(const K* __rest
         __syncwarp();
     }
     __syncthreads();
-    // thread d owns digit d: offsets of each warp inside the digit run, tile count, look-back
     {
         const int d = tid;
         uint32_t tot = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) { uint32_t c = s_whist[w * 256 + d]; s_whist[w * 256 + d] = tot; tot += c; }
-        // local exclusive scan over digits -> start of the digit run inside the staged tile
         uint32_t x = tot;
         for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
         if (lane == 31) s_wsum[warp] = x;
-        // publish / look back while the other warps finish their scans
-        uint32_t excl = 0;
-        if (tile == 0) {
-            status[(int64_t)tile * 256 + d] = tot | ST_INCL;
-        } else {
-            status[(int64_t)tile * 256 + d] = tot | ST_AGG;
-            // look back over the predecessor tiles, 8 status words in flight per step (the first wave of resident tiles has
-            // to walk back hundreds of tiles; one dependent L2 round trip per tile would serialise the whole pass)
-            int t = tile - 1;
-            bool done = false;
-            while (!done) {
-                uint32_t v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) { v[u] = 2u << 30; if (t - u >= 0) v[u] = status[(int64_t)(t - u) * 256 + d]; }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    if (done) break;
-                    const uint32_t f = v[u] & ~ST_MASK;
-                    if (f == 0) break;                   // predecessor not published yet: re-read from here
-                    excl += v[u] & ST_MASK;
-                    --t;
-                    if (f == ST_INCL) done = true;
-                }
-            }
-            status[(int64_t)tile * 256 + d] = (excl + tot) | ST_INCL;
-        }
         __syncthreads();
         uint32_t wb = 0;
         for (int i = 0; i < warp; ++i) wb += s_wsum[i];
         uint32_t dstart = wb + x - tot;
         s_dstart[d] = dstart;
-        s_base[d] = gofs[d] + excl - dstart;      // global position = s_base[digit] + local position (mod 2^32)
+        s_base[d] = my_off - dstart;              // global position = s_base[digit] + local position (mod 2^32)
     }
     __syncthreads();
 #pragma unroll
@@ -175,13 +187,12 @@ public:
         if (n > (int64_t)ST_MASK) throw CudaError("radix sort: n too large");
         const int npass = (end_bit - begin_bit + 7) / 8;
         const int64_t tiles = (n + RS_TILE - 1) / RS_TILE;
-        const size_t words = (size_t)npass * 256 * 2 + (size_t)npass + (size_t)npass * tiles * 256;
+        const size_t words = (size_t)npass * 256 * 2 + (size_t)256 * tiles;
         uint32_t* tmp = tmp_.ensure(words, false, st);
-        PB_CUDA(cudaMemsetAsync(tmp, 0, words * sizeof(uint32_t), st));
+        PB_CUDA(cudaMemsetAsync(tmp, 0, (size_t)npass * 256 * 2 * sizeof(uint32_t), st));
         uint32_t* ghist = tmp;
         uint32_t* gofs = tmp + (size_t)npass * 256;
-        uint32_t* counters = gofs + (size_t)npass * 256;
-        uint32_t* status = counters + npass;
+        uint32_t* counts = gofs + (size_t)npass * 256;
         int hb = (int)std::min<int64_t>((n + 256 * 16 - 1) / (256 * 16), 148 * 8);
         pb200::launch(hist_kernel<K>, hb, 256, 0, st, k0, n, begin_bit, end_bit, npass, ghist);
         pb200::launch(scan_hist_kernel, npass, 256, 0, st, ghist, gofs);
@@ -189,7 +200,7 @@ public:
         static bool attr_set[2][2] = {{false, false}, {false, false}};
         bool& a = attr_set[sizeof(K) == 8][sizeof(V) == 8];
         if (!a) {
-            PB_CUDA(cudaFuncSetAttribute(onesweep_kernel<K, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PB_CUDA(cudaFuncSetAttribute(scatter_kernel<K, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             a = true;
         }
         K* kin = k0; K* kout = k1; V* vin = v0; V* vout = v1;
@@ -197,8 +208,9 @@ public:
         for (int p = 0; p < npass; ++p) {
             int shift = begin_bit + 8 * p;
             int bits = std::min(8, end_bit - shift);
-            pb200::launch(onesweep_kernel<K, V>, (unsigned)tiles, RS_THREADS, smem, st, kin, kout, vin, vout, n, shift, bits, gofs + (size_t)p * 256,
-                                                                            status + (size_t)p * tiles * 256, counters + p);
+            pb200::launch(tile_hist_kernel<K>, (unsigned)tiles, RS_THREADS, 0, st, kin, n, shift, bits, counts, tiles);
+            pb200::launch(digit_scan_kernel, 256, 256, 0, st, counts, tiles, gofs + (size_t)p * 256);
+            pb200::launch(scatter_kernel<K, V>, (unsigned)tiles, RS_THREADS, smem, st, kin, kout, vin, vout, n, shift, bits, counts, tiles);
             std::swap(kin, kout);
             std::swap(vin, vout);
             res ^= 1;
