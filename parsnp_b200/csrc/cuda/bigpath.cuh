@@ -35,6 +35,18 @@ __device__ __forceinline__ uint64_t load8u(const uint8_t* p) {
 // number of equal leading bytes of a[0..limit) and b[0..limit)
 __device__ __forceinline__ int match_len(const uint8_t* a, const uint8_t* b, int limit) {
     int t = 0;
+    // long matches: 4 independent 8-byte compares per step, so a 100-base extension is ~4 dependent round trips, not 13
+    while (t + 32 <= limit) {
+        uint64_t x0 = load8u(a + t) ^ load8u(b + t), x1 = load8u(a + t + 8) ^ load8u(b + t + 8);
+        uint64_t x2 = load8u(a + t + 16) ^ load8u(b + t + 16), x3 = load8u(a + t + 24) ^ load8u(b + t + 24);
+        if (x0 | x1 | x2 | x3) {
+            if (x0) return t + ((__ffsll((long long)x0) - 1) >> 3);
+            if (x1) return t + 8 + ((__ffsll((long long)x1) - 1) >> 3);
+            if (x2) return t + 16 + ((__ffsll((long long)x2) - 1) >> 3);
+            return t + 24 + ((__ffsll((long long)x3) - 1) >> 3);
+        }
+        t += 32;
+    }
     while (t < limit) {
         uint64_t x = load8u(a + t) ^ load8u(b + t);
         if (x) { t += (__ffsll((long long)x) - 1) >> 3; break; }
@@ -320,7 +332,8 @@ __device__ __forceinline__ St st_shfl_up(const St& s, int o) {
     r.d1 = __shfl_up_sync(0xffffffffu, s.d1, o);
     return r;
 }
-// one block per strand: inclusive scan of the strand's events (sorted by l)
+// one block per strand: inclusive scan of the strand's events (sorted by l); 8 consecutive events per thread
+constexpr int ES_ITEMS = 8;
 __global__ void __launch_bounds__(256) event_scan_kernel(const uint32_t* __restrict__ evl, const uint64_t* __restrict__ ev_val,
                                                          const int32_t* __restrict__ lrp, const uint32_t* __restrict__ seg_lo,
                                                          const uint32_t* __restrict__ seg_hi, int4* __restrict__ states) {
@@ -329,17 +342,26 @@ __global__ void __launch_bounds__(256) event_scan_kernel(const uint32_t* __restr
     const int lo = (int)seg_lo[strand], hi = (int)seg_hi[strand];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     St carry = {0, 0, 0, 0};
-    for (int base = lo; base < hi; base += 256) {
-        int i = base + threadIdx.x;
+    for (int base = lo; base < hi; base += 256 * ES_ITEMS) {
+        const int i0 = base + threadIdx.x * ES_ITEMS;
+        St v[ES_ITEMS];
         St x = {0, 0, 0, 0};
-        if (i < hi) {
-            int l = (int)evl[i];
-            uint64_t v = ev_val[i];
-            x.fl = l + lrp[l];
-            x.t1 = (int)(uint32_t)(v >> 32);
-            x.t2 = 0;
-            x.d1 = (int)(uint32_t)v - l;
+#pragma unroll
+        for (int r = 0; r < ES_ITEMS; ++r) {
+            const int i = i0 + r;
+            St e = {0, 0, 0, 0};
+            if (i < hi) {
+                int l = (int)evl[i];
+                uint64_t val = ev_val[i];
+                e.fl = l + lrp[l];
+                e.t1 = (int)(uint32_t)(val >> 32);
+                e.t2 = 0;
+                e.d1 = (int)(uint32_t)val - l;
+            }
+            x = st_combine(x, e);
+            v[r] = x;                                   // thread-local inclusive prefix
         }
+        St tot_thread = x;
         for (int o = 1; o < 32; o <<= 1) { St y = st_shfl_up(x, o); if (lane >= o) x = st_combine(y, x); }
         if (lane == 31) s_w[w] = x;
         __syncthreads();
@@ -347,8 +369,15 @@ __global__ void __launch_bounds__(256) event_scan_kernel(const uint32_t* __restr
         for (int q = 0; q < w; ++q) pre = st_combine(pre, s_w[q]);
         St tot = carry;
         for (int q = 0; q < 8; ++q) tot = st_combine(tot, s_w[q]);
-        x = st_combine(pre, x);
-        if (i < hi) states[i] = make_int4(x.fl, x.t1, x.t2, x.d1);
+        // exclusive prefix of this thread = pre (+) inclusive warp scan of the previous lane
+        St prev = st_shfl_up(x, 1);
+        if (lane > 0) pre = st_combine(pre, prev);
+        (void)tot_thread;
+#pragma unroll
+        for (int r = 0; r < ES_ITEMS; ++r) {
+            const int i = i0 + r;
+            if (i < hi) { St o = st_combine(pre, v[r]); states[i] = make_int4(o.fl, o.t1, o.t2, o.d1); }
+        }
         carry = tot;
         __syncthreads();
     }
@@ -431,24 +460,33 @@ __global__ void emit_flags_kernel(const int32_t* __restrict__ MUP, const int32_t
     flag[k] = (ep > prev && MUP[k] < ep && ep - k >= minsize) ? 1u : 0u;
 }
 
-// per candidate: replay the fold at position k to recover every query's strand and start (SP)
-__global__ void pass2_kernel(const uint32_t* __restrict__ ck, int ncand, const uint32_t* __restrict__ evl, const int4* __restrict__ states,
-                             const uint32_t* __restrict__ seg_lo, const uint32_t* __restrict__ seg_hi, int nq, int n,
-                             const int32_t* __restrict__ MEP, const int32_t* __restrict__ initEP, int32_t* __restrict__ out_lon,
-                             int32_t* __restrict__ out_sp, uint8_t* __restrict__ out_fwd) {
+// per (candidate, local query): the two strands' (EP, diagonal) at the candidate position
+__global__ void pass2a_kernel(const uint32_t* __restrict__ ck, int ncand, const uint32_t* __restrict__ evl, const int4* __restrict__ states,
+                              const uint32_t* __restrict__ seg_lo, const uint32_t* __restrict__ seg_hi, int nq, int4* __restrict__ tmp) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)ncand * nq) return;
+    const int c = (int)(idx / nq), q = (int)(idx % nq);
+    const uint32_t k = ck[c];
+    int UPf, EPf, df, UPc, EPc, dc;
+    int lo = (int)seg_lo[2 * q], hi = (int)seg_hi[2 * q];
+    strand_at(evl, states, lo, lo, hi, k, UPf, EPf, df);
+    lo = (int)seg_lo[2 * q + 1]; hi = (int)seg_hi[2 * q + 1];
+    strand_at(evl, states, lo, lo, hi, k, UPc, EPc, dc);
+    tmp[idx] = make_int4(EPf, EPc, df, dc);
+}
+// per candidate: replay the fold over the local queries (ini order) to recover every query's strand and start (SP)
+__global__ void pass2b_kernel(const uint32_t* __restrict__ ck, int ncand, const int4* __restrict__ tmp, int nq, int n,
+                              const int32_t* __restrict__ MEP, const int32_t* __restrict__ initEP, int32_t* __restrict__ out_lon,
+                              int32_t* __restrict__ out_sp, uint8_t* __restrict__ out_fwd) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncand) return;
     const uint32_t k = ck[c];
     int M = initEP ? initEP[k] : n;        // Master.EP[k] before this rank's first query (multi-GPU: prefix over earlier ranks)
     for (int q = 0; q < nq; ++q) {
-        int UPf, EPf, df, UPc, EPc, dc;
-        int lo = (int)seg_lo[2 * q], hi = (int)seg_hi[2 * q];
-        strand_at(evl, states, lo, lo, hi, k, UPf, EPf, df);
-        lo = (int)seg_lo[2 * q + 1]; hi = (int)seg_hi[2 * q + 1];
-        strand_at(evl, states, lo, lo, hi, k, UPc, EPc, dc);
-        int fe = min(M, EPf), ce = min(M, EPc);
-        if (fe > ce) { out_sp[(size_t)c * nq + q] = (int)k + df; out_fwd[(size_t)c * nq + q] = 1; M = fe; }
-        else { out_sp[(size_t)c * nq + q] = (int)k + dc; out_fwd[(size_t)c * nq + q] = 0; M = ce; }
+        const int4 t = tmp[(size_t)c * nq + q];
+        int fe = min(M, t.x), ce = min(M, t.y);
+        if (fe > ce) { out_sp[(size_t)c * nq + q] = (int)k + t.z; out_fwd[(size_t)c * nq + q] = 1; M = fe; }
+        else { out_sp[(size_t)c * nq + q] = (int)k + t.w; out_fwd[(size_t)c * nq + q] = 0; M = ce; }
     }
     out_lon[c] = MEP[k] - (int)k;
 }
@@ -701,8 +739,17 @@ public:
             int32_t* d_lon = olon_.ensure(ncand, false, st);
             int32_t* d_sp = osp_.ensure((size_t)ncand * std::max(nq, 1), false, st);
             uint8_t* d_fwd = ofwd_.ensure((size_t)ncand * std::max(nq, 1), false, st);
-            pb200::launch(pass2_kernel, (ncand + 127) / 128, 128, 0, st, ck_.get(), (int)ncand, evl_.get(), states_.get(), seglo_.get(),
-                          seghi_.get(), nq, n, mep_.get(), initEP, d_lon, d_sp, d_fwd);
+            if (nq) {
+                int4* tmp = p2tmp_.ensure((size_t)ncand * nq, false, st);
+                const long long tot = (long long)ncand * nq;
+                pb200::launch(pass2a_kernel, (unsigned)((tot + 127) / 128), 128, 0, st, ck_.get(), (int)ncand, evl_.get(), states_.get(),
+                              seglo_.get(), seghi_.get(), nq, tmp);
+                pb200::launch(pass2b_kernel, (ncand + 127) / 128, 128, 0, st, ck_.get(), (int)ncand, tmp, nq, n, mep_.get(), initEP, d_lon, d_sp,
+                              d_fwd);
+            } else {
+                pb200::launch(pass2b_kernel, (ncand + 127) / 128, 128, 0, st, ck_.get(), (int)ncand, (const int4*)nullptr, 0, n, mep_.get(),
+                              initEP, d_lon, d_sp, d_fwd);
+            }
             PB_CUDA(cudaMemcpyAsync(out_k.data() + base, ck_.get(), (size_t)ncand * 4, cudaMemcpyDeviceToHost, st));
             PB_CUDA(cudaMemcpyAsync(out_lon.data() + base, d_lon, (size_t)ncand * 4, cudaMemcpyDeviceToHost, st));
             if (nq) {
@@ -741,7 +788,7 @@ private:
     DevBuf<uint32_t> vals0_, vals1_, sa_, rank_, tmpA_, tmpB_, tmpC_, cs0_, cs1_, total_, seglo_, seghi_, evl_, ck_;
     DevBuf<int32_t> lcp_, lrp_, mup_, mep_, olon_, osp_;
     DevBuf<uint8_t> ofwd_;
-    DevBuf<int4> states_;
+    DevBuf<int4> states_, p2tmp_;
     DevBuf<uint2> table_;
     DevBuf<StrandDesc> strands_;
     DevBuf<unsigned long long> evcount_;

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) digit_scan_kernel(uint32_t* __restrict__ 
 }
 
 template <class K, class V>
-__global__ void __launch_bounds__(RS_THREADS, 4) scatter_kernel(const K* __restrict__ kin, K* __restrict__ kout,
+__global__ void __launch_bounds__(RS_THREADS, (sizeof(K) == 4 ? 6 : 4)) scatter_kernel(const K* __restrict__ kin, K* __restrict__ kout,
                                                                 const V* __restrict__ vin, V* __restrict__ vout, int64_t n, int shift,
                                                                 int bits, const uint32_t* __restrict__ offsets, int64_t tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
