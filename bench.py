@@ -26,6 +26,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ["NCCL_DEBUG"] = os.environ.get("PB200_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
 
 L_FULL, NQ, DIV, SEED = 5_000_000, 8, 0.01, 1
 L_CPU_SAMPLE = 1_000_000          # cpu_baseline leg: ~20 s of single-thread CPU work

@@ -25,6 +25,9 @@
  *   pb200_minsize
  *       Converter()+Calculator() as used at src/parsnp.cpp:1502-1514.
  *
+ *   pb200_mumi
+ *       Aligner::setMumi (src/parsnp.cpp:1869-2115), the calcmumi=1 mode the Python driver runs first (parsnp:1365-1373).
+ *
  *   pb200_comm_set / pb200_comm_clear  (multi-GPU; one process per GPU)
  *       no reference counterpart (the reference has no distributed backend): query genomes are sharded over
  *       ranks for the anchor scan, windows are sharded for the recursion; the caller's collectives carry the exchange.
@@ -116,6 +119,12 @@ int pb200_result_trace(const pb200_result* r, int64_t* pairs);
 int pb200_result_stats(const pb200_result* r, double* values, int cap);
 const char* pb200_stats_names(void);                       /* comma-separated names matching pb200_result_stats */
 void pb200_result_free(pb200_result* r);
+
+/* ---- MUMi mode (ini calcmumi=1): Aligner::setMumi (src/parsnp.cpp:1869-2115) ----
+ * out[j-1] = MUMi distance of query j to the reference = 1 - (reference positions of the first window covered by
+ * MUMs >= 15 bp) / window length, with the reference's length-ratio rule; the value parsnp_core prints as
+ * "<j>:<%f>" into all.mumi.  out must hold n-1 doubles. */
+int pb200_mumi(pb200_genomes* g, const pb200_params* prm, double* out);
 
 /* ---- minsize ---- */
 int pb200_minsize(const char* expr, int64_t slength);

@@ -25,6 +25,7 @@ int pbtest_align(int backend, int n, const uint8_t* const* seqs, const int64_t* 
         pb200::Aligner a(n, seqs, lens, pb200::to_align_params(prm), be);
         a.enable_trace(prm->flags & PB200_FLAG_TRACE_WINDOWS);
         a.set_speculate(!(prm->flags & PB200_FLAG_NO_SPECULATION));
+        a.set_threads(pb200::default_host_threads());
         bool ok = a.run();
         *out = pb200::make_result(a);
         delete be;
@@ -48,6 +49,7 @@ int pbtest_align_sharded(int rank, int world, pb200_allgather_cb ag, pb200_allre
         CbComm comm; comm.rank = rank; comm.world = world; comm.ag = ag; comm.ar = ar; comm.bc = bc; comm.user = nullptr;
         pb200::ShardedBackend sb(local.get(), pb200_oracle::as_staged(local.get()), &comm, true);
         pb200::Aligner a(n, seqs, lens, pb200::to_align_params(prm), &sb);
+        a.set_threads(pb200::default_host_threads());
         bool ok = a.run();
         *out = pb200::make_result(a);
         if (counters) { counters[0] = sb.staged_windows; counters[1] = sb.sharded_small_windows; }

@@ -103,3 +103,15 @@ def run_ref(ref, queries, workdir, dump=True, cands=False, dump_exit=True, timeo
     if cands and os.path.exists(env.get("PARSNP_ORACLE_CANDS", "")):
         res["cands"] = parse_cands(env["PARSNP_ORACLE_CANDS"])
     return res
+
+
+def run_ref_mumi(ref, queries, workdir, **kw):
+    """reference in calcmumi=1 mode (Aligner::setMumi) -> list of '%f' strings in query order (cores=1: deterministic order)"""
+    r = run_ref(ref, queries, workdir, dump=False, calcmumi=1, cores=1, **kw)
+    vals = {}
+    with open(os.path.join(r["outdir"], "all.mumi")) as f:
+        for line in f:
+            if ":" in line:
+                i, v = line.strip().split(":")
+                vals[int(i)] = v
+    return [vals[i + 1] for i in range(len(queries))]

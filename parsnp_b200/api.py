@@ -203,6 +203,7 @@ def load():
     lib.pb200_search_windows.argtypes = [vp, C.c_int, vp, vp, C.c_int64] + [vp] * 5
     lib.pb200_align_resident.argtypes = [vp, vp, vp]
     lib.pb200_align.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp]
+    lib.pb200_mumi.argtypes = [vp, vp, vp]
     lib.pb200_engine_timers.argtypes = [vp, vp, C.c_int]
     lib.pb200_engine_timer_names.restype = C.c_char_p
     lib.pb200_engine_reset_timers.argtypes = [vp]
@@ -269,6 +270,13 @@ class Genomes:
         for p in (off, k, lon, sp, fwd):
             self.lib.pb200_free_buffer(p)
         return res
+
+    def mumi(self, params=None):
+        """MUMi distance of every query to the reference (parsnp_core's calcmumi=1 mode, all.mumi)"""
+        prm = params or make_params()
+        out = np.zeros(self.n - 1, np.float64)
+        _check(self.lib, self.lib.pb200_mumi(self.h, C.byref(prm), _ptr(out)))
+        return out
 
     def set_comm(self, comm, bcast_index=True):
         """shard the search of align() over the ranks of `comm` (a TorchComm); every rank must hold the same genomes"""

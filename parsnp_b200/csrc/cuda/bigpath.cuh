@@ -460,6 +460,26 @@ __global__ void emit_flags_kernel(const int32_t* __restrict__ MUP, const int32_t
     flag[k] = (ep > prev && MUP[k] < ep && ep - k >= minsize) ? 1u : 0u;
 }
 
+// ---- MUMi mode (Aligner::setMumi, src/parsnp.cpp:1869-2115): per query, reference positions covered by MUMs >= 15 bp
+// a[k] = EP[k] where the position is "good" (UP < EP and EP - k < n), else 0
+__global__ void mumi_good_kernel(const int32_t* __restrict__ MUP, const int32_t* __restrict__ MEP, int n, uint32_t* __restrict__ a) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int up = MUP[k], ep = MEP[k];
+    a[k] = (up < ep && ep - k < n) ? (uint32_t)ep : 0u;
+}
+// v[k] = EP[k] for emitted candidates of length >= 15 (emitted = good and EP greater than at the previous good position)
+__global__ void mumi_val_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ prevmax, int n, uint32_t* __restrict__ v) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t ep = a[k];
+    v[k] = (ep && ep > prevmax[k] && (int)ep - k >= 15) ? ep : 0u;
+}
+__global__ void mumi_cover_kernel(const uint32_t* __restrict__ runmax, int n, uint32_t* __restrict__ c) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) c[k] = runmax[k] > (uint32_t)k ? 1u : 0u;
+}
+
 // per (candidate, local query): the two strands' (EP, diagonal) at the candidate position
 __global__ void pass2a_kernel(const uint32_t* __restrict__ ck, int ncand, const uint32_t* __restrict__ evl, const int4* __restrict__ states,
                               const uint32_t* __restrict__ seg_lo, const uint32_t* __restrict__ seg_hi, int nq, int4* __restrict__ tmp) {
@@ -767,6 +787,30 @@ public:
         fold(true, st);
         emit(st);
         pass2(nullptr, st, out_k, out_lon, out_sp, out_fwd);
+    }
+    // MUMi of query q (index into the strands given to scan_events): number of reference positions covered by MUMs >= 15
+    uint32_t mumi_covered(int q, cudaStream_t st) {
+        const int TB = 256;
+        const int n = cur_n_;
+        const unsigned nb = (unsigned)((n + TB - 1) / TB);
+        int32_t* MUP = mup_.ensure((size_t)n, false, st);
+        int32_t* MEP = mep_.ensure((size_t)n, false, st);
+        pb200::launch(fold_kernel, (unsigned)((n + FOLD_TILE - 1) / FOLD_TILE), FOLD_THREADS, 0, st, evl_.get(), states_.get(), seglo_.get() + 2 * q,
+                      seghi_.get() + 2 * q, 1, n, MUP, MEP, 1);
+        uint32_t* a = tmpA_.ensure((size_t)n + 1, false, st);
+        uint32_t* b = tmpB_.ensure((size_t)n + 1, false, st);
+        uint32_t* c = tmpC_.ensure((size_t)n + 1, false, st);
+        uint32_t* d_tot = total_.ensure(4, false, st);
+        pb200::launch(mumi_good_kernel, nb, TB, 0, st, MUP, MEP, n, a);
+        scanner_.scan<prim::OpMax, true>(a, b, n, nullptr, st);            // b = max EP over earlier good positions
+        pb200::launch(mumi_val_kernel, nb, TB, 0, st, a, b, n, c);
+        scanner_.scan<prim::OpMax, false>(c, c, n, nullptr, st);           // running max end of the counted MUMs
+        pb200::launch(mumi_cover_kernel, nb, TB, 0, st, c, n, a);
+        scanner_.scan<prim::OpSum, true>(a, b, n, d_tot, st);
+        uint32_t tot = 0;
+        PB_CUDA(cudaMemcpyAsync(&tot, d_tot, 4, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaStreamSynchronize(st));
+        return tot;
     }
     // multi-GPU: device pointers of the window index (for the broadcast from the building rank)
     uint32_t* index_sa() { return sa_.get(); }

@@ -233,6 +233,33 @@ public:
     }
     cudaStream_t stream() const { return st_; }
 
+    // ---- MUMi mode (Aligner::setMumi, src/parsnp.cpp:1869-2115): per query 1 - covered/len over the FIRST reference window
+    void mumi(int64_t P, std::vector<double>& out) {
+        PB_CUDA(cudaSetDevice(device_));
+        const int nq = n_ - 1;
+        out.assign(nq, 0.0);
+        const int64_t L0 = len_[0];
+        const int64_t p = P > L0 ? L0 : P;                 // src/parsnp.cpp:1903-1906; only partpos = 0 is ever processed (1907)
+        if (p <= 0 || nq <= 0) return;
+        std::vector<big::StrandDesc> sd((size_t)2 * nq);
+        for (int q = 0; q < nq; ++q) {
+            const int g = q + 1;
+            sd[2 * q] = big::StrandDesc{text_.get() + gfwd_[g], (int32_t)len_[g], 0};
+            sd[2 * q + 1] = big::StrandDesc{text_.get() + grc_[g], (int32_t)len_[g], 0};
+        }
+        const int minlon = 15;                             // only MUMs of >= 15 bp count (src/parsnp.cpp:2050-2062)
+        big_.build_index(text_.get() + gfwd_[0], (int)p, minlon, st_, window_is_n_free(0, p));
+        big_.scan_events(text_.get() + gfwd_[0], (int)p, nq, sd, minlon, st_);
+        for (int q = 0; q < nq; ++q) {
+            int total = (int)big_.mumi_covered(q, st_);
+            const int minlen = (int)p;
+            const float ratio = float(L0) / float(len_[q + 1]);
+            if (ratio > 1.3 || ratio < 0.7) total = 0;     // src/parsnp.cpp:2074-2075
+            if (total > minlen) total = minlen;
+            out[q] = 1.0 - (float(total) / float(minlen));
+        }
+    }
+
     // test hooks: suffix array + lrp of a window of genome 0
     void debug_index(int64_t ref_start, int n, int minsize, uint32_t* sa, int32_t* lrp) {
         PB_CUDA(cudaSetDevice(device_));
@@ -506,6 +533,7 @@ int pb200_align_resident(pb200_genomes* g, const pb200_params* prm, pb200_result
         pb200::Aligner a(g->n, g->seq.data(), g->len.data(), pb200::to_align_params(prm), &be);
         a.enable_trace(prm->flags & PB200_FLAG_TRACE_WINDOWS);
         a.set_speculate(!(prm->flags & PB200_FLAG_NO_SPECULATION));
+        a.set_threads(pb200::default_host_threads());
         bool ok = a.run();
         *out = pb200::make_result(a);
         return ok ? (int)PB200_OK : (int)PB200_ERR_NO_MUMS;
@@ -519,6 +547,16 @@ int pb200_align(int device, int n, const uint8_t* const* seqs, const int64_t* le
     rc = pb200_align_resident(g, prm, out);
     pb200_genomes_free(g);
     return rc;
+}
+
+int pb200_mumi(pb200_genomes* g, const pb200_params* prm, double* out) {
+    return guarded([&]() {
+        if (!g || !prm || !out) { pb200::g_last_error = "bad arguments"; return (int)PB200_ERR_ARG; }
+        std::vector<double> v;
+        g->eng->mumi(prm->p, v);
+        for (size_t i = 0; i < v.size(); ++i) out[i] = v[i];
+        return (int)PB200_OK;
+    });
 }
 
 int pb200_engine_timers(pb200_genomes* g, double* values, int cap) {

@@ -7,6 +7,9 @@
 #include <cstdio>
 #include <stdexcept>
 #include <unordered_set>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace pb200 {
 
@@ -38,6 +41,15 @@ void BitRow::set_range(int64_t a, int64_t b) {
     w_[wa] |= ma;
     for (int64_t i = wa + 1; i < wb; ++i) w_[i] = ~0ull;
     w_[wb] |= mb;
+}
+void BitRow::set_range_atomic(int64_t a, int64_t b) {
+    if (a >= b) return;
+    int64_t wa = a >> 6, wb = (b - 1) >> 6;
+    uint64_t ma = ~0ull << (a & 63), mb = ~0ull >> (63 - ((b - 1) & 63));
+    if (wa == wb) { __atomic_fetch_or(&w_[wa], ma & mb, __ATOMIC_RELAXED); return; }
+    __atomic_fetch_or(&w_[wa], ma, __ATOMIC_RELAXED);
+    for (int64_t i = wa + 1; i < wb; ++i) __atomic_store_n(&w_[i], ~0ull, __ATOMIC_RELAXED);
+    __atomic_fetch_or(&w_[wb], mb, __ATOMIC_RELAXED);
 }
 void BitRow::clear_range(int64_t a, int64_t b) {
     if (a >= b) return;
@@ -100,6 +112,7 @@ Aligner::Aligner(int n, const uint8_t* const* seq, const int64_t* len, const Ali
     if (!be) throw std::runtime_error("parsnp_b200: no search backend (the CUDA engine is required)");
     seq_.assign(seq, seq + n);
     len_.assign(len, len + n);
+    rp_.n = n;
     truth_.layout.resize(n);
     for (int i = 0; i < n; ++i) {                      // src/parsnp.cpp:3181-3186
         truth_.layout[i].init(len_[i] + 1);
@@ -108,32 +121,31 @@ Aligner::Aligner(int n, const uint8_t* const* seq, const int64_t* len, const Ali
     be_->set_genomes(n, seq, len);
 }
 
-int Aligner::new_region(const int64_t* start, const int64_t* end) {
-    int id = (int)rslength_.size();
-    rcoord_.insert(rcoord_.end(), start, start + n_);
-    rcoord_.insert(rcoord_.end(), end, end + n_);
+int RegionPool::add(const int64_t* start, const int64_t* end) {
+    int id = (int)slen.size();
+    coord.insert(coord.end(), start, start + n);
+    coord.insert(coord.end(), end, end + n);
     int64_t sl = 500000000;                             // TRegion ctor, src/LCR.cpp:16-37
-    for (int i = 0; i < n_; ++i) sl = std::min(sl, end[i] - start[i]);
-    rslength_.push_back(sl);
+    for (int i = 0; i < n; ++i) sl = std::min(sl, end[i] - start[i]);
+    slen.push_back(sl);
     return id;
 }
 bool Aligner::region_equal(int a, int b) const {        // operator==, src/LCR.cpp:48-58
     return std::memcmp(rstart(a), rstart(b), sizeof(int64_t) * 2 * n_) == 0;
 }
-uint64_t Aligner::region_hash(int r) const {
-    const int64_t* p = rstart(r);
+uint64_t Aligner::coords_hash(const int64_t* p, int count) {
     uint64_t h = 0x9E3779B97F4A7C15ull;
-    for (int i = 0; i < 2 * n_; ++i) {
+    for (int i = 0; i < count; ++i) {
         h ^= (uint64_t)p[i] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
         h *= 0xff51afd7ed558ccdull;
         h ^= h >> 29;
     }
     return h;
 }
-int Aligner::cache_lookup(int r) const {
-    auto range = cache_map_.equal_range(region_hash(r));
+int Aligner::cache_lookup_coords(const int64_t* coords) const {
+    auto range = cache_map_.equal_range(coords_hash(coords, 2 * n_));
     for (auto it = range.first; it != range.second; ++it)
-        if (region_equal(cache_entries_[it->second].region, r)) return it->second;
+        if (std::memcmp(rstart(cache_entries_[it->second].region), coords, sizeof(int64_t) * 2 * n_) == 0) return it->second;
     return -1;
 }
 
@@ -158,7 +170,7 @@ void Aligner::search_regions(const std::vector<int>& regs, bool anchors) {
         const int64_t* rs = rstart(r);
         const int64_t* re = rend(r);
         first_task[ri] = (int)tasks.size();
-        const int minsize = minsize_cached(anchors, rslength_[r]);
+        const int minsize = minsize_cached(anchors, rp_.slen[r]);
         const int64_t coff = (int64_t)coords.size();
         for (int j = 1; j < n_; ++j) coords.push_back(rs[j]);
         for (int j = 1; j < n_; ++j) coords.push_back(re[j] - rs[j]);
@@ -211,24 +223,26 @@ void Aligner::search_regions(const std::vector<int>& regs, bool anchors) {
             w.minsize = tasks[t].minsize;
             wins_.push_back(w);
         }
-        cache_map_.emplace(region_hash(regs[ri]), (int)cache_entries_.size());
+        cache_map_.emplace(coords_hash(rstart(regs[ri]), 2 * n_), (int)cache_entries_.size());
         cache_entries_.push_back(e);
     }
 }
 
 // ------------------------------------------------------------------ setMums1 loop D (src/parsnp.cpp:1713-1842)
-void Aligner::accept_candidates(int r, int cache_idx, World& w, std::vector<int>& found) {
+void Aligner::accept_candidates(const int64_t* rs, const int64_t* re, int64_t rsl, int cache_idx, std::vector<BitRow>& layout, MumPool& mp,
+                                std::vector<int>& found, bool atomic, bool trace) {
     const CacheEntry& ce = cache_entries_[cache_idx];
-    const int64_t* rs = rstart(r);
-    const int64_t* re = rend(r);
     const int nq = n_ - 1;
-    scratch_st_.resize(n_);
-    scratch_fw_.resize(n_);
-    std::vector<int64_t>& st = scratch_st_;
-    std::vector<uint8_t>& fw = scratch_fw_;
+    int64_t st_buf[64];
+    uint8_t fw_buf[64];
+    std::vector<int64_t> st_vec;
+    std::vector<uint8_t> fw_vec;
+    int64_t* st = st_buf;
+    uint8_t* fw = fw_buf;
+    if (n_ > 64) { st_vec.resize(n_); fw_vec.resize(n_); st = st_vec.data(); fw = fw_vec.data(); }
     for (int wi = 0; wi < ce.nwin; ++wi) {
         const WinRec& win = wins_[ce.first_win + wi];
-        if (trace_on_ && &w == &truth_) trace_.emplace_back(win.ref_start, win.ref_len);
+        if (trace) trace_.emplace_back(win.ref_start, win.ref_len);
         for (int32_t c = 0; c < win.ncand; ++c) {
             const int64_t ci = win.cand_off + c;
             const int64_t LON = clon_[ci];
@@ -258,10 +272,11 @@ void Aligner::accept_candidates(int r, int cache_idx, World& w, std::vector<int>
             // trim (src/parsnp.cpp:1399-1477): every trim shifts ALL genomes, strand ignored
             int64_t length = LON;
             for (int j = 0; j < n_; ++j) {
-                int64_t t1 = w.layout[j].run_up(st[j], st[j] + length);
+                int64_t t1 = layout[j].run_up(st[j], st[j] + length);
                 if (t1) { for (int i = 0; i < n_; ++i) st[i] += t1; length -= t1; }
-                int64_t t2 = w.layout[j].run_down(st[j], st[j] + length);
+                int64_t t2 = layout[j].run_down(st[j], st[j] + length);
                 length -= t2;
+                if (length <= 0) break;          // nothing left: the remaining genomes' loops would not execute (src/parsnp.cpp:1409,1443)
             }
             if (length < 2 || n_ <= 1) continue;
             // reverse-strand genomes are verified against the reference substring (src/parsnp.cpp:1800-1825)
@@ -274,16 +289,19 @@ void Aligner::accept_candidates(int r, int cache_idx, World& w, std::vector<int>
                     if (comp_base(gk[length - 1 - t]) != g0[t]) { badmum = true; break; }
             }
             if (badmum) continue;
-            for (int k = 0; k < n_; ++k) w.layout[k].set_range(st[k], st[k] + length);
+            for (int k = 0; k < n_; ++k) {
+                if (atomic) layout[k].set_range_atomic(st[k], st[k] + length);
+                else layout[k].set_range(st[k], st[k] + length);
+            }
             MumRec m;
             m.length = length;
-            m.slength = rslength_[r];
-            m.off = (int64_t)mum_start_.size();
+            m.slength = rsl;
+            m.off = (int64_t)mp.start.size();
             m.alive = true;
-            mum_start_.insert(mum_start_.end(), st.begin(), st.end());
-            mum_fwd_.insert(mum_fwd_.end(), fw.begin(), fw.end());
-            found.push_back((int)mums_.size());
-            mums_.push_back(m);
+            mp.start.insert(mp.start.end(), st, st + n_);
+            mp.fwd.insert(mp.fwd.end(), fw, fw + n_);
+            found.push_back((int)mp.mums.size());
+            mp.mums.push_back(m);
         }
     }
 }
@@ -314,12 +332,12 @@ static int64_t det_region(const std::vector<BitRow>& layout, const std::vector<i
 void Aligner::set_initial_clusters() {
     double t0 = now_s();
     std::vector<int64_t> S(n_, 0), E(len_);
-    int whole = new_region(S.data(), E.data());
+    int whole = rp_.add(S.data(), E.data());
     search_regions(std::vector<int>(1, whole), true);
     double t1 = now_s();
     stats_.t_anchor_search = t1 - t0;
     std::vector<int> found;
-    accept_candidates(whole, cache_lookup(whole), truth_, found);
+    accept_candidates(rstart(whole), rend(whole), rp_.slen[whole], cache_lookup(whole), truth_.layout, mp_, found, false, trace_on_);
     all_mums_ = found;
     stats_.anchors = (int64_t)found.size();
     std::vector<int64_t> lS(n_), lE(n_), rS(n_), rE(n_);
@@ -330,22 +348,51 @@ void Aligner::set_initial_clusters() {
         int64_t lsl = det_region(truth_.layout, len_, n_, ms, m.length, true, lS.data(), lE.data());
         bool l_eq_r = have_r && std::memcmp(lS.data(), rS.data(), sizeof(int64_t) * n_) == 0 &&
                       std::memcmp(lE.data(), rE.data(), sizeof(int64_t) * n_) == 0;
-        if (lsl > prm_.q && (i == 0 || !l_eq_r)) initial_regions_.push_back(new_region(lS.data(), lE.data()));
+        if (lsl > prm_.q && (i == 0 || !l_eq_r)) initial_regions_.push_back(rp_.add(lS.data(), lE.data()));
         int64_t rsl = det_region(truth_.layout, len_, n_, ms, m.length, false, rS.data(), rE.data());
         have_r = true;
         bool r_eq_l = std::memcmp(lS.data(), rS.data(), sizeof(int64_t) * n_) == 0 &&
                       std::memcmp(lE.data(), rE.data(), sizeof(int64_t) * n_) == 0;
-        if (rsl > prm_.q && !r_eq_l) initial_regions_.push_back(new_region(rS.data(), rE.data()));
+        if (rsl > prm_.q && !r_eq_l) initial_regions_.push_back(rp_.add(rS.data(), rE.data()));
     }
     stats_.t_anchor_host = now_s() - t1;
 }
 
 // ------------------------------------------------------------------ speculative level-synchronous discovery
+// One level over frontier[a,b) (sorted by start[0]): accept on the scratch layout, collect the children's coordinates.
+// Only a predictor of which regions the exact replay will ask for - races between threads merely cost cache misses.
+void Aligner::speculate_range(const std::vector<int>& frontier, size_t a, size_t b, std::vector<BitRow>& layout, MumPool& mp, RegionPool& out,
+                              bool atomic) {
+    std::vector<int> found;
+    std::vector<int64_t> lS(n_), lE(n_), rS(n_), rE(n_);
+    int prev = -1;
+    for (size_t x = a; x < b; ++x) {
+        const int r = frontier[x];
+        if (prev >= 0 && region_equal(prev, r)) continue;
+        prev = r;
+        found.clear();
+        const int ci = cache_lookup(r);
+        if (ci < 0) continue;
+        accept_candidates(rstart(r), rend(r), rp_.slen[r], ci, layout, mp, found, atomic, false);
+        int64_t lsl = 0;
+        for (size_t i = 0; i < found.size(); ++i) {
+            const MumRec& m = mp.mums[found[i]];
+            const int64_t* ms = &mp.start[m.off];
+            if (i == 0) lsl = det_region(layout, len_, n_, ms, m.length, true, lS.data(), lE.data());
+            int64_t rsl = det_region(layout, len_, n_, ms, m.length, false, rS.data(), rE.data());
+            if (lsl > prm_.q) out.add(lS.data(), lE.data());
+            if (rsl > prm_.q) out.add(rS.data(), rE.data());
+            if (i + 1 < found.size()) {
+                const MumRec& m2 = mp.mums[found[i + 1]];
+                lsl = det_region(layout, len_, n_, &mp.start[m2.off], m2.length, true, lS.data(), lE.data());
+            }
+        }
+    }
+}
+
 void Aligner::speculate(const std::vector<int>& initial, const World& truth) {
     World spec = truth;                                    // scratch copy of mumlayout
-    const size_t save_mums = mums_.size(), save_ms = mum_start_.size(), save_mf = mum_fwd_.size();
-    std::vector<int> frontier = initial, next, found, need;
-    std::vector<int64_t> lS(n_), lE(n_), rS(n_), rE(n_);
+    std::vector<int> frontier = initial, need;
     while (!frontier.empty()) {
         double t0 = now_s();
         need.clear();
@@ -353,7 +400,7 @@ void Aligner::speculate(const std::vector<int>& initial, const World& truth) {
             std::unordered_multimap<uint64_t, int> seen;
             for (int r : frontier) {
                 if (cache_lookup(r) >= 0) continue;
-                uint64_t h = region_hash(r);
+                uint64_t h = coords_hash(rstart(r), 2 * n_);
                 bool dup = false;
                 auto range = seen.equal_range(h);
                 for (auto it = range.first; it != range.second; ++it) if (region_equal(it->second, r)) { dup = true; break; }
@@ -368,33 +415,23 @@ void Aligner::speculate(const std::vector<int>& initial, const World& truth) {
         double t1 = now_s();
         stats_.t_spec_search += t1 - t0;
         std::stable_sort(frontier.begin(), frontier.end(), [&](int a, int b) { return rstart(a)[0] < rstart(b)[0]; });
-        next.clear();
-        int prev = -1;
-        for (int r : frontier) {
-            if (prev >= 0 && region_equal(prev, r)) continue;
-            prev = r;
-            found.clear();
-            accept_candidates(r, cache_lookup(r), spec, found);
-            int64_t lsl = 0;
-            for (size_t i = 0; i < found.size(); ++i) {
-                const MumRec& m = mums_[found[i]];
-                const int64_t* ms = &mum_start_[m.off];
-                if (i == 0) lsl = det_region(spec.layout, len_, n_, ms, m.length, true, lS.data(), lE.data());
-                int64_t rsl = det_region(spec.layout, len_, n_, ms, m.length, false, rS.data(), rE.data());
-                if (lsl > prm_.q) next.push_back(new_region(lS.data(), lE.data()));
-                if (rsl > prm_.q) next.push_back(new_region(rS.data(), rE.data()));
-                if (i + 1 < found.size()) {
-                    const MumRec& m2 = mums_[found[i + 1]];
-                    lsl = det_region(spec.layout, len_, n_, &mum_start_[m2.off], m2.length, true, lS.data(), lE.data());
-                }
-            }
+        // chunks of the frontier are processed concurrently on the shared scratch layout
+        const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads_, frontier.size() / 256 + 1));
+        const size_t nchunks = T > 1 ? (size_t)T * 4 : 1;
+        std::vector<RegionPool> outs(nchunks);
+        for (auto& o : outs) o.n = n_;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(T) if (T > 1)
+        for (long c = 0; c < (long)nchunks; ++c) {
+            MumPool mp;
+            const size_t a = frontier.size() * (size_t)c / nchunks, b = frontier.size() * (size_t)(c + 1) / nchunks;
+            speculate_range(frontier, a, b, spec.layout, mp, outs[c], T > 1);
         }
+        std::vector<int> next;
+        for (auto& o : outs)
+            for (int i = 0; i < o.size(); ++i) next.push_back(rp_.add(o.start(i), o.end(i)));
         frontier.swap(next);
         stats_.t_spec_host += now_s() - t1;
     }
-    mums_.resize(save_mums);
-    mum_start_.resize(save_ms);
-    mum_fwd_.resize(save_mf);
 }
 
 // ------------------------------------------------------------------ doWork (src/parsnp.cpp:173-317), exact order
@@ -403,12 +440,13 @@ struct QE { int64_t s0; int id; };
 inline bool operator<(const QE& a, const QE& b) { return a.s0 < b.s0; }   // operator<, src/LCR.cpp:42
 }
 
-void Aligner::do_work_exact() {
-    double t0 = now_s();
+void Aligner::process_queue_exact(const std::vector<int>& initial, RegionPool& rp, std::vector<BitRow>& layout, MumPool& mp,
+                                  std::vector<int>& out_mums) {
     // exact emulation of `vector<TRegion> regions`: slow mode keeps the vector itself; fast mode is valid while
     // all start[0] keys are distinct (then every correct sort yields the same sequence).
+    auto req = [&](int a, int b) { return std::memcmp(rp.start(a), rp.start(b), sizeof(int64_t) * 2 * n_) == 0; };
     std::vector<QE> vec;
-    for (int r : initial_regions_) vec.push_back(QE{rstart(r)[0], r});
+    for (int r : initial) vec.push_back(QE{rp.start(r)[0], r});
     std::map<int64_t, int> fast;
     bool fast_mode = false;
     std::vector<int> found, children;
@@ -417,42 +455,42 @@ void Aligner::do_work_exact() {
         int cur;
         if (fast_mode) { cur = fast.begin()->second; fast.erase(fast.begin()); }
         else { cur = vec.front().id; vec.erase(vec.begin()); }
-        int ci = cache_lookup(cur);
+        int ci = cache_lookup_coords(rp.start(cur));
         if (ci < 0) {
             double ts = now_s();
-            search_regions(std::vector<int>(1, cur), false);
+            search_regions(std::vector<int>(1, cur), false);          // a region the speculation did not predict
             stats_.t_replay_search += now_s() - ts;
             stats_.replay_misses++;
-            ci = cache_lookup(cur);
+            ci = cache_lookup_coords(rp.start(cur));
         }
         found.clear();
-        accept_candidates(cur, ci, truth_, found);
+        accept_candidates(rp.start(cur), rp.end(cur), rp.slen[cur], ci, layout, mp, found, false, trace_on_);
         children.clear();
         int64_t lsl = 0;
         for (size_t i = 0; i < found.size(); ++i) {
-            const MumRec& m = mums_[found[i]];
-            const int64_t* ms = &mum_start_[m.off];
-            if (i == 0) lsl = det_region(truth_.layout, len_, n_, ms, m.length, true, lS.data(), lE.data());
-            int64_t rsl = det_region(truth_.layout, len_, n_, ms, m.length, false, rS.data(), rE.data());
-            if (lsl > prm_.q) children.push_back(new_region(lS.data(), lE.data()));
-            if (rsl > prm_.q) children.push_back(new_region(rS.data(), rE.data()));
+            const MumRec& m = mp.mums[found[i]];
+            const int64_t* ms = &mp.start[m.off];
+            if (i == 0) lsl = det_region(layout, len_, n_, ms, m.length, true, lS.data(), lE.data());
+            int64_t rsl = det_region(layout, len_, n_, ms, m.length, false, rS.data(), rE.data());
+            if (lsl > prm_.q) children.push_back(rp.add(lS.data(), lE.data()));
+            if (rsl > prm_.q) children.push_back(rp.add(rS.data(), rE.data()));
             if (i + 1 < found.size()) {
-                const MumRec& m2 = mums_[found[i + 1]];
-                lsl = det_region(truth_.layout, len_, n_, &mum_start_[m2.off], m2.length, true, lS.data(), lE.data());
+                const MumRec& m2 = mp.mums[found[i + 1]];
+                lsl = det_region(layout, len_, n_, &mp.start[m2.off], m2.length, true, lS.data(), lE.data());
             }
-            all_mums_.push_back(found[i]);
+            out_mums.push_back(found[i]);
         }
         // sort + drop adjacent duplicates (src/parsnp.cpp:291-306)
         if (fast_mode) {
             bool distinct_tie = false;
             for (size_t a = 0; a < children.size() && !distinct_tie; ++a) {
-                auto it = fast.find(rstart(children[a])[0]);
-                if (it != fast.end() && !region_equal(it->second, children[a])) distinct_tie = true;
+                auto it = fast.find(rp.start(children[a])[0]);
+                if (it != fast.end() && !req(it->second, children[a])) distinct_tie = true;
                 for (size_t b = 0; b < a && !distinct_tie; ++b)
-                    if (rstart(children[a])[0] == rstart(children[b])[0] && !region_equal(children[a], children[b])) distinct_tie = true;
+                    if (rp.start(children[a])[0] == rp.start(children[b])[0] && !req(children[a], children[b])) distinct_tie = true;
             }
             if (!distinct_tie) {
-                for (int ch : children) fast.emplace(rstart(ch)[0], ch);   // identical duplicates collapse
+                for (int ch : children) fast.emplace(rp.start(ch)[0], ch);   // identical duplicates collapse
                 continue;
             }
             vec.clear();
@@ -461,13 +499,13 @@ void Aligner::do_work_exact() {
             fast_mode = false;
         }
         stats_.slow_queue_iters++;
-        for (int ch : children) vec.push_back(QE{rstart(ch)[0], ch});
+        for (int ch : children) vec.push_back(QE{rp.start(ch)[0], ch});
         if (!vec.empty()) std::sort(vec.begin(), vec.end());
         {
             size_t rsize = vec.size();
             if (rsize) {
                 for (size_t m = 0; m + 1 < rsize;) {
-                    if (region_equal(vec[m].id, vec[m + 1].id)) { vec.erase(vec.begin() + m); rsize -= 1; }
+                    if (req(vec[m].id, vec[m + 1].id)) { vec.erase(vec.begin() + m); rsize -= 1; }
                     else ++m;
                 }
             }
@@ -481,7 +519,14 @@ void Aligner::do_work_exact() {
             fast_mode = true;
         }
     }
-    stats_.t_replay = now_s() - t0;
+}
+
+void Aligner::do_work_exact() {
+    double t0 = now_s();
+    std::vector<int> out;
+    process_queue_exact(initial_regions_, rp_, truth_.layout, mp_, out);
+    all_mums_.insert(all_mums_.end(), out.begin(), out.end());
+    stats_.t_replay += now_s() - t0;
 }
 
 // sort(this->mums) by start[0] (operator<, src/TMum.cpp:151); starts are distinct (accepted MUMs are disjoint on the
@@ -496,9 +541,26 @@ void Aligner::sort_final_mums() {
         prev = s0;
     }
     if (sorted) return;
+    // this->mums = anchors (already ascending) followed by the recursion's MUMs (ascending apart from a few stragglers):
+    // sort the maximal ascending runs by merging instead of a full n log n sort
     std::vector<std::pair<int64_t, int>> kv(M);
     for (size_t i = 0; i < M; ++i) kv[i] = std::make_pair(mum_start_[mums_[final_mums_[i]].off], final_mums_[i]);
-    std::sort(kv.begin(), kv.end());
+    std::vector<size_t> runs(1, 0);
+    for (size_t i = 1; i < M; ++i) if (kv[i].first < kv[i - 1].first) runs.push_back(i);
+    runs.push_back(M);
+    if (runs.size() - 1 > 64) std::sort(kv.begin(), kv.end());
+    else {
+        while (runs.size() > 2) {
+            std::vector<size_t> nr(1, 0);
+            for (size_t r = 0; r + 1 < runs.size(); r += 2) {
+                if (r + 2 < runs.size()) {
+                    std::inplace_merge(kv.begin() + runs[r], kv.begin() + runs[r + 1], kv.begin() + runs[r + 2]);
+                    nr.push_back(runs[r + 2]);
+                } else nr.push_back(runs[r + 1]);
+            }
+            runs.swap(nr);
+        }
+    }
     for (size_t i = 0; i < M; ++i) final_mums_[i] = kv[i].second;
 }
 
@@ -664,6 +726,7 @@ bool Aligner::run() {
     set_initial_clusters();
     if (!prm_.anchors_only) {
         if (speculate_) speculate(initial_regions_, truth_);
+        stats_.host_threads = threads_;
         do_work_exact();
     }
     if (all_mums_.empty()) { stats_.t_total = now_s() - t0; return false; }

@@ -15,6 +15,7 @@
 //     The search is a pure function of the region coordinates, so pass (2) is exact by construction.
 #pragma once
 #include <cstdint>
+#include <climits>
 #include <string>
 #include <vector>
 #include <unordered_map>
@@ -42,6 +43,7 @@ public:
     void init(int64_t nbits_with_sentinel);
     inline bool get(int64_t i) const { return (w_[i >> 6] >> (i & 63)) & 1ull; }
     void set_range(int64_t a, int64_t b);     // [a,b)
+    void set_range_atomic(int64_t a, int64_t b);   // same, safe against concurrent writers of neighbouring bits
     void clear_range(int64_t a, int64_t b);   // [a,b)
     int64_t run_up(int64_t a, int64_t b) const;     // # consecutive set bits a, a+1, ... (< b)
     int64_t run_down(int64_t a, int64_t b) const;   // # consecutive set bits b-1, b-2, ... (>= a)
@@ -67,9 +69,24 @@ struct ClusterRec {
     std::vector<int64_t> start, end;
 };
 
+// flat pools (shared by the sequential path; thread-local in the chunk-parallel paths)
+struct RegionPool {
+    int n = 0;
+    std::vector<int64_t> coord;     // 2n per region: start[n], end[n]
+    std::vector<int64_t> slen;      // TRegion::slength
+    int add(const int64_t* start, const int64_t* end);
+    inline const int64_t* start(int r) const { return &coord[(size_t)r * 2 * n]; }
+    inline const int64_t* end(int r) const { return &coord[(size_t)r * 2 * n + n]; }
+    inline int size() const { return (int)slen.size(); }
+};
+struct MumPool {
+    std::vector<MumRec> mums;
+    std::vector<int64_t> start;
+    std::vector<uint8_t> fwd;
+};
 struct AlignStats {
     int64_t anchors = 0, regions_searched = 0, spec_regions = 0, replay_misses = 0, spec_levels = 0,
-            windows_searched = 0, candidates = 0, slow_queue_iters = 0;
+            windows_searched = 0, candidates = 0, slow_queue_iters = 0, host_threads = 1;
     double t_anchor_search = 0, t_anchor_host = 0, t_spec_search = 0, t_spec_host = 0, t_replay = 0,
            t_replay_search = 0, t_lcb = 0, t_total = 0;
 };
@@ -93,27 +110,33 @@ public:
     const std::vector<std::pair<int64_t, int64_t>>& window_trace() const { return trace_; }
     void enable_trace(bool on) { trace_on_ = on; }
     void set_speculate(bool on) { speculate_ = on; }
+    void set_threads(int t) { threads_ = t < 1 ? 1 : t; }
 
 private:
-    // ---- region pool: 2n coords per region (start[n], end[n]) ----
-    int new_region(const int64_t* start, const int64_t* end);
-    inline const int64_t* rstart(int r) const { return &rcoord_[(size_t)r * 2 * n_]; }
-    inline const int64_t* rend(int r) const { return &rcoord_[(size_t)r * 2 * n_ + n_]; }
+    inline const int64_t* rstart(int r) const { return rp_.start(r); }
+    inline const int64_t* rend(int r) const { return rp_.end(r); }
     bool region_equal(int a, int b) const;
-    uint64_t region_hash(int r) const;
+    static uint64_t coords_hash(const int64_t* p, int count);
 
     struct World {                     // one copy of the mutable alignment state
         std::vector<BitRow> layout;
     };
 
-    // search + cache
+    // search + cache (the cache is read-only while threads run)
     struct CacheEntry { int region; int64_t first_win; int nwin; };
-    int cache_lookup(int r) const;                    // -> index into cache_entries_ or -1
+    int cache_lookup(int r) const { return cache_lookup_coords(rstart(r)); }
+    int cache_lookup_coords(const int64_t* coords) const;    // -> index into cache_entries_ or -1
     void search_regions(const std::vector<int>& regs, bool anchors);   // batched GPU search, fills the cache
 
-    // setMums1 loop D on cached candidates; appends accepted MUM ids to `found`
-    void accept_candidates(int r, int cache_idx, World& w, std::vector<int>& found);
-    int determine_region(const World& w, const int64_t* mstart, int64_t mlen, bool left);
+    // setMums1 loop D on cached candidates; appends accepted MUMs to `mp`, their indices to `found`
+    void accept_candidates(const int64_t* rs, const int64_t* re, int64_t rsl, int cache_idx, std::vector<BitRow>& layout, MumPool& mp,
+                           std::vector<int>& found, bool atomic, bool trace);
+    // doWork's loop over a queue of regions living in `rp`, in the exact reference order
+    void process_queue_exact(const std::vector<int>& initial, RegionPool& rp, std::vector<BitRow>& layout, MumPool& mp,
+                             std::vector<int>& out_mums);
+    // one speculative level over frontier[a,b): children coordinates appended to `out`
+    void speculate_range(const std::vector<int>& frontier, size_t a, size_t b, std::vector<BitRow>& layout, MumPool& mp, RegionPool& out,
+                         bool atomic);
 
     void set_initial_clusters();     // anchors
     void speculate(const std::vector<int>& initial, const World& truth);
@@ -132,12 +155,11 @@ private:
     SearchBackend* be_;
     MinSizeExpr anchor_expr_, mum_expr_;
 
-    std::vector<int64_t> rcoord_;
-    std::vector<int64_t> rslength_;
-
-    std::vector<MumRec> mums_;
-    std::vector<int64_t> mum_start_;
-    std::vector<uint8_t> mum_fwd_;
+    RegionPool rp_;
+    MumPool mp_;
+    std::vector<MumRec>& mums_ = mp_.mums;
+    std::vector<int64_t>& mum_start_ = mp_.start;
+    std::vector<uint8_t>& mum_fwd_ = mp_.fwd;
     std::vector<int> all_mums_;       // this->mums in push order (ids into mums_)
     std::vector<int> final_mums_;
 
@@ -154,8 +176,7 @@ private:
 
     std::vector<ClusterRec> clusters_;
     std::unordered_map<int64_t, int> minsize_cache_[2];
-    std::vector<int64_t> scratch_st_;
-    std::vector<uint8_t> scratch_fw_;
+    int threads_ = 1;
     AlignStats stats_;
     std::vector<std::pair<int64_t, int64_t>> trace_;
     bool trace_on_ = false;

@@ -1,5 +1,7 @@
 #include "result.h"
 #include <cstring>
+#include <cstdlib>
+#include <thread>
 
 namespace pb200 {
 thread_local std::string g_last_error;
@@ -27,8 +29,19 @@ pb200_result* make_result(const Aligner& a) {
     r->stats = { (double)s.anchors, (double)s.regions_searched, (double)s.spec_regions, (double)s.replay_misses,
                  (double)s.spec_levels, (double)s.windows_searched, (double)s.candidates, (double)s.slow_queue_iters,
                  s.t_anchor_search, s.t_anchor_host, s.t_spec_search, s.t_spec_host, s.t_replay, s.t_replay_search,
-                 s.t_lcb, s.t_total };
+                 s.t_lcb, s.t_total, (double)s.host_threads };
     return r;
+}
+
+int default_host_threads() {
+    if (const char* e = getenv("PB200_HOST_THREADS")) { int v = atoi(e); return v < 1 ? 1 : v; }
+    int hw = (int)std::thread::hardware_concurrency();
+    if (hw < 1) hw = 1;
+    int ranks = 1;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) { int v = atoi(e); if (v > 0) ranks = v; }
+    int t = hw / ranks;
+    if (t > 32) t = 32;
+    return t < 1 ? 1 : t;
 }
 
 AlignParams to_align_params(const pb200_params* p) {
@@ -77,7 +90,7 @@ int pb200_result_stats(const pb200_result* r, double* values, int cap) {
 }
 const char* pb200_stats_names(void) {
     return "anchors,regions_searched,spec_regions,replay_misses,spec_levels,windows_searched,candidates,slow_queue_iters,"
-           "t_anchor_search,t_anchor_host,t_spec_search,t_spec_host,t_replay,t_replay_search,t_lcb,t_total";
+           "t_anchor_search,t_anchor_host,t_spec_search,t_spec_host,t_replay,t_replay_search,t_lcb,t_total,host_threads";
 }
 void pb200_result_free(pb200_result* r) { delete r; }
 int pb200_minsize(const char* expr, int64_t slength) { return pb200::MinSizeExpr(expr)(slength); }

@@ -65,6 +65,22 @@ def main():
             json.dump(dump_to_json(r["dump"]), open(os.path.join(G, name + ".json"), "w"))
             summary[name] = dict(mums=len(r["dump"]["mums"]), clusters=len(r["dump"]["clusters"]), windows=len(r["cands"]),
                                  rev=sum(1 for m in r["dump"]["mums"] if any(not x[2] for x in m[2])))
+    # MUMi mode (calcmumi=1)
+    mumi = {}
+    with tempfile.TemporaryDirectory() as td:
+        mumi["c1a"] = runner.run_ref_mumi(os.path.join(G, "mers", "England1.fna"), [os.path.join(G, "mers", q + ".fna") for q in C1A],
+                                          os.path.join(td, "m1"))
+        for name in ("rearr_60k", "pop_30k_x12", "indep_20k"):
+            g, kw = synth_cases()[name]
+            ref, qs = synth.write_dataset(os.path.join(td, name + "_d"), g)
+            mumi[name] = runner.run_ref_mumi(ref, qs, os.path.join(td, name))
+        # length-ratio rule (src/parsnp.cpp:2074): a query much shorter than the reference gets distance 1
+        g = synth.g_indep(40000, 2, 0.02, 17)
+        g[2] = g[2][:20000].copy()
+        ref, qs = synth.write_dataset(os.path.join(td, "ratio_d"), g)
+        mumi["ratio_40k"] = runner.run_ref_mumi(ref, qs, os.path.join(td, "ratio"))
+    json.dump(mumi, open(os.path.join(G, "mumi.json"), "w"), indent=1)
+    summary["mumi"] = {k: len(v) for k, v in mumi.items()}
     json.dump(summary, open(os.path.join(G, "summary.json"), "w"), indent=1)
     print(json.dumps(summary, indent=1)[:2000])
 

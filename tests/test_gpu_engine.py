@@ -221,3 +221,20 @@ def test_full_size_properties():
             assert np.array_equal(a, b)
     lcb = res["cluster_type"] == 1
     assert res["cluster_length"][lcb].sum() == ln.sum()
+
+
+@pytest.mark.parametrize("name", ["c1a", "rearr_60k", "pop_30k_x12", "indep_20k", "ratio_40k"])
+def test_mumi_matches_reference(name):
+    """calcmumi=1 mode (Aligner::setMumi): the distances parsnp_core writes to all.mumi, to the printed digit"""
+    import json
+    from tests.conftest import GOLDEN
+    gold = json.load(open(os.path.join(GOLDEN, "mumi.json")))[name]
+    if name == "ratio_40k":
+        g = synth.g_indep(40000, 2, 0.02, 17)
+        g[2] = g[2][:20000].copy()
+    else:
+        g, kw, _ = golden_case(name)
+    G = api.Genomes(g)
+    got = ["%f" % v for v in G.mumi()]
+    G.close()
+    assert got == gold
