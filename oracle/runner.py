@@ -115,3 +115,54 @@ def run_ref_mumi(ref, queries, workdir, **kw):
                 i, v = line.strip().split(":")
                 vals[int(i)] = v
     return [vals[i + 1] for i in range(len(queries))]
+
+
+def mumi_zero_init(genomes, p=15000000):
+    """Aligner::setMumi (src/parsnp.cpp:1869-2115) re-run through the REAL csgmum (oracle/_ref/libcsgmum_ref.so) with the
+    emission loop restated literally and MasterRC[].UP zero-initialised.  The binary leaves MasterRC[].UP uninitialised
+    (src/parsnp.cpp:1996-2001, App. B #1); from the second query on it holds stale heap data, which changes the printed
+    value whenever a reverse-strand match wins - so for inputs with inversions the binary's all.mumi is not a function of
+    its inputs, and this well-defined variant is the oracle.  -> list of '%f' strings."""
+    import ctypes as C
+    import numpy as np
+    lib = C.CDLL(os.path.join(HERE, "_ref", "libcsgmum_ref.so"))
+    lib.ref_index_build.restype = C.c_void_p
+    lib.ref_index_build.argtypes = [C.c_char_p, C.c_long, C.c_double]
+    lib.ref_index_free.argtypes = [C.c_void_p]
+    lib.ref_find_um.argtypes = [C.c_void_p, C.c_char_p, C.c_long, C.c_void_p, C.c_void_p]
+    lib.ref_intersect_um.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.ref_merge_master.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    comp = np.zeros(256, np.uint8)
+    for a, b in zip(b"ACGTN", b"TGCAN"):
+        comp[a] = b
+    L0 = len(genomes[0])
+    n = min(p, L0)
+    R = genomes[0][:n].tobytes()
+    ix = lib.ref_index_build(R, n, 2.0)
+    out = []
+    for Q in genomes[1:]:
+        rc = comp[Q[::-1]]
+        M = np.zeros(2 * n, np.int32); M[1::2] = n
+        MR = M.copy(); P = np.zeros(2 * n, np.int32); PR = np.zeros(2 * n, np.int32)
+        sp = np.zeros(n, np.uint64); tmp = np.zeros(n, np.uint64); fw = np.ones(n, np.int8)
+        lib.ref_find_um(ix, Q.tobytes(), len(Q), sp.ctypes.data, P.ctypes.data)
+        lib.ref_find_um(ix, rc.tobytes(), len(Q), tmp.ctypes.data, PR.ctypes.data)
+        lib.ref_intersect_um(ix, M.ctypes.data, P.ctypes.data, n, sp.ctypes.data)
+        lib.ref_intersect_um(ix, MR.ctypes.data, PR.ctypes.data, n, tmp.ctypes.data)
+        lib.ref_merge_master(M.ctypes.data, MR.ctypes.data, n, sp.ctypes.data, fw.ctypes.data, tmp.ctypes.data)
+        UP = M[0::2].astype(np.int64); EP = M[1::2].astype(np.int64)
+        covered = np.zeros(2 * n + 16, np.int8)
+        m_ep = 0
+        for k in range(n):                                  # src/parsnp.cpp:2031-2066
+            if EP[k] > m_ep and UP[k] < EP[k] and EP[k] - k < n:
+                m_ep = EP[k]
+                if EP[k] - k >= 15:
+                    covered[k:EP[k]] = 1
+        total = int(covered.sum())
+        ratio = np.float32(L0) / np.float32(len(Q))
+        if ratio > 1.3 or ratio < 0.7:
+            total = 0
+        total = min(total, n)
+        out.append("%f" % (1.0 - float(np.float32(total) / np.float32(n))))
+    lib.ref_index_free(ix)
+    return out
