@@ -340,20 +340,34 @@ void Aligner::set_initial_clusters() {
     accept_candidates(rstart(whole), rend(whole), rp_.slen[whole], cache_lookup(whole), truth_.layout, mp_, found, false, trace_on_);
     all_mums_ = found;
     stats_.anchors = (int64_t)found.size();
-    std::vector<int64_t> lS(n_), lE(n_), rS(n_), rE(n_);
+    // determineRegion of every anchor: mumlayout is final here (all anchors placed), so the scans are independent and run
+    // in parallel over blocks of anchors; the push rules (src/parsnp.cpp:2153-2172) are then applied in order
+    const size_t B = 2048;
+    std::vector<int64_t> buf(4 * B * (size_t)n_);
+    std::vector<int64_t> sl(2 * B);
+    std::vector<int64_t> prevS(n_), prevE(n_);
     bool have_r = false;
-    for (size_t i = 0; i < found.size(); ++i) {
-        const MumRec& m = mums_[found[i]];
-        const int64_t* ms = &mum_start_[m.off];
-        int64_t lsl = det_region(truth_.layout, len_, n_, ms, m.length, true, lS.data(), lE.data());
-        bool l_eq_r = have_r && std::memcmp(lS.data(), rS.data(), sizeof(int64_t) * n_) == 0 &&
-                      std::memcmp(lE.data(), rE.data(), sizeof(int64_t) * n_) == 0;
-        if (lsl > prm_.q && (i == 0 || !l_eq_r)) initial_regions_.push_back(rp_.add(lS.data(), lE.data()));
-        int64_t rsl = det_region(truth_.layout, len_, n_, ms, m.length, false, rS.data(), rE.data());
-        have_r = true;
-        bool r_eq_l = std::memcmp(lS.data(), rS.data(), sizeof(int64_t) * n_) == 0 &&
-                      std::memcmp(lE.data(), rE.data(), sizeof(int64_t) * n_) == 0;
-        if (rsl > prm_.q && !r_eq_l) initial_regions_.push_back(rp_.add(rS.data(), rE.data()));
+    for (size_t b0 = 0; b0 < found.size(); b0 += B) {
+        const size_t bn = std::min(B, found.size() - b0);
+#pragma omp parallel for schedule(static) num_threads(threads_) if (threads_ > 1 && bn > 64)
+        for (long x = 0; x < (long)bn; ++x) {
+            const MumRec& m = mums_[found[b0 + x]];
+            const int64_t* ms = &mum_start_[m.off];
+            int64_t* p = &buf[(size_t)x * 4 * n_];
+            sl[2 * x] = det_region(truth_.layout, len_, n_, ms, m.length, true, p, p + n_);
+            sl[2 * x + 1] = det_region(truth_.layout, len_, n_, ms, m.length, false, p + 2 * n_, p + 3 * n_);
+        }
+        for (size_t x = 0; x < bn; ++x) {
+            const size_t i = b0 + x;
+            const int64_t* lS = &buf[x * 4 * n_]; const int64_t* lE = lS + n_; const int64_t* rS = lE + n_; const int64_t* rE = rS + n_;
+            bool l_eq_r = have_r && std::memcmp(lS, prevS.data(), sizeof(int64_t) * n_) == 0 && std::memcmp(lE, prevE.data(), sizeof(int64_t) * n_) == 0;
+            if (sl[2 * x] > prm_.q && (i == 0 || !l_eq_r)) initial_regions_.push_back(rp_.add(lS, lE));
+            have_r = true;
+            bool r_eq_l = std::memcmp(lS, rS, sizeof(int64_t) * n_) == 0 && std::memcmp(lE, rE, sizeof(int64_t) * n_) == 0;
+            if (sl[2 * x + 1] > prm_.q && !r_eq_l) initial_regions_.push_back(rp_.add(rS, rE));
+            std::memcpy(prevS.data(), rS, sizeof(int64_t) * n_);
+            std::memcpy(prevE.data(), rE, sizeof(int64_t) * n_);
+        }
     }
     stats_.t_anchor_host = now_s() - t1;
 }

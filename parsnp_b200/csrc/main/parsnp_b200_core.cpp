@@ -1,0 +1,193 @@
+// parsnp_b200_core <ini> - the process boundary of parsnp_core (src/parsnp.cpp:2792-3299) on top of libparsnp_b200.so.
+//
+// Same argv (-h, -v, ini path), same ini keys and FASTA ingest rules, same exit codes (0 also for "NO MUMS FOUND", 1 for a
+// missing ini / reference).  Implemented: calcmumi=1 -> <outdir>/all.mumi;  otherwise the MUM + LCB path ->
+// <outdir>/parsnpAligner.log (MUMS FOUND / NO MUMS FOUND + the statistics block the Python driver parses, parsnp:1530-1536)
+// and <outdir>/parsnpAligner.mums (MUM and LCB coordinates).  NOT yet: parsnpAligner.xmfa (libMUSCLE alignment of the
+// inter-MUM regions).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <string>
+#include <vector>
+#include "../../../include/parsnp_b200.h"
+#include "../host/ingest.h"
+
+using namespace std;
+
+static string basename_of(const string& p) {       // src/parsnp.cpp:2925-2931
+    size_t loc = p.rfind('/');
+    return loc == string::npos ? p : p.substr(loc + 1);
+}
+
+int main(int argc, char** argv) {
+    bool help = false, version = false;
+    for (int i = 0; i < argc; i++)
+        if (argv[i][0] == '-') { if (argv[i][1] == 'h') help = true; else if (argv[i][1] == 'v') version = true; }
+    if (help) {
+        cout << "parsnp options:" << endl << "   -h <display this message>" << endl << "   -v <display the version>" << endl
+             << "   <parameter file with options>" << endl;
+        return 0;
+    }
+    if (version) { cout << "Parsnp v1.0.1 (" << pb200_version() << ")" << endl; return 0; }
+    if (argc < 2) { cout << "ERROR: No parameter file specified!" << endl; return 1; }
+    pb200::IniFile ini;
+    ini.read(argv[1]);
+    pb200_params prm;
+    pb200_params_default(&prm);
+    prm.c = ini.get_i("LCB", "c");
+    prm.d = ini.get_i("LCB", "d");
+    prm.diagdiff = (float)ini.get_f("LCB", "diagdiff");
+    prm.q = ini.get_i("LCB", "q");
+    prm.p = ini.get_i("LCB", "p");
+    const string anchors = ini.get("MUM", "anchors"), mums = ini.get("MUM", "mums");
+    prm.anchors = anchors.c_str();
+    prm.mums = mums.c_str();
+    prm.anchors_only = ini.get_b("MUM", "anchorsonly");
+    prm.filter = ini.get_i("MUM", "filter");
+    const bool calc_mumi = ini.get_b("MUM", "calcmumi");
+    const string outdir = ini.get("Output", "outdir", "output");
+    const bool reverse_ref = ini.get_b("Reference", "reverse");
+    const int qfiles = (int)ini.num_values("Query") / 2;
+
+    vector<pb200::IngestedGenome> G((size_t)qfiles + 1);
+    vector<string> files, names;
+    for (int i = 0; i <= qfiles; i++) {
+        string path;
+        bool rev;
+        if (i == 0) { path = ini.get("Reference", "file"); rev = reverse_ref; }
+        else {
+            char b[64];
+            snprintf(b, sizeof b, "file%d", i); path = ini.get("Query", b);
+            snprintf(b, sizeof b, "reverse%d", i); rev = ini.get_b("Query", b);
+        }
+        if (!pb200::ingest_fasta(path, i == 0, prm.d, rev, G[i])) {
+            if (i == 0) cout << " Cannot open reference file ! " << endl;
+            else cout << " Cannot open query file: " << path << endl;
+            return 1;
+        }
+        files.push_back(path);
+        names.push_back(basename_of(path));
+        const double sz = (double)G[i].text.size();
+        cout << names.back() << ",Len:" << G[i].text.size() << ",GC:" << ((float(G[i].g) + float(G[i].c)) / float(sz - G[i].n)) * 100 << endl;
+    }
+    const int n = qfiles + 1;
+    vector<const uint8_t*> seqs;
+    vector<int64_t> lens;
+    for (auto& g : G) { seqs.push_back((const uint8_t*)g.text.data()); lens.push_back((int64_t)g.text.size()); }
+    int device = 0;
+    if (const char* e = getenv("PB200_DEVICE")) device = atoi(e);
+
+    pb200_genomes* dev = nullptr;
+    int rc = pb200_genomes_create(device, n, seqs.data(), lens.data(), &dev);
+    if (rc != 0) { cerr << "parsnp_b200_core: " << pb200_last_error() << endl; return 1; }
+
+    if (calc_mumi) {                                        // src/parsnp.cpp:1964-2080
+        cerr << "Calculating mumi distances.." << endl;
+        vector<double> v((size_t)max(qfiles, 1));
+        rc = pb200_mumi(dev, &prm, v.data());
+        if (rc != 0) { cerr << "parsnp_b200_core: " << pb200_last_error() << endl; return 1; }
+        FILE* f = fopen((outdir + "/all.mumi").c_str(), "w");
+        if (!f) { cerr << "parsnp_b200_core: cannot write " << outdir << "/all.mumi" << endl; return 1; }
+        for (int i = 0; i < qfiles; i++) fprintf(f, "%d:%f\n", i + 1, v[i]);
+        fclose(f);
+        pb200_genomes_free(dev);
+        return 0;
+    }
+
+    cerr << "Searching for initial MUM anchors..." << endl;
+    pb200_result* res = nullptr;
+    rc = pb200_align_resident(dev, &prm, &res);
+    const string logpath = outdir + "/parsnpAligner.log";
+    if (rc == PB200_ERR_NO_MUMS) {                          // src/parsnp.cpp:3223-3229
+        ofstream mfile(logpath.c_str());
+        mfile << "NO MUMS FOUND" << endl;
+        return 0;
+    }
+    if (rc != 0) { cerr << "parsnp_b200_core: " << pb200_last_error() << endl; return 1; }
+    const int64_t M = pb200_result_num_mums(res), K = pb200_result_num_clusters(res);
+    vector<int64_t> mlen(M), msl(M), mst((size_t)M * n), men((size_t)M * n);
+    vector<uint8_t> mfw((size_t)M * n);
+    pb200_result_mums(res, mlen.data(), msl.data(), mst.data(), men.data(), mfw.data());
+    vector<int32_t> ctype(K);
+    vector<int64_t> cnm(K), clen(K), cst((size_t)K * n), cen((size_t)K * n);
+    pb200_result_clusters(res, ctype.data(), cnm.data(), clen.data(), cst.data(), cen.data());
+    double stats[32]; int ns = pb200_result_stats(res, stats, 32);
+    const long anchors_found = ns > 0 ? (long)stats[0] : 0;
+
+    // MUM / LCB coordinates (same record layout as the oracle dump hook, oracle/build_ref.py H1)
+    {
+        FILE* f = fopen((outdir + "/parsnpAligner.mums").c_str(), "w");
+        if (f) {
+            fprintf(f, "N %d\n", n);
+            for (int64_t i = 0; i < M; i++) {
+                fprintf(f, "M %ld %ld", (long)mlen[i], (long)msl[i]);
+                for (int k = 0; k < n; k++) fprintf(f, " %ld:%ld:%d", (long)mst[i * n + k], (long)men[i * n + k], (int)mfw[i * n + k]);
+                fprintf(f, "\n");
+            }
+            for (int64_t i = 0; i < K; i++) {
+                fprintf(f, "C %d %ld %ld", ctype[i], (long)cnm[i], (long)clen[i]);
+                for (int k = 0; k < n; k++) fprintf(f, " %ld:%ld", (long)cst[i * n + k], (long)cen[i * n + k]);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
+    // statistics block of parsnpAligner.log (src/parsnp.cpp:1082-1190); elapsed-time lines carry this run's own timings
+    {
+        ofstream log(logpath.c_str());
+        log << "Number of sequences analyzed:" << setiosflags(ios::fixed) << setprecision(1) << setw(10) << n << endl << endl;
+        for (int i = 0; i < n; i++) {
+            log << "Sequence " << i + 1 << " : " << files[i] << endl;
+            log << names[i] << endl;
+            log << "Length:" << setw(10) << (long)(G[i].text.size() - G[i].padding) << " bps" << endl;
+            log << " GC:" << setw(10) << setiosflags(ios::fixed) << setprecision(1) << (float(G[i].g) + float(G[i].c)) << endl;
+            log << " AT:" << setw(10) << setiosflags(ios::fixed) << setprecision(1) << (float(G[i].a) + float(G[i].t)) << endl;
+        }
+        log << setw(2) << setiosflags(ios::left) << "d value:   " << setw(2) << prm.d << endl;
+        log << setw(2) << "q value:   " << setw(2) << prm.q << endl << endl;
+        int64_t slength = 500000000;
+        for (auto& g : G) slength = min<int64_t>(slength, (int64_t)g.text.size());
+        log << setw(2) << "Mum anchor size:   " << setw(2) << (float)pb200_minsize(prm.anchors, slength) << endl;
+        log << setw(2) << "Number of MUM anchors found:   " << setw(2) << anchors_found << endl;
+        log << setw(2) << "Number of MUMs found:   " << setw(2) << (M >= anchors_found ? M - anchors_found : 0) << endl;
+        log << setw(2) << "Total MUMs found((Anchors+MUMs)-filtered):   " << setw(2) << M << endl << endl;
+        log << setw(2) << "Random MUM length:   " << setw(2) << prm.filter << endl;
+        log << setw(2) << "Minimum Cluster length:   " << setw(2) << prm.c << endl;
+        long ccount = 0;
+        for (int64_t i = 0; i < K; i++) if (ctype[i] && cnm[i] > 0) ccount++;
+        log << setw(2) << "Number of clusters created:   " << setw(2) << ccount << endl;
+        if (K == 0) log << setw(2) << "Number of clusters created:   " << setw(2) << "NONE" << endl;
+        if (ccount) log << setw(2) << "Average number of MUMs per cluster:   " << setw(2) << M / ccount << endl;
+        // LCB coverage per sequence: |last MUM end - first MUM start| summed over LCBs (forward) as at src/parsnp.cpp:1141-1160;
+        // the flat result keeps per-LCB start/end, which equal first-MUM start / last-MUM end
+        vector<long> coverage(n, 0);
+        long avg = 0, totcoverage = 0, totsize = 0;
+        for (int64_t c = 0; c < K; c++) {
+            if (!ctype[c] || cnm[c] <= 0) continue;
+            for (int i = 0; i < n; i++) {
+                long span = labs((long)(cen[c * n + i] - cst[c * n + i]));
+                coverage[i] += span;
+                if (i == 0) avg += span;
+            }
+        }
+        if (ccount) log << setw(2) << "Average cluster length:   " << avg / ccount << " bps" << endl;
+        for (int i = 0; i < n; i++) {
+            float percent = (float)coverage[i] / ((float)(G[i].g + G[i].c) + (float)(G[i].a + G[i].t));
+            log << setw(2) << "Cluster coverage in sequence " << i + 1 << ":   " << setiosflags(ios::fixed) << setprecision(1) << 100.00 * percent << "%" << endl;
+            totcoverage += coverage[i];
+            totsize += (long)(G[i].text.size() - G[i].padding);
+        }
+        float percent = (float)totcoverage / (float)totsize;
+        log << setw(2) << "Total coverage among all sequences:   " << setiosflags(ios::fixed) << setprecision(1) << 100.00 * percent << "%" << endl << endl;
+        log << setw(2) << " Total running time:   " << (ns > 15 ? stats[15] : 0.0) << "s " << endl;
+    }
+    pb200_result_free(res);
+    pb200_genomes_free(dev);
+    cerr << "Parsnp: Finished core genome alignment (MUM + LCB path; XMFA writer not built yet)" << endl;
+    return 0;
+}
