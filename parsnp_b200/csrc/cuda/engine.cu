@@ -74,7 +74,7 @@ public:
     }
     ~CudaEngine() override {
         cudaSetDevice(device_);
-        if (st_) cudaStreamDestroy(st_);
+        if (st_) { cudaStreamSynchronize(st_); cudaStreamDestroy(st_); }
     }
 
     void set_genomes(int n, const uint8_t* const* seq, const int64_t* len) override {

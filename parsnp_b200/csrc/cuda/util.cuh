@@ -26,7 +26,7 @@ template <class T>
 class DevBuf {
 public:
     DevBuf() {}
-    ~DevBuf() { if (p_) cudaFree(p_); }
+    ~DevBuf() { if (p_) cudaFreeAsync(p_, 0); }     // stream-ordered free back into the pool: no device-wide synchronisation
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     T* get() const { return p_; }
