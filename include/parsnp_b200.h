@@ -112,6 +112,9 @@ int pb200_result_mums(const pb200_result* r, int64_t* length, int64_t* slength, 
 int64_t pb200_result_num_clusters(const pb200_result* r);
 /* type[c] (1 = LCB, 0 = inter-cluster record), nmums[c], length[c], start[c*n], end[c*n]; order = this->clusters */
 int pb200_result_clusters(const pb200_result* r, int32_t* type, int64_t* nmums, int64_t* length, int64_t* start, int64_t* end);
+/* MUMs of every cluster (Cluster::mums): off[c]..off[c+1] index into idx[], idx = positions in the MUM list; returns the
+ * total number of indices (call with NULLs first). Inter-cluster records (type 0) have none. */
+int pb200_result_cluster_mums(const pb200_result* r, int64_t* off, int64_t* idx);
 /* searched windows in order (PB200_FLAG_TRACE_WINDOWS): pairs (ref_start, ref_len) */
 int64_t pb200_result_num_trace(const pb200_result* r);
 int pb200_result_trace(const pb200_result* r, int64_t* pairs);

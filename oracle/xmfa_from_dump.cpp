@@ -1,0 +1,57 @@
+// TEST-ONLY tool: writes the XMFA from an oracle MUM/LCB dump (hook H1 of oracle/build_ref.py) through the product's XMFA
+// writer (parsnp_b200/csrc/main/xmfa.cpp), so the writer can be checked against the reference's XMFA md5 without a GPU.
+//   xmfa_from_dump <ini> <dump.txt> <out.xmfa>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include "../parsnp_b200/csrc/host/ingest.h"
+#include "../parsnp_b200/csrc/main/xmfa.h"
+using namespace std;
+int main(int argc, char** argv) {
+    if (argc < 4) return 2;
+    pb200::IniFile ini;
+    ini.read(argv[1]);
+    const int d = ini.get_i("LCB", "d");
+    const int qfiles = (int)ini.num_values("Query") / 2;
+    vector<pb200::IngestedGenome> G((size_t)qfiles + 1);
+    pb200::XmfaInput xi;
+    xi.n = qfiles + 1;
+    for (int i = 0; i <= qfiles; i++) {
+        string path; bool rev;
+        char b[64];
+        if (i == 0) { path = ini.get("Reference", "file"); rev = ini.get_b("Reference", "reverse"); }
+        else { snprintf(b, sizeof b, "file%d", i); path = ini.get("Query", b); snprintf(b, sizeof b, "reverse%d", i); rev = ini.get_b("Query", b); }
+        if (!pb200::ingest_fasta(path, i == 0, d, rev, G[i])) return 3;
+        size_t loc = path.rfind('/');
+        xi.fasta_names.push_back(loc == string::npos ? path : path.substr(loc + 1));
+    }
+    for (auto& g : G) {
+        xi.genomes.push_back(&g.text); xi.headers.push_back(g.header); xi.genome_sizes.push_back((int64_t)g.text.size() - g.padding);
+        map<int, string> p2h; p2h[1] = "s1";
+        for (size_t k = 0; k + 1 < g.contig_ends.size(); k++) p2h[(int)g.contig_ends[k]] = "s" + to_string(k + 2);
+        xi.pos2hdr.push_back(p2h);
+    }
+    xi.c = ini.get_i("LCB", "c"); xi.doalign = ini.get_i("LCB", "doalign"); xi.cores = 1;
+    ifstream f(argv[2]);
+    string line;
+    int64_t nm = 0;
+    xi.cmum_off.push_back(0);
+    while (getline(f, line)) {
+        istringstream is(line);
+        string tag; is >> tag;
+        if (tag == "M") {
+            long len, sl; is >> len >> sl; xi.mlen.push_back(len);
+            string tok;
+            while (is >> tok) { long a, b; int fw; sscanf(tok.c_str(), "%ld:%ld:%d", &a, &b, &fw); xi.mstart.push_back(a); xi.mend.push_back(b); xi.mfwd.push_back((uint8_t)fw); }
+        } else if (tag == "C") {
+            int type; long cnt, len; is >> type >> cnt >> len; xi.ctype.push_back(type);
+            string tok;
+            while (is >> tok) { long a, b; sscanf(tok.c_str(), "%ld:%ld", &a, &b); xi.cstart.push_back(a); xi.cend.push_back(b); }
+            if (type == 1) for (long k = 0; k < cnt; k++) xi.cmum_idx.push_back(nm++);      // LCBs own consecutive runs of the sorted MUM list
+            xi.cmum_off.push_back((int64_t)xi.cmum_idx.size());
+        }
+    }
+    return pb200::write_xmfa(xi, argv[3]) ? 0 : 4;
+}

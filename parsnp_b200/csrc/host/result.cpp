@@ -19,7 +19,10 @@ pb200_result* make_result(const Aligner& a) {
         const int64_t* s = a.mum_start(i); const uint8_t* f = a.mum_fwd(i);
         for (int k = 0; k < n; ++k) { r->m_start[i * n + k] = s[k]; r->m_end[i * n + k] = s[k] + m.length; r->m_fwd[i * n + k] = f[k]; }
     }
+    r->c_mum_off.push_back(0);
     for (const ClusterRec& c : a.clusters()) {
+        for (int mi : c.mums) r->c_mum_idx.push_back(mi);
+        r->c_mum_off.push_back((int64_t)r->c_mum_idx.size());
         r->c_type.push_back(c.type); r->c_nmums.push_back(c.type == 1 ? (int64_t)c.mums.size() : 2); r->c_length.push_back(c.length);
         r->c_start.insert(r->c_start.end(), c.start.begin(), c.start.end());
         r->c_end.insert(r->c_end.end(), c.end.begin(), c.end.end());
@@ -80,6 +83,11 @@ int pb200_result_clusters(const pb200_result* r, int32_t* type, int64_t* nmums, 
     if (start) std::memcpy(start, r->c_start.data(), r->c_start.size() * 8);
     if (end) std::memcpy(end, r->c_end.data(), r->c_end.size() * 8);
     return 0;
+}
+int pb200_result_cluster_mums(const pb200_result* r, int64_t* off, int64_t* idx) {
+    if (off) std::memcpy(off, r->c_mum_off.data(), r->c_mum_off.size() * 8);
+    if (idx) std::memcpy(idx, r->c_mum_idx.data(), r->c_mum_idx.size() * 8);
+    return (int)r->c_mum_idx.size();
 }
 int64_t pb200_result_num_trace(const pb200_result* r) { return (int64_t)r->trace.size() / 2; }
 int pb200_result_trace(const pb200_result* r, int64_t* pairs) { std::memcpy(pairs, r->trace.data(), r->trace.size() * 8); return 0; }

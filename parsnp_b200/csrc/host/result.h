@@ -12,6 +12,7 @@ struct pb200_result {
     std::vector<uint8_t> m_fwd;
     std::vector<int32_t> c_type;
     std::vector<int64_t> c_nmums, c_length, c_start, c_end;
+    std::vector<int64_t> c_mum_off, c_mum_idx;      // MUM indices (into the MUM list) of every cluster
     std::vector<int64_t> trace;
     std::vector<double> stats;
 };

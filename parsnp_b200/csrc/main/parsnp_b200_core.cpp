@@ -1,10 +1,10 @@
 // parsnp_b200_core <ini> - the process boundary of parsnp_core (src/parsnp.cpp:2792-3299) on top of libparsnp_b200.so.
 //
 // Same argv (-h, -v, ini path), same ini keys and FASTA ingest rules, same exit codes (0 also for "NO MUMS FOUND", 1 for a
-// missing ini / reference).  Implemented: calcmumi=1 -> <outdir>/all.mumi;  otherwise the MUM + LCB path ->
-// <outdir>/parsnpAligner.log (MUMS FOUND / NO MUMS FOUND + the statistics block the Python driver parses, parsnp:1530-1536)
-// and <outdir>/parsnpAligner.mums (MUM and LCB coordinates).  NOT yet: parsnpAligner.xmfa (libMUSCLE alignment of the
-// inter-MUM regions).
+// missing ini / reference).  calcmumi=1 -> <outdir>/all.mumi;  otherwise the MUM + LCB path -> <outdir>/parsnpAligner.xmfa
+// (inter-MUM regions aligned with the reference's vendored libMUSCLE, linked unchanged), <outdir>/parsnpAligner.log
+// (MUMS FOUND / NO MUMS FOUND, then the statistics block the Python driver parses, parsnp:1530-1536) and
+// <outdir>/parsnpAligner.mums (MUM and LCB coordinates).  Not implemented: recombfilter=1 (blocks/), unaligned=1.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -16,6 +16,7 @@
 #include <vector>
 #include "../../../include/parsnp_b200.h"
 #include "../host/ingest.h"
+#include "xmfa.h"
 
 using namespace std;
 
@@ -137,6 +138,33 @@ int main(int argc, char** argv) {
             fclose(f);
         }
     }
+    // XMFA (Aligner::writeOutput, src/parsnp.cpp:505-1079)
+    {
+        pb200::XmfaInput xi;
+        xi.n = n;
+        for (auto& g : G) {
+            xi.genomes.push_back(&g.text);
+            xi.headers.push_back(g.header);
+            xi.genome_sizes.push_back((int64_t)g.text.size() - g.padding);
+            std::map<int, std::string> p2h;
+            p2h[1] = "s1";                                  // src/parsnp.cpp:2921,2947
+            for (size_t k = 0; k + 1 < g.contig_ends.size(); k++) p2h[(int)g.contig_ends[k]] = "s" + to_string(k + 2);   // 3120-3122
+            xi.pos2hdr.push_back(p2h);
+        }
+        xi.fasta_names = names;
+        xi.c = prm.c;
+        xi.doalign = ini.get_i("LCB", "doalign");
+        xi.cores = max(1, ini.get_i("LCB", "cores"));
+        if (xi.cores > 64) xi.cores = 64;                   // libMUSCLE thread-local storage holds 64 slots (threadstorage.h)
+        xi.ctype = ctype; xi.cstart = cst; xi.cend = cen;
+        xi.cmum_off.resize(K + 1);
+        const int tot = pb200_result_cluster_mums(res, nullptr, nullptr);
+        xi.cmum_idx.resize((size_t)max(tot, 1));
+        pb200_result_cluster_mums(res, xi.cmum_off.data(), xi.cmum_idx.data());
+        xi.mlen = mlen; xi.mstart = mst; xi.mend = men; xi.mfwd = mfw;
+        if (!pb200::muscle_available()) cerr << "parsnp_b200_core: built without libMUSCLE - no XMFA written" << endl;
+        else if (!pb200::write_xmfa(xi, outdir + "/parsnpAligner.xmfa")) { cerr << "parsnp_b200_core: XMFA writer failed" << endl; return 1; }
+    }
     // statistics block of parsnpAligner.log (src/parsnp.cpp:1082-1190); elapsed-time lines carry this run's own timings
     {
         ofstream log(logpath.c_str());
@@ -188,6 +216,6 @@ int main(int argc, char** argv) {
     }
     pb200_result_free(res);
     pb200_genomes_free(dev);
-    cerr << "Parsnp: Finished core genome alignment (MUM + LCB path; XMFA writer not built yet)" << endl;
+    cerr << "Parsnp: Finished core genome alignment" << endl;
     return 0;
 }

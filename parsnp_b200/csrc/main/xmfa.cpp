@@ -1,0 +1,169 @@
+#include "xmfa.h"
+#include <algorithm>
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+
+namespace pb200 {
+
+namespace {
+std::string reversec(const std::string& s) {           // Aligner::reversec (src/parsnp.cpp:1294-1393) on the ingest alphabet
+    std::string g;
+    g.reserve(s.size());
+    for (char ch : s) {
+        switch (toupper((unsigned char)ch)) {
+            case 'A': g.push_back('T'); break;
+            case 'G': g.push_back('C'); break;
+            case 'C': g.push_back('G'); break;
+            case 'T': g.push_back('A'); break;
+            default: g.push_back('N'); break;
+        }
+    }
+    std::reverse(g.begin(), g.end());
+    return g;
+}
+std::string lower(std::string s) { for (auto& c : s) c = (char)tolower((unsigned char)c); return s; }
+std::string upper(std::string s) { for (auto& c : s) c = (char)toupper((unsigned char)c); return s; }
+std::string sub(const std::string& g, int64_t pos, int64_t count) {     // std::string::substr semantics (count clamps; negative = npos)
+    if (pos < 0 || (size_t)pos > g.size()) return std::string();
+    return g.substr((size_t)pos, count < 0 ? std::string::npos : (size_t)count);
+}
+}  // namespace
+
+bool write_xmfa(const XmfaInput& in, const std::string& path) {
+    const int n = in.n;
+    const int64_t K = (int64_t)in.ctype.size();
+    std::vector<std::vector<std::string>> aln((size_t)K, std::vector<std::string>((size_t)n));
+    auto MS = [&](int64_t m, int i) { return in.mstart[(size_t)m * n + i]; };
+    auto ME = [&](int64_t m, int i) { return in.mend[(size_t)m * n + i]; };
+    auto MF = [&](int64_t m, int i) { return in.mfwd[(size_t)m * n + i] != 0; };
+
+    // ---- alignment assembly per LCB (src/parsnp.cpp:646-919); MUSCLE runs on the inter-MUM regions
+    bool muscle_failed = false;
+#pragma omp parallel for schedule(dynamic) num_threads(in.cores > 0 ? in.cores : 1)
+    for (int64_t z = 0; z < K; z++) {
+        const int64_t m0 = in.cmum_off[z], m1 = in.cmum_off[z + 1];
+        if (!(in.ctype[z] == 1 && m1 > m0 && in.doalign != 0)) continue;
+        const int64_t first = in.cmum_idx[m0];
+        std::vector<std::string>& T = aln[z];
+        for (int64_t t = m0; t < m1; t++) {
+            const int64_t dt = in.cmum_idx[t];
+            const bool has_next = t + 1 < m1;
+            const int64_t nx = has_next ? in.cmum_idx[t + 1] : -1;
+            std::vector<std::string> reg((size_t)n);
+            if (m1 - m0 == 1) {
+                for (int i = 0; i < n; i++) {
+                    std::string s = sub(*in.genomes[i], MS(dt, i), in.mlen[dt]);
+                    T[i].append(lower(MF(first, i) ? s : reversec(s)));
+                }
+            } else if (has_next) {
+                for (int i = 0; i < n; i++) {
+                    if (!MF(first, i)) {
+                        if (i == 0) std::cout << "Error!! MUM in - orientation for ref genome**" << std::endl;
+                        T[i].append(lower(reversec(sub(*in.genomes[i], MS(dt, i), in.mlen[dt]))));
+                        if (MS(dt, i) - ME(nx, i) >= 1) {
+                            std::string s1 = reversec(sub(*in.genomes[i], ME(nx, i), MS(dt, i) - ME(nx, i)));
+                            reg[i] = s1.size() >= 1 ? upper(s1) : std::string();
+                        }
+                    } else {
+                        T[i].append(lower(sub(*in.genomes[i], MS(dt, i), in.mlen[dt])));
+                        std::string s1 = sub(*in.genomes[i], ME(dt, i), MS(nx, i) - ME(dt, i));
+                        reg[i] = s1.size() >= 1 ? upper(s1) : std::string();
+                    }
+                }
+            }
+            if (has_next && in.doalign) {
+                size_t maxl = 0, minl = 1000000;
+                for (int k = 0; k < n; k++) { maxl = std::max(maxl, reg[k].size()); minl = std::min(minl, reg[k].size()); }
+                if (maxl > 1 && minl > 0) {
+                    if (n - 1 <= 0) {
+                        for (int j = 0; j < n; j++) T[j].append(reg[j]);       // total_skipped (0) >= nnum-1 only when nnum == 1
+                    } else {
+                        std::vector<std::string> res;
+                        if (!muscle_align(reg, res)) muscle_failed = true;
+                        for (size_t i = 0; i < res.size() && i < (size_t)n; i++) T[i].append(res[i]);
+                    }
+                } else if (maxl > 0) {
+                    for (int p = 0; p < n; p++) {
+                        if (reg[p].size() > 0) T[p].append(upper(reg[p]));
+                        if (reg[p].size() < maxl) T[p].append(maxl - reg[p].size(), '-');
+                    }
+                }
+            }
+            if (!has_next && m1 - m0 > 1) {
+                for (int i = 0; i < n; i++) {
+                    std::string s = sub(*in.genomes[i], MS(dt, i), in.mlen[dt]);
+                    T[i].append(lower(MF(first, i) ? s : reversec(s)));
+                }
+            }
+        }
+    }
+    if (muscle_failed) return false;
+
+    // ---- XMFA (src/parsnp.cpp:586-598, 921-1071)
+    std::ofstream x(path.c_str());
+    long total_clusters = 0;
+    for (int64_t z = 0; z < K; z++) if (in.ctype[z] == 1) total_clusters++;
+    x << "#FormatVersion Mauve" << std::endl;
+    x << "#SequenceCount " << n << std::endl;
+    for (int z = 0; z < n; z++) {
+        x << "##SequenceIndex " << z + 1 << std::endl;
+        x << "##SequenceFile " << in.fasta_names[z] << std::endl;
+        x << "##SequenceHeader " << in.headers[z] << std::endl;
+        x << "##SequenceLength " << in.genome_sizes[z] << "bp" << std::endl;
+    }
+    x << "#IntervalCount " << total_clusters << std::endl;
+    int prev_end = 0;
+    for (int64_t z = 0; z < K; z++) {
+        const int64_t m0 = in.cmum_off[z], m1 = in.cmum_off[z + 1];
+        std::vector<std::string>& T = aln[z];
+        if (!(in.ctype[z] == 1 && m1 > m0 && in.doalign != 0 && T[0].size() > (size_t)in.c)) continue;
+        std::vector<int64_t> cs(in.cstart.begin() + z * n, in.cstart.begin() + (z + 1) * n);
+        std::vector<int64_t> ce(in.cend.begin() + z * n, in.cend.begin() + (z + 1) * n);
+        const int64_t first = in.cmum_idx[m0], last = in.cmum_idx[m1 - 1];
+        // overlap trim with the previous LCB, reproduced literally (the scan position never advances, src/parsnp.cpp:935-940)
+        const int lcb_start = (int)cs[0] + 1, lcb_end = (int)ce[0];
+        int overlap = std::max(0, prev_end - lcb_start);
+        if (overlap > 0 && !T[0].empty() && T[0][0] != '-') {
+            const int cols_to_trim = overlap;
+            for (int i = 0; i < n; i++) {
+                int cnt = 0;
+                for (size_t pos = 0; pos < T[i].size(); pos++) if (pos < T[0].size() && T[0][pos] != '-') cnt++;
+                cs[i] += cnt;
+                T[i].erase(0, (size_t)cols_to_trim);
+            }
+        }
+        prev_end = lcb_end;
+        if (!(T[0].size() > (size_t)in.c)) continue;
+        char b[16];
+        snprintf(b, sizeof b, "%d", (int)z + 1);
+        for (int i = 0; i < n; i++) {
+            const std::string& s1s = T[i];
+            const bool fwd = MF(first, i);
+            if (fwd) x << "> " << i + 1 << ":" << cs[i] + 1 << "-" << ce[i] << " ";
+            else x << "> " << i + 1 << ":" << MS(last, i) + 1 << "-" << ME(first, i) << " ";
+            bool hit1 = false, hit2 = false;
+            std::string hdr1, lasthdr1;
+            int seqstart = 0, laststart = 0;
+            for (auto it = in.pos2hdr[i].begin(); it != in.pos2hdr[i].end(); ++it) {
+                if (hit1 && cs[i] < it->first) { hit2 = true; hdr1 = lasthdr1; seqstart = laststart; break; }
+                else if (cs[i] >= it->first && !hit2) { hit1 = true; laststart = it->first; lasthdr1 = it->second; continue; }
+                else if (hit1 & hit2) { hdr1 = lasthdr1; seqstart = laststart; break; }
+            }
+            if (hit1 && !hit2) { hdr1 = lasthdr1; seqstart = laststart; }
+            int offset = 0;
+            if (hdr1 == "") { hdr1 = "s1"; offset = -1; }
+            else if (hdr1 != "s1") offset = -1;
+            if (!fwd) x << "- cluster" << b << " " << hdr1 << ":p" << (cs[i] - seqstart) + 1 + in.mlen[first] + offset << std::endl;
+            else x << "+ cluster" << b << " " << hdr1 << ":p" << (cs[i] - seqstart) + 1 + offset << std::endl;
+            const size_t width = 80;
+            size_t k = 0;
+            for (; k + width < s1s.size(); k += width) x << s1s.substr(k, width) << std::endl;
+            x << s1s.substr(k, s1s.size() - k) << std::endl;
+        }
+        x << "=" << std::endl;
+    }
+    return true;
+}
+
+}  // namespace pb200

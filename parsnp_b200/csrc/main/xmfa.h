@@ -1,0 +1,35 @@
+// XMFA writer of parsnp_b200_core: restates Aligner::writeOutput (src/parsnp.cpp:505-1079) on the flat MUM/LCB lists of
+// the C ABI.  MUM columns lower case, inter-MUM regions aligned with the reference's vendored libMUSCLE (upper case),
+// LCB records `> i:start+1-end +/- cluster<z+1> s<contig>:p<pos>` (src/parsnp.cpp:980-1054).
+#pragma once
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace pb200 {
+
+struct XmfaInput {
+    int n = 0;
+    std::vector<const std::string*> genomes;             // ingested texts
+    std::vector<std::string> fasta_names, headers;       // file basenames, first FASTA lines
+    std::vector<int64_t> genome_sizes;                   // text size minus contig padding
+    std::vector<std::map<int, std::string>> pos2hdr;     // contig start -> "s<k>"
+    int c = 21, doalign = 2, cores = 1;
+    // clusters in this->clusters order
+    std::vector<int32_t> ctype;
+    std::vector<int64_t> cstart, cend;                   // [K*n]
+    std::vector<int64_t> cmum_off, cmum_idx;             // per cluster MUM indices
+    // MUM list
+    std::vector<int64_t> mlen, mstart, mend;             // [M], [M*n], [M*n]
+    std::vector<uint8_t> mfwd;                           // [M*n]
+};
+
+// aligns with MUSCLE (reference settings: DNA, 1 iteration, stable, ClustalW weights - src/MuscleInterface.cpp:38-49)
+bool muscle_align(const std::vector<std::string>& seqs, std::vector<std::string>& out);
+bool muscle_available();
+
+// returns false when libMUSCLE is not linked
+bool write_xmfa(const XmfaInput& in, const std::string& path);
+
+}  // namespace pb200

@@ -71,3 +71,62 @@ def test_binary_mumi_mode(tmp_path):
     assert r.returncode == 0, r.stderr
     got = [ln.strip().split(":")[1] for ln in (out / "all.mumi").read_text().splitlines()]
     assert got == json.load(open(os.path.join(GOLDEN, "mumi.json")))["c1a"]
+
+
+def _ref_run(tmp_path, ref, queries, **kw):
+    from oracle import runner
+    r = runner.run_ref(ref, queries, str(tmp_path / "refrun"), dump_exit=False, **kw)
+    return r, os.path.join(str(tmp_path / "refrun"), "dump.txt"), os.path.join(r["outdir"], "parsnpAligner.xmfa"), \
+        os.path.join(str(tmp_path / "refrun"), "ref.ini")
+
+
+def _synthetic(tmp_path, kind):
+    import numpy as np
+    from parsnp_b200 import synth
+    if kind == "rearr":
+        rng = np.random.default_rng(5)
+        g = synth.g_indep(40000, 3, 0.02, 33)
+        g = [g[0]] + [synth.rearrange(x, rng, n_inv=2, inv_len=2500) for x in g[1:]]
+        return synth.write_dataset(str(tmp_path / "data"), g)
+    g = synth.g_indep(30000, 2, 0.03, 8)
+    return synth.write_dataset(str(tmp_path / "data"), g, contigs=3)      # multi-contig: N padding + s<k>:p<pos> headers
+
+
+XTOOL = os.path.join(ROOT, "oracle", "_ref", "xmfa_from_dump")
+
+
+@pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(XTOOL)), reason="oracle/_ref tools not built")
+@pytest.mark.parametrize("kind", ["c1a", "rearr", "contigs"])
+def test_xmfa_writer_matches_reference_bytes(tmp_path, kind):
+    """the product's XMFA writer (csrc/main/xmfa.cpp + libMUSCLE) fed with the reference's own MUM/LCB dump == the reference's
+    parsnpAligner.xmfa, byte for byte (reverse-strand LCBs, multi-contig coordinates, MUSCLE-aligned gaps)"""
+    if kind == "c1a":
+        ref, qs = os.path.join(GOLDEN, "mers", "England1.fna"), [os.path.join(GOLDEN, "mers", q + ".fna") for q in C1A]
+    else:
+        ref, qs = _synthetic(tmp_path, kind)
+    r, dump, xmfa, ini = _ref_run(tmp_path, ref, qs)
+    mine = str(tmp_path / "mine.xmfa")
+    rc = subprocess.run([XTOOL, ini, dump, mine]).returncode
+    assert rc == 0
+    assert open(mine, "rb").read() == open(xmfa, "rb").read()
+    if kind == "c1a":
+        import hashlib
+        assert hashlib.md5(open(mine, "rb").read()).hexdigest() == "5b59e50c5b8c1f79165fc41cfd2a6ac4"     # SURVEY App. C
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["c1a", "rearr", "contigs"])
+def test_binary_xmfa_end_to_end(tmp_path, kind):
+    """parsnp_b200_core <ini> on the GPU == parsnp_core on the CPU: identical parsnpAligner.xmfa"""
+    from oracle import runner
+    if kind == "c1a":
+        ref, qs = os.path.join(GOLDEN, "mers", "England1.fna"), [os.path.join(GOLDEN, "mers", q + ".fna") for q in C1A]
+    else:
+        ref, qs = _synthetic(tmp_path, kind)
+    r, dump, xmfa, _ = _ref_run(tmp_path, ref, qs)
+    out = tmp_path / "mine"
+    out.mkdir()
+    ini = runner.write_ini(str(tmp_path / "mine.ini"), ref, qs, str(out), cores=4)
+    p = subprocess.run([EXE, ini], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=str(tmp_path))
+    assert p.returncode == 0, p.stderr
+    assert (out / "parsnpAligner.xmfa").read_bytes() == open(xmfa, "rb").read()
