@@ -7,15 +7,27 @@
 #include <cstdio>
 #include <stdexcept>
 #include <unordered_set>
-#ifdef _OPENMP
-#include <omp.h>
-#endif
+#include <atomic>
+#include <thread>
 
 namespace pb200 {
 
 namespace {
 inline double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+// Runs fn(chunk) for chunk = 0..nchunks-1 on up to `nthreads` threads (dynamic assignment).  Plain std::thread per phase:
+// a handful of phases per alignment, and no spinning worker pool that could starve a co-scheduled process.
+template <class F>
+void parallel_chunks(int nthreads, long nchunks, F&& fn) {
+    if (nthreads <= 1 || nchunks <= 1) { for (long c = 0; c < nchunks; ++c) fn(c); return; }
+    std::atomic<long> next(0);
+    auto worker = [&]() { for (long c; (c = next.fetch_add(1)) < nchunks;) fn(c); };
+    std::vector<std::thread> pool;
+    const int extra = (int)std::min<long>(nthreads, nchunks) - 1;
+    for (int t = 0; t < extra; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& th : pool) th.join();
 }
 inline uint8_t comp_base(uint8_t c) {          // Aligner::reversec (src/parsnp.cpp:1294-1393) on the ingest alphabet
     switch (c) {
@@ -142,11 +154,29 @@ uint64_t Aligner::coords_hash(const int64_t* p, int count) {
     }
     return h;
 }
+void Aligner::CoordIndex::insert(uint64_t hash, int value) {
+    if ((count + 1) * 2 > h.size()) {                       // grow / rehash at 50 % load
+        std::vector<uint64_t> oh;
+        std::vector<int> ov;
+        oh.swap(h);
+        ov.swap(v);
+        const size_t nsz = oh.empty() ? 1024 : oh.size() * 2;
+        h.assign(nsz, 0);
+        v.assign(nsz, -1);
+        count = 0;
+        for (size_t i = 0; i < oh.size(); ++i) if (ov[i] >= 0) insert(oh[i], ov[i]);
+    }
+    const size_t mask = h.size() - 1;
+    size_t i = (size_t)hash & mask;
+    while (v[i] >= 0) i = (i + 1) & mask;
+    h[i] = hash;
+    v[i] = value;
+    ++count;
+}
 int Aligner::cache_lookup_coords(const int64_t* coords) const {
-    auto range = cache_map_.equal_range(coords_hash(coords, 2 * n_));
-    for (auto it = range.first; it != range.second; ++it)
-        if (std::memcmp(rstart(cache_entries_[it->second].region), coords, sizeof(int64_t) * 2 * n_) == 0) return it->second;
-    return -1;
+    const size_t bytes = sizeof(int64_t) * 2 * n_;
+    return cache_map_.find(coords_hash(coords, 2 * n_),
+                           [&](int e) { return std::memcmp(rstart(cache_entries_[e].region), coords, bytes) == 0; });
 }
 
 int Aligner::minsize_cached(bool anchors, int64_t slength) {
@@ -223,7 +253,7 @@ void Aligner::search_regions(const std::vector<int>& regs, bool anchors) {
             w.minsize = tasks[t].minsize;
             wins_.push_back(w);
         }
-        cache_map_.emplace(coords_hash(rstart(regs[ri]), 2 * n_), (int)cache_entries_.size());
+        cache_map_.insert(coords_hash(rstart(regs[ri]), 2 * n_), (int)cache_entries_.size());
         cache_entries_.push_back(e);
     }
 }
@@ -342,21 +372,23 @@ void Aligner::set_initial_clusters() {
     stats_.anchors = (int64_t)found.size();
     // determineRegion of every anchor: mumlayout is final here (all anchors placed), so the scans are independent and run
     // in parallel over blocks of anchors; the push rules (src/parsnp.cpp:2153-2172) are then applied in order
-    const size_t B = 2048;
-    std::vector<int64_t> buf(4 * B * (size_t)n_);
+    const size_t B = 16384;
+    std::vector<int64_t> buf(4 * std::min(B, found.size() + 1) * (size_t)n_);
     std::vector<int64_t> sl(2 * B);
     std::vector<int64_t> prevS(n_), prevE(n_);
     bool have_r = false;
     for (size_t b0 = 0; b0 < found.size(); b0 += B) {
         const size_t bn = std::min(B, found.size() - b0);
-#pragma omp parallel for schedule(static) num_threads(threads_) if (threads_ > 1 && bn > 64)
-        for (long x = 0; x < (long)bn; ++x) {
-            const MumRec& m = mums_[found[b0 + x]];
-            const int64_t* ms = &mum_start_[m.off];
-            int64_t* p = &buf[(size_t)x * 4 * n_];
-            sl[2 * x] = det_region(truth_.layout, len_, n_, ms, m.length, true, p, p + n_);
-            sl[2 * x + 1] = det_region(truth_.layout, len_, n_, ms, m.length, false, p + 2 * n_, p + 3 * n_);
-        }
+        const long per = 128;
+        parallel_chunks(bn > 512 ? threads_ : 1, ((long)bn + per - 1) / per, [&](long c) {
+            for (long x = c * per; x < std::min<long>((long)bn, (c + 1) * per); ++x) {
+                const MumRec& m = mums_[found[b0 + x]];
+                const int64_t* ms = &mum_start_[m.off];
+                int64_t* p = &buf[(size_t)x * 4 * n_];
+                sl[2 * x] = det_region(truth_.layout, len_, n_, ms, m.length, true, p, p + n_);
+                sl[2 * x + 1] = det_region(truth_.layout, len_, n_, ms, m.length, false, p + 2 * n_, p + 3 * n_);
+            }
+        });
         for (size_t x = 0; x < bn; ++x) {
             const size_t i = b0 + x;
             const int64_t* lS = &buf[x * 4 * n_]; const int64_t* lE = lS + n_; const int64_t* rS = lE + n_; const int64_t* rE = rS + n_;
@@ -434,12 +466,11 @@ void Aligner::speculate(const std::vector<int>& initial, const World& truth) {
         const size_t nchunks = T > 1 ? (size_t)T * 4 : 1;
         std::vector<RegionPool> outs(nchunks);
         for (auto& o : outs) o.n = n_;
-#pragma omp parallel for schedule(dynamic, 1) num_threads(T) if (T > 1)
-        for (long c = 0; c < (long)nchunks; ++c) {
+        parallel_chunks(T, (long)nchunks, [&](long c) {
             MumPool mp;
             const size_t a = frontier.size() * (size_t)c / nchunks, b = frontier.size() * (size_t)(c + 1) / nchunks;
             speculate_range(frontier, a, b, spec.layout, mp, outs[c], T > 1);
-        }
+        });
         std::vector<int> next;
         for (auto& o : outs)
             for (int i = 0; i < o.size(); ++i) next.push_back(rp_.add(o.start(i), o.end(i)));
@@ -555,25 +586,19 @@ void Aligner::sort_final_mums() {
         prev = s0;
     }
     if (sorted) return;
-    // this->mums = anchors (already ascending) followed by the recursion's MUMs (ascending apart from a few stragglers):
-    // sort the maximal ascending runs by merging instead of a full n log n sort
-    std::vector<std::pair<int64_t, int>> kv(M);
-    for (size_t i = 0; i < M; ++i) kv[i] = std::make_pair(mum_start_[mums_[final_mums_[i]].off], final_mums_[i]);
-    std::vector<size_t> runs(1, 0);
-    for (size_t i = 1; i < M; ++i) if (kv[i].first < kv[i - 1].first) runs.push_back(i);
-    runs.push_back(M);
-    if (runs.size() - 1 > 64) std::sort(kv.begin(), kv.end());
-    else {
-        while (runs.size() > 2) {
-            std::vector<size_t> nr(1, 0);
-            for (size_t r = 0; r + 1 < runs.size(); r += 2) {
-                if (r + 2 < runs.size()) {
-                    std::inplace_merge(kv.begin() + runs[r], kv.begin() + runs[r + 1], kv.begin() + runs[r + 2]);
-                    nr.push_back(runs[r + 2]);
-                } else nr.push_back(runs[r + 1]);
-            }
-            runs.swap(nr);
-        }
+    // LSD byte radix sort of (start0, id) pairs: keys are distinct, so the result is the unique ascending order
+    std::vector<std::pair<int64_t, int>> kv(M), tmp(M);
+    int64_t maxkey = 0;
+    for (size_t i = 0; i < M; ++i) {
+        kv[i] = std::make_pair(mum_start_[mums_[final_mums_[i]].off], final_mums_[i]);
+        maxkey = std::max(maxkey, kv[i].first);
+    }
+    for (int shift = 0; shift < 64 && (maxkey >> shift) != 0; shift += 8) {
+        size_t cnt[257] = {0};
+        for (size_t i = 0; i < M; ++i) cnt[((uint64_t)kv[i].first >> shift & 0xff) + 1]++;
+        for (int d = 0; d < 256; ++d) cnt[d + 1] += cnt[d];
+        for (size_t i = 0; i < M; ++i) tmp[cnt[(uint64_t)kv[i].first >> shift & 0xff]++] = kv[i];
+        kv.swap(tmp);
     }
     for (size_t i = 0; i < M; ++i) final_mums_[i] = kv[i].second;
 }
@@ -622,9 +647,21 @@ void Aligner::set_final_clusters(std::vector<ClusterRec>& out) {
     sort_final_mums();
     const int64_t M = (int64_t)final_mums_.size();
     if (M == 0) return;
-    auto S = [&](int64_t i, int k) { return mum_start_[mums_[final_mums_[i]].off + k]; };
-    auto Len = [&](int64_t i) { return mums_[final_mums_[i]].length; };
-    auto F = [&](int64_t i, int k) { return (int)mum_fwd_[mums_[final_mums_[i]].off + k]; };
+    // contiguous copies in sorted order (the pools are in discovery order): the chaining below streams through them
+    std::vector<int64_t> ss((size_t)M * n_), sl((size_t)M);
+    std::vector<uint8_t> sf((size_t)M * n_);
+    const long per = 4096;
+    parallel_chunks(M > 32768 ? threads_ : 1, ((long)M + per - 1) / per, [&](long c) {
+        for (long i = c * per; i < std::min<long>((long)M, (c + 1) * per); ++i) {
+            const MumRec& m = mums_[final_mums_[i]];
+            sl[i] = m.length;
+            std::memcpy(&ss[(size_t)i * n_], &mum_start_[m.off], sizeof(int64_t) * n_);
+            std::memcpy(&sf[(size_t)i * n_], &mum_fwd_[m.off], (size_t)n_);
+        }
+    });
+    auto S = [&](int64_t i, int k) { return ss[(size_t)i * n_ + k]; };
+    auto Len = [&](int64_t i) { return sl[i]; };
+    auto F = [&](int64_t i, int k) { return (int)sf[(size_t)i * n_ + k]; };
     auto new_cluster = [&](int64_t i) {
         ClusterRec c;
         c.type = 1;

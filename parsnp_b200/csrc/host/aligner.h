@@ -172,7 +172,21 @@ private:
     std::vector<int32_t> ck_, clon_, csp_;
     std::vector<uint8_t> cfwd_;
     std::vector<CacheEntry> cache_entries_;
-    std::unordered_multimap<uint64_t, int> cache_map_;
+    // open-addressing index hash(coords) -> cache entry (read-only while the speculation threads run)
+    struct CoordIndex {
+        std::vector<uint64_t> h;
+        std::vector<int> v;
+        size_t count = 0;
+        void insert(uint64_t hash, int value);
+        template <class Pred> int find(uint64_t hash, Pred pred) const {
+            if (h.empty()) return -1;
+            const size_t mask = h.size() - 1;
+            for (size_t i = (size_t)hash & mask;; i = (i + 1) & mask) {
+                if (v[i] < 0) return -1;
+                if (h[i] == hash && pred(v[i])) return v[i];
+            }
+        }
+    } cache_map_;
 
     std::vector<ClusterRec> clusters_;
     std::unordered_map<int64_t, int> minsize_cache_[2];
