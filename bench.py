@@ -242,15 +242,16 @@ def main():
     small_ms, small_n = per_launch("small_regions")
     rounds = 1.0 + timers.get("index_rounds", 0.0) / max(1.0, timers.get("big_windows", 1.0))
     roof_kernels = {
-        # one launch group = the 8 one-sweep passes over (8 B key + 4 B value) of one window: 8 x (12 read + 12 write) B per base
-        "sa_build_radix_sort(onesweep_kernel x8)": {"bytes": 192.0 * timers.get("big_ref_bases", 0.0) / sort_n, "ms": sort_ms},
+        # one launch group = all LSD passes of one window's packed seed keys; accounted at SURVEY 8(d)'s sort share of A_sa: 8 passes x (12 B read + 12 B write) per window base
+        # (the 2-bit/32-bit key variant moves fewer bytes than this; the figure is the reference-algorithm byte count, not bytes moved)
+        "sa_build_radix_sort(tile_hist+digit_scan+scatter_kernel passes)": {"bytes": 192.0 * timers.get("big_ref_bases", 0.0) / sort_n, "ms": sort_ms},
         # A_scan = 20 B per query base (both strands)
         "mum_scan(seed_extend_kernel)": {"bytes": 20.0 * timers.get("big_query_bases", 0.0) / seed_n, "ms": seed_ms},
         # SURVEY 8(d) "recursion: same formulas applied to the sum of region lengths": A_sa(r=1) = 221 B per window base + 20 B per query base
         "recursion(small_region_kernel)": {"bytes": (221.0 * timers.get("small_ref_bases", 0.0) + 20.0 * timers.get("small_query_bases", 0.0)) / small_n,
                                            "ms": small_ms},
     }
-    dom_total = {"sa_build_radix_sort(onesweep_kernel x8)": groups.get("index_sort", 0.0), "mum_scan(seed_extend_kernel)": groups.get("scan_seed", 0.0),
+    dom_total = {"sa_build_radix_sort(tile_hist+digit_scan+scatter_kernel passes)": groups.get("index_sort", 0.0), "mum_scan(seed_extend_kernel)": groups.get("scan_seed", 0.0),
                  "recursion(small_region_kernel)": groups.get("small_regions", 0.0)}
     dom = max(dom_total, key=lambda k: dom_total[k])
     rk = roof_kernels[dom]

@@ -63,6 +63,7 @@ int pbtest_search_windows(int backend, int n, const uint8_t* const* seqs, const 
     be->set_genomes(n, seqs, lens);
     pb200::CandBatch cb;
     be->search((const pb200::WindowTask*)tasks, ntasks, coords, cb);
+    cb.compact(ntasks);
     delete be;
     auto dup = [](const void* p, size_t bytes) { void* q = malloc(bytes ? bytes : 1); if (bytes) memcpy(q, p, bytes); return q; };
     *cand_off = (int64_t*)dup(cb.off.data(), cb.off.size() * 8);

@@ -133,6 +133,8 @@ def _decl_result_api(lib):
     lib.pb200_result_num_mums.argtypes = [vp]
     lib.pb200_result_num_mums.restype = C.c_int64
     lib.pb200_result_mums.argtypes = [vp] + [vp] * 5
+    lib.pb200_result_mums_view.argtypes = [vp] + [vp] * 5
+    lib.pb200_result_free.argtypes = [vp]
     lib.pb200_result_num_clusters.argtypes = [vp]
     lib.pb200_result_num_clusters.restype = C.c_int64
     lib.pb200_result_clusters.argtypes = [vp] + [vp] * 5
@@ -150,13 +152,42 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+class _ResultOwner:
+    """keeps a pb200_result alive while numpy views of its arrays exist"""
+
+    def __init__(self, lib, h):
+        self.lib, self.h = lib, h
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.pb200_result_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def _view(owner, addr, shape, dtype):
+    """numpy array over library memory at `addr` (no copy); the array keeps `owner` alive"""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    if n == 0 or not addr:
+        return np.zeros(shape, dtype)
+    buf = (C.c_char * n).from_address(addr)
+    buf._owner = owner
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
 def unpack_result(lib, h):
-    """pb200_result* -> dict of numpy arrays; frees the handle"""
+    """pb200_result* -> dict of numpy arrays.  The MUM arrays are views of the result's own memory (pb200_result_mums_view);
+    the handle is freed when the last of them is garbage collected."""
     n = lib.pb200_result_n(h)
     M = lib.pb200_result_num_mums(h)
-    length = np.zeros(M, np.int64); slength = np.zeros(M, np.int64)
-    start = np.zeros((M, n), np.int64); end = np.zeros((M, n), np.int64); fwd = np.zeros((M, n), np.uint8)
-    lib.pb200_result_mums(h, _ptr(length), _ptr(slength), _ptr(start), _ptr(end), _ptr(fwd))
+    owner = _ResultOwner(lib, h)
+    p = [C.c_void_p() for _ in range(5)]
+    lib.pb200_result_mums_view(h, *[C.byref(x) for x in p])
+    length = _view(owner, p[0].value, (M,), np.int64); slength = _view(owner, p[1].value, (M,), np.int64)
+    start = _view(owner, p[2].value, (M, n), np.int64); end = _view(owner, p[3].value, (M, n), np.int64)
+    fwd = _view(owner, p[4].value, (M, n), np.uint8)
     K = lib.pb200_result_num_clusters(h)
     ctype = np.zeros(K, np.int32); cn = np.zeros(K, np.int64); cl = np.zeros(K, np.int64)
     cs = np.zeros((K, n), np.int64); ce = np.zeros((K, n), np.int64)
@@ -168,7 +199,7 @@ def unpack_result(lib, h):
     names = lib.pb200_stats_names().decode().split(",")
     sv = np.zeros(len(names), np.float64)
     lib.pb200_result_stats(h, _ptr(sv), len(names))
-    lib.pb200_result_free(h)
+    del owner                      # the views hold the remaining references
     return dict(n=n, mum_length=length, mum_slength=slength, mum_start=start, mum_end=end, mum_fwd=fwd,
                 cluster_type=ctype, cluster_nmums=cn, cluster_length=cl, cluster_start=cs, cluster_end=ce,
                 trace=tr, stats=dict(zip(names, sv.tolist())))

@@ -7,6 +7,9 @@
 #pragma once
 #include <cstdint>
 #include <cstddef>
+#include <cstring>
+#include <memory>
+#include <utility>
 #include <vector>
 
 namespace pb200 {
@@ -21,15 +24,50 @@ struct WindowTask {
     int32_t pad;
 };
 
-// Candidates of a batch of windows, SoA. Candidate c of window w lives at index off[w]+c (increasing k).
+// vector whose resize() leaves new elements uninitialised (the candidate arrays are filled by device-to-host copies)
+template <class T>
+struct default_init_allocator : std::allocator<T> {
+    template <class U> struct rebind { using other = default_init_allocator<U>; };
+    template <class U> void construct(U* p) noexcept { ::new ((void*)p) U; }
+    template <class U, class... A> void construct(U* p, A&&... a) { ::new ((void*)p) U(std::forward<A>(a)...); }
+};
+template <class T> using pod_vector = std::vector<T, default_init_allocator<T>>;
+
+// Candidates of a batch of windows, SoA. Candidate c of window w lives at index off[w]+c (increasing k), c < count(w).
+// A backend may return the windows' blocks in any order (`cnt` filled); with `cnt` empty the blocks are contiguous in
+// window order and off has ntasks+1 entries.
 struct CandBatch {
     int nq = 0;                      // number of query genomes (n-1)
-    std::vector<int64_t> off;        // [ntasks+1]
-    std::vector<int32_t> k;          // reference start inside the window (0-based)
-    std::vector<int32_t> lon;        // LON
-    std::vector<int32_t> sp;         // [ncand * nq] start inside the query region, in the winning strand's coordinates
-    std::vector<uint8_t> fwd;        // [ncand * nq] 1 = forward strand won
-    void clear() { off.clear(); k.clear(); lon.clear(); sp.clear(); fwd.clear(); }
+    std::vector<int64_t> off;        // [ntasks] (+1 when contiguous)
+    std::vector<int32_t> cnt;        // [ntasks] or empty
+    pod_vector<int32_t> k;           // reference start inside the window (0-based)
+    pod_vector<int32_t> lon;         // LON
+    pod_vector<int32_t> sp;          // [ncand * nq] start inside the query region, in the winning strand's coordinates
+    pod_vector<uint8_t> fwd;         // [ncand * nq] 1 = forward strand won
+    void clear() { off.clear(); cnt.clear(); k.clear(); lon.clear(); sp.clear(); fwd.clear(); }
+    int32_t count(int t) const { return cnt.empty() ? (int32_t)(off[t + 1] - off[t]) : cnt[t]; }
+    // rewrite into window order: off[ntasks+1] increasing, cnt empty
+    void compact(int ntasks) {
+        if (cnt.empty()) return;
+        std::vector<int64_t> noff((size_t)ntasks + 1, 0);
+        for (int t = 0; t < ntasks; ++t) noff[t + 1] = noff[t] + cnt[t];
+        const int64_t tot = noff[ntasks];
+        pod_vector<int32_t> nk((size_t)tot), nl((size_t)tot), ns((size_t)tot * nq);
+        pod_vector<uint8_t> nf((size_t)tot * nq);
+        for (int t = 0; t < ntasks; ++t) {
+            const size_t c = (size_t)cnt[t], a = (size_t)off[t], b = (size_t)noff[t];
+            if (!c) continue;
+            std::memcpy(nk.data() + b, k.data() + a, c * 4);
+            std::memcpy(nl.data() + b, lon.data() + a, c * 4);
+            if (nq) {
+                std::memcpy(ns.data() + b * nq, sp.data() + a * nq, c * nq * 4);
+                std::memcpy(nf.data() + b * nq, fwd.data() + a * nq, c * nq);
+            }
+        }
+        k.swap(nk); lon.swap(nl); sp.swap(ns); fwd.swap(nf);
+        off.swap(noff);
+        cnt.clear();
+    }
 };
 
 // Search engine interface. The product implementation is CUDA-only (cuda/engine.cu); tests may link the

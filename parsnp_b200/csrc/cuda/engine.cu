@@ -1,6 +1,7 @@
 // CUDA search engine + C ABI of libparsnp_b200.so (see include/parsnp_b200.h).  sm_100a only, no CPU path.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <cstdlib>
 #include <string>
@@ -50,10 +51,10 @@ public:
         if (e != cudaSuccess || count == 0) throw CudaError("parsnp_b200 requires a CUDA device (none found); there is no CPU fallback");
         if (device < 0 || device >= count) throw CudaError("parsnp_b200: bad device ordinal");
         PB_CUDA(cudaSetDevice(device));
-        cudaDeviceProp prop;
-        PB_CUDA(cudaGetDeviceProperties(&prop, device));
-        if (prop.major < 10) throw CudaError("parsnp_b200 kernels are built for sm_100a (Blackwell) only");
-        sm_count_ = prop.multiProcessorCount;
+        int cc_major = 0;
+        PB_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+        if (cc_major < 10) throw CudaError("parsnp_b200 kernels are built for sm_100a (Blackwell) only");
+        PB_CUDA(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, device));
         PB_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
         {   // keep freed blocks in the pool: later engines (one per pb200_align call) re-use them without cudaMalloc
             cudaMemPool_t pool;
@@ -93,25 +94,40 @@ public:
         }
         uint8_t* text = text_.ensure((size_t)tot + 256, false, st_);
         PB_CUDA(cudaMemsetAsync(text, 7, (size_t)tot + 256, st_));         // 7 never matches a base code
-        uint8_t* stage = stage_.ensure((size_t)maxlen + 64, false, st_);
+        // raw ASCII staged per genome (all copies and encode launches are queued back to back, one sync at the end)
+        (void)maxlen;
+        int64_t raw_tot = 0;
+        std::vector<int64_t> raw_off(n, 0);
+        for (int i = 0; i < n; ++i) { raw_off[i] = raw_tot; raw_tot += pad(len[i]); }
+        uint8_t* stage = stage_.ensure((size_t)raw_tot + 64, false, st_);
         for (int i = 0; i < n; ++i) {
             if (len[i] == 0) continue;
-            PB_CUDA(cudaMemcpyAsync(stage, seq[i], (size_t)len[i], cudaMemcpyHostToDevice, st_));
-            pb200::launch(encode_kernel, (unsigned)((len[i] + 255) / 256), 256, 0, st_, stage, len[i], text + gfwd_[i], i > 0 ? text + grc_[i] : nullptr);
-            PB_CUDA(cudaStreamSynchronize(st_));                             // stage is reused
+            PB_CUDA(cudaMemcpyAsync(stage + raw_off[i], seq[i], (size_t)len[i], cudaMemcpyHostToDevice, st_));
+            pb200::launch(encode_kernel, (unsigned)((len[i] + 255) / 256), 256, 0, st_, stage + raw_off[i], len[i], text + gfwd_[i],
+                          i > 0 ? text + grc_[i] : nullptr);
         }
         h2d_bytes_ = 0;
         for (int i = 0; i < n; ++i) h2d_bytes_ += len[i];
-        // positions of non-ACGT symbols in the reference (N is an ordinary symbol; windows without any take the 2-bit key path)
+        // positions of non-ACGT symbols in the reference (N is an ordinary symbol; windows without any take the 2-bit key path);
+        // scanned in blocks so that the common all-ACGT block is one vectorisable reduction
         ref_n_pos_.clear();
-        for (int64_t i = 0; i < len[0]; ++i) {
-            const uint8_t c = seq[0][i];
-            if (c != 'A' && c != 'C' && c != 'G' && c != 'T') ref_n_pos_.push_back(i);
+        const int64_t BLK = 4096;
+        for (int64_t b0 = 0; b0 < len[0]; b0 += BLK) {
+            const int64_t b1 = std::min(len[0], b0 + BLK);
+            const uint8_t* p = seq[0];
+            int bad = 0;
+            for (int64_t i = b0; i < b1; ++i) { const uint8_t c = p[i]; bad += (c != 'A') & (c != 'C') & (c != 'G') & (c != 'T'); }
+            if (!bad) continue;
+            for (int64_t i = b0; i < b1; ++i) {
+                const uint8_t c = p[i];
+                if (c != 'A' && c != 'C' && c != 'G' && c != 'T') ref_n_pos_.push_back(i);
+            }
         }
         int64_t* d = gmeta_.ensure((size_t)3 * n, false, st_);
         std::vector<int64_t> meta(3 * (size_t)n);
         for (int i = 0; i < n; ++i) { meta[i] = gfwd_[i]; meta[n + i] = grc_[i]; meta[2 * n + i] = len_[i]; }
         PB_CUDA(cudaMemcpyAsync(d, meta.data(), meta.size() * 8, cudaMemcpyHostToDevice, st_));
+        stage_.release(st_);                                                 // stream-ordered: freed after the encode kernels ran
         PB_CUDA(cudaStreamSynchronize(st_));
     }
 
@@ -124,6 +140,7 @@ public:
         int64_t ncoords = 0;
         for (int t = 0; t < ntasks; ++t) ncoords = std::max(ncoords, tasks[t].coord_off + 2 * (int64_t)nq);
         // classify
+        const double th0 = wall_s();
         std::vector<int> cls(ntasks, 3);
         std::vector<std::vector<int>> by_class(4);
         for (int t = 0; t < ntasks; ++t) {
@@ -138,39 +155,36 @@ public:
         sm_k_.clear(); sm_lon_.clear(); sm_sp_.clear(); sm_fwd_.clear();
         bg_k_.clear(); bg_lon_.clear(); bg_sp_.clear(); bg_fwd_.clear();
         const bool any_small = !by_class[0].empty() || !by_class[1].empty() || !by_class[2].empty();
+        const double th1 = wall_s();
+        host_classify_s += th1 - th0;
         if (any_small) upload_small_tasks(tasks, ntasks, coords, ncoords);
+        host_upload_s += wall_s() - th1;
         for (int c = 0; c < 3; ++c) {
             if (by_class[c].empty()) continue;
             std::vector<int> retry;
             run_small(c, by_class[c], nq, t_base, t_cnt, retry);
             for (int t : retry) by_class[c + 1].push_back(t);
         }
+        const double th2 = wall_s();
         for (int t : by_class[3]) {
             t_src[t] = 1;
             t_base[t] = (int64_t)bg_k_.size();
             run_big(tasks[t], coords, nq);
             t_cnt[t] = (int32_t)((int64_t)bg_k_.size() - t_base[t]);
         }
-        // assemble in task order
-        out.off.resize(ntasks + 1);
-        int64_t tot = 0;
-        for (int t = 0; t < ntasks; ++t) { out.off[t] = tot; tot += t_cnt[t]; }
-        out.off[ntasks] = tot;
-        out.k.resize(tot); out.lon.resize(tot); out.sp.resize((size_t)tot * nq); out.fwd.resize((size_t)tot * nq);
-        for (int t = 0; t < ntasks; ++t) {
-            const int32_t cnt = t_cnt[t];
-            if (!cnt) continue;
-            const std::vector<int32_t>& sk = t_src[t] ? bg_k_ : sm_k_;
-            const std::vector<int32_t>& sl = t_src[t] ? bg_lon_ : sm_lon_;
-            const std::vector<int32_t>& ss = t_src[t] ? bg_sp_ : sm_sp_;
-            const std::vector<uint8_t>& sf = t_src[t] ? bg_fwd_ : sm_fwd_;
-            std::memcpy(&out.k[out.off[t]], &sk[t_base[t]], (size_t)cnt * 4);
-            std::memcpy(&out.lon[out.off[t]], &sl[t_base[t]], (size_t)cnt * 4);
-            if (nq) {
-                std::memcpy(&out.sp[(size_t)out.off[t] * nq], &ss[(size_t)t_base[t] * nq], (size_t)cnt * nq * 4);
-                std::memcpy(&out.fwd[(size_t)out.off[t] * nq], &sf[(size_t)t_base[t] * nq], (size_t)cnt * nq);
-            }
+        host_big_s += wall_s() - th2;
+        // hand the blocks over where the kernels left them: small-window candidates first, then the large windows
+        const int64_t nsm = (int64_t)sm_k_.size();
+        out.k.swap(sm_k_); out.lon.swap(sm_lon_); out.sp.swap(sm_sp_); out.fwd.swap(sm_fwd_);
+        if (!bg_k_.empty()) {
+            out.k.insert(out.k.end(), bg_k_.begin(), bg_k_.end());
+            out.lon.insert(out.lon.end(), bg_lon_.begin(), bg_lon_.end());
+            out.sp.insert(out.sp.end(), bg_sp_.begin(), bg_sp_.end());
+            out.fwd.insert(out.fwd.end(), bg_fwd_.begin(), bg_fwd_.end());
         }
+        out.off.resize(ntasks);
+        out.cnt.assign(t_cnt.begin(), t_cnt.end());
+        for (int t = 0; t < ntasks; ++t) out.off[t] = t_base[t] + (t_src[t] ? nsm : 0);
     }
 
     // ---- StagedWindowEngine (query-sharded large windows, see host/sharded.h) ----
@@ -280,6 +294,7 @@ public:
     GpuTimers timers;
     int64_t big_windows = 0, small_windows = 0, small_retries = 0, big_events = 0, index_rounds = 0;
     int64_t small_class_tasks[3] = {0, 0, 0};
+    double host_classify_s = 0, host_upload_s = 0, host_small_wait_s = 0, host_small_d2h_s = 0, host_big_s = 0;   // wall clock, host side
     int64_t small_ref_bases = 0, small_query_bases = 0, big_ref_bases = 0, big_query_bases = 0;
 
 private:
@@ -314,7 +329,14 @@ private:
         cfg.ev_cap += 4 * nq;            // the event store holds all strands of all queries of a window
         if (cfg.ev_cap > 60000) cfg.ev_cap = 60000;
         for (int t : ids_in) { small_ref_bases += h_task_n_[t]; small_query_bases += h_task_m_[t]; }
-        size_t cand_cap = std::max<size_t>(cand_cap_hint_, (size_t)ids.size() * 2 + 4096);
+        // candidates per window seen so far in this process (x1.25) sizes the shared output buffer; an overflow re-runs only the
+        // windows that did not fit
+        static std::atomic<uint32_t> s_cand_per_task_x16(8 * 16);
+        size_t cand_cap = std::max<size_t>(cand_cap_hint_, (size_t)ids.size() * s_cand_per_task_x16.load() / 16 + 4096);
+        const size_t cap_limit = std::max<size_t>((size_t)1 << 16, ((size_t)1 << 30) / (size_t)(8 + 5 * std::max(nq, 1)));   // <= 1 GiB of candidate arrays
+        if (cand_cap > cap_limit) cand_cap = cap_limit;
+        const size_t ntasks_in = ids.size();
+        size_t cands_out = 0;
         while (!ids.empty()) {
             const int nt = (int)ids.size();
             int32_t* d_ids = d_ids_.ensure((size_t)nt, false, st_);
@@ -340,9 +362,13 @@ private:
             int maxid = *std::max_element(ids.begin(), ids.end());
             h_outs_all_.resize((size_t)maxid + 1);
             PB_CUDA(cudaMemcpyAsync(h_outs_all_.data(), d_outs_.get(), sizeof(small::TaskOut) * ((size_t)maxid + 1), cudaMemcpyDeviceToHost, st_));
+            const double tw0 = wall_s();
             PB_CUDA(cudaStreamSynchronize(st_));
+            const double tw1 = wall_s();
+            host_small_wait_s += tw1 - tw0;
             (void)ho;
             const size_t got = (size_t)std::min<unsigned long long>(used, cand_cap);
+            cands_out += got;
             const size_t hb = sm_k_.size();
             sm_k_.resize(hb + got); sm_lon_.resize(hb + got);
             sm_sp_.resize((hb + got) * nq); sm_fwd_.resize((hb + got) * nq);
@@ -355,6 +381,7 @@ private:
                 }
                 PB_CUDA(cudaStreamSynchronize(st_));
             }
+            host_small_d2h_s += wall_s() - tw1;
             std::vector<int> again;
             for (int t : ids) {
                 const small::TaskOut& o = h_outs_all_[t];
@@ -364,6 +391,11 @@ private:
             }
             ids.swap(again);
             if (!ids.empty()) { cand_cap = cand_cap * 2 + 4096; cand_cap_hint_ = cand_cap; }
+        }
+        if (ntasks_in >= 1024) {
+            const uint32_t r = (uint32_t)std::min<size_t>(1u << 20, cands_out * 20 / ntasks_in + 16);     // x16 fixed point, +25 %
+            uint32_t cur = s_cand_per_task_x16.load();
+            while (r > cur && !s_cand_per_task_x16.compare_exchange_weak(cur, r)) {}
         }
     }
 
@@ -412,8 +444,10 @@ private:
     small::ClassCfg classes_[3];
     size_t max_smem_ = 0, cand_cap_hint_ = 0;
     big::BigPath big_;
-    std::vector<int32_t> sm_k_, sm_lon_, sm_sp_, bg_k_, bg_lon_, bg_sp_;
-    std::vector<uint8_t> sm_fwd_, bg_fwd_;
+    pod_vector<int32_t> sm_k_, sm_lon_, sm_sp_;
+    pod_vector<uint8_t> sm_fwd_;
+    std::vector<int32_t> bg_k_, bg_lon_, bg_sp_;
+    std::vector<uint8_t> bg_fwd_;
 };
 
 }  // namespace pb200
@@ -477,12 +511,16 @@ int pb200_cuda_available(void) {
 int pb200_genomes_create(int device, int n, const uint8_t* const* seqs, const int64_t* lens, pb200_genomes** out) {
     return guarded([&]() {
         if (n < 1 || !seqs || !lens || !out) { pb200::g_last_error = "bad arguments"; return (int)PB200_ERR_ARG; }
+        const bool prof = getenv("PB200_PROFILE_HOST") != nullptr;
+        const double t0 = pb200::wall_s();
         std::unique_ptr<pb200_genomes> g(new pb200_genomes);
         g->eng.reset(new pb200::CudaEngine(device));
+        const double t1 = pb200::wall_s();
         g->n = n;
         g->seq.assign(seqs, seqs + n);
         g->len.assign(lens, lens + n);
         g->eng->set_genomes(n, seqs, lens);
+        if (prof) fprintf(stderr, "[pb200 create ms] engine %.2f set_genomes %.2f\n", (t1 - t0) * 1e3, (pb200::wall_s() - t1) * 1e3);
         *out = g.release();
         return (int)PB200_OK;
     });
@@ -496,6 +534,7 @@ int pb200_search_windows(pb200_genomes* g, int ntasks, const pb200_window* tasks
         static_assert(sizeof(pb200_window) == sizeof(pb200::WindowTask), "window layout");
         pb200::CandBatch cb;
         g->eng->search(reinterpret_cast<const pb200::WindowTask*>(tasks), ntasks, coords, cb);
+        cb.compact(ntasks);
         auto dup = [](const void* p, size_t bytes) { void* q = malloc(bytes ? bytes : 1); if (bytes) memcpy(q, p, bytes); return q; };
         *cand_off = (int64_t*)dup(cb.off.data(), cb.off.size() * 8);
         *k = (int32_t*)dup(cb.k.data(), cb.k.size() * 4);
@@ -530,12 +569,23 @@ int pb200_align_resident(pb200_genomes* g, const pb200_params* prm, pb200_result
             bep = sharded.get();
         }
         pb200::SearchBackend& be = *bep;
-        pb200::Aligner a(g->n, g->seq.data(), g->len.data(), pb200::to_align_params(prm), &be);
-        a.enable_trace(prm->flags & PB200_FLAG_TRACE_WINDOWS);
-        a.set_speculate(!(prm->flags & PB200_FLAG_NO_SPECULATION));
-        a.set_threads(pb200::default_host_threads());
-        bool ok = a.run();
-        *out = pb200::make_result(a);
+        const bool prof = getenv("PB200_PROFILE_HOST") != nullptr;
+        double tp[5] = {pb200::wall_s(), 0, 0, 0, 0};
+        bool ok = false;
+        {
+            pb200::Aligner a(g->n, g->seq.data(), g->len.data(), pb200::to_align_params(prm), &be);
+            a.enable_trace(prm->flags & PB200_FLAG_TRACE_WINDOWS);
+            a.set_speculate(!(prm->flags & PB200_FLAG_NO_SPECULATION));
+            a.set_threads(pb200::default_host_threads());
+            tp[1] = pb200::wall_s();
+            ok = a.run();
+            tp[2] = pb200::wall_s();
+            *out = pb200::make_result(a);
+            tp[3] = pb200::wall_s();
+        }
+        tp[4] = pb200::wall_s();
+        if (prof) fprintf(stderr, "[pb200 align ms] ctor %.2f run %.2f make_result %.2f dtor %.2f\n", (tp[1] - tp[0]) * 1e3, (tp[2] - tp[1]) * 1e3,
+                          (tp[3] - tp[2]) * 1e3, (tp[4] - tp[3]) * 1e3);
         return ok ? (int)PB200_OK : (int)PB200_ERR_NO_MUMS;
     });
 }
@@ -565,15 +615,16 @@ int pb200_engine_timers(pb200_genomes* g, double* values, int cap) {
     const int T = pb200::GpuTimers::T_COUNT;
     for (int i = 0; i < T && k < cap; ++i) values[k++] = g->eng->timers.ms[i];
     for (int i = 0; i < T && k < cap; ++i) values[k++] = g->eng->timers.cnt[i];
-    const double extra[13] = {(double)g->eng->small_class_tasks[0], (double)g->eng->small_class_tasks[1], (double)g->eng->small_class_tasks[2],(double)g->eng->big_windows, (double)g->eng->small_windows, (double)g->eng->small_retries,
+    const double extra[18] = {(double)g->eng->small_class_tasks[0], (double)g->eng->small_class_tasks[1], (double)g->eng->small_class_tasks[2],(double)g->eng->big_windows, (double)g->eng->small_windows, (double)g->eng->small_retries,
                               (double)g->eng->big_events, (double)g->eng->index_rounds, (double)pb200::g_kernel_launches,
                               (double)g->eng->small_ref_bases, (double)g->eng->small_query_bases, (double)g->eng->big_ref_bases,
-                              (double)g->eng->big_query_bases};
-    for (int i = 0; i < 13 && k < cap; ++i) values[k++] = extra[i];
+                              (double)g->eng->big_query_bases, g->eng->host_classify_s, g->eng->host_upload_s, g->eng->host_small_wait_s,
+                              g->eng->host_small_d2h_s, g->eng->host_big_s};
+    for (int i = 0; i < 18 && k < cap; ++i) values[k++] = extra[i];
     return k;
 }
 const char* pb200_engine_timer_names(void) {
-    static std::string s = std::string(pb200::GpuTimers::names()) + ",tasks_class_a,tasks_class_b,tasks_class_c,big_windows,small_windows,small_retries,big_events,index_rounds,kernel_launches,small_ref_bases,small_query_bases,big_ref_bases,big_query_bases";
+    static std::string s = std::string(pb200::GpuTimers::names()) + ",tasks_class_a,tasks_class_b,tasks_class_c,big_windows,small_windows,small_retries,big_events,index_rounds,kernel_launches,small_ref_bases,small_query_bases,big_ref_bases,big_query_bases,host_classify_s,host_upload_s,host_small_wait_s,host_small_d2h_s,host_big_s";
     return s.c_str();
 }
 void pb200_engine_reset_timers(pb200_genomes* g) {
@@ -583,6 +634,7 @@ void pb200_engine_reset_timers(pb200_genomes* g) {
     pb200::g_kernel_launches = 0;
     g->eng->small_ref_bases = g->eng->small_query_bases = g->eng->big_ref_bases = g->eng->big_query_bases = 0;
     g->eng->small_class_tasks[0] = g->eng->small_class_tasks[1] = g->eng->small_class_tasks[2] = 0;
+    g->eng->host_classify_s = g->eng->host_upload_s = g->eng->host_small_wait_s = g->eng->host_small_d2h_s = g->eng->host_big_s = 0;
 }
 
 // test hook (not in the public header): suffix array + longest-repeated-prefix of a window of genome 0

@@ -1,5 +1,6 @@
 // Small CUDA utilities: error checking, RAII device buffers, event timers.
 #pragma once
+#include <chrono>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -43,6 +44,7 @@ public:
         cap_ = ncap;
         return p_;
     }
+    void release(cudaStream_t st = 0) { if (p_) cudaFreeAsync(p_, st); p_ = nullptr; cap_ = 0; }
 private:
     T* p_ = nullptr;
     size_t cap_ = 0;
@@ -118,6 +120,7 @@ private:
 };
 
 // every kernel launch of the library goes through here so that the engine can report how many kernels it launched
+inline double wall_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 extern int64_t g_kernel_launches;
 template <class... KArgs, class... Args>
 inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

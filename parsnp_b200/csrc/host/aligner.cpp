@@ -1,4 +1,5 @@
 #include "aligner.h"
+#include "parallel.h"
 #include <algorithm>
 #include <chrono>
 #include <cstring>
@@ -16,19 +17,6 @@ namespace {
 inline double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
-// Runs fn(chunk) for chunk = 0..nchunks-1 on up to `nthreads` threads (dynamic assignment).  Plain std::thread per phase:
-// a handful of phases per alignment, and no spinning worker pool that could starve a co-scheduled process.
-template <class F>
-void parallel_chunks(int nthreads, long nchunks, F&& fn) {
-    if (nthreads <= 1 || nchunks <= 1) { for (long c = 0; c < nchunks; ++c) fn(c); return; }
-    std::atomic<long> next(0);
-    auto worker = [&]() { for (long c; (c = next.fetch_add(1)) < nchunks;) fn(c); };
-    std::vector<std::thread> pool;
-    const int extra = (int)std::min<long>(nthreads, nchunks) - 1;
-    for (int t = 0; t < extra; ++t) pool.emplace_back(worker);
-    worker();
-    for (auto& th : pool) th.join();
-}
 inline uint8_t comp_base(uint8_t c) {          // Aligner::reversec (src/parsnp.cpp:1294-1393) on the ingest alphabet
     switch (c) {
         case 'A': return 'T';
@@ -45,11 +33,9 @@ void BitRow::init(int64_t nbits) {
     nbits_ = nbits;
     w_.assign((size_t)((nbits + 63) >> 6) + 1, 0ull);
 }
-void BitRow::set_range(int64_t a, int64_t b) {
-    if (a >= b) return;
+void BitRow::set_range_slow(int64_t a, int64_t b) {
     int64_t wa = a >> 6, wb = (b - 1) >> 6;
     uint64_t ma = ~0ull << (a & 63), mb = ~0ull >> (63 - ((b - 1) & 63));
-    if (wa == wb) { w_[wa] |= (ma & mb); return; }
     w_[wa] |= ma;
     for (int64_t i = wa + 1; i < wb; ++i) w_[i] = ~0ull;
     w_[wb] |= mb;
@@ -72,7 +58,7 @@ void BitRow::clear_range(int64_t a, int64_t b) {
     for (int64_t i = wa + 1; i < wb; ++i) w_[i] = 0ull;
     w_[wb] &= ~mb;
 }
-int64_t BitRow::run_up(int64_t a, int64_t b) const {
+int64_t BitRow::run_up_slow(int64_t a, int64_t b) const {
     int64_t i = a;
     while (i < b) {
         uint64_t inv = ~(w_[i >> 6] >> (i & 63));          // first zero bit at or after i
@@ -84,7 +70,7 @@ int64_t BitRow::run_up(int64_t a, int64_t b) const {
     if (i > b) i = b;
     return i - a;
 }
-int64_t BitRow::run_down(int64_t a, int64_t b) const {
+int64_t BitRow::run_down_slow(int64_t a, int64_t b) const {
     int64_t i = b - 1;                                       // examine i, i-1, ...
     while (i >= a) {
         int pos = (int)(i & 63);
@@ -146,8 +132,13 @@ bool Aligner::region_equal(int a, int b) const {        // operator==, src/LCR.c
     return std::memcmp(rstart(a), rstart(b), sizeof(int64_t) * 2 * n_) == 0;
 }
 uint64_t Aligner::coords_hash(const int64_t* p, int count) {
+    // start and end of the first and the last genome: regions equal there and different elsewhere are rare and the table's
+    // equality callback compares all coordinates
     uint64_t h = 0x9E3779B97F4A7C15ull;
-    for (int i = 0; i < count; ++i) {
+    const int half = count / 2;
+    const int idx[4] = {0, half - 1, half, count - 1};
+    for (int t = 0; t < 4; ++t) {
+        const int i = idx[t];
         h ^= (uint64_t)p[i] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
         h *= 0xff51afd7ed558ccdull;
         h ^= h >> 29;
@@ -173,6 +164,19 @@ void Aligner::CoordIndex::insert(uint64_t hash, int value) {
     v[i] = value;
     ++count;
 }
+void Aligner::CoordIndex::reserve(size_t entries) {
+    size_t need = 1024;
+    while (need < (count + entries) * 2 + 2) need *= 2;
+    if (need <= h.size()) return;
+    std::vector<uint64_t> oh;
+    std::vector<int> ov;
+    oh.swap(h);
+    ov.swap(v);
+    h.assign(need, 0);
+    v.assign(need, -1);
+    count = 0;
+    for (size_t i = 0; i < oh.size(); ++i) if (ov[i] >= 0) insert(oh[i], ov[i]);
+}
 int Aligner::cache_lookup_coords(const int64_t* coords) const {
     const size_t bytes = sizeof(int64_t) * 2 * n_;
     return cache_map_.find(coords_hash(coords, 2 * n_),
@@ -191,10 +195,13 @@ int Aligner::minsize_cached(bool anchors, int64_t slength) {
 // ------------------------------------------------------------------ batched search (setMums1 up to the emission loop)
 void Aligner::search_regions(const std::vector<int>& regs, bool anchors) {
     if (regs.empty()) return;
+    const double tp0 = now_s();
     std::vector<WindowTask> tasks;
     std::vector<int64_t> coords;
     std::vector<int> first_task(regs.size() + 1, 0);
     const int nq = n_ - 1;
+    tasks.reserve(regs.size());
+    coords.reserve(regs.size() * 2 * (size_t)nq);
     for (size_t ri = 0; ri < regs.size(); ++ri) {
         const int r = regs[ri];
         const int64_t* rs = rstart(r);
@@ -226,19 +233,46 @@ void Aligner::search_regions(const std::vector<int>& regs, bool anchors) {
         }
     }
     first_task[regs.size()] = (int)tasks.size();
-    CandBatch cb;
+    const double tp1 = now_s();
+    chunks_.emplace_back();
+    CandBatch& cb = chunks_.back();
     cb.nq = nq;
     if (!tasks.empty()) be_->search(tasks.data(), (int)tasks.size(), coords.data(), cb);
     else cb.off.assign(1, 0);
+    if (!cb.cnt.empty()) {
+        // the engine delivers the windows' candidate blocks in kernel completion order; gather them into window order so that
+        // the accept passes (ascending reference order) stream through memory
+        const int nt = (int)tasks.size();
+        std::vector<int64_t> noff((size_t)nt + 1, 0);
+        for (int t = 0; t < nt; ++t) noff[t + 1] = noff[t] + cb.cnt[t];
+        const int64_t tot = noff[nt];
+        pod_vector<int32_t> nk((size_t)tot), nl((size_t)tot), ns((size_t)tot * nq);
+        pod_vector<uint8_t> nf((size_t)tot * nq);
+        const long per = 1024;
+        parallel_chunks(tot > 65536 ? threads_ : 1, ((long)nt + per - 1) / per, [&](long c) {
+            for (long t = c * per; t < std::min<long>(nt, (c + 1) * per); ++t) {
+                const size_t cn = (size_t)cb.cnt[t], a = (size_t)cb.off[t], b = (size_t)noff[t];
+                if (!cn) continue;
+                std::memcpy(nk.data() + b, cb.k.data() + a, cn * 4);
+                std::memcpy(nl.data() + b, cb.lon.data() + a, cn * 4);
+                if (nq) {
+                    std::memcpy(ns.data() + b * nq, cb.sp.data() + a * nq, cn * nq * 4);
+                    std::memcpy(nf.data() + b * nq, cb.fwd.data() + a * nq, cn * nq);
+                }
+            }
+        });
+        cb.k.swap(nk); cb.lon.swap(nl); cb.sp.swap(ns); cb.fwd.swap(nf);
+        cb.off.swap(noff);
+        cb.cnt.clear();
+    }
+    const double tp2 = now_s();
     stats_.windows_searched += (int64_t)tasks.size();
     stats_.regions_searched += (int64_t)regs.size();
-    // append to the cache stores
-    const int64_t base = (int64_t)ck_.size();
-    ck_.insert(ck_.end(), cb.k.begin(), cb.k.end());
-    clon_.insert(clon_.end(), cb.lon.begin(), cb.lon.end());
-    csp_.insert(csp_.end(), cb.sp.begin(), cb.sp.end());
-    cfwd_.insert(cfwd_.end(), cb.fwd.begin(), cb.fwd.end());
     stats_.candidates += (int64_t)cb.k.size();
+    const int32_t chunk = (int32_t)chunks_.size() - 1;
+    cache_entries_.reserve(cache_entries_.size() + regs.size());
+    cache_map_.reserve(regs.size());
+    wins_.reserve(wins_.size() + tasks.size());
     for (size_t ri = 0; ri < regs.size(); ++ri) {
         CacheEntry e;
         e.region = regs[ri];
@@ -248,14 +282,18 @@ void Aligner::search_regions(const std::vector<int>& regs, bool anchors) {
             WinRec w;
             w.ref_start = tasks[t].ref_start;
             w.ref_len = tasks[t].ref_len;
-            w.cand_off = base + cb.off[t];
-            w.ncand = (int32_t)(cb.off[t + 1] - cb.off[t]);
-            w.minsize = tasks[t].minsize;
+            w.cand_off = cb.off[t];
+            w.ncand = cb.count(t);
+            w.chunk = chunk;
             wins_.push_back(w);
         }
         cache_map_.insert(coords_hash(rstart(regs[ri]), 2 * n_), (int)cache_entries_.size());
         cache_entries_.push_back(e);
     }
+    const double tp3 = now_s();
+    stats_.t_search_prep += tp1 - tp0;
+    stats_.t_search_backend += tp2 - tp1;
+    stats_.t_search_cache += tp3 - tp2;
 }
 
 // ------------------------------------------------------------------ setMums1 loop D (src/parsnp.cpp:1713-1842)
@@ -272,33 +310,37 @@ void Aligner::accept_candidates(const int64_t* rs, const int64_t* re, int64_t rs
     if (n_ > 64) { st_vec.resize(n_); fw_vec.resize(n_); st = st_vec.data(); fw = fw_vec.data(); }
     for (int wi = 0; wi < ce.nwin; ++wi) {
         const WinRec& win = wins_[ce.first_win + wi];
+        const CandBatch& cb = chunks_[win.chunk];
         if (trace) trace_.emplace_back(win.ref_start, win.ref_len);
         for (int32_t c = 0; c < win.ncand; ++c) {
             const int64_t ci = win.cand_off + c;
-            const int64_t LON = clon_[ci];
+            const int64_t LON = cb.lon[ci];
             bool bad = false;
             // Mum.DSP is 1-based (src/parsnp.cpp:1671,1681); range pre-check in unsigned arithmetic (1723)
-            uint64_t dsp0 = (uint64_t)((int64_t)ck_[ci] + 1 + win.ref_start);
+            uint64_t dsp0 = (uint64_t)((int64_t)cb.k[ci] + 1 + win.ref_start);
             if ((uint64_t)(dsp0 - (uint64_t)rs[0]) > (uint64_t)(uint32_t)(re[0] - rs[0])) bad = true;
             st[0] = (int64_t)dsp0 - 1;
             fw[0] = 1;
+            // shortcut: a candidate whose reference interval is already covered trims to nothing in the first pass of the trim loop
+            // below whatever the other genomes hold, and nothing before that point has a side effect
+            if (!bad && st[0] + LON <= len_[0] && layout[0].get(st[0]) && layout[0].run_up(st[0], st[0] + LON) == LON) continue;
+            // TMum ctor (src/TMum.cpp:13-72): a reverse-strand start is mirrored on the WHOLE genome length; the ctor's `ok` ends up
+            // false as soon as one genome's interval leaves its sequence (a middle-genome failure makes the reference throw;
+            // unreachable).  Range pre-check and ctor are fused into one pass; both only ever skip the candidate.
+            bool any_fail = st[0] + LON > len_[0] || st[0] < 0;
+            const int32_t* spj = cb.sp.data() + ci * nq;
+            const uint8_t* fwj = cb.fwd.data() + ci * nq;
             for (int j = 1; j < n_; ++j) {
-                uint64_t dsp = (uint64_t)((int64_t)csp_[ci * nq + (j - 1)] + 1 + rs[j]);
-                if ((uint64_t)(dsp - (uint64_t)rs[j]) > (uint64_t)(uint32_t)(re[j] - rs[j])) bad = true;
-                st[j] = (int64_t)dsp - 1;
-                fw[j] = cfwd_[ci * nq + (j - 1)];
+                const uint64_t dsp = (uint64_t)((int64_t)spj[j - 1] + 1 + rs[j]);
+                bad |= (uint64_t)(dsp - (uint64_t)rs[j]) > (uint64_t)(uint32_t)(re[j] - rs[j]);
+                int64_t s = (int64_t)dsp - 1;
+                const uint8_t f = fwj[j - 1];
+                if (!f) s = len_[j] - (s + LON);
+                any_fail |= (s + LON > len_[j]) | (s < 0);
+                st[j] = s;
+                fw[j] = f;
             }
-            if (bad) continue;
-            // TMum ctor (src/TMum.cpp:13-72): reverse-strand start uses the WHOLE genome length; `ok` = last genome
-            bool ok = true, any_fail = false;
-            for (int j = 0; j < n_; ++j)
-                if (!fw[j]) st[j] = len_[j] - (st[j] + LON);
-            for (int j = 0; j < n_; ++j) {
-                if (st[j] + LON > len_[j] || st[j] < 0) { ok = false; any_fail = true; }
-                else ok = true;
-            }
-            if (any_fail) ok = false;      // (a middle-genome failure makes the reference throw; unreachable)
-            if (!ok || LON < 5) continue;
+            if (bad || any_fail || LON < 5) continue;
             // trim (src/parsnp.cpp:1399-1477): every trim shifts ALL genomes, strand ignored
             int64_t length = LON;
             for (int j = 0; j < n_; ++j) {
@@ -367,41 +409,85 @@ void Aligner::set_initial_clusters() {
     double t1 = now_s();
     stats_.t_anchor_search = t1 - t0;
     std::vector<int> found;
+    {   // room for the anchors plus the recursion's MUMs (about 3x the anchors on divergent genomes): no regrowth copies below
+        const size_t est = (size_t)stats_.candidates * 4 + 1024;
+        mp_.mums.reserve(est);
+        mp_.start.reserve(est * (size_t)n_);
+        mp_.fwd.reserve(est * (size_t)n_);
+        found.reserve((size_t)stats_.candidates);
+    }
     accept_candidates(rstart(whole), rend(whole), rp_.slen[whole], cache_lookup(whole), truth_.layout, mp_, found, false, trace_on_);
     all_mums_ = found;
     stats_.anchors = (int64_t)found.size();
+    const double ta1 = now_s();
+    double t_det = 0;
     // determineRegion of every anchor: mumlayout is final here (all anchors placed), so the scans are independent and run
     // in parallel over blocks of anchors; the push rules (src/parsnp.cpp:2153-2172) are then applied in order
-    const size_t B = 16384;
-    std::vector<int64_t> buf(4 * std::min(B, found.size() + 1) * (size_t)n_);
-    std::vector<int64_t> sl(2 * B);
+    // The push rules compare an anchor's left region with the previous anchor's right region and with its own right region:
+    // pairwise tests on the scan results, evaluated in parallel; the pool is then grown once and filled in parallel.
+    const size_t B = 262144;
+    const size_t stride = 4 * (size_t)n_;
+    pod_vector<int64_t> buf(stride * std::min(B, found.size() + 1));
+    pod_vector<int64_t> sl(2 * std::min(B, found.size() + 1));
+    pod_vector<int32_t> slot(2 * std::min(B, found.size() + 1) + 1);
+    const double ta2 = now_s();
     std::vector<int64_t> prevS(n_), prevE(n_);
-    bool have_r = false;
+    const size_t cbytes = sizeof(int64_t) * (size_t)n_;
     for (size_t b0 = 0; b0 < found.size(); b0 += B) {
         const size_t bn = std::min(B, found.size() - b0);
-        const long per = 128;
-        parallel_chunks(bn > 512 ? threads_ : 1, ((long)bn + per - 1) / per, [&](long c) {
+        const long per = 256;
+        const int T = bn > 512 ? threads_ : 1;
+        const double td0 = now_s();
+        parallel_chunks(T, ((long)bn + per - 1) / per, [&](long c) {
             for (long x = c * per; x < std::min<long>((long)bn, (c + 1) * per); ++x) {
                 const MumRec& m = mums_[found[b0 + x]];
                 const int64_t* ms = &mum_start_[m.off];
-                int64_t* p = &buf[(size_t)x * 4 * n_];
+                int64_t* p = &buf[(size_t)x * stride];
                 sl[2 * x] = det_region(truth_.layout, len_, n_, ms, m.length, true, p, p + n_);
                 sl[2 * x + 1] = det_region(truth_.layout, len_, n_, ms, m.length, false, p + 2 * n_, p + 3 * n_);
             }
         });
-        for (size_t x = 0; x < bn; ++x) {
-            const size_t i = b0 + x;
-            const int64_t* lS = &buf[x * 4 * n_]; const int64_t* lE = lS + n_; const int64_t* rS = lE + n_; const int64_t* rE = rS + n_;
-            bool l_eq_r = have_r && std::memcmp(lS, prevS.data(), sizeof(int64_t) * n_) == 0 && std::memcmp(lE, prevE.data(), sizeof(int64_t) * n_) == 0;
-            if (sl[2 * x] > prm_.q && (i == 0 || !l_eq_r)) initial_regions_.push_back(rp_.add(lS, lE));
-            have_r = true;
-            bool r_eq_l = std::memcmp(lS, rS, sizeof(int64_t) * n_) == 0 && std::memcmp(lE, rE, sizeof(int64_t) * n_) == 0;
-            if (sl[2 * x + 1] > prm_.q && !r_eq_l) initial_regions_.push_back(rp_.add(rS, rE));
-            std::memcpy(prevS.data(), rS, sizeof(int64_t) * n_);
-            std::memcpy(prevE.data(), rE, sizeof(int64_t) * n_);
-        }
+        t_det += now_s() - td0;
+        parallel_chunks(T, ((long)bn + per - 1) / per, [&](long c) {
+            for (long x = c * per; x < std::min<long>((long)bn, (c + 1) * per); ++x) {
+                const int64_t* lS = &buf[(size_t)x * stride];
+                const int64_t* rS = lS + 2 * n_;
+                const int64_t* pS = x ? lS - 2 * n_ : prevS.data();        // previous anchor's right region (start, end contiguous)
+                const int64_t* pE = x ? lS - n_ : prevE.data();
+                const bool first = (b0 + (size_t)x) == 0;
+                const bool l_eq_r = !first && std::memcmp(lS, pS, cbytes) == 0 && std::memcmp(lS + n_, pE, cbytes) == 0;
+                const bool r_eq_l = std::memcmp(lS, rS, 2 * cbytes) == 0;
+                slot[2 * x] = (sl[2 * x] > prm_.q && (first || !l_eq_r)) ? 1 : 0;
+                slot[2 * x + 1] = (sl[2 * x + 1] > prm_.q && !r_eq_l) ? 1 : 0;
+            }
+        });
+        int32_t total = 0;
+        for (size_t x = 0; x < 2 * bn; ++x) { const int32_t f = slot[x]; slot[x] = total; total += f; }
+        slot[2 * bn] = total;
+        const int base = rp_.size();
+        rp_.coord.resize(rp_.coord.size() + (size_t)total * 2 * n_);
+        rp_.slen.resize(rp_.slen.size() + (size_t)total);
+        const size_t ir0 = initial_regions_.size();
+        initial_regions_.resize(ir0 + (size_t)total);
+        parallel_chunks(T, ((long)bn + per - 1) / per, [&](long c) {
+            for (long x = c * per; x < std::min<long>((long)bn, (c + 1) * per); ++x) {
+                for (int side = 0; side < 2; ++side) {
+                    const int32_t at = slot[2 * x + side];
+                    if (slot[2 * x + side + 1] == at) continue;
+                    const int id = base + at;
+                    std::memcpy(&rp_.coord[(size_t)id * 2 * n_], &buf[(size_t)x * stride + (size_t)side * 2 * n_], 2 * cbytes);
+                    rp_.slen[id] = sl[2 * x + side];
+                    initial_regions_[ir0 + (size_t)at] = id;
+                }
+            }
+        });
+        std::memcpy(prevS.data(), &buf[(bn - 1) * stride + 2 * n_], cbytes);
+        std::memcpy(prevE.data(), &buf[(bn - 1) * stride + 3 * n_], cbytes);
     }
     stats_.t_anchor_host = now_s() - t1;
+    if (getenv("PB200_PROFILE_HOST"))
+        fprintf(stderr, "[pb200 anchors ms] accept %.2f alloc %.2f det_region %.2f push %.2f\n", (ta1 - t1) * 1e3, (ta2 - ta1) * 1e3, t_det * 1e3,
+                (now_s() - ta2 - t_det) * 1e3);
 }
 
 // ------------------------------------------------------------------ speculative level-synchronous discovery
@@ -443,15 +529,13 @@ void Aligner::speculate(const std::vector<int>& initial, const World& truth) {
         double t0 = now_s();
         need.clear();
         {
-            std::unordered_multimap<uint64_t, int> seen;
+            CoordIndex seen;
+            seen.reserve(frontier.size());
             for (int r : frontier) {
                 if (cache_lookup(r) >= 0) continue;
-                uint64_t h = coords_hash(rstart(r), 2 * n_);
-                bool dup = false;
-                auto range = seen.equal_range(h);
-                for (auto it = range.first; it != range.second; ++it) if (region_equal(it->second, r)) { dup = true; break; }
-                if (dup) continue;
-                seen.emplace(h, r);
+                const uint64_t h = coords_hash(rstart(r), 2 * n_);
+                if (seen.find(h, [&](int o) { return region_equal(o, r); }) >= 0) continue;
+                seen.insert(h, r);
                 need.push_back(r);
             }
         }
@@ -492,15 +576,38 @@ void Aligner::process_queue_exact(const std::vector<int>& initial, RegionPool& r
     auto req = [&](int a, int b) { return std::memcmp(rp.start(a), rp.start(b), sizeof(int64_t) * 2 * n_) == 0; };
     std::vector<QE> vec;
     for (int r : initial) vec.push_back(QE{rp.start(r)[0], r});
-    std::map<int64_t, int> fast;
+    // fast mode: the queue as a vector sorted by DESCENDING start[0] (front of the reference's vector = back of this one).
+    // Children of the region just taken lie inside it, i.e. next to the back, so insertion is a short walk + a short move.
+    std::vector<QE> fast;
+    auto fast_pos = [&](int64_t key) {          // index of the first element (from the front) with s0 <= key
+        size_t pos = fast.size();
+        int steps = 0;
+        while (pos > 0 && fast[pos - 1].s0 < key) {
+            --pos;
+            if (++steps == 16) {                 // far from the back: binary search over the descending prefix
+                pos = (size_t)(std::lower_bound(fast.begin(), fast.begin() + (long)pos, key,
+                                                [](const QE& e, int64_t k) { return e.s0 > k; }) - fast.begin());
+                return pos;
+            }
+        }
+        // here fast[pos-1].s0 >= key (or pos == 0)
+        if (pos > 0 && fast[pos - 1].s0 == key) return pos - 1;
+        return pos;
+    };
     bool fast_mode = false;
     std::vector<int> found, children;
     std::vector<int64_t> lS(n_), lE(n_), rS(n_), rE(n_);
+    static const bool prof = getenv("PB200_PROFILE_HOST") != nullptr;
+    uint64_t pc[5] = {0, 0, 0, 0, 0}, pt = 0;
+#define PROF_MARK(i) do { if (prof) { uint64_t x_ = __builtin_ia32_rdtsc(); pc[i] += x_ - pt; pt = x_; } } while (0)
+    if (prof) pt = __builtin_ia32_rdtsc();
     while (fast_mode ? !fast.empty() : !vec.empty()) {
         int cur;
-        if (fast_mode) { cur = fast.begin()->second; fast.erase(fast.begin()); }
+        if (fast_mode) { cur = fast.back().id; fast.pop_back(); }
         else { cur = vec.front().id; vec.erase(vec.begin()); }
+        PROF_MARK(0);
         int ci = cache_lookup_coords(rp.start(cur));
+        PROF_MARK(1);
         if (ci < 0) {
             double ts = now_s();
             search_regions(std::vector<int>(1, cur), false);          // a region the speculation did not predict
@@ -510,6 +617,7 @@ void Aligner::process_queue_exact(const std::vector<int>& initial, RegionPool& r
         }
         found.clear();
         accept_candidates(rp.start(cur), rp.end(cur), rp.slen[cur], ci, layout, mp, found, false, trace_on_);
+        PROF_MARK(2);
         children.clear();
         int64_t lsl = 0;
         for (size_t i = 0; i < found.size(); ++i) {
@@ -525,27 +633,56 @@ void Aligner::process_queue_exact(const std::vector<int>& initial, RegionPool& r
             }
             out_mums.push_back(found[i]);
         }
+        PROF_MARK(3);
         // sort + drop adjacent duplicates (src/parsnp.cpp:291-306)
         if (fast_mode) {
             bool distinct_tie = false;
             for (size_t a = 0; a < children.size() && !distinct_tie; ++a) {
-                auto it = fast.find(rp.start(children[a])[0]);
-                if (it != fast.end() && !req(it->second, children[a])) distinct_tie = true;
+                const int64_t key = rp.start(children[a])[0];
+                const size_t pos = fast_pos(key);
+                if (pos < fast.size() && fast[pos].s0 == key && !req(fast[pos].id, children[a])) distinct_tie = true;
                 for (size_t b = 0; b < a && !distinct_tie; ++b)
-                    if (rp.start(children[a])[0] == rp.start(children[b])[0] && !req(children[a], children[b])) distinct_tie = true;
+                    if (key == rp.start(children[b])[0] && !req(children[a], children[b])) distinct_tie = true;
             }
             if (!distinct_tie) {
-                for (int ch : children) fast.emplace(rp.start(ch)[0], ch);   // identical duplicates collapse
+                for (int ch : children) {                                    // identical duplicates collapse (the first one stays)
+                    const int64_t key = rp.start(ch)[0];
+                    const size_t pos = fast_pos(key);
+                    if (pos < fast.size() && fast[pos].s0 == key) continue;
+                    fast.insert(fast.begin() + (long)pos, QE{key, ch});
+                }
+                PROF_MARK(4);
                 continue;
             }
-            vec.clear();
-            for (auto& kv : fast) vec.push_back(QE{kv.first, kv.second});
+            vec.assign(fast.rbegin(), fast.rend());
             fast.clear();
             fast_mode = false;
         }
         stats_.slow_queue_iters++;
         for (int ch : children) vec.push_back(QE{rp.start(ch)[0], ch});
-        if (!vec.empty()) std::sort(vec.begin(), vec.end());
+        if (!vec.empty()) {
+            // The queue is nearly sorted (anchor order, then children next to their parent).  With distinct start[0] keys every
+            // correct sort gives the same sequence, so try a bounded insertion sort on a copy; ties (or too much disorder) fall
+            // back to the literal std::sort call of the reference on the untouched vector.
+            std::vector<QE> tmp(vec);
+            size_t budget = 8 * tmp.size() + 64;
+            bool done = true;
+            for (size_t i = 1; i < tmp.size() && done; ++i) {
+                if (!(tmp[i] < tmp[i - 1])) continue;
+                const QE x = tmp[i];
+                size_t j = i;
+                while (j > 0 && x < tmp[j - 1]) {
+                    tmp[j] = tmp[j - 1];
+                    --j;
+                    if (--budget == 0) { done = false; break; }
+                }
+                tmp[j] = x;
+            }
+            bool distinct = done;
+            for (size_t m = 0; distinct && m + 1 < tmp.size(); ++m) if (!(tmp[m].s0 < tmp[m + 1].s0)) distinct = false;
+            if (distinct) vec.swap(tmp);
+            else std::sort(vec.begin(), vec.end());
+        }
         {
             size_t rsize = vec.size();
             if (rsize) {
@@ -558,12 +695,15 @@ void Aligner::process_queue_exact(const std::vector<int>& initial, RegionPool& r
         bool strict = true;
         for (size_t m = 0; m + 1 < vec.size(); ++m) if (!(vec[m].s0 < vec[m + 1].s0)) { strict = false; break; }
         if (strict) {
-            fast.clear();
-            for (auto& e : vec) fast.emplace_hint(fast.end(), e.s0, e.id);
+            fast.assign(vec.rbegin(), vec.rend());
             vec.clear();
             fast_mode = true;
         }
+        PROF_MARK(4);
     }
+    if (prof) fprintf(stderr, "[pb200 replay cycles] pop %llu lookup %llu accept %llu det_region %llu queue %llu\n", (unsigned long long)pc[0],
+                      (unsigned long long)pc[1], (unsigned long long)pc[2], (unsigned long long)pc[3], (unsigned long long)pc[4]);
+#undef PROF_MARK
 }
 
 void Aligner::do_work_exact() {
@@ -578,27 +718,31 @@ void Aligner::do_work_exact() {
 // reference), so the order is unique.  Sorts compact (start0,id) pairs and skips the work when already sorted.
 void Aligner::sort_final_mums() {
     const size_t M = final_mums_.size();
-    bool sorted = true;
-    int64_t prev = INT64_MIN;
-    for (size_t i = 0; i < M; ++i) {
-        int64_t s0 = mum_start_[mums_[final_mums_[i]].off];
-        if (s0 < prev) { sorted = false; break; }
-        prev = s0;
-    }
-    if (sorted) return;
-    // LSD byte radix sort of (start0, id) pairs: keys are distinct, so the result is the unique ascending order
-    std::vector<std::pair<int64_t, int>> kv(M), tmp(M);
+    std::vector<std::pair<int64_t, int>> kv(M);
+    size_t descents = 0, split = 0;
     int64_t maxkey = 0;
     for (size_t i = 0; i < M; ++i) {
-        kv[i] = std::make_pair(mum_start_[mums_[final_mums_[i]].off], final_mums_[i]);
-        maxkey = std::max(maxkey, kv[i].first);
+        const int64_t s0 = mum_start_[mums_[final_mums_[i]].off];
+        kv[i] = std::make_pair(s0, final_mums_[i]);
+        if (i && s0 < kv[i - 1].first) { ++descents; split = i; }
+        maxkey = std::max(maxkey, s0);
     }
-    for (int shift = 0; shift < 64 && (maxkey >> shift) != 0; shift += 8) {
-        size_t cnt[257] = {0};
-        for (size_t i = 0; i < M; ++i) cnt[((uint64_t)kv[i].first >> shift & 0xff) + 1]++;
-        for (int d = 0; d < 256; ++d) cnt[d + 1] += cnt[d];
-        for (size_t i = 0; i < M; ++i) tmp[cnt[(uint64_t)kv[i].first >> shift & 0xff]++] = kv[i];
+    if (descents == 0) return;
+    std::vector<std::pair<int64_t, int>> tmp(M);
+    if (descents == 1) {
+        // the usual shape: the anchors (ascending) followed by the recursion's MUMs (ascending): one merge
+        std::merge(kv.begin(), kv.begin() + (long)split, kv.begin() + (long)split, kv.end(), tmp.begin(),
+                   [](const std::pair<int64_t, int>& x, const std::pair<int64_t, int>& y) { return x.first < y.first; });
         kv.swap(tmp);
+    } else {
+        // LSD byte radix sort of (start0, id) pairs: keys are distinct, so the result is the unique ascending order
+        for (int shift = 0; shift < 64 && (maxkey >> shift) != 0; shift += 8) {
+            size_t cnt[257] = {0};
+            for (size_t i = 0; i < M; ++i) cnt[((uint64_t)kv[i].first >> shift & 0xff) + 1]++;
+            for (int d = 0; d < 256; ++d) cnt[d + 1] += cnt[d];
+            for (size_t i = 0; i < M; ++i) tmp[cnt[(uint64_t)kv[i].first >> shift & 0xff]++] = kv[i];
+            kv.swap(tmp);
+        }
     }
     for (size_t i = 0; i < M; ++i) final_mums_[i] = kv[i].second;
 }
@@ -647,6 +791,73 @@ void Aligner::set_final_clusters(std::vector<ClusterRec>& out) {
     sort_final_mums();
     const int64_t M = (int64_t)final_mums_.size();
     if (M == 0) return;
+    const float dd = prm_.diag_diff;
+    if (!(dd > 1.0f)) {
+        // Default diagdiff (<= 1): every MUM either joins the open cluster or closes it and opens the next one, so the open cluster's
+        // last MUM is always nt-1 and all its members share one orientation vector (joining requires f == F(back) == F(front)).
+        // The join decision of the loop below is then a pure function of the pair (nt-1, nt): evaluate the pairs in parallel and
+        // cut the sorted MUM list into runs.  Any MUM shorter than `random` (skipped by the loop) sends us to the literal loop.
+        std::vector<uint8_t> joins((size_t)M, 0);
+        std::vector<int64_t> sl((size_t)M);
+        std::atomic<int> short_mum(0);
+        const long per = 2048;
+        parallel_chunks(M > 16384 ? threads_ : 1, ((long)M + per - 1) / per, [&](long c) {
+            const long i0 = c * per, i1 = std::min<long>((long)M, (c + 1) * per);
+            for (long i = i0; i < i1; ++i) {
+                const MumRec& m = mums_[final_mums_[i]];
+                sl[i] = m.length;
+                if (m.length < prm_.random) short_mum.store(1, std::memory_order_relaxed);
+                if (i == 0) continue;
+                const MumRec& b = mums_[final_mums_[i - 1]];
+                const int64_t* sn = &mum_start_[m.off];
+                const int64_t* sb = &mum_start_[b.off];
+                const uint8_t* fn = &mum_fwd_[m.off];
+                const uint8_t* fb = &mum_fwd_[b.off];
+                float max_length_region = 0, min_length_region = (float)(prm_.d + 10);
+                bool add = true;
+                for (int k = 0; k < n_; ++k) {
+                    const int f = fn[k];
+                    const int64_t gap = sn[k] - (sb[k] + b.length);
+                    const int64_t rgap = sb[k] - (sn[k] + m.length);
+                    if (f && (float)gap > max_length_region) max_length_region = (float)gap;
+                    else if (!f && (float)rgap > max_length_region) max_length_region = (float)gap;   // sic (src/parsnp.cpp:2608-2611)
+                    if (f && (float)gap < min_length_region) min_length_region = (float)gap;
+                    else if (!f && (float)rgap < min_length_region) min_length_region = (float)rgap;
+                    if (f != (int)fb[k]) add = false;
+                    else if (f && gap < 0) add = false;
+                    else if (!f && gap >= 0) add = false;
+                    else if (f && gap > prm_.d) add = false;
+                    else if (!f && rgap > prm_.d) add = false;
+                    if (!add) break;
+                }
+                if (add) {
+                    if (min_length_region == 0) min_length_region = 1;
+                    if (max_length_region == 0) max_length_region = 1;
+                    add = min_length_region / max_length_region >= 1.0 - dd;
+                }
+                joins[i] = add ? 1 : 0;
+            }
+        });
+        if (!short_mum.load()) {
+            for (int64_t a = 0; a < M;) {
+                int64_t b = a + 1;
+                while (b < M && joins[b]) ++b;
+                out.emplace_back();
+                ClusterRec& c = out.back();
+                c.type = 1;
+                c.length = 0;
+                c.mums.resize((size_t)(b - a));
+                for (int64_t i = a; i < b; ++i) { c.length += sl[i]; c.mums[(size_t)(i - a)] = (int)i; }
+                const MumRec& first = mums_[final_mums_[a]];
+                const MumRec& last = mums_[final_mums_[b - 1]];
+                c.start.assign(&mum_start_[first.off], &mum_start_[first.off] + n_);
+                c.end.resize(n_);
+                for (int k = 0; k < n_; ++k) c.end[k] = mum_start_[last.off + k] + last.length;
+                a = b;
+            }
+            return;
+        }
+    }
     // contiguous copies in sorted order (the pools are in discovery order): the chaining below streams through them
     std::vector<int64_t> ss((size_t)M * n_), sl((size_t)M);
     std::vector<uint8_t> sf((size_t)M * n_);
@@ -679,7 +890,6 @@ void Aligner::set_final_clusters(std::vector<ClusterRec>& out) {
     };
     ClusterRec cluster = new_cluster(0);
     bool addmum = true;
-    const float dd = prm_.diag_diff;
     for (int64_t nt = 1; nt < M; ++nt) {
         if (Len(nt) < prm_.random) { addmum = true; continue; }
         if (!addmum) cluster = new_cluster(nt - 1);
@@ -783,11 +993,20 @@ bool Aligner::run() {
     if (all_mums_.empty()) { stats_.t_total = now_s() - t0; return false; }
     double t1 = now_s();
     final_mums_ = all_mums_;
+    const bool prof = getenv("PB200_PROFILE_HOST") != nullptr;
+    double tl[6] = {now_s(), 0, 0, 0, 0, 0};
     if (prm_.random) filter_random1();
+    tl[1] = now_s();
     set_final_clusters(clusters_);
+    tl[2] = now_s();
     filter_clusters_simple(clusters_);
+    tl[3] = now_s();
     set_final_clusters(clusters_);
+    tl[4] = now_s();
     set_inter_cluster_regions(clusters_);
+    tl[5] = now_s();
+    if (prof) fprintf(stderr, "[pb200 lcb ms] copy %.2f filter_random1 %.2f set_final %.2f filter_simple %.2f set_final %.2f inter %.2f\n", (tl[0] - t1) * 1e3,
+                      (tl[1] - tl[0]) * 1e3, (tl[2] - tl[1]) * 1e3, (tl[3] - tl[2]) * 1e3, (tl[4] - tl[3]) * 1e3, (tl[5] - tl[4]) * 1e3);
     stats_.t_lcb = now_s() - t1;
     stats_.t_total = now_s() - t0;
     return true;

@@ -42,11 +42,21 @@ class BitRow {
 public:
     void init(int64_t nbits_with_sentinel);
     inline bool get(int64_t i) const { return (w_[i >> 6] >> (i & 63)) & 1ull; }
-    void set_range(int64_t a, int64_t b);     // [a,b)
+    inline void set_range(int64_t a, int64_t b) {   // [a,b)
+        if (a >= b) return;
+        const int64_t wa = a >> 6, wb = (b - 1) >> 6;
+        if (wa == wb) w_[wa] |= (~0ull << (a & 63)) & (~0ull >> (63 - ((b - 1) & 63)));
+        else set_range_slow(a, b);
+    }
+    void set_range_slow(int64_t a, int64_t b);
     void set_range_atomic(int64_t a, int64_t b);   // same, safe against concurrent writers of neighbouring bits
     void clear_range(int64_t a, int64_t b);   // [a,b)
-    int64_t run_up(int64_t a, int64_t b) const;     // # consecutive set bits a, a+1, ... (< b)
-    int64_t run_down(int64_t a, int64_t b) const;   // # consecutive set bits b-1, b-2, ... (>= a)
+    // # consecutive set bits a, a+1, ... (< b); the common case (bit a clear) is answered inline
+    inline int64_t run_up(int64_t a, int64_t b) const { return (a >= b || !get(a)) ? 0 : run_up_slow(a, b); }
+    // # consecutive set bits b-1, b-2, ... (>= a)
+    inline int64_t run_down(int64_t a, int64_t b) const { return (a >= b || !get(b - 1)) ? 0 : run_down_slow(a, b); }
+    int64_t run_up_slow(int64_t a, int64_t b) const;
+    int64_t run_down_slow(int64_t a, int64_t b) const;
     int64_t prev_set(int64_t i) const;        // largest set index <= i, or -1
     int64_t next_set(int64_t i, int64_t limit) const;   // smallest set index in [i,limit), or limit
     int64_t nbits() const { return nbits_; }
@@ -89,6 +99,7 @@ struct AlignStats {
             windows_searched = 0, candidates = 0, slow_queue_iters = 0, host_threads = 1;
     double t_anchor_search = 0, t_anchor_host = 0, t_spec_search = 0, t_spec_host = 0, t_replay = 0,
            t_replay_search = 0, t_lcb = 0, t_total = 0;
+    double t_search_prep = 0, t_search_backend = 0, t_search_cache = 0;   // split of the search_regions calls (all phases)
 };
 
 class Aligner {
@@ -167,10 +178,9 @@ private:
     std::vector<int> initial_regions_;
 
     // candidate cache
-    struct WinRec { int64_t ref_start, ref_len; int64_t cand_off; int32_t ncand; int32_t minsize; };
+    struct WinRec { int64_t ref_start, ref_len; int64_t cand_off; int32_t ncand; int32_t chunk; };
     std::vector<WinRec> wins_;
-    std::vector<int32_t> ck_, clon_, csp_;
-    std::vector<uint8_t> cfwd_;
+    std::vector<CandBatch> chunks_;        // one per search call; candidates stay where the backend delivered them
     std::vector<CacheEntry> cache_entries_;
     // open-addressing index hash(coords) -> cache entry (read-only while the speculation threads run)
     struct CoordIndex {
@@ -178,6 +188,7 @@ private:
         std::vector<int> v;
         size_t count = 0;
         void insert(uint64_t hash, int value);
+        void reserve(size_t entries);          // room for `entries` more without rehashing
         template <class Pred> int find(uint64_t hash, Pred pred) const {
             if (h.empty()) return -1;
             const size_t mask = h.size() - 1;

@@ -1,4 +1,6 @@
 #include "result.h"
+#include "parallel.h"
+#include <algorithm>
 #include <cstring>
 #include <cstdlib>
 #include <thread>
@@ -13,12 +15,15 @@ pb200_result* make_result(const Aligner& a) {
     const int64_t M = a.num_mums();
     r->m_length.resize(M); r->m_slength.resize(M);
     r->m_start.resize(M * n); r->m_end.resize(M * n); r->m_fwd.resize(M * n);
-    for (int64_t i = 0; i < M; ++i) {
-        const MumRec& m = a.mum(i);
-        r->m_length[i] = m.length; r->m_slength[i] = m.slength;
-        const int64_t* s = a.mum_start(i); const uint8_t* f = a.mum_fwd(i);
-        for (int k = 0; k < n; ++k) { r->m_start[i * n + k] = s[k]; r->m_end[i * n + k] = s[k] + m.length; r->m_fwd[i * n + k] = f[k]; }
-    }
+    const long per = 4096;
+    parallel_chunks(M > 32768 ? default_host_threads() : 1, ((long)M + per - 1) / per, [&](long c) {
+        for (int64_t i = c * per; i < std::min<int64_t>(M, (c + 1) * per); ++i) {
+            const MumRec& m = a.mum(i);
+            r->m_length[i] = m.length; r->m_slength[i] = m.slength;
+            const int64_t* s = a.mum_start(i); const uint8_t* f = a.mum_fwd(i);
+            for (int k = 0; k < n; ++k) { r->m_start[i * n + k] = s[k]; r->m_end[i * n + k] = s[k] + m.length; r->m_fwd[i * n + k] = f[k]; }
+        }
+    });
     r->c_mum_off.push_back(0);
     for (const ClusterRec& c : a.clusters()) {
         for (int mi : c.mums) r->c_mum_idx.push_back(mi);
@@ -32,7 +37,7 @@ pb200_result* make_result(const Aligner& a) {
     r->stats = { (double)s.anchors, (double)s.regions_searched, (double)s.spec_regions, (double)s.replay_misses,
                  (double)s.spec_levels, (double)s.windows_searched, (double)s.candidates, (double)s.slow_queue_iters,
                  s.t_anchor_search, s.t_anchor_host, s.t_spec_search, s.t_spec_host, s.t_replay, s.t_replay_search,
-                 s.t_lcb, s.t_total, (double)s.host_threads };
+                 s.t_lcb, s.t_total, (double)s.host_threads, s.t_search_prep, s.t_search_backend, s.t_search_cache };
     return r;
 }
 
@@ -75,6 +80,15 @@ int pb200_result_mums(const pb200_result* r, int64_t* length, int64_t* slength, 
     if (fwd) std::memcpy(fwd, r->m_fwd.data(), r->m_fwd.size());
     return 0;
 }
+int pb200_result_mums_view(const pb200_result* r, const int64_t** length, const int64_t** slength, const int64_t** start, const int64_t** end,
+                           const uint8_t** fwd) {
+    if (length) *length = r->m_length.data();
+    if (slength) *slength = r->m_slength.data();
+    if (start) *start = r->m_start.data();
+    if (end) *end = r->m_end.data();
+    if (fwd) *fwd = r->m_fwd.data();
+    return 0;
+}
 int64_t pb200_result_num_clusters(const pb200_result* r) { return (int64_t)r->c_type.size(); }
 int pb200_result_clusters(const pb200_result* r, int32_t* type, int64_t* nmums, int64_t* length, int64_t* start, int64_t* end) {
     if (type) std::memcpy(type, r->c_type.data(), r->c_type.size() * 4);
@@ -98,7 +112,7 @@ int pb200_result_stats(const pb200_result* r, double* values, int cap) {
 }
 const char* pb200_stats_names(void) {
     return "anchors,regions_searched,spec_regions,replay_misses,spec_levels,windows_searched,candidates,slow_queue_iters,"
-           "t_anchor_search,t_anchor_host,t_spec_search,t_spec_host,t_replay,t_replay_search,t_lcb,t_total,host_threads";
+           "t_anchor_search,t_anchor_host,t_spec_search,t_spec_host,t_replay,t_replay_search,t_lcb,t_total,host_threads,t_search_prep,t_search_backend,t_search_cache";
 }
 void pb200_result_free(pb200_result* r) { delete r; }
 int pb200_minsize(const char* expr, int64_t slength) { return pb200::MinSizeExpr(expr)(slength); }

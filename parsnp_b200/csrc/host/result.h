@@ -8,8 +8,8 @@
 
 struct pb200_result {
     int n = 0;
-    std::vector<int64_t> m_length, m_slength, m_start, m_end;
-    std::vector<uint8_t> m_fwd;
+    pb200::pod_vector<int64_t> m_length, m_slength, m_start, m_end;
+    pb200::pod_vector<uint8_t> m_fwd;
     std::vector<int32_t> c_type;
     std::vector<int64_t> c_nmums, c_length, c_start, c_end;
     std::vector<int64_t> c_mum_off, c_mum_idx;      // MUM indices (into the MUM list) of every cluster

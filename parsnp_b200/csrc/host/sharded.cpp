@@ -90,7 +90,7 @@ void ShardedBackend::search(const WindowTask* tasks, int ntasks, const int64_t* 
         for (int i = a; i < b; ++i) mine.push_back(tasks[small_ids[i]]);
         CandBatch cb;
         cb.nq = nq;
-        if (!mine.empty()) local_->search(mine.data(), (int)mine.size(), coords, cb);
+        if (!mine.empty()) { local_->search(mine.data(), (int)mine.size(), coords, cb); cb.compact((int)mine.size()); }
         else cb.off.assign(1, 0);
         int64_t hdr[2] = {(int64_t)mine.size(), (int64_t)cb.k.size()};
         std::vector<int64_t> hdrs((size_t)2 * W);
