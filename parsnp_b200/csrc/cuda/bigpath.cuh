@@ -86,22 +86,6 @@ __global__ void make_keys2_kernel(const uint8_t* __restrict__ R, int n, uint32_t
     keys[i] = key;
     sa[i] = (uint32_t)i;
 }
-__global__ void kmer_table2_kernel(const uint32_t* __restrict__ keys, int n, int k, uint2* __restrict__ table) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const int sh = 2 * (KEY2_BASES - k);
-    uint32_t c = keys[s] >> sh;
-    if (s == 0 || (keys[s - 1] >> sh) != c) table[c].x = (uint32_t)s;
-    if (s == n - 1 || (keys[s + 1] >> sh) != c) table[c].y = (uint32_t)s + 1u;
-}
-__global__ void head_flags2_kernel(const uint32_t* __restrict__ keys, int n, uint32_t* __restrict__ flag, uint32_t* __restrict__ hv) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    uint32_t f = (s == 0 || keys[s] != keys[s - 1]) ? 1u : 0u;
-    flag[s] = f;
-    hv[s] = f ? (uint32_t)s : 0u;
-}
-
 __device__ __forceinline__ bool kmer_of_key(uint64_t key, int k, uint32_t& code) {
     code = 0;
     for (int t = 0; t < k; ++t) {
@@ -111,19 +95,9 @@ __device__ __forceinline__ bool kmer_of_key(uint64_t key, int k, uint32_t& code)
     }
     return true;
 }
-// seed table entry: .x = first SA slot of the k-mer's bucket, .y = number of suffixes in it (0 = k-mer absent)
-__global__ void kmer_table_kernel(const uint64_t* __restrict__ keys, int n, int k, uint2* __restrict__ table) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    uint32_t c, cp = 0, cn = 0;
-    if (!kmer_of_key(keys[s], k, c)) return;
-    bool vp = s > 0 && kmer_of_key(keys[s - 1], k, cp);
-    bool vn = s + 1 < n && kmer_of_key(keys[s + 1], k, cn);
-    if (!vp || cp != c) table[c].x = (uint32_t)s;
-    if (!vn || cn != c) table[c].y = (uint32_t)s + 1u;       // end slot for now; turned into a count by kmer_table_fix_kernel
-}
-// .y = end - start.  Buckets of ONE suffix (the common case) store the text position itself in .x (saves the SA read in
-// the scan) and, in .y, bit 31 + a 24-bit signature = the 4 bases before and the 4 bases after the k-mer (3 bits each,
+// seed table entry (written by index_finish_kernel): k-mer absent = (0, 0).  Bucket of several suffixes: .x = first SA slot,
+// .y = one past the last SA slot.  Bucket of ONE suffix (the common case): .x = the text position itself (saves the SA read
+// in the scan) and .y = bit 31 + a 24-bit signature = the 4 bases before and the 4 bases after the k-mer (3 bits each,
 // 7 = outside the window): a match of >= k+7 bases around the seed must agree with the reference on one of the two
 // sides, so the scan can discard almost every chance k-mer hit without touching the reference text.
 constexpr uint32_t SIG_FLAG = 0x80000000u;
@@ -137,23 +111,8 @@ __device__ __forceinline__ uint32_t side_sig(const uint8_t* __restrict__ T, int 
     }
     return s;
 }
-__global__ void kmer_table_fix_kernel(uint2* __restrict__ table, size_t size, const uint32_t* __restrict__ sa_sorted,
-                                      const uint8_t* __restrict__ R, int n, int k) {
-    size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= size) return;
-    uint2 e = table[c];
-    if (e.y == 0) return;
-    uint32_t cnt = e.y - e.x;
-    if (cnt == 1) {
-        const int l = (int)sa_sorted[e.x];
-        e.x = (uint32_t)l;
-        e.y = SIG_FLAG | (side_sig(R, n, l - 4) << 12) | side_sig(R, n, l + k);
-    } else {
-        e.y = cnt;
-    }
-    table[c] = e;
-}
-__global__ void head_flags_kernel(const uint64_t* __restrict__ keys, int n, uint32_t* __restrict__ flag, uint32_t* __restrict__ hv) {
+template <class K>
+__global__ void head_flags_kernel(const K* __restrict__ keys, int n, uint32_t* __restrict__ flag, uint32_t* __restrict__ hv) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     uint32_t f = (s == 0 || keys[s] != keys[s - 1]) ? 1u : 0u;
@@ -202,17 +161,102 @@ __global__ void dbl_rank_kernel(const uint32_t* __restrict__ vals, const uint32_
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < U) rank[vals[c]] = head[c];
 }
-__global__ void lcp_kernel(const uint8_t* __restrict__ R, int n, const uint32_t* __restrict__ sa, int32_t* __restrict__ lcp) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s > n) return;
-    if (s == 0 || s == n) { lcp[s] = 0; return; }
-    int a = (int)sa[s - 1], b = (int)sa[s];
-    int limit = n - max(a, b);
-    lcp[s] = match_len(R + a, R + b, limit);
+
+// ---- tied groups of the k-mer sort, fast path: one warp per group of <= 32 equal keys, every lane ranks its suffix against
+// the others by direct comparison of the window text (depth-capped).  Larger or deeper groups raise *flag and the host
+// re-runs the window through the general prefix-doubling path.
+constexpr int TIE_MAX_GROUP = 32;
+constexpr int TIE_MAX_DEPTH = 8192;
+constexpr int TIE_ITEMS = 8;            // SA slots examined per lane
+// suffix order inside the window: when one suffix is a prefix of the other, the shorter (= later start) sorts first
+__device__ __forceinline__ bool suffix_less(const uint8_t* __restrict__ R, int n, int a, int b, bool& overflow) {
+    const int lim = n - max(a, b);
+    const int L = match_len(R + a, R + b, min(lim, TIE_MAX_DEPTH));
+    if (L >= lim) return a > b;
+    if (L >= TIE_MAX_DEPTH) { overflow = true; return a > b; }
+    return R[a + L] < R[b + L];
 }
-__global__ void lrp_kernel(const uint32_t* __restrict__ sa, const int32_t* __restrict__ lcp, int n, int32_t* __restrict__ lrp) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < n) lrp[sa[s]] = max(lcp[s], lcp[s + 1]);
+template <class K>
+__global__ void __launch_bounds__(256) tie_sort_kernel(const K* __restrict__ keys, int n, const uint8_t* __restrict__ R, uint32_t* __restrict__ sa,
+                                                       uint32_t* __restrict__ flag) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t base = warp_global * 32 * TIE_ITEMS;
+    for (int r = 0; r < TIE_ITEMS; ++r) {
+        const int64_t s = base + r * 32 + lane;
+        bool start = false;
+        if (s + 1 < n) {
+            const K kx = keys[s];
+            start = keys[s + 1] == kx && (s == 0 || keys[s - 1] != kx);
+        }
+        unsigned pend = __ballot_sync(0xffffffffu, start);
+        while (pend) {
+            const int src = __ffs(pend) - 1;
+            pend &= pend - 1;
+            const int64_t s0 = base + r * 32 + src;
+            uint32_t stop = 0;
+            if (lane == 0) stop = *reinterpret_cast<volatile uint32_t*>(flag);
+            if (__shfl_sync(0xffffffffu, stop, 0)) return;          // another group already sent the window to the general path
+            const K k0 = keys[s0];
+            const int64_t t = s0 + lane;
+            const unsigned m = __ballot_sync(0xffffffffu, t < n && keys[t] == k0);
+            const int g = (m == 0xffffffffu) ? 32 : __ffs(~m) - 1;   // sorted keys: the group is a prefix of the lanes
+            if (g == 32 && s0 + 32 < n && keys[s0 + 32] == k0) { if (lane == 0) atomicOr(flag, 1u); continue; }
+            const int a = lane < g ? (int)sa[s0 + lane] : 0;
+            int rank = 0;
+            bool ovf = false;
+            for (int j = 0; j < g; ++j) {
+                const int b = __shfl_sync(0xffffffffu, a, j);
+                if (lane < g && j != lane && suffix_less(R, n, b, a, ovf)) ++rank;
+            }
+            if (__any_sync(0xffffffffu, ovf)) { if (lane == 0) atomicOr(flag, 1u); continue; }
+            if (lane < g) sa[s0 + rank] = (uint32_t)a;
+        }
+    }
+}
+
+// ---- one pass over the final suffix array: adjacent LCPs (from the sorted keys; the window text is read only for equal
+// keys), lrp[l] = max(LCP left, LCP right) scattered to text order, and the seed table of the first k bases.
+template <class K> struct KeyTraits;
+template <> struct KeyTraits<uint32_t> {      // 16 bases, 2 bits each (N-free windows)
+    __device__ static int common(uint32_t a, uint32_t b) { const uint32_t x = a ^ b; return x ? (__clz((int)x) >> 1) : KEY2_BASES; }
+    __device__ static bool kmer(uint32_t key, int k, uint32_t& code) { code = key >> (2 * (KEY2_BASES - k)); return true; }
+};
+template <> struct KeyTraits<uint64_t> {      // 21 bases, 3 bits each (code + 1; 0 = past the window end)
+    __device__ static int common(uint64_t a, uint64_t b) { const uint64_t x = a ^ b; return x ? ((__clzll((long long)x) - 1) / 3) : KEY_BASES; }
+    __device__ static bool kmer(uint64_t key, int k, uint32_t& code) { return kmer_of_key(key, k, code); }
+};
+template <class K>
+__device__ __forceinline__ int pair_lcp(const K* __restrict__ keys, const uint32_t* __restrict__ sa, const uint8_t* __restrict__ R, int n, int64_t s) {
+    if (s <= 0 || s >= n) return 0;                    // lcp[0] = lcp[n] = 0
+    const K ka = keys[s - 1], kb = keys[s];
+    const int a = (int)sa[s - 1], b = (int)sa[s];
+    const int lim = n - max(a, b);
+    if (ka != kb) return min(KeyTraits<K>::common(ka, kb), lim);      // (key padding past the window end is cut off by lim)
+    return match_len(R + a, R + b, lim);
+}
+template <class K>
+__global__ void __launch_bounds__(256) index_finish_kernel(const K* __restrict__ keys, const uint32_t* __restrict__ sa, const uint8_t* __restrict__ R,
+                                                           int n, int k, int32_t* __restrict__ lrp, uint2* __restrict__ table) {
+    __shared__ int s_lcp[257];
+    const int64_t b0 = (int64_t)blockIdx.x * 256;
+    const int64_t s = b0 + threadIdx.x;
+    s_lcp[threadIdx.x] = pair_lcp(keys, sa, R, n, s);
+    if (threadIdx.x == 0) s_lcp[256] = pair_lcp(keys, sa, R, n, b0 + 256);
+    __syncthreads();
+    if (s >= n) return;
+    const int l = (int)sa[s];
+    lrp[l] = max(s_lcp[threadIdx.x], s_lcp[threadIdx.x + 1]);
+    uint32_t c, cp = 0, cn = 0;
+    if (!KeyTraits<K>::kmer(keys[s], k, c)) return;
+    const bool same_prev = s > 0 && KeyTraits<K>::kmer(keys[s - 1], k, cp) && cp == c;
+    const bool same_next = s + 1 < n && KeyTraits<K>::kmer(keys[s + 1], k, cn) && cn == c;
+    if (!same_prev && !same_next) {
+        table[c] = make_uint2((uint32_t)l, SIG_FLAG | (side_sig(R, n, l - 4) << 12) | side_sig(R, n, l + k));
+    } else {
+        if (!same_prev) table[c].x = (uint32_t)s;
+        if (!same_next) table[c].y = (uint32_t)s + 1u;
+    }
 }
 
 // ------------------------------------------------------------------ MEM scan (seed and extend)
@@ -265,7 +309,7 @@ __global__ void __launch_bounds__(128) seed_extend_kernel(const uint8_t* __restr
                 const uint32_t rl = (e.y >> 12) & 0xfffu, rr = e.y & 0xfffu;
                 if (ql != rl && qr != rr) return;
             }
-        } else { lo = (int)e.x; hi = lo + (int)e.y; }
+        } else { lo = (int)e.x; hi = (int)e.y; }
     } else {
         // k-mer with N: binary search the suffix array (rare)
         int a = 0, b = n;
@@ -512,7 +556,7 @@ __global__ void pass2b_kernel(const uint32_t* __restrict__ ck, int ncand, const 
 }
 
 // ------------------------------------------------------------------ host driver
-struct WindowIndexInfo { int rounds = 0; int64_t unsorted_after_sort = 0; bool two_bit = false; };
+struct WindowIndexInfo { int rounds = 0; int64_t unsorted_after_sort = 0; bool two_bit = false; bool fallback = false; };
 
 class BigPath {
 public:
@@ -529,72 +573,88 @@ public:
     }
 
     // debug/test access (device pointers valid until the next build_index)
-    const uint32_t* d_sa() const { return sa_.get(); }
+    const uint32_t* d_sa() const { return sa_ptr_; }
     const int32_t* d_lrp() const { return lrp_.get(); }
 
+    // Index of one window.  Fast path: k-mer radix sort, tied groups ranked by direct text comparison (tie_sort_kernel), one
+    // finishing pass (LCP -> lrp, seed table).  Windows with large or deep repeats raise a device flag; it is read at the next
+    // natural synchronisation point (ensure_index) and the window is then re-indexed through the general prefix-doubling path.
     void build_index(const uint8_t* R, int n, int minsize, cudaStream_t st, bool two_bit = false) {
+        idx_R_ = R; idx_n_ = n; idx_minsize_ = minsize; idx_two_bit_ = two_bit;
+        const bool force_doubling = getenv("PB200_FORCE_DOUBLING") != nullptr;      // tests: always take the general path
+        build_index_impl(st, force_doubling);
+        if (!force_doubling) {
+            uint32_t* h = tie_host_.ensure(1);
+            PB_CUDA(cudaMemcpyAsync(h, tieflag_.get(), 4, cudaMemcpyDeviceToHost, st));
+            idx_pending_ = true;
+        }
+    }
+    // true if the window had to be re-indexed (anything computed from the index since build_index must be redone)
+    bool ensure_index(cudaStream_t st) {
+        if (!idx_pending_) return false;
+        PB_CUDA(cudaStreamSynchronize(st));
+        idx_pending_ = false;
+        if (*tie_host_.get() == 0) return false;
+        build_index_impl(st, true);
+        last_index.fallback = true;
+        return true;
+    }
+
+
+private:
+    template <class K>
+    void sort_and_finish(K* k0, K* k1, int end_bit, int64_t h0, cudaStream_t st, bool doubling) {
         const int TB = 256;
+        const int n = idx_n_;
+        const uint8_t* R = idx_R_;
         const unsigned nb = (unsigned)((n + TB - 1) / TB);
-        uint64_t* k0 = keys0_.ensure((size_t)n, false, st);
-        uint64_t* k1 = keys1_.ensure((size_t)n, false, st);
-        uint32_t* v0 = vals0_.ensure((size_t)n, false, st);
-        uint32_t* v1 = vals1_.ensure((size_t)n, false, st);
-        uint32_t* sa = sa_.ensure((size_t)n, false, st);
+        uint32_t* v0 = vals0_.get();
+        uint32_t* v1 = vals1_.get();
+        if (tm) tm->start(GpuTimers::T_INDEX_SORT, st);
+        const int res = sorter_.sort<K, uint32_t>(k0, k1, v0, v1, n, 0, end_bit, st);
+        const K* ks = res ? k1 : k0;
+        uint32_t* sa = res ? v1 : v0;                          // the sorted values ARE the suffix array (refined in place below)
+        sa_ptr_ = sa;
+        if (tm) tm->stop(GpuTimers::T_INDEX_SORT, st);
+        if (tm) tm->start(GpuTimers::T_INDEX_DOUBLING, st);
+        uint32_t* flag = tieflag_.ensure(4, false, st);
+        PB_CUDA(cudaMemsetAsync(flag, 0, 4, st));
+        if (!doubling) {
+            const int64_t per_block = (int64_t)TB * TIE_ITEMS;
+            pb200::launch(tie_sort_kernel<K>, (unsigned)((n + per_block - 1) / per_block), TB, 0, st, ks, n, R, sa, flag);
+        } else {
+            refine_by_doubling(ks, sa, h0, st);
+        }
+        if (tm) tm->stop(GpuTimers::T_INDEX_DOUBLING, st);
+        if (tm) tm->start(GpuTimers::T_INDEX_LCP, st);
+        const size_t tsize = (size_t)1 << (2 * seed_k_);
+        uint2* table = table_.ensure(tsize, false, st);
+        PB_CUDA(cudaMemsetAsync(table, 0, tsize * sizeof(uint2), st));
+        pb200::launch(index_finish_kernel<K>, nb, TB, 0, st, ks, sa, R, n, seed_k_, lrp_.get(), table);
+        if (tm) tm->stop(GpuTimers::T_INDEX_LCP, st);
+    }
+
+    // general path: prefix doubling (Larsson-Sadakane with discarding) on the groups the k-mer sort left tied
+    template <class K>
+    void refine_by_doubling(const K* ks, uint32_t* sa, int64_t h0, cudaStream_t st) {
+        const int TB = 256;
+        const int n = idx_n_;
+        const unsigned nb = (unsigned)((n + TB - 1) / TB);
+        uint64_t* k0 = keys0_.get();
+        uint64_t* k1 = keys1_.get();
+        // the doubling rounds sort (key, value) pairs of their own: they must not clobber the sorted k-mer keys `ks` (needed by
+        // the finishing pass) nor `sa`
+        uint64_t* dk0 = dkeys0_.ensure((size_t)n, false, st);
+        uint64_t* dk1 = dkeys1_.ensure((size_t)n, false, st);
+        uint32_t* dv0 = dvals0_.ensure((size_t)n, false, st);
+        uint32_t* dv1 = dvals1_.ensure((size_t)n, false, st);
+        (void)k0; (void)k1;
         uint32_t* rank = rank_.ensure((size_t)n, false, st);
         uint32_t* tA = tmpA_.ensure((size_t)n + 1, false, st);
         uint32_t* tB = tmpB_.ensure((size_t)n + 1, false, st);
         uint32_t* tC = tmpC_.ensure((size_t)n + 1, false, st);
-        int32_t* lcp = lcp_.ensure((size_t)n + 1, false, st);
-        int32_t* lrp = lrp_.ensure((size_t)n, false, st);
         uint32_t* d_tot = total_.ensure(4, false, st);
-
-        seed_k_ = std::min(MAX_SEED_K, std::max(1, minsize));
-        const size_t tsize = (size_t)1 << (2 * seed_k_);
-        uint2* table = table_.ensure(tsize, false, st);
-        int64_t h0;
-        last_index.two_bit = two_bit;
-        if (two_bit) {
-            // N-free window: 32-bit keys of 16 bases, 4 one-sweep passes over (4 B key + 4 B value)
-            uint32_t* q0 = reinterpret_cast<uint32_t*>(k0);
-            uint32_t* q1 = reinterpret_cast<uint32_t*>(k1);
-            if (tm) tm->start(GpuTimers::T_INDEX_KEYS, st);
-            pb200::launch(make_keys2_kernel, nb, TB, 0, st, R, n, q0, v0);
-            if (tm) tm->stop(GpuTimers::T_INDEX_KEYS, st);
-            if (tm) tm->start(GpuTimers::T_INDEX_SORT, st);
-            int res = sorter_.sort<uint32_t, uint32_t>(q0, q1, v0, v1, n, 0, 2 * KEY2_BASES, st);
-            const uint32_t* ks = res ? q1 : q0;
-            const uint32_t* vs = res ? v1 : v0;
-            PB_CUDA(cudaMemcpyAsync(sa, vs, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
-            if (tm) tm->stop(GpuTimers::T_INDEX_SORT, st);
-            if (tm) tm->start(GpuTimers::T_INDEX_TABLE, st);
-            PB_CUDA(cudaMemsetAsync(table, 0, tsize * sizeof(uint2), st));
-            pb200::launch(kmer_table2_kernel, nb, TB, 0, st, ks, n, seed_k_, table);
-            pb200::launch(kmer_table_fix_kernel, (unsigned)((tsize + 255) / 256), 256, 0, st, table, tsize, vs, R, n, seed_k_);
-            if (tm) tm->stop(GpuTimers::T_INDEX_TABLE, st);
-            if (tm) tm->start(GpuTimers::T_INDEX_DOUBLING, st);
-            pb200::launch(head_flags2_kernel, nb, TB, 0, st, ks, n, tA /*flag*/, tB /*hv*/);
-            h0 = KEY2_BASES;
-        } else {
-            if (tm) tm->start(GpuTimers::T_INDEX_KEYS, st);
-            pb200::launch(make_keys_kernel, nb, TB, 0, st, R, n, k0, v0);
-            if (tm) tm->stop(GpuTimers::T_INDEX_KEYS, st);
-            if (tm) tm->start(GpuTimers::T_INDEX_SORT, st);
-            int res = sorter_.sort<uint64_t, uint32_t>(k0, k1, v0, v1, n, 0, 3 * KEY_BASES, st);
-            const uint64_t* ks = res ? k1 : k0;
-            const uint32_t* vs = res ? v1 : v0;
-            PB_CUDA(cudaMemcpyAsync(sa, vs, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
-            if (tm) tm->stop(GpuTimers::T_INDEX_SORT, st);
-            // seed table over the sorted 21-mer keys (buckets are unaffected by the refinement of tied groups)
-            if (tm) tm->start(GpuTimers::T_INDEX_TABLE, st);
-            PB_CUDA(cudaMemsetAsync(table, 0, tsize * sizeof(uint2), st));
-            pb200::launch(kmer_table_kernel, nb, TB, 0, st, ks, n, seed_k_, table);
-            pb200::launch(kmer_table_fix_kernel, (unsigned)((tsize + 255) / 256), 256, 0, st, table, tsize, vs, R, n, seed_k_);
-            if (tm) tm->stop(GpuTimers::T_INDEX_TABLE, st);
-            // prefix doubling on the groups the 21-mer sort left tied
-            if (tm) tm->start(GpuTimers::T_INDEX_DOUBLING, st);
-            pb200::launch(head_flags_kernel, nb, TB, 0, st, ks, n, tA /*flag*/, tB /*hv*/);
-            h0 = KEY_BASES;
-        }
+        pb200::launch(head_flags_kernel<K>, nb, TB, 0, st, ks, n, tA /*flag*/, tB /*hv*/);
         scanner_.scan<prim::OpMax, false>(tB, tB, n, nullptr, st);                 // tB = head index per SA slot
         pb200::launch(rank_scatter_kernel, nb, TB, 0, st, sa, tB, n, rank);
         pb200::launch(mark_unsorted_kernel, nb, TB, 0, st, tA, n, tC /*u*/);
@@ -604,43 +664,68 @@ public:
         PB_CUDA(cudaStreamSynchronize(st));
         last_index.unsorted_after_sort = U;
         last_index.rounds = 0;
-        if (U > 0) {
-            uint32_t* cs = cs0_.ensure((size_t)U, false, st);
-            uint32_t* cs2 = cs1_.ensure((size_t)U, false, st);
-            pb200::launch(compact_kernel, nb, TB, 0, st, tC, tB, n, nullptr, cs);
-            int nbits = 1;
-            while (((int64_t)1 << nbits) < (int64_t)n + 1) ++nbits;
-            int64_t h = h0;
-            while (U > 0) {
-                const unsigned ub = (unsigned)((U + TB - 1) / TB);
-                pb200::launch(dbl_keys_kernel, ub, TB, 0, st, cs, (int)U, sa, rank, n, (int)std::min<int64_t>(h, n), nbits, k0, v0);
-                int r2 = sorter_.sort<uint64_t, uint32_t>(k0, k1, v0, v1, U, 0, 2 * nbits + 1, st);
-                const uint64_t* k2 = r2 ? k1 : k0;
-                const uint32_t* v2 = r2 ? v1 : v0;
-                pb200::launch(dbl_writeback_kernel, ub, TB, 0, st, cs, (int)U, k2, v2, sa, tA /*cflag*/, tB /*hv*/);
-                scanner_.scan<prim::OpMax, false>(tB, tB, U, nullptr, st);         // head per compact slot
-                pb200::launch(dbl_rank_kernel, ub, TB, 0, st, v2, tB, (int)U, rank);
-                pb200::launch(mark_unsorted_kernel, ub, TB, 0, st, tA, (int)U, tC);
-                scanner_.scan<prim::OpSum, true>(tC, tB, U, d_tot, st);
-                uint32_t U2 = 0;
-                PB_CUDA(cudaMemcpyAsync(&U2, d_tot, 4, cudaMemcpyDeviceToHost, st));
-                PB_CUDA(cudaStreamSynchronize(st));
-                if (U2 > 0) pb200::launch(compact_kernel, ub, TB, 0, st, tC, tB, (int)U, cs, cs2);
-                std::swap(cs, cs2);
-                U = U2;
-                h *= 2;
-                last_index.rounds++;
-                if (last_index.rounds > 40) throw CudaError("prefix doubling did not converge");
-            }
+        if (U == 0) return;
+        uint32_t* cs = cs0_.ensure((size_t)U, false, st);
+        uint32_t* cs2 = cs1_.ensure((size_t)U, false, st);
+        pb200::launch(compact_kernel, nb, TB, 0, st, tC, tB, n, nullptr, cs);
+        int nbits = 1;
+        while (((int64_t)1 << nbits) < (int64_t)n + 1) ++nbits;
+        int64_t h = h0;
+        while (U > 0) {
+            const unsigned ub = (unsigned)((U + TB - 1) / TB);
+            pb200::launch(dbl_keys_kernel, ub, TB, 0, st, cs, (int)U, sa, rank, n, (int)std::min<int64_t>(h, n), nbits, dk0, dv0);
+            int r2 = sorter_.sort<uint64_t, uint32_t>(dk0, dk1, dv0, dv1, U, 0, 2 * nbits + 1, st);
+            const uint64_t* k2 = r2 ? dk1 : dk0;
+            const uint32_t* v2 = r2 ? dv1 : dv0;
+            pb200::launch(dbl_writeback_kernel, ub, TB, 0, st, cs, (int)U, k2, v2, sa, tA /*cflag*/, tB /*hv*/);
+            scanner_.scan<prim::OpMax, false>(tB, tB, U, nullptr, st);         // head per compact slot
+            pb200::launch(dbl_rank_kernel, ub, TB, 0, st, v2, tB, (int)U, rank);
+            pb200::launch(mark_unsorted_kernel, ub, TB, 0, st, tA, (int)U, tC);
+            scanner_.scan<prim::OpSum, true>(tC, tB, U, d_tot, st);
+            uint32_t U2 = 0;
+            PB_CUDA(cudaMemcpyAsync(&U2, d_tot, 4, cudaMemcpyDeviceToHost, st));
+            PB_CUDA(cudaStreamSynchronize(st));
+            if (U2 > 0) pb200::launch(compact_kernel, ub, TB, 0, st, tC, tB, (int)U, cs, cs2);
+            std::swap(cs, cs2);
+            U = U2;
+            h *= 2;
+            last_index.rounds++;
+            if (last_index.rounds > 40) throw CudaError("prefix doubling did not converge");
         }
-        if (tm) tm->stop(GpuTimers::T_INDEX_DOUBLING, st);
+    }
 
-        if (tm) tm->start(GpuTimers::T_INDEX_LCP, st);
-        pb200::launch(lcp_kernel, (unsigned)((n + 1 + TB - 1) / TB), TB, 0, st, R, n, sa, lcp);
-        pb200::launch(lrp_kernel, nb, TB, 0, st, sa, lcp, n, lrp);
-        if (tm) tm->stop(GpuTimers::T_INDEX_LCP, st);
+    void build_index_impl(cudaStream_t st, bool doubling) {
+        const int TB = 256;
+        const int n = idx_n_;
+        const uint8_t* R = idx_R_;
+        const unsigned nb = (unsigned)((n + TB - 1) / TB);
+        uint64_t* k0 = keys0_.ensure((size_t)n, false, st);
+        uint64_t* k1 = keys1_.ensure((size_t)n, false, st);
+        uint32_t* v0 = vals0_.ensure((size_t)n, false, st);
+        vals1_.ensure((size_t)n, false, st);
+        lrp_.ensure((size_t)n, false, st);
+        seed_k_ = std::min(MAX_SEED_K, std::max(1, idx_minsize_));
+        last_index.two_bit = idx_two_bit_;
+        last_index.fallback = false;
+        last_index.rounds = 0;
+        last_index.unsorted_after_sort = -1;
+        if (idx_two_bit_) {
+            // N-free window: 32-bit keys of 16 bases, 4 radix passes over (4 B key + 4 B value)
+            uint32_t* q0 = reinterpret_cast<uint32_t*>(k0);
+            uint32_t* q1 = reinterpret_cast<uint32_t*>(k1);
+            if (tm) tm->start(GpuTimers::T_INDEX_KEYS, st);
+            pb200::launch(make_keys2_kernel, nb, TB, 0, st, R, n, q0, v0);
+            if (tm) tm->stop(GpuTimers::T_INDEX_KEYS, st);
+            sort_and_finish<uint32_t>(q0, q1, 2 * KEY2_BASES, KEY2_BASES, st, doubling);
+        } else {
+            if (tm) tm->start(GpuTimers::T_INDEX_KEYS, st);
+            pb200::launch(make_keys_kernel, nb, TB, 0, st, R, n, k0, v0);
+            if (tm) tm->stop(GpuTimers::T_INDEX_KEYS, st);
+            sort_and_finish<uint64_t>(k0, k1, 3 * KEY_BASES, KEY_BASES, st, doubling);
+        }
         PB_CUDA(cudaGetLastError());
     }
+public:
 
     // ---- staged scan (the single-GPU path runs the stages back to back; the sharded path exchanges between them) ----
     // stage 1: MEM events of the given strands (2 per local query), ordered by (strand, l) and scanned
@@ -666,10 +751,11 @@ public:
             long long samples = ((long long)max_m + step - 1) / step;
             dim3 grid((unsigned)((samples + 127) / 128), (unsigned)std::max(ns, 1));
             if (samples > 0 && ns > 0)
-                pb200::launch(seed_extend_kernel, grid, 128, 0, st, R, n, sa_.get(), lrp_.get(), table_.get(), k, step, minsize, d_str, ek, ev,
+                pb200::launch(seed_extend_kernel, grid, 128, 0, st, R, n, sa_ptr_, lrp_.get(), table_.get(), k, step, minsize, d_str, ek, ev,
                               d_cnt, (unsigned long long)cap);
             PB_CUDA(cudaMemcpyAsync(&E, d_cnt, 8, cudaMemcpyDeviceToHost, st));
             PB_CUDA(cudaStreamSynchronize(st));
+            if (ensure_index(st)) continue;                 // the window needed the general index path: scan again
             if (E <= cap) break;
             cap = (size_t)E + (size_t)E / 8 + 1024;
             ev_cap_hint_ = cap;
@@ -813,13 +899,14 @@ public:
         return tot;
     }
     // multi-GPU: device pointers of the window index (for the broadcast from the building rank)
-    uint32_t* index_sa() { return sa_.get(); }
+    uint32_t* index_sa() { return sa_ptr_; }
     int32_t* index_lrp() { return lrp_.get(); }
     uint2* index_table() { return table_.get(); }
     size_t index_table_entries() const { return (size_t)1 << (2 * seed_k_); }
     void alloc_index(int n, int minsize, cudaStream_t st) {      // receiving side of the broadcast
         seed_k_ = std::min(MAX_SEED_K, std::max(1, minsize));
-        sa_.ensure((size_t)n, false, st);
+        sa_ptr_ = vals0_.ensure((size_t)n, false, st);
+        idx_pending_ = false;
         lrp_.ensure((size_t)n, false, st);
         table_.ensure(index_table_entries(), false, st);
     }
@@ -828,9 +915,14 @@ public:
 private:
     rsort::RadixSorter sorter_;
     prim::Scanner scanner_;
-    DevBuf<uint64_t> keys0_, keys1_, evk0_, evk1_, evv0_, evv1_;
-    DevBuf<uint32_t> vals0_, vals1_, sa_, rank_, tmpA_, tmpB_, tmpC_, cs0_, cs1_, total_, seglo_, seghi_, evl_, ck_;
-    DevBuf<int32_t> lcp_, lrp_, mup_, mep_, olon_, osp_;
+    DevBuf<uint64_t> keys0_, keys1_, dkeys0_, dkeys1_, evk0_, evk1_, evv0_, evv1_;
+    DevBuf<uint32_t> vals0_, vals1_, dvals0_, dvals1_, rank_, tmpA_, tmpB_, tmpC_, cs0_, cs1_, total_, seglo_, seghi_, evl_, ck_, tieflag_;
+    DevBuf<int32_t> lrp_, mup_, mep_, olon_, osp_;
+    PinBuf<uint32_t> tie_host_;
+    uint32_t* sa_ptr_ = nullptr;             // suffix array of the current window (lives in one of the sort's value buffers)
+    const uint8_t* idx_R_ = nullptr;
+    int idx_n_ = 0, idx_minsize_ = 0;
+    bool idx_two_bit_ = false, idx_pending_ = false;
     DevBuf<uint8_t> ofwd_;
     DevBuf<int4> states_, p2tmp_;
     DevBuf<uint2> table_;

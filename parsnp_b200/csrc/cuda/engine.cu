@@ -67,10 +67,11 @@ public:
         force_big_ = (fp && std::string(fp) == "big") ? 1 : 0;
         const char* fk = getenv("PB200_FORCE_3BIT_KEYS");  // tests: always use the 21-mer 3-bit key path
         force_3bit_ = fk && fk[0] == '1';
-        // {n_cap, m_cap, event store capacity (all strands), candidate capacity, threads}
-        classes_[0] = small::ClassCfg{256, 512, 512, 64, 128};
-        classes_[1] = small::ClassCfg{1024, 2048, 2048, 256, 256};
-        classes_[2] = small::ClassCfg{4096, 8192, 4096, 512, 256};
+        // {n_cap, m_cap, event store capacity (all strands), candidate capacity, threads,
+        //  group text bytes (>= 2 m_cap), group seed rows (>= m_cap, multiple of 4), seed-hit queue, staged events}
+        classes_[0] = small::ClassCfg{256, 512, 512, 64, 128, 4096, 1024, 1024, 192};
+        classes_[1] = small::ClassCfg{1024, 2048, 2048, 256, 256, 8192, 2048, 4096, 512};
+        classes_[2] = small::ClassCfg{4096, 8192, 3072, 512, 256, 16384, 8192, 8192, 1024};
         PB_CUDA(cudaFuncSetAttribute(small::small_region_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
     ~CudaEngine() override {
@@ -215,7 +216,7 @@ public:
             w_strands_[2 * q] = big::StrandDesc{text_.get() + gfwd_[g] + qs[q], (int32_t)ql[q], 0};
             w_strands_[2 * q + 1] = big::StrandDesc{text_.get() + grc_[g] + (len_[g] - qs[q] - ql[q]), (int32_t)ql[q], 0};
         }
-        if (build_index) big_.build_index(w_R_, (int)t.ref_len, t.minsize, st_, window_is_n_free(t.ref_start, t.ref_len));
+        if (build_index) { big_.build_index(w_R_, (int)t.ref_len, t.minsize, st_, window_is_n_free(t.ref_start, t.ref_len)); big_.ensure_index(st_); }
         else big_.alloc_index((int)t.ref_len, t.minsize, st_);
         PB_CUDA(cudaStreamSynchronize(st_));
         big_windows++;
@@ -278,10 +279,12 @@ public:
     void debug_index(int64_t ref_start, int n, int minsize, uint32_t* sa, int32_t* lrp) {
         PB_CUDA(cudaSetDevice(device_));
         big_.build_index(text_.get() + gfwd_[0] + ref_start, n, minsize, st_, window_is_n_free(ref_start, n));
+        big_.ensure_index(st_);
         PB_CUDA(cudaMemcpyAsync(sa, big_.d_sa(), (size_t)n * 4, cudaMemcpyDeviceToHost, st_));
         PB_CUDA(cudaMemcpyAsync(lrp, big_.d_lrp(), (size_t)n * 4, cudaMemcpyDeviceToHost, st_));
         PB_CUDA(cudaStreamSynchronize(st_));
     }
+    int debug_index_flags() const { return (big_.last_index.fallback ? 1 : 0) | (big_.last_index.two_bit ? 2 : 0); }
     void set_force_class(int c) { force_big_ = c; }
     void collect_timers() { cudaSetDevice(device_); timers.collect(st_); }
     bool window_is_n_free(int64_t start, int64_t len) const {
@@ -641,6 +644,9 @@ void pb200_engine_reset_timers(pb200_genomes* g) {
 int pb200_debug_index(pb200_genomes* g, int64_t ref_start, int32_t n, int32_t minsize, uint32_t* sa, int32_t* lrp) {
     return guarded([&]() { g->eng->debug_index(ref_start, n, minsize, sa, lrp); return (int)PB200_OK; });
 }
+
+// test hook: bit 0 = the last debug_index window went through the general prefix-doubling path, bit 1 = 2-bit keys
+int pb200_debug_index_flags(pb200_genomes* g) { return g->eng->debug_index_flags(); }
 
 int pb200_comm_set(pb200_genomes* g, int rank, int world, pb200_allgather_cb ag, pb200_allreduce_cb ar, pb200_bcast_cb bc, void* user,
                    int bcast_index) {

@@ -3,11 +3,18 @@
 // reference window and query regions fit in shared memory.  The recursion of Aligner::doWork (src/parsnp.cpp:173-317)
 // issues 10^5..10^6 such windows of ~10^2 bp; the reference builds and frees a suffix graph for each.
 //
-// In shared memory: the reference window R, lrp[l] (longest repeated prefix, brute force), the running Master (UP, EP),
-// one query strand at a time, the strand's MEM events.  Pass 1 folds all queries into Master and emits candidate
-// positions; pass 2 (only if there are candidates) replays the fold at the candidate positions to recover every
-// query's strand flag and start position.  MEMs are found by sampling every minsize-th cell of each diagonal and
-// extending (a run of >= minsize matches must contain a sampled cell).
+// The queries of a window are processed in GROUPS (as many consecutive queries as fit the shared-memory text buffer), each
+// group in a few block-wide stages so that every stage is a flat, balanced loop over all queries of the group:
+//   1. load both strands of the group's query regions
+//   2. pack the sampled seed rows (4 bases, 3 bits each; forward and reverse strand of one row share a 32-bit word)
+//   3. dense seed grid: reference positions x rows, four rows per 128-bit shared-memory load -> queue of seed hits
+//   4. one thread per queued hit: left extension (de-duplication: a match of >= minsize bases contains exactly one seed whose
+//      left extension is shorter than the seed spacing), right extension -> MEM events (staging buffer)
+//   5. one warp per event: uniqueness floor lrp[l] on demand (cached per reference position)
+//   6. counting sort of the staged events by query into the window's event store
+//   7. one thread per reference position: fold the group's queries (ini order) into the running Master (UP, EP)
+// After the last group: ordered emission of candidate positions and, for those only, a replay of the fold from the stored
+// events to recover every query's strand flag and start position.
 #pragma once
 #include "util.cuh"
 
@@ -21,19 +28,28 @@ struct TaskDev {
     int64_t qcoord_off;   // offset into qcoords: start[nq], len[nq] (int32 each)
 };
 struct TaskOut {
-    int32_t ncand;        // -1 = overflow (events or candidates): the task must be re-run with larger capacity
+    int32_t ncand;        // < 0 = overflow (-1: a per-CTA capacity, -2: the global candidate buffer): the task must be re-run
     int32_t pad;
     int64_t cand_base;    // first candidate slot in the global candidate arrays
 };
-struct Ev { uint16_t l, e, u, pad; int32_t d1; };      // ref start, ref end, uniqueness floor u = l + lrp[l], diagonal (query start - ref start)
+// MEM event: le = ref start | ref end << 16 ; ut = uniqueness floor u = l + lrp[l] | tag << 16 ; d1 = query start - ref start
+// tag: bit0 = unique in R (an event of Find_UM), bit1 = reverse strand, bits 2.. = query index inside its group (staging only)
+struct Ev { uint32_t le, ut; int32_t d1; };
+
+constexpr int GROUP_MAX = 64;           // queries per group
 
 struct ClassCfg {
     int n_cap, m_cap, ev_cap, cand_cap, threads;
+    int qbuf;             // bytes of query text per group (both strands); >= 2 * al(m_cap)
+    int rows_cap;         // seed rows per group; >= m_cap
+    int hq_cap;           // seed-hit queue entries per group
+    int stg_cap;          // staged events per group
     __host__ __device__ static size_t al(size_t x) { return (x + 15) & ~(size_t)15; }
     // ev_cap = capacity of the event store for ALL strands of ALL queries of the window
     __host__ __device__ size_t smem_bytes(int nq) const {
-        return al(n_cap) + 2 * al(m_cap) + 2 * al(2 * (size_t)m_cap) + 4 * al(2 * (size_t)n_cap) + al((size_t)ev_cap * sizeof(Ev)) + al(2 * (size_t)(2 * nq + 2)) +
-               2 * al(2 * (size_t)cand_cap) + 64;
+        return al(n_cap) + 4 * al(2 * (size_t)n_cap) + al((size_t)qbuf) + al(4 * (size_t)rows_cap) + al((size_t)rows_cap) + al(4 * (size_t)hq_cap) +
+               al((size_t)stg_cap * sizeof(Ev)) + al((size_t)ev_cap * sizeof(Ev)) + al(2 * (size_t)(nq + 2)) + 2 * al(2 * (size_t)cand_cap) +
+               al(2 * 3 * (size_t)(GROUP_MAX + 1)) + al(4 * 2 * (size_t)GROUP_MAX) + 64;
     }
 };
 
@@ -70,68 +86,37 @@ __device__ __forceinline__ int smatch_bwd(const uint8_t* a, const uint8_t* b, in
     return c;
 }
 
-// MEM events of one query (both strands) against R.  Seeds = SEED_K-base matches (packed 3 bits per base in R4[l]) at every
-// (minsize-SEED_K+1)-th query position against every reference position: a dense rows x n grid without divergence in
-// the enumeration, ~1/256 random hits.  A match of >= minsize bases contains exactly one seed whose left extension is
-// shorter than the seed spacing, and that seed reports it.  Events are stored unconditionally (strand in pad bit 1);
-// uniqueness is decided afterwards by resolve_unique().
 constexpr int SEED_K = 4;
 __device__ __forceinline__ uint32_t pack4(const uint8_t* p) {
     return (uint32_t)p[0] | ((uint32_t)p[1] << 3) | ((uint32_t)p[2] << 6) | ((uint32_t)p[3] << 9);
 }
-__device__ __forceinline__ void seed_hit(const uint8_t* __restrict__ R, int n, const uint8_t* __restrict__ Q, int m, int j, int l, int step,
-                                         int minsize, int strand, Ev* __restrict__ ev, int* __restrict__ ev_n, int ev_cap) {
-    const int cmax = min(step, min(j, l));
-    int c = 0;
-    while (c < cmax && Q[j - 1 - c] == R[l - 1 - c]) ++c;
-    if (c >= step) return;                        // the previous seed row lies in the same match
-    const int emax = min(m - j, n - l);
-    const int e = SEED_K + smatch_fwd(Q + j + SEED_K, R + l + SEED_K, emax - SEED_K);
-    const int L = c + e, l0 = l - c;
-    if (L < minsize) return;
-    int slot = atomicAdd(ev_n, 1);
-    if (slot < ev_cap) {
-        ev[slot].l = (uint16_t)l0; ev[slot].e = (uint16_t)(l0 + L); ev[slot].u = 0; ev[slot].pad = (uint16_t)(strand << 1);
-        ev[slot].d1 = (j - c) - l0;
-    }
-}
-// Q4f/Q4c: packed seed codes of the sampled query rows (filled by the caller, one row per thread)
-__device__ inline void find_events(const uint8_t* __restrict__ R, const uint16_t* __restrict__ R4, int n,
-                                   const uint8_t* __restrict__ Qf, const uint8_t* __restrict__ Qc, int m,
-                                   const uint16_t* __restrict__ Q4f, const uint16_t* __restrict__ Q4c, int nrows, int step,
-                                   int minsize, Ev* __restrict__ ev, int* __restrict__ ev_n, int ev_cap, int nthreads) {
-    for (int l = threadIdx.x; l + SEED_K <= n; l += nthreads) {
-        const uint32_t r4 = R4[l];
-        for (int row = 0; row < nrows; ++row) {
-            const uint32_t qf = Q4f[row], qc = Q4c[row];       // same address for the whole warp: broadcast
-            if (r4 == qf) seed_hit(R, n, Qf, m, row * step, l, step, minsize, 0, ev, ev_n, ev_cap);
-            if (r4 == qc) seed_hit(R, n, Qc, m, row * step, l, step, minsize, 1, ev, ev_n, ev_cap);
-        }
-    }
-}
-// A1 on demand: for every new event, lrp[l] = longest prefix of R[l..) occurring at another position of R (one warp per
+
+// A1 on demand: for every staged event, lrp[l] = longest prefix of R[l..) occurring at another position of R (one warp per
 // event, lanes stride over the other positions; cached per reference position), then u = l + lrp and validity L > lrp.
-__device__ inline void resolve_unique(const uint8_t* __restrict__ R, int n, uint16_t* __restrict__ lrp, Ev* __restrict__ ev, int e_begin,
-                                      int e_end, int nthreads) {
+// Repeats shorter than the 4-base seed are reported as 0: every event has L >= minsize >= 4, and a floor u <= l + 3 can
+// neither invalidate the event nor reach an emitted candidate's end (emission needs EP - k >= minsize with k >= l).
+__device__ inline void resolve_unique(const uint8_t* __restrict__ R, const uint16_t* __restrict__ R4, int n, uint16_t* __restrict__ lrp,
+                                      Ev* __restrict__ ev, int count, int nthreads) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = nthreads >> 5;
-    for (int i = e_begin + warp; i < e_end; i += nwarps) {
-        const int l = ev[i].l;
+    for (int i = warp; i < count; i += nwarps) {
+        const uint32_t le = ev[i].le;
+        const int l = (int)(le & 0xffffu);
         int v = lrp[l];
         if (v == LRP_UNKNOWN) {
             int best = 0;
-            const uint8_t c0 = R[l];
-            for (int l2 = lane; l2 < n; l2 += 32) {
-                if (l2 == l || R[l2] != c0) continue;
-                best = max(best, 1 + smatch_fwd(R + l + 1, R + l2 + 1, n - max(l, l2) - 1));
+            const uint32_t r4 = R4[l];
+            for (int l2 = lane; l2 + SEED_K <= n; l2 += 32) {
+                if (l2 == l || R4[l2] != r4) continue;
+                best = max(best, SEED_K + smatch_fwd(R + l + SEED_K, R + l2 + SEED_K, n - max(l, l2) - SEED_K));
             }
             for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
             v = best;
             if (lane == 0) lrp[l] = (uint16_t)v;      // racing warps store the same value
         }
         if (lane == 0) {
-            const int L = (int)ev[i].e - l;
-            ev[i].u = (uint16_t)(l + v);
-            ev[i].pad = (uint16_t)((ev[i].pad & 2) | ((L > v) ? 1 : 0));   // bit0: unique in R (an event of Find_UM); bit1: reverse strand
+            const int L = (int)(le >> 16) - l;
+            const uint32_t tag = (ev[i].ut >> 16) & ~1u;
+            ev[i].ut = (uint32_t)(l + v) | ((tag | (L > v ? 1u : 0u)) << 16);
         }
     }
 }
@@ -147,17 +132,17 @@ __device__ __forceinline__ void acc_add(Acc& a, int u, int e, int d1) {
 __device__ __forceinline__ void eval_at(const Ev* __restrict__ ev, int ne, int k, StrandVal& F, StrandVal& C) {
     Acc af = {0, 0, 0, 0}, ac = {0, 0, 0, 0};
     for (int i = 0; i < ne; ++i) {
-        const int l = ev[i].l;
-        const int tag = ev[i].pad;
-        if (l > k || !(tag & 1)) continue;
-        if (tag & 2) acc_add(ac, (int)ev[i].u, (int)ev[i].e, ev[i].d1);
-        else acc_add(af, (int)ev[i].u, (int)ev[i].e, ev[i].d1);
+        const uint32_t le = ev[i].le, ut = ev[i].ut;
+        const int l = (int)(le & 0xffffu);
+        if (l > k || !(ut & 0x10000u)) continue;
+        if (ut & 0x20000u) acc_add(ac, (int)(ut & 0xffffu), (int)(le >> 16), ev[i].d1);
+        else acc_add(af, (int)(ut & 0xffffu), (int)(le >> 16), ev[i].d1);
     }
     F.UP = max(af.fl, af.t2); F.EP = max(af.t1, af.fl); F.d1 = af.dd;
     C.UP = max(ac.fl, ac.t2); C.EP = max(ac.t1, ac.fl); C.d1 = ac.dd;
 }
 
-__global__ void __launch_bounds__(SM_MAX_THREADS, 6) small_region_kernel(
+__global__ void __launch_bounds__(SM_MAX_THREADS, 4) small_region_kernel(
     const uint8_t* __restrict__ text, const int64_t* __restrict__ gbase_fwd, const int64_t* __restrict__ gbase_rc,
     const int64_t* __restrict__ glen, int nq, const TaskDev* __restrict__ tasks, const int32_t* __restrict__ qcoords,
     const int32_t* __restrict__ task_ids, int ntasks, ClassCfg cfg, TaskOut* __restrict__ outs,
@@ -172,19 +157,28 @@ __global__ void __launch_bounds__(SM_MAX_THREADS, 6) small_region_kernel(
     const int n = tk.n, minsize = tk.minsize;
     size_t off = 0;
     uint8_t* R = smem + off; off += ClassCfg::al(cfg.n_cap);
-    uint8_t* Qf = smem + off; off += ClassCfg::al(cfg.m_cap);
-    uint8_t* Qc = smem + off; off += ClassCfg::al(cfg.m_cap);
     uint16_t* lrp = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
     uint16_t* R4 = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
-    uint16_t* Q4f = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.m_cap);
-    uint16_t* Q4c = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.m_cap);
     uint16_t* MUP = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
     uint16_t* MEP = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
+    uint8_t* QB = smem + off; off += ClassCfg::al((size_t)cfg.qbuf);                                              // group query text
+    uint32_t* Q4 = reinterpret_cast<uint32_t*>(smem + off); off += ClassCfg::al(4 * (size_t)cfg.rows_cap);       // seed rows: fwd | rc << 16
+    uint8_t* rowq = smem + off; off += ClassCfg::al((size_t)cfg.rows_cap);                                        // group-local query of each row
+    uint32_t* HQ = reinterpret_cast<uint32_t*>(smem + off); off += ClassCfg::al(4 * (size_t)cfg.hq_cap);         // seed hits: l | row << 12 | strand << 31
+    Ev* stg = reinterpret_cast<Ev*>(smem + off); off += ClassCfg::al((size_t)cfg.stg_cap * sizeof(Ev));
     Ev* evs = reinterpret_cast<Ev*>(smem + off); off += ClassCfg::al((size_t)cfg.ev_cap * sizeof(Ev));
-    uint16_t* evoff = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)(2 * nq + 2));   // [2*nq+1] strand starts
+    uint16_t* evoff = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)(nq + 2));        // [nq+1] first event of each query
     uint16_t* candK = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.cand_cap);
     uint16_t* candM = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.cand_cap);
-    int* s_int = reinterpret_cast<int*>(smem + off);     // [0]=event count [2]=ncand [3]=overflow ; [4..5] = cand base (int64)
+    uint16_t* qoff = reinterpret_cast<uint16_t*>(smem + off);                                                     // [GROUP_MAX+1] byte offset of the query's text in QB
+    uint16_t* rowoff = qoff + (GROUP_MAX + 1);                                                                    // [GROUP_MAX+1] first seed row
+    uint16_t* qm = rowoff + (GROUP_MAX + 1);                                                                      // [GROUP_MAX] region length
+    off += ClassCfg::al(2 * 3 * (size_t)(GROUP_MAX + 1));
+    int* qcnt = reinterpret_cast<int*>(smem + off);                                                               // [GROUP_MAX] staged events per query
+    int* qfill = qcnt + GROUP_MAX;
+    off += ClassCfg::al(4 * 2 * (size_t)GROUP_MAX);
+    // [0]=hit count [1]=staged events [2]=ncand [3]=overflow [4..5]=cand base (int64) [6]=group size
+    int* s_int = reinterpret_cast<int*>(smem + off);
     const int tid = threadIdx.x;
     const int32_t* qs = qcoords + tk.qcoord_off;
     const int32_t* ql = qs + nq;
@@ -192,39 +186,144 @@ __global__ void __launch_bounds__(SM_MAX_THREADS, 6) small_region_kernel(
     for (int i = tid; i < n; i += T) { R[i] = text[tk.ref_off + i]; MUP[i] = 0; MEP[i] = (uint16_t)n; lrp[i] = LRP_UNKNOWN; }
     if (tid < 8) s_int[tid] = 0;
     __syncthreads();
-    for (int i = tid; i + SEED_K <= n; i += T) R4[i] = (uint16_t)pack4(R + i);
-    __syncthreads();
+    const int nseed = n >= SEED_K ? n - SEED_K + 1 : 0;            // reference positions holding a seed
+    for (int i = tid; i < nseed; i += T) R4[i] = (uint16_t)pack4(R + i);
 
-    // pass 0: fold all queries (ini order) into Master, keeping every query's events in shared memory
-    int e0 = 0;
     const int step = max(1, minsize - SEED_K + 1);
-    for (int q = 0; q < nq; ++q) {
-        const int m = ql[q];
-        const int64_t g = q + 1;
-        const int64_t f_off = gbase_fwd[g] + qs[q];
-        const int64_t c_off = gbase_rc[g] + (glen[g] - qs[q] - m);
-        for (int i = tid; i < m; i += T) { Qf[i] = text[f_off + i]; Qc[i] = text[c_off + i]; }
+    int e0 = 0;                                                     // events stored so far (all earlier groups)
+    int q0 = 0;
+    while (q0 < nq) {
+        // ---- group [q0, q0 + G): as many queries as fit the text / row buffers (and a bounded expected number of seed hits)
+        if (tid == 0) {
+            int bytes = 0, rows = 0, g = 0;
+            while (q0 + g < nq && g < GROUP_MAX) {
+                const int m = ql[q0 + g];
+                const int nb = 2 * (int)ClassCfg::al((size_t)m);
+                const int nr = m >= SEED_K ? (m - SEED_K) / step + 1 : 0;
+                if (g > 0 && (bytes + nb > cfg.qbuf || rows + nr > cfg.rows_cap || (long long)(rows + nr) * nseed > 48ll * cfg.hq_cap)) break;
+                qoff[g] = (uint16_t)bytes; rowoff[g] = (uint16_t)rows; qm[g] = (uint16_t)m;
+                qcnt[g] = 0;
+                bytes += nb; rows += nr; ++g;
+            }
+            qoff[g] = (uint16_t)bytes; rowoff[g] = (uint16_t)rows;
+            s_int[6] = g; s_int[0] = 0; s_int[1] = 0;
+            if (bytes > cfg.qbuf || rows > cfg.rows_cap) s_int[3] = 1;      // (cannot happen for a correctly classified task)
+        }
         __syncthreads();
-        const int nrows = m >= SEED_K ? (m - SEED_K) / step + 1 : 0;
-        for (int row = tid; row < nrows; row += T) { Q4f[row] = (uint16_t)pack4(Qf + row * step); Q4c[row] = (uint16_t)pack4(Qc + row * step); }
+        const int G = s_int[6];
+        if (s_int[3]) break;
+        // ---- 1. both strands of every query region of the group
+        for (int g = 0; g < G; ++g) {
+            const int m = qm[g];
+            const int64_t gi = q0 + g + 1;
+            const int64_t f_off = gbase_fwd[gi] + qs[q0 + g];
+            const int64_t c_off = gbase_rc[gi] + (glen[gi] - qs[q0 + g] - m);
+            uint8_t* Qf = QB + qoff[g];
+            uint8_t* Qc = Qf + ClassCfg::al((size_t)m);
+            for (int i = tid; i < m; i += T) { Qf[i] = text[f_off + i]; Qc[i] = text[c_off + i]; }
+        }
         __syncthreads();
-        find_events(R, R4, n, Qf, Qc, m, Q4f, Q4c, nrows, step, minsize, evs, &s_int[0], cfg.ev_cap, T);
+        // ---- 2. seed rows
+        const int total_rows = rowoff[G];
+        for (int g = 0; g < G; ++g) {
+            const int m = qm[g];
+            const int r0 = rowoff[g], nr = rowoff[g + 1] - r0;
+            const uint8_t* Qf = QB + qoff[g];
+            const uint8_t* Qc = Qf + ClassCfg::al((size_t)m);
+            for (int row = tid; row < nr; row += T) {
+                Q4[r0 + row] = pack4(Qf + row * step) | (pack4(Qc + row * step) << 16);
+                rowq[r0 + row] = (uint8_t)g;
+            }
+        }
+        if (tid < 4 && total_rows + tid < ((total_rows + 3) & ~3)) Q4[total_rows + tid] = 0xffffffffu;     // pad to a multiple of 4 rows: matches nothing
         __syncthreads();
-        const int e2 = s_int[0];
-        if (e2 > cfg.ev_cap) { if (tid == 0) s_int[3] = 1; __syncthreads(); break; }
-        resolve_unique(R, n, lrp, evs, e0, e2, T);
-        if (tid == 0) { evoff[q] = (uint16_t)e0; evoff[q + 1] = (uint16_t)e2; }
+        // ---- 3. dense seed grid -> hit queue
+        {
+            const int nchunks = (total_rows + 3) >> 2;
+            const uint4* Q4v = reinterpret_cast<const uint4*>(Q4);
+            int l = tid, ch = 0;
+            while (nseed > 0 && l >= nseed) { l -= nseed; ++ch; }
+            while (nseed > 0 && ch < nchunks) {
+                const uint32_t r4 = R4[l];
+                const uint32_t rr = r4 | (r4 << 16);
+                const uint4 w = Q4v[ch];
+                const uint32_t x0 = w.x ^ rr, x1 = w.y ^ rr, x2 = w.z ^ rr, x3 = w.w ^ rr;
+                // a zero halfword in any of the four words = a seed hit on that row and strand
+                const uint32_t z = ((x0 - 0x00010001u) & ~x0) | ((x1 - 0x00010001u) & ~x1) | ((x2 - 0x00010001u) & ~x2) | ((x3 - 0x00010001u) & ~x3);
+                if (z & 0x80008000u) {
+                    const uint32_t xs[4] = {x0, x1, x2, x3};
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        if (!(xs[t] & 0xffffu)) { int slot = atomicAdd(&s_int[0], 1); if (slot < cfg.hq_cap) HQ[slot] = (uint32_t)l | ((uint32_t)(ch * 4 + t) << 12); }
+                        if (!(xs[t] >> 16)) { int slot = atomicAdd(&s_int[0], 1); if (slot < cfg.hq_cap) HQ[slot] = (uint32_t)l | ((uint32_t)(ch * 4 + t) << 12) | 0x80000000u; }
+                    }
+                }
+                l += T;
+                while (l >= nseed) { l -= nseed; ++ch; }
+            }
+        }
         __syncthreads();
+        const int nh = s_int[0];
+        if (nh > cfg.hq_cap) { if (tid == 0) s_int[3] = 1; __syncthreads(); break; }
+        // ---- 4. one thread per hit: extend left (de-duplication) and right -> staged MEM events
+        for (int h = tid; h < nh; h += T) {
+            const uint32_t hw = HQ[h];
+            const int l = (int)(hw & 0xfffu), row = (int)((hw >> 12) & 0x7ffffu), strand = (int)(hw >> 31);
+            const int g = rowq[row];
+            const int m = qm[g];
+            const int j = (row - rowoff[g]) * step;
+            const uint8_t* Q = QB + qoff[g] + (strand ? ClassCfg::al((size_t)m) : 0);
+            const int cmax = min(step, min(j, l));
+            const int c = smatch_bwd(Q + j, R + l, cmax);
+            if (c >= step) continue;                      // the previous seed row lies in the same match
+            const int emax = min(m - j, n - l);
+            const int e = SEED_K + smatch_fwd(Q + j + SEED_K, R + l + SEED_K, emax - SEED_K);
+            const int L = c + e, l0 = l - c;
+            if (L < minsize) continue;
+            const int slot = atomicAdd(&s_int[1], 1);
+            if (slot < cfg.stg_cap) {
+                stg[slot].le = (uint32_t)l0 | ((uint32_t)(l0 + L) << 16);
+                stg[slot].ut = ((uint32_t)(strand << 1) | ((uint32_t)g << 2)) << 16;
+                stg[slot].d1 = (j - c) - l0;
+                atomicAdd(&qcnt[g], 1);
+            }
+        }
+        __syncthreads();
+        const int ns = s_int[1];
+        if (ns > cfg.stg_cap || e0 + ns > cfg.ev_cap) { if (tid == 0) s_int[3] = 1; __syncthreads(); break; }
+        // ---- 5. uniqueness; thread 0 lays out the group's slice of the event store meanwhile
+        if (tid == 0) {
+            int run = e0;
+            for (int g = 0; g < G; ++g) { evoff[q0 + g] = (uint16_t)run; qfill[g] = run; run += qcnt[g]; }
+            evoff[q0 + G] = (uint16_t)run;
+        }
+        resolve_unique(R, R4, n, lrp, stg, ns, T);
+        __syncthreads();
+        // ---- 6. counting sort by query into the event store
+        for (int i = tid; i < ns; i += T) {
+            const Ev e = stg[i];
+            const int g = (int)(e.ut >> 18);
+            const int pos = atomicAdd(&qfill[g], 1);
+            evs[pos].le = e.le;
+            evs[pos].ut = e.ut & 0x3ffffu;
+            evs[pos].d1 = e.d1;
+        }
+        __syncthreads();
+        // ---- 7. fold the group's queries (ini order) into Master
         for (int k = tid; k < n; k += T) {
-            StrandVal F, C;
-            eval_at(evs + e0, e2 - e0, k, F, C);
             int mep = MEP[k], mup = MUP[k];
-            int fe = min(mep, F.EP), ce = min(mep, C.EP);
-            if (fe > ce) { mup = max(mup, F.UP); mep = fe; }
-            else { mup = max(mup, C.UP); mep = ce; }
+            for (int g = 0; g < G; ++g) {
+                const int a0 = evoff[q0 + g], a1 = evoff[q0 + g + 1];
+                StrandVal F, C;
+                eval_at(evs + a0, a1 - a0, k, F, C);
+                const int fe = min(mep, F.EP), ce = min(mep, C.EP);
+                if (fe > ce) { mup = max(mup, F.UP); mep = fe; }
+                else { mup = max(mup, C.UP); mep = ce; }
+            }
             MUP[k] = (uint16_t)mup; MEP[k] = (uint16_t)mep;
         }
-        e0 = e2;
+        e0 += ns;
+        q0 += G;
         __syncthreads();
     }
     __syncthreads();
@@ -262,7 +361,7 @@ __global__ void __launch_bounds__(SM_MAX_THREADS, 6) small_region_kernel(
     const int ovf = s_int[3];
     const int nc = ovf ? 0 : s_int[2];
     const int64_t base = *reinterpret_cast<int64_t*>(&s_int[4]);
-    // pass 1: replay the fold at the candidate positions from the stored events (strand flag + start per query)
+    // replay of the fold at the candidate positions from the stored events (strand flag + start per query)
     for (int c = tid; c < nc; c += T) {
         const int k = candK[c];
         int M = n;

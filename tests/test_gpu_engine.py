@@ -86,25 +86,49 @@ def _texts():
     out["ends_in_A"] = np.concatenate([A[rng.integers(0, 4, 3000)], np.full(23, ord("A"), np.uint8)])
     out["all_A"] = np.full(700, ord("A"), np.uint8)
     out["short"] = np.frombuffer(b"ACGTA", np.uint8)
+    t = A[rng.integers(0, 4, 30000)]
+    t[20000:23000] = t[1000:4000]            # one 3 kb duplication: tied pairs, ranked by direct text comparison
+    t[26000:27500] = t[2500:4000]            # third copy of its second half: tied triples
+    out["dup_3k"] = t
+    t = A[rng.integers(0, 4, 60000)]
+    t[35000:55000] = t[5000:25000]           # 20 kb duplication: deeper than the direct comparison goes -> general path
+    out["dup_20k"] = t
     return out
 
 
+# which index path each text must take when nothing is forced: False = tied groups ranked directly, True = prefix doubling
+_EXPECT_DOUBLING = {"tiny": False, "random_5k": False, "random_200k": False, "dup_3k": False, "ends_in_A": False, "short": False,
+                    "repeats_30k": True, "tandem": True, "all_A": True, "dup_20k": True}
+
+
+@pytest.mark.parametrize("doubling", [False, True])
 @pytest.mark.parametrize("three_bit", [False, True])
-@pytest.mark.parametrize("name", ["tiny", "random_5k", "repeats_30k", "tandem", "random_200k", "ends_in_A", "all_A", "short"])
-def test_suffix_index_matches_cpu(name, three_bit):
+@pytest.mark.parametrize("name", ["tiny", "random_5k", "repeats_30k", "tandem", "random_200k", "ends_in_A", "all_A", "short", "dup_3k", "dup_20k"])
+def test_suffix_index_matches_cpu(name, three_bit, doubling):
     """suffix array + longest-repeated-prefix; N-free windows take the 16-mer 2-bit key path unless forced to the 21-mer
-    3-bit one - both must give the true suffix order (window end sorts first)"""
+    3-bit one; tied k-mer groups are ranked by direct text comparison unless the window has large/deep repeats (or the test
+    forces it), then by prefix doubling - all four combinations must give the true suffix order (window end sorts first)"""
     text = np.ascontiguousarray(_texts()[name])
     if three_bit:
         os.environ["PB200_FORCE_3BIT_KEYS"] = "1"
+    if doubling:
+        os.environ["PB200_FORCE_DOUBLING"] = "1"
     try:
         G = api.Genomes([text, text[: max(3, len(text) // 2)].copy()])
+        sa, lrp = _debug_index(G, len(text))
+        lib = api.load()
+        lib.pb200_debug_index_flags.argtypes = [C.c_void_p]
+        lib.pb200_debug_index_flags.restype = C.c_int
+        flags = lib.pb200_debug_index_flags(G.h)
     finally:
         os.environ.pop("PB200_FORCE_3BIT_KEYS", None)
-    sa, lrp = _debug_index(G, len(text))
+        os.environ.pop("PB200_FORCE_DOUBLING", None)
     wsa, wlrp = cpu_sa_lrp(text)
     assert np.array_equal(sa, wsa)
     assert np.array_equal(lrp, wlrp)
+    assert bool(flags & 2) == (not three_bit and ord("N") not in text)
+    if not doubling:
+        assert bool(flags & 1) == _EXPECT_DOUBLING[name]
     G.close()
 
 
