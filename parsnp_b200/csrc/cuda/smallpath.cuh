@@ -6,10 +6,12 @@
 // The queries of a window are processed in GROUPS (as many consecutive queries as fit the shared-memory text buffer), each
 // group in a few block-wide stages so that every stage is a flat, balanced loop over all queries of the group:
 //   1. load both strands of the group's query regions
-//   2. pack the sampled seed rows (4 bases, 3 bits each; forward and reverse strand of one row share a 32-bit word)
-//   3. dense seed grid: reference positions x rows, four rows per 128-bit shared-memory load -> queue of seed hits
-//   4. one thread per queued hit: left extension (de-duplication: a match of >= minsize bases contains exactly one seed whose
-//      left extension is shorter than the seed spacing), right extension -> MEM events (staging buffer)
+//   2. pack the sampled seed rows: K bases at 3 bits each, every (minsize-K+1)-th query position, both strands.  K is chosen
+//      per window so that consecutive seeds of a diagonal abut or overlap (K >= (minsize+1)/2, 4 <= K <= 10)
+//   3. every (row, strand) looks its seed up in a hash table of the window's K-mers (open addressing in shared memory, built
+//      once per window).  A match of >= minsize bases contains exactly one seed whose left extension is shorter than the seed
+//      spacing; with abutting seeds that is the seed whose predecessor on the diagonal is NOT a hit, so only those are queued
+//   4. one thread per queued hit: left extension, right extension -> MEM events (staging buffer)
 //   5. one warp per event: uniqueness floor lrp[l] on demand (cached per reference position)
 //   6. counting sort of the staged events by query into the window's event store
 //   7. one thread per reference position: fold the group's queries (ini order) into the running Master (UP, EP)
@@ -41,13 +43,14 @@ constexpr int GROUP_MAX = 64;           // queries per group
 struct ClassCfg {
     int n_cap, m_cap, ev_cap, cand_cap, threads;
     int qbuf;             // bytes of query text per group (both strands); >= 2 * al(m_cap)
-    int rows_cap;         // seed rows per group; >= m_cap
+    int rows_cap;         // seed rows per group (incl. one pad row per query); >= m_cap
     int hq_cap;           // seed-hit queue entries per group
     int stg_cap;          // staged events per group
     __host__ __device__ static size_t al(size_t x) { return (x + 15) & ~(size_t)15; }
     // ev_cap = capacity of the event store for ALL strands of ALL queries of the window
     __host__ __device__ size_t smem_bytes(int nq) const {
-        return al(n_cap) + 4 * al(2 * (size_t)n_cap) + al((size_t)qbuf) + al(4 * (size_t)rows_cap) + al((size_t)rows_cap) + al(4 * (size_t)hq_cap) +
+        return al(n_cap) + 3 * al(2 * (size_t)n_cap) + al(4 * (size_t)n_cap) + al(8 * (size_t)n_cap) + al((size_t)qbuf) + al(8 * (size_t)rows_cap) +
+               al((size_t)rows_cap) + al(4 * (size_t)hq_cap) +
                al((size_t)stg_cap * sizeof(Ev)) + al((size_t)ev_cap * sizeof(Ev)) + al(2 * (size_t)(nq + 2)) + 2 * al(2 * (size_t)cand_cap) +
                al(2 * 3 * (size_t)(GROUP_MAX + 1)) + al(4 * 2 * (size_t)GROUP_MAX) + 64;
     }
@@ -86,16 +89,20 @@ __device__ __forceinline__ int smatch_bwd(const uint8_t* a, const uint8_t* b, in
     return c;
 }
 
-constexpr int SEED_K = 4;
-__device__ __forceinline__ uint32_t pack4(const uint8_t* p) {
-    return (uint32_t)p[0] | ((uint32_t)p[1] << 3) | ((uint32_t)p[2] << 6) | ((uint32_t)p[3] << 9);
+constexpr int SEED_K_MIN = 4, SEED_K_MAX = 10;
+constexpr uint32_t SEED_PAD = 0xffffffffu;      // never a seed code (codes use 30 bits), never a table entry
+__device__ __forceinline__ uint32_t pack_seed(const uint8_t* p, int K) {
+    uint32_t c = 0;
+    for (int t = 0; t < K; ++t) c |= (uint32_t)p[t] << (3 * t);
+    return c;
 }
+__device__ __forceinline__ uint32_t seed_hash(uint32_t code, int hbits) { return (code * 0x9E3779B1u) >> (32 - hbits); }
 
 // A1 on demand: for every staged event, lrp[l] = longest prefix of R[l..) occurring at another position of R (one warp per
 // event, lanes stride over the other positions; cached per reference position), then u = l + lrp and validity L > lrp.
-// Repeats shorter than the 4-base seed are reported as 0: every event has L >= minsize >= 4, and a floor u <= l + 3 can
+// Repeats shorter than the K-base seed are reported as 0: every event has L >= minsize >= K, and a floor u <= l + K - 1 can
 // neither invalidate the event nor reach an emitted candidate's end (emission needs EP - k >= minsize with k >= l).
-__device__ inline void resolve_unique(const uint8_t* __restrict__ R, const uint16_t* __restrict__ R4, int n, uint16_t* __restrict__ lrp,
+__device__ inline void resolve_unique(const uint8_t* __restrict__ R, const uint32_t* __restrict__ R4, int n, int SEED_K, uint16_t* __restrict__ lrp,
                                       Ev* __restrict__ ev, int count, int nthreads) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = nthreads >> 5;
     for (int i = warp; i < count; i += nwarps) {
@@ -158,11 +165,12 @@ __global__ void __launch_bounds__(SM_MAX_THREADS, 4) small_region_kernel(
     size_t off = 0;
     uint8_t* R = smem + off; off += ClassCfg::al(cfg.n_cap);
     uint16_t* lrp = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
-    uint16_t* R4 = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
     uint16_t* MUP = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
     uint16_t* MEP = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
+    uint32_t* R4 = reinterpret_cast<uint32_t*>(smem + off); off += ClassCfg::al(4 * (size_t)cfg.n_cap);          // seed code of every window position
+    uint32_t* tab = reinterpret_cast<uint32_t*>(smem + off); off += ClassCfg::al(8 * (size_t)cfg.n_cap);         // hash table of positions (2 n_cap slots)
     uint8_t* QB = smem + off; off += ClassCfg::al((size_t)cfg.qbuf);                                              // group query text
-    uint32_t* Q4 = reinterpret_cast<uint32_t*>(smem + off); off += ClassCfg::al(4 * (size_t)cfg.rows_cap);       // seed rows: fwd | rc << 16
+    uint32_t* Q4 = reinterpret_cast<uint32_t*>(smem + off); off += ClassCfg::al(8 * (size_t)cfg.rows_cap);       // seed rows: [2 row] = fwd, [2 row + 1] = rc
     uint8_t* rowq = smem + off; off += ClassCfg::al((size_t)cfg.rows_cap);                                        // group-local query of each row
     uint32_t* HQ = reinterpret_cast<uint32_t*>(smem + off); off += ClassCfg::al(4 * (size_t)cfg.hq_cap);         // seed hits: l | row << 12 | strand << 31
     Ev* stg = reinterpret_cast<Ev*>(smem + off); off += ClassCfg::al((size_t)cfg.stg_cap * sizeof(Ev));
@@ -183,29 +191,41 @@ __global__ void __launch_bounds__(SM_MAX_THREADS, 4) small_region_kernel(
     const int32_t* qs = qcoords + tk.qcoord_off;
     const int32_t* ql = qs + nq;
 
+    // seed length: consecutive seeds of a diagonal abut (step <= K) whenever minsize <= 19
+    const int SEED_K = min(SEED_K_MAX, max(SEED_K_MIN, (minsize + 2) >> 1));
+    const int step = max(1, minsize - SEED_K + 1);
+    const bool abut = step <= SEED_K;
+    int hbits = 1;
+    while ((1 << hbits) < 2 * cfg.n_cap) ++hbits;
+    const uint32_t hmask = (1u << hbits) - 1u;
     for (int i = tid; i < n; i += T) { R[i] = text[tk.ref_off + i]; MUP[i] = 0; MEP[i] = (uint16_t)n; lrp[i] = LRP_UNKNOWN; }
+    for (int i = tid; i < (1 << hbits); i += T) tab[i] = SEED_PAD;
     if (tid < 8) s_int[tid] = 0;
     __syncthreads();
     const int nseed = n >= SEED_K ? n - SEED_K + 1 : 0;            // reference positions holding a seed
-    for (int i = tid; i < nseed; i += T) R4[i] = (uint16_t)pack4(R + i);
+    for (int i = tid; i < nseed; i += T) {
+        const uint32_t code = pack_seed(R + i, SEED_K);
+        R4[i] = code;
+        uint32_t h = seed_hash(code, hbits);
+        while (atomicCAS(&tab[h], SEED_PAD, (uint32_t)i) != SEED_PAD) h = (h + 1) & hmask;
+    }
 
-    const int step = max(1, minsize - SEED_K + 1);
     int e0 = 0;                                                     // events stored so far (all earlier groups)
     int q0 = 0;
     while (q0 < nq) {
-        // ---- group [q0, q0 + G): as many queries as fit the text / row buffers (and a bounded expected number of seed hits)
+        // ---- group [q0, q0 + G): as many queries as fit the text / row buffers
         if (tid == 0) {
             int bytes = 0, rows = 0, g = 0;
             while (q0 + g < nq && g < GROUP_MAX) {
                 const int m = ql[q0 + g];
                 const int nb = 2 * (int)ClassCfg::al((size_t)m);
-                const int nr = m >= SEED_K ? (m - SEED_K) / step + 1 : 0;
-                if (g > 0 && (bytes + nb > cfg.qbuf || rows + nr > cfg.rows_cap || (long long)(rows + nr) * nseed > 48ll * cfg.hq_cap)) break;
-                qoff[g] = (uint16_t)bytes; rowoff[g] = (uint16_t)rows; qm[g] = (uint16_t)m;
+                const int nr = 1 + (m >= SEED_K ? (m - SEED_K) / step + 1 : 0);           // one pad row in front of every query
+                if (g > 0 && (bytes + nb > cfg.qbuf || rows + nr > cfg.rows_cap)) break;
+                qoff[g] = (uint16_t)bytes; rowoff[g] = (uint16_t)(rows + 1); qm[g] = (uint16_t)m;
                 qcnt[g] = 0;
                 bytes += nb; rows += nr; ++g;
             }
-            qoff[g] = (uint16_t)bytes; rowoff[g] = (uint16_t)rows;
+            qoff[g] = (uint16_t)bytes; rowoff[g] = (uint16_t)(rows + 1);
             s_int[6] = g; s_int[0] = 0; s_int[1] = 0;
             if (bytes > cfg.qbuf || rows > cfg.rows_cap) s_int[3] = 1;      // (cannot happen for a correctly classified task)
         }
@@ -223,43 +243,36 @@ __global__ void __launch_bounds__(SM_MAX_THREADS, 4) small_region_kernel(
             for (int i = tid; i < m; i += T) { Qf[i] = text[f_off + i]; Qc[i] = text[c_off + i]; }
         }
         __syncthreads();
-        // ---- 2. seed rows
-        const int total_rows = rowoff[G];
+        // ---- 2. seed rows (row r0-1 of every query is a pad row: "no predecessor on the diagonal")
+        const int total_rows = rowoff[G] - 1;
         for (int g = 0; g < G; ++g) {
             const int m = qm[g];
-            const int r0 = rowoff[g], nr = rowoff[g + 1] - r0;
+            const int r0 = rowoff[g], nr = rowoff[g + 1] - 1 - r0;
             const uint8_t* Qf = QB + qoff[g];
             const uint8_t* Qc = Qf + ClassCfg::al((size_t)m);
             for (int row = tid; row < nr; row += T) {
-                Q4[r0 + row] = pack4(Qf + row * step) | (pack4(Qc + row * step) << 16);
+                Q4[2 * (r0 + row)] = pack_seed(Qf + row * step, SEED_K);
+                Q4[2 * (r0 + row) + 1] = pack_seed(Qc + row * step, SEED_K);
                 rowq[r0 + row] = (uint8_t)g;
             }
+            if (tid == 0) { Q4[2 * (r0 - 1)] = SEED_PAD; Q4[2 * (r0 - 1) + 1] = SEED_PAD; }
         }
-        if (tid < 4 && total_rows + tid < ((total_rows + 3) & ~3)) Q4[total_rows + tid] = 0xffffffffu;     // pad to a multiple of 4 rows: matches nothing
         __syncthreads();
-        // ---- 3. dense seed grid -> hit queue
-        {
-            const int nchunks = (total_rows + 3) >> 2;
-            const uint4* Q4v = reinterpret_cast<const uint4*>(Q4);
-            int l = tid, ch = 0;
-            while (nseed > 0 && l >= nseed) { l -= nseed; ++ch; }
-            while (nseed > 0 && ch < nchunks) {
-                const uint32_t r4 = R4[l];
-                const uint32_t rr = r4 | (r4 << 16);
-                const uint4 w = Q4v[ch];
-                const uint32_t x0 = w.x ^ rr, x1 = w.y ^ rr, x2 = w.z ^ rr, x3 = w.w ^ rr;
-                // a zero halfword in any of the four words = a seed hit on that row and strand
-                const uint32_t z = ((x0 - 0x00010001u) & ~x0) | ((x1 - 0x00010001u) & ~x1) | ((x2 - 0x00010001u) & ~x2) | ((x3 - 0x00010001u) & ~x3);
-                if (z & 0x80008000u) {
-                    const uint32_t xs[4] = {x0, x1, x2, x3};
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        if (!(xs[t] & 0xffffu)) { int slot = atomicAdd(&s_int[0], 1); if (slot < cfg.hq_cap) HQ[slot] = (uint32_t)l | ((uint32_t)(ch * 4 + t) << 12); }
-                        if (!(xs[t] >> 16)) { int slot = atomicAdd(&s_int[0], 1); if (slot < cfg.hq_cap) HQ[slot] = (uint32_t)l | ((uint32_t)(ch * 4 + t) << 12) | 0x80000000u; }
-                    }
-                }
-                l += T;
-                while (l >= nseed) { l -= nseed; ++ch; }
+        // ---- 3. every (row, strand) looks its seed up in the window's table -> hit queue
+        for (int it = tid; it < 2 * total_rows; it += T) {
+            const uint32_t code = Q4[it];
+            if (code == SEED_PAD) continue;
+            const uint32_t prev = Q4[it - 2];                   // the seed one row up the diagonal (pad row: never matches)
+            uint32_t h = seed_hash(code, hbits);
+            for (;;) {
+                const uint32_t l = tab[h];
+                if (l == SEED_PAD) break;
+                h = (h + 1) & hmask;
+                if (R4[l] != code) continue;
+                // abutting seeds: the left extension reaches the seed spacing iff the predecessor seed is a hit too
+                if (abut && (int)l >= step && R4[l - step] == prev) continue;
+                const int slot = atomicAdd(&s_int[0], 1);
+                if (slot < cfg.hq_cap) HQ[slot] = l | ((uint32_t)(it >> 1) << 12) | ((uint32_t)(it & 1) << 31);
             }
         }
         __syncthreads();
@@ -297,7 +310,7 @@ __global__ void __launch_bounds__(SM_MAX_THREADS, 4) small_region_kernel(
             for (int g = 0; g < G; ++g) { evoff[q0 + g] = (uint16_t)run; qfill[g] = run; run += qcnt[g]; }
             evoff[q0 + G] = (uint16_t)run;
         }
-        resolve_unique(R, R4, n, lrp, stg, ns, T);
+        resolve_unique(R, R4, n, SEED_K, lrp, stg, ns, T);
         __syncthreads();
         // ---- 6. counting sort by query into the event store
         for (int i = tid; i < ns; i += T) {

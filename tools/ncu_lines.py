@@ -28,6 +28,6 @@ for b in blocks:
     if seen != which: seen += 1; continue
     seen += 1
     print("### %s  samples=%d inst=%.3g" % (b["file"].split("/")[-1], tot_s, tot_i))
-    for r in sorted(b["lines"], key=lambda r: -f(r[cs]))[:top]:
+    for r in sorted(b["lines"], key=lambda r: -(f(r[ci]) if len(sys.argv) > 4 else f(r[cs])))[:top]:
         print("  %5.1f%% smp  %5.1f%% inst  thr=%-5s L%-4s %s" % (100 * f(r[cs]) / tot_s, 100 * f(r[ci]) / tot_i, r[ct] if ct else "", r[0], r[1].strip()[:130]))
     break
