@@ -270,78 +270,140 @@ __device__ __forceinline__ int cmp_kmer(const uint8_t* __restrict__ R, int n, in
     return 0;
 }
 
-__global__ void __launch_bounds__(128) seed_extend_kernel(const uint8_t* __restrict__ R, int n, const uint32_t* __restrict__ sa,
+// four 2-bit base codes (one per byte, first base in byte 0) -> 8 bits, first base most significant
+__device__ __forceinline__ uint32_t pack4x2(uint32_t w) { return ((w & 0x03030303u) * 0x40100401u) >> 24; }
+// 4 bases packed like side_sig from bytes 4..7 of a little-endian 8-byte word (byte 4 = first base)
+__device__ __forceinline__ uint32_t sig_hi4(uint64_t w) {
+    return (uint32_t)((w >> 32) & 7u) << 9 | (uint32_t)((w >> 40) & 7u) << 6 | (uint32_t)((w >> 48) & 7u) << 3 | (uint32_t)((w >> 56) & 7u);
+}
+
+// One thread per sampled query position (every step-th base): k-mer -> seed table -> flank-signature filter -> left extension
+// (de-duplication: a match of >= minsize bases contains exactly one sampled seed whose left extension is shorter than the
+// sample spacing).  The right extensions of a warp's surviving seeds are then done by the WHOLE warp, one seed after the other,
+// 32 x 8 bytes per step with a ballot for the first mismatch: the extension of a 100-base match is one step for everybody
+// instead of four divergent 32-byte steps for one lane.  Events are appended with one atomic per warp and round.
+__global__ void __launch_bounds__(128, 12) seed_extend_kernel(const uint8_t* __restrict__ R, int n, const uint32_t* __restrict__ sa,
                                                           const int32_t* __restrict__ lrp, const uint2* __restrict__ table,
                                                           int k, int step, int minsize,
                                                           const StrandDesc* __restrict__ strands, uint64_t* __restrict__ ev_key,
                                                           uint64_t* __restrict__ ev_val, unsigned long long* __restrict__ ev_count,
                                                           unsigned long long ev_cap) {
+    const unsigned FULL = 0xffffffffu;
     const int strand = blockIdx.y;
     const uint8_t* __restrict__ Q = strands[strand].q;
     const int m = strands[strand].m;
+    const int lane = threadIdx.x & 31;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((idx - lane) * step + k > m) return;            // the whole warp lies past the end of the strand
     const long long jl = idx * step;
-    if (jl + k > m) return;
-    const int j = (int)jl;
-    // k <= 12 bases = the low 2 bits of 12 consecutive bytes: two 8-byte loads instead of k byte loads
-    uint32_t code = 0;
-    bool plain = true;
-    {
-        uint64_t w0 = load8u(Q + j), w1 = load8u(Q + j + 8);
-#pragma unroll
-        for (int t = 0; t < MAX_SEED_K; ++t) {
-            if (t < k) {
-                uint32_t c = (uint32_t)((t < 8 ? (w0 >> (8 * t)) : (w1 >> (8 * (t - 8)))) & 0xffu);
-                if (c > 3u) plain = false;
-                code = (code << 2) | (c & 3u);
-            }
+    const bool valid = jl + k <= m;
+    const int j = valid ? (int)jl : 0;
+    // ---- the lane's seed: bucket [lo, hi) of the suffix array, or one text position (`single`)
+    int lo = 0, hi = 0;
+    int single = -1;
+    if (valid) {
+        // k <= 12 bases = the low 2 bits of 12 consecutive bytes: two 8-byte loads; four bases are gathered by one multiply
+        const uint64_t w0 = load8u(Q + j), w1 = load8u(Q + j + 8);
+        const uint64_t m0 = k >= 8 ? ~0ull : ((1ull << (8 * k)) - 1ull);
+        const uint64_t m1 = k > 8 ? ((1ull << (8 * (k - 8))) - 1ull) : 0ull;
+        const bool plain = (((w0 & m0) | (w1 & m1)) & 0xfcfcfcfcfcfcfcfcull) == 0ull;      // no N (code 4) / padding among the k bases
+        const uint32_t code = ((pack4x2((uint32_t)w0) << 16) | (pack4x2((uint32_t)(w0 >> 32)) << 8) | pack4x2((uint32_t)w1)) >> (2 * (MAX_SEED_K - k));
+        if (plain) {
+            const uint2 e = table[code];
+            if (e.y & SIG_FLAG) {
+                single = (int)e.x; hi = 1;
+                if (minsize >= k + 7) {
+                    // one of the two 4-base flanks must agree (see index_finish_kernel); flanks outside the query never agree
+                    uint32_t ql, qr;
+                    if (k == MAX_SEED_K && j >= 8 && j + 16 <= m) { ql = sig_hi4(load8u(Q + j - 8)); qr = sig_hi4(w1); }
+                    else { ql = side_sig(Q, m, j - 4); qr = side_sig(Q, m, j + k); }
+                    const uint32_t rl = (e.y >> 12) & 0xfffu, rr = e.y & 0xfffu;
+                    if (ql != rl && qr != rr) hi = 0;
+                }
+            } else { lo = (int)e.x; hi = (int)e.y; }
+        } else {
+            // k-mer with N: binary search the suffix array (rare)
+            int a = 0, b = n;
+            while (a < b) { int mid = (a + b) >> 1; if (cmp_kmer(R, n, (int)sa[mid], Q + j, k) < 0) a = mid + 1; else b = mid; }
+            lo = a;
+            b = n;
+            while (a < b) { int mid = (a + b) >> 1; if (cmp_kmer(R, n, (int)sa[mid], Q + j, k) <= 0) a = mid + 1; else b = mid; }
+            hi = a;
         }
     }
-    int lo, hi;
-    int single = -1;                                  // text position when the bucket holds exactly one suffix
-    if (plain) {
-        const uint2 e = table[code];
-        if (e.y & SIG_FLAG) {
-            single = (int)e.x; lo = 0; hi = 1;
-            if (minsize >= k + 7) {
-                // one of the two 4-base flanks must agree (see kmer_table_fix_kernel); flanks outside the query never agree
-                const uint32_t ql = side_sig(Q, m, j - 4), qr = side_sig(Q, m, j + k);
-                const uint32_t rl = (e.y >> 12) & 0xfffu, rr = e.y & 0xfffu;
-                if (ql != rl && qr != rr) return;
+    // ---- rounds: every lane takes the next suffix of its bucket; a round ends with the warp's cooperative right extensions
+    int sidx = lo;
+    while (__any_sync(FULL, sidx < hi)) {
+        bool pend = false;
+        int c = 0, l = 0, lim = 0;
+        if (sidx < hi) {
+            l = single >= 0 ? single : (int)sa[sidx];
+            ++sidx;
+            if (l + k <= n) {                             // (2-bit keys: suffixes shorter than k sit in the bucket of their padded key)
+                const int room = min(j, l);               // bases to the left of the seed inside both strings
+                const int cmax = min(step, room);
+                // left extension, 8 bytes per compare (the byte just left of the seed is the top byte of the word); a compare may
+                // look further left than cmax as long as it stays inside the strings - the result is capped
+                while (c < cmax) {
+                    if (c + 8 <= room) {
+                        const uint64_t x = load8u(Q + j - c - 8) ^ load8u(R + l - c - 8);
+                        if (x) { c += __clzll((long long)x) >> 3; break; }
+                        c += 8;
+                    } else {
+                        while (c < cmax && Q[j - 1 - c] == R[l - 1 - c]) ++c;
+                        break;
+                    }
+                }
+                c = min(c, cmax);
+                if (c < step) {                           // else: an earlier sampled seed lies inside the same match
+                    pend = true;
+                    lim = min(m - (j + k), n - (l + k));
+                }
             }
-        } else { lo = (int)e.x; hi = (int)e.y; }
-    } else {
-        // k-mer with N: binary search the suffix array (rare)
-        int a = 0, b = n;
-        while (a < b) { int mid = (a + b) >> 1; if (cmp_kmer(R, n, (int)sa[mid], Q + j, k) < 0) a = mid + 1; else b = mid; }
-        lo = a;
-        b = n;
-        while (a < b) { int mid = (a + b) >> 1; if (cmp_kmer(R, n, (int)sa[mid], Q + j, k) <= 0) a = mid + 1; else b = mid; }
-        hi = a;
-    }
-    for (int sidx = lo; sidx < hi; ++sidx) {
-        const int l = single >= 0 ? single : (int)sa[sidx];
-        if (l + k > n) continue;                      // (2-bit keys: suffixes shorter than k sit in the bucket of their padded key)
-        int c = 0;
-        const int cmax = min(step, min(j, l));
-        // left extension, 8 bytes per compare (the byte just left of the seed is the top byte of the word)
-        while (c + 8 <= cmax) {
-            uint64_t x = load8u(Q + j - c - 8) ^ load8u(R + l - c - 8);
-            if (x) { c += __clzll((long long)x) >> 3; goto left_done; }
-            c += 8;
         }
-        while (c < cmax && Q[j - 1 - c] == R[l - 1 - c]) ++c;
-    left_done:
-        if (c >= step) continue;                      // an earlier sampled seed lies inside the same match
-        const int lim = min(m - (j + k), n - (l + k));
-        const int e = match_len(Q + j + k, R + l + k, lim);
-        const int L = c + k + e;
-        const int l0 = l - c;
-        if (L >= minsize && L > lrp[l0]) {
-            unsigned long long slot = atomicAdd(ev_count, 1ull);
-            if (slot < ev_cap) {
-                ev_key[slot] = ((uint64_t)(uint32_t)strand << 32) | (uint32_t)l0;
-                ev_val[slot] = ((uint64_t)(uint32_t)(l0 + L) << 32) | (uint32_t)(j - c);
+        // cooperative right extension of the pending seeds
+        int ext = 0;
+        unsigned pm = __ballot_sync(FULL, pend);
+        while (pm) {
+            const int src = __ffs(pm) - 1;
+            pm &= pm - 1;
+            const int qp = __shfl_sync(FULL, j + k, src), rp = __shfl_sync(FULL, l + k, src), lm = __shfl_sync(FULL, lim, src);
+            int e = lm;
+            for (int base = 0; base < lm; base += 256) {
+                const int off = base + lane * 8;
+                int my = 0;                                // equal leading bytes of this lane's 8 (0 = stop here: past the limit)
+                if (off < lm) {
+                    const uint64_t x = load8u(Q + qp + off) ^ load8u(R + rp + off);
+                    my = x ? ((__ffsll((long long)x) - 1) >> 3) : 8;
+                }
+                const unsigned stop = __ballot_sync(FULL, my < 8);
+                if (stop) {
+                    const int fl = __ffs(stop) - 1;
+                    e = min(lm, base + fl * 8 + __shfl_sync(FULL, my, fl));
+                    break;
+                }
+            }
+            if (lane == src) ext = e;
+        }
+        // events of this round: one atomic per warp
+        bool emit = false;
+        int L = 0, l0 = 0;
+        if (pend) {
+            L = c + k + ext;
+            l0 = l - c;
+            emit = L >= minsize && L > lrp[l0];
+        }
+        const unsigned em = __ballot_sync(FULL, emit);
+        if (em) {
+            unsigned long long basev = 0;
+            if (lane == __ffs(em) - 1) basev = atomicAdd(ev_count, (unsigned long long)__popc(em));
+            basev = __shfl_sync(FULL, basev, __ffs(em) - 1);
+            if (emit) {
+                const unsigned long long slot = basev + (unsigned long long)__popc(em & ((1u << lane) - 1u));
+                if (slot < ev_cap) {
+                    ev_key[slot] = ((uint64_t)(uint32_t)strand << 32) | (uint32_t)l0;
+                    ev_val[slot] = ((uint64_t)(uint32_t)(l0 + L) << 32) | (uint32_t)(j - c);
+                }
             }
         }
     }
@@ -357,6 +419,29 @@ __global__ void strand_segments_kernel(const uint64_t* __restrict__ ev_key, int 
     evl[i] = (uint32_t)kx;
     if (i == 0 || (uint32_t)(ev_key[i - 1] >> 32) != st) seg_lo[st] = (uint32_t)i;
     if (i == E - 1 || (uint32_t)(ev_key[i + 1] >> 32) != st) seg_hi[st] = (uint32_t)i + 1u;
+}
+
+// bounds[strand][t] = first event of the strand with l >= t * FOLD_TILE (t = 0..ntiles): the fold and the candidate pass look
+// events up inside one tile instead of searching the whole strand
+__global__ void tile_bounds_init_kernel(const uint32_t* __restrict__ seg_hi, int ns, int ntiles1, uint32_t* __restrict__ bounds) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)ns * ntiles1) return;
+    bounds[i] = seg_hi[i / ntiles1];                 // (strands without events: seg_lo = seg_hi = 0)
+}
+__global__ void tile_bounds_fill_kernel(const uint64_t* __restrict__ ev_key, int E, int tile_shift, int ntiles1, uint32_t* __restrict__ bounds) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E) return;
+    const uint64_t kx = ev_key[i];
+    const uint32_t st = (uint32_t)(kx >> 32);
+    const int t1 = (int)((uint32_t)kx >> tile_shift);          // tile of this event
+    int t0 = 0;                                               // first tile whose lower bound this event is
+    if (i > 0) {
+        const uint64_t kp = ev_key[i - 1];
+        if ((uint32_t)(kp >> 32) == st) {
+            t0 = (int)((uint32_t)kp >> tile_shift) + 1;
+        }
+    }
+    for (int t = t0; t <= t1; ++t) bounds[(size_t)st * ntiles1 + t] = (uint32_t)i;
 }
 
 // scan state: fl = max floor u[l], (t1, t2) = two largest ends, d1 = (query start - ref start) of the event holding t1
@@ -446,14 +531,22 @@ __device__ __forceinline__ void strand_at(const uint32_t* __restrict__ evl, cons
 constexpr int FOLD_THREADS = 256;
 constexpr int FOLD_ITEMS = 4;
 constexpr int FOLD_TILE = FOLD_THREADS * FOLD_ITEMS;
-// fold over queries q0..q1 (ini order) for a tile of reference positions; master_in may be null (= initial (0, n))
+constexpr int FOLD_TILE_SHIFT = 10;
+static_assert(FOLD_TILE == (1 << FOLD_TILE_SHIFT), "tile size");
+constexpr int FOLD_QB = 4;              // queries per round (their tile events are staged in shared memory together)
+constexpr int FOLD_EV = 96;             // staged events per strand and tile; denser tiles are searched in global memory
+// Fold over `nq` queries starting at strand `s0` (ini order) for a tile of reference positions.  The scan state of a strand
+// at position k is the state of its last event with l <= k: the events of the tile (bounds[]) plus the state carried in
+// from the left are staged in shared memory, the lookup is a short walk there.
 __global__ void __launch_bounds__(FOLD_THREADS) fold_kernel(const uint32_t* __restrict__ evl, const int4* __restrict__ states,
-                                                            const uint32_t* __restrict__ seg_lo, const uint32_t* __restrict__ seg_hi,
-                                                            int nq, int n, int32_t* __restrict__ MUP, int32_t* __restrict__ MEP,
-                                                            int init_master) {
-    __shared__ int s_a[2], s_b[2], s_lo[2];
-    const int tile0 = blockIdx.x * FOLD_TILE;
-    const int tile1 = min(n, tile0 + FOLD_TILE);
+                                                            const uint32_t* __restrict__ seg_lo, const uint32_t* __restrict__ bounds,
+                                                            int ntiles1, int s0, int nq, int n, int32_t* __restrict__ MUP,
+                                                            int32_t* __restrict__ MEP, int init_master) {
+    __shared__ uint32_t s_l[2 * FOLD_QB][FOLD_EV];
+    __shared__ int4 s_st[2 * FOLD_QB][FOLD_EV + 1];         // [0] = state carried in from the left of the tile
+    __shared__ int s_a[2 * FOLD_QB], s_b[2 * FOLD_QB], s_lo[2 * FOLD_QB];
+    const int tile = blockIdx.x;
+    const int tile0 = tile * FOLD_TILE;
     int up[FOLD_ITEMS], ep[FOLD_ITEMS];
 #pragma unroll
     for (int r = 0; r < FOLD_ITEMS; ++r) {
@@ -461,29 +554,46 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_kernel(const uint32_t* __re
         if (init_master || k >= n) { up[r] = 0; ep[r] = n; }
         else { up[r] = MUP[k]; ep[r] = MEP[k]; }
     }
-    for (int q = 0; q < nq; ++q) {
-        if (threadIdx.x < 2) {
-            int st = 2 * q + threadIdx.x;
-            int lo = (int)seg_lo[st], hi = (int)seg_hi[st];
-            int a = lo, b = hi;
-            while (a < b) { int mid = (a + b) >> 1; if (evl[mid] < (uint32_t)tile0) a = mid + 1; else b = mid; }
-            int first = a;
-            b = hi;
-            while (a < b) { int mid = (a + b) >> 1; if (evl[mid] < (uint32_t)tile1) a = mid + 1; else b = mid; }
-            s_a[threadIdx.x] = first; s_b[threadIdx.x] = a; s_lo[threadIdx.x] = lo;
+    for (int qb = 0; qb < nq; qb += FOLD_QB) {
+        const int ns = 2 * min(FOLD_QB, nq - qb);          // strands of this round
+        if (threadIdx.x < ns) {
+            const int st = s0 + 2 * qb + threadIdx.x;
+            s_a[threadIdx.x] = (int)bounds[(size_t)st * ntiles1 + tile];
+            s_b[threadIdx.x] = (int)bounds[(size_t)st * ntiles1 + tile + 1];
+            s_lo[threadIdx.x] = (int)seg_lo[st];
         }
         __syncthreads();
-        const int fa = s_a[0], fb = s_b[0], flo = s_lo[0], ca = s_a[1], cb = s_b[1], clo = s_lo[1];
+        for (int x = threadIdx.x; x < ns * (FOLD_EV + 1); x += FOLD_THREADS) {
+            const int s = x / (FOLD_EV + 1), i = x - s * (FOLD_EV + 1);
+            const int a = s_a[s], cnt = s_b[s] - a;
+            if (cnt > FOLD_EV) continue;
+            if (i == 0) s_st[s][0] = (a - 1 >= s_lo[s]) ? states[a - 1] : make_int4(0, 0, 0, 0);
+            else if (i <= cnt) { s_l[s][i - 1] = evl[a + i - 1]; s_st[s][i] = states[a + i - 1]; }
+        }
+        __syncthreads();
+        for (int q = 0; q < ns / 2; ++q) {
 #pragma unroll
-        for (int r = 0; r < FOLD_ITEMS; ++r) {
-            int k = tile0 + r * FOLD_THREADS + threadIdx.x;
-            if (k < n) {
-                int UPf, EPf, df, UPc, EPc, dc;
-                strand_at(evl, states, flo, fa, fb, (uint32_t)k, UPf, EPf, df);
-                strand_at(evl, states, clo, ca, cb, (uint32_t)k, UPc, EPc, dc);
-                int fe = min(ep[r], EPf), ce = min(ep[r], EPc);
-                if (fe > ce) { up[r] = max(up[r], UPf); ep[r] = fe; }
-                else { up[r] = max(up[r], UPc); ep[r] = ce; }
+            for (int r = 0; r < FOLD_ITEMS; ++r) {
+                const int k = tile0 + r * FOLD_THREADS + threadIdx.x;
+                if (k >= n) continue;
+                int UP2[2], EP2[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int s = 2 * q + h;
+                    const int a = s_a[s], cnt = s_b[s] - a;
+                    if (cnt <= FOLD_EV) {
+                        int p = 0;
+                        while (p < cnt && s_l[s][p] <= (uint32_t)k) ++p;
+                        const int4 v = s_st[s][p];
+                        UP2[h] = max(v.x, v.z); EP2[h] = max(v.y, v.x);
+                    } else {
+                        int d;
+                        strand_at(evl, states, s_lo[s], a, s_b[s], (uint32_t)k, UP2[h], EP2[h], d);
+                    }
+                }
+                const int fe = min(ep[r], EP2[0]), ce = min(ep[r], EP2[1]);
+                if (fe > ce) { up[r] = max(up[r], UP2[0]); ep[r] = fe; }
+                else { up[r] = max(up[r], UP2[1]); ep[r] = ce; }
             }
         }
         __syncthreads();
@@ -526,16 +636,18 @@ __global__ void mumi_cover_kernel(const uint32_t* __restrict__ runmax, int n, ui
 
 // per (candidate, local query): the two strands' (EP, diagonal) at the candidate position
 __global__ void pass2a_kernel(const uint32_t* __restrict__ ck, int ncand, const uint32_t* __restrict__ evl, const int4* __restrict__ states,
-                              const uint32_t* __restrict__ seg_lo, const uint32_t* __restrict__ seg_hi, int nq, int4* __restrict__ tmp) {
+                              const uint32_t* __restrict__ seg_lo, const uint32_t* __restrict__ bounds, int ntiles1, int nq,
+                              int4* __restrict__ tmp) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)ncand * nq) return;
     const int c = (int)(idx / nq), q = (int)(idx % nq);
     const uint32_t k = ck[c];
+    const int tile = (int)(k >> FOLD_TILE_SHIFT);
     int UPf, EPf, df, UPc, EPc, dc;
-    int lo = (int)seg_lo[2 * q], hi = (int)seg_hi[2 * q];
-    strand_at(evl, states, lo, lo, hi, k, UPf, EPf, df);
-    lo = (int)seg_lo[2 * q + 1]; hi = (int)seg_hi[2 * q + 1];
-    strand_at(evl, states, lo, lo, hi, k, UPc, EPc, dc);
+    const uint32_t* bf = bounds + (size_t)(2 * q) * ntiles1 + tile;
+    strand_at(evl, states, (int)seg_lo[2 * q], (int)bf[0], (int)bf[1], k, UPf, EPf, df);
+    const uint32_t* bc = bounds + (size_t)(2 * q + 1) * ntiles1 + tile;
+    strand_at(evl, states, (int)seg_lo[2 * q + 1], (int)bc[0], (int)bc[1], k, UPc, EPc, dc);
     tmp[idx] = make_int4(EPf, EPc, df, dc);
 }
 // per candidate: replay the fold over the local queries (ini order) to recover every query's strand and start (SP)
@@ -788,6 +900,11 @@ public:
         uint32_t* evl = evl_.ensure(std::max<size_t>((size_t)E, 1), false, st);
         int4* states = states_.ensure(std::max<size_t>((size_t)E, 1), false, st);
         if (E > 0) pb200::launch(strand_segments_kernel, (unsigned)((E + TB - 1) / TB), TB, 0, st, eks, (int)E, seg_lo, seg_hi, evl);
+        ntiles1_ = (n + FOLD_TILE - 1) / FOLD_TILE + 1;
+        const size_t nb_ent = (size_t)std::max(ns, 1) * ntiles1_;
+        uint32_t* bounds = bounds_.ensure(nb_ent, false, st);
+        if (ns > 0) pb200::launch(tile_bounds_init_kernel, (unsigned)((nb_ent + TB - 1) / TB), TB, 0, st, seg_hi, ns, ntiles1_, bounds);
+        if (E > 0) pb200::launch(tile_bounds_fill_kernel, (unsigned)((E + TB - 1) / TB), TB, 0, st, eks, (int)E, FOLD_TILE_SHIFT, ntiles1_, bounds);
         if (tm) tm->stop(GpuTimers::T_SCAN_EVSORT, st);
 
         if (tm) tm->start(GpuTimers::T_SCAN_EVSCAN, st);
@@ -803,7 +920,7 @@ public:
         int32_t* MUP = mup_.ensure((size_t)n, true, st);
         int32_t* MEP = mep_.ensure((size_t)n, true, st);
         pb200::launch(fold_kernel, (unsigned)((n + FOLD_TILE - 1) / FOLD_TILE), FOLD_THREADS, 0, st, evl_.get(), states_.get(), seglo_.get(),
-                      seghi_.get(), cur_nq_, n, MUP, MEP, init ? 1 : 0);
+                      bounds_.get(), ntiles1_, 0, cur_nq_, n, MUP, MEP, init ? 1 : 0);
         if (tm) tm->stop(GpuTimers::T_SCAN_FOLD, st);
     }
     int32_t* master_up(cudaStream_t st) { return mup_.ensure((size_t)cur_n_, true, st); }
@@ -849,7 +966,7 @@ public:
                 int4* tmp = p2tmp_.ensure((size_t)ncand * nq, false, st);
                 const long long tot = (long long)ncand * nq;
                 pb200::launch(pass2a_kernel, (unsigned)((tot + 127) / 128), 128, 0, st, ck_.get(), (int)ncand, evl_.get(), states_.get(),
-                              seglo_.get(), seghi_.get(), nq, tmp);
+                              seglo_.get(), bounds_.get(), ntiles1_, nq, tmp);
                 pb200::launch(pass2b_kernel, (ncand + 127) / 128, 128, 0, st, ck_.get(), (int)ncand, tmp, nq, n, mep_.get(), initEP, d_lon, d_sp,
                               d_fwd);
             } else {
@@ -881,8 +998,8 @@ public:
         const unsigned nb = (unsigned)((n + TB - 1) / TB);
         int32_t* MUP = mup_.ensure((size_t)n, false, st);
         int32_t* MEP = mep_.ensure((size_t)n, false, st);
-        pb200::launch(fold_kernel, (unsigned)((n + FOLD_TILE - 1) / FOLD_TILE), FOLD_THREADS, 0, st, evl_.get(), states_.get(), seglo_.get() + 2 * q,
-                      seghi_.get() + 2 * q, 1, n, MUP, MEP, 1);
+        pb200::launch(fold_kernel, (unsigned)((n + FOLD_TILE - 1) / FOLD_TILE), FOLD_THREADS, 0, st, evl_.get(), states_.get(), seglo_.get(),
+                      bounds_.get(), ntiles1_, 2 * q, 1, n, MUP, MEP, 1);
         uint32_t* a = tmpA_.ensure((size_t)n + 1, false, st);
         uint32_t* b = tmpB_.ensure((size_t)n + 1, false, st);
         uint32_t* c = tmpC_.ensure((size_t)n + 1, false, st);
@@ -916,7 +1033,8 @@ private:
     rsort::RadixSorter sorter_;
     prim::Scanner scanner_;
     DevBuf<uint64_t> keys0_, keys1_, dkeys0_, dkeys1_, evk0_, evk1_, evv0_, evv1_;
-    DevBuf<uint32_t> vals0_, vals1_, dvals0_, dvals1_, rank_, tmpA_, tmpB_, tmpC_, cs0_, cs1_, total_, seglo_, seghi_, evl_, ck_, tieflag_;
+    DevBuf<uint32_t> vals0_, vals1_, dvals0_, dvals1_, rank_, tmpA_, tmpB_, tmpC_, cs0_, cs1_, total_, seglo_, seghi_, evl_, ck_, tieflag_, bounds_;
+    int ntiles1_ = 1;
     DevBuf<int32_t> lrp_, mup_, mep_, olon_, osp_;
     PinBuf<uint32_t> tie_host_;
     uint32_t* sa_ptr_ = nullptr;             // suffix array of the current window (lives in one of the sort's value buffers)
