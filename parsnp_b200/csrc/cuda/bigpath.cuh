@@ -973,13 +973,32 @@ public:
                 pb200::launch(pass2b_kernel, (ncand + 127) / 128, 128, 0, st, ck_.get(), (int)ncand, (const int4*)nullptr, 0, n, mep_.get(),
                               initEP, d_lon, d_sp, d_fwd);
             }
-            PB_CUDA(cudaMemcpyAsync(out_k.data() + base, ck_.get(), (size_t)ncand * 4, cudaMemcpyDeviceToHost, st));
-            PB_CUDA(cudaMemcpyAsync(out_lon.data() + base, d_lon, (size_t)ncand * 4, cudaMemcpyDeviceToHost, st));
+            // device -> pinned staging at link speed, then a parallel copy into the (pageable) result vectors
+            const size_t cq = (size_t)ncand * std::max(nq, 1);
+            int32_t* hk = pin_k_.ensure(ncand);
+            int32_t* hl = pin_lon_.ensure(ncand);
+            int32_t* hs = pin_sp_.ensure(cq);
+            uint8_t* hf = pin_fwd_.ensure(cq);
+            PB_CUDA(cudaMemcpyAsync(hk, ck_.get(), (size_t)ncand * 4, cudaMemcpyDeviceToHost, st));
+            PB_CUDA(cudaMemcpyAsync(hl, d_lon, (size_t)ncand * 4, cudaMemcpyDeviceToHost, st));
             if (nq) {
-                PB_CUDA(cudaMemcpyAsync(out_sp.data() + bsp, d_sp, (size_t)ncand * nq * 4, cudaMemcpyDeviceToHost, st));
-                PB_CUDA(cudaMemcpyAsync(out_fwd.data() + bsp, d_fwd, (size_t)ncand * nq, cudaMemcpyDeviceToHost, st));
+                PB_CUDA(cudaMemcpyAsync(hs, d_sp, (size_t)ncand * nq * 4, cudaMemcpyDeviceToHost, st));
+                PB_CUDA(cudaMemcpyAsync(hf, d_fwd, (size_t)ncand * nq, cudaMemcpyDeviceToHost, st));
             }
             PB_CUDA(cudaStreamSynchronize(st));
+            std::memcpy(out_k.data() + base, hk, (size_t)ncand * 4);
+            std::memcpy(out_lon.data() + base, hl, (size_t)ncand * 4);
+            if (nq) {
+                const size_t bytes_sp = (size_t)ncand * nq * 4, bytes_fw = (size_t)ncand * nq;
+                const size_t CH = (size_t)1 << 20;
+                const long nch_sp = (long)((bytes_sp + CH - 1) / CH), nch_fw = (long)((bytes_fw + CH - 1) / CH);
+                uint8_t* dsp = reinterpret_cast<uint8_t*>(out_sp.data() + bsp);
+                uint8_t* dfw = out_fwd.data() + bsp;
+                parallel_chunks(bytes_sp > 4 * CH ? default_host_threads() : 1, nch_sp + nch_fw, [&](long c) {
+                    if (c < nch_sp) { const size_t o = (size_t)c * CH; std::memcpy(dsp + o, reinterpret_cast<const uint8_t*>(hs) + o, std::min(CH, bytes_sp - o)); }
+                    else { const size_t o = (size_t)(c - nch_sp) * CH; std::memcpy(dfw + o, hf + o, std::min(CH, bytes_fw - o)); }
+                });
+            }
         }
         if (tm) tm->stop(GpuTimers::T_SCAN_PASS2, st);
         PB_CUDA(cudaGetLastError());
@@ -1037,6 +1056,8 @@ private:
     int ntiles1_ = 1;
     DevBuf<int32_t> lrp_, mup_, mep_, olon_, osp_;
     PinBuf<uint32_t> tie_host_;
+    PinBuf<int32_t> pin_k_, pin_lon_, pin_sp_;
+    PinBuf<uint8_t> pin_fwd_;
     uint32_t* sa_ptr_ = nullptr;             // suffix array of the current window (lives in one of the sort's value buffers)
     const uint8_t* idx_R_ = nullptr;
     int idx_n_ = 0, idx_minsize_ = 0;

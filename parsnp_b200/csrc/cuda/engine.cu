@@ -13,6 +13,7 @@
 #include "../host/aligner.h"
 #include "../host/result.h"
 #include "../host/sharded.h"
+#include "../host/parallel.h"
 #include "util.cuh"
 #include "bigpath.cuh"
 #include "smallpath.cuh"
@@ -153,7 +154,7 @@ public:
         std::vector<int64_t> t_base(ntasks, 0);
         std::vector<int32_t> t_cnt(ntasks, 0);
         std::vector<int8_t> t_src(ntasks, 0);              // 0 = small arrays, 1 = big arrays
-        sm_k_.clear(); sm_lon_.clear(); sm_sp_.clear(); sm_fwd_.clear();
+        small_cands_ = 0;
         bg_k_.clear(); bg_lon_.clear(); bg_sp_.clear(); bg_fwd_.clear();
         const bool any_small = !by_class[0].empty() || !by_class[1].empty() || !by_class[2].empty();
         const double th1 = wall_s();
@@ -174,18 +175,35 @@ public:
             t_cnt[t] = (int32_t)((int64_t)bg_k_.size() - t_base[t]);
         }
         host_big_s += wall_s() - th2;
-        // hand the blocks over where the kernels left them: small-window candidates first, then the large windows
-        const int64_t nsm = (int64_t)sm_k_.size();
-        out.k.swap(sm_k_); out.lon.swap(sm_lon_); out.sp.swap(sm_sp_); out.fwd.swap(sm_fwd_);
-        if (!bg_k_.empty()) {
-            out.k.insert(out.k.end(), bg_k_.begin(), bg_k_.end());
-            out.lon.insert(out.lon.end(), bg_lon_.begin(), bg_lon_.end());
-            out.sp.insert(out.sp.end(), bg_sp_.begin(), bg_sp_.end());
-            out.fwd.insert(out.fwd.end(), bg_fwd_.begin(), bg_fwd_.end());
+        // gather the windows' candidate blocks (pinned staging: kernel completion order; large windows: bg_ arrays) into window
+        // order, so that the accept passes (ascending reference order) stream through memory
+        const double th3 = wall_s();
+        out.off.assign((size_t)ntasks + 1, 0);
+        for (int t = 0; t < ntasks; ++t) out.off[t + 1] = out.off[t] + t_cnt[t];
+        const int64_t tot = out.off[ntasks];
+        out.k.resize((size_t)tot); out.lon.resize((size_t)tot); out.sp.resize((size_t)tot * nq); out.fwd.resize((size_t)tot * nq);
+        out.cnt.clear();
+        {
+            const int32_t* pk = pin_k_.get(); const int32_t* pl = pin_lon_.get(); const int32_t* ps = pin_sp_.get(); const uint8_t* pf = pin_fwd_.get();
+            const long per = 1024;
+            parallel_chunks(tot > 65536 ? default_host_threads() : 1, ((long)ntasks + per - 1) / per, [&](long c) {
+                for (long t = c * per; t < std::min<long>(ntasks, (c + 1) * per); ++t) {
+                    const size_t cn = (size_t)t_cnt[t], a = (size_t)t_base[t], b = (size_t)out.off[t];
+                    if (!cn) continue;
+                    const int32_t* sk = t_src[t] ? bg_k_.data() : pk;
+                    const int32_t* sl = t_src[t] ? bg_lon_.data() : pl;
+                    const int32_t* ss = t_src[t] ? bg_sp_.data() : ps;
+                    const uint8_t* sf = t_src[t] ? bg_fwd_.data() : pf;
+                    std::memcpy(out.k.data() + b, sk + a, cn * 4);
+                    std::memcpy(out.lon.data() + b, sl + a, cn * 4);
+                    if (nq) {
+                        std::memcpy(out.sp.data() + b * nq, ss + a * nq, cn * nq * 4);
+                        std::memcpy(out.fwd.data() + b * nq, sf + a * nq, cn * nq);
+                    }
+                }
+            });
         }
-        out.off.resize(ntasks);
-        out.cnt.assign(t_cnt.begin(), t_cnt.end());
-        for (int t = 0; t < ntasks; ++t) out.off[t] = t_base[t] + (t_src[t] ? nsm : 0);
+        host_gather_s += wall_s() - th3;
     }
 
     // ---- StagedWindowEngine (query-sharded large windows, see host/sharded.h) ----
@@ -297,12 +315,12 @@ public:
     GpuTimers timers;
     int64_t big_windows = 0, small_windows = 0, small_retries = 0, big_events = 0, index_rounds = 0;
     int64_t small_class_tasks[3] = {0, 0, 0};
-    double host_classify_s = 0, host_upload_s = 0, host_small_wait_s = 0, host_small_d2h_s = 0, host_big_s = 0;   // wall clock, host side
+    double host_classify_s = 0, host_upload_s = 0, host_small_wait_s = 0, host_small_d2h_s = 0, host_big_s = 0, host_gather_s = 0;   // wall clock, host side
     int64_t small_ref_bases = 0, small_query_bases = 0, big_ref_bases = 0, big_query_bases = 0;
 
 private:
     void upload_small_tasks(const WindowTask* tasks, int ntasks, const int64_t* coords, int64_t ncoords) {
-        std::vector<small::TaskDev> td(ntasks);
+        small::TaskDev* td = pin_tasks_.ensure((size_t)ntasks);        // pinned staging: the copies below run at link speed
         h_task_n_.assign(ntasks, 0);
         h_task_m_.assign(ntasks, 0);
         const int nq_ = n_ - 1;
@@ -315,13 +333,13 @@ private:
             td[t].minsize = tasks[t].minsize;
             td[t].qcoord_off = tasks[t].coord_off;
         }
-        std::vector<int32_t> qc((size_t)ncoords);
+        int32_t* qc = pin_qc_.ensure((size_t)std::max<int64_t>(ncoords, 1));
         for (int64_t i = 0; i < ncoords; ++i) qc[i] = (int32_t)coords[i];
         small::TaskDev* d_t = d_tasks_.ensure((size_t)ntasks, false, st_);
         int32_t* d_q = d_qcoords_.ensure((size_t)std::max<int64_t>(ncoords, 1), false, st_);
         d_outs_.ensure((size_t)ntasks, false, st_);
-        PB_CUDA(cudaMemcpyAsync(d_t, td.data(), sizeof(small::TaskDev) * ntasks, cudaMemcpyHostToDevice, st_));
-        if (ncoords) PB_CUDA(cudaMemcpyAsync(d_q, qc.data(), (size_t)ncoords * 4, cudaMemcpyHostToDevice, st_));
+        PB_CUDA(cudaMemcpyAsync(d_t, td, sizeof(small::TaskDev) * ntasks, cudaMemcpyHostToDevice, st_));
+        if (ncoords) PB_CUDA(cudaMemcpyAsync(d_q, qc, (size_t)ncoords * 4, cudaMemcpyHostToDevice, st_));
         PB_CUDA(cudaStreamSynchronize(st_));
     }
 
@@ -359,35 +377,35 @@ private:
             small_class_tasks[c] += nt;
             unsigned long long used = 0;
             PB_CUDA(cudaMemcpyAsync(&used, d_cnt, 8, cudaMemcpyDeviceToHost, st_));
-            h_outs_.resize(nt);
             // outs are indexed by task id; fetch the ones of this launch
-            std::vector<small::TaskOut>& ho = h_outs_;
             int maxid = *std::max_element(ids.begin(), ids.end());
-            h_outs_all_.resize((size_t)maxid + 1);
-            PB_CUDA(cudaMemcpyAsync(h_outs_all_.data(), d_outs_.get(), sizeof(small::TaskOut) * ((size_t)maxid + 1), cudaMemcpyDeviceToHost, st_));
+            small::TaskOut* h_outs_all = pin_outs_.ensure((size_t)maxid + 1);
+            PB_CUDA(cudaMemcpyAsync(h_outs_all, d_outs_.get(), sizeof(small::TaskOut) * ((size_t)maxid + 1), cudaMemcpyDeviceToHost, st_));
             const double tw0 = wall_s();
             PB_CUDA(cudaStreamSynchronize(st_));
             const double tw1 = wall_s();
             host_small_wait_s += tw1 - tw0;
-            (void)ho;
             const size_t got = (size_t)std::min<unsigned long long>(used, cand_cap);
             cands_out += got;
-            const size_t hb = sm_k_.size();
-            sm_k_.resize(hb + got); sm_lon_.resize(hb + got);
-            sm_sp_.resize((hb + got) * nq); sm_fwd_.resize((hb + got) * nq);
+            const size_t hb = small_cands_;
+            small_cands_ = hb + got;
+            int32_t* pk = pin_k_.ensure(hb + got, hb);
+            int32_t* pl = pin_lon_.ensure(hb + got, hb);
+            int32_t* ps = pin_sp_.ensure((hb + got) * std::max(nq, 1), hb * nq);
+            uint8_t* pf = pin_fwd_.ensure((hb + got) * std::max(nq, 1), hb * nq);
             if (got) {
-                PB_CUDA(cudaMemcpyAsync(sm_k_.data() + hb, d_k, got * 4, cudaMemcpyDeviceToHost, st_));
-                PB_CUDA(cudaMemcpyAsync(sm_lon_.data() + hb, d_lon, got * 4, cudaMemcpyDeviceToHost, st_));
+                PB_CUDA(cudaMemcpyAsync(pk + hb, d_k, got * 4, cudaMemcpyDeviceToHost, st_));
+                PB_CUDA(cudaMemcpyAsync(pl + hb, d_lon, got * 4, cudaMemcpyDeviceToHost, st_));
                 if (nq) {
-                    PB_CUDA(cudaMemcpyAsync(sm_sp_.data() + hb * nq, d_sp, got * nq * 4, cudaMemcpyDeviceToHost, st_));
-                    PB_CUDA(cudaMemcpyAsync(sm_fwd_.data() + hb * nq, d_fw, got * nq, cudaMemcpyDeviceToHost, st_));
+                    PB_CUDA(cudaMemcpyAsync(ps + hb * nq, d_sp, got * nq * 4, cudaMemcpyDeviceToHost, st_));
+                    PB_CUDA(cudaMemcpyAsync(pf + hb * nq, d_fw, got * nq, cudaMemcpyDeviceToHost, st_));
                 }
                 PB_CUDA(cudaStreamSynchronize(st_));
             }
             host_small_d2h_s += wall_s() - tw1;
             std::vector<int> again;
             for (int t : ids) {
-                const small::TaskOut& o = h_outs_all_[t];
+                const small::TaskOut& o = h_outs_all[t];
                 if (o.ncand >= 0) { t_cnt[t] = o.ncand; t_base[t] = (int64_t)hb + o.cand_base; small_windows++; }
                 else if (o.ncand == -2) again.push_back(t);      // global candidate buffer full: same class, bigger buffer
                 else { retry.push_back(t); small_retries++; }     // per-CTA event/candidate capacity: next class
@@ -442,13 +460,16 @@ private:
     const uint8_t* w_R_ = nullptr;
     std::vector<big::StrandDesc> w_strands_;
     int w_q0_ = 0, w_q1_ = 0;
-    std::vector<small::TaskOut> h_outs_, h_outs_all_;
+    PinBuf<small::TaskOut> pin_outs_;
+    PinBuf<small::TaskDev> pin_tasks_;
+    PinBuf<int32_t> pin_qc_;
     std::vector<int64_t> h_task_n_, h_task_m_;
     small::ClassCfg classes_[3];
     size_t max_smem_ = 0, cand_cap_hint_ = 0;
     big::BigPath big_;
-    pod_vector<int32_t> sm_k_, sm_lon_, sm_sp_;
-    pod_vector<uint8_t> sm_fwd_;
+    PinBuf<int32_t> pin_k_, pin_lon_, pin_sp_;       // small-window candidates of the current search() call (pinned staging)
+    PinBuf<uint8_t> pin_fwd_;
+    size_t small_cands_ = 0;
     std::vector<int32_t> bg_k_, bg_lon_, bg_sp_;
     std::vector<uint8_t> bg_fwd_;
 };
@@ -618,16 +639,16 @@ int pb200_engine_timers(pb200_genomes* g, double* values, int cap) {
     const int T = pb200::GpuTimers::T_COUNT;
     for (int i = 0; i < T && k < cap; ++i) values[k++] = g->eng->timers.ms[i];
     for (int i = 0; i < T && k < cap; ++i) values[k++] = g->eng->timers.cnt[i];
-    const double extra[18] = {(double)g->eng->small_class_tasks[0], (double)g->eng->small_class_tasks[1], (double)g->eng->small_class_tasks[2],(double)g->eng->big_windows, (double)g->eng->small_windows, (double)g->eng->small_retries,
+    const double extra[19] = {(double)g->eng->small_class_tasks[0], (double)g->eng->small_class_tasks[1], (double)g->eng->small_class_tasks[2],(double)g->eng->big_windows, (double)g->eng->small_windows, (double)g->eng->small_retries,
                               (double)g->eng->big_events, (double)g->eng->index_rounds, (double)pb200::g_kernel_launches,
                               (double)g->eng->small_ref_bases, (double)g->eng->small_query_bases, (double)g->eng->big_ref_bases,
                               (double)g->eng->big_query_bases, g->eng->host_classify_s, g->eng->host_upload_s, g->eng->host_small_wait_s,
-                              g->eng->host_small_d2h_s, g->eng->host_big_s};
-    for (int i = 0; i < 18 && k < cap; ++i) values[k++] = extra[i];
+                              g->eng->host_small_d2h_s, g->eng->host_big_s, g->eng->host_gather_s};
+    for (int i = 0; i < 19 && k < cap; ++i) values[k++] = extra[i];
     return k;
 }
 const char* pb200_engine_timer_names(void) {
-    static std::string s = std::string(pb200::GpuTimers::names()) + ",tasks_class_a,tasks_class_b,tasks_class_c,big_windows,small_windows,small_retries,big_events,index_rounds,kernel_launches,small_ref_bases,small_query_bases,big_ref_bases,big_query_bases,host_classify_s,host_upload_s,host_small_wait_s,host_small_d2h_s,host_big_s";
+    static std::string s = std::string(pb200::GpuTimers::names()) + ",tasks_class_a,tasks_class_b,tasks_class_c,big_windows,small_windows,small_retries,big_events,index_rounds,kernel_launches,small_ref_bases,small_query_bases,big_ref_bases,big_query_bases,host_classify_s,host_upload_s,host_small_wait_s,host_small_d2h_s,host_big_s,host_gather_s";
     return s.c_str();
 }
 void pb200_engine_reset_timers(pb200_genomes* g) {
@@ -637,7 +658,7 @@ void pb200_engine_reset_timers(pb200_genomes* g) {
     pb200::g_kernel_launches = 0;
     g->eng->small_ref_bases = g->eng->small_query_bases = g->eng->big_ref_bases = g->eng->big_query_bases = 0;
     g->eng->small_class_tasks[0] = g->eng->small_class_tasks[1] = g->eng->small_class_tasks[2] = 0;
-    g->eng->host_classify_s = g->eng->host_upload_s = g->eng->host_small_wait_s = g->eng->host_small_d2h_s = g->eng->host_big_s = 0;
+    g->eng->host_classify_s = g->eng->host_upload_s = g->eng->host_small_wait_s = g->eng->host_small_d2h_s = g->eng->host_big_s = g->eng->host_gather_s = 0;
 }
 
 // test hook (not in the public header): suffix array + longest-repeated-prefix of a window of genome 0

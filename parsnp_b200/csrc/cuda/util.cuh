@@ -4,6 +4,10 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include <mutex>
+#include <utility>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -50,22 +54,61 @@ private:
     size_t cap_ = 0;
 };
 
-// pinned host buffer
+// Process-wide cache of pinned host blocks: cudaHostAlloc costs milliseconds, and an engine (with its staging buffers) is
+// created and destroyed by every pb200_align call.  Blocks are handed back on destruction and never returned to the OS.
+class PinnedPool {
+public:
+    static void* take(size_t bytes, size_t& cap_bytes) {
+        {
+            std::lock_guard<std::mutex> lk(mu());
+            auto& f = free_list();
+            size_t best = f.size();
+            for (size_t i = 0; i < f.size(); ++i)
+                if (f[i].second >= bytes && (best == f.size() || f[i].second < f[best].second)) best = i;
+            if (best != f.size()) {
+                void* p = f[best].first;
+                cap_bytes = f[best].second;
+                f.erase(f.begin() + (long)best);
+                return p;
+            }
+        }
+        void* p = nullptr;
+        cap_bytes = bytes + bytes / 4 + 4096;
+        PB_CUDA(cudaHostAlloc(&p, cap_bytes, cudaHostAllocPortable));
+        return p;
+    }
+    static void give(void* p, size_t cap_bytes) {
+        if (!p) return;
+        std::lock_guard<std::mutex> lk(mu());
+        free_list().emplace_back(p, cap_bytes);
+    }
+private:
+    static std::mutex& mu() { static std::mutex m; return m; }
+    static std::vector<std::pair<void*, size_t>>& free_list() { static std::vector<std::pair<void*, size_t>> f; return f; }
+};
+
+// pinned host buffer (from the process-wide pool); ensure(n, keep) preserves the first `keep` elements on growth
 template <class T>
 class PinBuf {
 public:
-    ~PinBuf() { if (p_) cudaFreeHost(p_); }
-    T* ensure(size_t n) {
-        if (n <= cap_) return p_;
-        if (p_) cudaFreeHost(p_);
-        cap_ = n + n / 4 + 64;
-        PB_CUDA(cudaMallocHost(&p_, cap_ * sizeof(T)));
+    PinBuf() {}
+    ~PinBuf() { PinnedPool::give(p_, cap_bytes_); }
+    PinBuf(const PinBuf&) = delete;
+    PinBuf& operator=(const PinBuf&) = delete;
+    T* ensure(size_t n, size_t keep = 0) {
+        if (n * sizeof(T) <= cap_bytes_ && p_) return p_;
+        size_t ncap = 0;
+        T* q = (T*)PinnedPool::take(std::max<size_t>(n, 16) * sizeof(T), ncap);
+        if (keep && p_) memcpy(q, p_, keep * sizeof(T));
+        PinnedPool::give(p_, cap_bytes_);
+        p_ = q;
+        cap_bytes_ = ncap;
         return p_;
     }
     T* get() const { return p_; }
 private:
     T* p_ = nullptr;
-    size_t cap_ = 0;
+    size_t cap_bytes_ = 0;
 };
 
 // Named GPU timers: CUDA event pairs recorded on the engine stream WITHOUT synchronising; collect() (called once
