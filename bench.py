@@ -197,9 +197,10 @@ def main():
         step_ms.append(e0.elapsed_time(e1))
     timers = G.engine_timers()
     clocks = sampler.stop()
-    # end-to-end: host buffers in, results out, through the user-facing call
+    # end-to-end: host buffers in, results out, through the user-facing call (one untimed call first: the first engine of
+    # a process that is created while another one holds the pool's memory has to obtain fresh device memory from the driver)
     e2e_ms = []
-    for _ in range(max(1, min(args.steps, 3))):
+    for it in range(1 + max(1, min(args.steps, 3))):
         flush.zero_()
         barrier()
         e0.record()
@@ -212,7 +213,8 @@ def main():
             res_e = api.align(host_g, prm, device=local_rank)
         e1.record()
         barrier()
-        e2e_ms.append(e0.elapsed_time(e1))
+        if it > 0:
+            e2e_ms.append(e0.elapsed_time(e1))
     t_sum = torch.tensor([sum(step_ms), sum(e2e_ms) / len(e2e_ms) * args.steps], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t_sum, op=dist.ReduceOp.MAX)
@@ -256,8 +258,18 @@ def main():
     dom = max(dom_total, key=lambda k: dom_total[k])
     rk = roof_kernels[dom]
     ach = rk["bytes"] / (rk["ms"] / 1000.0) / 1e9 if rk["ms"] > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                "peak_source": peak_src,
+    # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this workload (tools/ncu_traffic.py)
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        kname = {"recursion(small_region_kernel)": "small_region_kernel", "mum_scan(seed_extend_kernel)": "seed_extend_kernel"}.get(dom)
+        if args.workload == "configs1" and L == L_FULL and kname in tj["kernels"]:
+            traffic = tj["kernels"][kname]["dram_bytes_per_launch"]
+            traffic_src = "profiles/ncu_traffic.json (" + tj["source"] + ")"
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": rk["bytes"], "ms_per_launch": rk["ms"],
                 "share_of_gpu_time": dom_total[dom] / gpu_ms_total if gpu_ms_total else 0.0,
                 "other": {k: {"GBps": (v["bytes"] / (v["ms"] / 1000.0) / 1e9 if v["ms"] > 0 else 0.0), "ms": v["ms"]}

@@ -24,14 +24,6 @@ constexpr int MAX_SEED_K = 12;
 
 struct StrandDesc { const uint8_t* q; int32_t m; int32_t pad; };
 
-__device__ __forceinline__ uint64_t load8u(const uint8_t* p) {
-    const uint64_t* a = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)7);
-    const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(p) & 7) * 8;
-    uint64_t lo = a[0];
-    if (sh == 0) return lo;
-    uint64_t hi = a[1];
-    return (lo >> sh) | (hi << (64 - sh));
-}
 // number of equal leading bytes of a[0..limit) and b[0..limit)
 __device__ __forceinline__ int match_len(const uint8_t* a, const uint8_t* b, int limit) {
     int t = 0;
@@ -270,8 +262,6 @@ __device__ __forceinline__ int cmp_kmer(const uint8_t* __restrict__ R, int n, in
     return 0;
 }
 
-// four 2-bit base codes (one per byte, first base in byte 0) -> 8 bits, first base most significant
-__device__ __forceinline__ uint32_t pack4x2(uint32_t w) { return ((w & 0x03030303u) * 0x40100401u) >> 24; }
 // 4 bases packed like side_sig from bytes 4..7 of a little-endian 8-byte word (byte 4 = first base)
 __device__ __forceinline__ uint32_t sig_hi4(uint64_t w) {
     return (uint32_t)((w >> 32) & 7u) << 9 | (uint32_t)((w >> 40) & 7u) << 6 | (uint32_t)((w >> 48) & 7u) << 3 | (uint32_t)((w >> 56) & 7u);
@@ -715,7 +705,7 @@ public:
 
 private:
     template <class K>
-    void sort_and_finish(K* k0, K* k1, int end_bit, int64_t h0, cudaStream_t st, bool doubling) {
+    void sort_and_finish(K* k0, K* k1, int end_bit, int64_t h0, cudaStream_t st, bool doubling, const uint8_t* key_text) {
         const int TB = 256;
         const int n = idx_n_;
         const uint8_t* R = idx_R_;
@@ -723,7 +713,7 @@ private:
         uint32_t* v0 = vals0_.get();
         uint32_t* v1 = vals1_.get();
         if (tm) tm->start(GpuTimers::T_INDEX_SORT, st);
-        const int res = sorter_.sort<K, uint32_t>(k0, k1, v0, v1, n, 0, end_bit, st);
+        const int res = sorter_.sort<K, uint32_t>(k0, k1, v0, v1, n, 0, end_bit, st, key_text);
         const K* ks = res ? k1 : k0;
         uint32_t* sa = res ? v1 : v0;                          // the sorted values ARE the suffix array (refined in place below)
         sa_ptr_ = sa;
@@ -822,18 +812,20 @@ private:
         last_index.rounds = 0;
         last_index.unsorted_after_sort = -1;
         if (idx_two_bit_) {
-            // N-free window: 32-bit keys of 16 bases, 4 radix passes over (4 B key + 4 B value)
+            // N-free window: 32-bit keys of 16 bases, 4 radix passes over (4 B key + 4 B value); the first pass packs the keys
+            // straight from the window text (no key-generation kernel)
             uint32_t* q0 = reinterpret_cast<uint32_t*>(k0);
             uint32_t* q1 = reinterpret_cast<uint32_t*>(k1);
-            if (tm) tm->start(GpuTimers::T_INDEX_KEYS, st);
-            pb200::launch(make_keys2_kernel, nb, TB, 0, st, R, n, q0, v0);
-            if (tm) tm->stop(GpuTimers::T_INDEX_KEYS, st);
-            sort_and_finish<uint32_t>(q0, q1, 2 * KEY2_BASES, KEY2_BASES, st, doubling);
+            if (n >= 2) sort_and_finish<uint32_t>(q0, q1, 2 * KEY2_BASES, KEY2_BASES, st, doubling, R);
+            else {
+                pb200::launch(make_keys2_kernel, nb, TB, 0, st, R, n, q0, v0);
+                sort_and_finish<uint32_t>(q0, q1, 2 * KEY2_BASES, KEY2_BASES, st, doubling, nullptr);
+            }
         } else {
             if (tm) tm->start(GpuTimers::T_INDEX_KEYS, st);
             pb200::launch(make_keys_kernel, nb, TB, 0, st, R, n, k0, v0);
             if (tm) tm->stop(GpuTimers::T_INDEX_KEYS, st);
-            sort_and_finish<uint64_t>(k0, k1, 3 * KEY_BASES, KEY_BASES, st, doubling);
+            sort_and_finish<uint64_t>(k0, k1, 3 * KEY_BASES, KEY_BASES, st, doubling, nullptr);
         }
         PB_CUDA(cudaGetLastError());
     }

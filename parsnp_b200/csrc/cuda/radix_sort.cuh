@@ -3,7 +3,10 @@
 //   digit_scan_kernel  one block per digit: exclusive scan over the tiles + global digit offset (in place)
 //   scatter_kernel     ranks a 2048-key tile in shared memory (warp match_any multisplit), stages the tile sorted by
 //                      digit in shared memory and writes each digit run out contiguously (coalesced)
-// plus one hist_kernel/scan_hist_kernel pair up front for the global digit offsets of all passes.
+// The global offset of a digit is the sum of the totals of the smaller digits: digit_scan_kernel leaves the totals, every
+// scatter block adds them up itself (256 values) - no separate histogram pass over the keys.
+// The first pass can take its keys straight from the window text (N-free windows: the packed 16-mer of suffix i, value i),
+// so the suffix-array build has no key-generation kernel and pass 1 reads 1 byte instead of 8 per suffix.
 // (A one-sweep variant with decoupled look-back was measured first: with ~600 resident tiles every tile walks hundreds of
 //  predecessor states and the pass time stayed at ~75 us whatever the record size - profiles/r01_*; the split form moves
 //  8 (4) more bytes per key and pass but has no cross-block dependency.)
@@ -24,42 +27,8 @@ constexpr int RS_TILE = RS_THREADS * RS_ITEMS;   // 2048 keys per tile: ~64 regi
 constexpr uint32_t ST_MASK = (1u << 30) - 1;
 
 template <class K>
-__global__ void __launch_bounds__(256) hist_kernel(const K* __restrict__ keys, int64_t n, int begin_bit, int end_bit, int npass,
-                                                   uint32_t* __restrict__ ghist) {
-    __shared__ uint32_t h[8 * 256];
-    for (int i = threadIdx.x; i < npass * 256; i += blockDim.x) h[i] = 0;
-    __syncthreads();
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        K key = keys[i];
-        for (int p = 0; p < npass; ++p) {
-            int shift = begin_bit + 8 * p;
-            int bits = min(8, end_bit - shift);
-            uint32_t d = (uint32_t)(key >> shift) & ((1u << bits) - 1);
-            atomicAdd(&h[p * 256 + d], 1u);
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < npass * 256; i += blockDim.x)
-        if (h[i]) atomicAdd(&ghist[i], h[i]);
-}
-
-// exclusive scan of each pass's 256 bins: one block of 256 threads per pass
-__global__ void __launch_bounds__(256) scan_hist_kernel(const uint32_t* __restrict__ ghist, uint32_t* __restrict__ gofs) {
-    __shared__ uint32_t wsum[8];
-    const int p = blockIdx.x, d = threadIdx.x, lane = d & 31, w = d >> 5;
-    uint32_t v = ghist[p * 256 + d];
-    uint32_t x = v;
-    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-    if (lane == 31) wsum[w] = x;
-    __syncthreads();
-    uint32_t base = 0;
-    for (int i = 0; i < w; ++i) base += wsum[i];
-    gofs[p * 256 + d] = base + x - v;
-}
-
-template <class K>
 __global__ void __launch_bounds__(RS_THREADS) tile_hist_kernel(const K* __restrict__ kin, int64_t n, int shift, int bits,
-                                                               uint32_t* __restrict__ counts, int64_t tiles) {
+                                                               uint32_t* __restrict__ counts, int64_t tiles, const uint8_t* __restrict__ text) {
     __shared__ uint32_t h[256];
     const int tid = threadIdx.x;
     h[tid] = 0;
@@ -69,18 +38,23 @@ __global__ void __launch_bounds__(RS_THREADS) tile_hist_kernel(const K* __restri
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
         int64_t i = tile_base + r * RS_THREADS + tid;
-        if (i < n) atomicAdd(&h[(uint32_t)(kin[i] >> shift) & mask], 1u);
+        if (i < n) {
+            uint32_t d;
+            if (text) d = (shift == 0 ? text_key2_low8(text, n, i) : (uint32_t)(text_key2(text, n, i) >> shift)) & mask;
+            else d = (uint32_t)(kin[i] >> shift) & mask;
+            atomicAdd(&h[d], 1u);
+        }
     }
     __syncthreads();
     counts[(int64_t)tid * tiles + blockIdx.x] = h[tid];
 }
 
-// block d: counts[d][0..tiles) -> exclusive prefix + gofs[d]
-__global__ void __launch_bounds__(256) digit_scan_kernel(uint32_t* __restrict__ counts, int64_t tiles, const uint32_t* __restrict__ gofs) {
+// block d: counts[d][0..tiles) -> exclusive prefix over the tiles; totals[d] = number of keys with digit d
+__global__ void __launch_bounds__(256) digit_scan_kernel(uint32_t* __restrict__ counts, int64_t tiles, uint32_t* __restrict__ totals) {
     __shared__ uint32_t s_w[8];
     uint32_t* row = counts + (int64_t)blockIdx.x * tiles;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint32_t carry = gofs[blockIdx.x];
+    uint32_t carry = 0;
     for (int64_t b = 0; b < tiles; b += 256) {
         int64_t i = b + threadIdx.x;
         uint32_t v = i < tiles ? row[i] : 0u;
@@ -94,12 +68,14 @@ __global__ void __launch_bounds__(256) digit_scan_kernel(uint32_t* __restrict__ 
         carry += tot;
         __syncthreads();
     }
+    if (threadIdx.x == 0) totals[blockIdx.x] = carry;
 }
 
-template <class K, class V>
-__global__ void __launch_bounds__(RS_THREADS, (sizeof(K) == 4 ? 6 : 4)) scatter_kernel(const K* __restrict__ kin, K* __restrict__ kout,
+template <class K, class V, bool FROM_TEXT>
+__global__ void __launch_bounds__(RS_THREADS, (sizeof(K) == 4 ? (FROM_TEXT ? 5 : 6) : 4)) scatter_kernel(const K* __restrict__ kin, K* __restrict__ kout,
                                                                 const V* __restrict__ vin, V* __restrict__ vout, int64_t n, int shift,
-                                                                int bits, const uint32_t* __restrict__ offsets, int64_t tiles) {
+                                                                int bits, const uint32_t* __restrict__ offsets, int64_t tiles,
+                                                                const uint32_t* __restrict__ totals, const uint8_t* __restrict__ text) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     K* s_keys = reinterpret_cast<K*>(smem_raw);                                  // RS_TILE
     V* s_vals = reinterpret_cast<V*>(smem_raw + sizeof(K) * RS_TILE);            // RS_TILE
@@ -113,16 +89,30 @@ __global__ void __launch_bounds__(RS_THREADS, (sizeof(K) == 4 ? 6 : 4)) scatter_
     const int64_t tile = blockIdx.x;
     const int64_t tile_base = tile * RS_TILE;
     const int64_t wbase = tile_base + (int64_t)warp * (RS_ITEMS * 32);
+    // global start of digit `tid` for this tile = keys with a smaller digit (exclusive scan of the 256 totals) + the
+    // digit's keys in earlier tiles
+    {
+        const uint32_t t = totals[tid];
+        uint32_t x = t;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_wsum[warp] = x;
+        __syncthreads();
+        uint32_t wb = 0;
+        for (int i = 0; i < warp; ++i) wb += s_wsum[i];
+        s_base[tid] = offsets[(int64_t)tid * tiles + tile] + wb + x - t;      // parked in shared memory (turned into base - local start below)
+    }
     K key[RS_ITEMS];
     V val[RS_ITEMS];
     uint16_t rank[RS_ITEMS];
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
         int64_t i = wbase + r * 32 + lane;
-        if (i < n) { key[r] = kin[i]; val[r] = vin[i]; }
+        if (i < n) {
+            if (FROM_TEXT) { key[r] = (K)text_key2(text, n, i); val[r] = (V)i; }  // first pass of the suffix-array build
+            else { key[r] = kin[i]; val[r] = vin[i]; }
+        }
         else { key[r] = (K)0; val[r] = (V)0; }
     }
-    const uint32_t my_off = offsets[(int64_t)tid * tiles + tile];      // global start of digit `tid` for this tile
     __syncthreads();
     uint32_t* mywh = s_whist + warp * 256;
 #pragma unroll
@@ -160,7 +150,7 @@ __global__ void __launch_bounds__(RS_THREADS, (sizeof(K) == 4 ? 6 : 4)) scatter_
         for (int i = 0; i < warp; ++i) wb += s_wsum[i];
         uint32_t dstart = wb + x - tot;
         s_dstart[d] = dstart;
-        s_base[d] = my_off - dstart;              // global position = s_base[digit] + local position (mod 2^32)
+        s_base[d] = s_base[d] - dstart;           // global position = s_base[digit] + local position (mod 2^32)
     }
     __syncthreads();
 #pragma unroll
@@ -189,25 +179,24 @@ public:
     // Sorts n pairs by key bits [begin_bit, end_bit).  Buffers 0 hold the input; returns the index (0/1) of the
     // buffer pair holding the sorted output.  Stable.
     template <class K, class V>
-    int sort(K* k0, K* k1, V* v0, V* v1, int64_t n, int begin_bit, int end_bit, cudaStream_t st) {
-        if (n <= 1 || end_bit <= begin_bit) return 0;
+    int sort(K* k0, K* k1, V* v0, V* v1, int64_t n, int begin_bit, int end_bit, cudaStream_t st, const uint8_t* first_pass_text = nullptr) {
+        if (n <= 1 || end_bit <= begin_bit) {
+            if (first_pass_text) throw CudaError("radix sort: a text-keyed sort needs at least one pass");
+            return 0;
+        }
         if (n > (int64_t)ST_MASK) throw CudaError("radix sort: n too large");
         const int npass = (end_bit - begin_bit + 7) / 8;
         const int64_t tiles = (n + RS_TILE - 1) / RS_TILE;
-        const size_t words = (size_t)npass * 256 * 2 + (size_t)256 * tiles;
+        const size_t words = (size_t)256 + (size_t)256 * tiles;
         uint32_t* tmp = tmp_.ensure(words, false, st);
-        PB_CUDA(cudaMemsetAsync(tmp, 0, (size_t)npass * 256 * 2 * sizeof(uint32_t), st));
-        uint32_t* ghist = tmp;
-        uint32_t* gofs = tmp + (size_t)npass * 256;
-        uint32_t* counts = gofs + (size_t)npass * 256;
-        int hb = (int)std::min<int64_t>((n + 256 * 16 - 1) / (256 * 16), 148 * 8);
-        pb200::launch(hist_kernel<K>, hb, 256, 0, st, k0, n, begin_bit, end_bit, npass, ghist);
-        pb200::launch(scan_hist_kernel, npass, 256, 0, st, ghist, gofs);
+        uint32_t* totals = tmp;
+        uint32_t* counts = tmp + 256;
         const size_t smem = (sizeof(K) + sizeof(V)) * RS_TILE + (RS_WARPS * 256 + 512) * sizeof(uint32_t);
         static bool attr_set[2][2] = {{false, false}, {false, false}};
         bool& a = attr_set[sizeof(K) == 8][sizeof(V) == 8];
         if (!a) {
-            PB_CUDA(cudaFuncSetAttribute(scatter_kernel<K, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PB_CUDA(cudaFuncSetAttribute(scatter_kernel<K, V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PB_CUDA(cudaFuncSetAttribute(scatter_kernel<K, V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             a = true;
         }
         K* kin = k0; K* kout = k1; V* vin = v0; V* vout = v1;
@@ -215,9 +204,11 @@ public:
         for (int p = 0; p < npass; ++p) {
             int shift = begin_bit + 8 * p;
             int bits = std::min(8, end_bit - shift);
-            pb200::launch(tile_hist_kernel<K>, (unsigned)tiles, RS_THREADS, 0, st, kin, n, shift, bits, counts, tiles);
-            pb200::launch(digit_scan_kernel, 256, 256, 0, st, counts, tiles, gofs + (size_t)p * 256);
-            pb200::launch(scatter_kernel<K, V>, (unsigned)tiles, RS_THREADS, smem, st, kin, kout, vin, vout, n, shift, bits, counts, tiles);
+            const uint8_t* text = p == 0 ? first_pass_text : nullptr;
+            pb200::launch(tile_hist_kernel<K>, (unsigned)tiles, RS_THREADS, 0, st, kin, n, shift, bits, counts, tiles, text);
+            pb200::launch(digit_scan_kernel, 256, 256, 0, st, counts, tiles, totals);
+            if (text) pb200::launch(scatter_kernel<K, V, true>, (unsigned)tiles, RS_THREADS, smem, st, kin, kout, vin, vout, n, shift, bits, counts, tiles, totals, text);
+            else pb200::launch(scatter_kernel<K, V, false>, (unsigned)tiles, RS_THREADS, smem, st, kin, kout, vin, vout, n, shift, bits, counts, tiles, totals, text);
             std::swap(kin, kout);
             std::swap(vin, vout);
             res ^= 1;

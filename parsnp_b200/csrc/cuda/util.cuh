@@ -171,6 +171,36 @@ inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
     kernel<<<grid, block, smem, st>>>(static_cast<KArgs>(args)...);
 }
 
+// unaligned 8-byte load (two aligned loads + funnel shift); may read up to 15 bytes past p: every text buffer is padded
+__device__ __forceinline__ uint64_t load8u(const uint8_t* p) {
+    const uint64_t* a = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)7);
+    const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(p) & 7) * 8;
+    uint64_t lo = a[0];
+    if (sh == 0) return lo;
+    uint64_t hi = a[1];
+    return (lo >> sh) | (hi << (64 - sh));
+}
+// four 2-bit base codes (one per byte, first base in byte 0) -> 8 bits, first base most significant
+__device__ __forceinline__ uint32_t pack4x2(uint32_t w) { return ((w & 0x03030303u) * 0x40100401u) >> 24; }
+// key of suffix i of an N-free window: its first 16 bases at 2 bits each, first base most significant, past the end = 0
+__device__ __forceinline__ uint32_t text_key2(const uint8_t* __restrict__ R, int64_t n, int64_t i) {
+    uint64_t w0 = load8u(R + i), w1 = load8u(R + i + 8);
+    const int64_t valid = n - i;
+    if (valid < 16) {
+        w0 = valid >= 8 ? w0 : (valid <= 0 ? 0ull : (w0 & ((1ull << (8 * valid)) - 1ull)));
+        w1 = valid <= 8 ? 0ull : (w1 & ((1ull << (8 * (valid - 8))) - 1ull));
+    }
+    return (pack4x2((uint32_t)w0) << 24) | (pack4x2((uint32_t)(w0 >> 32)) << 16) | (pack4x2((uint32_t)w1) << 8) | pack4x2((uint32_t)(w1 >> 32));
+}
+
+// its low 8 bits (bases 12..15 of the suffix) without reading the other twelve
+__device__ __forceinline__ uint32_t text_key2_low8(const uint8_t* __restrict__ R, int64_t n, int64_t i) {
+    uint32_t w = (uint32_t)load8u(R + i + 12);
+    const int64_t valid = n - (i + 12);
+    if (valid < 4) w = valid <= 0 ? 0u : (w & ((1u << (8 * valid)) - 1u));
+    return pack4x2(w);
+}
+
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 }  // namespace pb200

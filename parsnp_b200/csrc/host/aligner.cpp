@@ -378,6 +378,180 @@ void Aligner::accept_candidates(const int64_t* rs, const int64_t* re, int64_t rs
     }
 }
 
+// The same loop for a big candidate list on an EMPTY layout region (the anchors): candidates whose intervals overlap no other
+// candidate's interval in any genome are untouched by the trim loop whatever the order (the only bits in their intervals
+// would be their own), so they are validated and placed in parallel; the overlapping ones (few) go through the literal
+// sequential loop above, in candidate order, among themselves.  Result identical to accept_candidates().
+void Aligner::accept_candidates_parallel(const int64_t* rs, const int64_t* re, int64_t rsl, int cache_idx, std::vector<BitRow>& layout,
+                                         MumPool& mp, std::vector<int>& found, bool trace) {
+    const CacheEntry& ce = cache_entries_[cache_idx];
+    const int nq = n_ - 1;
+    const size_t N = (size_t)n_;
+    std::vector<int64_t> wbase((size_t)ce.nwin + 1, 0);
+    for (int wi = 0; wi < ce.nwin; ++wi) {
+        const WinRec& win = wins_[ce.first_win + wi];
+        wbase[wi + 1] = wbase[wi] + win.ncand;
+        if (trace) trace_.emplace_back(win.ref_start, win.ref_len);
+    }
+    const size_t C = (size_t)wbase[ce.nwin];
+    if (C == 0) return;
+    pod_vector<int64_t> ST(C * N), STT(C * N), LON(C);          // starts: candidate-major and genome-major
+    pod_vector<uint8_t> FW(C * N), state(C);                     // state: 0 = skipped, 1 = valid, 3 = valid + overlapping
+    const long per = 256;
+    const long nblk = ((long)C + per - 1) / per;
+    // ---- pass 1: coordinates and the pre-checks of src/parsnp.cpp:1723 / TMum ctor, per candidate
+    parallel_chunks(threads_, nblk, [&](long b) {
+        const size_t c0 = (size_t)b * per, c1 = std::min(C, c0 + (size_t)per);
+        int wi = (int)(std::upper_bound(wbase.begin(), wbase.end(), (int64_t)c0) - wbase.begin()) - 1;
+        for (size_t c = c0; c < c1; ++c) {
+            while ((int64_t)c >= wbase[wi + 1]) ++wi;
+            const WinRec& win = wins_[ce.first_win + wi];
+            const CandBatch& cb = chunks_[win.chunk];
+            const int64_t ci = win.cand_off + ((int64_t)c - wbase[wi]);
+            const int64_t lon = cb.lon[ci];
+            int64_t* st = &ST[c * N];
+            uint8_t* fw = &FW[c * N];
+            bool bad = false;
+            const uint64_t dsp0 = (uint64_t)((int64_t)cb.k[ci] + 1 + win.ref_start);
+            if ((uint64_t)(dsp0 - (uint64_t)rs[0]) > (uint64_t)(uint32_t)(re[0] - rs[0])) bad = true;
+            st[0] = (int64_t)dsp0 - 1;
+            fw[0] = 1;
+            bool any_fail = st[0] + lon > len_[0] || st[0] < 0;
+            const int32_t* spj = cb.sp.data() + ci * nq;
+            const uint8_t* fwj = cb.fwd.data() + ci * nq;
+            for (int j = 1; j < n_; ++j) {
+                const uint64_t dsp = (uint64_t)((int64_t)spj[j - 1] + 1 + rs[j]);
+                bad |= (uint64_t)(dsp - (uint64_t)rs[j]) > (uint64_t)(uint32_t)(re[j] - rs[j]);
+                int64_t s = (int64_t)dsp - 1;
+                const uint8_t f = fwj[j - 1];
+                if (!f) s = len_[j] - (s + lon);
+                any_fail |= (s + lon > len_[j]) | (s < 0);
+                st[j] = s;
+                fw[j] = f;
+            }
+            LON[c] = lon;
+            state[c] = (bad || any_fail || lon < 5) ? 0 : 1;
+        }
+        for (int j = 0; j < n_; ++j) {                      // genome-major copy of the block (contiguous runs)
+            int64_t* d = &STT[(size_t)j * C];
+            for (size_t c = c0; c < c1; ++c) d[c] = ST[c * N + j];
+        }
+    });
+    // ---- pass 2: per genome, mark the valid candidates whose interval overlaps another valid candidate's
+    parallel_chunks(threads_, (long)n_, [&](long j) {
+        const int64_t* sj = &STT[(size_t)j * C];
+        auto mark = [&](size_t c) { __atomic_store_n(&state[c], (uint8_t)3, __ATOMIC_RELAXED); };
+        bool sorted = true;
+        int64_t prev = INT64_MIN;
+        for (size_t c = 0; c < C && sorted; ++c) {
+            if (!(__atomic_load_n(&state[c], __ATOMIC_RELAXED) & 1)) continue;
+            if (sj[c] < prev) sorted = false;
+            prev = sj[c];
+        }
+        int64_t max_end = INT64_MIN;
+        size_t arg = 0;
+        auto visit = [&](size_t c) {
+            const int64_t s = sj[c], e = s + LON[c];
+            if (s < max_end) { mark(c); mark(arg); }
+            if (e > max_end) { max_end = e; arg = c; }
+        };
+        if (sorted) {
+            for (size_t c = 0; c < C; ++c) if (__atomic_load_n(&state[c], __ATOMIC_RELAXED) & 1) visit(c);
+        } else {
+            std::vector<std::pair<int64_t, uint32_t>> iv;
+            iv.reserve(C);
+            for (size_t c = 0; c < C; ++c) if (__atomic_load_n(&state[c], __ATOMIC_RELAXED) & 1) iv.emplace_back(sj[c], (uint32_t)c);
+            std::sort(iv.begin(), iv.end());
+            for (const auto& x : iv) visit(x.second);
+        }
+    });
+    // ---- pass 3a: the overlapping candidates, literally as in accept_candidates(), in candidate order
+    pod_vector<int64_t> LEN(C);                                 // accepted length, 0 = not accepted
+    for (size_t c = 0; c < C; ++c) {
+        LEN[c] = 0;
+        if (state[c] != 3) continue;
+        int64_t* st = &ST[c * N];
+        const uint8_t* fw = &FW[c * N];
+        int64_t length = LON[c];
+        for (int j = 0; j < n_; ++j) {
+            int64_t t1 = layout[j].run_up(st[j], st[j] + length);
+            if (t1) { for (int i = 0; i < n_; ++i) st[i] += t1; length -= t1; }
+            int64_t t2 = layout[j].run_down(st[j], st[j] + length);
+            length -= t2;
+            if (length <= 0) break;
+        }
+        if (length < 2 || n_ <= 1) continue;
+        bool badmum = false;
+        for (int k = 0; k < n_ && !badmum; ++k) {
+            if (fw[k]) continue;
+            const uint8_t* g0 = seq_[0] + st[0];
+            const uint8_t* gk = seq_[k] + st[k];
+            for (int64_t t = 0; t < length; ++t)
+                if (comp_base(gk[length - 1 - t]) != g0[t]) { badmum = true; break; }
+        }
+        if (badmum) continue;
+        for (int k = 0; k < n_; ++k) layout[k].set_range(st[k], st[k] + length);
+        LEN[c] = length;
+    }
+    // ---- pass 3b: everybody else, in parallel (nothing to trim)
+    parallel_chunks(threads_, nblk, [&](long b) {
+        const size_t c0 = (size_t)b * per, c1 = std::min(C, c0 + (size_t)per);
+        for (size_t c = c0; c < c1; ++c) {
+            if (state[c] != 1) continue;
+            const int64_t length = LON[c];
+            if (length < 2 || n_ <= 1) continue;
+            const int64_t* st = &ST[c * N];
+            const uint8_t* fw = &FW[c * N];
+            bool badmum = false;
+            for (int k = 0; k < n_ && !badmum; ++k) {
+                if (fw[k]) continue;
+                const uint8_t* g0 = seq_[0] + st[0];
+                const uint8_t* gk = seq_[k] + st[k];
+                for (int64_t t = 0; t < length; ++t)
+                    if (comp_base(gk[length - 1 - t]) != g0[t]) { badmum = true; break; }
+            }
+            if (badmum) continue;
+            for (int k = 0; k < n_; ++k) layout[k].set_range_atomic(st[k], st[k] + length);
+            LEN[c] = length;
+        }
+    });
+    if (getenv("PB200_PROFILE_HOST")) {
+        size_t nv = 0, no = 0;
+        for (size_t c = 0; c < C; ++c) { nv += state[c] & 1; no += state[c] == 3; }
+        fprintf(stderr, "[pb200 anchors] parallel accept: %zu candidates, %zu valid, %zu overlapping (sequential)\n", C, nv, no);
+    }
+    // ---- accepted MUMs into the pool, in candidate order
+    std::vector<size_t> blk_cnt((size_t)nblk + 1, 0);
+    for (long b = 0; b < nblk; ++b) {
+        size_t k = 0;
+        for (size_t c = (size_t)b * per; c < std::min(C, (size_t)(b + 1) * per); ++c) k += LEN[c] > 0;
+        blk_cnt[b + 1] = blk_cnt[b] + k;
+    }
+    const size_t A = blk_cnt[nblk];
+    const size_t m0 = mp.mums.size(), s0 = mp.start.size();
+    mp.mums.resize(m0 + A);
+    mp.start.resize(s0 + A * N);
+    mp.fwd.resize(s0 + A * N);
+    const size_t f0 = found.size();
+    found.resize(f0 + A);
+    parallel_chunks(threads_, nblk, [&](long b) {
+        size_t a = blk_cnt[b];
+        for (size_t c = (size_t)b * per; c < std::min(C, (size_t)(b + 1) * per); ++c) {
+            if (LEN[c] <= 0) continue;
+            MumRec m;
+            m.length = LEN[c];
+            m.slength = rsl;
+            m.off = (int64_t)(s0 + a * N);
+            m.alive = true;
+            std::memcpy(&mp.start[s0 + a * N], &ST[c * N], sizeof(int64_t) * N);
+            std::memcpy(&mp.fwd[s0 + a * N], &FW[c * N], N);
+            mp.mums[m0 + a] = m;
+            found[f0 + a] = (int)(m0 + a);
+            ++a;
+        }
+    });
+}
+
 // determineRegion (src/parsnp.cpp:1199-1290) into tmp coordinate buffers; returns slength
 static int64_t det_region(const std::vector<BitRow>& layout, const std::vector<int64_t>& len, int n,
                           const int64_t* mstart, int64_t mlen, bool left, int64_t* S, int64_t* E) {
@@ -416,7 +590,11 @@ void Aligner::set_initial_clusters() {
         mp_.fwd.reserve(est * (size_t)n_);
         found.reserve((size_t)stats_.candidates);
     }
-    accept_candidates(rstart(whole), rend(whole), rp_.slen[whole], cache_lookup(whole), truth_.layout, mp_, found, false, trace_on_);
+    const char* pmin = getenv("PB200_PAR_ANCHORS_MIN");          // tests: 1 forces the parallel accept, a huge value the serial one
+    if (threads_ > 1 && stats_.candidates >= (pmin ? atoll(pmin) : 8192))
+        accept_candidates_parallel(rstart(whole), rend(whole), rp_.slen[whole], cache_lookup(whole), truth_.layout, mp_, found, trace_on_);
+    else
+        accept_candidates(rstart(whole), rend(whole), rp_.slen[whole], cache_lookup(whole), truth_.layout, mp_, found, false, trace_on_);
     all_mums_ = found;
     stats_.anchors = (int64_t)found.size();
     const double ta1 = now_s();
@@ -718,15 +896,37 @@ void Aligner::do_work_exact() {
 // reference), so the order is unique.  Sorts compact (start0,id) pairs and skips the work when already sorted.
 void Aligner::sort_final_mums() {
     const size_t M = final_mums_.size();
+    if (final_sorted_) return;                  // (removals keep the order; only `final_mums_ = all_mums_` resets the flag)
     std::vector<std::pair<int64_t, int>> kv(M);
+    // gather the keys (random reads into the MUM pools) in parallel; per chunk: descents inside, first/last key, min length
+    const long per = 8192;
+    const long nch = ((long)M + per - 1) / per;
+    std::vector<size_t> ch_desc((size_t)nch, 0), ch_split((size_t)nch, 0);
+    std::vector<int64_t> ch_max((size_t)nch, 0), ch_minlen((size_t)nch, INT64_MAX);
+    parallel_chunks(M > 32768 ? threads_ : 1, nch, [&](long c) {
+        size_t d = 0, sp = 0;
+        int64_t mx = 0, ml = INT64_MAX;
+        const size_t i0 = (size_t)c * per, i1 = std::min(M, (size_t)(c + 1) * per);
+        for (size_t i = i0; i < i1; ++i) {
+            const MumRec& m = mums_[final_mums_[i]];
+            const int64_t s0 = mum_start_[m.off];
+            kv[i] = std::make_pair(s0, final_mums_[i]);
+            if (i > i0 && s0 < kv[i - 1].first) { ++d; sp = i; }
+            mx = std::max(mx, s0);
+            ml = std::min(ml, m.length);
+        }
+        ch_desc[c] = d; ch_split[c] = sp; ch_max[c] = mx; ch_minlen[c] = ml;
+    });
     size_t descents = 0, split = 0;
     int64_t maxkey = 0;
-    for (size_t i = 0; i < M; ++i) {
-        const int64_t s0 = mum_start_[mums_[final_mums_[i]].off];
-        kv[i] = std::make_pair(s0, final_mums_[i]);
-        if (i && s0 < kv[i - 1].first) { ++descents; split = i; }
-        maxkey = std::max(maxkey, s0);
+    final_min_length_ = INT64_MAX;
+    for (long c = 0; c < nch; ++c) {
+        if (ch_desc[c]) { descents += ch_desc[c]; split = ch_split[c]; }
+        if (c > 0 && kv[(size_t)c * per].first < kv[(size_t)c * per - 1].first) { ++descents; split = (size_t)c * per; }
+        maxkey = std::max(maxkey, ch_max[c]);
+        final_min_length_ = std::min(final_min_length_, ch_minlen[c]);
     }
+    final_sorted_ = true;
     if (descents == 0) return;
     std::vector<std::pair<int64_t, int>> tmp(M);
     if (descents == 1) {
@@ -755,6 +955,7 @@ void Aligner::filter_random1() {
     const int rvalue = prm_.random;
     size_t numums = final_mums_.size();
     if (numums == 0) return;
+    if (final_min_length_ > rvalue) return;        // no MUM is short enough to be examined by the loop below
     for (size_t ms = 0; ms + 1 < numums; ++ms) {
         const MumRec& mt = mums_[final_mums_[ms]];
         if (mt.length > rvalue) continue;
@@ -993,6 +1194,7 @@ bool Aligner::run() {
     if (all_mums_.empty()) { stats_.t_total = now_s() - t0; return false; }
     double t1 = now_s();
     final_mums_ = all_mums_;
+    final_sorted_ = false;
     const bool prof = getenv("PB200_PROFILE_HOST") != nullptr;
     double tl[6] = {now_s(), 0, 0, 0, 0, 0};
     if (prm_.random) filter_random1();

@@ -142,6 +142,9 @@ private:
     // setMums1 loop D on cached candidates; appends accepted MUMs to `mp`, their indices to `found`
     void accept_candidates(const int64_t* rs, const int64_t* re, int64_t rsl, int cache_idx, std::vector<BitRow>& layout, MumPool& mp,
                            std::vector<int>& found, bool atomic, bool trace);
+    // the same for a long candidate list on an empty layout (anchors): non-overlapping candidates in parallel
+    void accept_candidates_parallel(const int64_t* rs, const int64_t* re, int64_t rsl, int cache_idx, std::vector<BitRow>& layout, MumPool& mp,
+                                    std::vector<int>& found, bool trace);
     // doWork's loop over a queue of regions living in `rp`, in the exact reference order
     void process_queue_exact(const std::vector<int>& initial, RegionPool& rp, std::vector<BitRow>& layout, MumPool& mp,
                              std::vector<int>& out_mums);
@@ -173,6 +176,8 @@ private:
     std::vector<uint8_t>& mum_fwd_ = mp_.fwd;
     std::vector<int> all_mums_;       // this->mums in push order (ids into mums_)
     std::vector<int> final_mums_;
+    bool final_sorted_ = false;              // final_mums_ is in ascending start[0] order
+    int64_t final_min_length_ = 0;           // shortest MUM seen by the last sort_final_mums()
 
     World truth_;
     std::vector<int> initial_regions_;

@@ -114,6 +114,39 @@ def test_host_orchestrator_reproduces_reference(name):
         assert diff_dumps(result_to_dump(res2), gold) == []
 
 
+@pytest.mark.parametrize("name", ["c1a", "indep_20k", "rearr_60k", "windows_50k", "pop_30k_x12", "c1c"])
+def test_parallel_anchor_accept_reproduces_reference(name, monkeypatch):
+    """the anchors' accept pass split into non-overlapping candidates (parallel) and overlapping ones (literal loop) == golden;
+    rearr_60k has reverse-strand anchors and out-of-order query coordinates, windows_50k several reference windows"""
+    from oracle import hosttest
+    monkeypatch.setenv("PB200_PAR_ANCHORS_MIN", "1")
+    monkeypatch.setenv("PB200_HOST_THREADS", "4")
+    g, kw, gold = golden_case(name)
+    res = hosttest.align(g, api.make_params(**kw), backend=1)
+    assert diff_dumps(result_to_dump(res), gold) == []
+
+
+def test_parallel_anchor_accept_equals_serial_random(monkeypatch):
+    """random rearranged / repeat-carrying sets: parallel anchor accept == the literal serial loop (MUMs, LCBs, window trace)"""
+    from oracle import hosttest
+    from parsnp_b200 import synth
+    monkeypatch.setenv("PB200_HOST_THREADS", "4")
+    rng = np.random.default_rng(77)
+    for it in range(5):
+        g = synth.g_indep(25000, 3, 0.03, 200 + it)
+        ref = g[0].copy()
+        for _ in range(3):                     # short repeats inside the reference: overlapping / trimmed anchors
+            a, b, L = (int(x) for x in (rng.integers(0, 20000), rng.integers(0, 20000), rng.integers(30, 200)))
+            ref[b:b + L] = ref[a:a + L]
+        g = [ref] + [synth.rearrange(x, rng, n_inv=2, inv_len=1500) for x in g[1:]]
+        outs = []
+        for pmin in ("1", "1000000000"):
+            monkeypatch.setenv("PB200_PAR_ANCHORS_MIN", pmin)
+            outs.append(hosttest.align(g, api.make_params(flags=api.FLAG_TRACE_WINDOWS), backend=1))
+        assert diff_dumps(result_to_dump(outs[0]), result_to_dump(outs[1])) == []
+        assert np.array_equal(outs[0]["trace"], outs[1]["trace"])
+
+
 def test_window_order_matches_reference_trace():
     """sequence of (window start, length) searched by the exact replay == the reference's setMums1 call sequence"""
     from oracle import hosttest, runner
