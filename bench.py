@@ -26,7 +26,16 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ["NCCL_DEBUG"] = os.environ.get("PB200_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+if "PB200_NCCL_DEBUG" in os.environ:
+    os.environ["NCCL_DEBUG"] = os.environ["PB200_NCCL_DEBUG"]
+# stdout carries exactly ONE line, the JSON record: everything else any library prints to fd 1 (NCCL's version banner, ...) goes
+# to stderr; the record is written to the saved descriptor at the end
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 L_FULL, NQ, DIV, SEED = 5_000_000, 8, 0.01, 1
 L_CPU_SAMPLE = 1_000_000          # cpu_baseline leg: ~20 s of single-thread CPU work
@@ -118,7 +127,7 @@ def run_reference(args, rank, world):
                              "sample": "G_indep(%d,8,0.01,1); MUM+LCB path of parsnp_core is single-threaded (ini cores=%d only affects MUSCLE)"
                                        % (L_REF_STEP, os.cpu_count() or 1)},
             "e2e": {"value": val, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -129,8 +138,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--length", type=int, default=L_FULL, help="reference length (default = configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="configs1", choices=["configs1", "pop"],
-                    help="configs1 = G_indep(L, 8 q) [default, BASELINE configs[1]]; pop = G_pop(L, --nq) [configs[2] shape]")
+    ap.add_argument("--workload", default="configs1", choices=["configs1", "pop", "c4"],
+                    help="configs1 = G_indep(L, 8 q) [default, BASELINE configs[1]]; pop = G_pop(L, --nq) [configs[2] shape]; "
+                         "c4 = configs[3] shape: G_pop(--length [50 Mbp], --nq [64]) as 10 contigs, queries N-padded at contig breaks")
     ap.add_argument("--nq", type=int, default=NQ)
     ap.add_argument("--sharded", action="store_true", help="N>1: one alignment sharded over the ranks instead of one partition per rank")
     args = ap.parse_args()
@@ -154,7 +164,10 @@ def main():
     L = args.length
     sharded = args.sharded and world > 1
     seed = SEED if sharded else SEED + rank
-    if args.workload == "pop":
+    if args.workload == "c4":
+        genomes = synth.g_pop(L, args.nq, DIV, seed)
+        genomes = [genomes[0]] + [synth.with_contig_padding(g, 10) for g in genomes[1:]]
+    elif args.workload == "pop":
         genomes = synth.g_pop(L, args.nq, DIV, seed)
     else:
         genomes = synth.g_indep(L, NQ, DIV, seed)
@@ -281,7 +294,10 @@ def main():
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": ("configs[1]: G_indep(%d bp reference + %d queries, 1%% independent divergence, seed 1+rank), "
                                     "ini = template defaults (c=21 d=300 q=30 p=15000000 diagdiff=0.12)" % (L, NQ)) if args.workload == "configs1"
-                       else ("configs[2] shape: G_pop(%d bp reference + %d queries, 1%% divergence, seed 1), ini = template defaults" % (L, args.nq)),
+                       else (("configs[2] shape: G_pop(%d bp reference + %d queries, 1%% divergence, seed 1), ini = template defaults" % (L, args.nq))
+                             if args.workload == "pop" else
+                             ("configs[3] shape: G_pop(%d bp reference in 10 contigs + %d queries of 10 contigs with 310-N padding, 1%% divergence), "
+                              "p=15000000 (%d reference windows), ini = template defaults" % (L, args.nq, (L + 14999999) // 15000000))),
                        "bases_per_step_per_gpu": bases, "l2": "flushed between timed steps (256 MiB write)",
                        "parallelism": ("one alignment sharded over %d GPUs (queries / windows), NCCL exchange" % world) if sharded
                        else ("1 partition per GPU" if world > 1 else "single GPU")},
@@ -307,7 +323,7 @@ def main():
         except Exception as ex:  # the oracle binary is test infrastructure; absence must not break the bench
             line["cpu_baseline"] = {"value": None, "unit": "bases/s", "cores": 1, "kind": "reference", "sample": "unavailable: %s" % ex}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     G.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -68,6 +68,20 @@ def rearrange(g, rng, n_inv=2, inv_len=20000, dels=(37, 500), ins=(50,)):
     return g
 
 
+def with_contig_padding(g, contigs, d=300):
+    """a multi-contig QUERY as parsnp_core ingests it: d+10 N's at every contig break (src/parsnp.cpp:3114-3118); the reference
+    gets none. Same contig bounds as write_fasta(..., contigs=contigs)."""
+    L = len(g)
+    bounds = [L * i // contigs for i in range(contigs + 1)]
+    pad = np.full(d + 10, ord("N"), np.uint8)
+    parts = []
+    for c in range(contigs):
+        if c:
+            parts.append(pad)
+        parts.append(g[bounds[c]:bounds[c + 1]])
+    return np.concatenate(parts)
+
+
 def write_fasta(path, name, seq, width=80, contigs=1):
     """seq: uint8 ASCII array. contigs>1 splits into equal contigs with their own headers."""
     L = len(seq)

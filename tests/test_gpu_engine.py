@@ -226,6 +226,23 @@ def test_align_matches_reference_binary_fresh_input():
     G.close()
 
 
+def test_c4_shape_matches_reference_binary():
+    """BASELINE configs[3] shape at a size the reference finishes in seconds: multi-contig reference (concatenated seamlessly),
+    multi-contig queries (310 N's at every contig break - N is an ordinary matching symbol), several reference windows
+    (p < reference length, so 3-bit keys for no window but N-runs in every query) == reference binary run here"""
+    from oracle import runner
+    g = synth.g_pop(240_000, 5, 0.01, 9)
+    with tempfile.TemporaryDirectory() as td:
+        ref, qs = synth.write_dataset(os.path.join(td, "d"), g, contigs=4)
+        r = runner.run_ref(ref, qs, os.path.join(td, "r"), p=70000)
+        gi = [api.ingest_fasta(ref, True)] + [api.ingest_fasta(q, False) for q in qs]
+    for a, b in zip(gi[1:], g[1:]):
+        assert np.array_equal(a, synth.with_contig_padding(b, 4))
+    res = api.align(gi, api.make_params(p=70000))
+    assert len(res["mum_length"]) > 500
+    assert diff_dumps(result_to_dump(res), r["dump"]) == []
+
+
 def test_full_size_properties():
     """BASELINE config-2 shape at reduced query count (5 Mbp reference, 2 queries): size-independent properties -
     MUMs are exact matches in every genome, disjoint on the reference, LCB MUM sums consistent."""
