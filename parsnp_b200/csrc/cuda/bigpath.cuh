@@ -267,11 +267,29 @@ __device__ __forceinline__ uint32_t sig_hi4(uint64_t w) {
     return (uint32_t)((w >> 32) & 7u) << 9 | (uint32_t)((w >> 40) & 7u) << 6 | (uint32_t)((w >> 48) & 7u) << 3 | (uint32_t)((w >> 56) & 7u);
 }
 
+// one 256-byte step of a warp-cooperative comparison: equal leading bytes (0..8) of this lane's 8 bytes; 0 past the limit
+__device__ __forceinline__ int coop_step(const uint8_t* __restrict__ Q, const uint8_t* __restrict__ R, int qp, int rp, int lm, int base, int lane) {
+    const int off = base + lane * 8;
+    if (off >= lm) return 0;
+    const uint64_t x = load8u(Q + qp + off) ^ load8u(R + rp + off);
+    return x ? ((__ffsll((long long)x) - 1) >> 3) : 8;
+}
+// stop = ballot(my < 8): if some lane saw the end of the match, e = its length (capped by the limit)
+__device__ __forceinline__ bool coop_resolve(unsigned stop, int my, int lm, int base, int& e) {
+    if (!stop) return false;
+    const int fl = __ffs(stop) - 1;
+    e = min(lm, base + fl * 8 + __shfl_sync(0xffffffffu, my, fl));
+    return true;
+}
+
 // One thread per sampled query position (every step-th base): k-mer -> seed table -> flank-signature filter -> left extension
 // (de-duplication: a match of >= minsize bases contains exactly one sampled seed whose left extension is shorter than the
 // sample spacing).  The right extensions of a warp's surviving seeds are then done by the WHOLE warp, one seed after the other,
 // 32 x 8 bytes per step with a ballot for the first mismatch: the extension of a 100-base match is one step for everybody
-// instead of four divergent 32-byte steps for one lane.  Events are appended with one atomic per warp and round.
+// instead of four divergent 32-byte steps for one lane.  A seed whose
+// left neighbour in the warp hit the same diagonal one sample earlier, and whose 4-base left flank agrees with the reference,
+// lies inside that neighbour's match (sample spacing <= k + 4) and is dropped without touching the reference text.
+// Events are appended with one atomic per warp and round.
 __global__ void __launch_bounds__(128, 12) seed_extend_kernel(const uint8_t* __restrict__ R, int n, const uint32_t* __restrict__ sa,
                                                           const int32_t* __restrict__ lrp, const uint2* __restrict__ table,
                                                           int k, int step, int minsize,
@@ -291,6 +309,7 @@ __global__ void __launch_bounds__(128, 12) seed_extend_kernel(const uint8_t* __r
     // ---- the lane's seed: bucket [lo, hi) of the suffix array, or one text position (`single`)
     int lo = 0, hi = 0;
     int single = -1;
+    bool left_flank_eq = false;
     if (valid) {
         // k <= 12 bases = the low 2 bits of 12 consecutive bytes: two 8-byte loads; four bases are gathered by one multiply
         const uint64_t w0 = load8u(Q + j), w1 = load8u(Q + j + 8);
@@ -309,6 +328,7 @@ __global__ void __launch_bounds__(128, 12) seed_extend_kernel(const uint8_t* __r
                     else { ql = side_sig(Q, m, j - 4); qr = side_sig(Q, m, j + k); }
                     const uint32_t rl = (e.y >> 12) & 0xfffu, rr = e.y & 0xfffu;
                     if (ql != rl && qr != rr) hi = 0;
+                    left_flank_eq = ql == rl;
                 }
             } else { lo = (int)e.x; hi = (int)e.y; }
         } else {
@@ -320,6 +340,13 @@ __global__ void __launch_bounds__(128, 12) seed_extend_kernel(const uint8_t* __r
             while (a < b) { int mid = (a + b) >> 1; if (cmp_kmer(R, n, (int)sa[mid], Q + j, k) <= 0) a = mid + 1; else b = mid; }
             hi = a;
         }
+    }
+    // ---- same diagonal as the previous sample (= previous lane): Q[j-step, j-step+k) == R[l-step, l-step+k) by its table entry,
+    // the step-k <= 4 bases in between by the flank signature => the left extension reaches the sample spacing: not the
+    // first seed of its match
+    {
+        const int prev_single = __shfl_up_sync(FULL, single, 1);
+        if (lane > 0 && single >= 0 && prev_single >= 0 && single - prev_single == step && left_flank_eq && step <= k + 4) hi = 0;
     }
     // ---- rounds: every lane takes the next suffix of its bucket; a round ends with the warp's cooperative right extensions
     int sidx = lo;
@@ -360,18 +387,8 @@ __global__ void __launch_bounds__(128, 12) seed_extend_kernel(const uint8_t* __r
             const int qp = __shfl_sync(FULL, j + k, src), rp = __shfl_sync(FULL, l + k, src), lm = __shfl_sync(FULL, lim, src);
             int e = lm;
             for (int base = 0; base < lm; base += 256) {
-                const int off = base + lane * 8;
-                int my = 0;                                // equal leading bytes of this lane's 8 (0 = stop here: past the limit)
-                if (off < lm) {
-                    const uint64_t x = load8u(Q + qp + off) ^ load8u(R + rp + off);
-                    my = x ? ((__ffsll((long long)x) - 1) >> 3) : 8;
-                }
-                const unsigned stop = __ballot_sync(FULL, my < 8);
-                if (stop) {
-                    const int fl = __ffs(stop) - 1;
-                    e = min(lm, base + fl * 8 + __shfl_sync(FULL, my, fl));
-                    break;
-                }
+                const int my = coop_step(Q, R, qp, rp, lm, base, lane);
+                if (coop_resolve(__ballot_sync(FULL, my < 8), my, lm, base, e)) break;
             }
             if (lane == src) ext = e;
         }

@@ -82,8 +82,8 @@ struct ClusterRec {
 // flat pools (shared by the sequential path; thread-local in the chunk-parallel paths)
 struct RegionPool {
     int n = 0;
-    std::vector<int64_t> coord;     // 2n per region: start[n], end[n]
-    std::vector<int64_t> slen;      // TRegion::slength
+    pod_vector<int64_t> coord;      // 2n per region: start[n], end[n] (resize leaves new rows uninitialised: filled by the caller)
+    pod_vector<int64_t> slen;       // TRegion::slength
     int add(const int64_t* start, const int64_t* end);
     inline const int64_t* start(int r) const { return &coord[(size_t)r * 2 * n]; }
     inline const int64_t* end(int r) const { return &coord[(size_t)r * 2 * n + n]; }
@@ -91,8 +91,8 @@ struct RegionPool {
 };
 struct MumPool {
     std::vector<MumRec> mums;
-    std::vector<int64_t> start;
-    std::vector<uint8_t> fwd;
+    pod_vector<int64_t> start;      // (pod_vector: a parallel fill after resize() touches the new pages first)
+    pod_vector<uint8_t> fwd;
 };
 struct AlignStats {
     int64_t anchors = 0, regions_searched = 0, spec_regions = 0, replay_misses = 0, spec_levels = 0,
@@ -172,8 +172,8 @@ private:
     RegionPool rp_;
     MumPool mp_;
     std::vector<MumRec>& mums_ = mp_.mums;
-    std::vector<int64_t>& mum_start_ = mp_.start;
-    std::vector<uint8_t>& mum_fwd_ = mp_.fwd;
+    pod_vector<int64_t>& mum_start_ = mp_.start;
+    pod_vector<uint8_t>& mum_fwd_ = mp_.fwd;
     std::vector<int> all_mums_;       // this->mums in push order (ids into mums_)
     std::vector<int> final_mums_;
     bool final_sorted_ = false;              // final_mums_ is in ascending start[0] order
