@@ -286,10 +286,10 @@ __device__ __forceinline__ bool coop_resolve(unsigned stop, int my, int lm, int 
 // (de-duplication: a match of >= minsize bases contains exactly one sampled seed whose left extension is shorter than the
 // sample spacing).  The right extensions of a warp's surviving seeds are then done by the WHOLE warp, one seed after the other,
 // 32 x 8 bytes per step with a ballot for the first mismatch: the extension of a 100-base match is one step for everybody
-// instead of four divergent 32-byte steps for one lane.  A seed whose
-// left neighbour in the warp hit the same diagonal one sample earlier, and whose 4-base left flank agrees with the reference,
-// lies inside that neighbour's match (sample spacing <= k + 4) and is dropped without touching the reference text.
-// Events are appended with one atomic per warp and round.
+// instead of four divergent 32-byte steps for one lane.  Events are appended with one atomic per warp and round.
+// (Measured and dropped: extending two seeds per iteration - registers cost more occupancy than the overlap gained, +15 %;
+//  dropping seeds that continue the previous lane's diagonal from the flank signature alone - the saved left check is an L1
+//  hit, the shuffle is not free, +4 %; loading lrp[] ahead of the extension - chance hits then pay a DRAM sector, +8 %.)
 __global__ void __launch_bounds__(128, 12) seed_extend_kernel(const uint8_t* __restrict__ R, int n, const uint32_t* __restrict__ sa,
                                                           const int32_t* __restrict__ lrp, const uint2* __restrict__ table,
                                                           int k, int step, int minsize,
@@ -309,7 +309,6 @@ __global__ void __launch_bounds__(128, 12) seed_extend_kernel(const uint8_t* __r
     // ---- the lane's seed: bucket [lo, hi) of the suffix array, or one text position (`single`)
     int lo = 0, hi = 0;
     int single = -1;
-    bool left_flank_eq = false;
     if (valid) {
         // k <= 12 bases = the low 2 bits of 12 consecutive bytes: two 8-byte loads; four bases are gathered by one multiply
         const uint64_t w0 = load8u(Q + j), w1 = load8u(Q + j + 8);
@@ -328,7 +327,6 @@ __global__ void __launch_bounds__(128, 12) seed_extend_kernel(const uint8_t* __r
                     else { ql = side_sig(Q, m, j - 4); qr = side_sig(Q, m, j + k); }
                     const uint32_t rl = (e.y >> 12) & 0xfffu, rr = e.y & 0xfffu;
                     if (ql != rl && qr != rr) hi = 0;
-                    left_flank_eq = ql == rl;
                 }
             } else { lo = (int)e.x; hi = (int)e.y; }
         } else {
@@ -340,13 +338,6 @@ __global__ void __launch_bounds__(128, 12) seed_extend_kernel(const uint8_t* __r
             while (a < b) { int mid = (a + b) >> 1; if (cmp_kmer(R, n, (int)sa[mid], Q + j, k) <= 0) a = mid + 1; else b = mid; }
             hi = a;
         }
-    }
-    // ---- same diagonal as the previous sample (= previous lane): Q[j-step, j-step+k) == R[l-step, l-step+k) by its table entry,
-    // the step-k <= 4 bases in between by the flank signature => the left extension reaches the sample spacing: not the
-    // first seed of its match
-    {
-        const int prev_single = __shfl_up_sync(FULL, single, 1);
-        if (lane > 0 && single >= 0 && prev_single >= 0 && single - prev_single == step && left_flank_eq && step <= k + 4) hi = 0;
     }
     // ---- rounds: every lane takes the next suffix of its bucket; a round ends with the warp's cooperative right extensions
     int sidx = lo;

@@ -5,7 +5,8 @@
 //
 // The queries of a window are processed in GROUPS (as many consecutive queries as fit the shared-memory text buffer), each
 // group in a few block-wide stages so that every stage is a flat, balanced loop over all queries of the group:
-//   1. load both strands of the group's query regions
+//   1. both strands of the group's query regions arrive by TMA bulk copies (cp.async.bulk of the 16-byte-aligned superset of
+//      each region, one issuing thread per query, completion on an mbarrier that doubles as the block barrier of the stage)
 //   2. pack the sampled seed rows: K bases at 3 bits each, every (minsize-K+1)-th query position, both strands.  K is chosen
 //      per window so that consecutive seeds of a diagonal abut or overlap (K >= (minsize+1)/2, 4 <= K <= 10)
 //   3. every (row, strand) looks its seed up in a hash table of the window's K-mers (open addressing in shared memory, built
@@ -42,14 +43,14 @@ constexpr int GROUP_MAX = 64;           // queries per group
 
 struct ClassCfg {
     int n_cap, m_cap, ev_cap, cand_cap, threads;
-    int qbuf;             // bytes of query text per group (both strands); >= 2 * al(m_cap)
+    int qbuf;             // bytes of query text per group (both strands, each with room for its misalignment); >= 2 * al(m_cap + 15)
     int rows_cap;         // seed rows per group (incl. one pad row per query); >= m_cap
     int hq_cap;           // seed-hit queue entries per group
     int stg_cap;          // staged events per group
     __host__ __device__ static size_t al(size_t x) { return (x + 15) & ~(size_t)15; }
     // ev_cap = capacity of the event store for ALL strands of ALL queries of the window
     __host__ __device__ size_t smem_bytes(int nq) const {
-        return al(n_cap) + 3 * al(2 * (size_t)n_cap) + al(4 * (size_t)n_cap) + al(8 * (size_t)n_cap) + al((size_t)qbuf) + al(8 * (size_t)rows_cap) +
+        return al(n_cap + 16) + 3 * al(2 * (size_t)n_cap) + al(4 * (size_t)n_cap) + al(8 * (size_t)n_cap) + al((size_t)qbuf) + al(8 * (size_t)rows_cap) +
                al((size_t)rows_cap) + al(4 * (size_t)hq_cap) +
                al((size_t)stg_cap * sizeof(Ev)) + al((size_t)ev_cap * sizeof(Ev)) + al(2 * (size_t)(nq + 2)) + 2 * al(2 * (size_t)cand_cap) +
                al(2 * 3 * (size_t)(GROUP_MAX + 1)) + al(4 * 2 * (size_t)GROUP_MAX) + 64;
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(SM_MAX_THREADS, 4) small_region_kernel(
     const TaskDev tk = tasks[task_id];
     const int n = tk.n, minsize = tk.minsize;
     size_t off = 0;
-    uint8_t* R = smem + off; off += ClassCfg::al(cfg.n_cap);
+    uint8_t* Rbuf = smem + off; off += ClassCfg::al(cfg.n_cap + 16);       // the window, at its global misalignment
     uint16_t* lrp = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
     uint16_t* MUP = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
     uint16_t* MEP = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
@@ -182,6 +183,8 @@ __global__ void __launch_bounds__(SM_MAX_THREADS, 4) small_region_kernel(
     uint16_t* rowoff = qoff + (GROUP_MAX + 1);                                                                    // [GROUP_MAX+1] first seed row
     uint16_t* qm = rowoff + (GROUP_MAX + 1);                                                                      // [GROUP_MAX] region length
     off += ClassCfg::al(2 * 3 * (size_t)(GROUP_MAX + 1));
+    __shared__ uint64_t s_bar[2];                          // [0]: the window text has arrived  [1]: a group's query texts have arrived
+    __shared__ uint8_t s_mis[2 * GROUP_MAX];               // misalignment (0..15) of every staged strand: the string starts there in its slot
     int* qcnt = reinterpret_cast<int*>(smem + off);                                                               // [GROUP_MAX] staged events per query
     int* qfill = qcnt + GROUP_MAX;
     off += ClassCfg::al(4 * 2 * (size_t)GROUP_MAX);
@@ -198,17 +201,21 @@ __global__ void __launch_bounds__(SM_MAX_THREADS, 4) small_region_kernel(
     int hbits = 1;
     while ((1 << hbits) < 2 * cfg.n_cap) ++hbits;
     const uint32_t hmask = (1u << hbits) - 1u;
-    for (int i = tid; i < n; i += T) { R[i] = text[tk.ref_off + i]; MUP[i] = 0; MEP[i] = (uint16_t)n; lrp[i] = LRP_UNKNOWN; }
+    const uint8_t* R = Rbuf + (int)(tk.ref_off & 15);
+    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], (uint32_t)T); fence_mbar_init(); }
+    for (int i = tid; i < n; i += T) { MUP[i] = 0; MEP[i] = (uint16_t)n; lrp[i] = LRP_UNKNOWN; }
     for (int i = tid; i < (1 << hbits); i += T) tab[i] = SEED_PAD;
     if (tid < 8) s_int[tid] = 0;
     __syncthreads();
-    const int nseed = n >= SEED_K ? n - SEED_K + 1 : 0;            // reference positions holding a seed
-    for (int i = tid; i < nseed; i += T) {
-        const uint32_t code = pack_seed(R + i, SEED_K);
-        R4[i] = code;
-        uint32_t h = seed_hash(code, hbits);
-        while (atomicCAS(&tab[h], SEED_PAD, (uint32_t)i) != SEED_PAD) h = (h + 1) & hmask;
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)ClassCfg::al((size_t)(tk.ref_off & 15) + (size_t)n);
+        fence_proxy_async();
+        mbar_arrive_expect_tx(&s_bar[0], bytes);
+        bulk_g2s(Rbuf, text + (tk.ref_off & ~(int64_t)15), bytes, &s_bar[0]);
     }
+    const int nseed = n >= SEED_K ? n - SEED_K + 1 : 0;            // reference positions holding a seed
+    bool window_ready = false;
+    uint32_t qphase = 0;
 
     int e0 = 0;                                                     // events stored so far (all earlier groups)
     int q0 = 0;
@@ -218,7 +225,7 @@ __global__ void __launch_bounds__(SM_MAX_THREADS, 4) small_region_kernel(
             int bytes = 0, rows = 0, g = 0;
             while (q0 + g < nq && g < GROUP_MAX) {
                 const int m = ql[q0 + g];
-                const int nb = 2 * (int)ClassCfg::al((size_t)m);
+                const int nb = 2 * (int)ClassCfg::al((size_t)m + 15);
                 const int nr = 1 + (m >= SEED_K ? (m - SEED_K) / step + 1 : 0);           // one pad row in front of every query
                 if (g > 0 && (bytes + nb > cfg.qbuf || rows + nr > cfg.rows_cap)) break;
                 qoff[g] = (uint16_t)bytes; rowoff[g] = (uint16_t)(rows + 1); qm[g] = (uint16_t)m;
@@ -232,24 +239,44 @@ __global__ void __launch_bounds__(SM_MAX_THREADS, 4) small_region_kernel(
         __syncthreads();
         const int G = s_int[6];
         if (s_int[3]) break;
-        // ---- 1. both strands of every query region of the group
-        for (int g = 0; g < G; ++g) {
+        // ---- 1. both strands of every query region of the group: thread g issues the two bulk copies of query g
+        if (tid < G) {
+            const int g = tid;
             const int m = qm[g];
             const int64_t gi = q0 + g + 1;
             const int64_t f_off = gbase_fwd[gi] + qs[q0 + g];
             const int64_t c_off = gbase_rc[gi] + (glen[gi] - qs[q0 + g] - m);
-            uint8_t* Qf = QB + qoff[g];
-            uint8_t* Qc = Qf + ClassCfg::al((size_t)m);
-            for (int i = tid; i < m; i += T) { Qf[i] = text[f_off + i]; Qc[i] = text[c_off + i]; }
+            const uint32_t mf = (uint32_t)(f_off & 15), mc = (uint32_t)(c_off & 15);
+            const uint32_t bf = m ? (uint32_t)ClassCfg::al(mf + (size_t)m) : 0u, bc = m ? (uint32_t)ClassCfg::al(mc + (size_t)m) : 0u;
+            s_mis[2 * g] = (uint8_t)mf; s_mis[2 * g + 1] = (uint8_t)mc;
+            uint8_t* slot = QB + qoff[g];
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&s_bar[1], bf + bc);
+            if (bf) bulk_g2s(slot, text + (f_off & ~(int64_t)15), bf, &s_bar[1]);
+            if (bc) bulk_g2s(slot + ClassCfg::al((size_t)m + 15), text + (c_off & ~(int64_t)15), bc, &s_bar[1]);
+        } else {
+            mbar_arrive(&s_bar[1]);
         }
-        __syncthreads();
+        if (!window_ready) {
+            // the window's seed codes and their hash table (the group's copies are in flight meanwhile)
+            mbar_wait(&s_bar[0], 0);
+            for (int i = tid; i < nseed; i += T) {
+                const uint32_t code = pack_seed(R + i, SEED_K);
+                R4[i] = code;
+                uint32_t h = seed_hash(code, hbits);
+                while (atomicCAS(&tab[h], SEED_PAD, (uint32_t)i) != SEED_PAD) h = (h + 1) & hmask;
+            }
+            window_ready = true;
+        }
+        mbar_wait(&s_bar[1], qphase);
+        qphase ^= 1u;
         // ---- 2. seed rows (row r0-1 of every query is a pad row: "no predecessor on the diagonal")
         const int total_rows = rowoff[G] - 1;
         for (int g = 0; g < G; ++g) {
             const int m = qm[g];
             const int r0 = rowoff[g], nr = rowoff[g + 1] - 1 - r0;
-            const uint8_t* Qf = QB + qoff[g];
-            const uint8_t* Qc = Qf + ClassCfg::al((size_t)m);
+            const uint8_t* Qf = QB + qoff[g] + s_mis[2 * g];
+            const uint8_t* Qc = QB + qoff[g] + ClassCfg::al((size_t)m + 15) + s_mis[2 * g + 1];
             for (int row = tid; row < nr; row += T) {
                 Q4[2 * (r0 + row)] = pack_seed(Qf + row * step, SEED_K);
                 Q4[2 * (r0 + row) + 1] = pack_seed(Qc + row * step, SEED_K);
@@ -285,7 +312,7 @@ __global__ void __launch_bounds__(SM_MAX_THREADS, 4) small_region_kernel(
             const int g = rowq[row];
             const int m = qm[g];
             const int j = (row - rowoff[g]) * step;
-            const uint8_t* Q = QB + qoff[g] + (strand ? ClassCfg::al((size_t)m) : 0);
+            const uint8_t* Q = QB + qoff[g] + (strand ? ClassCfg::al((size_t)m + 15) : 0) + s_mis[2 * g + strand];
             const int cmax = min(step, min(j, l));
             const int c = smatch_bwd(Q + j, R + l, cmax);
             if (c >= step) continue;                      // the previous seed row lies in the same match
@@ -339,6 +366,7 @@ __global__ void __launch_bounds__(SM_MAX_THREADS, 4) small_region_kernel(
         q0 += G;
         __syncthreads();
     }
+    if (!window_ready) mbar_wait(&s_bar[0], 0);        // (no query, or an early exit: never leave with the window copy in flight)
     __syncthreads();
     // A5: ordered emission by warp 0
     if (!s_int[3] && tid < 32) {
