@@ -70,7 +70,7 @@ public:
         force_3bit_ = fk && fk[0] == '1';
         // {n_cap (power of two), m_cap, event store capacity (all strands), candidate capacity, threads,
         //  group text bytes (>= 2 al(m_cap + 15)), group seed rows (>= m_cap), seed-hit queue, staged events}
-        classes_[0] = small::ClassCfg{256, 512, 512, 64, 128, 4096, 768, 512, 192};
+        classes_[0] = small::ClassCfg{256, 512, 512, 64, 128, 3584, 640, 512, 192};
         classes_[1] = small::ClassCfg{1024, 2048, 1536, 256, 256, 8192, 2048, 1024, 384};
         classes_[2] = small::ClassCfg{4096, 4096, 3072, 512, 256, 8448, 4096, 2048, 1024};
         PB_CUDA(cudaFuncSetAttribute(small::small_region_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
