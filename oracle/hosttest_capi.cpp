@@ -50,6 +50,7 @@ int pbtest_align_sharded(int rank, int world, pb200_allgather_cb ag, pb200_allre
         pb200::ShardedBackend sb(local.get(), pb200_oracle::as_staged(local.get()), &comm, true);
         pb200::Aligner a(n, seqs, lens, pb200::to_align_params(prm), &sb);
         a.set_threads(pb200::default_host_threads());
+        a.set_pipeline(false);            // collectives inside the search: same call order on every rank
         bool ok = a.run();
         *out = pb200::make_result(a);
         if (counters) { counters[0] = sb.staged_windows; counters[1] = sb.sharded_small_windows; }

@@ -601,6 +601,7 @@ int pb200_align_resident(pb200_genomes* g, const pb200_params* prm, pb200_result
             a.enable_trace(prm->flags & PB200_FLAG_TRACE_WINDOWS);
             a.set_speculate(!(prm->flags & PB200_FLAG_NO_SPECULATION));
             a.set_threads(pb200::default_host_threads());
+            a.set_pipeline(!sharded);           // collectives inside the search: every rank must issue them in the same order
             tp[1] = pb200::wall_s();
             ok = a.run();
             tp[2] = pb200::wall_s();

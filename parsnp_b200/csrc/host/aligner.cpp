@@ -177,14 +177,15 @@ void Aligner::CoordIndex::reserve(size_t entries) {
     count = 0;
     for (size_t i = 0; i < oh.size(); ++i) if (ov[i] >= 0) insert(oh[i], ov[i]);
 }
-int Aligner::cache_lookup_coords(const int64_t* coords) const {
-    const size_t bytes = sizeof(int64_t) * 2 * n_;
-    return cache_map_.find(coords_hash(coords, 2 * n_),
-                           [&](int e) { return std::memcmp(rstart(cache_entries_[e].region), coords, bytes) == 0; });
+int Aligner::CandCache::lookup(const int64_t* coords) const {
+    const int n = rp.n;
+    const size_t bytes = sizeof(int64_t) * 2 * n;
+    return map.find(Aligner::coords_hash(coords, 2 * n),
+                    [&](int e) { return std::memcmp(rp.start(entries[e].region), coords, bytes) == 0; });
 }
 
-int Aligner::minsize_cached(bool anchors, int64_t slength) {
-    std::unordered_map<int64_t, int>& c = minsize_cache_[anchors ? 1 : 0];
+int Aligner::minsize_cached(CandCache& C, bool anchors, int64_t slength) {
+    std::unordered_map<int64_t, int>& c = C.minsize[anchors ? 1 : 0];
     auto it = c.find(slength);
     if (it != c.end()) return it->second;
     int v = anchors ? anchor_expr_(slength) : mum_expr_(slength);
@@ -193,8 +194,9 @@ int Aligner::minsize_cached(bool anchors, int64_t slength) {
 }
 
 // ------------------------------------------------------------------ batched search (setMums1 up to the emission loop)
-void Aligner::search_regions(const std::vector<int>& regs, bool anchors) {
+void Aligner::search_regions(CandCache& C, const RegionPool& src, const std::vector<int>& regs, bool anchors) {
     if (regs.empty()) return;
+    C.rp.n = n_;
     const double tp0 = now_s();
     std::vector<WindowTask> tasks;
     std::vector<int64_t> coords;
@@ -204,10 +206,10 @@ void Aligner::search_regions(const std::vector<int>& regs, bool anchors) {
     coords.reserve(regs.size() * 2 * (size_t)nq);
     for (size_t ri = 0; ri < regs.size(); ++ri) {
         const int r = regs[ri];
-        const int64_t* rs = rstart(r);
-        const int64_t* re = rend(r);
+        const int64_t* rs = src.start(r);
+        const int64_t* re = src.end(r);
         first_task[ri] = (int)tasks.size();
-        const int minsize = minsize_cached(anchors, rp_.slen[r]);
+        const int minsize = minsize_cached(C, anchors, src.slen[r]);
         const int64_t coff = (int64_t)coords.size();
         for (int j = 1; j < n_; ++j) coords.push_back(rs[j]);
         for (int j = 1; j < n_; ++j) coords.push_back(re[j] - rs[j]);
@@ -234,11 +236,13 @@ void Aligner::search_regions(const std::vector<int>& regs, bool anchors) {
     }
     first_task[regs.size()] = (int)tasks.size();
     const double tp1 = now_s();
-    chunks_.emplace_back();
-    CandBatch& cb = chunks_.back();
+    C.chunks.emplace_back();
+    CandBatch& cb = C.chunks.back();
     cb.nq = nq;
-    if (!tasks.empty()) be_->search(tasks.data(), (int)tasks.size(), coords.data(), cb);
-    else cb.off.assign(1, 0);
+    if (!tasks.empty()) {
+        std::lock_guard<std::mutex> lk(backend_mu_);       // one search at a time: the engine owns one stream and one set of buffers
+        be_->search(tasks.data(), (int)tasks.size(), coords.data(), cb);
+    } else cb.off.assign(1, 0);
     if (!cb.cnt.empty()) {
         // the engine delivers the windows' candidate blocks in kernel completion order; gather them into window order so that
         // the accept passes (ascending reference order) stream through memory
@@ -266,17 +270,14 @@ void Aligner::search_regions(const std::vector<int>& regs, bool anchors) {
         cb.cnt.clear();
     }
     const double tp2 = now_s();
-    stats_.windows_searched += (int64_t)tasks.size();
-    stats_.regions_searched += (int64_t)regs.size();
-    stats_.candidates += (int64_t)cb.k.size();
-    const int32_t chunk = (int32_t)chunks_.size() - 1;
-    cache_entries_.reserve(cache_entries_.size() + regs.size());
-    cache_map_.reserve(regs.size());
-    wins_.reserve(wins_.size() + tasks.size());
+    const int32_t chunk = (int32_t)C.chunks.size() - 1;
+    C.entries.reserve(C.entries.size() + regs.size());
+    C.map.reserve(regs.size());
+    C.wins.reserve(C.wins.size() + tasks.size());
     for (size_t ri = 0; ri < regs.size(); ++ri) {
         CacheEntry e;
-        e.region = regs[ri];
-        e.first_win = (int64_t)wins_.size();
+        e.region = C.rp.add(src.start(regs[ri]), src.end(regs[ri]));
+        e.first_win = (int64_t)C.wins.size();
         e.nwin = first_task[ri + 1] - first_task[ri];
         for (int t = first_task[ri]; t < first_task[ri + 1]; ++t) {
             WinRec w;
@@ -285,21 +286,27 @@ void Aligner::search_regions(const std::vector<int>& regs, bool anchors) {
             w.cand_off = cb.off[t];
             w.ncand = cb.count(t);
             w.chunk = chunk;
-            wins_.push_back(w);
+            C.wins.push_back(w);
         }
-        cache_map_.insert(coords_hash(rstart(regs[ri]), 2 * n_), (int)cache_entries_.size());
-        cache_entries_.push_back(e);
+        C.map.insert(coords_hash(src.start(regs[ri]), 2 * n_), (int)C.entries.size());
+        C.entries.push_back(e);
     }
     const double tp3 = now_s();
-    stats_.t_search_prep += tp1 - tp0;
-    stats_.t_search_backend += tp2 - tp1;
-    stats_.t_search_cache += tp3 - tp2;
+    {
+        std::lock_guard<std::mutex> lk(backend_mu_);       // (the statistics are shared between the two producer threads)
+        stats_.windows_searched += (int64_t)tasks.size();
+        stats_.regions_searched += (int64_t)regs.size();
+        stats_.candidates += (int64_t)cb.k.size();
+        stats_.t_search_prep += tp1 - tp0;
+        stats_.t_search_backend += tp2 - tp1;
+        stats_.t_search_cache += tp3 - tp2;
+    }
 }
 
 // ------------------------------------------------------------------ setMums1 loop D (src/parsnp.cpp:1713-1842)
-void Aligner::accept_candidates(const int64_t* rs, const int64_t* re, int64_t rsl, int cache_idx, std::vector<BitRow>& layout, MumPool& mp,
-                                std::vector<int>& found, bool atomic, bool trace) {
-    const CacheEntry& ce = cache_entries_[cache_idx];
+void Aligner::accept_candidates(const int64_t* rs, const int64_t* re, int64_t rsl, const CandCache& C, int cache_idx,
+                                std::vector<BitRow>& layout, MumPool& mp, std::vector<int>& found, bool atomic, bool trace) {
+    const CacheEntry& ce = C.entries[cache_idx];
     const int nq = n_ - 1;
     int64_t st_buf[64];
     uint8_t fw_buf[64];
@@ -309,8 +316,8 @@ void Aligner::accept_candidates(const int64_t* rs, const int64_t* re, int64_t rs
     uint8_t* fw = fw_buf;
     if (n_ > 64) { st_vec.resize(n_); fw_vec.resize(n_); st = st_vec.data(); fw = fw_vec.data(); }
     for (int wi = 0; wi < ce.nwin; ++wi) {
-        const WinRec& win = wins_[ce.first_win + wi];
-        const CandBatch& cb = chunks_[win.chunk];
+        const WinRec& win = C.wins[ce.first_win + wi];
+        const CandBatch& cb = C.chunks[win.chunk];
         if (trace) trace_.emplace_back(win.ref_start, win.ref_len);
         for (int32_t c = 0; c < win.ncand; ++c) {
             const int64_t ci = win.cand_off + c;
@@ -382,14 +389,14 @@ void Aligner::accept_candidates(const int64_t* rs, const int64_t* re, int64_t rs
 // candidate's interval in any genome are untouched by the trim loop whatever the order (the only bits in their intervals
 // would be their own), so they are validated and placed in parallel; the overlapping ones (few) go through the literal
 // sequential loop above, in candidate order, among themselves.  Result identical to accept_candidates().
-void Aligner::accept_candidates_parallel(const int64_t* rs, const int64_t* re, int64_t rsl, int cache_idx, std::vector<BitRow>& layout,
-                                         MumPool& mp, std::vector<int>& found, bool trace) {
-    const CacheEntry& ce = cache_entries_[cache_idx];
+void Aligner::accept_candidates_parallel(const int64_t* rs, const int64_t* re, int64_t rsl, const CandCache& CC, int cache_idx,
+                                         std::vector<BitRow>& layout, MumPool& mp, std::vector<int>& found, bool trace) {
+    const CacheEntry& ce = CC.entries[cache_idx];
     const int nq = n_ - 1;
     const size_t N = (size_t)n_;
     std::vector<int64_t> wbase((size_t)ce.nwin + 1, 0);
     for (int wi = 0; wi < ce.nwin; ++wi) {
-        const WinRec& win = wins_[ce.first_win + wi];
+        const WinRec& win = CC.wins[ce.first_win + wi];
         wbase[wi + 1] = wbase[wi] + win.ncand;
         if (trace) trace_.emplace_back(win.ref_start, win.ref_len);
     }
@@ -405,8 +412,8 @@ void Aligner::accept_candidates_parallel(const int64_t* rs, const int64_t* re, i
         int wi = (int)(std::upper_bound(wbase.begin(), wbase.end(), (int64_t)c0) - wbase.begin()) - 1;
         for (size_t c = c0; c < c1; ++c) {
             while ((int64_t)c >= wbase[wi + 1]) ++wi;
-            const WinRec& win = wins_[ce.first_win + wi];
-            const CandBatch& cb = chunks_[win.chunk];
+            const WinRec& win = CC.wins[ce.first_win + wi];
+            const CandBatch& cb = CC.chunks[win.chunk];
             const int64_t ci = win.cand_off + ((int64_t)c - wbase[wi]);
             const int64_t lon = cb.lon[ci];
             int64_t* st = &ST[c * N];
@@ -579,7 +586,7 @@ void Aligner::set_initial_clusters() {
     double t0 = now_s();
     std::vector<int64_t> S(n_, 0), E(len_);
     int whole = rp_.add(S.data(), E.data());
-    search_regions(std::vector<int>(1, whole), true);
+    search_regions(main_cache_, rp_, std::vector<int>(1, whole), true);
     double t1 = now_s();
     stats_.t_anchor_search = t1 - t0;
     std::vector<int> found;
@@ -592,9 +599,11 @@ void Aligner::set_initial_clusters() {
     }
     const char* pmin = getenv("PB200_PAR_ANCHORS_MIN");          // tests: 1 forces the parallel accept, a huge value the serial one
     if (threads_ > 1 && stats_.candidates >= (pmin ? atoll(pmin) : 8192))
-        accept_candidates_parallel(rstart(whole), rend(whole), rp_.slen[whole], cache_lookup(whole), truth_.layout, mp_, found, trace_on_);
+        accept_candidates_parallel(rstart(whole), rend(whole), rp_.slen[whole], main_cache_, main_cache_.lookup(rstart(whole)), truth_.layout, mp_,
+                                   found, trace_on_);
     else
-        accept_candidates(rstart(whole), rend(whole), rp_.slen[whole], cache_lookup(whole), truth_.layout, mp_, found, false, trace_on_);
+        accept_candidates(rstart(whole), rend(whole), rp_.slen[whole], main_cache_, main_cache_.lookup(rstart(whole)), truth_.layout, mp_, found,
+                          false, trace_on_);
     all_mums_ = found;
     stats_.anchors = (int64_t)found.size();
     const double ta1 = now_s();
@@ -671,19 +680,20 @@ void Aligner::set_initial_clusters() {
 // ------------------------------------------------------------------ speculative level-synchronous discovery
 // One level over frontier[a,b) (sorted by start[0]): accept on the scratch layout, collect the children's coordinates.
 // Only a predictor of which regions the exact replay will ask for - races between threads merely cost cache misses.
-void Aligner::speculate_range(const std::vector<int>& frontier, size_t a, size_t b, std::vector<BitRow>& layout, MumPool& mp, RegionPool& out,
-                              bool atomic) {
+void Aligner::speculate_range(const CandCache& C, const RegionPool& F, const std::vector<int>& frontier, size_t a, size_t b,
+                              std::vector<BitRow>& layout, MumPool& mp, RegionPool& out, bool atomic) {
     std::vector<int> found;
     std::vector<int64_t> lS(n_), lE(n_), rS(n_), rE(n_);
+    const size_t cbytes = sizeof(int64_t) * 2 * n_;
     int prev = -1;
     for (size_t x = a; x < b; ++x) {
         const int r = frontier[x];
-        if (prev >= 0 && region_equal(prev, r)) continue;
+        if (prev >= 0 && std::memcmp(F.start(prev), F.start(r), cbytes) == 0) continue;
         prev = r;
         found.clear();
-        const int ci = cache_lookup(r);
+        const int ci = C.lookup(F.start(r));
         if (ci < 0) continue;
-        accept_candidates(rstart(r), rend(r), rp_.slen[r], ci, layout, mp, found, atomic, false);
+        accept_candidates(F.start(r), F.end(r), F.slen[r], C, ci, layout, mp, found, atomic, false);
         int64_t lsl = 0;
         for (size_t i = 0; i < found.size(); ++i) {
             const MumRec& m = mp.mums[found[i]];
@@ -700,9 +710,13 @@ void Aligner::speculate_range(const std::vector<int>& frontier, size_t a, size_t
     }
 }
 
-void Aligner::speculate(const std::vector<int>& initial, const World& truth) {
-    World spec = truth;                                    // scratch copy of mumlayout
-    std::vector<int> frontier = initial, need;
+void Aligner::speculate_slice(CandCache& C, const RegionPool& src, const std::vector<int>& initial, World& spec) {
+    RegionPool F;                                          // the slice's frontier regions, level after level
+    F.n = n_;
+    std::vector<int> frontier, need;
+    frontier.reserve(initial.size());
+    for (int r : initial) frontier.push_back(F.add(src.start(r), src.end(r)));
+    const size_t cbytes = sizeof(int64_t) * 2 * n_;
     while (!frontier.empty()) {
         double t0 = now_s();
         need.clear();
@@ -710,19 +724,19 @@ void Aligner::speculate(const std::vector<int>& initial, const World& truth) {
             CoordIndex seen;
             seen.reserve(frontier.size());
             for (int r : frontier) {
-                if (cache_lookup(r) >= 0) continue;
-                const uint64_t h = coords_hash(rstart(r), 2 * n_);
-                if (seen.find(h, [&](int o) { return region_equal(o, r); }) >= 0) continue;
+                if (C.lookup(F.start(r)) >= 0) continue;
+                const uint64_t h = coords_hash(F.start(r), 2 * n_);
+                if (seen.find(h, [&](int o) { return std::memcmp(F.start(o), F.start(r), cbytes) == 0; }) >= 0) continue;
                 seen.insert(h, r);
                 need.push_back(r);
             }
         }
-        search_regions(need, false);
+        search_regions(C, F, need, false);
         stats_.spec_regions += (int64_t)need.size();
         stats_.spec_levels++;
         double t1 = now_s();
         stats_.t_spec_search += t1 - t0;
-        std::stable_sort(frontier.begin(), frontier.end(), [&](int a, int b) { return rstart(a)[0] < rstart(b)[0]; });
+        std::stable_sort(frontier.begin(), frontier.end(), [&](int a, int b) { return F.start(a)[0] < F.start(b)[0]; });
         // chunks of the frontier are processed concurrently on the shared scratch layout
         const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads_, frontier.size() / 256 + 1));
         const size_t nchunks = T > 1 ? (size_t)T * 4 : 1;
@@ -731,19 +745,49 @@ void Aligner::speculate(const std::vector<int>& initial, const World& truth) {
         parallel_chunks(T, (long)nchunks, [&](long c) {
             MumPool mp;
             const size_t a = frontier.size() * (size_t)c / nchunks, b = frontier.size() * (size_t)(c + 1) / nchunks;
-            speculate_range(frontier, a, b, spec.layout, mp, outs[c], T > 1);
+            speculate_range(C, F, frontier, a, b, spec.layout, mp, outs[c], T > 1);
         });
         std::vector<int> next;
         for (auto& o : outs)
-            for (int i = 0; i < o.size(); ++i) next.push_back(rp_.add(o.start(i), o.end(i)));
+            for (int i = 0; i < o.size(); ++i) next.push_back(F.add(o.start(i), o.end(i)));
         frontier.swap(next);
         stats_.t_spec_host += now_s() - t1;
     }
 }
 
+// the speculation thread: slice after slice, each published as soon as it is complete
+void Aligner::speculation_thread_main() {
+    try {
+        for (size_t k = 0; k < slice_cache_.size(); ++k) {
+            speculate_slice(*slice_cache_[k], frozen_rp_, slice_regions_[k], spec_world_);
+            {
+                std::lock_guard<std::mutex> lk(slice_mu_);
+                slices_ready_ = (int)k + 1;
+            }
+            slice_cv_.notify_all();
+        }
+    } catch (...) {
+        std::lock_guard<std::mutex> lk(slice_mu_);
+        spec_error_ = std::current_exception();
+        slices_ready_ = (int)slice_cache_.size();          // nobody waits for ever; the replay searches on demand and run() rethrows
+        slice_cv_.notify_all();
+    }
+}
+
+const Aligner::CandCache* Aligner::wait_slice(int slice) {
+    if (slice < 0 || slice >= (int)slice_cache_.size()) return nullptr;
+    std::unique_lock<std::mutex> lk(slice_mu_);
+    if (slices_ready_ <= slice) {
+        const double t0 = now_s();
+        slice_cv_.wait(lk, [&] { return slices_ready_ > slice; });
+        stats_.t_replay_wait += now_s() - t0;
+    }
+    return slice_cache_[slice].get();
+}
+
 // ------------------------------------------------------------------ doWork (src/parsnp.cpp:173-317), exact order
 namespace {
-struct QE { int64_t s0; int id; };
+struct QE { int64_t s0; int id; int slice; };      // slice: the speculation slice the region descends from
 inline bool operator<(const QE& a, const QE& b) { return a.s0 < b.s0; }   // operator<, src/LCR.cpp:42
 }
 
@@ -753,7 +797,9 @@ void Aligner::process_queue_exact(const std::vector<int>& initial, RegionPool& r
     // all start[0] keys are distinct (then every correct sort yields the same sequence).
     auto req = [&](int a, int b) { return std::memcmp(rp.start(a), rp.start(b), sizeof(int64_t) * 2 * n_) == 0; };
     std::vector<QE> vec;
-    for (int r : initial) vec.push_back(QE{rp.start(r)[0], r});
+    for (size_t i = 0; i < initial.size(); ++i)
+        vec.push_back(QE{rp.start(initial[i])[0], initial[i], i < slice_of_initial_.size() ? slice_of_initial_[i] : -1});
+    int ready_upto = 0;                       // speculation slices [0, ready_upto) are known to be published
     // fast mode: the queue as a vector sorted by DESCENDING start[0] (front of the reference's vector = back of this one).
     // Children of the region just taken lie inside it, i.e. next to the back, so insertion is a short walk + a short move.
     std::vector<QE> fast;
@@ -780,21 +826,28 @@ void Aligner::process_queue_exact(const std::vector<int>& initial, RegionPool& r
 #define PROF_MARK(i) do { if (prof) { uint64_t x_ = __builtin_ia32_rdtsc(); pc[i] += x_ - pt; pt = x_; } } while (0)
     if (prof) pt = __builtin_ia32_rdtsc();
     while (fast_mode ? !fast.empty() : !vec.empty()) {
-        int cur;
-        if (fast_mode) { cur = fast.back().id; fast.pop_back(); }
-        else { cur = vec.front().id; vec.erase(vec.begin()); }
+        int cur, cur_slice;
+        if (fast_mode) { cur = fast.back().id; cur_slice = fast.back().slice; fast.pop_back(); }
+        else { cur = vec.front().id; cur_slice = vec.front().slice; vec.erase(vec.begin()); }
         PROF_MARK(0);
-        int ci = cache_lookup_coords(rp.start(cur));
+        // candidates: the slice's speculation (wait for it if it is still in flight), else the main cache, else search now
+        const CandCache* C = nullptr;
+        if (cur_slice >= 0 && cur_slice < (int)slice_cache_.size()) {
+            if (cur_slice >= ready_upto) { wait_slice(cur_slice); ready_upto = cur_slice + 1; }
+            C = slice_cache_[cur_slice].get();
+        }
+        int ci = C ? C->lookup(rp.start(cur)) : -1;
+        if (ci < 0) { C = &main_cache_; ci = main_cache_.lookup(rp.start(cur)); }
         PROF_MARK(1);
         if (ci < 0) {
             double ts = now_s();
-            search_regions(std::vector<int>(1, cur), false);          // a region the speculation did not predict
+            search_regions(main_cache_, rp, std::vector<int>(1, cur), false);          // a region the speculation did not predict
             stats_.t_replay_search += now_s() - ts;
             stats_.replay_misses++;
-            ci = cache_lookup_coords(rp.start(cur));
+            ci = main_cache_.lookup(rp.start(cur));
         }
         found.clear();
-        accept_candidates(rp.start(cur), rp.end(cur), rp.slen[cur], ci, layout, mp, found, false, trace_on_);
+        accept_candidates(rp.start(cur), rp.end(cur), rp.slen[cur], *C, ci, layout, mp, found, false, trace_on_);
         PROF_MARK(2);
         children.clear();
         int64_t lsl = 0;
@@ -827,7 +880,7 @@ void Aligner::process_queue_exact(const std::vector<int>& initial, RegionPool& r
                     const int64_t key = rp.start(ch)[0];
                     const size_t pos = fast_pos(key);
                     if (pos < fast.size() && fast[pos].s0 == key) continue;
-                    fast.insert(fast.begin() + (long)pos, QE{key, ch});
+                    fast.insert(fast.begin() + (long)pos, QE{key, ch, cur_slice});
                 }
                 PROF_MARK(4);
                 continue;
@@ -837,7 +890,7 @@ void Aligner::process_queue_exact(const std::vector<int>& initial, RegionPool& r
             fast_mode = false;
         }
         stats_.slow_queue_iters++;
-        for (int ch : children) vec.push_back(QE{rp.start(ch)[0], ch});
+        for (int ch : children) vec.push_back(QE{rp.start(ch)[0], ch, cur_slice});
         if (!vec.empty()) {
             // The queue is nearly sorted (anchor order, then children next to their parent).  With distinct start[0] keys every
             // correct sort gives the same sequence, so try a bounded insertion sort on a copy; ties (or too much disorder) fall
@@ -1187,9 +1240,37 @@ bool Aligner::run() {
     double t0 = now_s();
     set_initial_clusters();
     if (!prm_.anchors_only) {
-        if (speculate_) speculate(initial_regions_, truth_);
         stats_.host_threads = threads_;
-        do_work_exact();
+        if (speculate_ && !initial_regions_.empty()) {
+            // slices of the initial regions (reference order): the speculation thread discovers and searches slice k+1 while the
+            // replay below consumes slice k
+            const char* es = getenv("PB200_SPEC_SLICES");
+            size_t K = es ? (size_t)std::max(1, atoi(es)) : std::min<size_t>(8, initial_regions_.size() / 4096 + 1);
+            K = std::min(K, initial_regions_.size());
+            stats_.spec_slices = (int64_t)K;
+            frozen_rp_ = rp_;                              // (the replay appends to rp_ while the speculation reads the initial regions)
+            spec_world_ = truth_;                          // scratch copy of mumlayout
+            slice_regions_.assign(K, std::vector<int>());
+            slice_of_initial_.resize(initial_regions_.size());
+            for (size_t i = 0; i < initial_regions_.size(); ++i) {
+                const size_t k = i * K / initial_regions_.size();
+                slice_regions_[k].push_back(initial_regions_[i]);
+                slice_of_initial_[i] = (int)k;
+            }
+            slice_cache_.clear();
+            for (size_t k = 0; k < K; ++k) slice_cache_.emplace_back(new CandCache);
+            slices_ready_ = 0;
+            if (pipeline_) spec_thread_ = std::thread([this] { speculation_thread_main(); });
+            else speculation_thread_main();
+        }
+        try {
+            do_work_exact();
+        } catch (...) {
+            if (spec_thread_.joinable()) spec_thread_.join();
+            throw;
+        }
+        if (spec_thread_.joinable()) spec_thread_.join();
+        if (spec_error_) std::rethrow_exception(spec_error_);
     }
     if (all_mums_.empty()) { stats_.t_total = now_s() - t0; return false; }
     double t1 = now_s();

@@ -20,6 +20,10 @@
 #include <vector>
 #include <unordered_map>
 #include <map>
+#include <memory>
+#include <mutex>
+#include <condition_variable>
+#include <thread>
 #include "../common.h"
 #include "minsize.h"
 
@@ -100,6 +104,8 @@ struct AlignStats {
     double t_anchor_search = 0, t_anchor_host = 0, t_spec_search = 0, t_spec_host = 0, t_replay = 0,
            t_replay_search = 0, t_lcb = 0, t_total = 0;
     double t_search_prep = 0, t_search_backend = 0, t_search_cache = 0;   // split of the search_regions calls (all phases)
+    double t_replay_wait = 0;        // replay blocked on a speculation slice still in flight
+    int64_t spec_slices = 0;
 };
 
 class Aligner {
@@ -122,6 +128,9 @@ public:
     void enable_trace(bool on) { trace_on_ = on; }
     void set_speculate(bool on) { speculate_ = on; }
     void set_threads(int t) { threads_ = t < 1 ? 1 : t; }
+    // speculation slices run on their own thread while the replay consumes the finished ones (off: a backend whose search
+    // involves collectives must see the same call sequence on every rank)
+    void set_pipeline(bool on) { pipeline_ = on; }
 
 private:
     inline const int64_t* rstart(int r) const { return rp_.start(r); }
@@ -133,31 +142,61 @@ private:
         std::vector<BitRow> layout;
     };
 
-    // search + cache (the cache is read-only while threads run)
+    // ---- candidate cache: the candidates of searched regions, keyed by the regions' coordinates.  One instance per producer
+    // (anchors and on-demand searches: the main thread; every speculation slice: the speculation thread); a published
+    // instance is read-only.
     struct CacheEntry { int region; int64_t first_win; int nwin; };
-    int cache_lookup(int r) const { return cache_lookup_coords(rstart(r)); }
-    int cache_lookup_coords(const int64_t* coords) const;    // -> index into cache_entries_ or -1
-    void search_regions(const std::vector<int>& regs, bool anchors);   // batched GPU search, fills the cache
+    struct WinRec { int64_t ref_start, ref_len; int64_t cand_off; int32_t ncand; int32_t chunk; };
+    // open-addressing index hash(coords) -> cache entry
+    struct CoordIndex {
+        std::vector<uint64_t> h;
+        std::vector<int> v;
+        size_t count = 0;
+        void insert(uint64_t hash, int value);
+        void reserve(size_t entries);          // room for `entries` more without rehashing
+        template <class Pred> int find(uint64_t hash, Pred pred) const {
+            if (h.empty()) return -1;
+            const size_t mask = h.size() - 1;
+            for (size_t i = (size_t)hash & mask;; i = (i + 1) & mask) {
+                if (v[i] < 0) return -1;
+                if (h[i] == hash && pred(v[i])) return v[i];
+            }
+        }
+    };
+    struct CandCache {
+        RegionPool rp;                         // own copies of the searched regions' coordinates (the keys)
+        std::vector<CacheEntry> entries;       // .region indexes rp
+        CoordIndex map;
+        std::vector<WinRec> wins;
+        std::vector<CandBatch> chunks;         // one per search call; candidates stay where the backend delivered them
+        std::unordered_map<int64_t, int> minsize[2];
+        int lookup(const int64_t* coords) const;    // -> index into entries or -1
+    };
+    int minsize_cached(CandCache& C, bool anchors, int64_t slength);
+    // batched GPU search of regions `regs` of pool `src`, fills C
+    void search_regions(CandCache& C, const RegionPool& src, const std::vector<int>& regs, bool anchors);
 
     // setMums1 loop D on cached candidates; appends accepted MUMs to `mp`, their indices to `found`
-    void accept_candidates(const int64_t* rs, const int64_t* re, int64_t rsl, int cache_idx, std::vector<BitRow>& layout, MumPool& mp,
-                           std::vector<int>& found, bool atomic, bool trace);
+    void accept_candidates(const int64_t* rs, const int64_t* re, int64_t rsl, const CandCache& C, int cache_idx, std::vector<BitRow>& layout,
+                           MumPool& mp, std::vector<int>& found, bool atomic, bool trace);
     // the same for a long candidate list on an empty layout (anchors): non-overlapping candidates in parallel
-    void accept_candidates_parallel(const int64_t* rs, const int64_t* re, int64_t rsl, int cache_idx, std::vector<BitRow>& layout, MumPool& mp,
-                                    std::vector<int>& found, bool trace);
+    void accept_candidates_parallel(const int64_t* rs, const int64_t* re, int64_t rsl, const CandCache& C, int cache_idx,
+                                    std::vector<BitRow>& layout, MumPool& mp, std::vector<int>& found, bool trace);
     // doWork's loop over a queue of regions living in `rp`, in the exact reference order
     void process_queue_exact(const std::vector<int>& initial, RegionPool& rp, std::vector<BitRow>& layout, MumPool& mp,
                              std::vector<int>& out_mums);
     // one speculative level over frontier[a,b): children coordinates appended to `out`
-    void speculate_range(const std::vector<int>& frontier, size_t a, size_t b, std::vector<BitRow>& layout, MumPool& mp, RegionPool& out,
-                         bool atomic);
+    void speculate_range(const CandCache& C, const RegionPool& F, const std::vector<int>& frontier, size_t a, size_t b,
+                         std::vector<BitRow>& layout, MumPool& mp, RegionPool& out, bool atomic);
 
     void set_initial_clusters();     // anchors
-    void speculate(const std::vector<int>& initial, const World& truth);
+    // level-synchronous discovery for one slice of the initial regions (ids into `src`) on the scratch layout `spec`
+    void speculate_slice(CandCache& C, const RegionPool& src, const std::vector<int>& initial, World& spec);
+    void speculation_thread_main();
+    const CandCache* wait_slice(int slice);
     void do_work_exact();
     void filter_random1();
     void sort_final_mums();
-    int minsize_cached(bool anchors, int64_t slength);
     void set_final_clusters(std::vector<ClusterRec>& out);
     void filter_clusters_simple(std::vector<ClusterRec>& cl);
     void set_inter_cluster_regions(std::vector<ClusterRec>& cl);
@@ -182,30 +221,20 @@ private:
     World truth_;
     std::vector<int> initial_regions_;
 
-    // candidate cache
-    struct WinRec { int64_t ref_start, ref_len; int64_t cand_off; int32_t ncand; int32_t chunk; };
-    std::vector<WinRec> wins_;
-    std::vector<CandBatch> chunks_;        // one per search call; candidates stay where the backend delivered them
-    std::vector<CacheEntry> cache_entries_;
-    // open-addressing index hash(coords) -> cache entry (read-only while the speculation threads run)
-    struct CoordIndex {
-        std::vector<uint64_t> h;
-        std::vector<int> v;
-        size_t count = 0;
-        void insert(uint64_t hash, int value);
-        void reserve(size_t entries);          // room for `entries` more without rehashing
-        template <class Pred> int find(uint64_t hash, Pred pred) const {
-            if (h.empty()) return -1;
-            const size_t mask = h.size() - 1;
-            for (size_t i = (size_t)hash & mask;; i = (i + 1) & mask) {
-                if (v[i] < 0) return -1;
-                if (h[i] == hash && pred(v[i])) return v[i];
-            }
-        }
-    } cache_map_;
+    CandCache main_cache_;                                  // anchors + regions the speculation did not predict
+    std::vector<std::unique_ptr<CandCache>> slice_cache_;   // one per speculation slice
+    std::vector<std::vector<int>> slice_regions_;           // initial regions of every slice (ids into frozen_rp_)
+    std::vector<int> slice_of_initial_;                     // slice of initial_regions_[i]
+    RegionPool frozen_rp_;                                  // the initial regions' coordinates as the speculation thread sees them
+    World spec_world_;                                      // scratch copy of mumlayout for the speculation
+    std::thread spec_thread_;
+    std::mutex slice_mu_, backend_mu_;
+    std::condition_variable slice_cv_;
+    int slices_ready_ = 0;                                  // slices [0, slices_ready_) are published (guarded by slice_mu_)
+    std::exception_ptr spec_error_;
+    bool pipeline_ = true;
 
     std::vector<ClusterRec> clusters_;
-    std::unordered_map<int64_t, int> minsize_cache_[2];
     int threads_ = 1;
     AlignStats stats_;
     std::vector<std::pair<int64_t, int64_t>> trace_;

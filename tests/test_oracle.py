@@ -126,6 +126,21 @@ def test_parallel_anchor_accept_reproduces_reference(name, monkeypatch):
     assert diff_dumps(result_to_dump(res), gold) == []
 
 
+@pytest.mark.parametrize("slices,threads", [(1, 1), (4, 2), (9, 4)])
+@pytest.mark.parametrize("name", ["indep_20k", "rearr_60k", "windows_50k"])
+def test_pipelined_speculation_reproduces_reference(name, slices, threads, monkeypatch):
+    """the speculation runs slice by slice on its own thread while the exact replay consumes the finished slices: any
+    slicing gives the golden result and no region is left to an on-demand search"""
+    from oracle import hosttest
+    monkeypatch.setenv("PB200_SPEC_SLICES", str(slices))
+    monkeypatch.setenv("PB200_HOST_THREADS", str(threads))
+    g, kw, gold = golden_case(name)
+    res = hosttest.align(g, api.make_params(**kw), backend=1)
+    assert diff_dumps(result_to_dump(res), gold) == []
+    assert res["stats"]["spec_slices"] == slices
+    assert res["stats"]["replay_misses"] == 0
+
+
 def test_parallel_anchor_accept_equals_serial_random(monkeypatch):
     """random rearranged / repeat-carrying sets: parallel anchor accept == the literal serial loop (MUMs, LCBs, window trace)"""
     from oracle import hosttest
