@@ -1,5 +1,6 @@
 // CUDA search engine + C ABI of libparsnp_b200.so (see include/parsnp_b200.h).  sm_100a only, no CPU path.
 #include <cuda_runtime.h>
+#include <malloc.h>
 #include <algorithm>
 #include <atomic>
 #include <cstring>
@@ -508,6 +509,19 @@ struct pb200_genomes {
 };
 
 namespace {
+// One alignment allocates and frees ~100 MB of host vectors (candidate blocks, MUM / region pools, result arrays).  With
+// glibc's defaults every block above the (dynamic) mmap threshold is mapped fresh and unmapped again: tens of thousands of
+// page faults per alignment, and with one process per GPU they contend in the kernel.  Keep such blocks on the heap instead
+// (PB200_KEEP_MALLOC_DEFAULTS=1 leaves the allocator alone).
+void tune_host_allocator() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        if (getenv("PB200_KEEP_MALLOC_DEFAULTS")) return;
+        mallopt(M_MMAP_THRESHOLD, 32 * 1024 * 1024);       // the largest value glibc accepts
+        mallopt(M_TRIM_THRESHOLD, 0x7fffffff);             // do not give the top of the heap back between alignments
+    });
+}
+
 template <class F>
 int guarded(F&& f) {
     try { return f(); }
@@ -536,6 +550,7 @@ int pb200_genomes_create(int device, int n, const uint8_t* const* seqs, const in
     return guarded([&]() {
         if (n < 1 || !seqs || !lens || !out) { pb200::g_last_error = "bad arguments"; return (int)PB200_ERR_ARG; }
         const bool prof = getenv("PB200_PROFILE_HOST") != nullptr;
+        tune_host_allocator();
         const double t0 = pb200::wall_s();
         std::unique_ptr<pb200_genomes> g(new pb200_genomes);
         g->eng.reset(new pb200::CudaEngine(device));

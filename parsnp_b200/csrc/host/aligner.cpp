@@ -1245,7 +1245,7 @@ bool Aligner::run() {
             // slices of the initial regions (reference order): the speculation thread discovers and searches slice k+1 while the
             // replay below consumes slice k
             const char* es = getenv("PB200_SPEC_SLICES");
-            size_t K = es ? (size_t)std::max(1, atoi(es)) : std::min<size_t>(8, initial_regions_.size() / 4096 + 1);
+            size_t K = es ? (size_t)std::max(1, atoi(es)) : std::min<size_t>(16, initial_regions_.size() / 512 + 1);
             K = std::min(K, initial_regions_.size());
             stats_.spec_slices = (int64_t)K;
             frozen_rp_ = rp_;                              // (the replay appends to rp_ while the speculation reads the initial regions)

@@ -111,6 +111,7 @@ struct AlignStats {
 class Aligner {
 public:
     Aligner(int n, const uint8_t* const* seq, const int64_t* len, const AlignParams& prm, SearchBackend* be);
+    ~Aligner() { if (spec_thread_.joinable()) spec_thread_.join(); }
     // returns false when no MUMs were found (reference: "NO MUMS FOUND", src/parsnp.cpp:3223-3229)
     bool run();
 
