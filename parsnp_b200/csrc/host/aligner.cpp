@@ -184,9 +184,8 @@ int Aligner::CandCache::lookup(const int64_t* coords) const {
                     [&](int e) { return std::memcmp(rp.start(entries[e].region), coords, bytes) == 0; });
 }
 
-int Aligner::minsize_cached(bool anchors, int64_t slength) {
-    std::lock_guard<std::mutex> lk(minsize_mu_);           // (shared by the replay and the speculation thread)
-    std::unordered_map<int64_t, int>& c = minsize_cache_[anchors ? 1 : 0];
+int Aligner::minsize_cached(CandCache& C, bool anchors, int64_t slength) {
+    std::unordered_map<int64_t, int>& c = C.minsize[anchors ? 1 : 0];
     auto it = c.find(slength);
     if (it != c.end()) return it->second;
     int v = anchors ? anchor_expr_(slength) : mum_expr_(slength);
@@ -195,9 +194,9 @@ int Aligner::minsize_cached(bool anchors, int64_t slength) {
 }
 
 // ------------------------------------------------------------------ batched search (setMums1 up to the emission loop)
-void Aligner::search_regions(CandStore& store, const std::vector<CandCache*>& dst, const RegionPool& src, const std::vector<int>& regs,
-                             bool anchors) {
+void Aligner::search_regions(CandCache& C, const RegionPool& src, const std::vector<int>& regs, bool anchors) {
     if (regs.empty()) return;
+    C.rp.n = n_;
     const double tp0 = now_s();
     std::vector<WindowTask> tasks;
     std::vector<int64_t> coords;
@@ -210,7 +209,7 @@ void Aligner::search_regions(CandStore& store, const std::vector<CandCache*>& ds
         const int64_t* rs = src.start(r);
         const int64_t* re = src.end(r);
         first_task[ri] = (int)tasks.size();
-        const int minsize = minsize_cached(anchors, src.slen[r]);
+        const int minsize = minsize_cached(C, anchors, src.slen[r]);
         const int64_t coff = (int64_t)coords.size();
         for (int j = 1; j < n_; ++j) coords.push_back(rs[j]);
         for (int j = 1; j < n_; ++j) coords.push_back(re[j] - rs[j]);
@@ -237,8 +236,8 @@ void Aligner::search_regions(CandStore& store, const std::vector<CandCache*>& ds
     }
     first_task[regs.size()] = (int)tasks.size();
     const double tp1 = now_s();
-    store.emplace_back();
-    CandBatch& cb = store.back();
+    C.chunks.emplace_back();
+    CandBatch& cb = C.chunks.back();
     cb.nq = nq;
     if (!tasks.empty()) {
         std::lock_guard<std::mutex> lk(backend_mu_);       // one search at a time: the engine owns one stream and one set of buffers
@@ -271,14 +270,11 @@ void Aligner::search_regions(CandStore& store, const std::vector<CandCache*>& ds
         cb.cnt.clear();
     }
     const double tp2 = now_s();
-    if (dst.size() == 1) {
-        dst[0]->entries.reserve(dst[0]->entries.size() + regs.size());
-        dst[0]->map.reserve(regs.size());
-        dst[0]->wins.reserve(dst[0]->wins.size() + tasks.size());
-    }
+    const int32_t chunk = (int32_t)C.chunks.size() - 1;
+    C.entries.reserve(C.entries.size() + regs.size());
+    C.map.reserve(regs.size());
+    C.wins.reserve(C.wins.size() + tasks.size());
     for (size_t ri = 0; ri < regs.size(); ++ri) {
-        CandCache& C = *dst[dst.size() == 1 ? 0 : ri];
-        C.rp.n = n_;
         CacheEntry e;
         e.region = C.rp.add(src.start(regs[ri]), src.end(regs[ri]));
         e.first_win = (int64_t)C.wins.size();
@@ -289,7 +285,7 @@ void Aligner::search_regions(CandStore& store, const std::vector<CandCache*>& ds
             w.ref_len = tasks[t].ref_len;
             w.cand_off = cb.off[t];
             w.ncand = cb.count(t);
-            w.cb = &cb;
+            w.chunk = chunk;
             C.wins.push_back(w);
         }
         C.map.insert(coords_hash(src.start(regs[ri]), 2 * n_), (int)C.entries.size());
@@ -321,7 +317,7 @@ void Aligner::accept_candidates(const int64_t* rs, const int64_t* re, int64_t rs
     if (n_ > 64) { st_vec.resize(n_); fw_vec.resize(n_); st = st_vec.data(); fw = fw_vec.data(); }
     for (int wi = 0; wi < ce.nwin; ++wi) {
         const WinRec& win = C.wins[ce.first_win + wi];
-        const CandBatch& cb = *win.cb;
+        const CandBatch& cb = C.chunks[win.chunk];
         if (trace) trace_.emplace_back(win.ref_start, win.ref_len);
         for (int32_t c = 0; c < win.ncand; ++c) {
             const int64_t ci = win.cand_off + c;
@@ -417,7 +413,7 @@ void Aligner::accept_candidates_parallel(const int64_t* rs, const int64_t* re, i
         for (size_t c = c0; c < c1; ++c) {
             while ((int64_t)c >= wbase[wi + 1]) ++wi;
             const WinRec& win = CC.wins[ce.first_win + wi];
-            const CandBatch& cb = *win.cb;
+            const CandBatch& cb = CC.chunks[win.chunk];
             const int64_t ci = win.cand_off + ((int64_t)c - wbase[wi]);
             const int64_t lon = cb.lon[ci];
             int64_t* st = &ST[c * N];
@@ -590,7 +586,7 @@ void Aligner::set_initial_clusters() {
     double t0 = now_s();
     std::vector<int64_t> S(n_, 0), E(len_);
     int whole = rp_.add(S.data(), E.data());
-    search_regions(main_store_, std::vector<CandCache*>(1, &main_cache_), rp_, std::vector<int>(1, whole), true);
+    search_regions(main_cache_, rp_, std::vector<int>(1, whole), true);
     double t1 = now_s();
     stats_.t_anchor_search = t1 - t0;
     std::vector<int> found;
@@ -684,8 +680,8 @@ void Aligner::set_initial_clusters() {
 // ------------------------------------------------------------------ speculative level-synchronous discovery
 // One level over frontier[a,b) (sorted by start[0]): accept on the scratch layout, collect the children's coordinates.
 // Only a predictor of which regions the exact replay will ask for - races between threads merely cost cache misses.
-void Aligner::speculate_range(const RegionPool& F, const std::vector<int>& frontier, const std::vector<int>& slice_of, size_t a, size_t b,
-                              std::vector<BitRow>& layout, MumPool& mp, RegionPool& out, std::vector<int>& out_slice, bool atomic) {
+void Aligner::speculate_range(const CandCache& C, const RegionPool& F, const std::vector<int>& frontier, size_t a, size_t b,
+                              std::vector<BitRow>& layout, MumPool& mp, RegionPool& out, bool atomic) {
     std::vector<int> found;
     std::vector<int64_t> lS(n_), lE(n_), rS(n_), rE(n_);
     const size_t cbytes = sizeof(int64_t) * 2 * n_;
@@ -695,8 +691,6 @@ void Aligner::speculate_range(const RegionPool& F, const std::vector<int>& front
         if (prev >= 0 && std::memcmp(F.start(prev), F.start(r), cbytes) == 0) continue;
         prev = r;
         found.clear();
-        const int sl = slice_of[r];
-        const CandCache& C = *slice_cache_[sl];
         const int ci = C.lookup(F.start(r));
         if (ci < 0) continue;
         accept_candidates(F.start(r), F.end(r), F.slen[r], C, ci, layout, mp, found, atomic, false);
@@ -706,8 +700,8 @@ void Aligner::speculate_range(const RegionPool& F, const std::vector<int>& front
             const int64_t* ms = &mp.start[m.off];
             if (i == 0) lsl = det_region(layout, len_, n_, ms, m.length, true, lS.data(), lE.data());
             int64_t rsl = det_region(layout, len_, n_, ms, m.length, false, rS.data(), rE.data());
-            if (lsl > prm_.q) { out.add(lS.data(), lE.data()); out_slice.push_back(sl); }
-            if (rsl > prm_.q) { out.add(rS.data(), rE.data()); out_slice.push_back(sl); }
+            if (lsl > prm_.q) out.add(lS.data(), lE.data());
+            if (rsl > prm_.q) out.add(rS.data(), rE.data());
             if (i + 1 < found.size()) {
                 const MumRec& m2 = mp.mums[found[i + 1]];
                 lsl = det_region(layout, len_, n_, &mp.start[m2.off], m2.length, true, lS.data(), lE.data());
@@ -716,46 +710,28 @@ void Aligner::speculate_range(const RegionPool& F, const std::vector<int>& front
     }
 }
 
-// Speculative discovery in waves.  Wave w searches, in ONE backend batch, the initial regions of slice w together with the
-// children discovered by wave w-1 (which belong to slices w-1, w-2, ...), then accepts on the scratch layout and collects the
-// next children.  A slice is complete once it has been issued and none of its descendants is pending; complete slices are
-// published in order.  (Level-synchronous per slice would need ~3 batches per slice, each a fraction of the size.)
-void Aligner::speculate_waves() {
-    const size_t K = slice_cache_.size();
-    RegionPool F;                                          // every region the speculation has seen (frontier ids index it)
+void Aligner::speculate_slice(CandCache& C, const RegionPool& src, const std::vector<int>& initial, World& spec) {
+    RegionPool F;                                          // the slice's frontier regions, level after level
     F.n = n_;
-    std::vector<int> slice_of;                             // slice of every region of F
-    std::vector<int> frontier, need, next;
-    std::vector<CandCache*> need_dst;
+    std::vector<int> frontier, need;
+    frontier.reserve(initial.size());
+    for (int r : initial) frontier.push_back(F.add(src.start(r), src.end(r)));
     const size_t cbytes = sizeof(int64_t) * 2 * n_;
-    size_t next_slice = 0;
-    std::vector<int> pending(K, 0);                        // regions of the slice in the current frontier
-    while (next_slice < K || !frontier.empty()) {
+    while (!frontier.empty()) {
         double t0 = now_s();
-        if (next_slice < K) {
-            for (int r : slice_regions_[next_slice]) {
-                frontier.push_back(F.add(frozen_rp_.start(r), frozen_rp_.end(r)));
-                slice_of.push_back((int)next_slice);
-            }
-            ++next_slice;
-        }
         need.clear();
-        need_dst.clear();
         {
             CoordIndex seen;
             seen.reserve(frontier.size());
             for (int r : frontier) {
-                CandCache* C = slice_cache_[slice_of[r]].get();
-                if (C->lookup(F.start(r)) >= 0) continue;
+                if (C.lookup(F.start(r)) >= 0) continue;
                 const uint64_t h = coords_hash(F.start(r), 2 * n_);
-                if (seen.find(h, [&](int o) { return slice_of[o] == slice_of[r] && std::memcmp(F.start(o), F.start(r), cbytes) == 0; }) >= 0) continue;
+                if (seen.find(h, [&](int o) { return std::memcmp(F.start(o), F.start(r), cbytes) == 0; }) >= 0) continue;
                 seen.insert(h, r);
                 need.push_back(r);
-                need_dst.push_back(C);
             }
         }
-        if (need.size() == 1) need_dst.resize(1);
-        search_regions(spec_store_, need_dst, F, need, false);
+        search_regions(C, F, need, false);
         stats_.spec_regions += (int64_t)need.size();
         stats_.spec_levels++;
         double t1 = now_s();
@@ -765,44 +741,31 @@ void Aligner::speculate_waves() {
         const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads_, frontier.size() / 256 + 1));
         const size_t nchunks = T > 1 ? (size_t)T * 4 : 1;
         std::vector<RegionPool> outs(nchunks);
-        std::vector<std::vector<int>> out_slices(nchunks);
         for (auto& o : outs) o.n = n_;
         parallel_chunks(T, (long)nchunks, [&](long c) {
             MumPool mp;
             const size_t a = frontier.size() * (size_t)c / nchunks, b = frontier.size() * (size_t)(c + 1) / nchunks;
-            speculate_range(F, frontier, slice_of, a, b, spec_world_.layout, mp, outs[c], out_slices[c], T > 1);
+            speculate_range(C, F, frontier, a, b, spec.layout, mp, outs[c], T > 1);
         });
-        next.clear();
-        std::fill(pending.begin(), pending.end(), 0);
-        for (size_t c = 0; c < nchunks; ++c)
-            for (int i = 0; i < outs[c].size(); ++i) {
-                next.push_back(F.add(outs[c].start(i), outs[c].end(i)));
-                slice_of.push_back(out_slices[c][(size_t)i]);
-                pending[(size_t)out_slices[c][(size_t)i]]++;
-            }
+        std::vector<int> next;
+        for (auto& o : outs)
+            for (int i = 0; i < o.size(); ++i) next.push_back(F.add(o.start(i), o.end(i)));
         frontier.swap(next);
         stats_.t_spec_host += now_s() - t1;
-        // publish, in order, every issued slice without pending descendants
-        int ready;
-        {
-            std::lock_guard<std::mutex> lk(slice_mu_);
-            while ((size_t)slices_ready_ < next_slice && pending[(size_t)slices_ready_] == 0) ++slices_ready_;
-            ready = slices_ready_;
-        }
-        (void)ready;
-        slice_cv_.notify_all();
     }
-    {
-        std::lock_guard<std::mutex> lk(slice_mu_);
-        slices_ready_ = (int)K;
-    }
-    slice_cv_.notify_all();
 }
 
-// the speculation thread
+// the speculation thread: slice after slice, each published as soon as it is complete
 void Aligner::speculation_thread_main() {
     try {
-        speculate_waves();
+        for (size_t k = 0; k < slice_cache_.size(); ++k) {
+            speculate_slice(*slice_cache_[k], frozen_rp_, slice_regions_[k], spec_world_);
+            {
+                std::lock_guard<std::mutex> lk(slice_mu_);
+                slices_ready_ = (int)k + 1;
+            }
+            slice_cv_.notify_all();
+        }
     } catch (...) {
         std::lock_guard<std::mutex> lk(slice_mu_);
         spec_error_ = std::current_exception();
@@ -878,7 +841,7 @@ void Aligner::process_queue_exact(const std::vector<int>& initial, RegionPool& r
         PROF_MARK(1);
         if (ci < 0) {
             double ts = now_s();
-            search_regions(main_store_, std::vector<CandCache*>(1, &main_cache_), rp, std::vector<int>(1, cur), false);          // a region the speculation did not predict
+            search_regions(main_cache_, rp, std::vector<int>(1, cur), false);          // a region the speculation did not predict
             stats_.t_replay_search += now_s() - ts;
             stats_.replay_misses++;
             ci = main_cache_.lookup(rp.start(cur));

@@ -20,7 +20,6 @@
 #include <vector>
 #include <unordered_map>
 #include <map>
-#include <deque>
 #include <memory>
 #include <mutex>
 #include <condition_variable>
@@ -148,7 +147,7 @@ private:
     // (anchors and on-demand searches: the main thread; every speculation slice: the speculation thread); a published
     // instance is read-only.
     struct CacheEntry { int region; int64_t first_win; int nwin; };
-    struct WinRec { int64_t ref_start, ref_len; int64_t cand_off; const CandBatch* cb; int32_t ncand; };
+    struct WinRec { int64_t ref_start, ref_len; int64_t cand_off; int32_t ncand; int32_t chunk; };
     // open-addressing index hash(coords) -> cache entry
     struct CoordIndex {
         std::vector<uint64_t> h;
@@ -169,15 +168,14 @@ private:
         RegionPool rp;                         // own copies of the searched regions' coordinates (the keys)
         std::vector<CacheEntry> entries;       // .region indexes rp
         CoordIndex map;
-        std::vector<WinRec> wins;              // .cb points into a candidate store (below)
+        std::vector<WinRec> wins;
+        std::vector<CandBatch> chunks;         // one per search call; candidates stay where the backend delivered them
+        std::unordered_map<int64_t, int> minsize[2];
         int lookup(const int64_t* coords) const;    // -> index into entries or -1
     };
-    // candidate store: one CandBatch per search call, candidates stay where the backend delivered them (deque: stable addresses)
-    typedef std::deque<CandBatch> CandStore;
-    int minsize_cached(bool anchors, int64_t slength);
-    // batched GPU search of regions `regs` of pool `src`; the candidates go to `store`, region ri is entered into *dst[ri]
-    // (dst.size() == 1: all regions into that cache)
-    void search_regions(CandStore& store, const std::vector<CandCache*>& dst, const RegionPool& src, const std::vector<int>& regs, bool anchors);
+    int minsize_cached(CandCache& C, bool anchors, int64_t slength);
+    // batched GPU search of regions `regs` of pool `src`, fills C
+    void search_regions(CandCache& C, const RegionPool& src, const std::vector<int>& regs, bool anchors);
 
     // setMums1 loop D on cached candidates; appends accepted MUMs to `mp`, their indices to `found`
     void accept_candidates(const int64_t* rs, const int64_t* re, int64_t rsl, const CandCache& C, int cache_idx, std::vector<BitRow>& layout,
@@ -189,12 +187,13 @@ private:
     void process_queue_exact(const std::vector<int>& initial, RegionPool& rp, std::vector<BitRow>& layout, MumPool& mp,
                              std::vector<int>& out_mums);
     // one speculative level over frontier[a,b): children coordinates appended to `out`
-    void speculate_range(const RegionPool& F, const std::vector<int>& frontier, const std::vector<int>& slice_of, size_t a, size_t b,
-                         std::vector<BitRow>& layout, MumPool& mp, RegionPool& out, std::vector<int>& out_slice, bool atomic);
+    void speculate_range(const CandCache& C, const RegionPool& F, const std::vector<int>& frontier, size_t a, size_t b,
+                         std::vector<BitRow>& layout, MumPool& mp, RegionPool& out, bool atomic);
 
     void set_initial_clusters();     // anchors
+    // level-synchronous discovery for one slice of the initial regions (ids into `src`) on the scratch layout `spec`
+    void speculate_slice(CandCache& C, const RegionPool& src, const std::vector<int>& initial, World& spec);
     void speculation_thread_main();
-    void speculate_waves();
     const CandCache* wait_slice(int slice);
     void do_work_exact();
     void filter_random1();
@@ -224,9 +223,6 @@ private:
     std::vector<int> initial_regions_;
 
     CandCache main_cache_;                                  // anchors + regions the speculation did not predict
-    CandStore main_store_, spec_store_;                     // candidates found by the main thread / by the speculation thread
-    std::unordered_map<int64_t, int> minsize_cache_[2];
-    std::mutex minsize_mu_;
     std::vector<std::unique_ptr<CandCache>> slice_cache_;   // one per speculation slice
     std::vector<std::vector<int>> slice_regions_;           // initial regions of every slice (ids into frozen_rp_)
     std::vector<int> slice_of_initial_;                     // slice of initial_regions_[i]
