@@ -738,7 +738,9 @@ void Aligner::speculate_slice(CandCache& C, const RegionPool& src, const std::ve
         stats_.t_spec_search += t1 - t0;
         std::stable_sort(frontier.begin(), frontier.end(), [&](int a, int b) { return F.start(a)[0] < F.start(b)[0]; });
         // chunks of the frontier are processed concurrently on the shared scratch layout
-        const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads_, frontier.size() / 256 + 1));
+        // (pipelined: one core of this rank's share belongs to the replay thread)
+        const size_t share = (size_t)std::max(1, pipeline_ ? threads_ - 1 : threads_);
+        const int T = (int)std::max<size_t>(1, std::min<size_t>(share, frontier.size() / 256 + 1));
         const size_t nchunks = T > 1 ? (size_t)T * 4 : 1;
         std::vector<RegionPool> outs(nchunks);
         for (auto& o : outs) o.n = n_;
