@@ -243,6 +243,58 @@ def test_c4_shape_matches_reference_binary():
     assert diff_dumps(result_to_dump(res), r["dump"]) == []
 
 
+def _edge_cases():
+    """small inputs at the corners of the path: (genomes, make_params kwargs, run_ref kwargs)"""
+    rng = np.random.default_rng(2024)
+    A = np.frombuffer(b"ACGT", np.uint8)
+    base = synth.g_indep(60000, 3, 0.02, 41)
+    cases = {}
+    # ragged: one query is a prefix of its genome, one carries 40 % foreign sequence at the end
+    cases["ragged_lengths"] = ([base[0], base[1][:25000].copy(), np.concatenate([base[2], A[rng.integers(0, 4, 24000)]]), base[3]], {}, {})
+    # a single query
+    cases["single_query"] = (base[:2], {}, {})
+    # N runs inside the reference (3-bit key path for the anchors) and inside a query
+    g = [x.copy() for x in base]
+    g[0][10000:10400] = ord("N"); g[0][30000:30007] = ord("N"); g[2][45000:45300] = ord("N")
+    cases["n_runs"] = (g, {}, {})
+    # a query that is the reverse complement of its genome: every anchor on the reverse strand
+    cases["revcomp_query"] = ([base[0], synth.revcomp(base[1]), base[2]], {}, {})
+    # identical genomes: one match as long as the genome
+    cases["identical"] = ([base[0][:20000].copy(), base[0][:20000].copy(), base[0][:20000].copy()], {}, {})
+    # tiny genomes: the anchor search itself runs in the shared-memory kernel
+    t = synth.g_indep(700, 3, 0.03, 5)
+    cases["tiny"] = (t, {}, {})
+    # constant minimum lengths and other ini values; several reference windows
+    cases["ini_values"] = (base, dict(c=50, d=100, q=20, p=25000, diagdiff=0.3, anchors="25", mums="15"),
+                           dict(c=50, d=100, q=20, p=25000, diagdiff=0.3, anchors="25", mums="15"))
+    # diagdiff > 1 takes the absolute-difference branch of setFinalClusters
+    cases["diagdiff_abs"] = (base, dict(diagdiff=40.0), dict(diagdiff=40.0))
+    return cases
+
+
+@pytest.mark.parametrize("name", ["ragged_lengths", "single_query", "n_runs", "revcomp_query", "identical", "tiny", "ini_values", "diagdiff_abs"])
+def test_edge_cases_match_reference_binary(name):
+    """corner inputs: GPU path == reference binary run here (MUM coordinates, LCB records)"""
+    from oracle import runner
+    g, kw, rkw = _edge_cases()[name]
+    with tempfile.TemporaryDirectory() as td:
+        ref, qs = synth.write_dataset(os.path.join(td, "d"), g)
+        r = runner.run_ref(ref, qs, os.path.join(td, "r"), **rkw)
+    res = api.align(g, api.make_params(**kw))
+    assert r["dump"] is not None and len(r["dump"]["mums"]) > 0
+    assert diff_dumps(result_to_dump(res), r["dump"]) == []
+
+
+def test_no_mums_found():
+    """unrelated genomes: the reference writes NO MUMS FOUND and exits 0 (src/parsnp.cpp:3223-3229); the library returns
+    PB200_ERR_NO_MUMS with empty lists"""
+    rng = np.random.default_rng(8)
+    A = np.frombuffer(b"ACGT", np.uint8)
+    g = [A[rng.integers(0, 4, 30000)] for _ in range(3)]
+    res = api.align(g, api.make_params())
+    assert res["no_mums"] and len(res["mum_length"]) == 0 and len(res["cluster_type"]) == 0
+
+
 def test_full_size_properties():
     """BASELINE config-2 shape at reduced query count (5 Mbp reference, 2 queries): size-independent properties -
     MUMs are exact matches in every genome, disjoint on the reference, LCB MUM sums consistent."""
