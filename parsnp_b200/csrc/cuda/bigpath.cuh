@@ -369,19 +369,45 @@ __global__ void __launch_bounds__(128, 12) seed_extend_kernel(const uint8_t* __r
                 }
             }
         }
-        // cooperative right extension of the pending seeds
+        // cooperative right extension of the pending seeds, two at a time: each half-warp compares 16 x 8 bytes of one seed per
+        // step (most matches end within 128 bases: one step)
         int ext = 0;
         unsigned pm = __ballot_sync(FULL, pend);
+        const int half = lane >> 4, hl = lane & 15;
         while (pm) {
-            const int src = __ffs(pm) - 1;
+            const int sA = __ffs(pm) - 1;
             pm &= pm - 1;
-            const int qp = __shfl_sync(FULL, j + k, src), rp = __shfl_sync(FULL, l + k, src), lm = __shfl_sync(FULL, lim, src);
+            int sB = -1;
+            if (pm) { sB = __ffs(pm) - 1; pm &= pm - 1; }
+            const int src = half ? sB : sA;                   // this half's seed (-1: none)
+            const int ssrc = src < 0 ? 0 : src;
+            const int qp = __shfl_sync(FULL, j + k, ssrc), rp = __shfl_sync(FULL, l + k, ssrc);
+            const int lm_src = __shfl_sync(FULL, lim, ssrc);       // (every lane takes part in the shuffle)
+            const int lm = src < 0 ? 0 : lm_src;
             int e = lm;
-            for (int base = 0; base < lm; base += 256) {
-                const int my = coop_step(Q, R, qp, rp, lm, base, lane);
-                if (coop_resolve(__ballot_sync(FULL, my < 8), my, lm, base, e)) break;
+            bool done = lm == 0;
+            for (int base = 0;; base += 128) {
+                int my = 8;
+                if (!done) {
+                    const int off = base + hl * 8;
+                    my = 0;                                     // past the limit: the match stops here
+                    if (off < lm) {
+                        const uint64_t x = load8u(Q + qp + off) ^ load8u(R + rp + off);
+                        my = x ? ((__ffsll((long long)x) - 1) >> 3) : 8;
+                    }
+                }
+                const unsigned hb = (__ballot_sync(FULL, !done && my < 8) >> (16 * half)) & 0xffffu;
+                const int fl = hb ? __ffs(hb) - 1 : 0;
+                const int mlen = __shfl_sync(FULL, my, 16 * half + fl);
+                if (!done) {
+                    if (hb) { e = min(lm, base + fl * 8 + mlen); done = true; }
+                    else if (base + 128 >= lm) { e = lm; done = true; }
+                }
+                if (!__any_sync(FULL, !done)) break;
             }
-            if (lane == src) ext = e;
+            const int eA = __shfl_sync(FULL, e, 0), eB = __shfl_sync(FULL, e, 16);
+            if (lane == sA) ext = eA;
+            if (lane == sB) ext = eB;
         }
         // events of this round: one atomic per warp
         bool emit = false;
