@@ -8,10 +8,11 @@
 //   * MUMs / regions live in flat SoA pools instead of vector<vector<long>> objects;
 //   * the index build + scan + fold + emission of setMums1 (its calls into csgmum) is delegated to a
 //     SearchBackend (the CUDA engine), batched over many regions at once;
-//   * the recursion runs as  (1) a speculative, level-synchronous pass that only exists to discover which
-//     regions will be searched and to batch them onto the GPU, then (2) an exact sequential replay in the
-//     reference's own order (pop smallest start[0], push children, sort, drop adjacent duplicates) that looks
-//     the candidates up by region coordinates and asks the GPU for any region the speculation did not predict.
+//   * the recursion runs as  (1) a speculative, level-synchronous pass (slice after slice of the initial regions, on its
+//     own thread) that only exists to discover which regions will be searched and to batch them onto the GPU, beside
+//     (2) an exact sequential replay in the reference's own order (pop smallest start[0], push children, sort, drop
+//     adjacent duplicates) that consumes the finished slices, looks the candidates up by region coordinates and asks
+//     the GPU for any region the speculation did not predict.
 //     The search is a pure function of the region coordinates, so pass (2) is exact by construction.
 #pragma once
 #include <cstdint>
