@@ -146,41 +146,38 @@ uint64_t Aligner::coords_hash(const int64_t* p, int count) {
     return h;
 }
 void Aligner::CoordIndex::insert(uint64_t hash, int value) {
-    if ((count + 1) * 2 > h.size()) {                       // grow / rehash at 50 % load
-        std::vector<uint64_t> oh;
-        std::vector<int> ov;
-        oh.swap(h);
-        ov.swap(v);
-        const size_t nsz = oh.empty() ? 1024 : oh.size() * 2;
-        h.assign(nsz, 0);
-        v.assign(nsz, -1);
+    if ((count + 1) * 2 > s.size()) {                       // grow / rehash at 50 % load
+        std::vector<Slot> os;
+        os.swap(s);
+        const size_t nsz = os.empty() ? 1024 : os.size() * 2;
+        s.assign(nsz, Slot{0, -1, 0});
         count = 0;
-        for (size_t i = 0; i < oh.size(); ++i) if (ov[i] >= 0) insert(oh[i], ov[i]);
+        for (size_t i = 0; i < os.size(); ++i) if (os[i].v >= 0) insert(os[i].h, os[i].v);
     }
-    const size_t mask = h.size() - 1;
+    const size_t mask = s.size() - 1;
     size_t i = (size_t)hash & mask;
-    while (v[i] >= 0) i = (i + 1) & mask;
-    h[i] = hash;
-    v[i] = value;
+    while (s[i].v >= 0) i = (i + 1) & mask;
+    s[i].h = hash;
+    s[i].v = value;
     ++count;
 }
 void Aligner::CoordIndex::reserve(size_t entries) {
     size_t need = 1024;
     while (need < (count + entries) * 2 + 2) need *= 2;
-    if (need <= h.size()) return;
-    std::vector<uint64_t> oh;
-    std::vector<int> ov;
-    oh.swap(h);
-    ov.swap(v);
-    h.assign(need, 0);
-    v.assign(need, -1);
+    if (need <= s.size()) return;
+    std::vector<Slot> os;
+    os.swap(s);
+    s.assign(need, Slot{0, -1, 0});
     count = 0;
-    for (size_t i = 0; i < oh.size(); ++i) if (ov[i] >= 0) insert(oh[i], ov[i]);
+    for (size_t i = 0; i < os.size(); ++i) if (os[i].v >= 0) insert(os[i].h, os[i].v);
 }
 int Aligner::CandCache::lookup(const int64_t* coords) const {
+    return lookup(coords, Aligner::coords_hash(coords, 2 * rp.n));
+}
+int Aligner::CandCache::lookup(const int64_t* coords, uint64_t hash) const {
     const int n = rp.n;
     const size_t bytes = sizeof(int64_t) * 2 * n;
-    return map.find(Aligner::coords_hash(coords, 2 * n),
+    return map.find(hash,
                     [&](int e) { return std::memcmp(rp.start(entries[e].region), coords, bytes) == 0; });
 }
 
@@ -724,8 +721,8 @@ void Aligner::speculate_slice(CandCache& C, const RegionPool& src, const std::ve
             CoordIndex seen;
             seen.reserve(frontier.size());
             for (int r : frontier) {
-                if (C.lookup(F.start(r)) >= 0) continue;
                 const uint64_t h = coords_hash(F.start(r), 2 * n_);
+                if (C.lookup(F.start(r), h) >= 0) continue;
                 if (seen.find(h, [&](int o) { return std::memcmp(F.start(o), F.start(r), cbytes) == 0; }) >= 0) continue;
                 seen.insert(h, r);
                 need.push_back(r);
@@ -789,7 +786,7 @@ const Aligner::CandCache* Aligner::wait_slice(int slice) {
 
 // ------------------------------------------------------------------ doWork (src/parsnp.cpp:173-317), exact order
 namespace {
-struct QE { int64_t s0; int id; int slice; };      // slice: the speculation slice the region descends from
+struct QE { int64_t s0; int id; int slice; uint64_t hash; };      // slice: the speculation slice the region descends from; hash of the coordinates
 inline bool operator<(const QE& a, const QE& b) { return a.s0 < b.s0; }   // operator<, src/LCR.cpp:42
 }
 
@@ -800,7 +797,8 @@ void Aligner::process_queue_exact(const std::vector<int>& initial, RegionPool& r
     auto req = [&](int a, int b) { return std::memcmp(rp.start(a), rp.start(b), sizeof(int64_t) * 2 * n_) == 0; };
     std::vector<QE> vec;
     for (size_t i = 0; i < initial.size(); ++i)
-        vec.push_back(QE{rp.start(initial[i])[0], initial[i], i < slice_of_initial_.size() ? slice_of_initial_[i] : -1});
+        vec.push_back(QE{rp.start(initial[i])[0], initial[i], i < slice_of_initial_.size() ? slice_of_initial_[i] : -1,
+                         coords_hash(rp.start(initial[i]), 2 * n_)});
     int ready_upto = 0;                       // speculation slices [0, ready_upto) are known to be published
     // fast mode: the queue as a vector sorted by DESCENDING start[0] (front of the reference's vector = back of this one).
     // Children of the region just taken lie inside it, i.e. next to the back, so insertion is a short walk + a short move.
@@ -829,8 +827,9 @@ void Aligner::process_queue_exact(const std::vector<int>& initial, RegionPool& r
     if (prof) pt = __builtin_ia32_rdtsc();
     while (fast_mode ? !fast.empty() : !vec.empty()) {
         int cur, cur_slice;
-        if (fast_mode) { cur = fast.back().id; cur_slice = fast.back().slice; fast.pop_back(); }
-        else { cur = vec.front().id; cur_slice = vec.front().slice; vec.erase(vec.begin()); }
+        uint64_t cur_hash;
+        if (fast_mode) { cur = fast.back().id; cur_slice = fast.back().slice; cur_hash = fast.back().hash; fast.pop_back(); }
+        else { cur = vec.front().id; cur_slice = vec.front().slice; cur_hash = vec.front().hash; vec.erase(vec.begin()); }
         PROF_MARK(0);
         // candidates: the slice's speculation (wait for it if it is still in flight), else the main cache, else search now
         const CandCache* C = nullptr;
@@ -838,8 +837,8 @@ void Aligner::process_queue_exact(const std::vector<int>& initial, RegionPool& r
             if (cur_slice >= ready_upto) { wait_slice(cur_slice); ready_upto = cur_slice + 1; }
             C = slice_cache_[cur_slice].get();
         }
-        int ci = C ? C->lookup(rp.start(cur)) : -1;
-        if (ci < 0) { C = &main_cache_; ci = main_cache_.lookup(rp.start(cur)); }
+        int ci = C ? C->lookup(rp.start(cur), cur_hash) : -1;
+        if (ci < 0) { C = &main_cache_; ci = main_cache_.lookup(rp.start(cur), cur_hash); }
         PROF_MARK(1);
         if (ci < 0) {
             double ts = now_s();
@@ -882,7 +881,9 @@ void Aligner::process_queue_exact(const std::vector<int>& initial, RegionPool& r
                     const int64_t key = rp.start(ch)[0];
                     const size_t pos = fast_pos(key);
                     if (pos < fast.size() && fast[pos].s0 == key) continue;
-                    fast.insert(fast.begin() + (long)pos, QE{key, ch, cur_slice});
+                    const uint64_t hh = coords_hash(rp.start(ch), 2 * n_);
+                    if (cur_slice >= 0 && cur_slice < (int)slice_cache_.size()) slice_cache_[cur_slice]->map.prefetch(hh);   // (looked up a few pops from now)
+                    fast.insert(fast.begin() + (long)pos, QE{key, ch, cur_slice, hh});
                 }
                 PROF_MARK(4);
                 continue;
@@ -892,7 +893,7 @@ void Aligner::process_queue_exact(const std::vector<int>& initial, RegionPool& r
             fast_mode = false;
         }
         stats_.slow_queue_iters++;
-        for (int ch : children) vec.push_back(QE{rp.start(ch)[0], ch, cur_slice});
+        for (int ch : children) vec.push_back(QE{rp.start(ch)[0], ch, cur_slice, coords_hash(rp.start(ch), 2 * n_)});
         if (!vec.empty()) {
             // The queue is nearly sorted (anchor order, then children next to their parent).  With distinct start[0] keys every
             // correct sort gives the same sequence, so try a bounded insertion sort on a copy; ties (or too much disorder) fall

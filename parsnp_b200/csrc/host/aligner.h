@@ -151,19 +151,20 @@ private:
     struct WinRec { int64_t ref_start, ref_len; int64_t cand_off; int32_t ncand; int32_t chunk; };
     // open-addressing index hash(coords) -> cache entry
     struct CoordIndex {
-        std::vector<uint64_t> h;
-        std::vector<int> v;
+        struct Slot { uint64_t h; int32_t v; int32_t pad; };      // hash and entry side by side: one cache line per probe
+        std::vector<Slot> s;
         size_t count = 0;
         void insert(uint64_t hash, int value);
         void reserve(size_t entries);          // room for `entries` more without rehashing
         template <class Pred> int find(uint64_t hash, Pred pred) const {
-            if (h.empty()) return -1;
-            const size_t mask = h.size() - 1;
+            if (s.empty()) return -1;
+            const size_t mask = s.size() - 1;
             for (size_t i = (size_t)hash & mask;; i = (i + 1) & mask) {
-                if (v[i] < 0) return -1;
-                if (h[i] == hash && pred(v[i])) return v[i];
+                if (s[i].v < 0) return -1;
+                if (s[i].h == hash && pred(s[i].v)) return s[i].v;
             }
         }
+        void prefetch(uint64_t hash) const { if (!s.empty()) __builtin_prefetch(&s[(size_t)hash & (s.size() - 1)]); }
     };
     struct CandCache {
         RegionPool rp;                         // own copies of the searched regions' coordinates (the keys)
@@ -173,6 +174,7 @@ private:
         std::vector<CandBatch> chunks;         // one per search call; candidates stay where the backend delivered them
         std::unordered_map<int64_t, int> minsize[2];
         int lookup(const int64_t* coords) const;    // -> index into entries or -1
+        int lookup(const int64_t* coords, uint64_t hash) const;      // hash = coords_hash(coords) computed by the caller
     };
     int minsize_cached(CandCache& C, bool anchors, int64_t slength);
     // batched GPU search of regions `regs` of pool `src`, fills C
