@@ -68,6 +68,7 @@ typedef struct {
 
 #define PB200_FLAG_TRACE_WINDOWS 1   /* record the sequence of searched windows (tests) */
 #define PB200_FLAG_NO_SPECULATION 2  /* skip the speculative batching pass: every region is searched on demand */
+#define PB200_FLAG_UNALIGNED 4       /* also list the unaligned regions (ini [LCB] unaligned=1) */
 
 void pb200_params_default(pb200_params* p);
 const char* pb200_last_error(void);
@@ -118,6 +119,10 @@ int pb200_result_clusters(const pb200_result* r, int32_t* type, int64_t* nmums, 
 /* MUMs of every cluster (Cluster::mums): off[c]..off[c+1] index into idx[], idx = positions in the MUM list; returns the
  * total number of indices (call with NULLs first). Inter-cluster records (type 0) have none. */
 int pb200_result_cluster_mums(const pb200_result* r, int64_t* off, int64_t* idx);
+/* unaligned regions (PB200_FLAG_UNALIGNED): the records Aligner::setUnalignableRegions (src/parsnp.cpp:2310-2382) writes to
+ * parsnp.unalign, in its order: genome[r] (0-based), start[r], end[r] (`>genome+1:start-end`; the sequence printed is
+ * genomes[genome].substr(start, end-start)).  Returns the number of records; any pointer may be NULL. */
+int64_t pb200_result_unaligned(const pb200_result* r, int32_t* genome, int64_t* start, int64_t* end);
 /* searched windows in order (PB200_FLAG_TRACE_WINDOWS): pairs (ref_start, ref_len) */
 int64_t pb200_result_num_trace(const pb200_result* r);
 int pb200_result_trace(const pb200_result* r, int64_t* pairs);

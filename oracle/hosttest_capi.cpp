@@ -27,7 +27,7 @@ int pbtest_align(int backend, int n, const uint8_t* const* seqs, const int64_t* 
         a.set_speculate(!(prm->flags & PB200_FLAG_NO_SPECULATION));
         a.set_threads(pb200::default_host_threads());
         bool ok = a.run();
-        *out = pb200::make_result(a);
+        *out = pb200::make_result(a, (prm->flags & PB200_FLAG_UNALIGNED) != 0);
         delete be;
         return ok ? 0 : PB200_ERR_NO_MUMS;
     } catch (const std::exception& e) { pb200::g_last_error = e.what(); return PB200_ERR_INTERNAL; }
@@ -52,7 +52,7 @@ int pbtest_align_sharded(int rank, int world, pb200_allgather_cb ag, pb200_allre
         a.set_threads(pb200::default_host_threads());
         a.set_pipeline(false);            // collectives inside the search: same call order on every rank
         bool ok = a.run();
-        *out = pb200::make_result(a);
+        *out = pb200::make_result(a, (prm->flags & PB200_FLAG_UNALIGNED) != 0);
         if (counters) { counters[0] = sb.staged_windows; counters[1] = sb.sharded_small_windows; }
         return ok ? 0 : PB200_ERR_NO_MUMS;
     } catch (const std::exception& e) { pb200::g_last_error = e.what(); return PB200_ERR_INTERNAL; }

@@ -1,6 +1,6 @@
 // TEST-ONLY tool: writes the XMFA from an oracle MUM/LCB dump (hook H1 of oracle/build_ref.py) through the product's XMFA
 // writer (parsnp_b200/csrc/main/xmfa.cpp), so the writer can be checked against the reference's XMFA md5 without a GPU.
-//   xmfa_from_dump <ini> <dump.txt> <out.xmfa>
+//   xmfa_from_dump <ini> <dump.txt> <out.xmfa> [<outdir for blocks/ and parsnp.unalign> [<unaligned records: "genome start end" lines>]]
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -53,5 +53,14 @@ int main(int argc, char** argv) {
             xi.cmum_off.push_back((int64_t)xi.cmum_idx.size());
         }
     }
-    return pb200::write_xmfa(xi, argv[3]) ? 0 : 4;
+    if (argc > 4) { xi.outdir = argv[4]; xi.recombfilter = ini.get_b("LCB", "recombfilter"); }
+    if (!pb200::write_xmfa(xi, argv[3])) return 4;
+    if (argc > 5) {
+        ifstream uf(argv[5]);
+        vector<int32_t> ug; vector<int64_t> us, ue;
+        long a, b, c;
+        while (uf >> a >> b >> c) { ug.push_back((int32_t)a); us.push_back(b); ue.push_back(c); }
+        if (!pb200::write_unaligned(xi, ug, us, ue, string(argv[4]) + "/parsnp.unalign")) return 5;
+    }
+    return 0;
 }

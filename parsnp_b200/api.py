@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libparsnp_b200.so")
 
 FLAG_TRACE_WINDOWS = 1
 FLAG_NO_SPECULATION = 2
+FLAG_UNALIGNED = 4
 
 
 class Pb200Error(RuntimeError):
@@ -138,6 +139,8 @@ def _decl_result_api(lib):
     lib.pb200_result_num_clusters.argtypes = [vp]
     lib.pb200_result_num_clusters.restype = C.c_int64
     lib.pb200_result_clusters.argtypes = [vp] + [vp] * 5
+    lib.pb200_result_unaligned.argtypes = [vp, vp, vp, vp]
+    lib.pb200_result_unaligned.restype = C.c_int64
     lib.pb200_result_num_trace.argtypes = [vp]
     lib.pb200_result_num_trace.restype = C.c_int64
     lib.pb200_result_trace.argtypes = [vp, vp]
@@ -196,13 +199,17 @@ def unpack_result(lib, h):
     tr = np.zeros((T, 2), np.int64)
     if T:
         lib.pb200_result_trace(h, _ptr(tr))
+    U = lib.pb200_result_unaligned(h, None, None, None)
+    ug = np.zeros(U, np.int32); us = np.zeros(U, np.int64); ue = np.zeros(U, np.int64)
+    if U:
+        lib.pb200_result_unaligned(h, _ptr(ug), _ptr(us), _ptr(ue))
     names = lib.pb200_stats_names().decode().split(",")
     sv = np.zeros(len(names), np.float64)
     lib.pb200_result_stats(h, _ptr(sv), len(names))
     del owner                      # the views hold the remaining references
     return dict(n=n, mum_length=length, mum_slength=slength, mum_start=start, mum_end=end, mum_fwd=fwd,
                 cluster_type=ctype, cluster_nmums=cn, cluster_length=cl, cluster_start=cs, cluster_end=ce,
-                trace=tr, stats=dict(zip(names, sv.tolist())))
+                trace=tr, unaligned=np.stack([ug.astype(np.int64), us, ue], axis=1), stats=dict(zip(names, sv.tolist())))
 
 
 def _seq_arrays(genomes):

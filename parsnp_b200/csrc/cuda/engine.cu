@@ -620,7 +620,7 @@ int pb200_align_resident(pb200_genomes* g, const pb200_params* prm, pb200_result
             tp[1] = pb200::wall_s();
             ok = a.run();
             tp[2] = pb200::wall_s();
-            *out = pb200::make_result(a);
+            *out = pb200::make_result(a, (prm->flags & PB200_FLAG_UNALIGNED) != 0);
             tp[3] = pb200::wall_s();
         }
         tp[4] = pb200::wall_s();

@@ -1238,6 +1238,43 @@ void Aligner::set_inter_cluster_regions(std::vector<ClusterRec>& cl) {
     cl.insert(cl.begin(), inter.begin(), inter.end());
 }
 
+// ------------------------------------------------------------------ setUnalignableRegions (src/parsnp.cpp:2310-2382)
+// The reference walks mumlayout bit by bit, round-robin over the genomes: in every round each genome contributes its next run
+// of clear bits [startpos, endpos] (setting them on the way); a record is written when startpos != endpos (a single clear
+// bit is skipped), and the walk stops the first time the LAST genome has no run left - whatever the others still hold.
+// Restated with word-level scans on the final layout (runs are found, not set: every round resumes behind its last run).
+void Aligner::unaligned_regions(std::vector<int32_t>& genome, std::vector<int64_t>& start, std::vector<int64_t>& end) const {
+    genome.clear(); start.clear(); end.clear();
+    std::vector<int64_t> lastpos((size_t)n_, 0);
+    std::vector<uint8_t> exhausted((size_t)n_, 0);           // a trailing run without a closing set bit is re-scanned as all ones
+    for (bool stop = false; !stop;) {
+        for (int k = 0; k < n_; ++k) {
+            const BitRow& row = truth_.layout[k];
+            const int64_t size = len_[k] + 1;                // mumlayout[k].size(), bit len_[k] is the sentinel
+            int64_t startpos = -1, endpos = -1;
+            if (!exhausted[k]) {
+                // first clear bit at or after lastpos
+                int64_t m = lastpos[k];
+                while (m < size && row.get(m)) {
+                    const int64_t r = row.run_up(m, size);
+                    m += r ? r : 1;
+                }
+                if (m < size) {
+                    startpos = m;
+                    const int64_t nx = row.next_set(m, size);    // first set bit behind the run (size: none)
+                    endpos = nx - 1;
+                    if (nx < size) lastpos[k] = endpos + 1;
+                    else exhausted[k] = 1;                        // (cannot happen: the sentinel closes every run)
+                } else {
+                    exhausted[k] = 1;
+                }
+            }
+            if (startpos != endpos) { genome.push_back(k); start.push_back(startpos); end.push_back(endpos); }
+            else if (startpos == -1 && k == n_ - 1) stop = true;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ main sequence (src/parsnp.cpp:3187-3273)
 bool Aligner::run() {
     double t0 = now_s();

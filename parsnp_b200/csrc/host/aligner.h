@@ -125,6 +125,8 @@ public:
     const uint8_t* mum_fwd(int64_t i) const { return &mum_fwd_[mums_[final_mums_[i]].off]; }
     const std::vector<ClusterRec>& clusters() const { return clusters_; }
     const AlignStats& stats() const { return stats_; }
+    // Aligner::setUnalignableRegions (src/parsnp.cpp:2310-2382): (genome, startpos, endpos) records in the reference's order
+    void unaligned_regions(std::vector<int32_t>& genome, std::vector<int64_t>& start, std::vector<int64_t>& end) const;
     // sequence of searched windows in exact reference order (ref_start, ref_len) - for order tests
     const std::vector<std::pair<int64_t, int64_t>>& window_trace() const { return trace_; }
     void enable_trace(bool on) { trace_on_ = on; }

@@ -8,7 +8,7 @@
 namespace pb200 {
 thread_local std::string g_last_error;
 
-pb200_result* make_result(const Aligner& a) {
+pb200_result* make_result(const Aligner& a, bool unaligned) {
     pb200_result* r = new pb200_result;
     const int n = a.n();
     r->n = n;
@@ -33,6 +33,7 @@ pb200_result* make_result(const Aligner& a) {
         r->c_end.insert(r->c_end.end(), c.end.begin(), c.end.end());
     }
     for (auto& p : a.window_trace()) { r->trace.push_back(p.first); r->trace.push_back(p.second); }
+    if (unaligned) a.unaligned_regions(r->u_genome, r->u_start, r->u_end);
     const AlignStats& s = a.stats();
     r->stats = { (double)s.anchors, (double)s.regions_searched, (double)s.spec_regions, (double)s.replay_misses,
                  (double)s.spec_levels, (double)s.windows_searched, (double)s.candidates, (double)s.slow_queue_iters,
@@ -103,6 +104,12 @@ int pb200_result_cluster_mums(const pb200_result* r, int64_t* off, int64_t* idx)
     if (off) std::memcpy(off, r->c_mum_off.data(), r->c_mum_off.size() * 8);
     if (idx) std::memcpy(idx, r->c_mum_idx.data(), r->c_mum_idx.size() * 8);
     return (int)r->c_mum_idx.size();
+}
+int64_t pb200_result_unaligned(const pb200_result* r, int32_t* genome, int64_t* start, int64_t* end) {
+    if (genome) std::memcpy(genome, r->u_genome.data(), r->u_genome.size() * 4);
+    if (start) std::memcpy(start, r->u_start.data(), r->u_start.size() * 8);
+    if (end) std::memcpy(end, r->u_end.data(), r->u_end.size() * 8);
+    return (int64_t)r->u_genome.size();
 }
 int64_t pb200_result_num_trace(const pb200_result* r) { return (int64_t)r->trace.size() / 2; }
 int pb200_result_trace(const pb200_result* r, int64_t* pairs) { std::memcpy(pairs, r->trace.data(), r->trace.size() * 8); return 0; }

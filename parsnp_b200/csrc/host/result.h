@@ -13,13 +13,15 @@ struct pb200_result {
     std::vector<int32_t> c_type;
     std::vector<int64_t> c_nmums, c_length, c_start, c_end;
     std::vector<int64_t> c_mum_off, c_mum_idx;      // MUM indices (into the MUM list) of every cluster
+    std::vector<int32_t> u_genome;                  // unaligned regions (PB200_FLAG_UNALIGNED)
+    std::vector<int64_t> u_start, u_end;
     std::vector<int64_t> trace;
     std::vector<double> stats;
 };
 
 namespace pb200 {
 extern thread_local std::string g_last_error;
-pb200_result* make_result(const Aligner& a);
+pb200_result* make_result(const Aligner& a, bool unaligned = false);
 AlignParams to_align_params(const pb200_params* p);
 int default_host_threads();      // PB200_HOST_THREADS, else min(32, cores / local ranks)
 }

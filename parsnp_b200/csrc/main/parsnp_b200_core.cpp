@@ -4,7 +4,8 @@
 // missing ini / reference).  calcmumi=1 -> <outdir>/all.mumi;  otherwise the MUM + LCB path -> <outdir>/parsnpAligner.xmfa
 // (inter-MUM regions aligned with the reference's vendored libMUSCLE, linked unchanged), <outdir>/parsnpAligner.log
 // (MUMS FOUND / NO MUMS FOUND, then the statistics block the Python driver parses, parsnp:1530-1536) and
-// <outdir>/parsnpAligner.mums (MUM and LCB coordinates).  Not implemented: recombfilter=1 (blocks/), unaligned=1.
+// <outdir>/parsnpAligner.mums (MUM and LCB coordinates); recombfilter=1 -> <outdir>/blocks/b<k>/seq.fna (src/parsnp.cpp:538-543,
+// 958-963); unaligned=1 -> <outdir>/parsnp.unalign (Aligner::setUnalignableRegions, src/parsnp.cpp:2310-2382).
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -51,6 +52,8 @@ int main(int argc, char** argv) {
     prm.anchors_only = ini.get_b("MUM", "anchorsonly");
     prm.filter = ini.get_i("MUM", "filter");
     const bool calc_mumi = ini.get_b("MUM", "calcmumi");
+    const bool recomb_filter = ini.get_b("LCB", "recombfilter"), do_unalign = ini.get_b("LCB", "unaligned");
+    if (do_unalign) prm.flags |= PB200_FLAG_UNALIGNED;
     const string outdir = ini.get("Output", "outdir", "output");
     const bool reverse_ref = ini.get_b("Reference", "reverse");
     const int qfiles = (int)ini.num_values("Query") / 2;
@@ -156,6 +159,8 @@ int main(int argc, char** argv) {
         xi.doalign = ini.get_i("LCB", "doalign");
         xi.cores = max(1, ini.get_i("LCB", "cores"));
         if (xi.cores > 64) xi.cores = 64;                   // libMUSCLE thread-local storage holds 64 slots (threadstorage.h)
+        xi.recombfilter = recomb_filter;
+        xi.outdir = outdir;
         xi.ctype = ctype; xi.cstart = cst; xi.cend = cen;
         xi.cmum_off.resize(K + 1);
         const int tot = pb200_result_cluster_mums(res, nullptr, nullptr);
@@ -164,6 +169,12 @@ int main(int argc, char** argv) {
         xi.mlen = mlen; xi.mstart = mst; xi.mend = men; xi.mfwd = mfw;
         if (!pb200::muscle_available()) cerr << "parsnp_b200_core: built without libMUSCLE - no XMFA written" << endl;
         else if (!pb200::write_xmfa(xi, outdir + "/parsnpAligner.xmfa")) { cerr << "parsnp_b200_core: XMFA writer failed" << endl; return 1; }
+        if (do_unalign) {                                   // src/parsnp.cpp:3283-3287
+            const int64_t U = pb200_result_unaligned(res, nullptr, nullptr, nullptr);
+            vector<int32_t> ug((size_t)U); vector<int64_t> us((size_t)U), ue((size_t)U);
+            pb200_result_unaligned(res, ug.data(), us.data(), ue.data());
+            if (!pb200::write_unaligned(xi, ug, us, ue, outdir + "/parsnp.unalign")) { cerr << "parsnp_b200_core: cannot write parsnp.unalign" << endl; return 1; }
+        }
     }
     // statistics block of parsnpAligner.log (src/parsnp.cpp:1082-1190); elapsed-time lines carry this run's own timings
     {

@@ -1,4 +1,7 @@
 #include "xmfa.h"
+#include <sstream>
+#include <sys/stat.h>
+#include <sys/types.h>
 #include <algorithm>
 #include <cstdio>
 #include <fstream>
@@ -100,6 +103,15 @@ bool write_xmfa(const XmfaInput& in, const std::string& path) {
     }
     if (muscle_failed) return false;
 
+    // ---- recombfilter: blocks/ and one directory per LCB that has MUMs (src/parsnp.cpp:538-543, 605-644)
+    const std::string lcbprefix = in.outdir + "/blocks/b";
+    if (in.recombfilter) {
+        ::mkdir((in.outdir + "/blocks/").c_str(), 0777);
+        for (int64_t z = 0; z < K; z++) {
+            if (!(in.ctype[z] == 1 && in.cmum_off[z + 1] > in.cmum_off[z] && in.doalign != 0)) continue;
+            ::mkdir((lcbprefix + std::to_string(z + 1)).c_str(), 0777);
+        }
+    }
     // ---- XMFA (src/parsnp.cpp:586-598, 921-1071)
     std::ofstream x(path.c_str());
     long total_clusters = 0;
@@ -137,11 +149,14 @@ bool write_xmfa(const XmfaInput& in, const std::string& path) {
         if (!(T[0].size() > (size_t)in.c)) continue;
         char b[16];
         snprintf(b, sizeof b, "%d", (int)z + 1);
+        std::ofstream clcb;                                  // the LCB's own copy (records only, no "=" line; src/parsnp.cpp:958-963)
+        if (in.recombfilter) clcb.open((lcbprefix + b + "/seq.fna").c_str());
         for (int i = 0; i < n; i++) {
             const std::string& s1s = T[i];
             const bool fwd = MF(first, i);
-            if (fwd) x << "> " << i + 1 << ":" << cs[i] + 1 << "-" << ce[i] << " ";
-            else x << "> " << i + 1 << ":" << MS(last, i) + 1 << "-" << ME(first, i) << " ";
+            std::ostringstream rec;
+            if (fwd) rec << "> " << i + 1 << ":" << cs[i] + 1 << "-" << ce[i] << " ";
+            else rec << "> " << i + 1 << ":" << MS(last, i) + 1 << "-" << ME(first, i) << " ";
             bool hit1 = false, hit2 = false;
             std::string hdr1, lasthdr1;
             int seqstart = 0, laststart = 0;
@@ -154,14 +169,36 @@ bool write_xmfa(const XmfaInput& in, const std::string& path) {
             int offset = 0;
             if (hdr1 == "") { hdr1 = "s1"; offset = -1; }
             else if (hdr1 != "s1") offset = -1;
-            if (!fwd) x << "- cluster" << b << " " << hdr1 << ":p" << (cs[i] - seqstart) + 1 + in.mlen[first] + offset << std::endl;
-            else x << "+ cluster" << b << " " << hdr1 << ":p" << (cs[i] - seqstart) + 1 + offset << std::endl;
+            if (!fwd) rec << "- cluster" << b << " " << hdr1 << ":p" << (cs[i] - seqstart) + 1 + in.mlen[first] + offset << "\n";
+            else rec << "+ cluster" << b << " " << hdr1 << ":p" << (cs[i] - seqstart) + 1 + offset << "\n";
             const size_t width = 80;
             size_t k = 0;
-            for (; k + width < s1s.size(); k += width) x << s1s.substr(k, width) << std::endl;
-            x << s1s.substr(k, s1s.size() - k) << std::endl;
+            for (; k + width < s1s.size(); k += width) rec << s1s.substr(k, width) << "\n";
+            rec << s1s.substr(k, s1s.size() - k) << "\n";
+            x << rec.str();
+            if (in.recombfilter) clcb << rec.str();
         }
         x << "=" << std::endl;
+    }
+    return true;
+}
+
+bool write_unaligned(const XmfaInput& in, const std::vector<int32_t>& genome, const std::vector<int64_t>& start,
+                     const std::vector<int64_t>& end, const std::string& path) {
+    std::ofstream u(path.c_str());
+    if (!u) return false;
+    for (size_t r = 0; r < genome.size(); r++) {
+        const int k = genome[r];
+        const int64_t startpos = start[r], endpos = end[r];
+        u << ">" << k + 1 << ":" << startpos << "-" << endpos << " + " << in.fasta_names[(size_t)k] << "\n";
+        const std::string& g = *in.genomes[(size_t)k];
+        const std::string s1 = (startpos >= 0 && (size_t)startpos <= g.size()) ? g.substr((size_t)startpos, (size_t)std::max<int64_t>(0, endpos - startpos))
+                                                                                : std::string();
+        size_t pos = 0;
+        while (pos + 80 < s1.size()) { u << s1.substr(pos, 80) << "\n"; pos += 80; }
+        if (pos + 1 < s1.size()) u << s1.substr(pos, s1.size()) << "\n";       // (a last line of exactly one base is dropped, src/parsnp.cpp:2366)
+        if (s1.size() == 0) u << "-" << "\n";
+        u << "=" << "\n";
     }
     return true;
 }

@@ -16,6 +16,8 @@ struct XmfaInput {
     std::vector<int64_t> genome_sizes;                   // text size minus contig padding
     std::vector<std::map<int, std::string>> pos2hdr;     // contig start -> "s<k>"
     int c = 21, doalign = 2, cores = 1;
+    bool recombfilter = false;                           // ini [LCB] recombfilter: every LCB also goes to <outdir>/blocks/b<k>/seq.fna
+    std::string outdir;                                  // (only used for blocks/)
     // clusters in this->clusters order
     std::vector<int32_t> ctype;
     std::vector<int64_t> cstart, cend;                   // [K*n]
@@ -31,5 +33,9 @@ bool muscle_available();
 
 // returns false when libMUSCLE is not linked
 bool write_xmfa(const XmfaInput& in, const std::string& path);
+
+// parsnp.unalign (Aligner::setUnalignableRegions, src/parsnp.cpp:2310-2382) from the records of pb200_result_unaligned
+bool write_unaligned(const XmfaInput& in, const std::vector<int32_t>& genome, const std::vector<int64_t>& start,
+                     const std::vector<int64_t>& end, const std::string& path);
 
 }  // namespace pb200

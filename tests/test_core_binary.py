@@ -114,6 +114,78 @@ def test_xmfa_writer_matches_reference_bytes(tmp_path, kind):
         assert hashlib.md5(open(mine, "rb").read()).hexdigest() == "5b59e50c5b8c1f79165fc41cfd2a6ac4"
 
 
+def _tree(root):
+    """{relative path: bytes} of every file below root"""
+    out = {}
+    for base, _, files in os.walk(root):
+        for f in files:
+            p = os.path.join(base, f)
+            out[os.path.relpath(p, root)] = open(p, "rb").read()
+    return out
+
+
+@pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(XTOOL)), reason="oracle/_ref tools not built")
+@pytest.mark.parametrize("kind", ["c1a", "rearr"])
+def test_recombfilter_blocks_match_reference(tmp_path, kind):
+    """ini recombfilter=1: <outdir>/blocks/b<k>/seq.fna (one directory per LCB, src/parsnp.cpp:538-543, 605-644, 958-963) from
+    the product's writer == the reference's, file for file"""
+    if kind == "c1a":
+        ref, qs = os.path.join(GOLDEN, "mers", "England1.fna"), [os.path.join(GOLDEN, "mers", q + ".fna") for q in C1A]
+    else:
+        ref, qs = _synthetic(tmp_path, kind)
+    r, dump, xmfa, ini = _ref_run(tmp_path, ref, qs, recombfilter=1)
+    want = _tree(os.path.join(r["outdir"], "blocks"))
+    assert len(want) >= 2
+    mine = tmp_path / "mine"
+    mine.mkdir()
+    rc = subprocess.run([XTOOL, ini, dump, str(mine / "parsnpAligner.xmfa"), str(mine)]).returncode
+    assert rc == 0
+    assert (mine / "parsnpAligner.xmfa").read_bytes() == open(xmfa, "rb").read()
+    assert _tree(str(mine / "blocks")) == want
+    assert sorted(os.listdir(str(mine / "blocks"))) == sorted(os.listdir(os.path.join(r["outdir"], "blocks")))
+
+
+@pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(XTOOL)), reason="oracle/_ref tools not built")
+@pytest.mark.parametrize("kind", ["c1a", "rearr", "contigs"])
+def test_unaligned_regions_match_reference(tmp_path, kind):
+    """ini unaligned=1: parsnp.unalign (Aligner::setUnalignableRegions, src/parsnp.cpp:2310-2382) - the records come from the
+    product's host orchestrator (final mumlayout; search by the reference's csgmum on the CPU), the file from its writer"""
+    from oracle import hosttest
+    from parsnp_b200 import api
+    if kind == "c1a":
+        ref, qs = os.path.join(GOLDEN, "mers", "England1.fna"), [os.path.join(GOLDEN, "mers", q + ".fna") for q in C1A]
+    else:
+        ref, qs = _synthetic(tmp_path, kind)
+    r, dump, xmfa, ini = _ref_run(tmp_path, ref, qs, unaligned=1)
+    want = open(os.path.join(r["outdir"], "parsnp.unalign"), "rb").read()
+    assert len(want) > 100
+    g = [api.ingest_fasta(ref, True)] + [api.ingest_fasta(q, False) for q in qs]
+    res = hosttest.align(g, api.make_params(flags=api.FLAG_UNALIGNED), backend=1)
+    rec = tmp_path / "unaligned.txt"
+    rec.write_text("".join("%d %d %d\n" % tuple(x) for x in res["unaligned"].tolist()))
+    mine = tmp_path / "mine"
+    mine.mkdir()
+    rc = subprocess.run([XTOOL, ini, dump, str(mine / "parsnpAligner.xmfa"), str(mine), str(rec)]).returncode
+    assert rc == 0
+    assert (mine / "parsnp.unalign").read_bytes() == want
+
+
+@pytest.mark.gpu
+def test_binary_blocks_and_unaligned_end_to_end(tmp_path):
+    """parsnp_b200_core with recombfilter=1 and unaligned=1 on the GPU == parsnp_core: XMFA, blocks/ tree, parsnp.unalign"""
+    from oracle import runner
+    ref, qs = _synthetic(tmp_path, "rearr")
+    r, dump, xmfa, _ = _ref_run(tmp_path, ref, qs, recombfilter=1, unaligned=1)
+    out = tmp_path / "mine"
+    out.mkdir()
+    ini = runner.write_ini(str(tmp_path / "mine.ini"), ref, qs, str(out), cores=4, recombfilter=1, unaligned=1)
+    p = subprocess.run([EXE, ini], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=str(tmp_path))
+    assert p.returncode == 0, p.stderr
+    assert (out / "parsnpAligner.xmfa").read_bytes() == open(xmfa, "rb").read()
+    assert _tree(str(out / "blocks")) == _tree(os.path.join(r["outdir"], "blocks"))
+    assert (out / "parsnp.unalign").read_bytes() == open(os.path.join(r["outdir"], "parsnp.unalign"), "rb").read()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind", ["c1a", "rearr", "contigs"])
 def test_binary_xmfa_end_to_end(tmp_path, kind):
