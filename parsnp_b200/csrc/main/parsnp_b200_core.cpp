@@ -15,6 +15,8 @@
 #include <iostream>
 #include <string>
 #include <vector>
+#include <sys/stat.h>
+#include <sys/types.h>
 #include "../../../include/parsnp_b200.h"
 #include "../host/ingest.h"
 #include "xmfa.h"
@@ -103,6 +105,13 @@ int main(int argc, char** argv) {
         return 0;
     }
 
+    {   // src/parsnp.cpp:3166-3168, 521-537: an output directory that does not exist is created (one level, like `mkdir <outdir>`)
+        struct stat sb;
+        if (stat(outdir.c_str(), &sb) != 0 && mkdir(outdir.c_str(), 0777) != 0) {
+            cerr << "ParSNP:: error creating output directory, exiting.." << endl;
+            return 1;
+        }
+    }
     cerr << "Searching for initial MUM anchors..." << endl;
     pb200_result* res = nullptr;
     rc = pb200_align_resident(dev, &prm, &res);
