@@ -1035,6 +1035,7 @@ void Aligner::filter_random1() {
         if (!adjacent) {
             for (int k = 0; k < n_; ++k) truth_.layout[k].clear_range(mts[k], mts[k] + mt.length);
             mums_[final_mums_[ms]].alive = false;
+            stats_.mums_filtered++;
             final_mums_.erase(final_mums_.begin() + ms);
             ms -= 1;               // size_t wrap + ++ms == stay, like the reference's ulong msize
             numums -= 1;
@@ -1196,6 +1197,8 @@ void Aligner::filter_clusters_simple(std::vector<ClusterRec>& cl) {
     if (num == 0) return;
     for (size_t cs = 0; cs + 1 < num;) {
         if (cl[cs].length <= prm_.c) {
+            stats_.clusters_filtered++;
+            stats_.mums_filtered += (int64_t)cl[cs].mums.size();
             for (int mi : cl[cs].mums) {
                 MumRec& m = mums_[final_mums_[mi]];
                 for (int k = 0; k < n_; ++k) truth_.layout[k].clear_range(mum_start_[m.off + k], mum_start_[m.off + k] + m.length);

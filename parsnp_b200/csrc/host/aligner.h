@@ -107,6 +107,7 @@ struct AlignStats {
     double t_search_prep = 0, t_search_backend = 0, t_search_cache = 0;   // split of the search_regions calls (all phases)
     double t_replay_wait = 0;        // replay blocked on a speculation slice still in flight
     int64_t spec_slices = 0;
+    int64_t mums_filtered = 0, clusters_filtered = 0;      // Aligner::filtered / filtered_clusters (src/parsnp.cpp:406,451,460)
 };
 
 class Aligner {

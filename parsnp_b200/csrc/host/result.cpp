@@ -39,7 +39,7 @@ pb200_result* make_result(const Aligner& a, bool unaligned) {
                  (double)s.spec_levels, (double)s.windows_searched, (double)s.candidates, (double)s.slow_queue_iters,
                  s.t_anchor_search, s.t_anchor_host, s.t_spec_search, s.t_spec_host, s.t_replay, s.t_replay_search,
                  s.t_lcb, s.t_total, (double)s.host_threads, s.t_search_prep, s.t_search_backend, s.t_search_cache, s.t_replay_wait,
-                 (double)s.spec_slices };
+                 (double)s.spec_slices, (double)s.mums_filtered, (double)s.clusters_filtered };
     return r;
 }
 
@@ -120,7 +120,7 @@ int pb200_result_stats(const pb200_result* r, double* values, int cap) {
 }
 const char* pb200_stats_names(void) {
     return "anchors,regions_searched,spec_regions,replay_misses,spec_levels,windows_searched,candidates,slow_queue_iters,"
-           "t_anchor_search,t_anchor_host,t_spec_search,t_spec_host,t_replay,t_replay_search,t_lcb,t_total,host_threads,t_search_prep,t_search_backend,t_search_cache,t_replay_wait,spec_slices";
+           "t_anchor_search,t_anchor_host,t_spec_search,t_spec_host,t_replay,t_replay_search,t_lcb,t_total,host_threads,t_search_prep,t_search_backend,t_search_cache,t_replay_wait,spec_slices,mums_filtered,clusters_filtered";
 }
 void pb200_result_free(pb200_result* r) { delete r; }
 int pb200_minsize(const char* expr, int64_t slength) { return pb200::MinSizeExpr(expr)(slength); }

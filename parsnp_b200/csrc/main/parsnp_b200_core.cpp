@@ -185,8 +185,24 @@ int main(int argc, char** argv) {
             if (!pb200::write_unaligned(xi, ug, us, ue, outdir + "/parsnp.unalign")) { cerr << "parsnp_b200_core: cannot write parsnp.unalign" << endl; return 1; }
         }
     }
-    // statistics block of parsnpAligner.log (src/parsnp.cpp:1082-1190); elapsed-time lines carry this run's own timings
+    // statistics block of parsnpAligner.log (src/parsnp.cpp:1082-1190), line for line; the elapsed-time lines carry this run's
+    // own timings (the reference's have a resolution of one second)
     {
+        // named statistics of the result
+        vector<double> sv(64, 0.0);
+        const int nsv = pb200_result_stats(res, sv.data(), 64);
+        auto stat = [&](const char* name) -> double {
+            const string names = pb200_stats_names();
+            size_t pos = 0; int idx = 0;
+            while (pos <= names.size()) {
+                size_t e = names.find(',', pos);
+                if (e == string::npos) e = names.size();
+                if (names.compare(pos, e - pos, name) == 0) return idx < nsv ? sv[idx] : 0.0;
+                pos = e + 1; idx++;
+            }
+            return 0.0;
+        };
+        const long filtered = (long)stat("mums_filtered"), filtered_clusters = (long)stat("clusters_filtered");
         ofstream log(logpath.c_str());
         log << "Number of sequences analyzed:" << setiosflags(ios::fixed) << setprecision(1) << setw(10) << n << endl << endl;
         for (int i = 0; i < n; i++) {
@@ -202,27 +218,35 @@ int main(int argc, char** argv) {
         for (auto& g : G) slength = min<int64_t>(slength, (int64_t)g.text.size());
         log << setw(2) << "Mum anchor size:   " << setw(2) << (float)pb200_minsize(prm.anchors, slength) << endl;
         log << setw(2) << "Number of MUM anchors found:   " << setw(2) << anchors_found << endl;
-        log << setw(2) << "Number of MUMs found:   " << setw(2) << (M >= anchors_found ? M - anchors_found : 0) << endl;
+        if (M + filtered >= anchors_found) log << setw(2) << "Number of MUMs found:   " << setw(2) << (M + filtered) - anchors_found << endl;
+        else log << setw(2) << "Number of MUMs found:   " << setw(2) << 0 << endl;
         log << setw(2) << "Total MUMs found((Anchors+MUMs)-filtered):   " << setw(2) << M << endl << endl;
         log << setw(2) << "Random MUM length:   " << setw(2) << prm.filter << endl;
         log << setw(2) << "Minimum Cluster length:   " << setw(2) << prm.c << endl;
+        log << setw(2) << "Number of MUMs filtered:   " << setw(2) << filtered << endl;
+        log << setw(2) << "Number of Clusters filtered:   " << setw(2) << filtered_clusters << endl << endl;
         long ccount = 0;
         for (int64_t i = 0; i < K; i++) if (ctype[i] && cnm[i] > 0) ccount++;
         log << setw(2) << "Number of clusters created:   " << setw(2) << ccount << endl;
         if (K == 0) log << setw(2) << "Number of clusters created:   " << setw(2) << "NONE" << endl;
-        if (ccount) log << setw(2) << "Average number of MUMs per cluster:   " << setw(2) << M / ccount << endl;
-        // LCB coverage per sequence: |last MUM end - first MUM start| summed over LCBs (forward) as at src/parsnp.cpp:1141-1160;
-        // the flat result keeps per-LCB start/end, which equal first-MUM start / last-MUM end
+        if (ccount) log << setw(2) << "Average number of MUMs per cluster:   " << setw(2) << M / ccount << endl;     // (the reference divides by zero here)
+        // LCB coverage per sequence (src/parsnp.cpp:1141-1160): |last MUM end - first MUM start| of every LCB, per strand
+        vector<int64_t> cmoff((size_t)K + 1);
+        const int tot = pb200_result_cluster_mums(res, nullptr, nullptr);
+        vector<int64_t> cmidx((size_t)max(tot, 1));
+        pb200_result_cluster_mums(res, cmoff.data(), cmidx.data());
         vector<long> coverage(n, 0);
         long avg = 0, totcoverage = 0, totsize = 0;
-        for (int64_t c = 0; c < K; c++) {
-            if (!ctype[c] || cnm[c] <= 0) continue;
-            for (int i = 0; i < n; i++) {
-                long span = labs((long)(cen[c * n + i] - cst[c * n + i]));
+        for (int i = 0; i < n; i++)
+            for (int64_t c = 0; c < K; c++) {
+                if (!ctype[c] || cmoff[c + 1] <= cmoff[c]) continue;
+                const int64_t front = cmidx[cmoff[c]], back = cmidx[cmoff[c + 1] - 1];
+                long span;
+                if (mfw[front * n + i]) span = labs((long)((mst[back * n + i] + mlen[back]) - mst[front * n + i]));
+                else span = labs((long)((mst[front * n + i] + mlen[front]) - mst[back * n + i]));
                 coverage[i] += span;
                 if (i == 0) avg += span;
             }
-        }
         if (ccount) log << setw(2) << "Average cluster length:   " << avg / ccount << " bps" << endl;
         for (int i = 0; i < n; i++) {
             float percent = (float)coverage[i] / ((float)(G[i].g + G[i].c) + (float)(G[i].a + G[i].t));
@@ -232,7 +256,13 @@ int main(int argc, char** argv) {
         }
         float percent = (float)totcoverage / (float)totsize;
         log << setw(2) << "Total coverage among all sequences:   " << setiosflags(ios::fixed) << setprecision(1) << 100.00 * percent << "%" << endl << endl;
-        log << setw(2) << " Total running time:   " << (ns > 15 ? stats[15] : 0.0) << "s " << endl;
+        const double t_anchor = stat("t_anchor_search") + stat("t_anchor_host"), t_coarsen = stat("t_replay"), t_lcb = stat("t_lcb");
+        log << setw(2) << " MUM anchor search elapsed time:   " << t_anchor << "s " << endl;
+        log << setw(2) << " MUM coarsening elapsed time:   " << t_coarsen << "s " << endl;
+        if (prm.filter) log << setw(2) << " MUM filtering elapsed time:   " << 0.0 << "s " << endl;
+        log << setw(2) << " MUM clustering elapsed time:   " << t_lcb << "s " << endl;
+        log << setw(2) << " Inter-clustering elapsed time:   " << 0.0 << "s " << endl;
+        log << setw(2) << " Total running time:   " << stat("t_total") << "s " << endl;
     }
     pb200_result_free(res);
     pb200_genomes_free(dev);

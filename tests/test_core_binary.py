@@ -114,6 +114,19 @@ def test_xmfa_writer_matches_reference_bytes(tmp_path, kind):
         assert hashlib.md5(open(mine, "rb").read()).hexdigest() == "5b59e50c5b8c1f79165fc41cfd2a6ac4"
 
 
+def _log_lines(path, own_paths=False):
+    """parsnpAligner.log, comparable: elapsed-time values dropped (the reference's have 1 s resolution, ours are the run's own),
+    `Sequence i : <path>` reduced to the file name"""
+    out = []
+    for ln in open(path).read().splitlines():
+        if "elapsed time:" in ln or "running time:" in ln:
+            ln = ln.split(":")[0]
+        if ln.startswith("Sequence ") and " : " in ln:
+            ln = ln.split(" : ")[0] + " : " + os.path.basename(ln.split(" : ")[1])
+        out.append(ln)
+    return out
+
+
 def _tree(root):
     """{relative path: bytes} of every file below root"""
     out = {}
@@ -182,8 +195,10 @@ def test_binary_blocks_and_unaligned_end_to_end(tmp_path):
     p = subprocess.run([EXE, ini], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=str(tmp_path))
     assert p.returncode == 0, p.stderr
     assert (out / "parsnpAligner.xmfa").read_bytes() == open(xmfa, "rb").read()
+    # the statistics log the Python driver parses (parsnp:1530-1536), line for line
     assert _tree(str(out / "blocks")) == _tree(os.path.join(r["outdir"], "blocks"))
     assert (out / "parsnp.unalign").read_bytes() == open(os.path.join(r["outdir"], "parsnp.unalign"), "rb").read()
+    assert _log_lines(str(out / "parsnpAligner.log")) == _log_lines(os.path.join(r["outdir"], "parsnpAligner.log"))
 
 
 @pytest.mark.gpu
@@ -202,3 +217,5 @@ def test_binary_xmfa_end_to_end(tmp_path, kind):
     p = subprocess.run([EXE, ini], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=str(tmp_path))
     assert p.returncode == 0, p.stderr
     assert (out / "parsnpAligner.xmfa").read_bytes() == open(xmfa, "rb").read()
+    # the statistics log the Python driver parses (parsnp:1530-1536), line for line
+    assert _log_lines(str(out / "parsnpAligner.log")) == _log_lines(os.path.join(r["outdir"], "parsnpAligner.log"))
