@@ -128,9 +128,6 @@ int RegionPool::add(const int64_t* start, const int64_t* end) {
     slen.push_back(sl);
     return id;
 }
-bool Aligner::region_equal(int a, int b) const {        // operator==, src/LCR.cpp:48-58
-    return std::memcmp(rstart(a), rstart(b), sizeof(int64_t) * 2 * n_) == 0;
-}
 uint64_t Aligner::coords_hash(const int64_t* p, int count) {
     // start and end of the first and the last genome: regions equal there and different elsewhere are rare and the table's
     // equality callback compares all coordinates

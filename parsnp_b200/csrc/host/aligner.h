@@ -140,7 +140,6 @@ public:
 private:
     inline const int64_t* rstart(int r) const { return rp_.start(r); }
     inline const int64_t* rend(int r) const { return rp_.end(r); }
-    bool region_equal(int a, int b) const;
     static uint64_t coords_hash(const int64_t* p, int count);
 
     struct World {                     // one copy of the mutable alignment state
