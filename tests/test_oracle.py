@@ -162,6 +162,43 @@ def test_parallel_anchor_accept_equals_serial_random(monkeypatch):
         assert np.array_equal(outs[0]["trace"], outs[1]["trace"])
 
 
+def test_small_windows_with_inversions_zero_init_reference(monkeypatch):
+    """Several reference windows small enough for the reference's per-window arrays to come from the heap (p = 5000 -> 40 kB)
+    + reverse-strand matches: `MasterRC[].UP` is never initialised (src/parsnp.cpp:1591-1597), a later
+    window's array re-uses a freed chunk and the binary's MUM count then varies with the heap contents (434 / 439 / 426 on one
+    input under MALLOC_PERTURB_ = unset / 255 / 170).  Real windows (15 Mbp -> 120 MB) are mmap'ed, i.e. zero.  The product
+    implements the zero-initialised semantics; the oracle for this corner is the reference under MALLOC_PERTURB_=255 (glibc
+    fills every allocation with ~255 = 0)."""
+    from oracle import hosttest, runner
+    from parsnp_b200 import synth
+    monkeypatch.setenv("MALLOC_PERTURB_", "255")
+    rng = np.random.default_rng(1032)
+    total_rc = 0
+    for it in range(3):
+        g = synth.g_indep(20000, 3, 0.03, 900 + it)
+        g = [g[0]] + [synth.rearrange(x, rng, n_inv=2, inv_len=1500, dels=(30,), ins=(20,)) for x in g[1:]]
+        with tempfile.TemporaryDirectory() as td:
+            ref, qs = synth.write_dataset(os.path.join(td, "d"), g)
+            r = runner.run_ref(ref, qs, os.path.join(td, "r"), p=5000)
+        res = hosttest.align(g, api.make_params(p=5000), backend=1)
+        assert diff_dumps(result_to_dump(res), r["dump"]) == []
+        total_rc += int((res["mum_fwd"] == 0).any(axis=1).sum())
+    assert total_rc > 10
+
+
+def test_host_fuzz_against_reference_binary():
+    """tools/fuzz_host.py: 25 random genome sets x ini values x speculation slicings == reference binary (zero-initialising
+    allocator, see the test above); includes poly-N windows, on which csgmum's Find_UM runs off the query buffer when a strand
+    shares no symbol with the window (the checker skips that call, oracle/ref_backend.cpp)"""
+    import subprocess
+    import sys
+    env = dict(os.environ, MALLOC_PERTURB_="255", PB200_HOST_THREADS="4")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_host.py"), "5070", "25"], env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "done 25 cases, 0 mismatches" in r.stdout, r.stdout[-2000:]
+
+
 def test_window_order_matches_reference_trace():
     """sequence of (window start, length) searched by the exact replay == the reference's setMums1 call sequence"""
     from oracle import hosttest, runner
