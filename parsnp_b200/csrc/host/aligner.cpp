@@ -945,8 +945,9 @@ void Aligner::do_work_exact() {
     stats_.t_replay += now_s() - t0;
 }
 
-// sort(this->mums) by start[0] (operator<, src/TMum.cpp:151); starts are distinct (accepted MUMs are disjoint on the
-// reference), so the order is unique.  Sorts compact (start0,id) pairs and skips the work when already sorted.
+// sort(this->mums) by start[0] (operator<, src/TMum.cpp:151).  With distinct starts (the rule: accepted MUMs are disjoint on
+// the reference) the order is unique: compact (start0,id) pairs are merged / radix-sorted and the work is skipped when already
+// sorted.  With ties the reference's own std::sort call is replayed literally (see below).
 void Aligner::sort_final_mums() {
     const size_t M = final_mums_.size();
     if (final_sorted_) return;                  // (removals keep the order; only `final_mums_ = all_mums_` resets the flag)
@@ -979,8 +980,26 @@ void Aligner::sort_final_mums() {
         maxkey = std::max(maxkey, ch_max[c]);
         final_min_length_ = std::min(final_min_length_, ch_minlen[c]);
     }
+    // ties on start[0] (two accepted MUMs starting at the same reference position: a trimmed remnant of length 2 next to a
+    // later MUM) make the order implementation-defined: the reference calls std::sort (libstdc++ introsort, unstable) with
+    // operator< on start[0] (src/TMum.cpp:151) at every one of these calls.  The same algorithm on (start0, id) records in the
+    // same initial order makes the same comparisons and moves, hence the same permutation - whatever the element type.
+    const std::vector<std::pair<int64_t, int>> original(kv);
+    auto literal_sort = [&]() {
+        kv = original;
+        std::sort(kv.begin(), kv.end(), [](const std::pair<int64_t, int>& x, const std::pair<int64_t, int>& y) { return x.first < y.first; });
+        for (size_t i = 0; i < M; ++i) final_mums_[i] = kv[i].second;
+        final_sorted_ = false;                         // the next call sorts again, like the reference
+    };
+    auto has_ties = [&]() {
+        for (size_t i = 1; i < M; ++i) if (kv[i].first == kv[i - 1].first) return true;
+        return false;
+    };
     final_sorted_ = true;
-    if (descents == 0) return;
+    if (descents == 0) {
+        if (has_ties()) literal_sort();
+        return;
+    }
     std::vector<std::pair<int64_t, int>> tmp(M);
     if (descents == 1) {
         // the usual shape: the anchors (ascending) followed by the recursion's MUMs (ascending): one merge
@@ -988,7 +1007,7 @@ void Aligner::sort_final_mums() {
                    [](const std::pair<int64_t, int>& x, const std::pair<int64_t, int>& y) { return x.first < y.first; });
         kv.swap(tmp);
     } else {
-        // LSD byte radix sort of (start0, id) pairs: keys are distinct, so the result is the unique ascending order
+        // LSD byte radix sort of (start0, id) pairs: with distinct keys the result is the unique ascending order
         for (int shift = 0; shift < 64 && (maxkey >> shift) != 0; shift += 8) {
             size_t cnt[257] = {0};
             for (size_t i = 0; i < M; ++i) cnt[((uint64_t)kv[i].first >> shift & 0xff) + 1]++;
@@ -997,6 +1016,7 @@ void Aligner::sort_final_mums() {
             kv.swap(tmp);
         }
     }
+    if (has_ties()) { literal_sort(); return; }
     for (size_t i = 0; i < M; ++i) final_mums_[i] = kv[i].second;
 }
 

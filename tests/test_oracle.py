@@ -168,10 +168,12 @@ def test_small_windows_with_inversions_zero_init_reference(monkeypatch):
     window's array re-uses a freed chunk and the binary's MUM count then varies with the heap contents (434 / 439 / 426 on one
     input under MALLOC_PERTURB_ = unset / 255 / 170).  Real windows (15 Mbp -> 120 MB) are mmap'ed, i.e. zero.  The product
     implements the zero-initialised semantics; the oracle for this corner is the reference under MALLOC_PERTURB_=255 (glibc
-    fills every allocation with ~255 = 0)."""
+    fills every allocation with ~255 = 0) with the thread cache off (tcache hits bypass the fill: arrays of <= 129 positions,
+    i.e. the small recursion windows, would keep their stale contents)."""
     from oracle import hosttest, runner
     from parsnp_b200 import synth
     monkeypatch.setenv("MALLOC_PERTURB_", "255")
+    monkeypatch.setenv("GLIBC_TUNABLES", "glibc.malloc.tcache_count=0")      # (tcache hits bypass the perturbation)
     rng = np.random.default_rng(1032)
     total_rc = 0
     for it in range(3):
@@ -192,7 +194,7 @@ def test_host_fuzz_against_reference_binary():
     shares no symbol with the window (the checker skips that call, oracle/ref_backend.cpp)"""
     import subprocess
     import sys
-    env = dict(os.environ, MALLOC_PERTURB_="255", PB200_HOST_THREADS="4")
+    env = dict(os.environ, MALLOC_PERTURB_="255", GLIBC_TUNABLES="glibc.malloc.tcache_count=0", PB200_HOST_THREADS="4")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_host.py"), "5070", "25"], env=env, stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:]

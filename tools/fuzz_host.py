@@ -1,14 +1,15 @@
 #!/usr/bin/env python3
 """CPU fuzz of the host orchestrator against the reference binary (test infrastructure, no GPU).
 
-  MALLOC_PERTURB_=255 python tools/fuzz_host.py <first seed> <cases>
+  GLIBC_TUNABLES=glibc.malloc.tcache_count=0 MALLOC_PERTURB_=255 python tools/fuzz_host.py <first seed> <cases>
 
 Random genome sets (independent / population divergence, repeats and N runs in the reference, inversions, deletions, insertions,
 whole-query reverse complements, multi-contig FASTA) x random ini values (c, d, q, diagdiff, p -> several reference windows)
 x random speculation slicing / anchor-accept mode.  Every case runs oracle/_ref/parsnp_core_ref and the product's host
 orchestrator with the reference's own csgmum as search backend (oracle/hosttest.py) and compares MUM and LCB lists bit for bit.
-MALLOC_PERTURB_=255 makes glibc zero every allocation of the reference binary: with several small reference windows and
-reverse-strand matches its result otherwise depends on stale heap contents."""
+MALLOC_PERTURB_=255 makes glibc zero every allocation of the reference binary (tcache off: its hits bypass the fill): wherever
+a reverse-strand match wins, the binary's result otherwise depends on the stale contents of the never-initialised
+MasterRC[].UP."""
 import os
 import sys
 import tempfile
