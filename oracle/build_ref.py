@@ -180,10 +180,11 @@ def main():
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--jobs", type=int, default=os.cpu_count() or 4)
     ap.add_argument("--force", action="store_true")
+    ap.add_argument("--asan", action="store_true", help="also build oracle/_ref/parsnp_core_ref_asan (AddressSanitizer, -O1) for diagnosing reference UB")
     a = ap.parse_args()
     exe = os.path.join(OUT, "parsnp_core_ref")
     lib = os.path.join(OUT, "libcsgmum_ref.so")
-    if os.path.exists(exe) and os.path.exists(lib) and not a.force:
+    if os.path.exists(exe) and os.path.exists(lib) and not a.force and not a.asan:
         print("oracle/_ref up to date")
         return 0
     if not os.path.isdir(os.path.join(a.ref, "src")):
@@ -227,6 +228,11 @@ def main():
              "-w", "-fpermissive", "-I../muscle", "-o", exe,
              "MuscleInterface.cpp", "parsnp.cpp", "LCB.cpp", "LCR.cpp", "TMum.cpp", "Converter.cpp", "ext/iniFile.cpp",
              ar, "-lpthread"], cwd=sd)
+        if a.asan:
+            run(["g++", "-fopenmp", "-O1", "-g", "-m64", "-fsanitize=address", "-fsanitize-recover=address", "-fno-omit-frame-pointer", "-w", "-fpermissive",
+                 "-I../muscle", "-o", exe + "_asan",
+                 "MuscleInterface.cpp", "parsnp.cpp", "LCB.cpp", "LCR.cpp", "TMum.cpp", "Converter.cpp", "ext/iniFile.cpp",
+                 ar, "-lpthread"], cwd=sd)
         # ---- csgmum + Converter shared library
         shim = os.path.join(sd, "_oracle_shim.cpp")
         with open(shim, "w") as f:

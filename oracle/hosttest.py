@@ -19,6 +19,8 @@ def load():
         _lib.pbtest_align.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp]
         _lib.pbtest_search_windows.argtypes = [C.c_int, C.c_int, vp, vp, C.c_int, vp, vp] + [vp] * 5
         _lib.pbtest_lrp.argtypes = [vp, C.c_int64, vp]
+        _lib.pbtest_runoff_skips.argtypes = [C.c_int]
+        _lib.pbtest_runoff_skips.restype = C.c_long
     return _lib
 
 
@@ -33,6 +35,12 @@ def align(genomes, params=None, backend=1):
     res = api.unpack_result(lib, out)
     res["no_mums"] = rc == -5
     return res
+
+
+def runoff_skips(reset=True):
+    """Find_UM calls the csgmum backend skipped since the last reset because the real function would have read past the end
+    of the query buffer (oracle/ref_backend.cpp): on such inputs the reference binary's own answer depends on heap contents."""
+    return int(load().pbtest_runoff_skips(1 if reset else 0))
 
 
 def search_windows(genomes, windows, coords, backend=0):

@@ -984,9 +984,8 @@ void Aligner::sort_final_mums() {
     // later MUM) make the order implementation-defined: the reference calls std::sort (libstdc++ introsort, unstable) with
     // operator< on start[0] (src/TMum.cpp:151) at every one of these calls.  The same algorithm on (start0, id) records in the
     // same initial order makes the same comparisons and moves, hence the same permutation - whatever the element type.
-    const std::vector<std::pair<int64_t, int>> original(kv);
     auto literal_sort = [&]() {
-        kv = original;
+        for (size_t i = 0; i < M; ++i) kv[i] = std::make_pair(mum_start_[mums_[final_mums_[i]].off], final_mums_[i]);   // (final_mums_ still holds the initial order)
         std::sort(kv.begin(), kv.end(), [](const std::pair<int64_t, int>& x, const std::pair<int64_t, int>& y) { return x.first < y.first; });
         for (size_t i = 0; i < M; ++i) final_mums_[i] = kv[i].second;
         final_sorted_ = false;                         // the next call sorts again, like the reference

@@ -191,7 +191,9 @@ def test_small_windows_with_inversions_zero_init_reference(monkeypatch):
 def test_host_fuzz_against_reference_binary():
     """tools/fuzz_host.py: 25 random genome sets x ini values x speculation slicings == reference binary (zero-initialising
     allocator, see the test above); includes poly-N windows, on which csgmum's Find_UM runs off the query buffer when a strand
-    shares no symbol with the window (the checker skips that call, oracle/ref_backend.cpp)"""
+    shares no symbol with the window (the checker skips that call, oracle/ref_backend.cpp).  Where that happened and the binary's
+    answer differs (it depends on the bytes behind the buffer and on the length of the file names, or is a crash) the case is
+    reported as not comparable, never as equal; at most 2 of the 25 seeds may end there"""
     import subprocess
     import sys
     env = dict(os.environ, MALLOC_PERTURB_="255", GLIBC_TUNABLES="glibc.malloc.tcache_count=0", PB200_HOST_THREADS="4")
@@ -199,6 +201,7 @@ def test_host_fuzz_against_reference_binary():
                        stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:]
     assert "done 25 cases, 0 mismatches" in r.stdout, r.stdout[-2000:]
+    assert int(r.stdout.rsplit("mismatches,", 1)[1].split()[0]) <= 2, r.stdout[-2000:]
 
 
 def test_window_order_matches_reference_trace():

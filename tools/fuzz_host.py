@@ -23,6 +23,7 @@ from oracle import runner, hosttest
 from tests.refcmp import result_to_dump, diff_dumps
 seed0 = int(sys.argv[1]); ncases = int(sys.argv[2])
 bad = 0
+ub = 0
 t0 = time.time()
 for it in range(ncases):
     rng = np.random.default_rng(seed0 + it)
@@ -63,7 +64,9 @@ for it in range(ncases):
         gi = [api.ingest_fasta(rf, True, d=kw.get("d", 300))] + [api.ingest_fasta(x, False, d=kw.get("d", 300)) for x in qf]
     os.environ["PB200_SPEC_SLICES"] = str(int(rng.choice([1, 3, 8])))
     os.environ["PB200_PAR_ANCHORS_MIN"] = str(int(rng.choice([1, 10**9])))
+    hosttest.runoff_skips()
     res = hosttest.align(gi, api.make_params(**kw), backend=1)
+    runoff = hosttest.runoff_skips()
     if r["dump"] is None:
         ok = res.get("no_mums", False) or len(res["mum_length"]) == 0
         nm = 0
@@ -71,9 +74,17 @@ for it in range(ncases):
         dd = diff_dumps(result_to_dump(res), r["dump"])
         ok = dd == []
         nm = len(r["dump"]["mums"])
-    if not ok:
+    if not ok and (runoff or r["returncode"] < 0):
+        # Find_UM walked off the end of a query buffer (a window sharing no symbol with a query strand, e.g. inside an N run;
+        # src/csgmum/mum.c:193-198 has no bound): the binary's answer then depends on the bytes behind that buffer, changes
+        # with the length of the file names, and sometimes is a crash.  Not a parity case.
+        ub += 1
+        print("reference UB (Find_UM run-off x%d, rc %d), case not comparable: seed" % (runoff, r["returncode"]), seed0 + it, flush=True)
+    elif not ok:
         bad += 1
         print("MISMATCH seed", seed0 + it, L, nq, div, contigs, kw, flush=True)
+        if os.environ.get("FUZZ_VERBOSE"):
+            print("  reference rc", r["returncode"], "dump", r["dump"] is not None, "diffs", dd[:4] if r["dump"] is not None else None, flush=True)
     elif it % 10 == 0:
         print("ok", seed0 + it, L, nq, contigs, kw, "mums", nm, "%.0fs" % (time.time() - t0), flush=True)
-print("done", ncases, "cases,", bad, "mismatches")
+print("done", ncases, "cases,", bad, "mismatches,", ub, "not comparable (reference UB)")
