@@ -58,6 +58,17 @@ for it in range(ncases):
                   diagdiff=float(rng.choice([0.05, 0.12, 0.5, 30.0])))
     if rng.random() < 0.4:
         kw["p"] = int(rng.choice([5000, 17000, 40000]))
+    if rng.random() < 0.25:                     # MUM / anchor length expressions (Converter + Calculator) and the LCB filter
+        kw["anchors"] = str(rng.choice(["1.1*(Log(S))", "2*(Log(S))", "25", "1.5*(Log(S))+3"]))
+        kw["mums"] = str(rng.choice(["1.1*(Log(S))", "0.9*(Log(S))", "14", "1.1*(Log(S))"]))
+    if rng.random() < 0.15:
+        kw["filter"] = 0
+    if rng.random() < 0.12:                     # many queries: mutated copies of the first ones
+        for _ in range(int(rng.integers(3, 9))):
+            x = g[int(rng.integers(0, len(g)))].copy()
+            hit = rng.random(len(x)) < float(rng.choice([0.002, 0.01, 0.03]))
+            x[hit] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(hit.sum()))]
+            g.append(x)
     with tempfile.TemporaryDirectory() as td:
         rf, qf = synth.write_dataset(os.path.join(td, "d"), g, contigs=contigs)
         r = runner.run_ref(rf, qf, os.path.join(td, "r"), **kw)
