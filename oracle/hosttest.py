@@ -43,6 +43,97 @@ def runoff_skips(reset=True):
     return int(load().pbtest_runoff_skips(1 if reset else 0))
 
 
+class ThreadRanks:
+    """The collectives of include/parsnp_b200.h (pb200_comm_set) among `world` THREADS of this process: lets a test run the
+    N>1 host path (queries / windows sharded over ranks, parsnp_b200/csrc/host/sharded.cpp) without torchrun."""
+
+    def __init__(self, world):
+        import threading
+        self.world, self.bar, self.slot = world, threading.Barrier(world), [None] * world
+        self.calls = 0
+
+    def _callbacks(self, rank):
+        import numpy as np
+
+        def view(ptr, nbytes):
+            return np.frombuffer((C.c_uint8 * nbytes).from_address(ptr), dtype=np.uint8)
+
+        def ag(user, send, recv, nbytes, dev):
+            if nbytes == 0:
+                return 0
+            self.slot[rank] = view(send, nbytes).copy()
+            self.bar.wait()
+            view(recv, nbytes * self.world)[:] = np.concatenate(self.slot)
+            self.bar.wait()
+            self.calls += rank == 0
+            return 0
+
+        def ar(user, buf, count, is_max, dev):
+            if count == 0:
+                return 0
+            v = view(buf, count * 4).view(np.int32)
+            self.slot[rank] = v.copy()
+            self.bar.wait()
+            v[:] = (np.max if is_max else np.min)(np.stack(self.slot), axis=0)
+            self.bar.wait()
+            self.calls += rank == 0
+            return 0
+
+        def bc(user, buf, nbytes, root, dev):
+            if nbytes == 0:
+                return 0
+            if rank == root:
+                self.slot[root] = view(buf, nbytes).copy()
+            self.bar.wait()
+            if rank != root:
+                view(buf, nbytes)[:] = self.slot[root]
+            self.bar.wait()
+            self.calls += rank == 0
+            return 0
+        def guarded(f):                         # a broken barrier (another rank failed) -> error code, the library throws
+            def g(*a):
+                try:
+                    return f(*a)
+                except Exception:  # noqa: BLE001
+                    return 1
+            return g
+        return api.AG_CB(guarded(ag)), api.AR_CB(guarded(ar)), api.BC_CB(guarded(bc))
+
+    def align(self, genomes, params=None, params_of_rank=None):
+        """-> per-rank results of pbtest_align_sharded (csgmum backend), counters of rank 0.  params_of_rank: {rank: params}
+        overrides (a test of the lock-step check: ranks that search different windows must fail, not mix their results)"""
+        import threading
+        import numpy as np
+        lib = load()
+        lib.pbtest_align_sharded.argtypes = [C.c_int, C.c_int, api.AG_CB, api.AR_CB, api.BC_CB, C.c_int] + [C.c_void_p] * 5
+        keep, ptrs, lens = api._seq_arrays(genomes)
+        prm = params or api.make_params()
+        out, err, counters = [None] * self.world, [None] * self.world, np.zeros((self.world, 2), np.int64)
+
+        def run(rank):
+            try:
+                cbs = self._callbacks(rank)
+                h = C.c_void_p()
+                mine = (params_of_rank or {}).get(rank, prm)
+                rc = lib.pbtest_align_sharded(rank, self.world, *cbs, len(keep), ptrs, api._ptr(lens), C.byref(mine), C.byref(h),
+                                              counters[rank].ctypes.data)
+                if rc not in (0, -5):
+                    raise RuntimeError("rank %d: rc %d: %s" % (rank, rc, lib.pb200_last_error().decode()))
+                out[rank] = api.unpack_result(lib, h)
+                out[rank]["no_mums"] = rc == -5
+            except Exception as e:  # noqa: BLE001 - re-raised on the caller's thread
+                err[rank] = e
+                self.bar.abort()
+        ts = [threading.Thread(target=run, args=(r,)) for r in range(self.world)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        for e in sorted((e for e in err if e is not None), key=lambda e: "allgather failed" in str(e) or "allreduce failed" in str(e)):
+            raise e                             # the first cause, not the ranks that were only cut off by it
+        return out, counters[0].tolist()
+
+
 def search_windows(genomes, windows, coords, backend=0):
     lib = load()
     keep, ptrs, lens = api._seq_arrays(genomes)

@@ -734,7 +734,7 @@ void Aligner::speculate_slice(CandCache& C, const RegionPool& src, const std::ve
         // chunks of the frontier are processed concurrently on the shared scratch layout
         // (pipelined: one core of this rank's share belongs to the replay thread)
         const size_t share = (size_t)std::max(1, pipeline_ ? threads_ - 1 : threads_);
-        const int T = (int)std::max<size_t>(1, std::min<size_t>(share, frontier.size() / 256 + 1));
+        const int T = pipeline_ ? (int)std::max<size_t>(1, std::min<size_t>(share, frontier.size() / 256 + 1)) : 1;   // lock step: aligner.h
         const size_t nchunks = T > 1 ? (size_t)T * 4 : 1;
         std::vector<RegionPool> outs(nchunks);
         for (auto& o : outs) o.n = n_;

@@ -133,8 +133,11 @@ public:
     void enable_trace(bool on) { trace_on_ = on; }
     void set_speculate(bool on) { speculate_ = on; }
     void set_threads(int t) { threads_ = t < 1 ? 1 : t; }
-    // speculation slices run on their own thread while the replay consumes the finished ones (off: a backend whose search
-    // involves collectives must see the same call sequence on every rank)
+    // speculation slices run on their own thread while the replay consumes the finished ones.  Off = lock step: a backend whose
+    // search involves collectives must see the same call sequence on every rank, so there is no speculation thread AND the
+    // speculative accept walks the frontier on one thread - chunks racing on the scratch layout can accept different candidates
+    // where two regions overlap in a rearranged query genome, which is harmless for one rank (the replay searches what the
+    // cache misses) but would make the ranks' search calls, i.e. their collectives, diverge.
     void set_pipeline(bool on) { pipeline_ = on; }
 
 private:

@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cstring>
 #include <stdexcept>
+#include <string>
 
 namespace pb200 {
 
@@ -75,6 +76,25 @@ void ShardedBackend::search(const WindowTask* tasks, int ntasks, const int64_t* 
     const int W = comm_->world, r = comm_->rank;
     out.clear();
     out.nq = nq;
+    // The replicated orchestrators must arrive here in lock step with the same windows; a rank that is somewhere else would
+    // have its blocks attributed to the wrong windows.  One 16-byte all-gather per call turns that into an error.
+    {
+        uint64_t h = 1469598103934665603ull;
+        auto mix = [&](uint64_t v) { h = (h ^ v) * 1099511628211ull; };
+        for (int t = 0; t < ntasks; ++t) {
+            mix((uint64_t)tasks[t].ref_start); mix((uint64_t)tasks[t].ref_len); mix((uint64_t)(uint32_t)tasks[t].minsize);
+            const int64_t* c = coords + tasks[t].coord_off;
+            for (int j = 0; j < 2 * nq; ++j) mix((uint64_t)c[j]);
+        }
+        uint64_t mine[2] = {(uint64_t)ntasks, h};
+        std::vector<uint64_t> all((size_t)2 * W);
+        comm_->allgather(mine, all.data(), sizeof(mine), false);
+        for (int p = 0; p < W; ++p)
+            if (all[2 * p] != mine[0] || all[2 * p + 1] != mine[1])
+                throw std::runtime_error("sharded search: rank " + std::to_string(r) + " and rank " + std::to_string(p) +
+                                         " are not searching the same windows (" + std::to_string(ntasks) + " vs " +
+                                         std::to_string(all[2 * p]) + " tasks)");
+    }
     std::vector<int> small_ids, staged_ids;
     for (int t = 0; t < ntasks; ++t) (staged_->wants_staged(tasks[t], coords) ? staged_ids : small_ids).push_back(t);
     std::vector<int32_t> t_cnt(ntasks, 0);

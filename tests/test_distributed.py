@@ -52,3 +52,45 @@ def test_sharded_search_nccl(case, extra):
     out = _run(2, "gpu", case, extra)
     assert out["ok"], out
     assert out["calls"]["bcast"] >= 3         # SA, lrp, seed table broadcast from rank 0
+
+
+@pytest.mark.skipif(not have_ref, reason="oracle/_ref not built")
+@pytest.mark.parametrize("world,case", [(2, "rearr_60k"), (4, "rearr_60k"), (3, "windows_50k")])
+def test_sharded_search_thread_ranks(world, case):
+    """the same N>1 host path with the ranks as threads of this process (oracle/hosttest.py ThreadRanks): every rank == golden.
+    rearr_60k has inversions, i.e. regions that overlap in a query genome: the case in which a speculative accept racing on the
+    scratch layout made the ranks ask for different windows (found by FUZZ_WORLD=2 tools/fuzz_host.py)"""
+    from oracle import hosttest
+    from parsnp_b200 import api
+    from tests.conftest import golden_case
+    from tests.refcmp import result_to_dump, diff_dumps
+    g, kw, gold = golden_case(case)
+    for _ in range(3):
+        outs, counters = hosttest.ThreadRanks(world).align(g, api.make_params(**kw))
+        for o in outs:
+            assert diff_dumps(result_to_dump(o), gold) == []
+    assert counters[0] >= 1 and counters[1] >= 1
+
+
+@pytest.mark.skipif(not have_ref, reason="oracle/_ref not built")
+def test_sharded_search_refuses_ranks_out_of_step():
+    """ranks that arrive at a search with different window lists (here: different ini values) get an error, not each other's
+    candidates (parsnp_b200/csrc/host/sharded.cpp, the check at the top of ShardedBackend::search)"""
+    from oracle import hosttest
+    from parsnp_b200 import api
+    from tests.conftest import golden_case
+    g, kw, _ = golden_case("windows_50k")
+    other = dict(kw)
+    other["q"] = kw.get("q", 30) + 40
+    with pytest.raises(RuntimeError, match="not searching the same windows"):
+        hosttest.ThreadRanks(2).align(g, api.make_params(**kw), params_of_rank={1: api.make_params(**other)})
+
+
+@pytest.mark.skipif(not have_ref, reason="oracle/_ref not built")
+def test_sharded_host_fuzz_thread_ranks():
+    """tools/fuzz_host.py with FUZZ_WORLD=2: 12 random cases, every rank of the sharded path == the single-rank result == the
+    reference binary (seed 51031 is the case of test_sharded_search_thread_ranks' docstring)"""
+    env = dict(os.environ, MALLOC_PERTURB_="255", GLIBC_TUNABLES="glibc.malloc.tcache_count=0", PB200_HOST_THREADS="2", FUZZ_WORLD="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_host.py"), "51024", "12"], env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "done 12 cases, 0 mismatches" in r.stdout, r.stdout[-2000:]

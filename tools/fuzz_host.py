@@ -5,7 +5,7 @@
 
 Random genome sets (independent / population divergence, repeats and N runs in the reference, inversions, deletions, insertions,
 whole-query reverse complements, multi-contig FASTA) x random ini values (c, d, q, diagdiff, p -> several reference windows)
-x random speculation slicing / anchor-accept mode.  Every case runs oracle/_ref/parsnp_core_ref and the product's host
+x random speculation slicing / anchor-accept mode (FUZZ_WORLD=N: also the N-rank sharded host path, ranks as threads).  Every case runs oracle/_ref/parsnp_core_ref and the product's host
 orchestrator with the reference's own csgmum as search backend (oracle/hosttest.py) and compares MUM and LCB lists bit for bit.
 MALLOC_PERTURB_=255 makes glibc zero every allocation of the reference binary (tcache off: its hits bypass the fill): wherever
 a reverse-strand match wins, the binary's result otherwise depends on the stale contents of the never-initialised
@@ -78,6 +78,16 @@ for it in range(ncases):
     hosttest.runoff_skips()
     res = hosttest.align(gi, api.make_params(**kw), backend=1)
     runoff = hosttest.runoff_skips()
+    world = int(os.environ.get("FUZZ_WORLD", "0"))
+    if world > 1:                               # N>1 host path (thread ranks): every rank must hold the single-rank result
+        mine = result_to_dump(res)
+        outs, counters = hosttest.ThreadRanks(world).align(gi, api.make_params(**kw))
+        for rk, o in enumerate(outs):
+            dd = diff_dumps(result_to_dump(o), mine)
+            if dd or o["no_mums"] != res["no_mums"]:
+                bad += 1
+                print("SHARDED MISMATCH seed", seed0 + it, "world", world, "rank", rk, dd[:3], flush=True)
+                break
     if r["dump"] is None:
         ok = res.get("no_mums", False) or len(res["mum_length"]) == 0
         nm = 0
