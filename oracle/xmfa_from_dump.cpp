@@ -36,8 +36,8 @@ int main(int argc, char** argv) {
     xi.c = ini.get_i("LCB", "c"); xi.doalign = ini.get_i("LCB", "doalign"); xi.cores = 1;
     ifstream f(argv[2]);
     string line;
-    int64_t nm = 0;
-    xi.cmum_off.push_back(0);
+    vector<vector<int64_t>> members;
+    bool located_ok = true, explicit_lists = false;
     while (getline(f, line)) {
         istringstream is(line);
         string tag; is >> tag;
@@ -49,10 +49,28 @@ int main(int argc, char** argv) {
             int type; long cnt, len; is >> type >> cnt >> len; xi.ctype.push_back(type);
             string tok;
             while (is >> tok) { long a, b; sscanf(tok.c_str(), "%ld:%ld", &a, &b); xi.cstart.push_back(a); xi.cend.push_back(b); }
-            if (type == 1) for (long k = 0; k < cnt; k++) xi.cmum_idx.push_back(nm++);      // LCBs own consecutive runs of the sorted MUM list
-            xi.cmum_off.push_back((int64_t)xi.cmum_idx.size());
+            // An LCB owns a consecutive run of the MUM list (sorted by reference start); MUMs of clusters the filter removed
+            // stay in the list between the runs, so the run is located by the LCB's reference start and checked by its end - unless an "I" line
+            // (the product's own cluster -> MUM index list, tests/refcmp.py write_dump) follows and replaces it.
+            members.emplace_back();
+            if (type == 1) {
+                const size_t N = (size_t)xi.n;
+                const long c0 = xi.cstart[xi.cstart.size() - N], c1 = xi.cend[xi.cend.size() - N];
+                size_t m = 0;
+                while (m < xi.mlen.size() && xi.mstart[m * N] != c0) m++;
+                for (long k = 0; k < cnt && m + k < xi.mlen.size(); k++) members.back().push_back((int64_t)(m + k));
+                if ((long)members.back().size() != cnt || xi.mend[(m + cnt - 1) * N] != c1) located_ok = false;
+            }
+        } else if (tag == "I" && !members.empty()) {
+            members.back().clear();
+            long m;
+            while (is >> m) members.back().push_back(m);
+            explicit_lists = true;
         }
     }
+    if (!located_ok && !explicit_lists) { fprintf(stderr, "xmfa_from_dump: an LCB interval does not hold the number of MUMs the dump states\n"); return 6; }
+    xi.cmum_off.push_back(0);
+    for (auto& v : members) { xi.cmum_idx.insert(xi.cmum_idx.end(), v.begin(), v.end()); xi.cmum_off.push_back((int64_t)xi.cmum_idx.size()); }
     if (argc > 4) { xi.outdir = argv[4]; xi.recombfilter = ini.get_b("LCB", "recombfilter"); }
     if (!pb200::write_xmfa(xi, argv[3])) return 4;
     if (argc > 5) {

@@ -139,6 +139,7 @@ def _decl_result_api(lib):
     lib.pb200_result_num_clusters.argtypes = [vp]
     lib.pb200_result_num_clusters.restype = C.c_int64
     lib.pb200_result_clusters.argtypes = [vp] + [vp] * 5
+    lib.pb200_result_cluster_mums.argtypes = [vp, vp, vp]
     lib.pb200_result_unaligned.argtypes = [vp, vp, vp, vp]
     lib.pb200_result_unaligned.restype = C.c_int64
     lib.pb200_result_num_trace.argtypes = [vp]
@@ -195,6 +196,9 @@ def unpack_result(lib, h):
     ctype = np.zeros(K, np.int32); cn = np.zeros(K, np.int64); cl = np.zeros(K, np.int64)
     cs = np.zeros((K, n), np.int64); ce = np.zeros((K, n), np.int64)
     lib.pb200_result_clusters(h, _ptr(ctype), _ptr(cn), _ptr(cl), _ptr(cs), _ptr(ce))
+    cmo = np.zeros(K + 1, np.int64)
+    cmi = np.zeros(max(1, lib.pb200_result_cluster_mums(h, None, None)), np.int64)
+    nidx = lib.pb200_result_cluster_mums(h, _ptr(cmo), _ptr(cmi))
     T = lib.pb200_result_num_trace(h)
     tr = np.zeros((T, 2), np.int64)
     if T:
@@ -209,7 +213,7 @@ def unpack_result(lib, h):
     del owner                      # the views hold the remaining references
     return dict(n=n, mum_length=length, mum_slength=slength, mum_start=start, mum_end=end, mum_fwd=fwd,
                 cluster_type=ctype, cluster_nmums=cn, cluster_length=cl, cluster_start=cs, cluster_end=ce,
-                trace=tr, unaligned=np.stack([ug.astype(np.int64), us, ue], axis=1), stats=dict(zip(names, sv.tolist())))
+                cluster_mum_off=cmo, cluster_mum_idx=cmi[:nidx], trace=tr, unaligned=np.stack([ug.astype(np.int64), us, ue], axis=1), stats=dict(zip(names, sv.tolist())))
 
 
 def _seq_arrays(genomes):

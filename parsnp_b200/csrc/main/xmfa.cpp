@@ -133,14 +133,25 @@ bool write_xmfa(const XmfaInput& in, const std::string& path) {
         std::vector<int64_t> cs(in.cstart.begin() + z * n, in.cstart.begin() + (z + 1) * n);
         std::vector<int64_t> ce(in.cend.begin() + z * n, in.cend.begin() + (z + 1) * n);
         const int64_t first = in.cmum_idx[m0], last = in.cmum_idx[m1 - 1];
-        // overlap trim with the previous LCB, reproduced literally (the scan position never advances, src/parsnp.cpp:935-940)
+        // overlap trim with the previous LCB, reproduced literally (src/parsnp.cpp:927-951).  The scan position of the first
+        // loop never advances, so cols_to_trim == overlap.  The second loop counts the non-gap columns of row 0 over the length
+        // of row i - but row 0 has lost its head by the time rows 1.. are counted, and the reference keeps indexing it up to the
+        // old length: behind the new terminator (which counts as a base) std::string still holds the old tail, unmoved.
         const int lcb_start = (int)cs[0] + 1, lcb_end = (int)ce[0];
         int overlap = std::max(0, prev_end - lcb_start);
         if (overlap > 0 && !T[0].empty() && T[0][0] != '-') {
             const int cols_to_trim = overlap;
+            const std::string row0 = T[0];
+            const size_t kept = row0.size() - std::min(row0.size(), (size_t)cols_to_trim);
             for (int i = 0; i < n; i++) {
                 int cnt = 0;
-                for (size_t pos = 0; pos < T[i].size(); pos++) if (pos < T[0].size() && T[0][pos] != '-') cnt++;
+                for (size_t pos = 0; pos < T[i].size(); pos++) {
+                    char ch;
+                    if (i == 0) ch = pos < row0.size() ? row0[pos] : '\0';
+                    else if (pos < kept) ch = row0[pos + (row0.size() - kept)];
+                    else ch = (pos == kept || pos >= row0.size()) ? '\0' : row0[pos];
+                    if (ch != '-') cnt++;
+                }
                 cs[i] += cnt;
                 T[i].erase(0, (size_t)cols_to_trim);
             }

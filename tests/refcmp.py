@@ -14,6 +14,20 @@ def result_to_dump(res):
     return dict(n=res["n"], mums=mums, clusters=cl)
 
 
+def write_dump(res, path):
+    """a result of the product in the format of the reference's hook dump (oracle/build_ref.py H1) plus one "I" line per
+    cluster: the indices of its MUMs in the list - input of oracle/_ref/xmfa_from_dump"""
+    d = result_to_dump(res)
+    off, idx = res["cluster_mum_off"], res["cluster_mum_idx"]
+    with open(path, "w") as f:
+        f.write("N %d\n" % d["n"])
+        for ln, sl, cols in d["mums"]:
+            f.write("M %d %d %s\n" % (ln, sl, " ".join("%d:%d:%d" % c for c in cols)))
+        for k, (t, nm, ln, cols) in enumerate(d["clusters"]):
+            f.write("C %d %d %d %s\n" % (t, nm, ln, " ".join("%d:%d" % c for c in cols)))
+            f.write("I %s\n" % " ".join(str(int(x)) for x in idx[off[k]:off[k + 1]]))
+
+
 def diff_dumps(a, b, limit=5):
     """returns list of human-readable differences (empty = identical)"""
     out = []

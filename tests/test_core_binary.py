@@ -114,6 +114,19 @@ def test_xmfa_writer_matches_reference_bytes(tmp_path, kind):
         assert hashlib.md5(open(mine, "rb").read()).hexdigest() == "5b59e50c5b8c1f79165fc41cfd2a6ac4"
 
 
+@pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(XTOOL)), reason="oracle/_ref tools not built")
+def test_writer_fuzz_against_reference_binary():
+    """tools/fuzz_xmfa.py, 12 random cases: XMFA, blocks/ and parsnp.unalign written from the product's own MUMs, LCBs and
+    cluster -> MUM lists (host orchestrator over csgmum) == the reference binary's files.  Seed 61174 has LCBs that overlap on
+    the reference: the header coordinates then come out of the reference's trim loop reading row 0 behind its new end
+    (src/parsnp.cpp:941-949), reproduced in csrc/main/xmfa.cpp"""
+    import sys
+    env = dict(os.environ, MALLOC_PERTURB_="255", GLIBC_TUNABLES="glibc.malloc.tcache_count=0", PB200_HOST_THREADS="4")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_xmfa.py"), "61170", "12"], env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0 and "done 12 cases, 0 mismatches" in r.stdout, r.stdout[-2000:]
+
+
 def _log_lines(path, own_paths=False):
     """parsnpAligner.log, comparable: elapsed-time values dropped (the reference's have 1 s resolution, ours are the run's own),
     `Sequence i : <path>` reduced to the file name"""

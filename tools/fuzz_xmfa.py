@@ -1,0 +1,82 @@
+#!/usr/bin/env python3
+"""CPU fuzz of the output writers against the reference binary (test infrastructure, no GPU).
+
+  GLIBC_TUNABLES=glibc.malloc.tcache_count=0 MALLOC_PERTURB_=255 python tools/fuzz_xmfa.py <first seed> <cases>
+
+Every case (tools/fuzz_cases.py) runs oracle/_ref/parsnp_core_ref to the end (libMUSCLE, XMFA, recombfilter blocks, parsnp.unalign)
+and the product's writer (parsnp_b200/csrc/main/xmfa.cpp through oracle/_ref/xmfa_from_dump) twice: on the reference's own
+MUM/LCB dump, and on the result of the product's host orchestrator (csgmum as search, oracle/hosttest.py: MUMs, LCBs, cluster ->
+MUM lists, unaligned-region records) - everything of the product between the search kernels and the files.  Every output file is
+compared byte for byte."""
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from parsnp_b200 import api, synth
+from oracle import runner, hosttest
+from tools.fuzz_cases import make_case
+from tests.refcmp import write_dump
+
+XTOOL = os.path.join(os.path.dirname(runner.EXE), "xmfa_from_dump")
+
+
+def tree(root):
+    out = {}
+    for base, _, files in os.walk(root):
+        for f in files:
+            p = os.path.join(base, f)
+            out[os.path.relpath(p, root)] = open(p, "rb").read()
+    return out
+
+
+seed0 = int(sys.argv[1]); ncases = int(sys.argv[2])
+bad = skipped = 0
+t0 = time.time()
+for it in range(ncases):
+    g, contigs, kw, (L, nq, div), rng = make_case(seed0 + it)
+    if L > 50000:
+        g = [x[:50000] for x in g]              # bounds the libMUSCLE time of a case
+    kw["recombfilter"] = int(rng.random() < 0.4)
+    kw["unaligned"] = int(rng.random() < 0.5)
+    with tempfile.TemporaryDirectory() as td:
+        rf, qf = synth.write_dataset(os.path.join(td, "d"), g, contigs=contigs)
+        r = runner.run_ref(rf, qf, os.path.join(td, "r"), dump_exit=False, **kw)
+        if r["dump"] is None or r["returncode"] != 0:
+            skipped += 1                         # no MUMs, or one of the reference's own crashes
+            continue
+        hosttest.runoff_skips()
+        prm = {k: v for k, v in kw.items() if k not in ("recombfilter", "unaligned")}
+        gi = [api.ingest_fasta(rf, True, d=kw.get("d", 300))] + [api.ingest_fasta(x, False, d=kw.get("d", 300)) for x in qf]
+        res = hosttest.align(gi, api.make_params(flags=api.FLAG_UNALIGNED if kw["unaligned"] else 0, **prm), backend=1)
+        runoff = hosttest.runoff_skips()
+        rec = os.path.join(td, "unaligned.txt")
+        with open(rec, "w") as f:
+            f.write("".join("%d %d %d\n" % tuple(x) for x in res["unaligned"].tolist()))
+        write_dump(res, os.path.join(td, "mine.dump"))
+        want = {k: v for k, v in tree(r["outdir"]).items() if k.endswith(".xmfa") or k.startswith("blocks") or k.endswith(".unalign")}
+        rc, diff = 0, []
+        # writer on the reference's MUM/LCB dump, then the whole CPU chain: product's own MUMs, LCBs and cluster -> MUM lists
+        for tag, dump in (("refdump", os.path.join(td, "r", "dump.txt")), ("product", os.path.join(td, "mine.dump"))):
+            out = os.path.join(td, tag)
+            os.makedirs(out)
+            args = [XTOOL, os.path.join(td, "r", "ref.ini"), dump, os.path.join(out, "parsnpAligner.xmfa"), out]
+            if kw["unaligned"]:
+                args.append(rec)
+            leg = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT).returncode
+            if leg == 6 and tag == "refdump":
+                continue                         # overlapping LCBs: the hook dump alone does not say which MUMs an LCB owns
+            rc |= leg
+            got = {k: v for k, v in tree(out).items() if k in want or k.startswith("blocks")}
+            diff += sorted(tag + ":" + k for k in set(want) | set(got) if want.get(k) != got.get(k))
+        if runoff and diff and all(x.startswith("product:") or x.endswith(".unalign") for x in diff):
+            skipped += 1                         # the binary's own MUM list is heap dependent there (tools/fuzz_host.py)
+            continue
+    if rc != 0 or diff:
+        bad += 1
+        print("MISMATCH seed", seed0 + it, L, nq, div, contigs, kw, "rc", rc, "files", diff[:5], flush=True)
+    elif it % 10 == 0:
+        print("ok", seed0 + it, L, nq, contigs, kw, "files", len(want), "%.0fs" % (time.time() - t0), flush=True)
+print("done", ncases, "cases,", bad, "mismatches,", skipped, "skipped")
