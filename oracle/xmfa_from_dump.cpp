@@ -1,12 +1,14 @@
 // TEST-ONLY tool: writes the XMFA from an oracle MUM/LCB dump (hook H1 of oracle/build_ref.py) through the product's XMFA
 // writer (parsnp_b200/csrc/main/xmfa.cpp), so the writer can be checked against the reference's XMFA md5 without a GPU.
-//   xmfa_from_dump <ini> <dump.txt> <out.xmfa> [<outdir for blocks/ and parsnp.unalign> [<unaligned records: "genome start end" lines>]]
+//   xmfa_from_dump <ini> <dump.txt> <out.xmfa> [<outdir for blocks/, parsnp.unalign, parsnpAligner.log>
+//                  [<unaligned records: "genome start end" lines, or -> [<log counters: "anchors_found mums_filtered clusters_filtered">]]]
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
 #include <sstream>
 #include "../parsnp_b200/csrc/host/ingest.h"
+#include "../parsnp_b200/csrc/host/minsize.h"
 #include "../parsnp_b200/csrc/main/xmfa.h"
 using namespace std;
 int main(int argc, char** argv) {
@@ -37,6 +39,7 @@ int main(int argc, char** argv) {
     ifstream f(argv[2]);
     string line;
     vector<vector<int64_t>> members;
+    vector<int64_t> cnm;
     bool located_ok = true, explicit_lists = false;
     while (getline(f, line)) {
         istringstream is(line);
@@ -46,7 +49,7 @@ int main(int argc, char** argv) {
             string tok;
             while (is >> tok) { long a, b; int fw; sscanf(tok.c_str(), "%ld:%ld:%d", &a, &b, &fw); xi.mstart.push_back(a); xi.mend.push_back(b); xi.mfwd.push_back((uint8_t)fw); }
         } else if (tag == "C") {
-            int type; long cnt, len; is >> type >> cnt >> len; xi.ctype.push_back(type);
+            int type; long cnt, len; is >> type >> cnt >> len; xi.ctype.push_back(type); cnm.push_back(cnt);
             string tok;
             while (is >> tok) { long a, b; sscanf(tok.c_str(), "%ld:%ld", &a, &b); xi.cstart.push_back(a); xi.cend.push_back(b); }
             // An LCB owns a consecutive run of the MUM list (sorted by reference start); MUMs of clusters the filter removed
@@ -73,7 +76,24 @@ int main(int argc, char** argv) {
     for (auto& v : members) { xi.cmum_idx.insert(xi.cmum_idx.end(), v.begin(), v.end()); xi.cmum_off.push_back((int64_t)xi.cmum_idx.size()); }
     if (argc > 4) { xi.outdir = argv[4]; xi.recombfilter = ini.get_b("LCB", "recombfilter"); }
     if (!pb200::write_xmfa(xi, argv[3])) return 4;
-    if (argc > 5) {
+    if (argc > 6) {                             // parsnpAligner.log through the product's writer (csrc/main/xmfa.cpp write_log)
+        pb200::LogInput li;
+        ifstream sf(argv[6]);
+        sf >> li.anchors_found >> li.mums_filtered >> li.clusters_filtered;
+        int64_t slength = 500000000;
+        for (int i = 0; i <= qfiles; i++) {
+            char b[64];
+            if (i == 0) li.files.push_back(ini.get("Reference", "file"));
+            else { snprintf(b, sizeof b, "file%d", i); li.files.push_back(ini.get("Query", b)); }
+            li.a.push_back(G[i].a); li.c.push_back(G[i].c); li.g.push_back(G[i].g); li.t.push_back(G[i].t);
+            slength = min<int64_t>(slength, (int64_t)G[i].text.size());
+        }
+        li.d = d; li.q = ini.get_i("LCB", "q"); li.filter = ini.get_i("MUM", "filter");
+        li.anchor_size = (float)pb200::MinSizeExpr(ini.get("MUM", "anchors"))(slength);
+        li.cnm = cnm;
+        if (!pb200::write_log(xi, li, string(argv[4]) + "/parsnpAligner.log")) return 7;
+    }
+    if (argc > 5 && string(argv[5]) != "-") {
         ifstream uf(argv[5]);
         vector<int32_t> ug; vector<int64_t> us, ue;
         long a, b, c;

@@ -188,7 +188,6 @@ int main(int argc, char** argv) {
     // statistics block of parsnpAligner.log (src/parsnp.cpp:1082-1190), line for line; the elapsed-time lines carry this run's
     // own timings (the reference's have a resolution of one second)
     {
-        // named statistics of the result
         vector<double> sv(64, 0.0);
         const int nsv = pb200_result_stats(res, sv.data(), 64);
         auto stat = [&](const char* name) -> double {
@@ -202,67 +201,30 @@ int main(int argc, char** argv) {
             }
             return 0.0;
         };
-        const long filtered = (long)stat("mums_filtered"), filtered_clusters = (long)stat("clusters_filtered");
-        ofstream log(logpath.c_str());
-        log << "Number of sequences analyzed:" << setiosflags(ios::fixed) << setprecision(1) << setw(10) << n << endl << endl;
-        for (int i = 0; i < n; i++) {
-            log << "Sequence " << i + 1 << " : " << files[i] << endl;
-            log << names[i] << endl;
-            log << "Length:" << setw(10) << (long)(G[i].text.size() - G[i].padding) << " bps" << endl;
-            log << " GC:" << setw(10) << setiosflags(ios::fixed) << setprecision(1) << (float(G[i].g) + float(G[i].c)) << endl;
-            log << " AT:" << setw(10) << setiosflags(ios::fixed) << setprecision(1) << (float(G[i].a) + float(G[i].t)) << endl;
-        }
-        log << setw(2) << setiosflags(ios::left) << "d value:   " << setw(2) << prm.d << endl;
-        log << setw(2) << "q value:   " << setw(2) << prm.q << endl << endl;
+        pb200::LogInput li;
+        li.files = files;
+        for (auto& g : G) { li.a.push_back(g.a); li.c.push_back(g.c); li.g.push_back(g.g); li.t.push_back(g.t); }
+        li.d = prm.d; li.q = prm.q; li.filter = prm.filter;
         int64_t slength = 500000000;
         for (auto& g : G) slength = min<int64_t>(slength, (int64_t)g.text.size());
-        log << setw(2) << "Mum anchor size:   " << setw(2) << (float)pb200_minsize(prm.anchors, slength) << endl;
-        log << setw(2) << "Number of MUM anchors found:   " << setw(2) << anchors_found << endl;
-        if (M + filtered >= anchors_found) log << setw(2) << "Number of MUMs found:   " << setw(2) << (M + filtered) - anchors_found << endl;
-        else log << setw(2) << "Number of MUMs found:   " << setw(2) << 0 << endl;
-        log << setw(2) << "Total MUMs found((Anchors+MUMs)-filtered):   " << setw(2) << M << endl << endl;
-        log << setw(2) << "Random MUM length:   " << setw(2) << prm.filter << endl;
-        log << setw(2) << "Minimum Cluster length:   " << setw(2) << prm.c << endl;
-        log << setw(2) << "Number of MUMs filtered:   " << setw(2) << filtered << endl;
-        log << setw(2) << "Number of Clusters filtered:   " << setw(2) << filtered_clusters << endl << endl;
-        long ccount = 0;
-        for (int64_t i = 0; i < K; i++) if (ctype[i] && cnm[i] > 0) ccount++;
-        log << setw(2) << "Number of clusters created:   " << setw(2) << ccount << endl;
-        if (K == 0) log << setw(2) << "Number of clusters created:   " << setw(2) << "NONE" << endl;
-        if (ccount) log << setw(2) << "Average number of MUMs per cluster:   " << setw(2) << M / ccount << endl;     // (the reference divides by zero here)
-        // LCB coverage per sequence (src/parsnp.cpp:1141-1160): |last MUM end - first MUM start| of every LCB, per strand
-        vector<int64_t> cmoff((size_t)K + 1);
+        li.anchor_size = (float)pb200_minsize(prm.anchors, slength);
+        li.anchors_found = anchors_found;
+        li.mums_filtered = (long)stat("mums_filtered"); li.clusters_filtered = (long)stat("clusters_filtered");
+        li.cnm = cnm;
+        li.t_anchor = stat("t_anchor_search") + stat("t_anchor_host"); li.t_coarsen = stat("t_replay"); li.t_lcb = stat("t_lcb");
+        li.t_total = stat("t_total");
+        pb200::XmfaInput xi;                                // the lists the log reads: names, sizes, clusters, MUMs
+        xi.n = n;
+        xi.fasta_names = names;
+        for (auto& g : G) xi.genome_sizes.push_back((int64_t)g.text.size() - g.padding);
+        xi.c = prm.c;
+        xi.ctype = ctype;
+        xi.cmum_off.resize(K + 1);
         const int tot = pb200_result_cluster_mums(res, nullptr, nullptr);
-        vector<int64_t> cmidx((size_t)max(tot, 1));
-        pb200_result_cluster_mums(res, cmoff.data(), cmidx.data());
-        vector<long> coverage(n, 0);
-        long avg = 0, totcoverage = 0, totsize = 0;
-        for (int i = 0; i < n; i++)
-            for (int64_t c = 0; c < K; c++) {
-                if (!ctype[c] || cmoff[c + 1] <= cmoff[c]) continue;
-                const int64_t front = cmidx[cmoff[c]], back = cmidx[cmoff[c + 1] - 1];
-                long span;
-                if (mfw[front * n + i]) span = labs((long)((mst[back * n + i] + mlen[back]) - mst[front * n + i]));
-                else span = labs((long)((mst[front * n + i] + mlen[front]) - mst[back * n + i]));
-                coverage[i] += span;
-                if (i == 0) avg += span;
-            }
-        if (ccount) log << setw(2) << "Average cluster length:   " << avg / ccount << " bps" << endl;
-        for (int i = 0; i < n; i++) {
-            float percent = (float)coverage[i] / ((float)(G[i].g + G[i].c) + (float)(G[i].a + G[i].t));
-            log << setw(2) << "Cluster coverage in sequence " << i + 1 << ":   " << setiosflags(ios::fixed) << setprecision(1) << 100.00 * percent << "%" << endl;
-            totcoverage += coverage[i];
-            totsize += (long)(G[i].text.size() - G[i].padding);
-        }
-        float percent = (float)totcoverage / (float)totsize;
-        log << setw(2) << "Total coverage among all sequences:   " << setiosflags(ios::fixed) << setprecision(1) << 100.00 * percent << "%" << endl << endl;
-        const double t_anchor = stat("t_anchor_search") + stat("t_anchor_host"), t_coarsen = stat("t_replay"), t_lcb = stat("t_lcb");
-        log << setw(2) << " MUM anchor search elapsed time:   " << t_anchor << "s " << endl;
-        log << setw(2) << " MUM coarsening elapsed time:   " << t_coarsen << "s " << endl;
-        if (prm.filter) log << setw(2) << " MUM filtering elapsed time:   " << 0.0 << "s " << endl;
-        log << setw(2) << " MUM clustering elapsed time:   " << t_lcb << "s " << endl;
-        log << setw(2) << " Inter-clustering elapsed time:   " << 0.0 << "s " << endl;
-        log << setw(2) << " Total running time:   " << stat("t_total") << "s " << endl;
+        xi.cmum_idx.resize((size_t)max(tot, 1));
+        pb200_result_cluster_mums(res, xi.cmum_off.data(), xi.cmum_idx.data());
+        xi.mlen = mlen; xi.mstart = mst; xi.mfwd = mfw;
+        if (!pb200::write_log(xi, li, logpath)) { cerr << "parsnp_b200_core: cannot write " << logpath << endl; return 1; }
     }
     pb200_result_free(res);
     pb200_genomes_free(dev);

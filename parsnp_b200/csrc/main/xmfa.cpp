@@ -4,6 +4,8 @@
 #include <sys/types.h>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
+#include <iomanip>
 #include <fstream>
 #include <iostream>
 
@@ -211,6 +213,67 @@ bool write_unaligned(const XmfaInput& in, const std::vector<int32_t>& genome, co
         if (s1.size() == 0) u << "-" << "\n";
         u << "=" << "\n";
     }
+    return true;
+}
+
+bool write_log(const XmfaInput& in, const LogInput& li, const std::string& path) {
+    using namespace std;
+    const int n = in.n;
+    const int64_t K = (int64_t)in.ctype.size(), M = (int64_t)in.mlen.size();
+    ofstream log(path.c_str());
+    if (!log) return false;
+    log << "Number of sequences analyzed:" << setiosflags(ios::fixed) << setprecision(1) << setw(10) << n << endl << endl;
+    for (int i = 0; i < n; i++) {
+        log << "Sequence " << i + 1 << " : " << li.files[i] << endl;
+        log << in.fasta_names[i] << endl;
+        log << "Length:" << setw(10) << (long)in.genome_sizes[i] << " bps" << endl;
+        log << " GC:" << setw(10) << setiosflags(ios::fixed) << setprecision(1) << (float(li.g[i]) + float(li.c[i])) << endl;
+        log << " AT:" << setw(10) << setiosflags(ios::fixed) << setprecision(1) << (float(li.a[i]) + float(li.t[i])) << endl;
+    }
+    log << setw(2) << setiosflags(ios::left) << "d value:   " << setw(2) << li.d << endl;
+    log << setw(2) << "q value:   " << setw(2) << li.q << endl << endl;
+    log << setw(2) << "Mum anchor size:   " << setw(2) << li.anchor_size << endl;
+    log << setw(2) << "Number of MUM anchors found:   " << setw(2) << li.anchors_found << endl;
+    if (M + li.mums_filtered >= li.anchors_found) log << setw(2) << "Number of MUMs found:   " << setw(2) << (M + li.mums_filtered) - li.anchors_found << endl;
+    else log << setw(2) << "Number of MUMs found:   " << setw(2) << 0 << endl;
+    log << setw(2) << "Total MUMs found((Anchors+MUMs)-filtered):   " << setw(2) << M << endl << endl;
+    log << setw(2) << "Random MUM length:   " << setw(2) << li.filter << endl;
+    log << setw(2) << "Minimum Cluster length:   " << setw(2) << in.c << endl;
+    log << setw(2) << "Number of MUMs filtered:   " << setw(2) << li.mums_filtered << endl;
+    log << setw(2) << "Number of Clusters filtered:   " << setw(2) << li.clusters_filtered << endl << endl;
+    long ccount = 0;
+    for (int64_t i = 0; i < K; i++) if (in.ctype[i] && li.cnm[i] > 0) ccount++;
+    log << setw(2) << "Number of clusters created:   " << setw(2) << ccount << endl;
+    if (K == 0) log << setw(2) << "Number of clusters created:   " << setw(2) << "NONE" << endl;
+    if (ccount) log << setw(2) << "Average number of MUMs per cluster:   " << setw(2) << M / ccount << endl;     // (the reference divides by zero here)
+    // LCB coverage per sequence (src/parsnp.cpp:1141-1160): |last MUM end - first MUM start| of every LCB, per strand
+    vector<long> coverage(n, 0);
+    long avg = 0, totcoverage = 0, totsize = 0;
+    for (int i = 0; i < n; i++)
+        for (int64_t c = 0; c < K; c++) {
+            if (!in.ctype[c] || in.cmum_off[c + 1] <= in.cmum_off[c]) continue;
+            const int64_t front = in.cmum_idx[in.cmum_off[c]], back = in.cmum_idx[in.cmum_off[c + 1] - 1];
+            long span;
+            if (in.mfwd[front * n + i]) span = labs((long)((in.mstart[back * n + i] + in.mlen[back]) - in.mstart[front * n + i]));
+            else span = labs((long)((in.mstart[front * n + i] + in.mlen[front]) - in.mstart[back * n + i]));
+            coverage[i] += span;
+            if (i == 0) avg += span;
+        }
+    if (ccount) log << setw(2) << "Average cluster length:   " << avg / ccount << " bps" << endl;
+    for (int i = 0; i < n; i++) {
+        float percent = (float)coverage[i] / ((float)(li.g[i] + li.c[i]) + (float)(li.a[i] + li.t[i]));
+        log << setw(2) << "Cluster coverage in sequence " << i + 1 << ":   " << setiosflags(ios::fixed) << setprecision(1) << 100.00 * percent << "%" << endl;
+        totcoverage += coverage[i];
+        totsize += (long)in.genome_sizes[i];
+    }
+    float percent = (float)totcoverage / (float)totsize;
+    log << setw(2) << "Total coverage among all sequences:   " << setiosflags(ios::fixed) << setprecision(1) << 100.00 * percent << "%" << endl << endl;
+    log << setw(2) << " MUM anchor search elapsed time:   " << li.t_anchor << "s " << endl;
+    log << setw(2) << " MUM coarsening elapsed time:   " << li.t_coarsen << "s " << endl;
+    if (li.filter) log << setw(2) << " MUM filtering elapsed time:   " << 0.0 << "s " << endl;
+    log << setw(2) << " MUM clustering elapsed time:   " << li.t_lcb << "s " << endl;
+    log << setw(2) << " Inter-clustering elapsed time:   " << 0.0 << "s " << endl;
+    log << setw(2) << " Total running time:   " << li.t_total << "s " << endl;
     return true;
 }
 

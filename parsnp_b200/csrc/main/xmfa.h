@@ -38,4 +38,19 @@ bool write_xmfa(const XmfaInput& in, const std::string& path);
 bool write_unaligned(const XmfaInput& in, const std::vector<int32_t>& genome, const std::vector<int64_t>& start,
                      const std::vector<int64_t>& end, const std::string& path);
 
+// what the statistics block of parsnpAligner.log needs besides the MUM / LCB lists
+struct LogInput {
+    std::vector<std::string> files;                      // the paths as the ini gives them
+    std::vector<int64_t> a, c, g, t;                     // base counts per genome (ingest)
+    int d = 300, q = 30, filter = 1;
+    float anchor_size = 0;                               // Calculator(anchors, shortest genome)
+    long anchors_found = 0, mums_filtered = 0, clusters_filtered = 0;
+    std::vector<int64_t> cnm;                            // MUMs per cluster
+    double t_anchor = 0, t_coarsen = 0, t_lcb = 0, t_total = 0;
+};
+
+// statistics block of parsnpAligner.log (src/parsnp.cpp:1082-1190), line for line; uses n, fasta_names, genome_sizes, c,
+// ctype, cmum_off/cmum_idx, mlen, mstart, mfwd of `in`
+bool write_log(const XmfaInput& in, const LogInput& li, const std::string& path);
+
 }  // namespace pb200

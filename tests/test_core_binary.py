@@ -117,7 +117,7 @@ def test_xmfa_writer_matches_reference_bytes(tmp_path, kind):
 @pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(XTOOL)), reason="oracle/_ref tools not built")
 def test_writer_fuzz_against_reference_binary():
     """tools/fuzz_xmfa.py, 12 random cases: XMFA, blocks/ and parsnp.unalign written from the product's own MUMs, LCBs and
-    cluster -> MUM lists (host orchestrator over csgmum) == the reference binary's files.  Seed 61174 has LCBs that overlap on
+    cluster -> MUM lists and log counters (host orchestrator over csgmum) == the reference binary's files, parsnpAligner.log included.  Seed 61174 has LCBs that overlap on
     the reference: the header coordinates then come out of the reference's trim loop reading row 0 behind its new end
     (src/parsnp.cpp:941-949), reproduced in csrc/main/xmfa.cpp"""
     import sys

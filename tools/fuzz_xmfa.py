@@ -6,7 +6,8 @@
 Every case (tools/fuzz_cases.py) runs oracle/_ref/parsnp_core_ref to the end (libMUSCLE, XMFA, recombfilter blocks, parsnp.unalign)
 and the product's writer (parsnp_b200/csrc/main/xmfa.cpp through oracle/_ref/xmfa_from_dump) twice: on the reference's own
 MUM/LCB dump, and on the result of the product's host orchestrator (csgmum as search, oracle/hosttest.py: MUMs, LCBs, cluster ->
-MUM lists, unaligned-region records) - everything of the product between the search kernels and the files.  Every output file is
+MUM lists, unaligned-region records, log counters) - everything of the product between the search kernels and the files, parsnpAligner.log
+included.  Every output file is
 compared byte for byte."""
 import os
 import subprocess
@@ -30,6 +31,11 @@ def tree(root):
             p = os.path.join(base, f)
             out[os.path.relpath(p, root)] = open(p, "rb").read()
     return out
+
+
+def log_lines(path):
+    """parsnpAligner.log without the values of the elapsed-time lines (the reference's have 1 s resolution)"""
+    return [ln.split(":")[0] if ("elapsed time:" in ln or "running time:" in ln) else ln for ln in open(path).read().splitlines()]
 
 
 seed0 = int(sys.argv[1]); ncases = int(sys.argv[2])
@@ -62,15 +68,21 @@ for it in range(ncases):
         for tag, dump in (("refdump", os.path.join(td, "r", "dump.txt")), ("product", os.path.join(td, "mine.dump"))):
             out = os.path.join(td, tag)
             os.makedirs(out)
-            args = [XTOOL, os.path.join(td, "r", "ref.ini"), dump, os.path.join(out, "parsnpAligner.xmfa"), out]
-            if kw["unaligned"]:
-                args.append(rec)
+            args = [XTOOL, os.path.join(td, "r", "ref.ini"), dump, os.path.join(out, "parsnpAligner.xmfa"), out,
+                    rec if kw["unaligned"] else "-"]
+            if tag == "product":                 # parsnpAligner.log from the product's counters
+                st = res["stats"]
+                with open(os.path.join(td, "logstats.txt"), "w") as f:
+                    f.write("%d %d %d\n" % (st["anchors"], st["mums_filtered"], st["clusters_filtered"]))
+                args.append(os.path.join(td, "logstats.txt"))
             leg = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT).returncode
             if leg == 6 and tag == "refdump":
                 continue                         # overlapping LCBs: the hook dump alone does not say which MUMs an LCB owns
             rc |= leg
             got = {k: v for k, v in tree(out).items() if k in want or k.startswith("blocks")}
             diff += sorted(tag + ":" + k for k in set(want) | set(got) if want.get(k) != got.get(k))
+            if tag == "product" and log_lines(os.path.join(out, "parsnpAligner.log")) != log_lines(os.path.join(r["outdir"], "parsnpAligner.log")):
+                diff.append("product:parsnpAligner.log")
         if runoff and diff and all(x.startswith("product:") or x.endswith(".unalign") for x in diff):
             skipped += 1                         # the binary's own MUM list is heap dependent there (tools/fuzz_host.py)
             continue
