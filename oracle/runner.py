@@ -19,9 +19,10 @@ DEFAULTS = dict(anchors="1.1*(Log(S))", mums="1.1*(Log(S))", filter=1, factor="2
 def write_ini(path, ref, queries, outdir, **kw):
     o = dict(DEFAULTS)
     o.update(kw)
-    L = ["[Reference]", "file=%s" % ref, "reverse=0", "[Query]"]
+    rev = o.pop("reverse", None) or [0] * (len(queries) + 1)      # per genome (reference first): ini reverse / reverse<i>
+    L = ["[Reference]", "file=%s" % ref, "reverse=%d" % rev[0], "[Query]"]
     for i, q in enumerate(queries):
-        L += ["file%d=%s" % (i + 1, q), "reverse%d=0" % (i + 1)]
+        L += ["file%d=%s" % (i + 1, q), "reverse%d=%d" % (i + 1, rev[i + 1])]
     L += ["[MUM]", "anchors=%s" % o["anchors"], "anchorfile=", "anchorsonly=%d" % o["anchorsonly"],
           "calcmumi=%d" % o["calcmumi"], "mums=%s" % o["mums"], "mumfile=", "filter=%d" % o["filter"],
           "factor=%s" % o["factor"], "extendmums=%d" % o["extendmums"],

@@ -15,6 +15,8 @@ import sys
 import tempfile
 import time
 
+import numpy as np
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from parsnp_b200 import api, synth
 from oracle import runner, hosttest
@@ -33,6 +35,31 @@ def tree(root):
     return out
 
 
+def messy_fasta(path, rng, allow_u):
+    """rewrites a FASTA file the way real ones look: lower-case lines, IUPAC codes, '-', U, blanks, digits, '*', blank lines,
+    CRLF - everything the character loop of src/parsnp.cpp:2999-3133 folds, maps to N or skips"""
+    codes = np.frombuffer(b"RYKMSWBDHVNXrykn-" + (b"Uu" if allow_u else b""), np.uint8)
+    out = []
+    for ln in open(path, "rb").read().split(b"\n"):
+        if ln.startswith(b">") or not ln:
+            out.append(ln)
+            continue
+        a = np.frombuffer(ln, np.uint8).copy()
+        if rng.random() < 0.3:
+            a |= 0x20
+        hit = rng.random(len(a)) < 0.003
+        a[hit] = codes[rng.integers(0, len(codes), int(hit.sum()))]
+        b = a.tobytes()
+        if rng.random() < 0.05:
+            k = int(rng.integers(0, len(b) + 1))
+            b = b[:k] + [b" ", b"\t", b"12", b"*", b"zq", b"."][int(rng.integers(0, 6))] + b[k:]
+        out.append(b)
+        if rng.random() < 0.01:
+            out.append(b"")
+    with open(path, "wb") as f:
+        f.write((b"\r\n" if rng.random() < 0.2 else b"\n").join(out))
+
+
 def log_lines(path):
     """parsnpAligner.log without the values of the elapsed-time lines (the reference's have 1 s resolution)"""
     return [ln.split(":")[0] if ("elapsed time:" in ln or "running time:" in ln) else ln for ln in open(path).read().splitlines()]
@@ -49,13 +76,19 @@ for it in range(ncases):
     kw["unaligned"] = int(rng.random() < 0.5)
     with tempfile.TemporaryDirectory() as td:
         rf, qf = synth.write_dataset(os.path.join(td, "d"), g, contigs=contigs)
-        r = runner.run_ref(rf, qf, os.path.join(td, "r"), dump_exit=False, **kw)
+        rev = [0] * len(g)
+        if rng.random() < 0.3:                   # real-life FASTA text and ini reverse flags (whole genome reverse-complemented at ingest)
+            rev = [int(rng.random() < 0.3) for _ in g]
+            for k, path in enumerate([rf] + qf):
+                messy_fasta(path, rng, allow_u=not rev[k])       # (a U stays T under reverse=1, src/parsnp.cpp:3090: not modelled by the numpy ingest)
+        r = runner.run_ref(rf, qf, os.path.join(td, "r"), dump_exit=False, reverse=rev, **kw)
         if r["dump"] is None or r["returncode"] != 0:
             skipped += 1                         # no MUMs, or one of the reference's own crashes
             continue
         hosttest.runoff_skips()
         prm = {k: v for k, v in kw.items() if k not in ("recombfilter", "unaligned")}
         gi = [api.ingest_fasta(rf, True, d=kw.get("d", 300))] + [api.ingest_fasta(x, False, d=kw.get("d", 300)) for x in qf]
+        gi = [synth.revcomp(x) if rv else x for x, rv in zip(gi, rev)]
         res = hosttest.align(gi, api.make_params(flags=api.FLAG_UNALIGNED if kw["unaligned"] else 0, **prm), backend=1)
         runoff = hosttest.runoff_skips()
         rec = os.path.join(td, "unaligned.txt")
