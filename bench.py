@@ -102,7 +102,7 @@ def cpu_reference_run(L, workdir, nq=NQ, seed=SEED):
     from oracle import runner
     g = synth.g_indep(L, nq, DIV, seed)
     ref, qs = synth.write_dataset(os.path.join(workdir, "data"), g)
-    r = runner.run_ref(ref, qs, os.path.join(workdir, "run"), cores=os.cpu_count() or 1)
+    r = runner.run_ref(ref, qs, os.path.join(workdir, "run"), cores=os.cpu_count() or 1, zero_heap=False)    # timed: stock allocator
     bases = sum(len(x) for x in g)
     return bases, r["mumlcb_seconds"], len(r["dump"]["mums"]) if r["dump"] else 0
 

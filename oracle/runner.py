@@ -67,8 +67,11 @@ def parse_cands(path):
     return wins
 
 
-def run_ref(ref, queries, workdir, dump=True, cands=False, dump_exit=True, timeout=None, **kw):
-    """run the reference binary; returns dict(dump=..., cands=..., mumlcb_seconds=..., wall=..., stdout=...)"""
+def run_ref(ref, queries, workdir, dump=True, cands=False, dump_exit=True, timeout=None, zero_heap=True, **kw):
+    """run the reference binary; returns dict(dump=..., cands=..., mumlcb_seconds=..., wall=..., stdout=...).
+    zero_heap (default): glibc hands out zero-filled memory (MALLOC_PERTURB_=255, tcache off) - the binary never initialises
+    MasterRC[].UP (src/parsnp.cpp:1591-1597), so on small windows its answer otherwise depends on stale heap contents; with the
+    fill it is the function of its inputs the product implements.  Timed runs (bench.py) switch it off."""
     if not os.path.exists(EXE):
         raise RuntimeError("oracle/_ref/parsnp_core_ref missing: run python oracle/build_ref.py")
     os.makedirs(workdir, exist_ok=True)
@@ -76,6 +79,9 @@ def run_ref(ref, queries, workdir, dump=True, cands=False, dump_exit=True, timeo
     os.makedirs(outdir, exist_ok=True)
     ini = write_ini(os.path.join(workdir, "ref.ini"), ref, queries, outdir, **kw)
     env = dict(os.environ)
+    if zero_heap:
+        env["MALLOC_PERTURB_"] = "255"
+        env["GLIBC_TUNABLES"] = "glibc.malloc.tcache_count=0"
     res = {}
     if dump:
         env["PARSNP_ORACLE_DUMP"] = os.path.join(workdir, "dump.txt")

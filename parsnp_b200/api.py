@@ -197,7 +197,7 @@ def unpack_result(lib, h):
     cs = np.zeros((K, n), np.int64); ce = np.zeros((K, n), np.int64)
     lib.pb200_result_clusters(h, _ptr(ctype), _ptr(cn), _ptr(cl), _ptr(cs), _ptr(ce))
     cmo = np.zeros(K + 1, np.int64)
-    cmi = np.zeros(max(1, lib.pb200_result_cluster_mums(h, None, None)), np.int64)
+    cmi = np.empty(max(1, lib.pb200_result_cluster_mums(h, None, None)), np.int64)
     nidx = lib.pb200_result_cluster_mums(h, _ptr(cmo), _ptr(cmi))
     T = lib.pb200_result_num_trace(h)
     tr = np.zeros((T, 2), np.int64)

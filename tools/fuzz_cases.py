@@ -3,6 +3,8 @@
 make_case(seed) -> (genomes, contigs, ini keywords, description, rng): random genome sets (independent / population divergence,
 repeats and N runs in the reference, inversions, deletions, insertions, whole-query reverse complements, up to 13 queries,
 multi-contig FASTA) x random ini values (c, d, q, diagdiff, p -> several reference windows, length expressions, filter)."""
+import os
+
 import numpy as np
 
 from parsnp_b200 import synth
@@ -10,7 +12,7 @@ from parsnp_b200 import synth
 
 def make_case(seed):
     rng = np.random.default_rng(seed)
-    L = int(rng.choice([8000, 20000, 50000, 90000]))
+    L = int(rng.choice([8000, 20000, 50000, 90000])) * int(os.environ.get("FUZZ_SCALE", "1"))    # FUZZ_SCALE=4: up to 360 kbp
     nq = int(rng.integers(1, 6))
     div = float(rng.choice([0.005, 0.01, 0.03, 0.06]))
     if rng.random() < 0.5:

@@ -34,6 +34,8 @@ for it in range(ncases):
         gi = [api.ingest_fasta(rf, True, d=kw.get("d", 300))] + [api.ingest_fasta(x, False, d=kw.get("d", 300)) for x in qf]
     os.environ["PB200_SPEC_SLICES"] = str(int(rng.choice([1, 3, 8])))
     os.environ["PB200_PAR_ANCHORS_MIN"] = str(int(rng.choice([1, 10**9])))
+    if rng.random() < 0.25:                     # the defaults: slices by the number of initial regions, parallel accept by size
+        del os.environ["PB200_SPEC_SLICES"], os.environ["PB200_PAR_ANCHORS_MIN"]
     hosttest.runoff_skips()
     res = hosttest.align(gi, api.make_params(**kw), backend=1)
     runoff = hosttest.runoff_skips()
