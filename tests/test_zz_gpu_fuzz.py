@@ -1,0 +1,37 @@
+"""CUDA search against the reference's csgmum on random cases (runs last: the fixed parity cases come first).
+
+The host orchestrator is the same on both sides (parsnp_b200/csrc/host); only the search differs - the CUDA engine behind
+pb200_align_resident versus the unmodified csg.c + mum.c behind oracle/ref_backend.cpp - so any difference is a kernel
+difference.  The csgmum side was itself compared with the reference binary on the same generator (tools/fuzz_host.py, thousands
+of cases on the CPU).  Where csgmum's Find_UM would have read past a query buffer the checker skips the call, which is the
+product's semantics (no seed), so those cases stay comparable here."""
+import os
+import tempfile
+
+import pytest
+
+from tests.conftest import ROOT
+from tests.refcmp import result_to_dump, diff_dumps
+
+have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libpb200_hosttest.so"))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not have_ref, reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed0", [80000, 80012, 80024, 80036])
+def test_cuda_search_fuzz_against_csgmum(seed0):
+    from oracle import hosttest
+    from parsnp_b200 import api, synth
+    from tools.fuzz_cases import make_case
+    bad = []
+    for seed in range(seed0, seed0 + 12):
+        g, contigs, kw, desc, _ = make_case(seed)
+        with tempfile.TemporaryDirectory() as td:
+            rf, qf = synth.write_dataset(os.path.join(td, "d"), g, contigs=contigs)
+            gi = [api.ingest_fasta(rf, True, d=kw.get("d", 300))] + [api.ingest_fasta(x, False, d=kw.get("d", 300)) for x in qf]
+        want = hosttest.align(gi, api.make_params(**kw), backend=1)
+        got = api.align(gi, api.make_params(**kw))
+        d = diff_dumps(result_to_dump(got), result_to_dump(want))
+        if d or got["no_mums"] != want["no_mums"]:
+            bad.append((seed, desc, kw, d[:2]))
+    assert bad == []
