@@ -35,3 +35,38 @@ def test_cuda_search_fuzz_against_csgmum(seed0):
         if d or got["no_mums"] != want["no_mums"]:
             bad.append((seed, desc, kw, d[:2]))
     assert bad == []
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not have_ref, reason="oracle/_ref not built")
+@pytest.mark.parametrize("force_big", [False, True])
+def test_cuda_window_fuzz_wide_regimes(force_big):
+    """single windows far from the comfortable regime - homopolymers and two-letter alphabets (everything repeats), N runs in
+    both sequences, 30 to 1 200 bases, up to 6 queries, minsize 2 to 13 (below 4 the engine must leave the shared-memory
+    path) - through the shared-memory path and forced through the suffix-array path == real csgmum (oracle/ref_backend.cpp);
+    tools/fuzz_spec.py runs the same generator for the CPU specification (23 000 windows, no difference)"""
+    import numpy as np
+    from oracle import hosttest
+    from parsnp_b200 import api
+    from tests.conftest import random_case, whole_window_task
+    rng = np.random.default_rng(4242 + force_big)
+    bad, total = [], 0
+    if force_big:
+        os.environ["PB200_FORCE_PATH"] = "big"
+    try:
+        for it in range(160):
+            alphabet = [b"AT", b"ACGT", b"ACGT", b"AACGGT", b"A", b"AC"][int(rng.integers(0, 6))]
+            with_n = bool(rng.random() < 0.5)
+            g = random_case(rng, 30, int(rng.choice([60, 160, 400, 1200])), 6, alphabet, with_n)
+            minsize = int(rng.integers(2, 14))
+            w, coords = whole_window_task(g, minsize)
+            want = hosttest.search_windows(g, w, coords, backend=1)[0]
+            G = api.Genomes(g)
+            got = G.search_windows(w, coords)[0]
+            G.close()
+            if not all(np.array_equal(x, y) for x, y in zip(got, want)):
+                bad.append((it, alphabet, with_n, minsize, [len(x) for x in g]))
+            total += len(want[0])
+    finally:
+        os.environ.pop("PB200_FORCE_PATH", None)
+    assert bad == [] and total > 100
