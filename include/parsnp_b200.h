@@ -155,7 +155,10 @@ void pb200_engine_reset_timers(pb200_genomes* g);
 typedef int (*pb200_allgather_cb)(void* user, const void* send, void* recv, int64_t bytes_per_rank, int on_device);
 typedef int (*pb200_allreduce_cb)(void* user, void* buf_i32, int64_t count, int is_max, int on_device);   /* int32 min / max */
 typedef int (*pb200_bcast_cb)(void* user, void* buf, int64_t bytes, int root, int on_device);
-/* bcast_index != 0: the window index is built on rank 0 and broadcast; 0: every rank rebuilds it */
+/* Every rank must then call pb200_align* with the same genomes and parameters: the ranks run in lock step and every search
+ * starts with a 16-byte all-gather that compares their window lists - ranks that are out of step get PB200_ERR_INTERNAL
+ * ("not searching the same windows"), never each other's candidates.
+ * bcast_index != 0: the window index is built on rank 0 and broadcast; 0: every rank rebuilds it */
 int pb200_comm_set(pb200_genomes* g, int rank, int world, pb200_allgather_cb ag, pb200_allreduce_cb ar, pb200_bcast_cb bc,
                    void* user, int bcast_index);
 void pb200_comm_clear(pb200_genomes* g);
