@@ -23,7 +23,7 @@ from oracle import runner, hosttest
 from tools.fuzz_cases import make_case
 from tests.refcmp import write_dump
 
-XTOOL = os.path.join(os.path.dirname(runner.EXE), "xmfa_from_dump")
+XTOOL = os.environ.get("PB200_XTOOL") or os.path.join(os.path.dirname(runner.EXE), "xmfa_from_dump")
 
 
 def tree(root):
