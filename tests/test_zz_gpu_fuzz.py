@@ -70,3 +70,26 @@ def test_cuda_window_fuzz_wide_regimes(force_big):
     finally:
         os.environ.pop("PB200_FORCE_PATH", None)
     assert bad == [] and total > 100
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "parsnp_core_ref")), reason="oracle/_ref not built")
+def test_cuda_mumi_fuzz_against_reference_binary():
+    """calcmumi=1 on 12 random cases (rearranged queries, contigs, several reference windows): pb200_mumi == the distances the
+    reference binary, run here on the zero-filled heap, prints to all.mumi - to the digit"""
+    from oracle import runner
+    from parsnp_b200 import api, synth
+    from tools.fuzz_cases import make_case
+    bad = []
+    for seed in range(81000, 81012):
+        g, contigs, kw, desc, _ = make_case(seed)
+        with tempfile.TemporaryDirectory() as td:
+            rf, qf = synth.write_dataset(os.path.join(td, "d"), g, contigs=contigs)
+            want = runner.run_ref_mumi(rf, qf, os.path.join(td, "r"), **kw)
+            gi = [api.ingest_fasta(rf, True, d=kw.get("d", 300))] + [api.ingest_fasta(x, False, d=kw.get("d", 300)) for x in qf]
+        G = api.Genomes(gi)
+        got = ["%f" % v for v in G.mumi(api.make_params(**kw))]
+        G.close()
+        if got != want:
+            bad.append((seed, desc, kw, got, want))
+    assert bad == []
