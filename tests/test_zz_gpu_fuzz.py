@@ -22,15 +22,15 @@ have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libpb200_hosttes
 def test_cuda_search_fuzz_against_csgmum(seed0):
     from oracle import hosttest
     from parsnp_b200 import api, synth
-    from tools.fuzz_cases import make_case
+    from tools.fuzz_cases import make_case, params_kw
     bad = []
     for seed in range(seed0, seed0 + 12):
         g, contigs, kw, desc, _ = make_case(seed)
         with tempfile.TemporaryDirectory() as td:
             rf, qf = synth.write_dataset(os.path.join(td, "d"), g, contigs=contigs)
             gi = [api.ingest_fasta(rf, True, d=kw.get("d", 300))] + [api.ingest_fasta(x, False, d=kw.get("d", 300)) for x in qf]
-        want = hosttest.align(gi, api.make_params(**kw), backend=1)
-        got = api.align(gi, api.make_params(**kw))
+        want = hosttest.align(gi, api.make_params(**params_kw(kw)), backend=1)
+        got = api.align(gi, api.make_params(**params_kw(kw)))
         d = diff_dumps(result_to_dump(got), result_to_dump(want))
         if d or got["no_mums"] != want["no_mums"]:
             bad.append((seed, desc, kw, d[:2]))
@@ -79,7 +79,7 @@ def test_cuda_mumi_fuzz_against_reference_binary():
     reference binary, run here on the zero-filled heap, prints to all.mumi - to the digit"""
     from oracle import runner
     from parsnp_b200 import api, synth
-    from tools.fuzz_cases import make_case
+    from tools.fuzz_cases import make_case, params_kw
     bad = []
     for seed in range(81000, 81012):
         g, contigs, kw, desc, _ = make_case(seed)
@@ -88,7 +88,7 @@ def test_cuda_mumi_fuzz_against_reference_binary():
             want = runner.run_ref_mumi(rf, qf, os.path.join(td, "r"), **kw)
             gi = [api.ingest_fasta(rf, True, d=kw.get("d", 300))] + [api.ingest_fasta(x, False, d=kw.get("d", 300)) for x in qf]
         G = api.Genomes(gi)
-        got = ["%f" % v for v in G.mumi(api.make_params(**kw))]
+        got = ["%f" % v for v in G.mumi(api.make_params(**params_kw(kw)))]
         G.close()
         if got != want:
             bad.append((seed, desc, kw, got, want))

@@ -2,7 +2,7 @@
 
 make_case(seed) -> (genomes, contigs, ini keywords, description, rng): random genome sets (independent / population divergence,
 repeats and N runs in the reference, inversions, deletions, insertions, whole-query reverse complements, up to 13 queries,
-multi-contig FASTA) x random ini values (c, d, q, diagdiff, p -> several reference windows, length expressions, filter)."""
+multi-contig FASTA) x random ini values (c, d, q, diagdiff, p -> several reference windows, length expressions, filter, anchorsonly)."""
 import os
 
 import numpy as np
@@ -54,4 +54,14 @@ def make_case(seed):
             hit = rng.random(len(x)) < float(rng.choice([0.002, 0.01, 0.03]))
             x[hit] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(hit.sum()))]
             g.append(x)
+    if rng.random() < 0.1:
+        kw["anchorsonly"] = 1                    # ini [MUM] anchorsonly: no recursion into the regions between the anchors
     return g, contigs, kw, (L, nq, div), rng
+
+
+def params_kw(kw):
+    """ini keywords of a case (oracle/runner.py write_ini) -> keywords of api.make_params"""
+    out = {k: v for k, v in kw.items() if k not in ("recombfilter", "unaligned", "anchorsonly")}
+    if kw.get("anchorsonly"):
+        out["anchors_only"] = 1
+    return out

@@ -21,7 +21,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from parsnp_b200 import api, synth
 from oracle import runner, hosttest
 from tests.refcmp import result_to_dump, diff_dumps
-from tools.fuzz_cases import make_case
+from tools.fuzz_cases import make_case, params_kw
 seed0 = int(sys.argv[1]); ncases = int(sys.argv[2])
 bad = 0
 ub = 0
@@ -37,12 +37,12 @@ for it in range(ncases):
     if rng.random() < 0.25:                     # the defaults: slices by the number of initial regions, parallel accept by size
         del os.environ["PB200_SPEC_SLICES"], os.environ["PB200_PAR_ANCHORS_MIN"]
     hosttest.runoff_skips()
-    res = hosttest.align(gi, api.make_params(**kw), backend=1)
+    res = hosttest.align(gi, api.make_params(**params_kw(kw)), backend=1)
     runoff = hosttest.runoff_skips()
     world = int(os.environ.get("FUZZ_WORLD", "0"))
     if world > 1:                               # N>1 host path (thread ranks): every rank must hold the single-rank result
         mine = result_to_dump(res)
-        outs, counters = hosttest.ThreadRanks(world).align(gi, api.make_params(**kw))
+        outs, counters = hosttest.ThreadRanks(world).align(gi, api.make_params(**params_kw(kw)))
         for rk, o in enumerate(outs):
             dd = diff_dumps(result_to_dump(o), mine)
             if dd or o["no_mums"] != res["no_mums"]:

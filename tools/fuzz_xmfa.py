@@ -20,7 +20,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from parsnp_b200 import api, synth
 from oracle import runner, hosttest
-from tools.fuzz_cases import make_case
+from tools.fuzz_cases import make_case, params_kw
 from tests.refcmp import write_dump
 
 XTOOL = os.environ.get("PB200_XTOOL") or os.path.join(os.path.dirname(runner.EXE), "xmfa_from_dump")
@@ -86,7 +86,7 @@ for it in range(ncases):
             skipped += 1                         # no MUMs, or one of the reference's own crashes
             continue
         hosttest.runoff_skips()
-        prm = {k: v for k, v in kw.items() if k not in ("recombfilter", "unaligned")}
+        prm = params_kw(kw)
         gi = [api.ingest_fasta(rf, True, d=kw.get("d", 300))] + [api.ingest_fasta(x, False, d=kw.get("d", 300)) for x in qf]
         gi = [synth.revcomp(x) if rv else x for x, rv in zip(gi, rev)]
         res = hosttest.align(gi, api.make_params(flags=api.FLAG_UNALIGNED if kw["unaligned"] else 0, **prm), backend=1)
