@@ -61,7 +61,7 @@ def make_case(seed):
 
 def params_kw(kw):
     """ini keywords of a case (oracle/runner.py write_ini) -> keywords of api.make_params"""
-    out = {k: v for k, v in kw.items() if k not in ("recombfilter", "unaligned", "anchorsonly")}
+    out = {k: v for k, v in kw.items() if k not in ("recombfilter", "unaligned", "anchorsonly", "doalign")}
     if kw.get("anchorsonly"):
         out["anchors_only"] = 1
     return out

@@ -74,6 +74,8 @@ for it in range(ncases):
         g = [x[:50000] for x in g]              # bounds the libMUSCLE time of a case
     kw["recombfilter"] = int(rng.random() < 0.4)
     kw["unaligned"] = int(rng.random() < 0.5)
+    if rng.random() < 0.08:
+        kw["doalign"] = 0                        # ini [LCB] doalign=0: header and statistics only, no LCB records
     with tempfile.TemporaryDirectory() as td:
         rf, qf = synth.write_dataset(os.path.join(td, "d"), g, contigs=contigs)
         rev = [0] * len(g)
