@@ -101,6 +101,17 @@ def test_minsize_matches_reference_calculator():
         assert ht.pb200_minsize(b"1.1*(Log(S))", s) == want
 
 
+def test_minsize_fuzz_random_expressions():
+    """tools/fuzz_minsize.py: 400 random infix expressions x 14 lengths == the reference's Converter + Calculator wherever the
+    reference survives the expression"""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_minsize.py"), "7", "400"], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and " differ 0 " in r.stdout, r.stdout[-1500:]
+    assert int(r.stdout.split(" equal ")[1].split()[0]) > 200
+
+
 @pytest.mark.parametrize("name", ["c1a", "c1b", "indep_20k", "rearr_60k", "windows_50k", "pop_30k_x12", "c1c"])
 def test_host_orchestrator_reproduces_reference(name):
     """the product's host logic (queue order, trim, accept, LCB chaining) fed by the reference's own search == golden"""
