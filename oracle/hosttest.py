@@ -49,7 +49,7 @@ class ThreadRanks:
 
     def __init__(self, world):
         import threading
-        self.world, self.bar, self.slot = world, threading.Barrier(world), [None] * world
+        self.world, self.bar, self.slot = world, threading.Barrier(world, timeout=300), [None] * world   # a rank that never arrives breaks the barrier instead of hanging the test
         self.calls = 0
 
     def _callbacks(self, rank):
