@@ -8,6 +8,11 @@
 #include <cstdlib>
 #include <vector>
 #include <algorithm>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
 #include "../parsnp_b200/csrc/common.h"
 #include "../parsnp_b200/csrc/host/sharded.h"
 
@@ -157,7 +162,85 @@ private:
     std::vector<std::vector<unsigned long>> msp_; std::vector<std::vector<char>> fw_;
 };
 
+// Record/replay: answers every window it has seen before from a process-wide table and sends the others to csgmum, in parallel
+// (the windows are independent).  After one warm-up alignment the same input runs with a search that costs next to nothing,
+// i.e. the host orchestrator alone can be timed on the CPU at the sizes where the GPU makes the search disappear
+// (tools/host_bench.py).  The key is the window itself (reference interval, minimum length, query intervals), so the way the
+// orchestrator batches its windows does not matter.
+class RecordReplayBackend : public pb200::SearchBackend {
+public:
+    struct Entry { std::vector<int32_t> k, lon, sp; std::vector<uint8_t> fwd; };
+    void set_genomes(int n, const uint8_t* const* seq, const int64_t* len) override {
+        n_ = n; seq_.assign(seq, seq + n); len_.assign(len, len + n);
+    }
+    void search(const pb200::WindowTask* tasks, int ntasks, const int64_t* coords, pb200::CandBatch& out) override {
+        const int nq = n_ - 1;
+        std::vector<std::string> keys((size_t)ntasks);
+        std::vector<const Entry*> hit((size_t)ntasks, nullptr);
+        std::vector<int> miss;
+        {
+            std::lock_guard<std::mutex> lk(mu());
+            for (int t = 0; t < ntasks; ++t) {
+                std::string& key = keys[t];
+                key.assign((const char*)&tasks[t].ref_start, 8); key.append((const char*)&tasks[t].ref_len, 8);
+                key.append((const char*)&tasks[t].minsize, 4); key.append((const char*)(coords + tasks[t].coord_off), (size_t)16 * nq);
+                auto it = table().find(key);
+                if (it != table().end()) hit[t] = it->second.get(); else miss.push_back(t);
+            }
+        }
+        if (!miss.empty()) {
+            std::vector<std::unique_ptr<Entry>> fresh(miss.size());
+            std::atomic<size_t> next{0};
+            auto work = [&]() {
+                RefBackend rb;
+                rb.set_genomes(n_, seq_.data(), len_.data());
+                pb200::CandBatch cb;
+                for (size_t i; (i = next.fetch_add(1)) < miss.size();) {
+                    rb.search(&tasks[miss[i]], 1, coords, cb);
+                    std::unique_ptr<Entry> e(new Entry);
+                    e->k.assign(cb.k.begin(), cb.k.end()); e->lon.assign(cb.lon.begin(), cb.lon.end());
+                    e->sp.assign(cb.sp.begin(), cb.sp.end()); e->fwd.assign(cb.fwd.begin(), cb.fwd.end());
+                    fresh[i] = std::move(e);
+                }
+            };
+            const unsigned T = std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), miss.size());
+            std::vector<std::thread> th;
+            for (unsigned i = 1; i < T; ++i) th.emplace_back(work);
+            work();
+            for (auto& x : th) x.join();
+            std::lock_guard<std::mutex> lk(mu());
+            for (size_t i = 0; i < miss.size(); ++i) {
+                auto ins = table().emplace(keys[miss[i]], std::move(fresh[i]));
+                hit[miss[i]] = ins.first->second.get();
+            }
+            misses() += (long)miss.size();
+        }
+        out.clear(); out.nq = nq; out.off.assign((size_t)ntasks + 1, 0);
+        for (int t = 0; t < ntasks; ++t) out.off[t + 1] = out.off[t] + (int64_t)hit[t]->k.size();
+        const size_t tot = (size_t)out.off[ntasks];
+        out.k.resize(tot); out.lon.resize(tot); out.sp.resize(tot * nq); out.fwd.resize(tot * nq);
+        for (int t = 0; t < ntasks; ++t) {
+            const Entry& e = *hit[t];
+            const size_t b = (size_t)out.off[t], c = e.k.size();
+            if (!c) continue;
+            std::memcpy(out.k.data() + b, e.k.data(), c * 4);
+            std::memcpy(out.lon.data() + b, e.lon.data(), c * 4);
+            if (nq) { std::memcpy(out.sp.data() + b * nq, e.sp.data(), c * nq * 4); std::memcpy(out.fwd.data() + b * nq, e.fwd.data(), c * nq); }
+        }
+    }
+    static std::mutex& mu() { static std::mutex m; return m; }
+    static std::unordered_map<std::string, std::unique_ptr<Entry>>& table() { static std::unordered_map<std::string, std::unique_ptr<Entry>> t; return t; }
+    static long& misses() { static long m = 0; return m; }
+private:
+    int n_ = 0;
+    std::vector<const uint8_t*> seq_;
+    std::vector<int64_t> len_;
+};
+extern "C" long pbtest_replay_misses(int reset) { long v = RecordReplayBackend::misses(); if (reset) RecordReplayBackend::misses() = 0; return v; }
+extern "C" void pbtest_replay_clear() { std::lock_guard<std::mutex> lk(RecordReplayBackend::mu()); RecordReplayBackend::table().clear(); }
+
 pb200::SearchBackend* make_ref_backend() { return new RefBackend(); }
+pb200::SearchBackend* make_replay_backend() { return new RecordReplayBackend(); }
 pb200::StagedWindowEngine* as_staged(pb200::SearchBackend* b) { return dynamic_cast<RefBackend*>(b); }
 
 }  // namespace pb200_oracle

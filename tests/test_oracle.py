@@ -101,6 +101,24 @@ def test_minsize_matches_reference_calculator():
         assert ht.pb200_minsize(b"1.1*(Log(S))", s) == want
 
 
+def test_record_replay_backend_is_transparent():
+    """the record/replay search backend of tools/host_bench.py (oracle/ref_backend.cpp): same alignment as csgmum directly, and
+    the second run of an input finds every window in the table"""
+    import ctypes
+    from oracle import hosttest
+    g, kw, gold = golden_case("rearr_60k")
+    lib = hosttest.load()
+    lib.pbtest_replay_misses.restype = ctypes.c_long
+    lib.pbtest_replay_clear()
+    lib.pbtest_replay_misses(1)
+    a = hosttest.align(g, api.make_params(**kw), backend=2)
+    assert lib.pbtest_replay_misses(1) > 100
+    b = hosttest.align(g, api.make_params(**kw), backend=2)
+    assert lib.pbtest_replay_misses(1) == 0
+    assert diff_dumps(result_to_dump(a), gold) == [] and diff_dumps(result_to_dump(b), gold) == []
+    lib.pbtest_replay_clear()
+
+
 def test_minsize_fuzz_random_expressions():
     """tools/fuzz_minsize.py: 400 random infix expressions x 14 lengths == the reference's Converter + Calculator wherever the
     reference survives the expression"""
