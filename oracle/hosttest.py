@@ -13,7 +13,11 @@ _lib = None
 def load():
     global _lib
     if _lib is None:
-        _lib = C.CDLL(LIB)
+        # RTLD_DEEPBIND: the library holds its own copy of the host orchestrator; in a process that has also loaded the product
+        # library (RTLD_GLOBAL, parsnp_b200/api.py) its calls must keep binding to that copy, not to the product's.
+        # (Sanitizer runtimes refuse DEEPBIND: not used when one is preloaded.)
+        mode = C.DEFAULT_MODE if os.environ.get("LD_PRELOAD") else (os.RTLD_NOW | os.RTLD_LOCAL | os.RTLD_DEEPBIND)
+        _lib = C.CDLL(LIB, mode=mode)
         api._decl_result_api(_lib)
         vp = C.c_void_p
         _lib.pbtest_align.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp]
