@@ -76,6 +76,9 @@ const char* pb200_version(void);
 
 /* 1 when a CUDA device of compute capability >= 10.0 is present and the kernels are loadable, else 0 */
 int pb200_cuda_available(void);
+/* number of CUDA devices this process can see (CUDA_VISIBLE_DEVICES applies); 0 without a driver.  parsnp_b200_core uses it to
+ * spread the concurrent copies the Python driver launches (parsnp:1572-1597) over the GPUs of a box. */
+int pb200_device_count(void);
 
 /* ---- genomes ---- */
 /* seqs[i] = ASCII text of genome i (A,C,G,T,N), lens[i] its length; genome 0 is the reference.
@@ -100,7 +103,12 @@ int pb200_search_windows(pb200_genomes* g, int ntasks, const pb200_window* tasks
                          int64_t** cand_off, int32_t** k, int32_t** lon, int32_t** sp, uint8_t** fwd);
 void pb200_free_buffer(void* p);
 
-/* ---- B1: the whole MUM + LCB path ---- */
+/* ---- B1: the whole MUM + LCB path ----
+ * Return value PB200_OK, or PB200_ERR_NO_MUMS when the anchor search found nothing (the reference then writes
+ * "NO MUMS FOUND" and exits 0, src/parsnp.cpp:3223-3229): in BOTH cases *out is a valid result (empty lists for NO_MUMS,
+ * its stats filled) that the caller must release with pb200_result_free.  On every other negative status *out is untouched.
+ * An invalid minimum-length expression (e.g. "S/0") is reported as PB200_ERR_ARG (the reference's calculator calls exit(1),
+ * src/Converter.cpp:252; a library must not end its host process). */
 int pb200_align_resident(pb200_genomes* g, const pb200_params* prm, pb200_result** out);
 /* convenience: upload + align + free the device copy (the end-to-end call a user makes with host buffers) */
 int pb200_align(int device, int n, const uint8_t* const* seqs, const int64_t* lens, const pb200_params* prm,

@@ -530,6 +530,7 @@ int guarded(F&& f) {
         std::string s = e.what();
         return (s.find("requires a CUDA device") != std::string::npos || s.find("sm_100a") != std::string::npos) ? PB200_ERR_NO_CUDA : PB200_ERR_CUDA;
     }
+    catch (const std::invalid_argument& e) { pb200::g_last_error = e.what(); return PB200_ERR_ARG; }
     catch (const std::exception& e) { pb200::g_last_error = e.what(); return PB200_ERR_INTERNAL; }
 }
 }  // namespace
@@ -544,6 +545,12 @@ int pb200_cuda_available(void) {
     cudaDeviceProp p;
     if (cudaGetDeviceProperties(&p, 0) != cudaSuccess) return 0;
     return p.major >= 10 ? 1 : 0;
+}
+
+int pb200_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return count;
 }
 
 int pb200_genomes_create(int device, int n, const uint8_t* const* seqs, const int64_t* lens, pb200_genomes** out) {

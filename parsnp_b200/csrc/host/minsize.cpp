@@ -1,4 +1,5 @@
 #include "minsize.h"
+#include <stdexcept>
 #include <cmath>
 #include <cctype>
 #include <cstdlib>
@@ -88,7 +89,7 @@ float minsize_eval(const std::string& in, float seqlen) {
                 case '+': x = st.pop(); y = st.pop(); z = y + x; st.push(z); break;
                 case '-': x = st.pop(); y = st.pop(); z = y - x; st.push(z); break;
                 case '*': x = st.pop(); y = st.pop(); z = y * x; st.push(z); break;
-                case '/': x = st.pop(); y = st.pop(); if (x == 0) exit(1); z = y / x; st.push(z); break;
+                case '/': x = st.pop(); y = st.pop(); if (x == 0) throw std::invalid_argument("parsnp_b200: division by zero in the minimum-length expression"); z = y / x; st.push(z); break;
                 case '^': x = st.pop(); y = st.pop(); z = std::pow(y, x); st.push(z); break;
                 case 'L': x = st.pop(); z = (float)(std::log(x) / std::log(2.0)); st.push(z); break;
                 default: break;

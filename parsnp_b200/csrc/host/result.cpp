@@ -123,6 +123,10 @@ const char* pb200_stats_names(void) {
            "t_anchor_search,t_anchor_host,t_spec_search,t_spec_host,t_replay,t_replay_search,t_lcb,t_total,host_threads,t_search_prep,t_search_backend,t_search_cache,t_replay_wait,spec_slices,mums_filtered,clusters_filtered";
 }
 void pb200_result_free(pb200_result* r) { delete r; }
-int pb200_minsize(const char* expr, int64_t slength) { return pb200::MinSizeExpr(expr)(slength); }
+int pb200_minsize(const char* expr, int64_t slength) {
+    // (the reference's calculator exits the process on a division by zero, src/Converter.cpp:252; here: -1 + pb200_last_error)
+    try { return pb200::MinSizeExpr(expr)(slength); }
+    catch (const std::exception& e) { pb200::g_last_error = e.what(); return -1; }
+}
 void pb200_free_buffer(void* p) { free(p); }
 }

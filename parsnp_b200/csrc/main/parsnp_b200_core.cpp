@@ -16,6 +16,9 @@
 #include <string>
 #include <vector>
 #include <sys/stat.h>
+#include <sys/file.h>
+#include <fcntl.h>
+#include <unistd.h>
 #include <sys/types.h>
 #include "../../../include/parsnp_b200.h"
 #include "../host/ingest.h"
@@ -26,6 +29,25 @@ using namespace std;
 static string basename_of(const string& p) {       // src/parsnp.cpp:2925-2931
     size_t loc = p.rfind('/');
     return loc == string::npos ? p : p.substr(loc + 1);
+}
+
+// one advisory lock file per device ordinal; returns the chosen ordinal (the descriptor stays open = locked until exit)
+static int choose_device() {
+    if (const char* e = getenv("PB200_DEVICE")) return atoi(e);
+    const int count = pb200_device_count();
+    if (count <= 1) return 0;
+    const char* dir = getenv("PB200_LOCK_DIR");
+    const string base = string(dir && *dir ? dir : "/tmp") + "/parsnp_b200.gpu";
+    const int first = (int)(getpid() % count);
+    for (int t = 0; t < count; t++) {
+        const int k = (first + t) % count;                  // start at pid % count: concurrent starters probe different files first
+        const string path = base + to_string(k) + ".lock";
+        int fd = open(path.c_str(), O_CREAT | O_RDWR, 0666);
+        if (fd < 0) continue;
+        if (flock(fd, LOCK_EX | LOCK_NB) == 0) return k;    // (never closed: released by the kernel at exit)
+        close(fd);
+    }
+    return first;                                           // more processes than devices: share round-robin
 }
 
 int main(int argc, char** argv) {
@@ -85,8 +107,11 @@ int main(int argc, char** argv) {
     vector<const uint8_t*> seqs;
     vector<int64_t> lens;
     for (auto& g : G) { seqs.push_back((const uint8_t*)g.text.data()); lens.push_back((int64_t)g.text.size()); }
-    int device = 0;
-    if (const char* e = getenv("PB200_DEVICE")) device = atoi(e);
+    // GPU choice is implicit: the Python driver launches up to min(threads, partitions) concurrent copies of this binary with
+    // identical arguments apart from the ini (parsnp:1572-1597), so the processes spread themselves over the visible devices
+    // (CUDA_VISIBLE_DEVICES is honoured by the runtime): PB200_DEVICE if set, else the first device whose advisory lock file
+    // is free, else pid % devices.  The lock (flock on /tmp/parsnp_b200.gpu<k>.lock) is held until the process exits.
+    int device = choose_device();
 
     pb200_genomes* dev = nullptr;
     int rc = pb200_genomes_create(device, n, seqs.data(), lens.data(), &dev);
@@ -119,6 +144,8 @@ int main(int argc, char** argv) {
     if (rc == PB200_ERR_NO_MUMS) {                          // src/parsnp.cpp:3223-3229
         ofstream mfile(logpath.c_str());
         mfile << "NO MUMS FOUND" << endl;
+        pb200_result_free(res);                             // (*out is valid on PB200_ERR_NO_MUMS, see parsnp_b200.h)
+        pb200_genomes_free(dev);
         return 0;
     }
     if (rc != 0) { cerr << "parsnp_b200_core: " << pb200_last_error() << endl; return 1; }
@@ -176,7 +203,13 @@ int main(int argc, char** argv) {
         xi.cmum_idx.resize((size_t)max(tot, 1));
         pb200_result_cluster_mums(res, xi.cmum_off.data(), xi.cmum_idx.data());
         xi.mlen = mlen; xi.mstart = mst; xi.mend = men; xi.mfwd = mfw;
-        if (!pb200::muscle_available()) cerr << "parsnp_b200_core: built without libMUSCLE - no XMFA written" << endl;
+        { ofstream allmums("allmums.out"); }              // the reference creates this (empty) file in the CWD: src/parsnp.cpp:600-601
+        if (!pb200::muscle_available()) {
+            // the XMFA is the main output of this process: without the inter-MUM aligner there is none, and the Python driver
+            // treats exit code 0 as success (parsnp:1146) - so this build configuration fails loudly
+            cerr << "parsnp_b200_core: built without libMUSCLE - cannot write parsnpAligner.xmfa (rebuild with PB200_MUSCLE_SRC=<parsnp>/muscle)" << endl;
+            return 1;
+        }
         else if (!pb200::write_xmfa(xi, outdir + "/parsnpAligner.xmfa")) { cerr << "parsnp_b200_core: XMFA writer failed" << endl; return 1; }
         if (do_unalign) {                                   // src/parsnp.cpp:3283-3287
             const int64_t U = pb200_result_unaligned(res, nullptr, nullptr, nullptr);

@@ -48,3 +48,18 @@ def diff_dumps(a, b, limit=5):
             if len(out) > 2 * limit:
                 break
     return out
+
+
+def dump_lines(res):
+    """the product's result as the lines of the reference's hook dump (oracle/build_ref.py H1: 'N', 'M ...', 'C ...'), without
+    newlines - vectorised, for full-size results (10^5..10^6 MUMs)"""
+    yield "N %d" % res["n"]
+    ln, sl = res["mum_length"], res["mum_slength"]
+    st, en, fw = res["mum_start"], res["mum_end"], res["mum_fwd"]
+    n = st.shape[1] if len(ln) else 0
+    for i in range(len(ln)):
+        yield "M %d %d " % (ln[i], sl[i]) + " ".join("%d:%d:%d" % (st[i, k], en[i, k], fw[i, k]) for k in range(n))
+    ct, cn, cl = res["cluster_type"], res["cluster_nmums"], res["cluster_length"]
+    cs, ce = res["cluster_start"], res["cluster_end"]
+    for i in range(len(ct)):
+        yield "C %d %d %d " % (ct[i], cn[i], cl[i]) + " ".join("%d:%d" % (cs[i, k], ce[i, k]) for k in range(cs.shape[1]))
