@@ -70,6 +70,29 @@ struct CandBatch {
     }
 };
 
+// Device-resident discovery of the recursion (cuda/recursion.cuh): every region the engine searched while following the
+// accept / trim / determineRegion rules on a scratch copy of mumlayout, with the candidates of its (single) window.
+struct RecursionRequest {
+    int n = 0;                           // genomes
+    const int64_t* coords = nullptr;     // initial regions: start[n] then end[n] each
+    int nregions = 0;
+    const uint64_t* const* layout = nullptr;   // mumlayout after the anchors: per genome its words ...
+    const int64_t* layout_words = nullptr;     // ... and their number (len + 1 bits incl. the sentinel)
+    int q = 30;                          // ini [LCB] q
+    int64_t p = 15000000;                // ini [LCB] p
+    const int32_t* minsize_tab = nullptr;      // minsize(slength) of the ini `mums` expression for slength < minsize_n
+    int minsize_n = 0;
+};
+struct RecursionResult {
+    size_t nregions = 0;
+    pod_vector<int32_t> coords;          // [nregions * 2n]: start[n] then LENGTH[n]
+    pod_vector<int32_t> slen, ncand;     // ncand < 0: not searched (left to the caller)
+    pod_vector<int64_t> cand_base;       // first candidate of the region in `cand`
+    pod_vector<int32_t> k, lon, sp;      // candidates as in CandBatch (sp / fwd: nq per candidate)
+    pod_vector<uint8_t> fwd;
+    int64_t levels = 0, deferred = 0, dropped = 0, searched = 0;
+};
+
 // Search engine interface. The product implementation is CUDA-only (cuda/engine.cu); tests may link the
 // CPU specification from oracle/ behind the same interface to exercise the host logic without a GPU.
 class SearchBackend {
@@ -79,6 +102,9 @@ public:
     virtual void set_genomes(int n, const uint8_t* const* seq, const int64_t* len) = 0;
     // coords: pool referenced by WindowTask::coord_off
     virtual void search(const WindowTask* tasks, int ntasks, const int64_t* coords, CandBatch& out) = 0;
+    // optional: follow the recursion on the device; false = not supported for this input (the host then discovers the regions
+    // level by level through search())
+    virtual bool discover_recursion(const RecursionRequest&, RecursionResult&) { return false; }
 };
 
 }  // namespace pb200

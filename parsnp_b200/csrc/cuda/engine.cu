@@ -18,6 +18,7 @@
 #include "util.cuh"
 #include "bigpath.cuh"
 #include "smallpath.cuh"
+#include "recursion.cuh"
 
 namespace pb200 {
 
@@ -207,6 +208,196 @@ public:
         host_gather_s += wall_s() - th3;
     }
 
+    // ---- the recursion followed on the device (cuda/recursion.cuh): one upload, a fixed number of levels per round enqueued
+    // without synchronising, one download.  false = this input is left to the host's level-by-level discovery.
+    bool discover_recursion(const RecursionRequest& rq, RecursionResult& out) override {
+        PB_CUDA(cudaSetDevice(device_));
+        const int n = n_, nq = n - 1;
+        if (rq.n != n || nq < 1 || n > 224 || rq.q < 0 || rq.nregions <= 0 || force_big_ || getenv("PB200_NO_DEVICE_RECURSION")) return false;
+        for (int g = 0; g < n; ++g) if (len_[g] >= ((int64_t)1 << 31) - 64) return false;
+        const double t0 = wall_s();
+        const size_t R = (size_t)rq.nregions;
+        const size_t cap = R * 4 + 65536;
+        // ---- scratch mumlayout
+        std::vector<int64_t> bit_off((size_t)n + 1, 0);
+        for (int g = 0; g < n; ++g) bit_off[(size_t)g + 1] = bit_off[(size_t)g] + rq.layout_words[g];
+        unsigned long long* d_bits = r_bits_.ensure((size_t)bit_off[(size_t)n] + 8, false, st_);
+        for (int g = 0; g < n; ++g)
+            PB_CUDA(cudaMemcpyAsync(d_bits + bit_off[(size_t)g], rq.layout[g], (size_t)rq.layout_words[g] * 8, cudaMemcpyHostToDevice, st_));
+        int64_t* d_bit_off = r_bitoff_.ensure((size_t)n + 1, false, st_);
+        int64_t* h_bit_off = r_pin_bitoff_.ensure((size_t)n + 1);
+        std::memcpy(h_bit_off, bit_off.data(), ((size_t)n + 1) * 8);
+        PB_CUDA(cudaMemcpyAsync(d_bit_off, h_bit_off, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st_));
+        int32_t* d_tab = r_tab_.ensure((size_t)std::max(rq.minsize_n, 1), false, st_);
+        int32_t* h_tab = r_pin_tab_.ensure((size_t)std::max(rq.minsize_n, 1));
+        std::memcpy(h_tab, rq.minsize_tab, (size_t)rq.minsize_n * 4);
+        PB_CUDA(cudaMemcpyAsync(d_tab, h_tab, (size_t)rq.minsize_n * 4, cudaMemcpyHostToDevice, st_));
+        // ---- region store + work lists
+        rec::Store St;
+        St.coords = r_coords_.ensure(cap * 2 * (size_t)n, false, st_);
+        St.slen = r_slen_.ensure(cap, false, st_);
+        St.minsize = r_minsize_.ensure(cap, false, st_);
+        St.ncand = r_ncand_.ensure(cap, false, st_);
+        St.cand_base = r_candbase_.ensure(cap, false, st_);
+        int32_t* lists = r_lists_.ensure(cap * (2 * rec::NCLASS + 1), false, st_);
+        unsigned int* ctr = r_ctr_.ensure(32, false, st_);
+        PB_CUDA(cudaMemsetAsync(ctr, 0, 32 * sizeof(unsigned int), st_));
+        rec::Queues Q;
+        for (int h = 0; h < 2; ++h) for (int c = 0; c < rec::NCLASS; ++c) Q.list[h][c] = lists + cap * (size_t)(h * rec::NCLASS + c);
+        Q.deferred = lists + cap * (size_t)(2 * rec::NCLASS);
+        Q.count = ctr; Q.taken = ctr + 8; Q.nregions = ctr + 16; Q.ndeferred = ctr + 17; Q.dropped = ctr + 18;
+        Q.cap = (unsigned int)std::min<size_t>(cap, 0x7fffffffu);
+        {   // initial regions: start[n], len[n] as int32 (pinned staging)
+            int32_t* h = r_pin_coords_.ensure(R * 2 * (size_t)n);
+            const long per = 4096;
+            parallel_chunks(R > 16384 ? default_host_threads() : 1, ((long)R + per - 1) / per, [&](long c) {
+                for (size_t r = (size_t)c * per; r < std::min(R, (size_t)(c + 1) * per); ++r) {
+                    const int64_t* s = rq.coords + r * 2 * (size_t)n;
+                    int32_t* d = h + r * 2 * (size_t)n;
+                    for (int g = 0; g < n; ++g) { d[g] = (int32_t)s[g]; d[n + g] = (int32_t)(s[n + g] - s[g]); }
+                }
+            });
+            PB_CUDA(cudaMemcpyAsync(St.coords, h, R * 2 * (size_t)n * 4, cudaMemcpyHostToDevice, st_));
+            const unsigned int r32 = (unsigned int)R;
+            unsigned int* hr = r_pin_ctr_.ensure(32);
+            hr[0] = r32;
+            PB_CUDA(cudaMemcpyAsync(Q.nregions, hr, 4, cudaMemcpyHostToDevice, st_));
+        }
+        // ---- candidate arrays: sized from what earlier alignments of this process needed
+        static std::atomic<uint32_t> s_cand_per_region_x16(6 * 16);
+        size_t cand_cap = std::max<size_t>(r_cand_hint_, R * s_cand_per_region_x16.load() / 16 + 65536);
+        const size_t cap_limit = std::max<size_t>((size_t)1 << 16, ((size_t)4 << 30) / (size_t)(8 + 5 * nq));       // <= 4 GiB of candidate arrays
+        cand_cap = std::min(cand_cap, cap_limit);
+        unsigned long long* d_cnt = d_candcnt_.ensure(1, false, st_);
+        PB_CUDA(cudaMemsetAsync(d_cnt, 0, 8, st_));
+        int32_t* d_k = d_ck_.ensure(cand_cap, false, st_);
+        int32_t* d_lon = d_clon_.ensure(cand_cap, false, st_);
+        int32_t* d_sp = d_csp_.ensure(cand_cap * (size_t)nq, false, st_);
+        uint8_t* d_fw = d_cfwd_.ensure(cand_cap * (size_t)nq, false, st_);
+        rec::Params P;
+        P.n = n; P.q = rq.q; P.p = rq.p; P.minsize_tab = d_tab; P.minsize_n = rq.minsize_n; P.bit_off = d_bit_off; P.bits = d_bits;
+        small::ClassCfg cfg[rec::NCLASS];
+        for (int c = 0; c < rec::NCLASS; ++c) {
+            cfg[c] = classes_[c];
+            cfg[c].ev_cap += 4 * nq;
+            if (cfg[c].ev_cap > 60000) cfg[c].ev_cap = 60000;
+            P.n_cap[c] = cfg[c].n_cap; P.m_cap[c] = cfg[c].m_cap;
+        }
+        const int gpl = n <= 32 ? 1 : (n <= 64 ? 2 : (n <= 128 ? 4 : 7));
+        auto kern = gpl == 1 ? rec::recursion_level_kernel<1> : (gpl == 2 ? rec::recursion_level_kernel<2> : (gpl == 4 ? rec::recursion_level_kernel<4> : rec::recursion_level_kernel<7>));
+        if (!r_attr_set_[gpl]) {
+            PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            r_attr_set_[gpl] = true;
+        }
+        int ctas[rec::NCLASS];
+        for (int c = 0; c < rec::NCLASS; ++c) {
+            int per_sm = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, cfg[c].threads, cfg[c].smem_bytes(nq)) != cudaSuccess || per_sm < 1) per_sm = 1;
+            ctas[c] = sm_count_ * per_sm;
+        }
+        pb200::launch(rec::seed_lists_kernel, (unsigned)((R + 255) / 256), 256, 0, st_, P, St, Q, (int)R);
+        unsigned int* h_ctr = r_pin_ctr_.ensure(32);
+        int level = 0;
+        const int LEVELS_PER_ROUND = 8;
+        for (int round = 0; round < 64; ++round) {
+            for (int l = 0; l < LEVELS_PER_ROUND; ++l, ++level) {
+                for (int c = 0; c < rec::NCLASS; ++c) {
+                    timers.start(GpuTimers::T_SMALL + c, st_);
+                    pb200::launch(kern, ctas[c], cfg[c].threads, cfg[c].smem_bytes(nq), st_, text_.get(), gmeta_.get(), gmeta_.get() + n_, gmeta_.get() + 2 * n_,
+                                  P, St, Q, level, c, cfg[c], d_cnt, (unsigned long long)cand_cap, d_k, d_lon, d_sp, d_fw);
+                    timers.stop(GpuTimers::T_SMALL + c, st_);
+                }
+                pb200::launch(rec::level_advance_kernel, 1, 32, 0, st_, Q, level);
+            }
+            PB_CUDA(cudaGetLastError());
+            PB_CUDA(cudaMemcpyAsync(h_ctr, ctr, 32 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
+            PB_CUDA(cudaStreamSynchronize(st_));
+            const int nx = level & 1;                       // the lists the next level would read
+            if (h_ctr[nx * rec::NCLASS] + h_ctr[nx * rec::NCLASS + 1] + h_ctr[nx * rec::NCLASS + 2] == 0) break;
+        }
+        // ---- results: sorted by start[0] on the device, then one download
+        const size_t NR = std::min<size_t>(h_ctr[16], cap);
+        uint32_t* sk0 = r_sortk_.ensure(2 * NR + 64, false, st_);
+        uint32_t* sv0 = r_sortv_.ensure(2 * NR + 64, false, st_);
+        uint32_t* sk1 = sk0 + NR; uint32_t* sv1 = sv0 + NR;
+        const unsigned int nr32 = (unsigned int)NR;
+        pb200::launch(rec::region_keys_kernel, (unsigned)((NR + 255) / 256), 256, 0, st_, St, n, nr32, sk0, sv0);
+        int key_bits = 1;
+        while (((int64_t)1 << key_bits) <= len_[0] && key_bits < 32) ++key_bits;
+        const int which = r_sorter_.sort<uint32_t, uint32_t>(sk0, sk1, sv0, sv1, (int64_t)NR, 0, key_bits, st_);
+        const uint32_t* perm = which ? sv1 : sv0;
+        uint32_t* cnt = which ? sk0 : sk1;                 // (the key buffer that does not hold the sorted keys is free)
+        uint32_t* d_total = reinterpret_cast<uint32_t*>(ctr + 24);
+        pb200::launch(rec::sorted_counts_kernel, (unsigned)((NR + 255) / 256), 256, 0, st_, St, perm, nr32, cnt);
+        r_scanner_.scan<prim::OpSum, true>(cnt, cnt, (int64_t)NR, d_total, st_);
+        int32_t* o_coords = r_ocoords_.ensure(NR * 2 * (size_t)n + 64, false, st_);
+        int32_t* o_slen = r_oslen_.ensure(2 * NR + 64, false, st_);
+        int32_t* o_ncand = o_slen + NR;
+        int64_t* o_base = r_obase_.ensure(NR + 8, false, st_);
+        // (capacity of the regrouped candidate arrays = what was produced: read the counter first)
+        unsigned long long used = 0;
+        PB_CUDA(cudaMemcpyAsync(&used, d_cnt, 8, cudaMemcpyDeviceToHost, st_));
+        PB_CUDA(cudaStreamSynchronize(st_));
+        const size_t NCmax = (size_t)std::min<unsigned long long>(used, cand_cap);
+        if (used > cand_cap) r_cand_hint_ = (size_t)used + (size_t)used / 4;          // (the windows that did not fit are searched on demand)
+        int32_t* o_k = r_ok_.ensure(2 * NCmax + 64, false, st_);
+        int32_t* o_lon = o_k + NCmax;
+        int32_t* o_sp = r_osp_.ensure(NCmax * (size_t)nq + 64, false, st_);
+        uint8_t* o_fw = r_ofwd_.ensure(NCmax * (size_t)nq + 64, false, st_);
+        pb200::launch(rec::gather_sorted_kernel, (unsigned)((NR * 32 + 255) / 256), 256, 0, st_, St, n, perm, cnt, nr32, d_k, d_lon, d_sp, d_fw, o_coords, o_slen,
+                      o_ncand, o_base, o_k, o_lon, o_sp, o_fw);
+        PB_CUDA(cudaGetLastError());
+        PB_CUDA(cudaMemcpyAsync(h_ctr, ctr, 32 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
+        PB_CUDA(cudaStreamSynchronize(st_));
+        const double t1 = wall_s();
+        const size_t NC = std::min<size_t>(h_ctr[24], NCmax);
+        out.nregions = NR;
+        out.coords.resize(NR * 2 * (size_t)n); out.slen.resize(NR); out.ncand.resize(NR); out.cand_base.resize(NR);
+        out.k.resize(NC); out.lon.resize(NC); out.sp.resize(NC * (size_t)nq); out.fwd.resize(NC * (size_t)nq);
+        // device -> pinned staging -> the caller's vectors (parallel memcpy)
+        struct Part { void* dst; const void* src; size_t bytes; };
+        const Part parts[8] = {{out.coords.data(), o_coords, NR * 2 * (size_t)n * 4}, {out.slen.data(), o_slen, NR * 4}, {out.ncand.data(), o_ncand, NR * 4},
+                               {out.cand_base.data(), o_base, NR * 8}, {out.k.data(), o_k, NC * 4}, {out.lon.data(), o_lon, NC * 4},
+                               {out.sp.data(), o_sp, NC * (size_t)nq * 4}, {out.fwd.data(), o_fw, NC * (size_t)nq}};
+        size_t tot = 0, offs[9];
+        for (int i = 0; i < 8; ++i) { offs[i] = tot; tot += (parts[i].bytes + 63) & ~(size_t)63; }
+        offs[8] = tot;
+        uint8_t* stage = r_pin_stage_.ensure(tot + 64);
+        for (int i = 0; i < 8; ++i)
+            if (parts[i].bytes) PB_CUDA(cudaMemcpyAsync(stage + offs[i], parts[i].src, parts[i].bytes, cudaMemcpyDeviceToHost, st_));
+        PB_CUDA(cudaStreamSynchronize(st_));
+        const double t2 = wall_s();
+        {
+            const size_t CH = (size_t)1 << 20;
+            std::vector<std::pair<int, size_t>> chunks;
+            for (int i = 0; i < 8; ++i) for (size_t o = 0; o < parts[i].bytes; o += CH) chunks.emplace_back(i, o);
+            parallel_chunks(default_host_threads(), (long)chunks.size(), [&](long c) {
+                const int i = chunks[(size_t)c].first; const size_t o = chunks[(size_t)c].second;
+                std::memcpy((char*)parts[i].dst + o, stage + offs[i] + o, std::min(CH, parts[i].bytes - o));
+            });
+        }
+        out.levels = level; out.deferred = h_ctr[17]; out.dropped = h_ctr[18];
+        // statistics: searched windows, their reference / query bases (bench.py's algorithmic-byte model)
+        int64_t searched = 0, rb = 0, qb = 0, cands = 0;
+        for (size_t r = 0; r < NR; ++r) {
+            if (out.ncand[r] < 0) continue;
+            ++searched;
+            cands += out.ncand[r];
+            const int32_t* c = &out.coords[r * 2 * (size_t)n];
+            rb += c[n];
+            for (int g = 1; g < n; ++g) qb += c[n + g];
+        }
+        out.searched = searched;
+        small_windows += searched; small_ref_bases += rb; small_query_bases += qb;
+        if (searched >= 1024) {
+            const uint32_t r16 = (uint32_t)std::min<int64_t>(1 << 20, cands * 20 / searched + 16);
+            uint32_t cur = s_cand_per_region_x16.load();
+            while (r16 > cur && !s_cand_per_region_x16.compare_exchange_weak(cur, r16)) {}
+        }
+        host_rec_device_s += t1 - t0; host_rec_d2h_s += t2 - t1; host_rec_copy_s += wall_s() - t2;
+        return true;
+    }
+
     // ---- StagedWindowEngine (query-sharded large windows, see host/sharded.h) ----
     int classify(const WindowTask& t, const int64_t* coords) const {
         const int nq = n_ - 1;
@@ -316,6 +507,7 @@ public:
     GpuTimers timers;
     int64_t big_windows = 0, small_windows = 0, small_retries = 0, big_events = 0, index_rounds = 0;
     int64_t small_class_tasks[3] = {0, 0, 0};
+    double host_rec_device_s = 0, host_rec_d2h_s = 0, host_rec_copy_s = 0;
     double host_classify_s = 0, host_upload_s = 0, host_small_wait_s = 0, host_small_d2h_s = 0, host_big_s = 0, host_gather_s = 0;   // wall clock, host side
     int64_t small_ref_bases = 0, small_query_bases = 0, big_ref_bases = 0, big_query_bases = 0;
 
@@ -468,6 +660,23 @@ private:
     small::ClassCfg classes_[3];
     size_t max_smem_ = 0, cand_cap_hint_ = 0;
     big::BigPath big_;
+    // device recursion (discover_recursion)
+    DevBuf<unsigned long long> r_bits_;
+    DevBuf<int64_t> r_bitoff_, r_candbase_;
+    DevBuf<int32_t> r_tab_, r_coords_, r_slen_, r_minsize_, r_ncand_, r_lists_;
+    DevBuf<unsigned int> r_ctr_;
+    PinBuf<int64_t> r_pin_bitoff_;
+    PinBuf<int32_t> r_pin_tab_, r_pin_coords_;
+    PinBuf<unsigned int> r_pin_ctr_;
+    PinBuf<uint8_t> r_pin_stage_;
+    DevBuf<uint32_t> r_sortk_, r_sortv_;
+    DevBuf<int32_t> r_ocoords_, r_oslen_, r_ok_, r_osp_;
+    DevBuf<int64_t> r_obase_;
+    DevBuf<uint8_t> r_ofwd_;
+    rsort::RadixSorter r_sorter_;
+    prim::Scanner r_scanner_;
+    size_t r_cand_hint_ = 0;
+    bool r_attr_set_[8] = {false, false, false, false, false, false, false, false};
     PinBuf<int32_t> pin_k_, pin_lon_, pin_sp_;       // small-window candidates of the current search() call (pinned staging)
     PinBuf<uint8_t> pin_fwd_;
     size_t small_cands_ = 0;
@@ -598,6 +807,7 @@ public:
     explicit ResidentBackend(pb200::CudaEngine* e) : e_(e) {}
     void set_genomes(int, const uint8_t* const*, const int64_t*) override {}
     void search(const pb200::WindowTask* t, int nt, const int64_t* c, pb200::CandBatch& out) override { e_->search(t, nt, c, out); }
+    bool discover_recursion(const pb200::RecursionRequest& rq, pb200::RecursionResult& out) override { return e_->discover_recursion(rq, out); }
 private:
     pb200::CudaEngine* e_;
 };
@@ -662,16 +872,17 @@ int pb200_engine_timers(pb200_genomes* g, double* values, int cap) {
     const int T = pb200::GpuTimers::T_COUNT;
     for (int i = 0; i < T && k < cap; ++i) values[k++] = g->eng->timers.ms[i];
     for (int i = 0; i < T && k < cap; ++i) values[k++] = g->eng->timers.cnt[i];
-    const double extra[19] = {(double)g->eng->small_class_tasks[0], (double)g->eng->small_class_tasks[1], (double)g->eng->small_class_tasks[2],(double)g->eng->big_windows, (double)g->eng->small_windows, (double)g->eng->small_retries,
+    const double extra[22] = {(double)g->eng->small_class_tasks[0], (double)g->eng->small_class_tasks[1], (double)g->eng->small_class_tasks[2],(double)g->eng->big_windows, (double)g->eng->small_windows, (double)g->eng->small_retries,
                               (double)g->eng->big_events, (double)g->eng->index_rounds, (double)pb200::g_kernel_launches,
                               (double)g->eng->small_ref_bases, (double)g->eng->small_query_bases, (double)g->eng->big_ref_bases,
                               (double)g->eng->big_query_bases, g->eng->host_classify_s, g->eng->host_upload_s, g->eng->host_small_wait_s,
-                              g->eng->host_small_d2h_s, g->eng->host_big_s, g->eng->host_gather_s};
-    for (int i = 0; i < 19 && k < cap; ++i) values[k++] = extra[i];
+                              g->eng->host_small_d2h_s, g->eng->host_big_s, g->eng->host_gather_s, g->eng->host_rec_device_s, g->eng->host_rec_d2h_s,
+                              g->eng->host_rec_copy_s};
+    for (int i = 0; i < 22 && k < cap; ++i) values[k++] = extra[i];
     return k;
 }
 const char* pb200_engine_timer_names(void) {
-    static std::string s = std::string(pb200::GpuTimers::names()) + ",tasks_class_a,tasks_class_b,tasks_class_c,big_windows,small_windows,small_retries,big_events,index_rounds,kernel_launches,small_ref_bases,small_query_bases,big_ref_bases,big_query_bases,host_classify_s,host_upload_s,host_small_wait_s,host_small_d2h_s,host_big_s,host_gather_s";
+    static std::string s = std::string(pb200::GpuTimers::names()) + ",tasks_class_a,tasks_class_b,tasks_class_c,big_windows,small_windows,small_retries,big_events,index_rounds,kernel_launches,small_ref_bases,small_query_bases,big_ref_bases,big_query_bases,host_classify_s,host_upload_s,host_small_wait_s,host_small_d2h_s,host_big_s,host_gather_s,host_rec_device_s,host_rec_d2h_s,host_rec_copy_s";
     return s.c_str();
 }
 void pb200_engine_reset_timers(pb200_genomes* g) {
@@ -682,6 +893,7 @@ void pb200_engine_reset_timers(pb200_genomes* g) {
     g->eng->small_ref_bases = g->eng->small_query_bases = g->eng->big_ref_bases = g->eng->big_query_bases = 0;
     g->eng->small_class_tasks[0] = g->eng->small_class_tasks[1] = g->eng->small_class_tasks[2] = 0;
     g->eng->host_classify_s = g->eng->host_upload_s = g->eng->host_small_wait_s = g->eng->host_small_d2h_s = g->eng->host_big_s = g->eng->host_gather_s = 0;
+    g->eng->host_rec_device_s = g->eng->host_rec_d2h_s = g->eng->host_rec_copy_s = 0;
 }
 
 // test hook (not in the public header): suffix array + longest-repeated-prefix of a window of genome 0

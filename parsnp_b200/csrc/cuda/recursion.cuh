@@ -1,0 +1,416 @@
+// Device-resident discovery of the recursion of Aligner::doWork (src/parsnp.cpp:173-317).
+//
+// The host's exact replay (host/replay.cpp) needs, for every region it will pop, the candidates of that region's window search.
+// Which regions exist is only known after the candidates of their parents have been validated, trimmed against `mumlayout` and
+// placed (setMums1 loop D, src/parsnp.cpp:1713-1842; trim 1399-1477; determineRegion 1199-1290).  Round 1 ran that discovery on
+// the host, level by level, with a GPU batch + upload + download + gather per level.  Here the whole discovery stays on the
+// device: one CTA searches a region's window in shared memory (smallpath.cuh) and then, with its first warp, runs the accept /
+// trim / determineRegion rules on a SCRATCH copy of mumlayout in HBM and appends the child regions to the next level's work
+// list itself.  The host enqueues a fixed number of levels without synchronising and reads everything back once.
+//
+// It is a PREDICTOR, exactly like the host pass it replaces: regions of one level are processed in no particular order, so a
+// reverse-strand candidate (whose mirrored coordinates point into some other region) may see another state of
+// the scratch layout than the reference would.  The replay recomputes every accept decision in the reference's order on the
+// true layout and merely LOOKS UP the candidate lists by region coordinates; a region this pass did not predict is searched on
+// demand.  Results are therefore exact whatever this pass does; it only has to be right almost always to be fast.
+#pragma once
+#include "smallpath.cuh"
+
+namespace pb200 {
+namespace rec {
+
+constexpr int NCLASS = 3;
+
+// work lists of one run: level L reads list[L & 1][c][0 .. count[L & 1][c]) and appends children to list[(L + 1) & 1]
+struct Queues {
+    int32_t* list[2][NCLASS];           // region ids
+    unsigned int* count;                // [2][NCLASS] entries appended
+    unsigned int* taken;                // [2][NCLASS] entries handed out (dynamic scheduling inside a level)
+    unsigned int* nregions;             // regions in the store
+    unsigned int* ndeferred;            // regions the device could not take (too large, minsize < 4, ...): left to the host
+    unsigned int* dropped;              // children lost to a full store / list (the replay searches them on demand)
+    int32_t* deferred;                  // their ids
+    unsigned int cap;                   // capacity of the region store and of every list
+};
+
+// one region: start[n] then len[n] at coords + id * 2n; everything else per region below
+struct Store {
+    int32_t* coords;
+    int32_t* slen;                      // TRegion::slength
+    int32_t* minsize;
+    int32_t* ncand;                     // -1 = not searched (deferred / dropped), else candidates in the global arrays
+    int64_t* cand_base;
+};
+
+struct Params {
+    int n;                              // genomes
+    int q;                              // ini [LCB] q: sub-regions need slength > q
+    int64_t p;                          // ini [LCB] p: a region longer than this has several windows (host only)
+    const int32_t* minsize_tab;         // minsize(slength) of the `mums` expression for slength < minsize_n
+    int minsize_n;
+    const int64_t* bit_off;             // per genome: first word of its row in `bits`
+    unsigned long long* bits;           // scratch mumlayout (len + 1 bits per genome, sentinel at len)
+    int n_cap[NCLASS], m_cap[NCLASS];
+};
+
+// ---- scratch layout access (L2: rows are written with atomics by other CTAs and by this one)
+__device__ __forceinline__ unsigned long long ld_word(const unsigned long long* p) { return __ldcg(p); }
+__device__ __forceinline__ bool bit_get(const unsigned long long* row, int64_t i) { return (ld_word(row + (i >> 6)) >> (i & 63)) & 1ull; }
+// # consecutive set bits a, a+1, ... (< b)
+__device__ inline int64_t bits_run_up(const unsigned long long* row, int64_t a, int64_t b) {
+    int64_t i = a;
+    while (i < b) {
+        const unsigned long long inv = ~(ld_word(row + (i >> 6)) >> (i & 63));
+        const int avail = 64 - (int)(i & 63);
+        const int z = inv ? __ffsll((long long)inv) - 1 : 64;
+        if (z < avail) { i += z; break; }
+        i += avail;
+    }
+    if (i > b) i = b;
+    return i - a;
+}
+// # consecutive set bits b-1, b-2, ... (>= a)
+__device__ inline int64_t bits_run_down(const unsigned long long* row, int64_t a, int64_t b) {
+    int64_t i = b - 1;
+    while (i >= a) {
+        const int pos = (int)(i & 63);
+        const unsigned long long inv = ~(ld_word(row + (i >> 6)) << (63 - pos));
+        const int z = inv ? __clzll((long long)inv) : 64;
+        const int avail = pos + 1;
+        if (z < avail) { i -= z; break; }
+        i -= avail;
+    }
+    if (i < a - 1) i = a - 1;
+    return (b - 1) - i;
+}
+__device__ inline int64_t bits_prev_set(const unsigned long long* row, int64_t i) {          // largest set index <= i, or -1
+    if (i < 0) return -1;
+    int64_t wi = i >> 6;
+    unsigned long long cur = ld_word(row + wi) & (~0ull >> (63 - (i & 63)));
+    for (;;) {
+        if (cur) return (wi << 6) + 63 - __clzll((long long)cur);
+        if (wi == 0) return -1;
+        cur = ld_word(row + --wi);
+    }
+}
+__device__ inline int64_t bits_next_set(const unsigned long long* row, int64_t i, int64_t limit) {   // smallest set index in [i, limit), or limit
+    if (i >= limit) return limit;
+    int64_t wi = i >> 6;
+    const int64_t wl = (limit - 1) >> 6;
+    unsigned long long cur = ld_word(row + wi) & (~0ull << (i & 63));
+    for (;;) {
+        if (cur) { const int64_t r = (wi << 6) + __ffsll((long long)cur) - 1; return r < limit ? r : limit; }
+        if (wi >= wl) return limit;
+        cur = ld_word(row + ++wi);
+    }
+}
+__device__ inline void bits_set_range(unsigned long long* row, int64_t a, int64_t b) {       // [a, b)
+    if (a >= b) return;
+    const int64_t wa = a >> 6, wb = (b - 1) >> 6;
+    const unsigned long long ma = ~0ull << (a & 63), mb = ~0ull >> (63 - ((b - 1) & 63));
+    if (wa == wb) { atomicOr(row + wa, ma & mb); return; }
+    atomicOr(row + wa, ma);
+    for (int64_t w = wa + 1; w < wb; ++w) atomicOr(row + w, ~0ull);
+    atomicOr(row + wb, mb);
+}
+
+__device__ __forceinline__ int warp_or(int v) { return __any_sync(0xffffffffu, v); }
+__device__ __forceinline__ int64_t warp_min64(int64_t v) {
+    for (int o = 16; o > 0; o >>= 1) { const int64_t x = __shfl_xor_sync(0xffffffffu, v, o); v = x < v ? x : v; }
+    return v;
+}
+
+// class of a region (same rule as CudaEngine::classify), NCLASS = the device cannot take it
+__device__ __forceinline__ int class_of(const Params& P, int64_t ref_len, int64_t max_m, int minsize) {
+    if (minsize < 4 || ref_len > P.p || ref_len <= 0) return NCLASS;
+    for (int c = 0; c < NCLASS; ++c)
+        if (ref_len <= P.n_cap[c] && max_m <= P.m_cap[c]) return c;
+    return NCLASS;
+}
+
+// append region (S[], E[]) (lanes hold genomes lane, lane + 32, ...) to the store and to the next level's list of its class
+template <int GPL>
+__device__ inline void push_region(const Params& P, const Store& St, const Queues& Q, int next, const int64_t (&S)[GPL], const int64_t (&E)[GPL],
+                                   int64_t slength, int lane) {
+    const int n = P.n;
+    int64_t mm = 0;
+    for (int t = 0; t < GPL; ++t) { const int g = lane + 32 * t; if (g >= 1 && g < n) mm = max(mm, E[t] - S[t]); }
+    mm = -warp_min64(-mm);
+    const int64_t L0 = __shfl_sync(0xffffffffu, E[0] - S[0], 0);
+    const int ms = slength >= 0 && slength < P.minsize_n ? P.minsize_tab[slength] : 0;
+    const int cls = class_of(P, L0, mm, ms);
+    unsigned int id = 0;
+    if (lane == 0) id = atomicAdd(Q.nregions, 1u);
+    id = __shfl_sync(0xffffffffu, id, 0);
+    if (id >= Q.cap) { if (lane == 0) { atomicSub(Q.nregions, 1u); atomicAdd(Q.dropped, 1u); } return; }
+    int32_t* c = St.coords + (size_t)id * 2 * n;
+    for (int t = 0; t < GPL; ++t) {
+        const int g = lane + 32 * t;
+        if (g < n) { c[g] = (int32_t)S[t]; c[n + g] = (int32_t)(E[t] - S[t]); }
+    }
+    if (lane == 0) {
+        St.slen[id] = (int32_t)slength;
+        St.minsize[id] = ms;
+        St.ncand[id] = -1;
+        St.cand_base[id] = 0;
+        if (cls < NCLASS) {
+            const unsigned int at = atomicAdd(&Q.count[next * NCLASS + cls], 1u);
+            if (at < Q.cap) Q.list[next][cls][at] = (int32_t)id;
+            else { atomicSub(&Q.count[next * NCLASS + cls], 1u); atomicAdd(Q.dropped, 1u); }
+        } else {
+            const unsigned int at = atomicAdd(Q.ndeferred, 1u);
+            if (at < Q.cap) Q.deferred[at] = (int32_t)id;
+        }
+    }
+}
+
+// setMums1 loop D + determineRegion for the candidates of one searched region, by ONE WARP, on the scratch layout.
+// GPL = genomes per lane (n <= 32 * GPL).  cand arrays: the region's candidates at [base, base + nc) of the global arrays.
+template <int GPL>
+__device__ inline void accept_region(const Params& P, const Store& St, const Queues& Q, int next, const uint8_t* __restrict__ text,
+                                     const int64_t* __restrict__ gbase_fwd, const int64_t* __restrict__ glen, int region, int nc, int64_t base,
+                                     const int32_t* __restrict__ out_k, const int32_t* __restrict__ out_lon, const int32_t* __restrict__ out_sp,
+                                     const uint8_t* __restrict__ out_fwd, uint16_t* accC, uint16_t* accShift, uint16_t* accLen) {
+    const int lane = threadIdx.x & 31;
+    const int n = P.n, nq = n - 1;
+    const int32_t* rc = St.coords + (size_t)region * 2 * n;
+    int64_t rs[GPL], rl[GPL], gl[GPL];
+    const unsigned long long* row[GPL];
+    for (int t = 0; t < GPL; ++t) {
+        const int g = lane + 32 * t;
+        rs[t] = g < n ? rc[g] : 0;
+        rl[t] = g < n ? rc[n + g] : 0;
+        gl[t] = g < n ? glen[g] : 0;
+        row[t] = P.bits + (g < n ? P.bit_off[g] : 0);
+    }
+    int nacc = 0;
+    for (int c = 0; c < nc; ++c) {
+        const int64_t LON = out_lon[base + c];
+        const int k = out_k[base + c];
+        int64_t st[GPL];
+        bool fw[GPL];
+        int fail = 0;
+        for (int t = 0; t < GPL; ++t) {
+            const int g = lane + 32 * t;
+            st[t] = 0; fw[t] = true;
+            if (g >= n) continue;
+            int64_t off = g == 0 ? k : out_sp[(size_t)(base + c) * nq + (g - 1)];
+            fw[t] = g == 0 ? true : out_fwd[(size_t)(base + c) * nq + (g - 1)] != 0;
+            // range pre-check in unsigned arithmetic (src/parsnp.cpp:1723): (dsp - rs) > length, dsp = off + 1 + rs
+            if ((unsigned long long)(off + 1) > (unsigned long long)(unsigned int)rl[t]) fail = 1;
+            int64_t s = rs[t] + off;
+            if (!fw[t]) s = gl[t] - (s + LON);                  // TMum ctor: mirrored on the WHOLE genome (src/TMum.cpp:35)
+            if (s + LON > gl[t] || s < 0) fail = 1;
+            st[t] = s;
+        }
+        if (warp_or(fail) || LON < 5) continue;
+        // trim (src/parsnp.cpp:1399-1477): genome after genome, every trim shifts ALL genomes.  Only the two ends of an interval
+        // are looked at, so when no genome has a set bit at either end (the rule inside a gap) nothing moves.
+        int64_t length = LON, shift = 0;
+        int touch = 0;
+        for (int t = 0; t < GPL; ++t) {
+            const int g = lane + 32 * t;
+            if (g < n) touch |= (int)bit_get(row[t], st[t]) | (int)bit_get(row[t], st[t] + LON - 1);
+        }
+        if (warp_or(touch)) {
+            for (int g = 0; g < n && length > 0; ++g) {
+                const int t = g >> 5, owner = g & 31;
+                int64_t t1 = 0, t2 = 0;
+                if (lane == owner) t1 = bits_run_up(row[t], st[t] + shift, st[t] + shift + length);
+                t1 = __shfl_sync(0xffffffffu, t1, owner);
+                shift += t1; length -= t1;
+                if (lane == owner) t2 = bits_run_down(row[t], st[t] + shift, st[t] + shift + length);
+                t2 = __shfl_sync(0xffffffffu, t2, owner);
+                length -= t2;
+            }
+        }
+        if (length < 2) continue;
+        // reverse-strand genomes are verified against the reference substring (src/parsnp.cpp:1800-1825)
+        const int64_t s0 = __shfl_sync(0xffffffffu, st[0] + shift, 0);
+        int badmum = 0, anyrev = 0;
+        for (int t = 0; t < GPL; ++t) anyrev |= (lane + 32 * t < n) && !fw[t];
+        for (int g = 1; g < n && warp_or(anyrev); ++g) {
+            const int t = g >> 5, owner = g & 31;
+            const int isrev = __shfl_sync(0xffffffffu, (int)!fw[t], owner);
+            if (!isrev) continue;
+            const int64_t sg = __shfl_sync(0xffffffffu, st[t] + shift, owner);
+            const uint8_t* g0 = text + gbase_fwd[0] + s0;
+            const uint8_t* gk = text + gbase_fwd[g] + sg;
+            int bad = 0;
+            for (int64_t x = lane; x < length; x += 32) {
+                const uint8_t a = gk[length - 1 - x];
+                bad |= (a < 4 ? (uint8_t)(3 - a) : (uint8_t)4) != g0[x];
+            }
+            if (warp_or(bad)) { badmum = 1; break; }
+        }
+        if (badmum) continue;
+        for (int t = 0; t < GPL; ++t) {
+            const int g = lane + 32 * t;
+            if (g < n) bits_set_range(const_cast<unsigned long long*>(row[t]), st[t] + shift, st[t] + shift + length);
+        }
+        if (lane == 0) { accC[nacc] = (uint16_t)c; accShift[nacc] = (uint16_t)shift; accLen[nacc] = (uint16_t)length; }
+        ++nacc;
+    }
+    if (nacc == 0) return;
+    __threadfence();                                            // (this warp's own atomics are ordered before its reads below)
+    __syncwarp();
+    // determineRegion around every accepted MUM, on the layout as it is after ALL accepts of the region (src/parsnp.cpp:251-289)
+    for (int a = 0; a < nacc; ++a) {
+        const int c = accC[a];
+        const int64_t shift = accShift[a], length = accLen[a];
+        const int64_t LON = out_lon[base + c];
+        const int k = out_k[base + c];
+        int64_t lS[GPL], lE[GPL], rS[GPL], rE[GPL];
+        int64_t lsl = 500000000, rsl = 500000000;
+        for (int t = 0; t < GPL; ++t) {
+            const int g = lane + 32 * t;
+            lS[t] = lE[t] = rS[t] = rE[t] = 0;
+            if (g >= n) continue;
+            const int64_t off = g == 0 ? k : out_sp[(size_t)(base + c) * nq + (g - 1)];
+            const bool f = g == 0 ? true : out_fwd[(size_t)(base + c) * nq + (g - 1)] != 0;
+            int64_t s = rs[t] + off;
+            if (!f) s = gl[t] - (s + LON);
+            s += shift;
+            int64_t cp = bits_prev_set(row[t], s - 1);
+            if (cp < 0) cp = 0;
+            lS[t] = cp + 1; lE[t] = s - 1;
+            const int64_t en = s + length;
+            int64_t cq = en + 1;
+            if (cq < gl[t]) cq = bits_next_set(row[t], cq, gl[t]);
+            rS[t] = en + 1; rE[t] = cq - 1;
+            lsl = min(lsl, lE[t] - lS[t]);
+            rsl = min(rsl, rE[t] - rS[t]);
+        }
+        lsl = warp_min64(lsl);
+        rsl = warp_min64(rsl);
+        if (lsl > P.q) push_region<GPL>(P, St, Q, next, lS, lE, lsl, lane);
+        if (rsl > P.q) push_region<GPL>(P, St, Q, next, rS, rE, rsl, lane);
+    }
+}
+
+// One level of one size class: CTAs take regions from the level's list until it is empty (dynamic scheduling), search the
+// region's window (small_window) and run accept_region on the result.  A window that overflows a per-CTA capacity moves to the
+// next class (next level's list); one that does not fit the global candidate buffer is left to the host.
+template <int GPL>
+__global__ void __launch_bounds__(small::SM_MAX_THREADS, 4) recursion_level_kernel(
+    const uint8_t* __restrict__ text, const int64_t* __restrict__ gbase_fwd, const int64_t* __restrict__ gbase_rc,
+    const int64_t* __restrict__ glen, Params P, Store St, Queues Q, int level, int cls, small::ClassCfg cfg,
+    unsigned long long* __restrict__ cand_counter, unsigned long long cand_cap_global, int32_t* __restrict__ out_k,
+    int32_t* __restrict__ out_lon, int32_t* __restrict__ out_sp, uint8_t* __restrict__ out_fwd) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint64_t s_bar[2];
+    __shared__ uint8_t s_mis[2 * small::GROUP_MAX];
+    __shared__ int s_next;
+    const int cur = level & 1, next = cur ^ 1;
+    const int nq = P.n - 1;
+    small::SmemView sv;
+    sv.carve(smem, cfg, nq);
+    if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], (uint32_t)blockDim.x); fence_mbar_init(); }
+    uint32_t wphase = 0, qphase = 0;
+    const unsigned int total = min(Q.count[cur * NCLASS + cls], Q.cap);
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_next = (int)atomicAdd(&Q.taken[cur * NCLASS + cls], 1u);
+        __syncthreads();
+        const unsigned int ti = (unsigned int)s_next;
+        if (ti >= total) break;
+        const int region = Q.list[cur][cls][ti];
+        const int32_t* rc = St.coords + (size_t)region * 2 * P.n;
+        small::TaskDev tk;
+        tk.ref_off = gbase_fwd[0] + rc[0];
+        tk.n = rc[P.n];
+        tk.minsize = St.minsize[region];
+        tk.qcoord_off = 0;
+        small::small_window(text, gbase_fwd, gbase_rc, glen, nq, tk, rc + 1, rc + P.n + 1, cfg, sv, s_bar, s_mis, wphase, qphase, cand_counter,
+                            cand_cap_global, out_k, out_lon, out_sp, out_fwd);
+        const int ovf = sv.s_int[3];
+        const int nc = sv.s_int[2];
+        const int64_t base = *reinterpret_cast<int64_t*>(&sv.s_int[4]);
+        if (ovf) {
+            if (threadIdx.x == 0) {
+                if (ovf == 1 && cls + 1 < NCLASS) {
+                    const unsigned int at = atomicAdd(&Q.count[next * NCLASS + cls + 1], 1u);
+                    if (at < Q.cap) Q.list[next][cls + 1][at] = region;
+                    else { atomicSub(&Q.count[next * NCLASS + cls + 1], 1u); atomicAdd(Q.dropped, 1u); }
+                } else {
+                    const unsigned int at = atomicAdd(Q.ndeferred, 1u);
+                    if (at < Q.cap) Q.deferred[at] = region;
+                }
+            }
+            continue;
+        }
+        if (threadIdx.x == 0) { St.ncand[region] = nc; St.cand_base[region] = base; }
+        if (threadIdx.x < 32 && nc > 0) {
+            // (the candidate rows were written by this CTA before the barrier that ends small_window)
+            accept_region<GPL>(P, St, Q, next, text, gbase_fwd, glen, region, nc, base, out_k, out_lon, out_sp, out_fwd, sv.candK, sv.candM,
+                               reinterpret_cast<uint16_t*>(sv.HQ));
+        }
+    }
+}
+
+// between two levels: the finished level's counters are cleared for re-use two levels later
+__global__ void level_advance_kernel(Queues Q, int level) {
+    const int cur = level & 1;
+    if (threadIdx.x < NCLASS) { Q.count[cur * NCLASS + threadIdx.x] = 0; Q.taken[cur * NCLASS + threadIdx.x] = 0; }
+}
+
+// level 0: classify the initial regions (uploaded into the store by the host) into the first lists
+__global__ void seed_lists_kernel(Params P, Store St, Queues Q, int count) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= count) return;
+    const int n = P.n;
+    const int32_t* c = St.coords + (size_t)id * 2 * n;
+    int64_t mm = 0, sl = 500000000;
+    for (int g = 0; g < n; ++g) { if (g) mm = max(mm, (int64_t)c[n + g]); sl = min(sl, (int64_t)c[n + g]); }
+    const int ms = sl >= 0 && sl < P.minsize_n ? P.minsize_tab[sl] : 0;
+    St.slen[id] = (int32_t)sl;
+    St.minsize[id] = ms;
+    St.ncand[id] = -1;
+    St.cand_base[id] = 0;
+    const int cls = class_of(P, c[n], mm, ms);
+    if (cls < NCLASS) {
+        const unsigned int at = atomicAdd(&Q.count[cls], 1u);
+        Q.list[0][cls][at] = id;
+    } else {
+        const unsigned int at = atomicAdd(Q.ndeferred, 1u);
+        if (at < Q.cap) Q.deferred[at] = id;
+    }
+}
+
+// ---- after the last level: regions in ascending start[0] order (the order in which the replay pops them, so its lookups and
+// its candidate reads stream through memory), candidates regrouped to match
+__global__ void region_keys_kernel(Store St, int n, unsigned int nr, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nr) return;
+    keys[i] = (uint32_t)St.coords[(size_t)i * 2 * n];
+    vals[i] = i;
+}
+__global__ void sorted_counts_kernel(Store St, const uint32_t* __restrict__ perm, unsigned int nr, uint32_t* __restrict__ cnt) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nr) return;
+    const int c = St.ncand[perm[i]];
+    cnt[i] = c > 0 ? (uint32_t)c : 0u;
+}
+// one warp per region: its record and its candidates into sorted position
+__global__ void gather_sorted_kernel(Store St, int n, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ newbase, unsigned int nr,
+                                     const int32_t* __restrict__ k, const int32_t* __restrict__ lon, const int32_t* __restrict__ sp,
+                                     const uint8_t* __restrict__ fwd, int32_t* __restrict__ o_coords, int32_t* __restrict__ o_slen,
+                                     int32_t* __restrict__ o_ncand, int64_t* __restrict__ o_base, int32_t* __restrict__ o_k,
+                                     int32_t* __restrict__ o_lon, int32_t* __restrict__ o_sp, uint8_t* __restrict__ o_fwd) {
+    const unsigned int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= nr) return;
+    const unsigned int r = perm[i];
+    const int nq = n - 1;
+    for (int x = lane; x < 2 * n; x += 32) o_coords[(size_t)i * 2 * n + x] = St.coords[(size_t)r * 2 * n + x];
+    const int nc = St.ncand[r];
+    const int64_t ob = St.cand_base[r], nb = newbase[i];
+    if (lane == 0) { o_slen[i] = St.slen[r]; o_ncand[i] = nc; o_base[i] = nb; }
+    if (nc <= 0) return;
+    for (int x = lane; x < nc; x += 32) { o_k[nb + x] = k[ob + x]; o_lon[nb + x] = lon[ob + x]; }
+    const int64_t rows = (int64_t)nc * nq;
+    for (int64_t x = lane; x < rows; x += 32) { o_sp[nb * nq + x] = sp[ob * nq + x]; o_fwd[nb * nq + x] = fwd[ob * nq + x]; }
+}
+
+}  // namespace rec
+}  // namespace pb200

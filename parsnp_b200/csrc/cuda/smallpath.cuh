@@ -150,50 +150,58 @@ __device__ __forceinline__ void eval_at(const Ev* __restrict__ ev, int ne, int k
     C.UP = max(ac.fl, ac.t2); C.EP = max(ac.t1, ac.fl); C.d1 = ac.dd;
 }
 
-__global__ void __launch_bounds__(SM_MAX_THREADS, 4) small_region_kernel(
+// Shared-memory carve-up of one CTA (sizes from ClassCfg); the same layout serves every window the CTA processes.
+struct SmemView {
+    uint8_t* Rbuf; uint16_t* lrp; uint16_t* MUP; uint16_t* MEP; uint32_t* R4; uint32_t* tab; uint8_t* QB; uint32_t* Q4; uint8_t* rowq;
+    uint32_t* HQ; Ev* stg; Ev* evs; uint16_t* evoff; uint16_t* candK; uint16_t* candM; uint16_t* qoff; uint16_t* rowoff; uint16_t* qm;
+    int* qcnt; int* qfill; int* s_int;
+    __device__ void carve(unsigned char* smem, const ClassCfg& cfg, int nq) {
+        size_t off = 0;
+        Rbuf = smem + off; off += ClassCfg::al(cfg.n_cap + 16);       // the window, at its global misalignment
+        lrp = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
+        MUP = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
+        MEP = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
+        R4 = reinterpret_cast<uint32_t*>(smem + off); off += ClassCfg::al(4 * (size_t)cfg.n_cap);          // seed code of every window position
+        tab = reinterpret_cast<uint32_t*>(smem + off); off += ClassCfg::al(8 * (size_t)cfg.n_cap);         // hash table of positions (2 n_cap slots)
+        QB = smem + off; off += ClassCfg::al((size_t)cfg.qbuf);                                              // group query text
+        Q4 = reinterpret_cast<uint32_t*>(smem + off); off += ClassCfg::al(8 * (size_t)cfg.rows_cap);       // seed rows: [2 row] = fwd, [2 row + 1] = rc
+        rowq = smem + off; off += ClassCfg::al((size_t)cfg.rows_cap);                                        // group-local query of each row
+        HQ = reinterpret_cast<uint32_t*>(smem + off); off += ClassCfg::al(4 * (size_t)cfg.hq_cap);         // seed hits: l | row << 12 | strand << 31
+        stg = reinterpret_cast<Ev*>(smem + off); off += ClassCfg::al((size_t)cfg.stg_cap * sizeof(Ev));
+        evs = reinterpret_cast<Ev*>(smem + off); off += ClassCfg::al((size_t)cfg.ev_cap * sizeof(Ev));
+        evoff = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)(nq + 2));        // [nq+1] first event of each query
+        candK = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.cand_cap);
+        candM = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.cand_cap);
+        qoff = reinterpret_cast<uint16_t*>(smem + off);                                                     // [GROUP_MAX+1] byte offset of the query's text in QB
+        rowoff = qoff + (GROUP_MAX + 1);                                                                    // [GROUP_MAX+1] first seed row
+        qm = rowoff + (GROUP_MAX + 1);                                                                      // [GROUP_MAX] region length
+        off += ClassCfg::al(2 * 3 * (size_t)(GROUP_MAX + 1));
+        qcnt = reinterpret_cast<int*>(smem + off);                                                          // [GROUP_MAX] staged events per query
+        qfill = qcnt + GROUP_MAX;
+        off += ClassCfg::al(4 * 2 * (size_t)GROUP_MAX);
+        // [0]=hit count [1]=staged events [2]=ncand [3]=overflow [4..5]=cand base (int64) [6]=group size
+        s_int = reinterpret_cast<int*>(smem + off);
+    }
+};
+
+// The complete search of ONE window by the whole CTA.  `s_bar` = two mbarriers initialised by the caller ([0] count 1: the window
+// text; [1] count blockDim.x: a group's query texts); wphase / qphase carry their parities from window to window, so a CTA can
+// process any number of windows.  On return (after a __syncthreads) sv.s_int[3] = overflow code (0 = none, 1 = a per-CTA
+// capacity, 2 = the global candidate buffer), sv.s_int[2] = candidates written, sv.s_int[4..5] = their first slot in the global
+// arrays, sv.candK[] = their window positions, sv.MEP[] = the folded end positions.
+__device__ __forceinline__ void small_window(
     const uint8_t* __restrict__ text, const int64_t* __restrict__ gbase_fwd, const int64_t* __restrict__ gbase_rc,
-    const int64_t* __restrict__ glen, int nq, const TaskDev* __restrict__ tasks, const int32_t* __restrict__ qcoords,
-    const int32_t* __restrict__ task_ids, int ntasks, ClassCfg cfg, TaskOut* __restrict__ outs,
+    const int64_t* __restrict__ glen, int nq, const TaskDev tk, const int32_t* __restrict__ qs, const int32_t* __restrict__ ql,
+    const ClassCfg& cfg, SmemView& sv, uint64_t* s_bar, uint8_t* s_mis, uint32_t& wphase, uint32_t& qphase,
     unsigned long long* __restrict__ cand_counter, unsigned long long cand_cap_global, int32_t* __restrict__ out_k,
     int32_t* __restrict__ out_lon, int32_t* __restrict__ out_sp, uint8_t* __restrict__ out_fwd) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int ti = blockIdx.x;
-    if (ti >= ntasks) return;
     const int T = blockDim.x;
-    const int task_id = task_ids[ti];
-    const TaskDev tk = tasks[task_id];
     const int n = tk.n, minsize = tk.minsize;
-    size_t off = 0;
-    uint8_t* Rbuf = smem + off; off += ClassCfg::al(cfg.n_cap + 16);       // the window, at its global misalignment
-    uint16_t* lrp = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
-    uint16_t* MUP = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
-    uint16_t* MEP = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.n_cap);
-    uint32_t* R4 = reinterpret_cast<uint32_t*>(smem + off); off += ClassCfg::al(4 * (size_t)cfg.n_cap);          // seed code of every window position
-    uint32_t* tab = reinterpret_cast<uint32_t*>(smem + off); off += ClassCfg::al(8 * (size_t)cfg.n_cap);         // hash table of positions (2 n_cap slots)
-    uint8_t* QB = smem + off; off += ClassCfg::al((size_t)cfg.qbuf);                                              // group query text
-    uint32_t* Q4 = reinterpret_cast<uint32_t*>(smem + off); off += ClassCfg::al(8 * (size_t)cfg.rows_cap);       // seed rows: [2 row] = fwd, [2 row + 1] = rc
-    uint8_t* rowq = smem + off; off += ClassCfg::al((size_t)cfg.rows_cap);                                        // group-local query of each row
-    uint32_t* HQ = reinterpret_cast<uint32_t*>(smem + off); off += ClassCfg::al(4 * (size_t)cfg.hq_cap);         // seed hits: l | row << 12 | strand << 31
-    Ev* stg = reinterpret_cast<Ev*>(smem + off); off += ClassCfg::al((size_t)cfg.stg_cap * sizeof(Ev));
-    Ev* evs = reinterpret_cast<Ev*>(smem + off); off += ClassCfg::al((size_t)cfg.ev_cap * sizeof(Ev));
-    uint16_t* evoff = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)(nq + 2));        // [nq+1] first event of each query
-    uint16_t* candK = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.cand_cap);
-    uint16_t* candM = reinterpret_cast<uint16_t*>(smem + off); off += ClassCfg::al(2 * (size_t)cfg.cand_cap);
-    uint16_t* qoff = reinterpret_cast<uint16_t*>(smem + off);                                                     // [GROUP_MAX+1] byte offset of the query's text in QB
-    uint16_t* rowoff = qoff + (GROUP_MAX + 1);                                                                    // [GROUP_MAX+1] first seed row
-    uint16_t* qm = rowoff + (GROUP_MAX + 1);                                                                      // [GROUP_MAX] region length
-    off += ClassCfg::al(2 * 3 * (size_t)(GROUP_MAX + 1));
-    __shared__ uint64_t s_bar[2];                          // [0]: the window text has arrived  [1]: a group's query texts have arrived
-    __shared__ uint8_t s_mis[2 * GROUP_MAX];               // misalignment (0..15) of every staged strand: the string starts there in its slot
-    int* qcnt = reinterpret_cast<int*>(smem + off);                                                               // [GROUP_MAX] staged events per query
-    int* qfill = qcnt + GROUP_MAX;
-    off += ClassCfg::al(4 * 2 * (size_t)GROUP_MAX);
-    // [0]=hit count [1]=staged events [2]=ncand [3]=overflow [4..5]=cand base (int64) [6]=group size
-    int* s_int = reinterpret_cast<int*>(smem + off);
+    uint8_t* Rbuf = sv.Rbuf; uint16_t* lrp = sv.lrp; uint16_t* MUP = sv.MUP; uint16_t* MEP = sv.MEP; uint32_t* R4 = sv.R4; uint32_t* tab = sv.tab;
+    uint8_t* QB = sv.QB; uint32_t* Q4 = sv.Q4; uint8_t* rowq = sv.rowq; uint32_t* HQ = sv.HQ; Ev* stg = sv.stg; Ev* evs = sv.evs;
+    uint16_t* evoff = sv.evoff; uint16_t* candK = sv.candK; uint16_t* candM = sv.candM; uint16_t* qoff = sv.qoff; uint16_t* rowoff = sv.rowoff;
+    uint16_t* qm = sv.qm; int* qcnt = sv.qcnt; int* qfill = sv.qfill; int* s_int = sv.s_int;
     const int tid = threadIdx.x;
-    const int32_t* qs = qcoords + tk.qcoord_off;
-    const int32_t* ql = qs + nq;
-
     // seed length: consecutive seeds of a diagonal abut (step <= K) whenever minsize <= 19
     const int SEED_K = min(SEED_K_MAX, max(SEED_K_MIN, (minsize + 2) >> 1));
     const int step = max(1, minsize - SEED_K + 1);
@@ -202,7 +210,6 @@ __global__ void __launch_bounds__(SM_MAX_THREADS, 4) small_region_kernel(
     while ((1 << hbits) < 2 * cfg.n_cap) ++hbits;
     const uint32_t hmask = (1u << hbits) - 1u;
     const uint8_t* R = Rbuf + (int)(tk.ref_off & 15);
-    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], (uint32_t)T); fence_mbar_init(); }
     for (int i = tid; i < n; i += T) { MUP[i] = 0; MEP[i] = (uint16_t)n; lrp[i] = LRP_UNKNOWN; }
     for (int i = tid; i < (1 << hbits); i += T) tab[i] = SEED_PAD;
     if (tid < 8) s_int[tid] = 0;
@@ -215,7 +222,6 @@ __global__ void __launch_bounds__(SM_MAX_THREADS, 4) small_region_kernel(
     }
     const int nseed = n >= SEED_K ? n - SEED_K + 1 : 0;            // reference positions holding a seed
     bool window_ready = false;
-    uint32_t qphase = 0;
 
     int e0 = 0;                                                     // events stored so far (all earlier groups)
     int q0 = 0;
@@ -259,7 +265,7 @@ __global__ void __launch_bounds__(SM_MAX_THREADS, 4) small_region_kernel(
         }
         if (!window_ready) {
             // the window's seed codes and their hash table (the group's copies are in flight meanwhile)
-            mbar_wait(&s_bar[0], 0);
+            mbar_wait(&s_bar[0], wphase);
             for (int i = tid; i < nseed; i += T) {
                 const uint32_t code = pack_seed(R + i, SEED_K);
                 R4[i] = code;
@@ -366,7 +372,8 @@ __global__ void __launch_bounds__(SM_MAX_THREADS, 4) small_region_kernel(
         q0 += G;
         __syncthreads();
     }
-    if (!window_ready) mbar_wait(&s_bar[0], 0);        // (no query, or an early exit: never leave with the window copy in flight)
+    if (!window_ready) mbar_wait(&s_bar[0], wphase);   // (no query, or an early exit: never leave with the window copy in flight)
+    wphase ^= 1u;
     __syncthreads();
     // A5: ordered emission by warp 0
     if (!s_int[3] && tid < 32) {
@@ -418,7 +425,35 @@ __global__ void __launch_bounds__(SM_MAX_THREADS, 4) small_region_kernel(
         out_k[base + c] = k;
         out_lon[base + c] = (int)MEP[k] - k;
     }
-    if (tid == 0) { outs[task_id].ncand = ovf ? -ovf : nc; outs[task_id].cand_base = base; outs[task_id].pad = 0; }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SM_MAX_THREADS, 4) small_region_kernel(
+    const uint8_t* __restrict__ text, const int64_t* __restrict__ gbase_fwd, const int64_t* __restrict__ gbase_rc,
+    const int64_t* __restrict__ glen, int nq, const TaskDev* __restrict__ tasks, const int32_t* __restrict__ qcoords,
+    const int32_t* __restrict__ task_ids, int ntasks, ClassCfg cfg, TaskOut* __restrict__ outs,
+    unsigned long long* __restrict__ cand_counter, unsigned long long cand_cap_global, int32_t* __restrict__ out_k,
+    int32_t* __restrict__ out_lon, int32_t* __restrict__ out_sp, uint8_t* __restrict__ out_fwd) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint64_t s_bar[2];                          // [0]: the window text has arrived  [1]: a group's query texts have arrived
+    __shared__ uint8_t s_mis[2 * GROUP_MAX];               // misalignment (0..15) of every staged strand: the string starts there in its slot
+    const int ti = blockIdx.x;
+    if (ti >= ntasks) return;
+    const int task_id = task_ids[ti];
+    const TaskDev tk = tasks[task_id];
+    SmemView sv;
+    sv.carve(smem, cfg, nq);
+    if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], (uint32_t)blockDim.x); fence_mbar_init(); }
+    uint32_t wphase = 0, qphase = 0;
+    const int32_t* qs = qcoords + tk.qcoord_off;
+    small_window(text, gbase_fwd, gbase_rc, glen, nq, tk, qs, qs + nq, cfg, sv, s_bar, s_mis, wphase, qphase, cand_counter, cand_cap_global,
+                 out_k, out_lon, out_sp, out_fwd);
+    if (threadIdx.x == 0) {
+        const int ovf = sv.s_int[3];
+        outs[task_id].ncand = ovf ? -ovf : sv.s_int[2];
+        outs[task_id].cand_base = *reinterpret_cast<int64_t*>(&sv.s_int[4]);
+        outs[task_id].pad = 0;
+    }
 }
 
 }  // namespace small

@@ -1,5 +1,6 @@
 #include "aligner.h"
 #include "parallel.h"
+#include "accept_impl.h"
 #include <algorithm>
 #include <chrono>
 #include <cstring>
@@ -10,21 +11,15 @@
 #include <unordered_set>
 #include <atomic>
 #include <thread>
+#include <map>
+#include <memory>
+#include <mutex>
 
 namespace pb200 {
 
 namespace {
 inline double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
-}
-inline uint8_t comp_base(uint8_t c) {          // Aligner::reversec (src/parsnp.cpp:1294-1393) on the ingest alphabet
-    switch (c) {
-        case 'A': return 'T';
-        case 'T': return 'A';
-        case 'C': return 'G';
-        case 'G': return 'C';
-        default: return 'N';
-    }
 }
 }  // namespace
 
@@ -61,7 +56,7 @@ void BitRow::clear_range(int64_t a, int64_t b) {
 int64_t BitRow::run_up_slow(int64_t a, int64_t b) const {
     int64_t i = a;
     while (i < b) {
-        uint64_t inv = ~(w_[i >> 6] >> (i & 63));          // first zero bit at or after i
+        uint64_t inv = ~(word(i >> 6) >> (i & 63));          // first zero bit at or after i
         int avail = 64 - (int)(i & 63);
         int z = inv ? __builtin_ctzll(inv) : 64;
         if (z < avail) { i += z; break; }
@@ -74,7 +69,7 @@ int64_t BitRow::run_down_slow(int64_t a, int64_t b) const {
     int64_t i = b - 1;                                       // examine i, i-1, ...
     while (i >= a) {
         int pos = (int)(i & 63);
-        uint64_t inv = ~(w_[i >> 6] << (63 - pos));          // bit 63 corresponds to i
+        uint64_t inv = ~(word(i >> 6) << (63 - pos));          // bit 63 corresponds to i
         int z = inv ? __builtin_clzll(inv) : 64;
         int avail = pos + 1;
         if (z < avail) { i -= z; break; }
@@ -86,21 +81,45 @@ int64_t BitRow::run_down_slow(int64_t a, int64_t b) const {
 int64_t BitRow::prev_set(int64_t i) const {
     if (i < 0) return -1;
     int64_t wi = i >> 6;
-    uint64_t cur = w_[wi] & (~0ull >> (63 - (i & 63)));
+    uint64_t cur = word(wi) & (~0ull >> (63 - (i & 63)));
     for (;;) {
         if (cur) return (wi << 6) + 63 - __builtin_clzll(cur);
         if (wi == 0) return -1;
-        cur = w_[--wi];
+        cur = word(--wi);
+    }
+}
+int64_t BitRow::prev_set_from(int64_t i, int64_t lo) const {
+    if (i < lo || i < 0) return -1;
+    if (lo < 0) lo = 0;
+    int64_t wi = i >> 6;
+    const int64_t wl = lo >> 6;
+    uint64_t cur = word(wi) & (~0ull >> (63 - (i & 63)));
+    for (;;) {
+        if (cur) { const int64_t r = (wi << 6) + 63 - __builtin_clzll(cur); return r >= lo ? r : -1; }
+        if (wi <= wl) return -1;
+        cur = word(--wi);
+    }
+}
+void BitRow::copy_range_from(const BitRow& src, int64_t a, int64_t b) {
+    if (a >= b) return;
+    const int64_t wa = a >> 6, wb = (b - 1) >> 6;
+    for (int64_t wi = wa; wi <= wb; ++wi) {
+        uint64_t m = ~0ull;
+        if (wi == wa) m &= ~0ull << (a & 63);
+        if (wi == wb) m &= ~0ull >> (63 - ((b - 1) & 63));
+        const uint64_t v = src.word(wi) & m;
+        __atomic_fetch_and(&w_[(size_t)wi], ~m | v, __ATOMIC_RELAXED);
+        __atomic_fetch_or(&w_[(size_t)wi], v, __ATOMIC_RELAXED);
     }
 }
 int64_t BitRow::next_set(int64_t i, int64_t limit) const {
     if (i >= limit) return limit;
     int64_t wi = i >> 6, wl = (limit - 1) >> 6;
-    uint64_t cur = w_[wi] & (~0ull << (i & 63));
+    uint64_t cur = word(wi) & (~0ull << (i & 63));
     for (;;) {
         if (cur) { int64_t r = (wi << 6) + __builtin_ctzll(cur); return r < limit ? r : limit; }
         if (wi >= wl) return limit;
-        cur = w_[++wi];
+        cur = word(++wi);
     }
 }
 
@@ -297,86 +316,11 @@ void Aligner::search_regions(CandCache& C, const RegionPool& src, const std::vec
     }
 }
 
-// ------------------------------------------------------------------ setMums1 loop D (src/parsnp.cpp:1713-1842)
+// ------------------------------------------------------------------ setMums1 loop D (src/parsnp.cpp:1713-1842): accept_impl.h
 void Aligner::accept_candidates(const int64_t* rs, const int64_t* re, int64_t rsl, const CandCache& C, int cache_idx,
                                 std::vector<BitRow>& layout, MumPool& mp, std::vector<int>& found, bool atomic, bool trace) {
-    const CacheEntry& ce = C.entries[cache_idx];
-    const int nq = n_ - 1;
-    int64_t st_buf[64];
-    uint8_t fw_buf[64];
-    std::vector<int64_t> st_vec;
-    std::vector<uint8_t> fw_vec;
-    int64_t* st = st_buf;
-    uint8_t* fw = fw_buf;
-    if (n_ > 64) { st_vec.resize(n_); fw_vec.resize(n_); st = st_vec.data(); fw = fw_vec.data(); }
-    for (int wi = 0; wi < ce.nwin; ++wi) {
-        const WinRec& win = C.wins[ce.first_win + wi];
-        const CandBatch& cb = C.chunks[win.chunk];
-        if (trace) trace_.emplace_back(win.ref_start, win.ref_len);
-        for (int32_t c = 0; c < win.ncand; ++c) {
-            const int64_t ci = win.cand_off + c;
-            const int64_t LON = cb.lon[ci];
-            bool bad = false;
-            // Mum.DSP is 1-based (src/parsnp.cpp:1671,1681); range pre-check in unsigned arithmetic (1723)
-            uint64_t dsp0 = (uint64_t)((int64_t)cb.k[ci] + 1 + win.ref_start);
-            if ((uint64_t)(dsp0 - (uint64_t)rs[0]) > (uint64_t)(uint32_t)(re[0] - rs[0])) bad = true;
-            st[0] = (int64_t)dsp0 - 1;
-            fw[0] = 1;
-            // shortcut: a candidate whose reference interval is already covered trims to nothing in the first pass of the trim loop
-            // below whatever the other genomes hold, and nothing before that point has a side effect
-            if (!bad && st[0] + LON <= len_[0] && layout[0].get(st[0]) && layout[0].run_up(st[0], st[0] + LON) == LON) continue;
-            // TMum ctor (src/TMum.cpp:13-72): a reverse-strand start is mirrored on the WHOLE genome length; the ctor's `ok` ends up
-            // false as soon as one genome's interval leaves its sequence (a middle-genome failure makes the reference throw;
-            // unreachable).  Range pre-check and ctor are fused into one pass; both only ever skip the candidate.
-            bool any_fail = st[0] + LON > len_[0] || st[0] < 0;
-            const int32_t* spj = cb.sp.data() + ci * nq;
-            const uint8_t* fwj = cb.fwd.data() + ci * nq;
-            for (int j = 1; j < n_; ++j) {
-                const uint64_t dsp = (uint64_t)((int64_t)spj[j - 1] + 1 + rs[j]);
-                bad |= (uint64_t)(dsp - (uint64_t)rs[j]) > (uint64_t)(uint32_t)(re[j] - rs[j]);
-                int64_t s = (int64_t)dsp - 1;
-                const uint8_t f = fwj[j - 1];
-                if (!f) s = len_[j] - (s + LON);
-                any_fail |= (s + LON > len_[j]) | (s < 0);
-                st[j] = s;
-                fw[j] = f;
-            }
-            if (bad || any_fail || LON < 5) continue;
-            // trim (src/parsnp.cpp:1399-1477): every trim shifts ALL genomes, strand ignored
-            int64_t length = LON;
-            for (int j = 0; j < n_; ++j) {
-                int64_t t1 = layout[j].run_up(st[j], st[j] + length);
-                if (t1) { for (int i = 0; i < n_; ++i) st[i] += t1; length -= t1; }
-                int64_t t2 = layout[j].run_down(st[j], st[j] + length);
-                length -= t2;
-                if (length <= 0) break;          // nothing left: the remaining genomes' loops would not execute (src/parsnp.cpp:1409,1443)
-            }
-            if (length < 2 || n_ <= 1) continue;
-            // reverse-strand genomes are verified against the reference substring (src/parsnp.cpp:1800-1825)
-            bool badmum = false;
-            for (int k = 0; k < n_ && !badmum; ++k) {
-                if (fw[k]) continue;
-                const uint8_t* g0 = seq_[0] + st[0];
-                const uint8_t* gk = seq_[k] + st[k];
-                for (int64_t t = 0; t < length; ++t)
-                    if (comp_base(gk[length - 1 - t]) != g0[t]) { badmum = true; break; }
-            }
-            if (badmum) continue;
-            for (int k = 0; k < n_; ++k) {
-                if (atomic) layout[k].set_range_atomic(st[k], st[k] + length);
-                else layout[k].set_range(st[k], st[k] + length);
-            }
-            MumRec m;
-            m.length = length;
-            m.slength = rsl;
-            m.off = (int64_t)mp.start.size();
-            m.alive = true;
-            mp.start.insert(mp.start.end(), st, st + n_);
-            mp.fwd.insert(mp.fwd.end(), fw, fw + n_);
-            found.push_back((int)mp.mums.size());
-            mp.mums.push_back(m);
-        }
-    }
+    DirectAccess acc{layout, atomic};
+    accept_candidates_t(rs, re, rsl, C, cache_idx, acc, mp, found, trace);
 }
 
 // The same loop for a big candidate list on an EMPTY layout region (the anchors): candidates whose intervals overlap no other
@@ -553,26 +497,11 @@ void Aligner::accept_candidates_parallel(const int64_t* rs, const int64_t* re, i
     });
 }
 
-// determineRegion (src/parsnp.cpp:1199-1290) into tmp coordinate buffers; returns slength
+// determineRegion (src/parsnp.cpp:1199-1290) on one bitmap: accept_impl.h
 static int64_t det_region(const std::vector<BitRow>& layout, const std::vector<int64_t>& len, int n,
                           const int64_t* mstart, int64_t mlen, bool left, int64_t* S, int64_t* E) {
-    int64_t sl = 500000000;
-    for (int i = 0; i < n; ++i) {
-        if (left) {
-            int64_t cp = layout[i].prev_set(mstart[i] - 1);
-            if (cp < 0) cp = 0;
-            S[i] = cp + 1;
-            E[i] = mstart[i] - 1;
-        } else {
-            int64_t en = mstart[i] + mlen;
-            int64_t cp = en + 1;
-            if (cp < len[i]) cp = layout[i].next_set(cp, len[i]);
-            S[i] = en + 1;
-            E[i] = cp - 1;
-        }
-        sl = std::min(sl, E[i] - S[i]);
-    }
-    return sl;
+    DirectAccess acc{const_cast<std::vector<BitRow>&>(layout), false};
+    return det_region_impl(acc, len, n, mstart, mlen, left, S, E);
 }
 
 // ------------------------------------------------------------------ anchors (src/parsnp.cpp:2121-2174)
@@ -788,13 +717,13 @@ inline bool operator<(const QE& a, const QE& b) { return a.s0 < b.s0; }   // ope
 }
 
 void Aligner::process_queue_exact(const std::vector<int>& initial, RegionPool& rp, std::vector<BitRow>& layout, MumPool& mp,
-                                  std::vector<int>& out_mums) {
+                                  std::vector<int>& out_mums, const std::vector<int>* slice_ids) {
     // exact emulation of `vector<TRegion> regions`: slow mode keeps the vector itself; fast mode is valid while
     // all start[0] keys are distinct (then every correct sort yields the same sequence).
     auto req = [&](int a, int b) { return std::memcmp(rp.start(a), rp.start(b), sizeof(int64_t) * 2 * n_) == 0; };
     std::vector<QE> vec;
     for (size_t i = 0; i < initial.size(); ++i)
-        vec.push_back(QE{rp.start(initial[i])[0], initial[i], i < slice_of_initial_.size() ? slice_of_initial_[i] : -1,
+        vec.push_back(QE{rp.start(initial[i])[0], initial[i], slice_ids ? (*slice_ids)[i] : (i < slice_of_initial_.size() ? slice_of_initial_[i] : -1),
                          coords_hash(rp.start(initial[i]), 2 * n_)});
     int ready_upto = 0;                       // speculation slices [0, ready_upto) are known to be published
     // fast mode: the queue as a vector sorted by DESCENDING start[0] (front of the reference's vector = back of this one).
@@ -820,8 +749,13 @@ void Aligner::process_queue_exact(const std::vector<int>& initial, RegionPool& r
     std::vector<int64_t> lS(n_), lE(n_), rS(n_), rE(n_);
     static const bool prof = getenv("PB200_PROFILE_HOST") != nullptr;
     uint64_t pc[5] = {0, 0, 0, 0, 0}, pt = 0;
-#define PROF_MARK(i) do { if (prof) { uint64_t x_ = __builtin_ia32_rdtsc(); pc[i] += x_ - pt; pt = x_; } } while (0)
-    if (prof) pt = __builtin_ia32_rdtsc();
+#if defined(__x86_64__)
+#define PB_TICKS() __builtin_ia32_rdtsc()
+#else
+#define PB_TICKS() ((uint64_t)std::chrono::steady_clock::now().time_since_epoch().count())
+#endif
+#define PROF_MARK(i) do { if (prof) { uint64_t x_ = PB_TICKS(); pc[i] += x_ - pt; pt = x_; } } while (0)
+    if (prof) pt = PB_TICKS();
     while (fast_mode ? !fast.empty() : !vec.empty()) {
         int cur, cur_slice;
         uint64_t cur_hash;
@@ -939,9 +873,11 @@ void Aligner::process_queue_exact(const std::vector<int>& initial, RegionPool& r
 
 void Aligner::do_work_exact() {
     double t0 = now_s();
-    std::vector<int> out;
-    process_queue_exact(initial_regions_, rp_, truth_.layout, mp_, out);
-    all_mums_.insert(all_mums_.end(), out.begin(), out.end());
+    if (!do_work_parallel()) {                 // replay.cpp: independent gaps on several threads when the anchors allow it
+        std::vector<int> out;
+        process_queue_exact(initial_regions_, rp_, truth_.layout, mp_, out);
+        all_mums_.insert(all_mums_.end(), out.begin(), out.end());
+    }
     stats_.t_replay += now_s() - t0;
 }
 
@@ -1294,13 +1230,123 @@ void Aligner::unaligned_regions(std::vector<int32_t>& genome, std::vector<int64_
     }
 }
 
+// ------------------------------------------------------------------ recursion discovered by the engine (cuda/recursion.cuh)
+namespace {
+// minsize(slength) of an expression for slength < N, computed once per process and expression (the calculator is a string
+// interpreter: ~0.2 us per value)
+std::shared_ptr<const std::vector<int32_t>> minsize_table(const std::string& expr, int N, int threads) {
+    static std::mutex mu;
+    static std::map<std::string, std::shared_ptr<const std::vector<int32_t>>> cache;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(expr);
+        if (it != cache.end()) return it->second;
+    }
+    std::shared_ptr<std::vector<int32_t>> tab(new std::vector<int32_t>((size_t)N, 0));
+    const MinSizeExpr ex(expr);
+    std::atomic<int> bad(0);
+    const long per = 256;
+    parallel_chunks(threads, (N + per - 1) / per, [&](long c) {
+        for (long sl = c * per; sl < std::min<long>(N, (c + 1) * per); ++sl) {
+            try { (*tab)[(size_t)sl] = ex(sl); } catch (...) { bad.store(1); }
+        }
+    });
+    if (bad.load()) return nullptr;              // (an expression that fails for some length: left to the path that evaluates on demand)
+    std::lock_guard<std::mutex> lk(mu);
+    cache[expr] = tab;
+    return tab;
+}
+}  // namespace
+
+bool Aligner::discover_on_device() {
+    const double t0 = now_s();
+    const size_t R = initial_regions_.size();
+    const int TABN = 4160;                       // covers every window the shared-memory search kernel takes (<= 4096 bases)
+    std::shared_ptr<const std::vector<int32_t>> tab = minsize_table(prm_.mums, TABN, threads_);
+    if (!tab) return false;
+    pod_vector<int64_t> coords(R * 2 * (size_t)n_);
+    const long per = 4096;
+    parallel_chunks(R > 16384 ? threads_ : 1, ((long)R + per - 1) / per, [&](long c) {
+        for (size_t i = (size_t)c * per; i < std::min(R, (size_t)(c + 1) * per); ++i)
+            std::memcpy(&coords[i * 2 * (size_t)n_], rstart(initial_regions_[i]), sizeof(int64_t) * 2 * (size_t)n_);
+    });
+    std::vector<const uint64_t*> rows((size_t)n_);
+    std::vector<int64_t> nwords((size_t)n_);
+    for (int g = 0; g < n_; ++g) { rows[(size_t)g] = truth_.layout[(size_t)g].words(); nwords[(size_t)g] = truth_.layout[(size_t)g].nwords(); }
+    RecursionRequest rq;
+    rq.n = n_; rq.coords = coords.data(); rq.nregions = (int)R; rq.layout = rows.data(); rq.layout_words = nwords.data();
+    rq.q = prm_.q; rq.p = prm_.p; rq.minsize_tab = tab->data(); rq.minsize_n = TABN;
+    RecursionResult res;
+    {
+        std::lock_guard<std::mutex> lk(backend_mu_);
+        if (!be_->discover_recursion(rq, res)) return false;
+    }
+    const double t1 = now_s();
+    // ---- the result as a candidate cache (one window per region, candidates where the engine left them)
+    slice_cache_.clear();
+    slice_cache_.emplace_back(new CandCache);
+    CandCache& C = *slice_cache_.back();
+    const size_t NR = res.nregions;
+    C.rp.n = n_;
+    C.rp.coord.resize(NR * 2 * (size_t)n_);
+    C.rp.slen.resize(NR);
+    C.entries.resize(NR);
+    C.wins.resize(NR);
+    C.chunks.emplace_back();
+    CandBatch& cb = C.chunks.back();
+    cb.nq = n_ - 1;
+    cb.k.swap(res.k); cb.lon.swap(res.lon); cb.sp.swap(res.sp); cb.fwd.swap(res.fwd);
+    cb.off.assign(1, 0);
+    const size_t NC = cb.k.size();
+    std::vector<uint64_t> hashes(NR);
+    parallel_chunks(NR > 16384 ? threads_ : 1, ((long)NR + per - 1) / per, [&](long c) {
+        for (size_t r = (size_t)c * per; r < std::min(NR, (size_t)(c + 1) * per); ++r) {
+            const int32_t* s = &res.coords[r * 2 * (size_t)n_];
+            int64_t* d = &C.rp.coord[r * 2 * (size_t)n_];
+            for (int g = 0; g < n_; ++g) { d[g] = s[g]; d[n_ + g] = (int64_t)s[g] + s[n_ + g]; }
+            C.rp.slen[r] = res.slen[r];
+            CacheEntry e; e.region = (int)r; e.first_win = (int64_t)r; e.nwin = 1;
+            C.entries[r] = e;
+            WinRec w; w.ref_start = s[0]; w.ref_len = s[n_]; w.cand_off = res.cand_base[r]; w.ncand = res.ncand[r]; w.chunk = 0;
+            if (w.ncand < 0 || (uint64_t)w.cand_off + (uint64_t)w.ncand > NC) w.ncand = -1;       // not searched (or its candidates did not fit)
+            C.wins[r] = w;
+            hashes[r] = coords_hash(d, 2 * n_);
+        }
+    });
+    C.map.reserve(NR);
+    int64_t searched = 0, cands = 0;
+    for (size_t r = 0; r < NR; ++r) {
+        if (C.wins[r].ncand < 0) { C.wins[r].ncand = 0; continue; }       // stays out of the index: the replay searches it on demand
+        C.map.insert(hashes[r], (int)r);
+        ++searched;
+        cands += C.wins[r].ncand;
+    }
+    slice_of_initial_.assign(R, 0);
+    {
+        std::lock_guard<std::mutex> lk(slice_mu_);
+        slices_ready_ = 1;
+    }
+    stats_.spec_slices = 1;
+    stats_.spec_regions += searched;
+    stats_.regions_searched += searched;
+    stats_.windows_searched += searched;
+    stats_.candidates += cands;
+    stats_.spec_levels += res.levels;
+    stats_.spec_deferred += res.deferred + res.dropped;
+    stats_.t_spec_search += t1 - t0;
+    stats_.t_spec_host += now_s() - t1;
+    return true;
+}
+
 // ------------------------------------------------------------------ main sequence (src/parsnp.cpp:3187-3273)
 bool Aligner::run() {
     double t0 = now_s();
     set_initial_clusters();
     if (!prm_.anchors_only) {
         stats_.host_threads = threads_;
-        if (speculate_ && !initial_regions_.empty()) {
+        if (speculate_ && !initial_regions_.empty() && pipeline_ && discover_on_device()) {
+            // the engine followed the recursion itself (cuda/recursion.cuh): one published "slice" holds every predicted region
+        } else if (speculate_ && !initial_regions_.empty()) {
             // slices of the initial regions (reference order): the speculation thread discovers and searches slice k+1 while the
             // replay below consumes slice k
             const char* es = getenv("PB200_SPEC_SLICES");
@@ -1333,7 +1379,12 @@ bool Aligner::run() {
             for (size_t k = 0; k < K; ++k) slice_cache_.emplace_back(new CandCache);
             slices_ready_ = 0;
             if (pipeline_) spec_thread_ = std::thread([this] { speculation_thread_main(); });
-            else speculation_thread_main();
+            else {
+                // lock step (collectives inside the search): an error must surface HERE, on every rank at the same call - a rank
+                // that went on with a half-filled cache would issue searches, i.e. collectives, that the others never join
+                speculation_thread_main();
+                if (spec_error_) std::rethrow_exception(spec_error_);
+            }
         }
         try {
             do_work_exact();

@@ -46,7 +46,10 @@ struct AlignParams {                 // ini keys, src/parsnp.cpp:2866-2901
 class BitRow {
 public:
     void init(int64_t nbits_with_sentinel);
-    inline bool get(int64_t i) const { return (w_[i >> 6] >> (i & 63)) & 1ull; }
+    // (words are read with relaxed atomic loads: the replay tasks and the speculative passes read rows that other threads
+    //  extend with atomic ORs at other bit positions of the same words)
+    inline uint64_t word(int64_t wi) const { return __atomic_load_n(&w_[(size_t)wi], __ATOMIC_RELAXED); }
+    inline bool get(int64_t i) const { return (word(i >> 6) >> (i & 63)) & 1ull; }
     inline void set_range(int64_t a, int64_t b) {   // [a,b)
         if (a >= b) return;
         const int64_t wa = a >> 6, wb = (b - 1) >> 6;
@@ -63,8 +66,12 @@ public:
     int64_t run_up_slow(int64_t a, int64_t b) const;
     int64_t run_down_slow(int64_t a, int64_t b) const;
     int64_t prev_set(int64_t i) const;        // largest set index <= i, or -1
+    int64_t prev_set_from(int64_t i, int64_t lo) const;   // largest set index in [lo, i], or -1
+    void copy_range_from(const BitRow& src, int64_t a, int64_t b);   // bits [a,b) := src's (atomic per word)
     int64_t next_set(int64_t i, int64_t limit) const;   // smallest set index in [i,limit), or limit
     int64_t nbits() const { return nbits_; }
+    const uint64_t* words() const { return w_.data(); }
+    int64_t nwords() const { return (int64_t)w_.size(); }
 private:
     std::vector<uint64_t> w_;
     int64_t nbits_ = 0;
@@ -108,6 +115,11 @@ struct AlignStats {
     double t_replay_wait = 0;        // replay blocked on a speculation slice still in flight
     int64_t spec_slices = 0;
     int64_t mums_filtered = 0, clusters_filtered = 0;      // Aligner::filtered / filtered_clusters (src/parsnp.cpp:406,451,460)
+    // parallel exact replay (replay.cpp): tasks run, foreign (outside the task's own span) reads / writes, restarts after a
+    // foreign write hit a running task, 1 = the run fell back to the sequential loop (ties or non-collinear anchors), workers
+    int64_t replay_tasks = 0, replay_foreign_reads = 0, replay_foreign_writes = 0, replay_restarts = 0, replay_fallback = 0,
+            replay_workers = 1, spec_deferred = 0;
+    double t_replay_merge = 0;
 };
 
 class Aligner {
@@ -191,9 +203,21 @@ private:
     // the same for a long candidate list on an empty layout (anchors): non-overlapping candidates in parallel
     void accept_candidates_parallel(const int64_t* rs, const int64_t* re, int64_t rsl, const CandCache& C, int cache_idx,
                                     std::vector<BitRow>& layout, MumPool& mp, std::vector<int>& found, bool trace);
+    // the two loops above and determineRegion over a layout access policy (accept_impl.h): one bitmap (DirectAccess) or a
+    // replay task's view of the shared bitmaps (replay.cpp)
+    template <class Acc> void accept_candidates_t(const int64_t* rs, const int64_t* re, int64_t rsl, const CandCache& C, int cache_idx, Acc& acc,
+                                                  MumPool& mp, std::vector<int>& found, bool trace);
+    template <class Acc> int64_t det_region_t(Acc& acc, const int64_t* mstart, int64_t mlen, bool left, int64_t* S, int64_t* E) const;
+    friend struct ReplayCtx;
+    friend struct ReplayTask;
+    friend struct TaskAccess;
+    // doWork as independent tasks (runs of consecutive initial regions) on several threads, exact: replay.cpp.
+    // Returns false when the preconditions do not hold (nothing touched): the caller runs process_queue_exact.
+    bool do_work_parallel();
+    void set_replay_threads(int t) { replay_threads_ = t; }
     // doWork's loop over a queue of regions living in `rp`, in the exact reference order
     void process_queue_exact(const std::vector<int>& initial, RegionPool& rp, std::vector<BitRow>& layout, MumPool& mp,
-                             std::vector<int>& out_mums);
+                             std::vector<int>& out_mums, const std::vector<int>* slice_ids = nullptr);
     // one speculative level over frontier[a,b): children coordinates appended to `out`
     void speculate_range(const CandCache& C, const RegionPool& F, const std::vector<int>& frontier, size_t a, size_t b,
                          std::vector<BitRow>& layout, MumPool& mp, RegionPool& out, bool atomic);
@@ -202,7 +226,9 @@ private:
     // level-synchronous discovery for one slice of the initial regions (ids into `src`) on the scratch layout `spec`
     void speculate_slice(CandCache& C, const RegionPool& src, const std::vector<int>& initial, World& spec);
     void speculation_thread_main();
+    bool discover_on_device();           // the engine follows the recursion itself (SearchBackend::discover_recursion)
     const CandCache* wait_slice(int slice);
+    void wait_slice_quiet(int slice);
     void do_work_exact();
     void filter_random1();
     void sort_final_mums();
@@ -242,6 +268,7 @@ private:
     int slices_ready_ = 0;                                  // slices [0, slices_ready_) are published (guarded by slice_mu_)
     std::exception_ptr spec_error_;
     bool pipeline_ = true;
+    int replay_threads_ = 0;                                // 0 = threads_
 
     std::vector<ClusterRec> clusters_;
     int threads_ = 1;

@@ -39,7 +39,9 @@ pb200_result* make_result(const Aligner& a, bool unaligned) {
                  (double)s.spec_levels, (double)s.windows_searched, (double)s.candidates, (double)s.slow_queue_iters,
                  s.t_anchor_search, s.t_anchor_host, s.t_spec_search, s.t_spec_host, s.t_replay, s.t_replay_search,
                  s.t_lcb, s.t_total, (double)s.host_threads, s.t_search_prep, s.t_search_backend, s.t_search_cache, s.t_replay_wait,
-                 (double)s.spec_slices, (double)s.mums_filtered, (double)s.clusters_filtered };
+                 (double)s.spec_slices, (double)s.mums_filtered, (double)s.clusters_filtered,
+                 (double)s.replay_tasks, (double)s.replay_foreign_reads, (double)s.replay_foreign_writes, (double)s.replay_restarts,
+                 (double)s.replay_fallback, (double)s.replay_workers, s.t_replay_merge, (double)s.spec_deferred };
     return r;
 }
 
@@ -120,7 +122,8 @@ int pb200_result_stats(const pb200_result* r, double* values, int cap) {
 }
 const char* pb200_stats_names(void) {
     return "anchors,regions_searched,spec_regions,replay_misses,spec_levels,windows_searched,candidates,slow_queue_iters,"
-           "t_anchor_search,t_anchor_host,t_spec_search,t_spec_host,t_replay,t_replay_search,t_lcb,t_total,host_threads,t_search_prep,t_search_backend,t_search_cache,t_replay_wait,spec_slices,mums_filtered,clusters_filtered";
+           "t_anchor_search,t_anchor_host,t_spec_search,t_spec_host,t_replay,t_replay_search,t_lcb,t_total,host_threads,t_search_prep,t_search_backend,t_search_cache,t_replay_wait,spec_slices,mums_filtered,clusters_filtered,"
+           "replay_tasks,replay_foreign_reads,replay_foreign_writes,replay_restarts,replay_fallback,replay_workers,t_replay_merge,spec_deferred";
 }
 void pb200_result_free(pb200_result* r) { delete r; }
 int pb200_minsize(const char* expr, int64_t slength) {
