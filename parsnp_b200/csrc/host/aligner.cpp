@@ -44,6 +44,17 @@ void BitRow::set_range_atomic(int64_t a, int64_t b) {
     for (int64_t i = wa + 1; i < wb; ++i) __atomic_store_n(&w_[i], ~0ull, __ATOMIC_RELAXED);
     __atomic_fetch_or(&w_[wb], mb, __ATOMIC_RELAXED);
 }
+void BitRow::set_range_owned(int64_t a, int64_t b, int64_t wlo, int64_t whi) {
+    if (a >= b) return;
+    const int64_t wa = a >> 6, wb = (b - 1) >> 6;
+    for (int64_t wi = wa; wi <= wb; ++wi) {
+        uint64_t m = ~0ull;
+        if (wi == wa) m &= ~0ull << (a & 63);
+        if (wi == wb) m &= ~0ull >> (63 - ((b - 1) & 63));
+        if (wi > wlo && wi < whi) __atomic_store_n(&w_[(size_t)wi], __atomic_load_n(&w_[(size_t)wi], __ATOMIC_RELAXED) | m, __ATOMIC_RELAXED);
+        else __atomic_fetch_or(&w_[(size_t)wi], m, __ATOMIC_RELAXED);
+    }
+}
 void BitRow::clear_range(int64_t a, int64_t b) {
     if (a >= b) return;
     int64_t wa = a >> 6, wb = (b - 1) >> 6;
@@ -887,6 +898,38 @@ void Aligner::do_work_exact() {
 void Aligner::sort_final_mums() {
     const size_t M = final_mums_.size();
     if (final_sorted_) return;                  // (removals keep the order; only `final_mums_ = all_mums_` resets the flag)
+    if (sorted_hint_.size() == M && M > 0) {
+        // the parallel replay delivered the ascending order with its MUMs (every task's MUMs sorted by its worker, tasks in
+        // reference order, merged with the anchors): verify it in parallel; ties still go through the literal std::sort below
+        const long per = 8192;
+        const long nch = ((long)M + per - 1) / per;
+        std::vector<uint8_t> ch_bad((size_t)nch, 0), ch_tie((size_t)nch, 0);
+        std::vector<int64_t> ch_minlen((size_t)nch, INT64_MAX);
+        parallel_chunks(M > 32768 ? threads_ : 1, nch, [&](long c) {
+            const size_t i0 = (size_t)c * per, i1 = std::min(M, (size_t)(c + 1) * per);
+            int64_t prev = i0 ? mum_start_[mums_[sorted_hint_[i0 - 1]].off] : INT64_MIN, ml = INT64_MAX;
+            for (size_t i = i0; i < i1; ++i) {
+                const MumRec& m = mums_[sorted_hint_[i]];
+                const int64_t s0 = mum_start_[m.off];
+                if (s0 < prev) ch_bad[c] = 1;
+                if (s0 == prev) ch_tie[c] = 1;
+                prev = s0;
+                ml = std::min(ml, m.length);
+            }
+            ch_minlen[c] = ml;
+        });
+        bool bad = false, tie = false;
+        int64_t ml = INT64_MAX;
+        for (long c = 0; c < nch; ++c) { bad |= ch_bad[c] != 0; tie |= ch_tie[c] != 0; ml = std::min(ml, ch_minlen[c]); }
+        if (!bad && !tie) {
+            final_mums_ = sorted_hint_;
+            sorted_hint_.clear();
+            final_min_length_ = ml;
+            final_sorted_ = true;
+            return;
+        }
+        sorted_hint_.clear();                   // (ties or an unexpected order: the general path)
+    }
     std::vector<std::pair<int64_t, int>> kv(M);
     // gather the keys (random reads into the MUM pools) in parallel; per chunk: descents inside, first/last key, min length
     const long per = 8192;
@@ -1378,7 +1421,7 @@ bool Aligner::run() {
             slice_cache_.clear();
             for (size_t k = 0; k < K; ++k) slice_cache_.emplace_back(new CandCache);
             slices_ready_ = 0;
-            if (pipeline_) spec_thread_ = std::thread([this] { speculation_thread_main(); });
+            if (pipeline_ && !getenv("PB200_SPEC_SYNC")) spec_thread_ = std::thread([this] { speculation_thread_main(); });   // (PB200_SPEC_SYNC: tools/host_bench.py times the replay alone)
             else {
                 // lock step (collectives inside the search): an error must surface HERE, on every rank at the same call - a rank
                 // that went on with a half-filled cache would issue searches, i.e. collectives, that the others never join
@@ -1399,6 +1442,7 @@ bool Aligner::run() {
     double t1 = now_s();
     final_mums_ = all_mums_;
     final_sorted_ = false;
+    if (sorted_hint_.size() != all_mums_.size()) sorted_hint_.clear();
     const bool prof = getenv("PB200_PROFILE_HOST") != nullptr;
     double tl[6] = {now_s(), 0, 0, 0, 0, 0};
     if (prm_.random) filter_random1();

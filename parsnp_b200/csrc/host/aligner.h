@@ -58,6 +58,9 @@ public:
     }
     void set_range_slow(int64_t a, int64_t b);
     void set_range_atomic(int64_t a, int64_t b);   // same, safe against concurrent writers of neighbouring bits
+    // same with plain (relaxed atomic) loads and stores instead of locked read-modify-writes for the words strictly inside
+    // (wlo, whi): for a writer that is the only one for those words; the words at and outside the bounds are OR-ed atomically
+    void set_range_owned(int64_t a, int64_t b, int64_t wlo, int64_t whi);
     void clear_range(int64_t a, int64_t b);   // [a,b)
     // # consecutive set bits a, a+1, ... (< b); the common case (bit a clear) is answered inline
     inline int64_t run_up(int64_t a, int64_t b) const { return (a >= b || !get(a)) ? 0 : run_up_slow(a, b); }
@@ -250,6 +253,7 @@ private:
     pod_vector<uint8_t>& mum_fwd_ = mp_.fwd;
     std::vector<int> all_mums_;       // this->mums in push order (ids into mums_)
     std::vector<int> final_mums_;
+    std::vector<int> sorted_hint_;           // all_mums_ in ascending start[0] order when the producer knows it (parallel replay), else empty
     bool final_sorted_ = false;              // final_mums_ is in ascending start[0] order
     int64_t final_min_length_ = 0;           // shortest MUM seen by the last sort_final_mums()
 

@@ -57,20 +57,30 @@ enum : int { T_IDLE = 0, T_RUNNING = 1, T_DONE = 2, T_DIRTY = 3 };
 
 struct ReplayTask {
     int first = 0, last = 0;                    // order[first, last): the task's initial regions in ascending start[0] order
+    int gfirst = 0, glast = 0;                  // its gaps (groups of initial regions with overlapping spans): [gfirst, glast)
     std::atomic<int> state{T_IDLE};
     std::atomic<bool> abort{false};
-    MumPool mp;                                 // accepted MUMs in pop order
-    RegionPool rp;                              // the task's regions (initial ones copied in, then the children)
-    struct FRead { int g; int64_t a, b; };      // foreign reads, positions [a, b]
-    std::vector<FRead> freads;
+    int worker = -1;                            // the worker whose arenas hold the task's output ...
+    size_t mbegin = 0, mend = 0;                // ... its accepted MUMs in pop order: wmp[worker].mums[mbegin, mend)
+    // foreign reads, positions [a, b]: appended by the task's own thread (entry first, then the count with release order), read
+    // by a lower task's thread that checks whether its foreign write came too late for this task
+    struct FRead { int g; int64_t a, b; };
+    static constexpr uint32_t LOG_CAP = 2048;
+    FRead* flog = nullptr;                      // (LOG_CAP entries of the context's slab)
+    std::atomic<uint32_t> nlog{0};
+    std::atomic<bool> log_overflow{false};      // more reads than the log holds: "has read everything"
     std::unique_ptr<Aligner::CandCache> local;  // regions searched on demand (not predicted by the speculation)
-    int64_t n_fread = 0, n_fwrite = 0, misses = 0, regions = 0;
+    int64_t n_fread = 0, n_fwrite = 0, misses = 0, regions = 0, slow_iters = 0;
     double t_wait = 0, t_search = 0;
+    struct SegCache { int g = -1, owner = -1, gap = -1; int64_t slo = 0, shi = -1; } sc;   // last ownership lookup (run_up and run_down of one candidate hit the same segment)
+    uint64_t pc[6] = {0, 0, 0, 0, 0, 0};          // PB200_PROFILE_HOST: cycles in setup / pop / lookup / accept / det_region / queue
     void reset() {
-        mp.mums.clear(); mp.start.clear(); mp.fwd.clear();
-        rp.coord.clear(); rp.slen.clear();
-        freads.clear(); local.reset();
-        n_fread = n_fwrite = misses = regions = 0;
+        worker = -1; mbegin = mend = 0;
+        nlog.store(0, std::memory_order_relaxed); log_overflow.store(false, std::memory_order_relaxed);
+        local.reset();
+        n_fread = n_fwrite = misses = regions = slow_iters = 0;
+        for (auto& x : pc) x = 0;
+        sc = SegCache();
     }
 };
 
@@ -91,62 +101,100 @@ struct ReplayCtx {
     int64_t restarts = 0;
     unsigned jitter = 0;
     std::vector<int> order;                     // indices into A.initial_regions_, ascending start[0]
+    std::vector<int64_t> keys;                  // their start[0], same order
+    // GAPS: maximal runs of initial regions whose spans overlap (the right side of anchor i and the left side of anchor i+1 are
+    // the same gap).  Gap j owns [glo[j * n + g], ghi[j * n + g]] in genome g; gaps ascend in every genome.  A gap is DONE when
+    // its task has popped a region that starts behind it: nothing of its subtree is left in the queue.
+    int ngaps = 0;
+    std::vector<int32_t> glo, ghi;
+    std::vector<int64_t> gend0;                 // largest end[0] of the gap's regions
+    std::unique_ptr<std::atomic<uint8_t>[]> gdone;
+    std::unique_ptr<ReplayTask::FRead[]> log_slab;
+    // per worker: an append-only arena for the MUMs of the tasks it ran (a restarted task leaves its first attempt behind as
+    // unreferenced garbage) and a region pool that is cleared for every task
+    std::vector<MumPool> wmp;
+    std::vector<RegionPool> wrp;
 
     ReplayCtx(Aligner& a) : A(a), n(a.n_), truth(a.truth_.layout) {}
 
-    // ---- ownership of position x in genome g: owner task (or -1) and the extent [slo, shi] of that ownership segment
-    inline void seg(int g, int64_t x, int& owner, int64_t& slo, int64_t& shi) const {
+    // ---- ownership of position x in genome g: the task whose span holds it (or -1), the gap inside that task (or -1: between
+    // gaps, i.e. anchor bits and stretches too short to be searched - never written by a task's own accepts) and the extent
+    // [slo, shi] of that ownership segment
+    inline void seg_lookup(int g, int64_t x, int& owner, int& gap, int64_t& slo, int64_t& shi) const {
         const int64_t* L = &hlo[(size_t)g * ntasks];
         const int64_t* H = &hhi[(size_t)g * ntasks];
         const int k = (int)(std::upper_bound(L, L + ntasks, x) - L) - 1;
-        if (k >= 0 && x <= H[k]) { owner = k; slo = L[k]; shi = H[k]; return; }
-        owner = -1;
-        slo = k >= 0 ? H[k] + 1 : 0;
-        shi = k + 1 < ntasks ? L[k + 1] - 1 : A.len_[g];
+        gap = -1;
+        if (!(k >= 0 && x <= H[k])) {
+            owner = -1;
+            slo = k >= 0 ? H[k] + 1 : 0;
+            shi = k + 1 < ntasks ? L[k + 1] - 1 : A.len_[g];
+            return;
+        }
+        owner = k;
+        // last gap j of the task with glo[j][g] <= x
+        int a = tasks[k].gfirst, b = tasks[k].glast;             // invariant: glo[a-1] <= x < glo[b]
+        const int g0 = a, g1 = b;
+        while (a < b) {
+            const int mid = (a + b) >> 1;
+            if ((int64_t)glo[(size_t)mid * n + g] <= x) a = mid + 1; else b = mid;
+        }
+        const int j = a - 1;
+        if (j >= g0 && x <= (int64_t)ghi[(size_t)j * n + g]) { gap = j; slo = glo[(size_t)j * n + g]; shi = ghi[(size_t)j * n + g]; return; }
+        slo = j >= g0 ? (int64_t)ghi[(size_t)j * n + g] + 1 : L[k];
+        shi = j + 1 < g1 ? (int64_t)glo[(size_t)(j + 1) * n + g] - 1 : H[k];
     }
-    void wait_done(ReplayTask& T, int m) {
+    inline void seg(ReplayTask& T, int g, int64_t x, int& owner, int& gap, int64_t& slo, int64_t& shi) const {
+        ReplayTask::SegCache& c = T.sc;
+        if (c.g != g || x < c.slo || x > c.shi) { c.g = g; seg_lookup(g, x, c.owner, c.gap, c.slo, c.shi); }
+        owner = c.owner; gap = c.gap; slo = c.slo; shi = c.shi;
+    }
+    void wait_gap(ReplayTask& T, int j) {
         const double t0 = now_s();
-        while (tasks[m].state.load(std::memory_order_acquire) != T_DONE) {
+        while (!gdone[j].load(std::memory_order_acquire)) {
             if (T.abort.load(std::memory_order_relaxed)) throw TaskAborted();
             cpu_relax();
             std::this_thread::yield();
         }
         T.t_wait += now_s() - t0;
     }
-    // the bitmap task k sees for a segment owned by `owner`; need = a lower task that has to finish first
-    inline const BitRow* source(int k, int g, int owner, int& need) const {
-        if (owner >= 0 && owner < k) {
-            if (tasks[owner].state.load(std::memory_order_acquire) != T_DONE) { need = owner; return nullptr; }
-            return &truth[g];
-        }
-        return owner == k ? &truth[g] : &S[g];
+    // the bitmap task k sees for a segment; need = a gap of a lower task that has to be finished first
+    inline const BitRow* source(int k, int g, int owner, int gap, int& need) const {
+        if (owner < 0 || gap < 0 || owner > k) return &S[g];      // untouched by the reference at this point (or never written)
+        if (owner == k) return &truth[g];
+        if (!gdone[gap].load(std::memory_order_acquire)) { need = gap; return nullptr; }
+        return &truth[g];
     }
-    // a foreign read: body(need) runs under the mutex; when it meets a segment of an unfinished lower task it sets need and
-    // returns; the read is retried after that task is done
+    // A foreign read takes no lock.  It is logged BEFORE the bits are read (entry, count, full fence, read); a foreign write sets
+    // its bits, issues a full fence and THEN looks at the logs: whichever way the two interleave, either the reader sees the
+    // new bits or the writer sees the log entry (and restarts the reader's task).  body(need) sets need when it meets an
+    // unfinished gap of a lower task: the read is retried after that gap is done.
     template <class Body>
     int64_t foreign_read(ReplayTask& T, int g, int64_t lo, int64_t hi, Body&& body) {
+        const uint32_t at = T.nlog.load(std::memory_order_relaxed);
+        if (at < ReplayTask::LOG_CAP) {
+            T.flog[at] = ReplayTask::FRead{g, lo, hi};
+            T.nlog.store(at + 1, std::memory_order_release);
+        } else {
+            T.log_overflow.store(true, std::memory_order_release);
+        }
+        ++T.n_fread;
         for (;;) {
+            if (T.abort.load(std::memory_order_relaxed)) throw TaskAborted();
+            std::atomic_thread_fence(std::memory_order_seq_cst);
             int need = -1;
-            {
-                std::lock_guard<std::mutex> lk(mu);
-                if (T.abort.load(std::memory_order_relaxed)) throw TaskAborted();
-                const int64_t r = body(need);
-                if (need < 0) {
-                    T.freads.push_back(ReplayTask::FRead{g, lo, hi});
-                    ++T.n_fread;
-                    return r;
-                }
-            }
-            wait_done(T, need);
+            const int64_t r = body(need);
+            if (need < 0) return r;
+            wait_gap(T, need);
         }
     }
     int64_t f_run_up(ReplayTask& T, int k, int g, int64_t a, int64_t b) {
         return foreign_read(T, g, a, b - 1, [&](int& need) -> int64_t {
             int64_t x = a, total = 0;
             while (x < b) {
-                int owner; int64_t slo, shi;
-                seg(g, x, owner, slo, shi);
-                const BitRow* src = source(k, g, owner, need);
+                int owner, gap; int64_t slo, shi;
+                seg(T, g, x, owner, gap, slo, shi);
+                const BitRow* src = source(k, g, owner, gap, need);
                 if (!src) return 0;
                 const int64_t e = std::min(b, shi + 1);
                 const int64_t r = src->run_up(x, e);
@@ -161,9 +209,9 @@ struct ReplayCtx {
         return foreign_read(T, g, a, b - 1, [&](int& need) -> int64_t {
             int64_t x = b, total = 0;
             while (x > a) {
-                int owner; int64_t slo, shi;
-                seg(g, x - 1, owner, slo, shi);
-                const BitRow* src = source(k, g, owner, need);
+                int owner, gap; int64_t slo, shi;
+                seg(T, g, x - 1, owner, gap, slo, shi);
+                const BitRow* src = source(k, g, owner, gap, need);
                 if (!src) return 0;
                 const int64_t s = std::max(a, slo);
                 const int64_t r = src->run_down(s, x);
@@ -176,9 +224,9 @@ struct ReplayCtx {
     }
     bool f_get(ReplayTask& T, int k, int g, int64_t i) {
         return foreign_read(T, g, i, i, [&](int& need) -> int64_t {
-            int owner; int64_t slo, shi;
-            seg(g, i, owner, slo, shi);
-            const BitRow* src = source(k, g, owner, need);
+            int owner, gap; int64_t slo, shi;
+            seg(T, g, i, owner, gap, slo, shi);
+            const BitRow* src = source(k, g, owner, gap, need);
             return src ? (int64_t)src->get(i) : 0;
         }) != 0;
     }
@@ -187,9 +235,9 @@ struct ReplayCtx {
         return foreign_read(T, g, 0, i, [&](int& need) -> int64_t {          // (logged extent: conservative)
             int64_t x = i;
             while (x >= 0) {
-                int owner; int64_t slo, shi;
-                seg(g, x, owner, slo, shi);
-                const BitRow* src = source(k, g, owner, need);
+                int owner, gap; int64_t slo, shi;
+                seg(T, g, x, owner, gap, slo, shi);
+                const BitRow* src = source(k, g, owner, gap, need);
                 if (!src) return -1;
                 const int64_t r = src->prev_set_from(x, slo);
                 if (r >= 0) return r;
@@ -203,9 +251,9 @@ struct ReplayCtx {
         return foreign_read(T, g, i, limit - 1, [&](int& need) -> int64_t {
             int64_t x = i;
             while (x < limit) {
-                int owner; int64_t slo, shi;
-                seg(g, x, owner, slo, shi);
-                const BitRow* src = source(k, g, owner, need);
+                int owner, gap; int64_t slo, shi;
+                seg(T, g, x, owner, gap, slo, shi);
+                const BitRow* src = source(k, g, owner, gap, need);
                 if (!src) return limit;
                 const int64_t e = std::min(limit, shi + 1);
                 const int64_t r = src->next_set(x, e);
@@ -217,8 +265,8 @@ struct ReplayCtx {
     }
     void foreign_commit(ReplayTask& T, int k, const int64_t* st, int64_t length, const int64_t* lo, const int64_t* hi);
     void restart_above(int k);
-    void run_task(int k, std::vector<int>& found, std::vector<int>& children);
-    void worker();
+    void run_task(int k, int w, std::vector<int>& found, std::vector<int>& children);
+    void worker(int w);
 };
 
 // a task's view of the layout
@@ -258,7 +306,12 @@ struct TaskAccess {
     inline void commit(const int64_t* st, int64_t length, int n) {
         bool foreign = false;
         for (int g = 0; g < n; ++g) foreign |= !home(g, st[g], st[g] + length);
-        if (!foreign) { for (int g = 0; g < n; ++g) X.truth[g].set_range_atomic(st[g], st[g] + length); return; }
+        if (!foreign) {
+            // words strictly inside the span have no other writer (a lower task's foreign write there restarts this task and
+            // restores the span): plain stores; the two boundary words may be shared with the neighbouring spans
+            for (int g = 0; g < n; ++g) X.truth[g].set_range_owned(st[g], st[g] + length, lo[g] >> 6, hi[g] >> 6);
+            return;
+        }
         X.foreign_commit(T, k, st, length, lo, hi);
     }
 };
@@ -282,13 +335,21 @@ void ReplayCtx::foreign_commit(ReplayTask& T, int k, const int64_t* st, int64_t 
             const int64_t a = st[g], b = st[g] + length;
             truth[g].set_range_atomic(a, b);
             if (a >= lo[g] && b <= hi[g] + 1) continue;
-            S[g].set_range(a, b);
+            S[g].set_range_atomic(a, b);
             ++T.n_fwrite;
+        }
+        std::atomic_thread_fence(std::memory_order_seq_cst);       // bits before logs (see foreign_read)
+        for (int g = 0; g < n && !conflict; ++g) {
+            const int64_t a = st[g], b = st[g] + length;
+            if (a >= lo[g] && b <= hi[g] + 1) continue;
             for (int m = k + 1; m <= max_started && !conflict; ++m) {
-                if (tasks[m].state.load(std::memory_order_relaxed) == T_IDLE) continue;
+                ReplayTask& M = tasks[m];
+                if (M.state.load(std::memory_order_relaxed) == T_IDLE) continue;
                 if (a <= hhi[(size_t)g * ntasks + m] && b - 1 >= hlo[(size_t)g * ntasks + m]) { conflict = true; break; }
-                for (const ReplayTask::FRead& fr : tasks[m].freads)
-                    if (fr.g == g && fr.a <= b - 1 && fr.b >= a) { conflict = true; break; }
+                if (M.log_overflow.load(std::memory_order_acquire)) { conflict = true; break; }
+                const uint32_t cnt = M.nlog.load(std::memory_order_acquire);
+                for (uint32_t i = 0; i < cnt; ++i)
+                    if (M.flog[i].g == g && M.flog[i].a <= b - 1 && M.flog[i].b >= a) { conflict = true; break; }
             }
         }
         if (conflict) {
@@ -310,6 +371,7 @@ void ReplayCtx::restart_above(int k) {
         if (st != T_IDLE) {
             for (int g = 0; g < n; ++g) truth[g].copy_range_from(S[g], hlo[(size_t)g * ntasks + m], hhi[(size_t)g * ntasks + m] + 1);
             if (st == T_DONE) --done_count;
+            for (int j = M.gfirst; j < M.glast; ++j) gdone[j].store(0, std::memory_order_relaxed);
             M.reset();
             M.state.store(T_IDLE, std::memory_order_release);
         }
@@ -328,10 +390,25 @@ struct QE { int64_t s0; int id; int slice; uint64_t hash; };
 
 // the loop of Aligner::process_queue_exact restricted to one task (its queue is a contiguous piece of the reference's queue:
 // every other region has a smaller key and is finished, or a larger key and is untouched)
-void ReplayCtx::run_task(int k, std::vector<int>& found, std::vector<int>& children) {
+#if defined(__x86_64__)
+#define PB_TICKS() __builtin_ia32_rdtsc()
+#else
+#define PB_TICKS() ((uint64_t)std::chrono::steady_clock::now().time_since_epoch().count())
+#endif
+#define PROF_MARK(i) do { if (prof) { const uint64_t x_ = PB_TICKS(); T.pc[i] += x_ - pt; pt = x_; } } while (0)
+
+void ReplayCtx::run_task(int k, int w, std::vector<int>& found, std::vector<int>& children) {
     ReplayTask& T = tasks[k];
+    MumPool& MP = wmp[(size_t)w];
+    RegionPool& RP = wrp[(size_t)w];
+    static const bool prof = getenv("PB200_PROFILE_HOST") != nullptr;
+    uint64_t pt = prof ? PB_TICKS() : 0;
     T.reset();
-    T.rp.n = n;
+    T.worker = w;
+    T.mbegin = T.mend = MP.mums.size();
+    RP.n = n;
+    RP.coord.clear();
+    RP.slen.clear();
     std::vector<int64_t> lo((size_t)n), hi((size_t)n);
     for (int g = 0; g < n; ++g) { lo[g] = hlo[(size_t)g * ntasks + k]; hi[g] = hhi[(size_t)g * ntasks + k]; }
     TaskAccess acc{*this, T, k, lo.data(), hi.data()};
@@ -341,9 +418,9 @@ void ReplayCtx::run_task(int k, std::vector<int>& found, std::vector<int>& child
     for (int p = T.last - 1; p >= T.first; --p) {
         const int i = order[(size_t)p];
         const int r = A.initial_regions_[(size_t)i];
-        const int id = T.rp.add(A.rp_.start(r), A.rp_.end(r));
-        fast.push_back(QE{T.rp.start(id)[0], id, (size_t)i < A.slice_of_initial_.size() ? A.slice_of_initial_[(size_t)i] : -1,
-                          Aligner::coords_hash(T.rp.start(id), 2 * n)});
+        const int id = RP.add(A.rp_.start(r), A.rp_.end(r));
+        fast.push_back(QE{RP.start(id)[0], id, (size_t)i < A.slice_of_initial_.size() ? A.slice_of_initial_[(size_t)i] : -1,
+                          Aligner::coords_hash(RP.start(id), 2 * n)});
     }
     if (k == 0) {
         // the reference takes regions.begin() BEFORE its first sort (src/parsnp.cpp:192-195): the very first region searched is
@@ -358,20 +435,31 @@ void ReplayCtx::run_task(int k, std::vector<int>& found, std::vector<int>& child
         if (pos > 0 && fast[pos - 1].s0 == key) return pos - 1;
         return pos;
     };
-    auto req = [&](int a, int b) { return std::memcmp(T.rp.start(a), T.rp.start(b), cbytes) == 0; };
+    auto req = [&](int a, int b) { return std::memcmp(RP.start(a), RP.start(b), cbytes) == 0; };
     std::vector<int64_t> lS((size_t)n), lE((size_t)n), rS((size_t)n), rE((size_t)n);
     int ready_upto = 0;
+    int gnext = T.gfirst;                       // first gap of the task that is not done yet
     unsigned rnd = 12345u + (unsigned)k * 2654435761u;
-    while (!fast.empty()) {
+    // slow mode = the reference's literal vector handling while two DIFFERENT regions share a start[0] (see below)
+    bool slow = false, first_pop = true;
+    std::vector<QE> lvec;                       // ascending; the front is the front of the reference's vector
+    PROF_MARK(0);
+    const size_t R = order.size();
+    while (slow ? !lvec.empty() : !fast.empty()) {
         if (T.abort.load(std::memory_order_relaxed)) throw TaskAborted();
         if (jitter) {                           // tests: shake the interleavings
             rnd = rnd * 1664525u + 1013904223u;
             if ((rnd >> 16) % jitter == 0) std::this_thread::sleep_for(std::chrono::microseconds((rnd >> 8) % 200));
             else if ((rnd >> 20) % 3 == 0) std::this_thread::yield();
         }
-        const QE cur = fast.back();
-        fast.pop_back();
+        QE cur;
+        if (slow) { cur = lvec.front(); lvec.erase(lvec.begin()); }
+        else { cur = fast.back(); fast.pop_back(); }
         ++T.regions;
+        // regions come in ascending start[0] order and a sub-region starts at most one base before its parent: every gap that
+        // ends before cur.s0 - 1 has nothing left in the queue and never will - its part of the layout is final
+        while (gnext < T.glast && gend0[(size_t)gnext] <= cur.s0 - 1) gdone[gnext++].store(1, std::memory_order_release);
+        PROF_MARK(1);
         const Aligner::CandCache* C = nullptr;
         if (cur.slice >= 0 && cur.slice < (int)A.slice_cache_.size()) {
             if (cur.slice >= ready_upto) {
@@ -382,59 +470,114 @@ void ReplayCtx::run_task(int k, std::vector<int>& found, std::vector<int>& child
             }
             C = A.slice_cache_[(size_t)cur.slice].get();
         }
-        int ci = C ? C->lookup(T.rp.start(cur.id), cur.hash) : -1;
-        if (ci < 0) { C = &A.main_cache_; ci = A.main_cache_.lookup(T.rp.start(cur.id), cur.hash); }
-        if (ci < 0 && T.local) { C = T.local.get(); ci = C->lookup(T.rp.start(cur.id), cur.hash); }
+        int ci = C ? C->lookup(RP.start(cur.id), cur.hash) : -1;
+        if (ci < 0) { C = &A.main_cache_; ci = A.main_cache_.lookup(RP.start(cur.id), cur.hash); }
+        if (ci < 0 && T.local) { C = T.local.get(); ci = C->lookup(RP.start(cur.id), cur.hash); }
         if (ci < 0) {                           // a region the speculation did not predict: search it now
             const double t0 = now_s();
             if (!T.local) T.local.reset(new Aligner::CandCache);
-            A.search_regions(*T.local, T.rp, std::vector<int>(1, cur.id), false);
+            A.search_regions(*T.local, RP, std::vector<int>(1, cur.id), false);
             T.t_search += now_s() - t0;
             ++T.misses;
             C = T.local.get();
-            ci = C->lookup(T.rp.start(cur.id), cur.hash);
+            ci = C->lookup(RP.start(cur.id), cur.hash);
         }
         found.clear();
-        A.accept_candidates_t(T.rp.start(cur.id), T.rp.end(cur.id), T.rp.slen[(size_t)cur.id], *C, ci, acc, T.mp, found, false);
+        PROF_MARK(2);
+        A.accept_candidates_t(RP.start(cur.id), RP.end(cur.id), RP.slen[(size_t)cur.id], *C, ci, acc, MP, found, false);
+        T.mend = MP.mums.size();
+        PROF_MARK(3);
         children.clear();
         int64_t lsl = 0;
         for (size_t i = 0; i < found.size(); ++i) {
-            const MumRec& m = T.mp.mums[(size_t)found[i]];
-            const int64_t* ms = &T.mp.start[(size_t)m.off];
+            const MumRec& m = MP.mums[(size_t)found[i]];
+            const int64_t* ms = &MP.start[(size_t)m.off];
             if (i == 0) lsl = A.det_region_t(acc, ms, m.length, true, lS.data(), lE.data());
             const int64_t rsl = A.det_region_t(acc, ms, m.length, false, rS.data(), rE.data());
-            if (lsl > A.prm_.q) children.push_back(T.rp.add(lS.data(), lE.data()));
-            if (rsl > A.prm_.q) children.push_back(T.rp.add(rS.data(), rE.data()));
+            if (lsl > A.prm_.q) children.push_back(RP.add(lS.data(), lE.data()));
+            if (rsl > A.prm_.q) children.push_back(RP.add(rS.data(), rE.data()));
             if (i + 1 < found.size()) {
-                const MumRec& m2 = T.mp.mums[(size_t)found[i + 1]];
-                lsl = A.det_region_t(acc, &T.mp.start[(size_t)m2.off], m2.length, true, lS.data(), lE.data());
+                const MumRec& m2 = MP.mums[(size_t)found[i + 1]];
+                lsl = A.det_region_t(acc, &MP.start[(size_t)m2.off], m2.length, true, lS.data(), lE.data());
             }
         }
-        // sort + drop adjacent duplicates (src/parsnp.cpp:291-306): with distinct keys an ordered insert; a tie between
-        // DIFFERENT regions makes the order a property of std::sort over the whole queue -> sequential loop from this task on
-        for (size_t a = 0; a < children.size(); ++a) {
-            const int64_t key = T.rp.start(children[a])[0];
-            const size_t pos = fast_pos(key);
-            if (pos < fast.size() && fast[pos].s0 == key && !req(fast[pos].id, children[a])) {
-                if (getenv("PB200_REPLAY_DEBUG")) fprintf(stderr, "[pb200 replay] task %d: child ties with a queued region at start[0] = %lld\n", k, (long long)key);
-                throw NeedFallback();
+        PROF_MARK(4);
+        // sort + drop adjacent duplicates (src/parsnp.cpp:291-306).  With distinct keys: an ordered insert.
+        if (!slow) {
+            bool distinct_tie = false;
+            for (size_t a = 0; a < children.size() && !distinct_tie; ++a) {
+                const int64_t key = RP.start(children[a])[0];
+                const size_t pos = fast_pos(key);
+                if (pos < fast.size() && fast[pos].s0 == key && !req(fast[pos].id, children[a])) distinct_tie = true;
+                for (size_t b = 0; b < a && !distinct_tie; ++b)
+                    if (key == RP.start(children[b])[0] && !req(children[a], children[b])) distinct_tie = true;
             }
-            for (size_t b = 0; b < a; ++b)
-                if (key == T.rp.start(children[b])[0] && !req(children[a], children[b])) {
-                    if (getenv("PB200_REPLAY_DEBUG")) fprintf(stderr, "[pb200 replay] task %d: two children tie at start[0] = %lld\n", k, (long long)key);
-                    throw NeedFallback();
+            if (!distinct_tie) {
+                for (int ch : children) {                       // identical duplicates collapse (the first one stays)
+                    const int64_t key = RP.start(ch)[0];
+                    const size_t pos = fast_pos(key);
+                    if (pos < fast.size() && fast[pos].s0 == key) continue;
+                    fast.insert(fast.begin() + (long)pos, QE{key, ch, cur.slice, Aligner::coords_hash(RP.start(ch), 2 * n)});
                 }
+                first_pop = false;
+                PROF_MARK(5);
+                continue;
+            }
+            // A tie between DIFFERENT regions: the order is what the reference's unstable std::sort over its WHOLE vector makes
+            // of it.  That vector is known here: this task's pending regions (ascending), then every initial region behind the
+            // task (untouched so far, ascending, all keys above the task's), then the new children - so the call is replayed
+            // literally on (key, tag) records: same algorithm, same comparisons, same permutation.  Only before the very first
+            // sort (the reference's vector is still in push order) the run goes back to the sequential loop.
+            if (getenv("PB200_REPLAY_DEBUG")) fprintf(stderr, "[pb200 replay] task %d: tie between different regions, literal queue until it is gone\n", k);
+            if (k == 0 && first_pop) throw NeedFallback();
+            lvec.assign(fast.rbegin(), fast.rend());
+            fast.clear();
+            slow = true;
         }
-        for (int ch : children) {                               // identical duplicates collapse (the first one stays)
-            const int64_t key = T.rp.start(ch)[0];
-            const size_t pos = fast_pos(key);
-            if (pos < fast.size() && fast[pos].s0 == key) continue;
-            fast.insert(fast.begin() + (long)pos, QE{key, ch, cur.slice, Aligner::coords_hash(T.rp.start(ch), 2 * n)});
+        first_pop = false;
+        ++T.slow_iters;
+        const double tslow0 = prof ? now_s() : 0;
+        const size_t before = lvec.size();
+        for (int ch : children) lvec.push_back(QE{RP.start(ch)[0], ch, cur.slice, Aligner::coords_hash(RP.start(ch), 2 * n)});
+        if (!lvec.empty()) {
+            std::vector<int64_t> keys(lvec.size());
+            for (size_t i = 0; i < lvec.size(); ++i) keys[i] = lvec[i].s0;
+            std::sort(keys.begin(), keys.end());
+            bool tie = false;
+            for (size_t i = 1; i < keys.size() && !tie; ++i) tie = keys[i] == keys[i - 1];
+            if (!tie) {
+                // (bounded insertion sort or std::sort in the reference's loop: with distinct keys both give THE ascending order)
+                std::stable_sort(lvec.begin(), lvec.end(), [](const QE& a, const QE& b) { return a.s0 < b.s0; });
+            } else {
+                std::vector<std::pair<int64_t, int>> gv;
+                gv.reserve(lvec.size() + (R - (size_t)T.last));
+                for (size_t i = 0; i < before; ++i) gv.emplace_back(lvec[i].s0, (int)i);
+                for (size_t p = (size_t)T.last; p < R; ++p) gv.emplace_back(keys[p], -1);
+                for (size_t i = before; i < lvec.size(); ++i) gv.emplace_back(lvec[i].s0, (int)i);
+                std::sort(gv.begin(), gv.end(), [](const std::pair<int64_t, int>& a, const std::pair<int64_t, int>& b) { return a.first < b.first; });
+                std::vector<QE> nl;
+                nl.reserve(lvec.size());
+                for (const auto& e : gv) if (e.second >= 0) nl.push_back(lvec[(size_t)e.second]);
+                lvec.swap(nl);
+            }
         }
+        for (size_t m = 0; m + 1 < lvec.size();) {
+            if (req(lvec[m].id, lvec[m + 1].id)) lvec.erase(lvec.begin() + (long)m);
+            else ++m;
+        }
+        bool strict = true;
+        for (size_t m = 0; m + 1 < lvec.size() && strict; ++m) strict = lvec[m].s0 < lvec[m + 1].s0;
+        if (strict) {
+            fast.assign(lvec.rbegin(), lvec.rend());
+            lvec.clear();
+            slow = false;
+        }
+        if (prof) fprintf(stderr, "[pb200 replay] task %d: literal queue iteration %.2f ms\n", k, (now_s() - tslow0) * 1e3);
     }
+    while (gnext < T.glast) gdone[gnext++].store(1, std::memory_order_release);
 }
 
-void ReplayCtx::worker() {
+void ReplayCtx::worker(int w) {
     std::vector<int> found, children;
     for (;;) {
         int k = -1;
@@ -455,7 +598,7 @@ void ReplayCtx::worker() {
         }
         int outcome = T_DONE;
         std::exception_ptr err;
-        try { run_task(k, found, children); }
+        try { run_task(k, w, found, children); }
         catch (const TaskAborted&) { outcome = T_DIRTY; }
         catch (const NeedFallback&) { outcome = -1; }
         catch (...) { err = std::current_exception(); outcome = T_DIRTY; }
@@ -492,7 +635,8 @@ void Aligner::wait_slice_quiet(int slice) {
 }
 
 bool Aligner::do_work_parallel() {
-    const int W = replay_threads_ > 0 ? replay_threads_ : threads_;
+    int W = replay_threads_ > 0 ? replay_threads_ : threads_;
+    if (const char* ew = getenv("PB200_REPLAY_THREADS")) W = std::max(1, atoi(ew));
     const size_t R = initial_regions_.size();
     const char* et = getenv("PB200_REPLAY_TASK");               // initial regions per task (tests: 1 = one gap per task)
     const char* em = getenv("PB200_REPLAY_MODE");               // "seq" = never, "par" = also for tiny inputs / one worker
@@ -502,22 +646,48 @@ bool Aligner::do_work_parallel() {
     if (dbg) fprintf(stderr, "[pb200 replay] W %d R %zu trace %d pipeline %d\n", W, R, (int)trace_on_, (int)pipeline_);
     if (trace_on_ || !pipeline_ || R == 0) return false;
     if (!force && (W < 2 || R < 512)) return false;
+    const double tsetup0 = now_s();
     ReplayCtx X(*this);
     if (const char* ej = getenv("PB200_REPLAY_JITTER")) X.jitter = (unsigned)std::max(0, atoi(ej));
     // P1: the keys of the initial regions are distinct, so the reference's first sort has one possible outcome.  (Push order is
     // NOT ascending: the right side of anchor i starts one base behind the left side of anchor i+1 - the same gap twice.)
+    std::vector<int64_t> pushkey(R);
+    {
+        const long per_blk = 4096;
+        parallel_chunks(R > 16384 ? threads_ : 1, ((long)R + per_blk - 1) / per_blk, [&](long c) {
+            for (size_t i = (size_t)c * per_blk; i < std::min(R, (size_t)(c + 1) * per_blk); ++i) pushkey[i] = rstart(initial_regions_[i])[0];
+        });
+    }
     X.order.resize(R);
     for (size_t i = 0; i < R; ++i) X.order[i] = (int)i;
-    std::stable_sort(X.order.begin(), X.order.end(), [&](int a, int b) { return rstart(initial_regions_[(size_t)a])[0] < rstart(initial_regions_[(size_t)b])[0]; });
+    {   // (push order is ascending up to neighbour swaps: one insertion pass; anything else falls back to a real sort)
+        size_t moves = 0;
+        for (size_t i = 1; i < R && moves <= 4 * R; ++i) {
+            const int x = X.order[i];
+            const int64_t kx = pushkey[(size_t)x];
+            size_t j = i;
+            while (j > 0 && pushkey[(size_t)X.order[j - 1]] > kx) { X.order[j] = X.order[j - 1]; --j; ++moves; }
+            X.order[j] = x;
+        }
+        if (moves > 4 * R) {
+            for (size_t i = 0; i < R; ++i) X.order[i] = (int)i;
+            std::stable_sort(X.order.begin(), X.order.end(), [&](int a, int b) { return pushkey[(size_t)a] < pushkey[(size_t)b]; });
+        }
+    }
+    X.keys.resize(R);                            // start[0] of the initial regions in ascending order
+    for (size_t i = 0; i < R; ++i) X.keys[i] = pushkey[(size_t)X.order[i]];
     for (size_t i = 1; i < R; ++i)
-        if (!(rstart(initial_regions_[(size_t)X.order[i - 1]])[0] < rstart(initial_regions_[(size_t)X.order[i]])[0])) {
+        if (!(X.keys[i - 1] < X.keys[i])) {
             if (dbg) fprintf(stderr, "[pb200 replay] two initial regions tie on start[0]: sequential\n");
             return false;
         }
     size_t pos0 = 0;
     while (pos0 < R && X.order[pos0] != 0) ++pos0;
-    // spans of the initial regions: between the anchor bits that bound them, per genome (the layout holds exactly the anchors)
+    // spans of the initial regions: between the anchor bits that bound them, per genome (the layout holds exactly the anchors);
+    // cut[p] = region p starts behind everything before it in every genome.  Collinear anchors make the span ends ascend with p,
+    // so "everything before" is the previous region; anything else declines.
     std::vector<int64_t> rlo(R * (size_t)n_), rhi(R * (size_t)n_);
+    std::vector<uint8_t> cut(R, 0);
     std::atomic<int> bad(0);
     {
         const long per_blk = 512;
@@ -535,27 +705,75 @@ bool Aligner::do_work_parallel() {
                 }
             }
         });
-    }
-    if (bad.load()) return false;
-    // tasks: runs of >= `per` regions of the sorted list, cut only where the next region starts behind everything before it in
-    // every genome (the two regions of one gap, and whatever else overlaps, stay together)
-    const size_t per = et ? (size_t)std::max(1, atoi(et)) : std::min<size_t>(128, std::max<size_t>(8, R / ((size_t)W * 24) + 1));
-    std::vector<int> cuts(1, 0);
-    {
-        std::vector<int64_t> runmax((size_t)n_, -1);
-        size_t count = 0;
-        for (size_t p = 0; p < R; ++p) {
-            if (count >= per && p > pos0) {
+        if (bad.load()) return false;
+        parallel_chunks(threads_, ((long)R + per_blk - 1) / per_blk, [&](long c) {
+            for (size_t p = std::max<size_t>(1, (size_t)c * per_blk); p < std::min(R, (size_t)(c + 1) * per_blk); ++p) {
                 bool ok = true;
-                for (int g = 0; g < n_ && ok; ++g) ok = runmax[(size_t)g] <= rlo[p * (size_t)n_ + g];
-                if (ok) { cuts.push_back((int)p); count = 0; }
+                for (int g = 0; g < n_; ++g) {
+                    if (rhi[(p - 1) * (size_t)n_ + g] > rhi[p * (size_t)n_ + g]) bad.store(1);          // not ascending
+                    ok &= rhi[(p - 1) * (size_t)n_ + g] <= rlo[p * (size_t)n_ + g];
+                }
+                cut[p] = ok ? 1 : 0;
             }
-            for (int g = 0; g < n_; ++g) runmax[(size_t)g] = std::max(runmax[(size_t)g], rhi[p * (size_t)n_ + g]);
-            ++count;
+        });
+        if (bad.load()) {
+            if (dbg) fprintf(stderr, "[pb200 replay] the spans of the initial regions do not ascend in every genome: sequential\n");
+            return false;
         }
-        cuts.push_back((int)R);
     }
-    X.ntasks = (int)cuts.size() - 1;
+    // gaps: runs of regions between cuts (the two regions of one anchor gap, and whatever else overlaps, stay together);
+    // tasks: runs of gaps with >= `per` regions
+    const size_t per = et ? (size_t)std::max(1, atoi(et)) : std::min<size_t>(128, std::max<size_t>(8, R / ((size_t)W * 24) + 1));
+    std::vector<int> gcut(1, 0);                 // gap j = positions [gcut[j], gcut[j+1])
+    for (size_t p = 1; p < R; ++p) if (cut[p]) gcut.push_back((int)p);
+    gcut.push_back((int)R);
+    X.ngaps = (int)gcut.size() - 1;
+    X.glo.resize((size_t)X.ngaps * n_);
+    X.ghi.resize((size_t)X.ngaps * n_);
+    X.gend0.resize((size_t)X.ngaps);
+    X.gdone.reset(new std::atomic<uint8_t>[(size_t)X.ngaps]);
+    parallel_chunks(X.ngaps > 4096 ? threads_ : 1, ((long)X.ngaps + 1023) / 1024, [&](long c) {
+        for (int j = (int)c * 1024; j < std::min(X.ngaps, (int)(c + 1) * 1024); ++j) {
+            X.gdone[j].store(0, std::memory_order_relaxed);
+            int64_t e0 = 0;
+            for (int g = 0; g < n_; ++g) {
+                int64_t lo = INT64_MAX, hi = -1;
+                for (int p = gcut[(size_t)j]; p < gcut[(size_t)j + 1]; ++p) {
+                    lo = std::min(lo, rlo[(size_t)p * n_ + g]);
+                    hi = std::max(hi, rhi[(size_t)p * n_ + g]);
+                }
+                X.glo[(size_t)j * n_ + g] = (int32_t)lo;
+                X.ghi[(size_t)j * n_ + g] = (int32_t)hi;
+            }
+            for (int p = gcut[(size_t)j]; p < gcut[(size_t)j + 1]; ++p) e0 = std::max(e0, rend(initial_regions_[(size_t)X.order[(size_t)p]])[0]);
+            X.gend0[(size_t)j] = e0;
+        }
+    });
+    // P2: collinear anchors - the gaps ascend in every genome (neighbours may share a boundary anchor bit)
+    parallel_chunks(X.ngaps > 4096 ? threads_ : 1, ((long)X.ngaps + 1023) / 1024, [&](long c) {
+        for (int j = (int)c * 1024; j < std::min(X.ngaps - 1, (int)(c + 1) * 1024); ++j)
+            for (int g = 0; g < n_; ++g)
+                if (X.ghi[(size_t)j * n_ + g] > X.glo[(size_t)(j + 1) * n_ + g] || X.glo[(size_t)j * n_ + g] > X.ghi[(size_t)j * n_ + g]) bad.store(1);
+    });
+    if (bad.load()) {
+        if (dbg) fprintf(stderr, "[pb200 replay] gaps not in order in some genome: sequential\n");
+        return false;
+    }
+    // the reference's first pop is the first region PUSHED (see run_task): it must belong to the first gap
+    if ((int)pos0 >= gcut[1]) {
+        if (dbg) fprintf(stderr, "[pb200 replay] the first region pushed is not in the first gap: sequential\n");
+        return false;
+    }
+    std::vector<int> tcut(1, 0);                 // task k = gaps [tcut[k], tcut[k+1])
+    {
+        size_t count = 0;
+        for (int j = 0; j < X.ngaps; ++j) {
+            if (count >= per && j > 0) { tcut.push_back(j); count = 0; }
+            count += (size_t)(gcut[(size_t)j + 1] - gcut[(size_t)j]);
+        }
+        tcut.push_back(X.ngaps);
+    }
+    X.ntasks = (int)tcut.size() - 1;
     if (!force && X.ntasks < 2 * W) {
         if (dbg) fprintf(stderr, "[pb200 replay] only %d independent tasks for %d workers: sequential\n", X.ntasks, W);
         return false;
@@ -565,42 +783,48 @@ bool Aligner::do_work_parallel() {
     X.hhi.assign((size_t)n_ * X.ntasks, 0);
     for (int k = 0; k < X.ntasks; ++k) {
         ReplayTask& T = X.tasks[k];
-        T.first = cuts[(size_t)k];
-        T.last = cuts[(size_t)k + 1];
+        T.gfirst = tcut[(size_t)k];
+        T.glast = tcut[(size_t)k + 1];
+        T.first = gcut[(size_t)T.gfirst];
+        T.last = gcut[(size_t)T.glast];
         for (int g = 0; g < n_; ++g) {
-            int64_t lo = INT64_MAX, hi = -1;
-            for (int p = T.first; p < T.last; ++p) {
-                lo = std::min(lo, rlo[(size_t)p * n_ + g]);
-                hi = std::max(hi, rhi[(size_t)p * n_ + g]);
-            }
-            X.hlo[(size_t)g * X.ntasks + k] = lo;
-            X.hhi[(size_t)g * X.ntasks + k] = hi;
+            X.hlo[(size_t)g * X.ntasks + k] = X.glo[(size_t)T.gfirst * n_ + g];
+            X.hhi[(size_t)g * X.ntasks + k] = X.ghi[(size_t)(T.glast - 1) * n_ + g];
         }
     }
-    // P2: collinear anchors - the spans ascend with the task in every genome (neighbours may share their boundary anchor bit)
-    for (int g = 0; g < n_; ++g)
-        for (int k = 0; k + 1 < X.ntasks; ++k)
-            if (X.hhi[(size_t)g * X.ntasks + k] > X.hlo[(size_t)g * X.ntasks + k + 1] ||
-                X.hlo[(size_t)g * X.ntasks + k] > X.hhi[(size_t)g * X.ntasks + k]) {
-                if (dbg) fprintf(stderr, "[pb200 replay] spans of tasks %d and %d not in order in genome %d: sequential\n", k, k + 1, g);
-                return false;
-            }
     X.S.resize((size_t)n_);
     parallel_chunks(threads_, (long)n_, [&](long g) { X.S[(size_t)g] = truth_.layout[(size_t)g]; });
     const size_t anchors_in_pool = mp_.mums.size();
 
     const int nw = std::max(1, std::min(W, X.ntasks));
-    std::vector<std::thread> th;
-    for (int w = 1; w < nw; ++w) th.emplace_back([&X] { X.worker(); });
-    X.worker();
-    for (auto& t : th) t.join();
+    X.wmp.resize((size_t)nw);
+    X.wrp.resize((size_t)nw);
+    {
+        const size_t est = (size_t)stats_.anchors * 4 / (size_t)nw + 1024;       // (about 3 recursion MUMs per anchor on divergent genomes)
+        for (auto& m : X.wmp) { m.mums.reserve(est); m.start.reserve(est * (size_t)n_); m.fwd.reserve(est * (size_t)n_); }
+    }
+    X.log_slab.reset(new ReplayTask::FRead[(size_t)X.ntasks * ReplayTask::LOG_CAP]);
+    for (int k = 0; k < X.ntasks; ++k) X.tasks[k].flog = X.log_slab.get() + (size_t)k * ReplayTask::LOG_CAP;
+    const double tr0 = now_s();
+    // (the process-wide pool of sleeping threads: no thread is created per alignment.  If the pool is busy - the host's own
+    //  level-by-level speculation uses it when the engine does not follow the recursion itself - the workers run one after the
+    //  other on this thread: the first takes every task)
+    if (getenv("PB200_REPLAY_OWN_THREADS")) {                   // tests: real concurrency whatever the pool is doing
+        std::vector<std::thread> th;
+        for (int w = 1; w < nw; ++w) th.emplace_back([&X, w] { X.worker(w); });
+        X.worker(0);
+        for (auto& t : th) t.join();
+    } else {
+        parallel_chunks(nw, (long)nw, [&X](long w) { X.worker((int)w); });
+    }
     if (X.error) std::rethrow_exception(X.error);
+    if (getenv("PB200_PROFILE_HOST")) fprintf(stderr, "[pb200 replay ms] setup %.2f tasks %.2f (%d workers, %d tasks, %d gaps)\n", (tr0 - tsetup0) * 1e3, (now_s() - tr0) * 1e3, nw, X.ntasks, X.ngaps);
 
     // ---- the finished tasks' MUMs into the pools, task after task = the reference's push order
     const double tm0 = now_s();
     const int F = std::min(X.ntasks, X.fallback_from);
     std::vector<size_t> base((size_t)F + 1, 0);
-    for (int k = 0; k < F; ++k) base[(size_t)k + 1] = base[(size_t)k] + X.tasks[k].mp.mums.size();
+    for (int k = 0; k < F; ++k) base[(size_t)k + 1] = base[(size_t)k] + (X.tasks[k].mend - X.tasks[k].mbegin);
     const size_t M = base[(size_t)F], m0 = mp_.mums.size(), s0 = mp_.start.size(), a0 = all_mums_.size();
     mp_.mums.resize(m0 + M);
     mp_.start.resize(s0 + M * (size_t)n_);
@@ -608,25 +832,62 @@ bool Aligner::do_work_parallel() {
     all_mums_.resize(a0 + M);
     parallel_chunks(threads_, (long)F, [&](long k) {
         const ReplayTask& T = X.tasks[k];
-        const size_t b = base[(size_t)k], cnt = T.mp.mums.size();
+        const size_t b = base[(size_t)k], cnt = T.mend - T.mbegin;
         if (!cnt) return;
-        std::memcpy(&mp_.start[s0 + b * (size_t)n_], T.mp.start.data(), cnt * (size_t)n_ * sizeof(int64_t));
-        std::memcpy(&mp_.fwd[s0 + b * (size_t)n_], T.mp.fwd.data(), cnt * (size_t)n_);
+        const MumPool& MP = X.wmp[(size_t)T.worker];
+        const size_t src = (size_t)MP.mums[T.mbegin].off;             // (a task's rows are contiguous in its worker's arena)
+        std::memcpy(&mp_.start[s0 + b * (size_t)n_], &MP.start[src], cnt * (size_t)n_ * sizeof(int64_t));
+        std::memcpy(&mp_.fwd[s0 + b * (size_t)n_], &MP.fwd[src], cnt * (size_t)n_);
         for (size_t i = 0; i < cnt; ++i) {
-            MumRec m = T.mp.mums[i];
+            MumRec m = MP.mums[T.mbegin + i];
             m.off = (int64_t)(s0 + (b + i) * (size_t)n_);
             mp_.mums[m0 + b + i] = m;
             all_mums_[a0 + b + i] = (int)(m0 + b + i);
         }
     });
+    // ---- the ascending start[0] order of everything found so far, for the LCB stage (Aligner::sort_final_mums): every task's
+    // MUMs sorted on their own (tasks ascend on the reference), merged with the anchors (accepted in ascending order)
+    sorted_hint_.clear();
+    if (F == X.ntasks && a0 == m0) {             // (no sequential tail; all_mums_ ids == pool ids)
+        std::vector<int> rec(M);
+        parallel_chunks(threads_, (long)F, [&](long k) {
+            const size_t b = base[(size_t)k], cnt = base[(size_t)k + 1] - b;
+            for (size_t i = 0; i < cnt; ++i) rec[b + i] = (int)(m0 + b + i);
+            std::stable_sort(rec.begin() + (long)b, rec.begin() + (long)(b + cnt), [&](int x, int y) { return mp_.start[(size_t)mp_.mums[(size_t)x].off] < mp_.start[(size_t)mp_.mums[(size_t)y].off]; });
+        });
+        auto key = [&](int id) { return mp_.start[(size_t)mp_.mums[(size_t)id].off]; };
+        sorted_hint_.resize(a0 + M);
+        const long P = std::max<long>(1, std::min<long>(threads_ * 4, (long)(a0 / 1024) + 1));
+        std::vector<size_t> as((size_t)P + 1), rs_((size_t)P + 1);
+        for (long c = 0; c <= P; ++c) {
+            as[(size_t)c] = a0 * (size_t)c / (size_t)P;
+            if (c == 0) rs_[0] = 0;
+            else if (c == P) rs_[(size_t)P] = M;
+            else {
+                const int64_t kx = key(all_mums_[as[(size_t)c]]);       // recursion MUMs below this anchor go to the parts before
+                rs_[(size_t)c] = (size_t)(std::lower_bound(rec.begin(), rec.end(), kx, [&](int id, int64_t v) { return key(id) < v; }) - rec.begin());
+            }
+        }
+        parallel_chunks(threads_, P, [&](long c) {
+            std::merge(all_mums_.begin() + (long)as[(size_t)c], all_mums_.begin() + (long)as[(size_t)c + 1], rec.begin() + (long)rs_[(size_t)c],
+                       rec.begin() + (long)rs_[(size_t)c + 1], sorted_hint_.begin() + (long)(as[(size_t)c] + rs_[(size_t)c]),
+                       [&](int x, int y) { return key(x) < key(y); });
+        });
+    }
+    uint64_t pcs[6] = {0, 0, 0, 0, 0, 0};
     for (int k = 0; k < F; ++k) {
         const ReplayTask& T = X.tasks[k];
         stats_.replay_foreign_reads += T.n_fread;
         stats_.replay_foreign_writes += T.n_fwrite;
         stats_.replay_misses += T.misses;
+        stats_.slow_queue_iters += T.slow_iters;
+        for (int i = 0; i < 6; ++i) pcs[i] += T.pc[i];
         stats_.t_replay_wait += T.t_wait / nw;
         stats_.t_replay_search += T.t_search;
     }
+    if (getenv("PB200_PROFILE_HOST"))
+        fprintf(stderr, "[pb200 replay tasks cycles] setup %llu pop %llu lookup %llu accept %llu det_region %llu queue %llu\n", (unsigned long long)pcs[0],
+                (unsigned long long)pcs[1], (unsigned long long)pcs[2], (unsigned long long)pcs[3], (unsigned long long)pcs[4], (unsigned long long)pcs[5]);
     stats_.replay_tasks = F;
     stats_.replay_restarts = X.restarts;
     stats_.replay_workers = nw;

@@ -41,9 +41,10 @@ def one_case(seed, verbose=False):
     ref = hosttest.align(g, prm(), backend=2)
     want = result_to_dump(ref)
     bad = 0
-    tot = dict(replay_tasks=0, replay_foreign_reads=0, replay_foreign_writes=0, replay_restarts=0, replay_fallback=0)
+    tot = dict(replay_tasks=0, replay_foreign_reads=0, replay_foreign_writes=0, replay_restarts=0, replay_fallback=0, slow_queue_iters=0)
     for rep in range(4):
         os.environ["PB200_REPLAY_MODE"] = "par"
+        os.environ["PB200_REPLAY_OWN_THREADS"] = "1"
         os.environ["PB200_HOST_THREADS"] = str(int(rng.choice([2, 3, 8])))
         os.environ["PB200_REPLAY_TASK"] = str(int(rng.choice([1, 1, 2, 5, 40])))
         os.environ["PB200_REPLAY_JITTER"] = str(int(rng.choice([0, 3, 20])))
