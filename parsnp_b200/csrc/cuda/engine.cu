@@ -767,6 +767,7 @@ int pb200_genomes_create(int device, int n, const uint8_t* const* seqs, const in
         if (n < 1 || !seqs || !lens || !out) { pb200::g_last_error = "bad arguments"; return (int)PB200_ERR_ARG; }
         const bool prof = getenv("PB200_PROFILE_HOST") != nullptr;
         tune_host_allocator();
+        pb200::install_backtrace_handler();
         const double t0 = pb200::wall_s();
         std::unique_ptr<pb200_genomes> g(new pb200_genomes);
         g->eng.reset(new pb200::CudaEngine(device));

@@ -540,11 +540,11 @@ void ReplayCtx::run_task(int k, int w, std::vector<int>& found, std::vector<int>
         const size_t before = lvec.size();
         for (int ch : children) lvec.push_back(QE{RP.start(ch)[0], ch, cur.slice, Aligner::coords_hash(RP.start(ch), 2 * n)});
         if (!lvec.empty()) {
-            std::vector<int64_t> keys(lvec.size());
-            for (size_t i = 0; i < lvec.size(); ++i) keys[i] = lvec[i].s0;
-            std::sort(keys.begin(), keys.end());
+            std::vector<int64_t> lkeys(lvec.size());
+            for (size_t i = 0; i < lvec.size(); ++i) lkeys[i] = lvec[i].s0;
+            std::sort(lkeys.begin(), lkeys.end());
             bool tie = false;
-            for (size_t i = 1; i < keys.size() && !tie; ++i) tie = keys[i] == keys[i - 1];
+            for (size_t i = 1; i < lkeys.size() && !tie; ++i) tie = lkeys[i] == lkeys[i - 1];
             if (!tie) {
                 // (bounded insertion sort or std::sort in the reference's loop: with distinct keys both give THE ascending order)
                 std::stable_sort(lvec.begin(), lvec.end(), [](const QE& a, const QE& b) { return a.s0 < b.s0; });

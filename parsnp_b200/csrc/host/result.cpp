@@ -4,6 +4,11 @@
 #include <cstring>
 #include <cstdlib>
 #include <thread>
+#include <csignal>
+#include <cstdio>
+#include <execinfo.h>
+#include <dlfcn.h>
+#include <unistd.h>
 
 namespace pb200 {
 thread_local std::string g_last_error;
@@ -43,6 +48,36 @@ pb200_result* make_result(const Aligner& a, bool unaligned) {
                  (double)s.replay_tasks, (double)s.replay_foreign_reads, (double)s.replay_foreign_writes, (double)s.replay_restarts,
                  (double)s.replay_fallback, (double)s.replay_workers, s.t_replay_merge, (double)s.spec_deferred };
     return r;
+}
+
+// PB200_BACKTRACE=1: a fatal signal inside the library prints its frames as offsets into the shared object (addr2line -e
+// libparsnp_b200.so <offset>) before the default action - a debugging aid for boxes without a debugger
+namespace {
+void fatal_signal_handler(int sig) {
+    void* frames[64];
+    const int nf = backtrace(frames, 64);
+    Dl_info me;
+    const char* base = dladdr((void*)&fatal_signal_handler, &me) ? (const char*)me.dli_fbase : nullptr;
+    char buf[256];
+    int len = snprintf(buf, sizeof buf, "[pb200] fatal signal %d, library %s loaded at %p; frames:\n", sig, me.dli_fname ? me.dli_fname : "?", (const void*)base);
+    if (write(2, buf, (size_t)len) < 0) {}
+    for (int i = 0; i < nf; ++i) {
+        Dl_info di;
+        const bool in = dladdr(frames[i], &di) && di.dli_fbase;
+        len = snprintf(buf, sizeof buf, "  #%d %s +0x%lx\n", i, in && di.dli_fname ? di.dli_fname : "?", in ? (unsigned long)((const char*)frames[i] - (const char*)di.dli_fbase) : (unsigned long)(uintptr_t)frames[i]);
+        if (write(2, buf, (size_t)len) < 0) {}
+    }
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+}  // namespace
+void install_backtrace_handler() {
+    static bool done = false;
+    if (done || !getenv("PB200_BACKTRACE")) return;
+    done = true;
+    signal(SIGSEGV, fatal_signal_handler);
+    signal(SIGABRT, fatal_signal_handler);
+    signal(SIGBUS, fatal_signal_handler);
 }
 
 int default_host_threads() {

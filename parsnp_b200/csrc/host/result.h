@@ -23,5 +23,6 @@ namespace pb200 {
 extern thread_local std::string g_last_error;
 pb200_result* make_result(const Aligner& a, bool unaligned = false);
 AlignParams to_align_params(const pb200_params* p);
-int default_host_threads();      // PB200_HOST_THREADS, else min(32, cores / local ranks)
+int default_host_threads();
+void install_backtrace_handler();   // PB200_BACKTRACE=1      // PB200_HOST_THREADS, else min(32, cores / local ranks)
 }
