@@ -44,7 +44,15 @@ struct CandBatch {
     pod_vector<int32_t> lon;         // LON
     pod_vector<int32_t> sp;          // [ncand * nq] start inside the query region, in the winning strand's coordinates
     pod_vector<uint8_t> fwd;         // [ncand * nq] 1 = forward strand won
-    void clear() { off.clear(); cnt.clear(); k.clear(); lon.clear(); sp.clear(); fwd.clear(); }
+    // readers go through these: the batch's own arrays, or (device discovery) views into the engine's pinned staging memory
+    const int32_t* vk = nullptr; const int32_t* vlon = nullptr; const int32_t* vsp = nullptr; const uint8_t* vfwd = nullptr;
+    size_t vcount = 0;
+    const int32_t* K() const { return vk ? vk : k.data(); }
+    const int32_t* LON() const { return vlon ? vlon : lon.data(); }
+    const int32_t* SP() const { return vsp ? vsp : sp.data(); }
+    const uint8_t* FWD() const { return vfwd ? vfwd : fwd.data(); }
+    size_t ncands() const { return vk ? vcount : k.size(); }
+    void clear() { off.clear(); cnt.clear(); k.clear(); lon.clear(); sp.clear(); fwd.clear(); vk = vlon = vsp = nullptr; vfwd = nullptr; vcount = 0; }
     int32_t count(int t) const { return cnt.empty() ? (int32_t)(off[t + 1] - off[t]) : cnt[t]; }
     // rewrite into window order: off[ntasks+1] increasing, cnt empty
     void compact(int ntasks) {
@@ -70,12 +78,35 @@ struct CandBatch {
     }
 };
 
+#if defined(__CUDACC__)
+#define PB_HD __host__ __device__
+#else
+#define PB_HD
+#endif
+// hash of a region's 2n coordinates (start[n], end[n]): start and end of the first and the last genome - regions equal there and
+// different elsewhere are rare, and every table compares all coordinates on a hit.  Shared by the host's candidate cache and the
+// engine, which delivers the hashes of the regions it discovered.
+PB_HD inline uint64_t region_coords_hash(const int64_t* p, int count) {
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    const int half = count / 2;
+    const int idx[4] = {0, half - 1, half, count - 1};
+    for (int t = 0; t < 4; ++t) {
+        h ^= (uint64_t)p[idx[t]] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+        h *= 0xff51afd7ed558ccdull;
+        h ^= h >> 29;
+    }
+    return h;
+}
+// one searched reference window of a region in a candidate cache
+struct WindowRec { int64_t ref_start, ref_len; int64_t cand_off; int32_t ncand; int32_t chunk; };
+
 // Device-resident discovery of the recursion (cuda/recursion.cuh): every region the engine searched while following the
 // accept / trim / determineRegion rules on a scratch copy of mumlayout, with the candidates of its (single) window.
 struct RecursionRequest {
     int n = 0;                           // genomes
     const int64_t* coords = nullptr;     // initial regions: start[n] then end[n] each
     int nregions = 0;
+    bool upload_layout = true;           // false: keep the scratch layout of the previous call (next slice of the same alignment)
     const uint64_t* const* layout = nullptr;   // mumlayout after the anchors: per genome its words ...
     const int64_t* layout_words = nullptr;     // ... and their number (len + 1 bits incl. the sentinel)
     int q = 30;                          // ini [LCB] q
@@ -83,13 +114,18 @@ struct RecursionRequest {
     const int32_t* minsize_tab = nullptr;      // minsize(slength) of the ini `mums` expression for slength < minsize_n
     int minsize_n = 0;
 };
+// All arrays are VIEWS into memory of the backend (pinned staging), valid until its next discover_recursion call; regions are in
+// ascending start[0] order, candidates grouped accordingly.
 struct RecursionResult {
-    size_t nregions = 0;
-    pod_vector<int32_t> coords;          // [nregions * 2n]: start[n] then LENGTH[n]
-    pod_vector<int32_t> slen, ncand;     // ncand < 0: not searched (left to the caller)
-    pod_vector<int64_t> cand_base;       // first candidate of the region in `cand`
-    pod_vector<int32_t> k, lon, sp;      // candidates as in CandBatch (sp / fwd: nq per candidate)
-    pod_vector<uint8_t> fwd;
+    size_t nregions = 0, ncands = 0;
+    const int64_t* coords = nullptr;     // [nregions * 2n]: start[n] then end[n]
+    const int64_t* slen = nullptr;       // TRegion::slength
+    const uint64_t* hashes = nullptr;    // region_coords_hash of every region
+    const WindowRec* wins = nullptr;     // the region's single window; ncand < 0: not searched (left to the caller)
+    const int32_t* k = nullptr;          // candidates as in CandBatch (sp / fwd: nq per candidate)
+    const int32_t* lon = nullptr;
+    const int32_t* sp = nullptr;
+    const uint8_t* fwd = nullptr;
     int64_t levels = 0, deferred = 0, dropped = 0, searched = 0;
 };
 

@@ -221,9 +221,13 @@ public:
         // ---- scratch mumlayout
         std::vector<int64_t> bit_off((size_t)n + 1, 0);
         for (int g = 0; g < n; ++g) bit_off[(size_t)g + 1] = bit_off[(size_t)g] + rq.layout_words[g];
+        if (!rq.upload_layout && (r_bits_words_ != bit_off[(size_t)n] || !r_bits_.get())) return false;
         unsigned long long* d_bits = r_bits_.ensure((size_t)bit_off[(size_t)n] + 8, false, st_);
-        for (int g = 0; g < n; ++g)
-            PB_CUDA(cudaMemcpyAsync(d_bits + bit_off[(size_t)g], rq.layout[g], (size_t)rq.layout_words[g] * 8, cudaMemcpyHostToDevice, st_));
+        if (rq.upload_layout) {
+            for (int g = 0; g < n; ++g)
+                PB_CUDA(cudaMemcpyAsync(d_bits + bit_off[(size_t)g], rq.layout[g], (size_t)rq.layout_words[g] * 8, cudaMemcpyHostToDevice, st_));
+            r_bits_words_ = bit_off[(size_t)n];
+        }
         int64_t* d_bit_off = r_bitoff_.ensure((size_t)n + 1, false, st_);
         int64_t* h_bit_off = r_pin_bitoff_.ensure((size_t)n + 1);
         std::memcpy(h_bit_off, bit_off.data(), ((size_t)n + 1) * 8);
@@ -248,18 +252,25 @@ public:
         Q.count = ctr; Q.taken = ctr + 8; Q.nregions = ctr + 16; Q.ndeferred = ctr + 17; Q.dropped = ctr + 18;
         Q.cap = (unsigned int)std::min<size_t>(cap, 0x7fffffffu);
         {   // initial regions: start[n], len[n] as int32 (pinned staging)
-            int32_t* h = r_pin_coords_.ensure(R * 2 * (size_t)n);
+            // + one flag per region: "this region and the next one are the two sides of one anchor gap" (the right side of anchor
+            // i is pushed before the left side of anchor i+1, which starts one base earlier and is searched first)
+            int32_t* h = r_pin_coords_.ensure(R * 2 * (size_t)n + (R + 3) / 4 + 16);
+            uint8_t* hp = reinterpret_cast<uint8_t*>(h + R * 2 * (size_t)n);
             const long per = 4096;
             parallel_chunks(R > 16384 ? default_host_threads() : 1, ((long)R + per - 1) / per, [&](long c) {
                 for (size_t r = (size_t)c * per; r < std::min(R, (size_t)(c + 1) * per); ++r) {
                     const int64_t* s = rq.coords + r * 2 * (size_t)n;
                     int32_t* d = h + r * 2 * (size_t)n;
                     for (int g = 0; g < n; ++g) { d[g] = (int32_t)s[g]; d[n + g] = (int32_t)(s[n + g] - s[g]); }
+                    const int64_t* t = s + 2 * (size_t)n;
+                    hp[r] = (r + 1 < R && t[0] == s[0] - 1 && t[n] == s[n]) ? 1 : 0;
                 }
             });
             PB_CUDA(cudaMemcpyAsync(St.coords, h, R * 2 * (size_t)n * 4, cudaMemcpyHostToDevice, st_));
+            r_pairflag_ = r_pair_.ensure(R + 16, false, st_);
+            PB_CUDA(cudaMemcpyAsync(r_pairflag_, hp, R, cudaMemcpyHostToDevice, st_));
             const unsigned int r32 = (unsigned int)R;
-            unsigned int* hr = r_pin_ctr_.ensure(32);
+            unsigned int* hr = r_pin_ctr_.ensure(40);
             hr[0] = r32;
             PB_CUDA(cudaMemcpyAsync(Q.nregions, hr, 4, cudaMemcpyHostToDevice, st_));
         }
@@ -295,8 +306,8 @@ public:
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, cfg[c].threads, cfg[c].smem_bytes(nq)) != cudaSuccess || per_sm < 1) per_sm = 1;
             ctas[c] = sm_count_ * per_sm;
         }
-        pb200::launch(rec::seed_lists_kernel, (unsigned)((R + 255) / 256), 256, 0, st_, P, St, Q, (int)R);
-        unsigned int* h_ctr = r_pin_ctr_.ensure(32);
+        pb200::launch(rec::seed_lists_kernel, (unsigned)((R + 255) / 256), 256, 0, st_, P, St, Q, (int)R, (const uint8_t*)r_pairflag_);
+        unsigned int* h_ctr = r_pin_ctr_.ensure(40);
         int level = 0;
         const int LEVELS_PER_ROUND = 8;
         for (int round = 0; round < 64; ++round) {
@@ -311,6 +322,7 @@ public:
             }
             PB_CUDA(cudaGetLastError());
             PB_CUDA(cudaMemcpyAsync(h_ctr, ctr, 32 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
+            PB_CUDA(cudaMemcpyAsync(h_ctr + 32, d_cnt, 8, cudaMemcpyDeviceToHost, st_));       // (candidates produced so far)
             PB_CUDA(cudaStreamSynchronize(st_));
             const int nx = level & 1;                       // the lists the next level would read
             if (h_ctr[nx * rec::NCLASS] + h_ctr[nx * rec::NCLASS + 1] + h_ctr[nx * rec::NCLASS + 2] == 0) break;
@@ -330,62 +342,58 @@ public:
         uint32_t* d_total = reinterpret_cast<uint32_t*>(ctr + 24);
         pb200::launch(rec::sorted_counts_kernel, (unsigned)((NR + 255) / 256), 256, 0, st_, St, perm, nr32, cnt);
         r_scanner_.scan<prim::OpSum, true>(cnt, cnt, (int64_t)NR, d_total, st_);
-        int32_t* o_coords = r_ocoords_.ensure(NR * 2 * (size_t)n + 64, false, st_);
-        int32_t* o_slen = r_oslen_.ensure(2 * NR + 64, false, st_);
-        int32_t* o_ncand = o_slen + NR;
-        int64_t* o_base = r_obase_.ensure(NR + 8, false, st_);
         // (capacity of the regrouped candidate arrays = what was produced: read the counter first)
         unsigned long long used = 0;
-        PB_CUDA(cudaMemcpyAsync(&used, d_cnt, 8, cudaMemcpyDeviceToHost, st_));
-        PB_CUDA(cudaStreamSynchronize(st_));
+        std::memcpy(&used, h_ctr + 32, 8);                  // (read back with the level counters: final after the last level)
         const size_t NCmax = (size_t)std::min<unsigned long long>(used, cand_cap);
         if (used > cand_cap) r_cand_hint_ = (size_t)used + (size_t)used / 4;          // (the windows that did not fit are searched on demand)
-        int32_t* o_k = r_ok_.ensure(2 * NCmax + 64, false, st_);
-        int32_t* o_lon = o_k + NCmax;
-        int32_t* o_sp = r_osp_.ensure(NCmax * (size_t)nq + 64, false, st_);
-        uint8_t* o_fw = r_ofwd_.ensure(NCmax * (size_t)nq + 64, false, st_);
-        pb200::launch(rec::gather_sorted_kernel, (unsigned)((NR * 32 + 255) / 256), 256, 0, st_, St, n, perm, cnt, nr32, d_k, d_lon, d_sp, d_fw, o_coords, o_slen,
-                      o_ncand, o_base, o_k, o_lon, o_sp, o_fw);
+        // one device block laid out like the pinned block the host reads: coords | slen | hashes | wins | k | lon | sp | fwd
+        auto al64 = [](size_t x) { return (x + 63) & ~(size_t)63; };
+        size_t off[9];
+        off[0] = 0;
+        off[1] = off[0] + al64(NR * 2 * (size_t)n * 8);
+        off[2] = off[1] + al64(NR * 8);
+        off[3] = off[2] + al64(NR * 8);
+        off[4] = off[3] + al64(NR * sizeof(WindowRec));
+        off[5] = off[4] + al64(NCmax * 4);
+        off[6] = off[5] + al64(NCmax * 4);
+        off[7] = off[6] + al64(NCmax * (size_t)nq * 4);
+        off[8] = off[7] + al64(NCmax * (size_t)nq);
+        uint8_t* d_out = r_out_.ensure(off[8] + 64, false, st_);
+        pb200::launch(rec::gather_sorted_kernel, (unsigned)((NR * 32 + 255) / 256), 256, 0, st_, St, n, perm, cnt, nr32, d_k, d_lon, d_sp, d_fw,
+                      (int64_t*)(d_out + off[0]), (int64_t*)(d_out + off[1]), (WindowRec*)(d_out + off[3]), (uint64_t*)(d_out + off[2]),
+                      (int32_t*)(d_out + off[4]), (int32_t*)(d_out + off[5]), (int32_t*)(d_out + off[6]), d_out + off[7]);
         PB_CUDA(cudaGetLastError());
         PB_CUDA(cudaMemcpyAsync(h_ctr, ctr, 32 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
+        uint8_t* stage = r_pin_stage_.ensure(off[8] + 64);
+        PB_CUDA(cudaMemcpyAsync(stage, d_out, off[8], cudaMemcpyDeviceToHost, st_));
         PB_CUDA(cudaStreamSynchronize(st_));
         const double t1 = wall_s();
         const size_t NC = std::min<size_t>(h_ctr[24], NCmax);
-        out.nregions = NR;
-        out.coords.resize(NR * 2 * (size_t)n); out.slen.resize(NR); out.ncand.resize(NR); out.cand_base.resize(NR);
-        out.k.resize(NC); out.lon.resize(NC); out.sp.resize(NC * (size_t)nq); out.fwd.resize(NC * (size_t)nq);
-        // device -> pinned staging -> the caller's vectors (parallel memcpy)
-        struct Part { void* dst; const void* src; size_t bytes; };
-        const Part parts[8] = {{out.coords.data(), o_coords, NR * 2 * (size_t)n * 4}, {out.slen.data(), o_slen, NR * 4}, {out.ncand.data(), o_ncand, NR * 4},
-                               {out.cand_base.data(), o_base, NR * 8}, {out.k.data(), o_k, NC * 4}, {out.lon.data(), o_lon, NC * 4},
-                               {out.sp.data(), o_sp, NC * (size_t)nq * 4}, {out.fwd.data(), o_fw, NC * (size_t)nq}};
-        size_t tot = 0, offs[9];
-        for (int i = 0; i < 8; ++i) { offs[i] = tot; tot += (parts[i].bytes + 63) & ~(size_t)63; }
-        offs[8] = tot;
-        uint8_t* stage = r_pin_stage_.ensure(tot + 64);
-        for (int i = 0; i < 8; ++i)
-            if (parts[i].bytes) PB_CUDA(cudaMemcpyAsync(stage + offs[i], parts[i].src, parts[i].bytes, cudaMemcpyDeviceToHost, st_));
-        PB_CUDA(cudaStreamSynchronize(st_));
+        out.nregions = NR; out.ncands = NC;
+        out.coords = (const int64_t*)(stage + off[0]); out.slen = (const int64_t*)(stage + off[1]); out.hashes = (const uint64_t*)(stage + off[2]);
+        out.wins = (const WindowRec*)(stage + off[3]); out.k = (const int32_t*)(stage + off[4]); out.lon = (const int32_t*)(stage + off[5]);
+        out.sp = (const int32_t*)(stage + off[6]); out.fwd = stage + off[7];
         const double t2 = wall_s();
-        {
-            const size_t CH = (size_t)1 << 20;
-            std::vector<std::pair<int, size_t>> chunks;
-            for (int i = 0; i < 8; ++i) for (size_t o = 0; o < parts[i].bytes; o += CH) chunks.emplace_back(i, o);
-            parallel_chunks(default_host_threads(), (long)chunks.size(), [&](long c) {
-                const int i = chunks[(size_t)c].first; const size_t o = chunks[(size_t)c].second;
-                std::memcpy((char*)parts[i].dst + o, stage + offs[i] + o, std::min(CH, parts[i].bytes - o));
-            });
-        }
         out.levels = level; out.deferred = h_ctr[17]; out.dropped = h_ctr[18];
         // statistics: searched windows, their reference / query bases (bench.py's algorithmic-byte model)
         int64_t searched = 0, rb = 0, qb = 0, cands = 0;
-        for (size_t r = 0; r < NR; ++r) {
-            if (out.ncand[r] < 0) continue;
-            ++searched;
-            cands += out.ncand[r];
-            const int32_t* c = &out.coords[r * 2 * (size_t)n];
-            rb += c[n];
-            for (int g = 1; g < n; ++g) qb += c[n + g];
+        {
+            const long per = 4096;
+            const long nb = ((long)NR + per - 1) / per;
+            std::vector<int64_t> acc((size_t)nb * 4 + 4, 0);
+            parallel_chunks(NR > 16384 ? default_host_threads() : 1, nb, [&](long c) {
+                int64_t s = 0, r_ = 0, q_ = 0, k_ = 0;
+                for (size_t r = (size_t)c * per; r < std::min(NR, (size_t)(c + 1) * per); ++r) {
+                    if (out.wins[r].ncand < 0) continue;
+                    ++s; k_ += out.wins[r].ncand;
+                    const int64_t* cc = out.coords + r * 2 * (size_t)n;
+                    r_ += cc[n] - cc[0];
+                    for (int g = 1; g < n; ++g) q_ += cc[n + g] - cc[g];
+                }
+                acc[(size_t)c * 4] = s; acc[(size_t)c * 4 + 1] = r_; acc[(size_t)c * 4 + 2] = q_; acc[(size_t)c * 4 + 3] = k_;
+            });
+            for (long c = 0; c < nb; ++c) { searched += acc[(size_t)c * 4]; rb += acc[(size_t)c * 4 + 1]; qb += acc[(size_t)c * 4 + 2]; cands += acc[(size_t)c * 4 + 3]; }
         }
         out.searched = searched;
         small_windows += searched; small_ref_bases += rb; small_query_bases += qb;
@@ -669,13 +677,14 @@ private:
     PinBuf<int32_t> r_pin_tab_, r_pin_coords_;
     PinBuf<unsigned int> r_pin_ctr_;
     PinBuf<uint8_t> r_pin_stage_;
+    DevBuf<uint8_t> r_pair_;
+    uint8_t* r_pairflag_ = nullptr;
     DevBuf<uint32_t> r_sortk_, r_sortv_;
-    DevBuf<int32_t> r_ocoords_, r_oslen_, r_ok_, r_osp_;
-    DevBuf<int64_t> r_obase_;
-    DevBuf<uint8_t> r_ofwd_;
+    DevBuf<uint8_t> r_out_;
     rsort::RadixSorter r_sorter_;
     prim::Scanner r_scanner_;
     size_t r_cand_hint_ = 0;
+    int64_t r_bits_words_ = -1;
     bool r_attr_set_[8] = {false, false, false, false, false, false, false, false};
     PinBuf<int32_t> pin_k_, pin_lon_, pin_sp_;       // small-window candidates of the current search() call (pinned staging)
     PinBuf<uint8_t> pin_fwd_;

@@ -20,6 +20,10 @@ namespace pb200 {
 namespace rec {
 
 constexpr int NCLASS = 3;
+// a work-list entry: region id, optionally the PAIR (id, id + 1) = the two regions that cover one gap (the left side of a MUM
+// starts one base before the right side of its predecessor): the reference searches the one with the smaller start first and
+// the second one then sees its bits, so one CTA takes both, in that order
+constexpr int32_t E_PAIR = 1 << 30, E_SECOND_FIRST = 1 << 29, E_ID = (1 << 29) - 1;
 
 // work lists of one run: level L reads list[L & 1][c][0 .. count[L & 1][c]) and appends children to list[(L + 1) & 1]
 struct Queues {
@@ -128,40 +132,70 @@ __device__ __forceinline__ int class_of(const Params& P, int64_t ref_len, int64_
     return NCLASS;
 }
 
-// append region (S[], E[]) (lanes hold genomes lane, lane + 32, ...) to the store and to the next level's list of its class
+// class + minsize of region (S, E) (lanes hold genomes lane, lane + 32, ...)
 template <int GPL>
-__device__ inline void push_region(const Params& P, const Store& St, const Queues& Q, int next, const int64_t (&S)[GPL], const int64_t (&E)[GPL],
-                                   int64_t slength, int lane) {
+__device__ inline int region_class(const Params& P, const int64_t (&S)[GPL], const int64_t (&E)[GPL], int64_t slength, int lane, int& ms) {
     const int n = P.n;
     int64_t mm = 0;
     for (int t = 0; t < GPL; ++t) { const int g = lane + 32 * t; if (g >= 1 && g < n) mm = max(mm, E[t] - S[t]); }
     mm = -warp_min64(-mm);
     const int64_t L0 = __shfl_sync(0xffffffffu, E[0] - S[0], 0);
-    const int ms = slength >= 0 && slength < P.minsize_n ? P.minsize_tab[slength] : 0;
-    const int cls = class_of(P, L0, mm, ms);
-    unsigned int id = 0;
-    if (lane == 0) id = atomicAdd(Q.nregions, 1u);
-    id = __shfl_sync(0xffffffffu, id, 0);
-    if (id >= Q.cap) { if (lane == 0) { atomicSub(Q.nregions, 1u); atomicAdd(Q.dropped, 1u); } return; }
+    ms = slength >= 0 && slength < P.minsize_n ? P.minsize_tab[slength] : 0;
+    return class_of(P, L0, mm, ms);
+}
+template <int GPL>
+__device__ inline void write_region(const Params& P, const Store& St, unsigned int id, const int64_t (&S)[GPL], const int64_t (&E)[GPL], int64_t slength,
+                                    int ms, int lane) {
+    const int n = P.n;
     int32_t* c = St.coords + (size_t)id * 2 * n;
     for (int t = 0; t < GPL; ++t) {
         const int g = lane + 32 * t;
         if (g < n) { c[g] = (int32_t)S[t]; c[n + g] = (int32_t)(E[t] - S[t]); }
     }
-    if (lane == 0) {
-        St.slen[id] = (int32_t)slength;
-        St.minsize[id] = ms;
-        St.ncand[id] = -1;
-        St.cand_base[id] = 0;
-        if (cls < NCLASS) {
-            const unsigned int at = atomicAdd(&Q.count[next * NCLASS + cls], 1u);
-            if (at < Q.cap) Q.list[next][cls][at] = (int32_t)id;
-            else { atomicSub(&Q.count[next * NCLASS + cls], 1u); atomicAdd(Q.dropped, 1u); }
-        } else {
-            const unsigned int at = atomicAdd(Q.ndeferred, 1u);
-            if (at < Q.cap) Q.deferred[at] = (int32_t)id;
-        }
+    if (lane == 0) { St.slen[id] = (int32_t)slength; St.minsize[id] = ms; St.ncand[id] = -1; St.cand_base[id] = 0; }
+}
+__device__ inline void enqueue(const Queues& Q, int next, int cls, int32_t entry) {        // one lane
+    if (cls < NCLASS) {
+        const unsigned int at = atomicAdd(&Q.count[next * NCLASS + cls], 1u);
+        if (at < Q.cap) Q.list[next][cls][at] = entry;
+        else { atomicSub(&Q.count[next * NCLASS + cls], 1u); atomicAdd(Q.dropped, 1u); }
+    } else {
+        const unsigned int at = atomicAdd(Q.ndeferred, 1u);
+        if (at < Q.cap) Q.deferred[at] = entry & E_ID;
     }
+}
+// append region (S[], E[]) to the store and to the next level's list of its class
+template <int GPL>
+__device__ inline void push_region(const Params& P, const Store& St, const Queues& Q, int next, const int64_t (&S)[GPL], const int64_t (&E)[GPL],
+                                   int64_t slength, int lane) {
+    int ms;
+    const int cls = region_class<GPL>(P, S, E, slength, lane, ms);
+    unsigned int id = 0;
+    if (lane == 0) id = atomicAdd(Q.nregions, 1u);
+    id = __shfl_sync(0xffffffffu, id, 0);
+    if (id >= Q.cap) { if (lane == 0) { atomicSub(Q.nregions, 1u); atomicAdd(Q.dropped, 1u); } return; }
+    write_region<GPL>(P, St, id, S, E, slength, ms, lane);
+    if (lane == 0) enqueue(Q, next, cls, (int32_t)id);
+}
+// the two regions of one gap: A (smaller start[0], searched first) and B, as ONE entry when the device can take both
+template <int GPL>
+__device__ inline void push_pair(const Params& P, const Store& St, const Queues& Q, int next, const int64_t (&SA)[GPL], const int64_t (&EA)[GPL],
+                                 int64_t slA, const int64_t (&SB)[GPL], const int64_t (&EB)[GPL], int64_t slB, int lane) {
+    int msA, msB;
+    const int clsA = region_class<GPL>(P, SA, EA, slA, lane, msA);
+    const int clsB = region_class<GPL>(P, SB, EB, slB, lane, msB);
+    if (clsA >= NCLASS || clsB >= NCLASS) {
+        push_region<GPL>(P, St, Q, next, SA, EA, slA, lane);
+        push_region<GPL>(P, St, Q, next, SB, EB, slB, lane);
+        return;
+    }
+    unsigned int id = 0;
+    if (lane == 0) id = atomicAdd(Q.nregions, 2u);
+    id = __shfl_sync(0xffffffffu, id, 0);
+    if (id + 1 >= Q.cap) { if (lane == 0) { atomicSub(Q.nregions, 2u); atomicAdd(Q.dropped, 2u); } return; }
+    write_region<GPL>(P, St, id, SA, EA, slA, msA, lane);
+    write_region<GPL>(P, St, id + 1, SB, EB, slB, msB, lane);
+    if (lane == 0) enqueue(Q, next, max(clsA, clsB), (int32_t)id | E_PAIR);
 }
 
 // setMums1 loop D + determineRegion for the candidates of one searched region, by ONE WARP, on the scratch layout.
@@ -254,7 +288,9 @@ __device__ inline void accept_region(const Params& P, const Store& St, const Que
     if (nacc == 0) return;
     __threadfence();                                            // (this warp's own atomics are ordered before its reads below)
     __syncwarp();
-    // determineRegion around every accepted MUM, on the layout as it is after ALL accepts of the region (src/parsnp.cpp:251-289)
+    // determineRegion around every accepted MUM, on the layout as it is after ALL accepts of the region (src/parsnp.cpp:251-289).
+    // The right side of MUM a-1 and the left side of MUM a are the same gap: pushed as a pair, left side first.
+    int64_t pS[GPL], pE[GPL], psl = -1;                         // pending right side of the previous MUM (psl <= q: none)
     for (int a = 0; a < nacc; ++a) {
         const int c = accC[a];
         const int64_t shift = accShift[a], length = accLen[a];
@@ -283,9 +319,13 @@ __device__ inline void accept_region(const Params& P, const Store& St, const Que
         }
         lsl = warp_min64(lsl);
         rsl = warp_min64(rsl);
-        if (lsl > P.q) push_region<GPL>(P, St, Q, next, lS, lE, lsl, lane);
-        if (rsl > P.q) push_region<GPL>(P, St, Q, next, rS, rE, rsl, lane);
+        if (lsl > P.q && psl > P.q) push_pair<GPL>(P, St, Q, next, lS, lE, lsl, pS, pE, psl, lane);
+        else if (lsl > P.q) push_region<GPL>(P, St, Q, next, lS, lE, lsl, lane);
+        else if (psl > P.q) push_region<GPL>(P, St, Q, next, pS, pE, psl, lane);
+        for (int t = 0; t < GPL; ++t) { pS[t] = rS[t]; pE[t] = rE[t]; }
+        psl = rsl;
     }
+    if (psl > P.q) push_region<GPL>(P, St, Q, next, pS, pE, psl, lane);
 }
 
 // One level of one size class: CTAs take regions from the level's list until it is empty (dynamic scheduling), search the
@@ -314,36 +354,35 @@ __global__ void __launch_bounds__(small::SM_MAX_THREADS, 4) recursion_level_kern
         __syncthreads();
         const unsigned int ti = (unsigned int)s_next;
         if (ti >= total) break;
-        const int region = Q.list[cur][cls][ti];
-        const int32_t* rc = St.coords + (size_t)region * 2 * P.n;
-        small::TaskDev tk;
-        tk.ref_off = gbase_fwd[0] + rc[0];
-        tk.n = rc[P.n];
-        tk.minsize = St.minsize[region];
-        tk.qcoord_off = 0;
-        small::small_window(text, gbase_fwd, gbase_rc, glen, nq, tk, rc + 1, rc + P.n + 1, cfg, sv, s_bar, s_mis, wphase, qphase, cand_counter,
-                            cand_cap_global, out_k, out_lon, out_sp, out_fwd);
-        const int ovf = sv.s_int[3];
-        const int nc = sv.s_int[2];
-        const int64_t base = *reinterpret_cast<int64_t*>(&sv.s_int[4]);
-        if (ovf) {
-            if (threadIdx.x == 0) {
-                if (ovf == 1 && cls + 1 < NCLASS) {
-                    const unsigned int at = atomicAdd(&Q.count[next * NCLASS + cls + 1], 1u);
-                    if (at < Q.cap) Q.list[next][cls + 1][at] = region;
-                    else { atomicSub(&Q.count[next * NCLASS + cls + 1], 1u); atomicAdd(Q.dropped, 1u); }
-                } else {
-                    const unsigned int at = atomicAdd(Q.ndeferred, 1u);
-                    if (at < Q.cap) Q.deferred[at] = region;
-                }
+        const int32_t entry = Q.list[cur][cls][ti];
+        const int first = (entry & E_ID) + ((entry & E_PAIR) && (entry & E_SECOND_FIRST) ? 1 : 0);
+        const int second = (entry & E_PAIR) ? (entry & E_ID) + ((entry & E_SECOND_FIRST) ? 0 : 1) : -1;
+        for (int half = 0; half < 2; ++half) {
+            const int region = half == 0 ? first : second;
+            if (region < 0) break;
+            if (half == 1) __syncthreads();                     // (warp 0 has finished the first region's accepts)
+            const int32_t* rc = St.coords + (size_t)region * 2 * P.n;
+            small::TaskDev tk;
+            tk.ref_off = gbase_fwd[0] + rc[0];
+            tk.n = rc[P.n];
+            tk.minsize = St.minsize[region];
+            tk.qcoord_off = 0;
+            small::small_window(text, gbase_fwd, gbase_rc, glen, nq, tk, rc + 1, rc + P.n + 1, cfg, sv, s_bar, s_mis, wphase, qphase, cand_counter,
+                                cand_cap_global, out_k, out_lon, out_sp, out_fwd);
+            const int ovf = sv.s_int[3];
+            const int nc = sv.s_int[2];
+            const int64_t base = *reinterpret_cast<int64_t*>(&sv.s_int[4]);
+            if (ovf) {
+                // a per-CTA capacity: this region alone goes to the next class (next level's list); anything else: the host
+                if (threadIdx.x == 0) enqueue(Q, next, ovf == 1 && cls + 1 < NCLASS ? cls + 1 : NCLASS, (int32_t)region);
+                continue;
             }
-            continue;
-        }
-        if (threadIdx.x == 0) { St.ncand[region] = nc; St.cand_base[region] = base; }
-        if (threadIdx.x < 32 && nc > 0) {
-            // (the candidate rows were written by this CTA before the barrier that ends small_window)
-            accept_region<GPL>(P, St, Q, next, text, gbase_fwd, glen, region, nc, base, out_k, out_lon, out_sp, out_fwd, sv.candK, sv.candM,
-                               reinterpret_cast<uint16_t*>(sv.HQ));
+            if (threadIdx.x == 0) { St.ncand[region] = nc; St.cand_base[region] = base; }
+            if (threadIdx.x < 32 && nc > 0) {
+                // (the candidate rows were written by this CTA before the barrier that ends small_window)
+                accept_region<GPL>(P, St, Q, next, text, gbase_fwd, glen, region, nc, base, out_k, out_lon, out_sp, out_fwd, sv.candK, sv.candM,
+                                   reinterpret_cast<uint16_t*>(sv.HQ));
+            }
         }
     }
 }
@@ -354,8 +393,9 @@ __global__ void level_advance_kernel(Queues Q, int level) {
     if (threadIdx.x < NCLASS) { Q.count[cur * NCLASS + threadIdx.x] = 0; Q.taken[cur * NCLASS + threadIdx.x] = 0; }
 }
 
-// level 0: classify the initial regions (uploaded into the store by the host) into the first lists
-__global__ void seed_lists_kernel(Params P, Store St, Queues Q, int count) {
+// level 0: classify the initial regions (uploaded into the store by the host) into the first lists.  pair[id] = 1: regions id
+// and id + 1 are the right side of an anchor and the left side of the next one - one entry, the second searched first
+__global__ void seed_lists_kernel(Params P, Store St, Queues Q, int count, const uint8_t* __restrict__ pair) {
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= count) return;
     const int n = P.n;
@@ -367,14 +407,24 @@ __global__ void seed_lists_kernel(Params P, Store St, Queues Q, int count) {
     St.minsize[id] = ms;
     St.ncand[id] = -1;
     St.cand_base[id] = 0;
-    const int cls = class_of(P, c[n], mm, ms);
-    if (cls < NCLASS) {
-        const unsigned int at = atomicAdd(&Q.count[cls], 1u);
-        Q.list[0][cls][at] = id;
-    } else {
-        const unsigned int at = atomicAdd(Q.ndeferred, 1u);
-        if (at < Q.cap) Q.deferred[at] = id;
+    int cls = class_of(P, c[n], mm, ms);
+    const bool second = id > 0 && pair[id - 1];
+    bool head = pair[id] && id + 1 < count;
+    if (second || head) {
+        // class of the mate (recomputed: both threads must take the same decision)
+        const int o = second ? id - 1 : id + 1;
+        const int32_t* d = St.coords + (size_t)o * 2 * n;
+        int64_t mo = 0, so = 500000000;
+        for (int g = 0; g < n; ++g) { if (g) mo = max(mo, (int64_t)d[n + g]); so = min(so, (int64_t)d[n + g]); }
+        const int mso = so >= 0 && so < P.minsize_n ? P.minsize_tab[so] : 0;
+        const int co = class_of(P, d[n], mo, mso);
+        if (cls < NCLASS && co < NCLASS) {
+            if (second) return;                                 // the head enqueues the pair
+            enqueue(Q, 0, max(cls, co), (int32_t)id | E_PAIR | E_SECOND_FIRST);
+            return;
+        }
     }
+    enqueue(Q, 0, cls, (int32_t)id);
 }
 
 // ---- after the last level: regions in ascending start[0] order (the order in which the replay pops them, so its lookups and
@@ -391,21 +441,39 @@ __global__ void sorted_counts_kernel(Store St, const uint32_t* __restrict__ perm
     const int c = St.ncand[perm[i]];
     cnt[i] = c > 0 ? (uint32_t)c : 0u;
 }
-// one warp per region: its record and its candidates into sorted position
+// one warp per region: its record in the host's final form (int64 start / end coordinates, slength, window record, coordinate
+// hash) and its candidates, into sorted position
 __global__ void gather_sorted_kernel(Store St, int n, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ newbase, unsigned int nr,
                                      const int32_t* __restrict__ k, const int32_t* __restrict__ lon, const int32_t* __restrict__ sp,
-                                     const uint8_t* __restrict__ fwd, int32_t* __restrict__ o_coords, int32_t* __restrict__ o_slen,
-                                     int32_t* __restrict__ o_ncand, int64_t* __restrict__ o_base, int32_t* __restrict__ o_k,
+                                     const uint8_t* __restrict__ fwd, int64_t* __restrict__ o_coords, int64_t* __restrict__ o_slen,
+                                     WindowRec* __restrict__ o_wins, uint64_t* __restrict__ o_hash, int32_t* __restrict__ o_k,
                                      int32_t* __restrict__ o_lon, int32_t* __restrict__ o_sp, uint8_t* __restrict__ o_fwd) {
     const unsigned int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (i >= nr) return;
     const unsigned int r = perm[i];
     const int nq = n - 1;
-    for (int x = lane; x < 2 * n; x += 32) o_coords[(size_t)i * 2 * n + x] = St.coords[(size_t)r * 2 * n + x];
+    const int32_t* c = St.coords + (size_t)r * 2 * n;
+    int64_t* oc = o_coords + (size_t)i * 2 * n;
+    for (int g = lane; g < n; g += 32) { const int64_t s = c[g]; oc[g] = s; oc[n + g] = s + c[n + g]; }
     const int nc = St.ncand[r];
     const int64_t ob = St.cand_base[r], nb = newbase[i];
-    if (lane == 0) { o_slen[i] = St.slen[r]; o_ncand[i] = nc; o_base[i] = nb; }
+    __syncwarp();
+    if (lane == 0) {
+        o_slen[i] = St.slen[r];
+        WindowRec w;
+        w.ref_start = c[0]; w.ref_len = c[n]; w.cand_off = nb; w.ncand = nc; w.chunk = 0;
+        o_wins[i] = w;
+        const int64_t h4[4] = {(int64_t)c[0], (int64_t)c[n - 1], (int64_t)c[0] + c[n], (int64_t)c[n - 1] + c[2 * n - 1]};
+        // region_coords_hash over (start[0], start[n-1], end[0], end[n-1]) - the same four values, the same arithmetic
+        uint64_t h = 0x9E3779B97F4A7C15ull;
+        for (int t = 0; t < 4; ++t) {
+            h ^= (uint64_t)h4[t] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+            h *= 0xff51afd7ed558ccdull;
+            h ^= h >> 29;
+        }
+        o_hash[i] = h;
+    }
     if (nc <= 0) return;
     for (int x = lane; x < nc; x += 32) { o_k[nb + x] = k[ob + x]; o_lon[nb + x] = lon[ob + x]; }
     const int64_t rows = (int64_t)nc * nq;

@@ -82,10 +82,10 @@ void Aligner::accept_candidates_t(const int64_t* rs, const int64_t* re, int64_t 
         if (trace) trace_.emplace_back(win.ref_start, win.ref_len);
         for (int32_t c = 0; c < win.ncand; ++c) {
             const int64_t ci = win.cand_off + c;
-            const int64_t LON = cb.lon[ci];
+            const int64_t LON = cb.LON()[ci];
             bool bad = false;
             // Mum.DSP is 1-based (src/parsnp.cpp:1671,1681); range pre-check in unsigned arithmetic (1723)
-            uint64_t dsp0 = (uint64_t)((int64_t)cb.k[ci] + 1 + win.ref_start);
+            uint64_t dsp0 = (uint64_t)((int64_t)cb.K()[ci] + 1 + win.ref_start);
             if ((uint64_t)(dsp0 - (uint64_t)rs[0]) > (uint64_t)(uint32_t)(re[0] - rs[0])) bad = true;
             st[0] = (int64_t)dsp0 - 1;
             fw[0] = 1;
@@ -96,8 +96,8 @@ void Aligner::accept_candidates_t(const int64_t* rs, const int64_t* re, int64_t 
             // false as soon as one genome's interval leaves its sequence (a middle-genome failure makes the reference throw;
             // unreachable).  Range pre-check and ctor are fused into one pass; both only ever skip the candidate.
             bool any_fail = st[0] + LON > len_[0] || st[0] < 0;
-            const int32_t* spj = cb.sp.data() + ci * nq;
-            const uint8_t* fwj = cb.fwd.data() + ci * nq;
+            const int32_t* spj = cb.SP() + ci * nq;
+            const uint8_t* fwj = cb.FWD() + ci * nq;
             for (int j = 1; j < n_; ++j) {
                 const uint64_t dsp = (uint64_t)((int64_t)spj[j - 1] + 1 + rs[j]);
                 bad |= (uint64_t)(dsp - (uint64_t)rs[j]) > (uint64_t)(uint32_t)(re[j] - rs[j]);

@@ -158,20 +158,7 @@ int RegionPool::add(const int64_t* start, const int64_t* end) {
     slen.push_back(sl);
     return id;
 }
-uint64_t Aligner::coords_hash(const int64_t* p, int count) {
-    // start and end of the first and the last genome: regions equal there and different elsewhere are rare and the table's
-    // equality callback compares all coordinates
-    uint64_t h = 0x9E3779B97F4A7C15ull;
-    const int half = count / 2;
-    const int idx[4] = {0, half - 1, half, count - 1};
-    for (int t = 0; t < 4; ++t) {
-        const int i = idx[t];
-        h ^= (uint64_t)p[i] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
-        h *= 0xff51afd7ed558ccdull;
-        h ^= h >> 29;
-    }
-    return h;
-}
+uint64_t Aligner::coords_hash(const int64_t* p, int count) { return region_coords_hash(p, count); }
 void Aligner::CoordIndex::insert(uint64_t hash, int value) {
     if ((count + 1) * 2 > s.size()) {                       // grow / rehash at 50 % load
         std::vector<Slot> os;
@@ -197,6 +184,35 @@ void Aligner::CoordIndex::reserve(size_t entries) {
     s.assign(need, Slot{0, -1, 0});
     count = 0;
     for (size_t i = 0; i < os.size(); ++i) if (os[i].v >= 0) insert(os[i].h, os[i].v);
+}
+void Aligner::CoordIndex::build_parallel(const std::vector<uint64_t>& hashes, const std::vector<uint8_t>& valid, int threads) {
+    const size_t N = hashes.size();
+    size_t need = 1024;
+    while (need < N * 2 + 2) need *= 2;
+    s.resize(need);
+    const long per = 8192;
+    parallel_chunks(need > 65536 ? threads : 1, ((long)need + per - 1) / per, [&](long c) {
+        for (size_t i = (size_t)c * per; i < std::min(need, (size_t)(c + 1) * per); ++i) s[i] = Slot{0, -1, 0};
+    });
+    const size_t mask = need - 1;
+    std::vector<size_t> cnt((size_t)(((long)N + per - 1) / per) + 1, 0);
+    parallel_chunks(N > 16384 ? threads : 1, ((long)N + per - 1) / per, [&](long c) {
+        size_t k = 0;
+        for (size_t r = (size_t)c * per; r < std::min(N, (size_t)(c + 1) * per); ++r) {
+            if (!valid[r]) continue;
+            size_t i = (size_t)hashes[r] & mask;
+            for (;;) {
+                int32_t expect = -1;
+                if (__atomic_compare_exchange_n(&s[i].v, &expect, (int32_t)r, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) break;
+                i = (i + 1) & mask;
+            }
+            s[i].h = hashes[r];                  // (read only after the pass has ended)
+            ++k;
+        }
+        cnt[(size_t)c] = k;
+    });
+    count = 0;
+    for (size_t k : cnt) count += k;
 }
 int Aligner::CandCache::lookup(const int64_t* coords) const {
     return lookup(coords, Aligner::coords_hash(coords, 2 * rp.n));
@@ -364,17 +380,17 @@ void Aligner::accept_candidates_parallel(const int64_t* rs, const int64_t* re, i
             const WinRec& win = CC.wins[ce.first_win + wi];
             const CandBatch& cb = CC.chunks[win.chunk];
             const int64_t ci = win.cand_off + ((int64_t)c - wbase[wi]);
-            const int64_t lon = cb.lon[ci];
+            const int64_t lon = cb.LON()[ci];
             int64_t* st = &ST[c * N];
             uint8_t* fw = &FW[c * N];
             bool bad = false;
-            const uint64_t dsp0 = (uint64_t)((int64_t)cb.k[ci] + 1 + win.ref_start);
+            const uint64_t dsp0 = (uint64_t)((int64_t)cb.K()[ci] + 1 + win.ref_start);
             if ((uint64_t)(dsp0 - (uint64_t)rs[0]) > (uint64_t)(uint32_t)(re[0] - rs[0])) bad = true;
             st[0] = (int64_t)dsp0 - 1;
             fw[0] = 1;
             bool any_fail = st[0] + lon > len_[0] || st[0] < 0;
-            const int32_t* spj = cb.sp.data() + ci * nq;
-            const uint8_t* fwj = cb.fwd.data() + ci * nq;
+            const int32_t* spj = cb.SP() + ci * nq;
+            const uint8_t* fwj = cb.FWD() + ci * nq;
             for (int j = 1; j < n_; ++j) {
                 const uint64_t dsp = (uint64_t)((int64_t)spj[j - 1] + 1 + rs[j]);
                 bad |= (uint64_t)(dsp - (uint64_t)rs[j]) > (uint64_t)(uint32_t)(re[j] - rs[j]);
@@ -1301,75 +1317,125 @@ std::shared_ptr<const std::vector<int32_t>> minsize_table(const std::string& exp
 }
 }  // namespace
 
+// The initial regions are cut into a few slices in reference order; the first one is followed here, the others on their own
+// thread while the replay already consumes what is published (every task waits for the slice of its regions only).
 bool Aligner::discover_on_device() {
-    const double t0 = now_s();
     const size_t R = initial_regions_.size();
     const int TABN = 4160;                       // covers every window the shared-memory search kernel takes (<= 4096 bases)
-    std::shared_ptr<const std::vector<int32_t>> tab = minsize_table(prm_.mums, TABN, threads_);
-    if (!tab) return false;
-    pod_vector<int64_t> coords(R * 2 * (size_t)n_);
+    disc_tab_ = minsize_table(prm_.mums, TABN, threads_);
+    if (!disc_tab_) return false;
+    disc_coords_.resize(R * 2 * (size_t)n_);
     const long per = 4096;
     parallel_chunks(R > 16384 ? threads_ : 1, ((long)R + per - 1) / per, [&](long c) {
         for (size_t i = (size_t)c * per; i < std::min(R, (size_t)(c + 1) * per); ++i)
-            std::memcpy(&coords[i * 2 * (size_t)n_], rstart(initial_regions_[i]), sizeof(int64_t) * 2 * (size_t)n_);
+            std::memcpy(&disc_coords_[i * 2 * (size_t)n_], rstart(initial_regions_[i]), sizeof(int64_t) * 2 * (size_t)n_);
     });
+    // slices: a small first one (the replay starts as soon as it is there), then growing
+    const char* es = getenv("PB200_DISCOVERY_SLICES");
+    size_t K = es ? (size_t)std::max(1, atoi(es)) : 1;       // (measured on configs[1]: slices cost more in launches and syncs than the overlap returns)
+    K = std::min(K, R);
+    disc_begin_.assign(K + 1, 0);
+    {
+        double tot = 0, run = 0;
+        for (size_t k = 0; k < K; ++k) tot += 1.0 + (double)k;
+        for (size_t k = 0; k < K; ++k) { run += 1.0 + (double)k; disc_begin_[k + 1] = (size_t)((double)R * run / tot); }
+        disc_begin_[K] = R;
+    }
+    slice_cache_.clear();
+    for (size_t k = 0; k < K; ++k) slice_cache_.emplace_back(new CandCache);
+    slice_of_initial_.assign(R, 0);
+    for (size_t k = 0; k < K; ++k)
+        for (size_t i = disc_begin_[k]; i < disc_begin_[k + 1]; ++i) slice_of_initial_[i] = (int)k;
+    slices_ready_ = 0;
+    stats_.spec_slices = (int64_t)K;
+    if (!discover_slice(0)) { slice_cache_.clear(); slice_of_initial_.clear(); stats_.spec_slices = 0; return false; }
+    {
+        std::lock_guard<std::mutex> lk(slice_mu_);
+        slices_ready_ = 1;
+    }
+    if (K > 1)
+        spec_thread_ = std::thread([this, K] {
+            try {
+                for (size_t k = 1; k < K; ++k) {
+                    discover_slice((int)k);               // (false = left empty: the replay searches those regions on demand)
+                    {
+                        std::lock_guard<std::mutex> lk(slice_mu_);
+                        slices_ready_ = (int)k + 1;
+                    }
+                    slice_cv_.notify_all();
+                }
+            } catch (...) {
+                std::lock_guard<std::mutex> lk(slice_mu_);
+                spec_error_ = std::current_exception();
+                slices_ready_ = (int)K;                    // nobody waits for ever; run() rethrows
+                slice_cv_.notify_all();
+            }
+        });
+    return true;
+}
+
+bool Aligner::discover_slice(int k) {
+    const double t0 = now_s();
+    const size_t i0 = disc_begin_[(size_t)k], R = disc_begin_[(size_t)k + 1] - i0;
+    const long per = 4096;
     std::vector<const uint64_t*> rows((size_t)n_);
     std::vector<int64_t> nwords((size_t)n_);
     for (int g = 0; g < n_; ++g) { rows[(size_t)g] = truth_.layout[(size_t)g].words(); nwords[(size_t)g] = truth_.layout[(size_t)g].nwords(); }
     RecursionRequest rq;
-    rq.n = n_; rq.coords = coords.data(); rq.nregions = (int)R; rq.layout = rows.data(); rq.layout_words = nwords.data();
-    rq.q = prm_.q; rq.p = prm_.p; rq.minsize_tab = tab->data(); rq.minsize_n = TABN;
+    rq.n = n_; rq.coords = disc_coords_.data() + i0 * 2 * (size_t)n_; rq.nregions = (int)R; rq.layout = rows.data(); rq.layout_words = nwords.data();
+    rq.upload_layout = k == 0;                   // (later slices run beside the replay, which writes the layout: the engine keeps its scratch copy)
+    rq.q = prm_.q; rq.p = prm_.p; rq.minsize_tab = disc_tab_->data(); rq.minsize_n = (int)disc_tab_->size();
     RecursionResult res;
+    if (R == 0) return true;
     {
         std::lock_guard<std::mutex> lk(backend_mu_);
         if (!be_->discover_recursion(rq, res)) return false;
     }
     const double t1 = now_s();
-    // ---- the result as a candidate cache (one window per region, candidates where the engine left them)
-    slice_cache_.clear();
-    slice_cache_.emplace_back(new CandCache);
-    CandCache& C = *slice_cache_.back();
+    // ---- the result as a candidate cache: one window per region; coordinates, window records, hashes and candidates come from the
+    // engine in their final form (views into its pinned staging memory; with several slices they are copied, the next slice
+    // overwrites them)
+    CandCache& C = *slice_cache_[(size_t)k];
     const size_t NR = res.nregions;
+    const bool copy = slice_cache_.size() > 1;
     C.rp.n = n_;
-    C.rp.coord.resize(NR * 2 * (size_t)n_);
-    C.rp.slen.resize(NR);
     C.entries.resize(NR);
     C.wins.resize(NR);
     C.chunks.emplace_back();
     CandBatch& cb = C.chunks.back();
     cb.nq = n_ - 1;
-    cb.k.swap(res.k); cb.lon.swap(res.lon); cb.sp.swap(res.sp); cb.fwd.swap(res.fwd);
     cb.off.assign(1, 0);
-    const size_t NC = cb.k.size();
-    std::vector<uint64_t> hashes(NR);
-    parallel_chunks(NR > 16384 ? threads_ : 1, ((long)NR + per - 1) / per, [&](long c) {
+    const size_t NC = res.ncands;
+    if (copy) {
+        C.rp.coord.assign(res.coords, res.coords + NR * 2 * (size_t)n_);
+        cb.k.assign(res.k, res.k + NC); cb.lon.assign(res.lon, res.lon + NC);
+        cb.sp.assign(res.sp, res.sp + NC * (size_t)(n_ - 1)); cb.fwd.assign(res.fwd, res.fwd + NC * (size_t)(n_ - 1));
+    } else {
+        C.rp.ext_coord = res.coords;
+        cb.vk = res.k; cb.vlon = res.lon; cb.vsp = res.sp; cb.vfwd = res.fwd; cb.vcount = NC;
+    }
+    std::vector<uint8_t> valid(NR);
+    std::vector<uint64_t> hashes(res.hashes, res.hashes + NR);
+    const long nblk = ((long)NR + per - 1) / per;
+    std::vector<int64_t> blk_searched((size_t)nblk + 1, 0), blk_cands((size_t)nblk + 1, 0);
+    parallel_chunks(NR > 16384 ? threads_ : 1, nblk, [&](long c) {
+        int64_t ns = 0, nc = 0;
         for (size_t r = (size_t)c * per; r < std::min(NR, (size_t)(c + 1) * per); ++r) {
-            const int32_t* s = &res.coords[r * 2 * (size_t)n_];
-            int64_t* d = &C.rp.coord[r * 2 * (size_t)n_];
-            for (int g = 0; g < n_; ++g) { d[g] = s[g]; d[n_ + g] = (int64_t)s[g] + s[n_ + g]; }
-            C.rp.slen[r] = res.slen[r];
             CacheEntry e; e.region = (int)r; e.first_win = (int64_t)r; e.nwin = 1;
             C.entries[r] = e;
-            WinRec w; w.ref_start = s[0]; w.ref_len = s[n_]; w.cand_off = res.cand_base[r]; w.ncand = res.ncand[r]; w.chunk = 0;
+            WinRec w = res.wins[r];
             if (w.ncand < 0 || (uint64_t)w.cand_off + (uint64_t)w.ncand > NC) w.ncand = -1;       // not searched (or its candidates did not fit)
+            valid[r] = w.ncand >= 0;
+            if (!valid[r]) w.ncand = 0;                               // stays out of the index: the replay searches it on demand
+            else { ++ns; nc += w.ncand; }
             C.wins[r] = w;
-            hashes[r] = coords_hash(d, 2 * n_);
         }
+        blk_searched[(size_t)c] = ns; blk_cands[(size_t)c] = nc;
     });
-    C.map.reserve(NR);
     int64_t searched = 0, cands = 0;
-    for (size_t r = 0; r < NR; ++r) {
-        if (C.wins[r].ncand < 0) { C.wins[r].ncand = 0; continue; }       // stays out of the index: the replay searches it on demand
-        C.map.insert(hashes[r], (int)r);
-        ++searched;
-        cands += C.wins[r].ncand;
-    }
-    slice_of_initial_.assign(R, 0);
-    {
-        std::lock_guard<std::mutex> lk(slice_mu_);
-        slices_ready_ = 1;
-    }
-    stats_.spec_slices = 1;
+    for (long c = 0; c < nblk; ++c) { searched += blk_searched[(size_t)c]; cands += blk_cands[(size_t)c]; }
+    C.map.build_parallel(hashes, valid, threads_);
+    std::lock_guard<std::mutex> lk(backend_mu_);           // (the statistics are shared with the replay's on-demand searches)
     stats_.spec_regions += searched;
     stats_.regions_searched += searched;
     stats_.windows_searched += searched;
@@ -1387,6 +1453,7 @@ bool Aligner::run() {
     set_initial_clusters();
     if (!prm_.anchors_only) {
         stats_.host_threads = threads_;
+        if (speculate_ && !initial_regions_.empty() && pipeline_ && !getenv("PB200_NO_DEVICE_RECURSION")) replay_prepare_async();
         if (speculate_ && !initial_regions_.empty() && pipeline_ && discover_on_device()) {
             // the engine followed the recursion itself (cuda/recursion.cuh): one published "slice" holds every predicted region
         } else if (speculate_ && !initial_regions_.empty()) {

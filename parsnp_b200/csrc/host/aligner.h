@@ -100,8 +100,9 @@ struct RegionPool {
     pod_vector<int64_t> coord;      // 2n per region: start[n], end[n] (resize leaves new rows uninitialised: filled by the caller)
     pod_vector<int64_t> slen;       // TRegion::slength
     int add(const int64_t* start, const int64_t* end);
-    inline const int64_t* start(int r) const { return &coord[(size_t)r * 2 * n]; }
-    inline const int64_t* end(int r) const { return &coord[(size_t)r * 2 * n + n]; }
+    const int64_t* ext_coord = nullptr;   // a read-only pool over somebody else's array (the engine's discovery result)
+    inline const int64_t* start(int r) const { return (ext_coord ? ext_coord : coord.data()) + (size_t)r * 2 * n; }
+    inline const int64_t* end(int r) const { return start(r) + n; }
     inline int size() const { return (int)slen.size(); }
 };
 struct MumPool {
@@ -109,6 +110,7 @@ struct MumPool {
     pod_vector<int64_t> start;      // (pod_vector: a parallel fill after resize() touches the new pages first)
     pod_vector<uint8_t> fwd;
 };
+struct ReplayCtx;
 struct AlignStats {
     int64_t anchors = 0, regions_searched = 0, spec_regions = 0, replay_misses = 0, spec_levels = 0,
             windows_searched = 0, candidates = 0, slow_queue_iters = 0, host_threads = 1;
@@ -128,7 +130,7 @@ struct AlignStats {
 class Aligner {
 public:
     Aligner(int n, const uint8_t* const* seq, const int64_t* len, const AlignParams& prm, SearchBackend* be);
-    ~Aligner() { if (spec_thread_.joinable()) spec_thread_.join(); }
+    ~Aligner();
     // returns false when no MUMs were found (reference: "NO MUMS FOUND", src/parsnp.cpp:3223-3229)
     bool run();
 
@@ -168,7 +170,7 @@ private:
     // (anchors and on-demand searches: the main thread; every speculation slice: the speculation thread); a published
     // instance is read-only.
     struct CacheEntry { int region; int64_t first_win; int nwin; };
-    struct WinRec { int64_t ref_start, ref_len; int64_t cand_off; int32_t ncand; int32_t chunk; };
+    typedef WindowRec WinRec;
     // open-addressing index hash(coords) -> cache entry
     struct CoordIndex {
         struct Slot { uint64_t h; int32_t v; int32_t pad; };      // hash and entry side by side: one cache line per probe
@@ -176,6 +178,8 @@ private:
         size_t count = 0;
         void insert(uint64_t hash, int value);
         void reserve(size_t entries);          // room for `entries` more without rehashing
+        // an EMPTY index filled from hashes[i] -> i for every i with valid[i], on `threads` threads (slots are claimed with a CAS)
+        void build_parallel(const std::vector<uint64_t>& hashes, const std::vector<uint8_t>& valid, int threads);
         template <class Pred> int find(uint64_t hash, Pred pred) const {
             if (s.empty()) return -1;
             const size_t mask = s.size() - 1;
@@ -217,6 +221,9 @@ private:
     // doWork as independent tasks (runs of consecutive initial regions) on several threads, exact: replay.cpp.
     // Returns false when the preconditions do not hold (nothing touched): the caller runs process_queue_exact.
     bool do_work_parallel();
+    ReplayCtx* replay_prepare();         // nullptr = the preconditions do not hold
+    bool replay_run(ReplayCtx& X);
+    void replay_prepare_async();
     void set_replay_threads(int t) { replay_threads_ = t; }
     // doWork's loop over a queue of regions living in `rp`, in the exact reference order
     void process_queue_exact(const std::vector<int>& initial, RegionPool& rp, std::vector<BitRow>& layout, MumPool& mp,
@@ -230,6 +237,7 @@ private:
     void speculate_slice(CandCache& C, const RegionPool& src, const std::vector<int>& initial, World& spec);
     void speculation_thread_main();
     bool discover_on_device();           // the engine follows the recursion itself (SearchBackend::discover_recursion)
+    bool discover_slice(int k);
     const CandCache* wait_slice(int slice);
     void wait_slice_quiet(int slice);
     void do_work_exact();
@@ -266,6 +274,9 @@ private:
     std::vector<int> slice_of_initial_;                     // slice of initial_regions_[i]
     RegionPool frozen_rp_;                                  // the initial regions' coordinates as the speculation thread sees them
     World spec_world_;                                      // scratch copy of mumlayout for the speculation
+    std::shared_ptr<const std::vector<int32_t>> disc_tab_;  // device discovery: minsize table, initial coordinates, slice bounds
+    pod_vector<int64_t> disc_coords_;
+    std::vector<size_t> disc_begin_;
     std::thread spec_thread_;
     std::mutex slice_mu_, backend_mu_;
     std::condition_variable slice_cv_;
@@ -273,6 +284,10 @@ private:
     std::exception_ptr spec_error_;
     bool pipeline_ = true;
     int replay_threads_ = 0;                                // 0 = threads_
+    ReplayCtx* replay_ctx_ = nullptr;
+    std::thread replay_prep_thread_;
+    std::exception_ptr replay_prep_error_;
+    bool replay_prepared_ = false;
 
     std::vector<ClusterRec> clusters_;
     int threads_ = 1;

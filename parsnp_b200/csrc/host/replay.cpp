@@ -100,6 +100,8 @@ struct ReplayCtx {
     std::exception_ptr error;
     int64_t restarts = 0;
     unsigned jitter = 0;
+    int nw = 1;                                 // workers
+    double t_setup = 0;
     std::vector<int> order;                     // indices into A.initial_regions_, ascending start[0]
     std::vector<int64_t> keys;                  // their start[0], same order
     // GAPS: maximal runs of initial regions whose spans overlap (the right side of anchor i and the left side of anchor i+1 are
@@ -634,20 +636,46 @@ void Aligner::wait_slice_quiet(int slice) {
     slice_cv_.wait(lk, [&] { return slices_ready_ > slice; });
 }
 
+Aligner::~Aligner() {
+    if (spec_thread_.joinable()) spec_thread_.join();
+    if (replay_prep_thread_.joinable()) replay_prep_thread_.join();
+    delete replay_ctx_;
+}
+
+// The task structure depends on the anchors only: with the engine following the recursion on the device, it is built on a
+// second thread while the host would otherwise wait for the GPU.
+void Aligner::replay_prepare_async() {
+    replay_prep_thread_ = std::thread([this] {
+        try { replay_ctx_ = replay_prepare(); } catch (...) { replay_prep_error_ = std::current_exception(); }
+        replay_prepared_ = true;
+    });
+}
+
 bool Aligner::do_work_parallel() {
+    if (replay_prep_thread_.joinable()) replay_prep_thread_.join();
+    if (replay_prep_error_) std::rethrow_exception(replay_prep_error_);
+    if (!replay_prepared_) { replay_ctx_ = replay_prepare(); replay_prepared_ = true; }
+    if (!replay_ctx_) return false;
+    std::unique_ptr<ReplayCtx> holder(replay_ctx_);
+    replay_ctx_ = nullptr;
+    return replay_run(*holder);
+}
+
+ReplayCtx* Aligner::replay_prepare() {
     int W = replay_threads_ > 0 ? replay_threads_ : threads_;
     if (const char* ew = getenv("PB200_REPLAY_THREADS")) W = std::max(1, atoi(ew));
     const size_t R = initial_regions_.size();
     const char* et = getenv("PB200_REPLAY_TASK");               // initial regions per task (tests: 1 = one gap per task)
     const char* em = getenv("PB200_REPLAY_MODE");               // "seq" = never, "par" = also for tiny inputs / one worker
     const bool force = em && std::strcmp(em, "par") == 0;
-    if (em && std::strcmp(em, "seq") == 0) return false;
+    if (em && std::strcmp(em, "seq") == 0) return nullptr;
     const bool dbg = getenv("PB200_REPLAY_DEBUG") != nullptr;
     if (dbg) fprintf(stderr, "[pb200 replay] W %d R %zu trace %d pipeline %d\n", W, R, (int)trace_on_, (int)pipeline_);
-    if (trace_on_ || !pipeline_ || R == 0) return false;
-    if (!force && (W < 2 || R < 512)) return false;
+    if (trace_on_ || !pipeline_ || R == 0) return nullptr;
+    if (!force && (W < 2 || R < 512)) return nullptr;
     const double tsetup0 = now_s();
-    ReplayCtx X(*this);
+    std::unique_ptr<ReplayCtx> XP(new ReplayCtx(*this));
+    ReplayCtx& X = *XP;
     if (const char* ej = getenv("PB200_REPLAY_JITTER")) X.jitter = (unsigned)std::max(0, atoi(ej));
     // P1: the keys of the initial regions are distinct, so the reference's first sort has one possible outcome.  (Push order is
     // NOT ascending: the right side of anchor i starts one base behind the left side of anchor i+1 - the same gap twice.)
@@ -679,7 +707,7 @@ bool Aligner::do_work_parallel() {
     for (size_t i = 1; i < R; ++i)
         if (!(X.keys[i - 1] < X.keys[i])) {
             if (dbg) fprintf(stderr, "[pb200 replay] two initial regions tie on start[0]: sequential\n");
-            return false;
+            return nullptr;
         }
     size_t pos0 = 0;
     while (pos0 < R && X.order[pos0] != 0) ++pos0;
@@ -705,7 +733,7 @@ bool Aligner::do_work_parallel() {
                 }
             }
         });
-        if (bad.load()) return false;
+        if (bad.load()) return nullptr;
         parallel_chunks(threads_, ((long)R + per_blk - 1) / per_blk, [&](long c) {
             for (size_t p = std::max<size_t>(1, (size_t)c * per_blk); p < std::min(R, (size_t)(c + 1) * per_blk); ++p) {
                 bool ok = true;
@@ -718,7 +746,7 @@ bool Aligner::do_work_parallel() {
         });
         if (bad.load()) {
             if (dbg) fprintf(stderr, "[pb200 replay] the spans of the initial regions do not ascend in every genome: sequential\n");
-            return false;
+            return nullptr;
         }
     }
     // gaps: runs of regions between cuts (the two regions of one anchor gap, and whatever else overlaps, stay together);
@@ -757,12 +785,12 @@ bool Aligner::do_work_parallel() {
     });
     if (bad.load()) {
         if (dbg) fprintf(stderr, "[pb200 replay] gaps not in order in some genome: sequential\n");
-        return false;
+        return nullptr;
     }
     // the reference's first pop is the first region PUSHED (see run_task): it must belong to the first gap
     if ((int)pos0 >= gcut[1]) {
         if (dbg) fprintf(stderr, "[pb200 replay] the first region pushed is not in the first gap: sequential\n");
-        return false;
+        return nullptr;
     }
     std::vector<int> tcut(1, 0);                 // task k = gaps [tcut[k], tcut[k+1])
     {
@@ -776,7 +804,7 @@ bool Aligner::do_work_parallel() {
     X.ntasks = (int)tcut.size() - 1;
     if (!force && X.ntasks < 2 * W) {
         if (dbg) fprintf(stderr, "[pb200 replay] only %d independent tasks for %d workers: sequential\n", X.ntasks, W);
-        return false;
+        return nullptr;
     }
     X.tasks.reset(new ReplayTask[(size_t)X.ntasks]);
     X.hlo.assign((size_t)n_ * X.ntasks, 0);
@@ -794,17 +822,22 @@ bool Aligner::do_work_parallel() {
     }
     X.S.resize((size_t)n_);
     parallel_chunks(threads_, (long)n_, [&](long g) { X.S[(size_t)g] = truth_.layout[(size_t)g]; });
-    const size_t anchors_in_pool = mp_.mums.size();
+    X.nw = std::max(1, std::min(W, X.ntasks));
+    X.log_slab.reset(new ReplayTask::FRead[(size_t)X.ntasks * ReplayTask::LOG_CAP]);
+    for (int k = 0; k < X.ntasks; ++k) X.tasks[k].flog = X.log_slab.get() + (size_t)k * ReplayTask::LOG_CAP;
+    X.t_setup = now_s() - tsetup0;
+    return XP.release();
+}
 
-    const int nw = std::max(1, std::min(W, X.ntasks));
+bool Aligner::replay_run(ReplayCtx& X) {
+    const size_t R = initial_regions_.size();
+    const int nw = X.nw;
     X.wmp.resize((size_t)nw);
     X.wrp.resize((size_t)nw);
     {
         const size_t est = (size_t)stats_.anchors * 4 / (size_t)nw + 1024;       // (about 3 recursion MUMs per anchor on divergent genomes)
         for (auto& m : X.wmp) { m.mums.reserve(est); m.start.reserve(est * (size_t)n_); m.fwd.reserve(est * (size_t)n_); }
     }
-    X.log_slab.reset(new ReplayTask::FRead[(size_t)X.ntasks * ReplayTask::LOG_CAP]);
-    for (int k = 0; k < X.ntasks; ++k) X.tasks[k].flog = X.log_slab.get() + (size_t)k * ReplayTask::LOG_CAP;
     const double tr0 = now_s();
     // (the process-wide pool of sleeping threads: no thread is created per alignment.  If the pool is busy - the host's own
     //  level-by-level speculation uses it when the engine does not follow the recursion itself - the workers run one after the
@@ -818,7 +851,7 @@ bool Aligner::do_work_parallel() {
         parallel_chunks(nw, (long)nw, [&X](long w) { X.worker((int)w); });
     }
     if (X.error) std::rethrow_exception(X.error);
-    if (getenv("PB200_PROFILE_HOST")) fprintf(stderr, "[pb200 replay ms] setup %.2f tasks %.2f (%d workers, %d tasks, %d gaps)\n", (tr0 - tsetup0) * 1e3, (now_s() - tr0) * 1e3, nw, X.ntasks, X.ngaps);
+    if (getenv("PB200_PROFILE_HOST")) fprintf(stderr, "[pb200 replay ms] setup %.2f tasks %.2f (%d workers, %d tasks, %d gaps)\n", X.t_setup * 1e3, (now_s() - tr0) * 1e3, nw, X.ntasks, X.ngaps);
 
     // ---- the finished tasks' MUMs into the pools, task after task = the reference's push order
     const double tm0 = now_s();
@@ -896,7 +929,6 @@ bool Aligner::do_work_parallel() {
         // a tie inside task F: rebuild the layout as the reference has it when it reaches that task (anchors + the MUMs of
         // everything before), then its own loop from there
         stats_.replay_fallback = 1;
-        (void)anchors_in_pool;
         parallel_chunks(threads_, (long)n_, [&](long g) {
             BitRow& row = truth_.layout[(size_t)g];
             row.init(len_[(size_t)g] + 1);
