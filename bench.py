@@ -182,6 +182,7 @@ def main():
                     help="configs1 = G_indep(L, 8 q) [default, BASELINE configs[1]]; pop = G_pop(L, --nq) [configs[2] shape]; "
                          "c4 = configs[3] shape: G_pop(--length [50 Mbp], --nq [64]) as 10 contigs, queries N-padded at contig breaks")
     ap.add_argument("--nq", type=int, default=NQ)
+    ap.add_argument("--no-pin", action="store_true", help="N>1: leave the ranks' host threads unpinned")
     ap.add_argument("--sharded", action="store_true", help="N>1: one alignment sharded over the ranks instead of one partition per rank")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -191,6 +192,20 @@ def main():
         run_reference(args, rank, world)
         return 0
 
+    # one process per GPU: every rank keeps its host threads (the library's pool inherits the mask) on its own share of the cores,
+    # a contiguous block in local-rank order - GPUs and cores of one socket stay together on the usual two-socket boxes
+    pinned_cores = None
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+    if local_world > 1 and not args.no_pin and hasattr(os, "sched_setaffinity"):
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // local_world)
+            mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+            os.sched_setaffinity(0, mine)
+            os.environ.setdefault("PB200_HOST_THREADS", str(len(mine)))
+            pinned_cores = [mine[0], mine[-1]]
+        except OSError:
+            pass
     import torch
     from parsnp_b200 import api, synth
     if not torch.cuda.is_available() or not api.cuda_available():
@@ -269,7 +284,12 @@ def main():
         if it > 0:
             e2e_ms.append(e0.elapsed_time(e1))
     t_sum = torch.tensor([sum(step_ms), sum(e2e_ms) / len(e2e_ms) * args.steps], dtype=torch.float64, device="cuda")
+    per_rank = None
     if dist is not None:
+        mine = {"rank": rank, "ms_per_step": sum(step_ms) / args.steps, "t_total_ms": res["stats"]["t_total"] * 1e3,
+                "t_replay_ms": res["stats"]["t_replay"] * 1e3, "host_threads": int(res["stats"]["host_threads"]), "cores": pinned_cores}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
         dist.all_reduce(t_sum, op=dist.ReduceOp.MAX)
     tot_ms, tot_e2e_ms = t_sum.tolist()
     ms_per_step = tot_ms / args.steps
@@ -384,6 +404,8 @@ def main():
                                                   % (L_CPU_SAMPLE, sec, b, os.cpu_count() or 1, gold.get("reference_mumlcb_seconds"))}
             except Exception as ex:  # the oracle binary is test infrastructure; absence must not break the bench
                 line["cpu_baseline"] = {"value": None, "unit": "bases/s", "cores": 1, "kind": "reference", "sample": "unavailable: %s" % ex}
+    if per_rank is not None:
+        line["per_rank"] = per_rank
     if rank == 0:
         emit(line)
     G.close()

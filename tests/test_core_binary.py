@@ -232,3 +232,41 @@ def test_binary_xmfa_end_to_end(tmp_path, kind):
     assert (out / "parsnpAligner.xmfa").read_bytes() == open(xmfa, "rb").read()
     # the statistics log the Python driver parses (parsnp:1530-1536), line for line
     assert _log_lines(str(out / "parsnpAligner.log")) == _log_lines(os.path.join(r["outdir"], "parsnpAligner.log"))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref not built")
+def test_concurrent_partitions_match_reference(tmp_path):
+    """BASELINE configs[4] at reduced size, the way the Python driver runs partition mode (parsnp:1553-1615): one genome pool,
+    sorted + random.Random(42).shuffle, consecutive slices, one parsnp_core process per partition, min(threads, partitions) of
+    them AT THE SAME TIME with nothing but the ini differing - so the binary has to choose its GPU by itself (advisory lock per
+    device, else pid % devices; every process shares GPU 0 on a one-GPU box).  Every partition's parsnpAligner.xmfa must equal the
+    reference binary's byte for byte, and the cwd must hold the (empty) allmums.out the reference leaves there."""
+    import random
+    from oracle import runner
+    from parsnp_b200 import synth
+    NPART, PER, L = 10, 6, 120_000
+    g = synth.g_pop(L, NPART * PER, 0.01, 23)
+    ref, qs = synth.write_dataset(str(tmp_path / "pool"), g)
+    names = sorted(qs)
+    random.Random(42).shuffle(names)
+    parts = [names[i * PER:(i + 1) * PER] for i in range(NPART)]
+    procs, want = [], []
+    lockdir = tmp_path / "locks"
+    lockdir.mkdir()
+    for i, p in enumerate(parts):
+        d = tmp_path / ("part%d" % i)
+        (d / "out").mkdir(parents=True)
+        ini = runner.write_ini(str(d / "run.ini"), ref, p, str(d / "out"), cores=2)
+        procs.append((d, subprocess.Popen([EXE, ini], cwd=str(d), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                                          env=dict(os.environ, PB200_LOCK_DIR=str(lockdir), PB200_HOST_THREADS="2"))))
+    for i, p in enumerate(parts):                       # the reference meanwhile, on the CPU
+        r = runner.run_ref(ref, p, str(tmp_path / ("ref%d" % i)), dump=False, cores=2)
+        assert r["returncode"] == 0
+        want.append(open(os.path.join(r["outdir"], "parsnpAligner.xmfa"), "rb").read())
+    for i, (d, pr) in enumerate(procs):
+        out, err = pr.communicate(timeout=600)
+        assert pr.returncode == 0, err[-2000:]
+        got = (d / "out" / "parsnpAligner.xmfa").read_bytes()
+        assert got == want[i], "partition %d: XMFA differs from the reference" % i
+        assert (d / "allmums.out").exists() and (d / "allmums.out").stat().st_size == 0
