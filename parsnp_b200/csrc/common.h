@@ -107,6 +107,7 @@ struct RecursionRequest {
     const int64_t* coords = nullptr;     // initial regions: start[n] then end[n] each
     int nregions = 0;
     bool upload_layout = true;           // false: keep the scratch layout of the previous call (next slice of the same alignment)
+    bool resume = false;                 // true: collect the run that SearchBackend::anchor_stage started (nothing else is read)
     const uint64_t* const* layout = nullptr;   // mumlayout after the anchors: per genome its words ...
     const int64_t* layout_words = nullptr;     // ... and their number (len + 1 bits incl. the sentinel)
     int q = 30;                          // ini [LCB] q
@@ -129,6 +130,35 @@ struct RecursionResult {
     int64_t levels = 0, deferred = 0, dropped = 0, searched = 0;
 };
 
+// The anchor stage on the device (cuda/anchors.cuh): candidates of the whole-genome region -> accepted anchors, mumlayout and
+// the regions between the anchors, with the recursion (above) started from them right away.
+struct AnchorRequest {
+    int n = 0;
+    const WindowTask* tasks = nullptr;   // the reference windows of the whole-genome region (src/parsnp.cpp:1519-1547)
+    int ntasks = 0;
+    const int64_t* coords = nullptr;     // the task coordinate pool: q_start[n-1] = 0, q_len[n-1] = genome lengths
+    const int64_t* layout_words = nullptr;     // words per genome row of mumlayout (len + 1 bits incl. the sentinel)
+    int q = 30;
+    int64_t p = 15000000;
+    const int32_t* minsize_tab = nullptr;      // for the recursion that follows (RecursionRequest)
+    int minsize_n = 0;
+    bool follow_recursion = true;        // false: ini anchorsonly
+};
+struct AnchorResult {
+    // status 1: everything below is valid (views into the backend's pinned memory until its next call), the recursion is
+    //           running on the device and discover_recursion(resume) collects it
+    // status 2: the candidates overlap or are not collinear: `cands` holds them in search() format, the caller accepts them
+    int status = 0;
+    size_t ncand = 0, nanchors = 0, nregions = 0;
+    const int32_t* a_start = nullptr;    // [nanchors * n]
+    const int32_t* a_lon = nullptr;      // [nanchors]
+    const uint8_t* a_fwd = nullptr;      // [nanchors * n]
+    const int32_t* r_coords = nullptr;   // [nregions * 2n]: start[n] then LENGTH[n], in push order
+    const uint64_t* layout = nullptr;    // all rows of mumlayout after the anchors, row g at layout_off[g] words
+    std::vector<int64_t> layout_off;
+    CandBatch cands;
+};
+
 // Search engine interface. The product implementation is CUDA-only (cuda/engine.cu); tests may link the
 // CPU specification from oracle/ behind the same interface to exercise the host logic without a GPU.
 class SearchBackend {
@@ -141,6 +171,9 @@ public:
     // optional: follow the recursion on the device; false = not supported for this input (the host then discovers the regions
     // level by level through search())
     virtual bool discover_recursion(const RecursionRequest&, RecursionResult&) { return false; }
+    // optional: the anchor stage (search of the whole-genome region + accept + regions between the anchors) on the device.
+    // Returns AnchorResult::status (0 = not supported: the caller goes through search())
+    virtual int anchor_stage(const AnchorRequest&, AnchorResult&) { return 0; }
 };
 
 }  // namespace pb200

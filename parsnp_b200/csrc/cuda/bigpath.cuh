@@ -973,6 +973,35 @@ public:
     }
     // stage 4: per candidate, strand flag and start of every LOCAL query; initEP (device, n ints) = Master.EP before the
     // first local query, or null.  Appends to the host vectors.
+    // stage 4 on the device only: the candidates of the window stay where they are.  Pointers valid until the next window.
+    struct DeviceCands { uint32_t ncand = 0; const uint32_t* k = nullptr; const int32_t* lon = nullptr; const int32_t* sp = nullptr; const uint8_t* fwd = nullptr; };
+    DeviceCands pass2_device(const int32_t* initEP, cudaStream_t st) {
+        const uint32_t ncand = cur_ncand_;
+        const int nq = cur_nq_, n = cur_n_;
+        DeviceCands dc;
+        dc.ncand = ncand;
+        if (tm) tm->start(GpuTimers::T_SCAN_PASS2, st);
+        if (ncand) {
+            int32_t* d_lon = olon_.ensure(ncand, false, st);
+            int32_t* d_sp = osp_.ensure((size_t)ncand * std::max(nq, 1), false, st);
+            uint8_t* d_fwd = ofwd_.ensure((size_t)ncand * std::max(nq, 1), false, st);
+            if (nq) {
+                int4* tmp = p2tmp_.ensure((size_t)ncand * nq, false, st);
+                const long long tot = (long long)ncand * nq;
+                pb200::launch(pass2a_kernel, (unsigned)((tot + 127) / 128), 128, 0, st, ck_.get(), (int)ncand, evl_.get(), states_.get(),
+                              seglo_.get(), bounds_.get(), ntiles1_, nq, tmp);
+                pb200::launch(pass2b_kernel, (ncand + 127) / 128, 128, 0, st, ck_.get(), (int)ncand, tmp, nq, n, mep_.get(), initEP, d_lon, d_sp,
+                              d_fwd);
+            } else {
+                pb200::launch(pass2b_kernel, (ncand + 127) / 128, 128, 0, st, ck_.get(), (int)ncand, (const int4*)nullptr, 0, n, mep_.get(),
+                              initEP, d_lon, d_sp, d_fwd);
+            }
+            dc.k = ck_.get(); dc.lon = d_lon; dc.sp = d_sp; dc.fwd = d_fwd;
+        }
+        if (tm) tm->stop(GpuTimers::T_SCAN_PASS2, st);
+        PB_CUDA(cudaGetLastError());
+        return dc;
+    }
     void pass2(const int32_t* initEP, cudaStream_t st, std::vector<int32_t>& out_k, std::vector<int32_t>& out_lon,
                std::vector<int32_t>& out_sp, std::vector<uint8_t>& out_fwd) {
         const uint32_t ncand = cur_ncand_;

@@ -19,6 +19,7 @@
 #include "bigpath.cuh"
 #include "smallpath.cuh"
 #include "recursion.cuh"
+#include "anchors.cuh"
 
 namespace pb200 {
 
@@ -44,6 +45,54 @@ __global__ void prefix_min_kernel(const int32_t* __restrict__ gathered, int worl
     initEP[k] = m;
     MUP[k] = 0;
     MEP[k] = m;
+}
+
+// anchors.cuh kernels with the number of anchors read on the device (launched for the number of candidates)
+__global__ void anchor_push_flags_bounded(int n, int q, const uint32_t* __restrict__ nanchors, unsigned int ncand, const int32_t* __restrict__ REG,
+                                          const int32_t* __restrict__ SL, uint32_t* __restrict__ slot) {
+    const unsigned int x = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (x >= ncand) return;                                 // (slot holds 2 entries per candidate)
+    const unsigned int na = *nanchors;
+    if (x >= na) { if (lane == 0) { slot[2 * x] = 0; slot[2 * x + 1] = 0; } return; }
+    const int32_t* me = REG + (size_t)x * 4 * n;
+    int d_prev = 0, d_own = 0;
+    for (int i = lane; i < 2 * n; i += 32) {
+        if (x > 0 && me[i] != (me - 4 * n)[2 * n + i]) d_prev = 1;
+        if (me[i] != me[2 * n + i]) d_own = 1;
+    }
+    d_prev = __any_sync(0xffffffffu, d_prev);
+    d_own = __any_sync(0xffffffffu, d_own);
+    if (lane == 0) {
+        slot[2 * x] = (SL[2 * x] > q && (x == 0 || d_prev)) ? 1u : 0u;
+        slot[2 * x + 1] = (SL[2 * x + 1] > q && d_own) ? 1u : 0u;
+    }
+}
+__global__ void anchor_push_bounded(int n, const uint32_t* __restrict__ nanchors, const int32_t* __restrict__ REG, const int32_t* __restrict__ SL,
+                                    const uint32_t* __restrict__ slot, const uint32_t* __restrict__ pos, rec::Store St, uint8_t* __restrict__ pair,
+                                    unsigned int cap) {
+    const unsigned int x = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const unsigned int na = *nanchors;
+    if (x >= na) return;
+    const int32_t* me = REG + (size_t)x * 4 * n;
+    for (int side = 0; side < 2; ++side) {
+        if (!slot[2 * x + side]) continue;
+        const unsigned int id = pos[2 * x + side];
+        if (id >= cap) continue;
+        const int32_t* S = me + 2 * n * side;
+        int32_t* c = St.coords + (size_t)id * 2 * n;
+        for (int g = lane; g < n; g += 32) { c[g] = S[g]; c[n + g] = S[n + g] - S[g]; }
+        if (lane == 0) {
+            int p = 0;
+            if (side == 1 && x + 1 < na && slot[2 * x + 2]) {
+                const int32_t* nx = me + 4 * n;                 // left side of the next anchor
+                p = nx[0] == S[0] - 1 && nx[n] == S[n];
+            }
+            pair[id] = (uint8_t)p;
+        }
+    }
+    (void)SL;
 }
 
 class CudaEngine : public SearchBackend, public StagedWindowEngine {
@@ -80,6 +129,7 @@ public:
     ~CudaEngine() override {
         cudaSetDevice(device_);
         if (st_) { cudaStreamSynchronize(st_); cudaStreamDestroy(st_); }
+        if (st2_) { cudaStreamSynchronize(st2_); cudaStreamDestroy(st2_); }
     }
 
     void set_genomes(int n, const uint8_t* const* seq, const int64_t* len) override {
@@ -208,36 +258,51 @@ public:
         host_gather_s += wall_s() - th3;
     }
 
-    // ---- the recursion followed on the device (cuda/recursion.cuh): one upload, a fixed number of levels per round enqueued
-    // without synchronising, one download.  false = this input is left to the host's level-by-level discovery.
-    bool discover_recursion(const RecursionRequest& rq, RecursionResult& out) override {
-        PB_CUDA(cudaSetDevice(device_));
-        const int n = n_, nq = n - 1;
-        if (rq.n != n || nq < 1 || n > 224 || rq.q < 0 || rq.nregions <= 0 || force_big_ || getenv("PB200_NO_DEVICE_RECURSION")) return false;
+    // ---- the recursion followed on the device (cuda/recursion.cuh): one upload (or none: anchor_stage), a fixed number of
+    // levels per round enqueued without synchronising, one download.  false = left to the host's level-by-level discovery.
+    struct RecRun {
+        bool active = false;
+        size_t cap = 0, cand_cap = 0;
+        rec::Params P; rec::Store St; rec::Queues Q;
+        small::ClassCfg cfg[rec::NCLASS];
+        int ctas[rec::NCLASS] = {0, 0, 0};
+        int gpl = 1, level = 0;
+        unsigned int* ctr = nullptr;
+        unsigned long long* d_cnt = nullptr;
+        int32_t* d_k = nullptr; int32_t* d_lon = nullptr; int32_t* d_sp = nullptr; uint8_t* d_fw = nullptr;
+        double t0 = 0;
+    } rr_;
+    typedef void (*RecKernel)(const uint8_t*, const int64_t*, const int64_t*, const int64_t*, rec::Params, rec::Store, rec::Queues, int, int, small::ClassCfg,
+                              unsigned long long*, unsigned long long, int32_t*, int32_t*, int32_t*, uint8_t*);
+    RecKernel rec_kernel() const {
+        return rr_.gpl == 1 ? rec::recursion_level_kernel<1> : (rr_.gpl == 2 ? rec::recursion_level_kernel<2> : (rr_.gpl == 4 ? rec::recursion_level_kernel<4> : rec::recursion_level_kernel<7>));
+    }
+    bool rec_supported(int n, int q) const {
+        if (n != n_ || n < 2 || n > 224 || q < 0 || force_big_ || getenv("PB200_NO_DEVICE_RECURSION")) return false;
         for (int g = 0; g < n; ++g) if (len_[g] >= ((int64_t)1 << 31) - 64) return false;
-        const double t0 = wall_s();
-        const size_t R = (size_t)rq.nregions;
-        const size_t cap = R * 4 + 65536;
-        // ---- scratch mumlayout
+        return true;
+    }
+    // buffers and parameters for a run over at most R_est initial regions; the scratch layout is allocated, not filled
+    void rec_setup(size_t R_est, const int64_t* layout_words, const int32_t* tab, int tabn, int q, int64_t p) {
+        const int n = n_, nq = n - 1;
+        rr_ = RecRun();
+        rr_.t0 = wall_s();
+        const size_t cap = R_est * 4 + 65536;
+        rr_.cap = cap;
         std::vector<int64_t> bit_off((size_t)n + 1, 0);
-        for (int g = 0; g < n; ++g) bit_off[(size_t)g + 1] = bit_off[(size_t)g] + rq.layout_words[g];
-        if (!rq.upload_layout && (r_bits_words_ != bit_off[(size_t)n] || !r_bits_.get())) return false;
+        for (int g = 0; g < n; ++g) bit_off[(size_t)g + 1] = bit_off[(size_t)g] + layout_words[g];
         unsigned long long* d_bits = r_bits_.ensure((size_t)bit_off[(size_t)n] + 8, false, st_);
-        if (rq.upload_layout) {
-            for (int g = 0; g < n; ++g)
-                PB_CUDA(cudaMemcpyAsync(d_bits + bit_off[(size_t)g], rq.layout[g], (size_t)rq.layout_words[g] * 8, cudaMemcpyHostToDevice, st_));
-            r_bits_words_ = bit_off[(size_t)n];
-        }
+        r_bits_words_ = bit_off[(size_t)n];
+        r_bit_off_host_ = bit_off;
         int64_t* d_bit_off = r_bitoff_.ensure((size_t)n + 1, false, st_);
         int64_t* h_bit_off = r_pin_bitoff_.ensure((size_t)n + 1);
         std::memcpy(h_bit_off, bit_off.data(), ((size_t)n + 1) * 8);
         PB_CUDA(cudaMemcpyAsync(d_bit_off, h_bit_off, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st_));
-        int32_t* d_tab = r_tab_.ensure((size_t)std::max(rq.minsize_n, 1), false, st_);
-        int32_t* h_tab = r_pin_tab_.ensure((size_t)std::max(rq.minsize_n, 1));
-        std::memcpy(h_tab, rq.minsize_tab, (size_t)rq.minsize_n * 4);
-        PB_CUDA(cudaMemcpyAsync(d_tab, h_tab, (size_t)rq.minsize_n * 4, cudaMemcpyHostToDevice, st_));
-        // ---- region store + work lists
-        rec::Store St;
+        int32_t* d_tab = r_tab_.ensure((size_t)std::max(tabn, 1), false, st_);
+        int32_t* h_tab = r_pin_tab_.ensure((size_t)std::max(tabn, 1));
+        std::memcpy(h_tab, tab, (size_t)tabn * 4);
+        PB_CUDA(cudaMemcpyAsync(d_tab, h_tab, (size_t)tabn * 4, cudaMemcpyHostToDevice, st_));
+        rec::Store& St = rr_.St;
         St.coords = r_coords_.ensure(cap * 2 * (size_t)n, false, st_);
         St.slen = r_slen_.ensure(cap, false, st_);
         St.minsize = r_minsize_.ensure(cap, false, st_);
@@ -246,11 +311,83 @@ public:
         int32_t* lists = r_lists_.ensure(cap * (2 * rec::NCLASS + 1), false, st_);
         unsigned int* ctr = r_ctr_.ensure(32, false, st_);
         PB_CUDA(cudaMemsetAsync(ctr, 0, 32 * sizeof(unsigned int), st_));
-        rec::Queues Q;
+        rr_.ctr = ctr;
+        rec::Queues& Q = rr_.Q;
         for (int h = 0; h < 2; ++h) for (int c = 0; c < rec::NCLASS; ++c) Q.list[h][c] = lists + cap * (size_t)(h * rec::NCLASS + c);
         Q.deferred = lists + cap * (size_t)(2 * rec::NCLASS);
         Q.count = ctr; Q.taken = ctr + 8; Q.nregions = ctr + 16; Q.ndeferred = ctr + 17; Q.dropped = ctr + 18;
-        Q.cap = (unsigned int)std::min<size_t>(cap, 0x7fffffffu);
+        Q.cap = (unsigned int)std::min<size_t>(cap, 0x1fffffffu);
+        r_pairflag_ = r_pair_.ensure(cap + 16, false, st_);
+        // candidate arrays: sized from what earlier alignments of this process needed
+        size_t cand_cap = std::max<size_t>(r_cand_hint_, R_est * s_cand_per_region_x16_.load() / 16 + 65536);
+        const size_t cap_limit = std::max<size_t>((size_t)1 << 16, ((size_t)4 << 30) / (size_t)(8 + 5 * nq));       // <= 4 GiB of candidate arrays
+        cand_cap = std::min(cand_cap, cap_limit);
+        rr_.cand_cap = cand_cap;
+        rr_.d_cnt = d_candcnt_.ensure(1, false, st_);
+        PB_CUDA(cudaMemsetAsync(rr_.d_cnt, 0, 8, st_));
+        rr_.d_k = d_ck_.ensure(cand_cap, false, st_);
+        rr_.d_lon = d_clon_.ensure(cand_cap, false, st_);
+        rr_.d_sp = d_csp_.ensure(cand_cap * (size_t)nq, false, st_);
+        rr_.d_fw = d_cfwd_.ensure(cand_cap * (size_t)nq, false, st_);
+        rec::Params& P = rr_.P;
+        P.n = n; P.q = q; P.p = p; P.minsize_tab = d_tab; P.minsize_n = tabn; P.bit_off = d_bit_off; P.bits = d_bits;
+        for (int c = 0; c < rec::NCLASS; ++c) {
+            rr_.cfg[c] = classes_[c];
+            rr_.cfg[c].ev_cap += 4 * nq;
+            if (rr_.cfg[c].ev_cap > 60000) rr_.cfg[c].ev_cap = 60000;
+            P.n_cap[c] = rr_.cfg[c].n_cap; P.m_cap[c] = rr_.cfg[c].m_cap;
+        }
+        rr_.gpl = n <= 32 ? 1 : (n <= 64 ? 2 : (n <= 128 ? 4 : 7));
+        RecKernel kern = rec_kernel();
+        if (!r_attr_set_[rr_.gpl]) {
+            PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            r_attr_set_[rr_.gpl] = true;
+        }
+        for (int c = 0; c < rec::NCLASS; ++c) {
+            int per_sm = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, rr_.cfg[c].threads, rr_.cfg[c].smem_bytes(nq)) != cudaSuccess || per_sm < 1) per_sm = 1;
+            rr_.ctas[c] = sm_count_ * per_sm;
+        }
+        rr_.level = 0;
+        rr_.active = true;
+    }
+    // level 0 lists from the regions in the store (their number is read on the device), then one round of levels
+    void rec_seed(size_t R_upper) {
+        pb200::launch(rec::seed_lists_kernel, (unsigned)((R_upper + 255) / 256), 256, 0, st_, rr_.P, rr_.St, rr_.Q, (const unsigned int*)rr_.Q.nregions,
+                      (const uint8_t*)r_pairflag_);
+    }
+    void rec_launch_round() {
+        const int nq = n_ - 1;
+        RecKernel kern = rec_kernel();
+        for (int l = 0; l < 8; ++l, ++rr_.level) {
+            for (int c = 0; c < rec::NCLASS; ++c) {
+                timers.start(GpuTimers::T_SMALL + c, st_);
+                pb200::launch(kern, rr_.ctas[c], rr_.cfg[c].threads, rr_.cfg[c].smem_bytes(nq), st_, text_.get(), gmeta_.get(), gmeta_.get() + n_, gmeta_.get() + 2 * n_,
+                              rr_.P, rr_.St, rr_.Q, rr_.level, c, rr_.cfg[c], rr_.d_cnt, (unsigned long long)rr_.cand_cap, rr_.d_k, rr_.d_lon, rr_.d_sp, rr_.d_fw);
+                timers.stop(GpuTimers::T_SMALL + c, st_);
+            }
+            pb200::launch(rec::level_advance_kernel, 1, 32, 0, st_, rr_.Q, rr_.level);
+        }
+        PB_CUDA(cudaGetLastError());
+    }
+    bool discover_recursion(const RecursionRequest& rq, RecursionResult& out) override {
+        PB_CUDA(cudaSetDevice(device_));
+        const int n = n_, nq = n - 1;
+        if (rq.resume) {
+            if (!rr_.active) return false;                  // (anchor_stage did not start a run)
+            return rec_finish(out);
+        }
+        if (!rec_supported(rq.n, rq.q) || rq.nregions <= 0) return false;
+        const size_t R = (size_t)rq.nregions;
+        if (!rq.upload_layout) {
+            int64_t words = 0;
+            for (int g = 0; g < n; ++g) words += rq.layout_words[g];
+            if (r_bits_words_ != words || !r_bits_.get()) return false;
+        }
+        rec_setup(R, rq.layout_words, rq.minsize_tab, rq.minsize_n, rq.q, rq.p);
+        if (rq.upload_layout)
+            for (int g = 0; g < n; ++g)
+                PB_CUDA(cudaMemcpyAsync(rr_.P.bits + r_bit_off_host_[(size_t)g], rq.layout[g], (size_t)rq.layout_words[g] * 8, cudaMemcpyHostToDevice, st_));
         {   // initial regions: start[n], len[n] as int32 (pinned staging)
             // + one flag per region: "this region and the next one are the two sides of one anchor gap" (the right side of anchor
             // i is pushed before the left side of anchor i+1, which starts one base earlier and is searched first)
@@ -266,87 +403,49 @@ public:
                     hp[r] = (r + 1 < R && t[0] == s[0] - 1 && t[n] == s[n]) ? 1 : 0;
                 }
             });
-            PB_CUDA(cudaMemcpyAsync(St.coords, h, R * 2 * (size_t)n * 4, cudaMemcpyHostToDevice, st_));
-            r_pairflag_ = r_pair_.ensure(R + 16, false, st_);
+            PB_CUDA(cudaMemcpyAsync(rr_.St.coords, h, R * 2 * (size_t)n * 4, cudaMemcpyHostToDevice, st_));
             PB_CUDA(cudaMemcpyAsync(r_pairflag_, hp, R, cudaMemcpyHostToDevice, st_));
-            const unsigned int r32 = (unsigned int)R;
             unsigned int* hr = r_pin_ctr_.ensure(40);
-            hr[0] = r32;
-            PB_CUDA(cudaMemcpyAsync(Q.nregions, hr, 4, cudaMemcpyHostToDevice, st_));
+            hr[0] = (unsigned int)R;
+            PB_CUDA(cudaMemcpyAsync(rr_.Q.nregions, hr, 4, cudaMemcpyHostToDevice, st_));
         }
-        // ---- candidate arrays: sized from what earlier alignments of this process needed
-        static std::atomic<uint32_t> s_cand_per_region_x16(6 * 16);
-        size_t cand_cap = std::max<size_t>(r_cand_hint_, R * s_cand_per_region_x16.load() / 16 + 65536);
-        const size_t cap_limit = std::max<size_t>((size_t)1 << 16, ((size_t)4 << 30) / (size_t)(8 + 5 * nq));       // <= 4 GiB of candidate arrays
-        cand_cap = std::min(cand_cap, cap_limit);
-        unsigned long long* d_cnt = d_candcnt_.ensure(1, false, st_);
-        PB_CUDA(cudaMemsetAsync(d_cnt, 0, 8, st_));
-        int32_t* d_k = d_ck_.ensure(cand_cap, false, st_);
-        int32_t* d_lon = d_clon_.ensure(cand_cap, false, st_);
-        int32_t* d_sp = d_csp_.ensure(cand_cap * (size_t)nq, false, st_);
-        uint8_t* d_fw = d_cfwd_.ensure(cand_cap * (size_t)nq, false, st_);
-        rec::Params P;
-        P.n = n; P.q = rq.q; P.p = rq.p; P.minsize_tab = d_tab; P.minsize_n = rq.minsize_n; P.bit_off = d_bit_off; P.bits = d_bits;
-        small::ClassCfg cfg[rec::NCLASS];
-        for (int c = 0; c < rec::NCLASS; ++c) {
-            cfg[c] = classes_[c];
-            cfg[c].ev_cap += 4 * nq;
-            if (cfg[c].ev_cap > 60000) cfg[c].ev_cap = 60000;
-            P.n_cap[c] = cfg[c].n_cap; P.m_cap[c] = cfg[c].m_cap;
-        }
-        const int gpl = n <= 32 ? 1 : (n <= 64 ? 2 : (n <= 128 ? 4 : 7));
-        auto kern = gpl == 1 ? rec::recursion_level_kernel<1> : (gpl == 2 ? rec::recursion_level_kernel<2> : (gpl == 4 ? rec::recursion_level_kernel<4> : rec::recursion_level_kernel<7>));
-        if (!r_attr_set_[gpl]) {
-            PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            r_attr_set_[gpl] = true;
-        }
-        int ctas[rec::NCLASS];
-        for (int c = 0; c < rec::NCLASS; ++c) {
-            int per_sm = 1;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, cfg[c].threads, cfg[c].smem_bytes(nq)) != cudaSuccess || per_sm < 1) per_sm = 1;
-            ctas[c] = sm_count_ * per_sm;
-        }
-        pb200::launch(rec::seed_lists_kernel, (unsigned)((R + 255) / 256), 256, 0, st_, P, St, Q, (int)R, (const uint8_t*)r_pairflag_);
+        (void)nq;
+        rec_seed(R);
+        rec_launch_round();
+        return rec_finish(out);
+    }
+    // waits for the levels in flight, runs further rounds while a deeper level exists, sorts and downloads
+    bool rec_finish(RecursionResult& out) {
+        const int n = n_, nq = n - 1;
         unsigned int* h_ctr = r_pin_ctr_.ensure(40);
-        int level = 0;
-        const int LEVELS_PER_ROUND = 8;
         for (int round = 0; round < 64; ++round) {
-            for (int l = 0; l < LEVELS_PER_ROUND; ++l, ++level) {
-                for (int c = 0; c < rec::NCLASS; ++c) {
-                    timers.start(GpuTimers::T_SMALL + c, st_);
-                    pb200::launch(kern, ctas[c], cfg[c].threads, cfg[c].smem_bytes(nq), st_, text_.get(), gmeta_.get(), gmeta_.get() + n_, gmeta_.get() + 2 * n_,
-                                  P, St, Q, level, c, cfg[c], d_cnt, (unsigned long long)cand_cap, d_k, d_lon, d_sp, d_fw);
-                    timers.stop(GpuTimers::T_SMALL + c, st_);
-                }
-                pb200::launch(rec::level_advance_kernel, 1, 32, 0, st_, Q, level);
-            }
-            PB_CUDA(cudaGetLastError());
-            PB_CUDA(cudaMemcpyAsync(h_ctr, ctr, 32 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
-            PB_CUDA(cudaMemcpyAsync(h_ctr + 32, d_cnt, 8, cudaMemcpyDeviceToHost, st_));       // (candidates produced so far)
+            PB_CUDA(cudaMemcpyAsync(h_ctr, rr_.ctr, 32 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
+            PB_CUDA(cudaMemcpyAsync(h_ctr + 32, rr_.d_cnt, 8, cudaMemcpyDeviceToHost, st_));   // (candidates produced so far)
             PB_CUDA(cudaStreamSynchronize(st_));
-            const int nx = level & 1;                       // the lists the next level would read
+            const int nx = rr_.level & 1;                   // the lists the next level would read
             if (h_ctr[nx * rec::NCLASS] + h_ctr[nx * rec::NCLASS + 1] + h_ctr[nx * rec::NCLASS + 2] == 0) break;
+            rec_launch_round();
         }
         // ---- results: sorted by start[0] on the device, then one download
-        const size_t NR = std::min<size_t>(h_ctr[16], cap);
+        const size_t NR = std::min<size_t>(h_ctr[16], rr_.cap);
         uint32_t* sk0 = r_sortk_.ensure(2 * NR + 64, false, st_);
         uint32_t* sv0 = r_sortv_.ensure(2 * NR + 64, false, st_);
         uint32_t* sk1 = sk0 + NR; uint32_t* sv1 = sv0 + NR;
         const unsigned int nr32 = (unsigned int)NR;
-        pb200::launch(rec::region_keys_kernel, (unsigned)((NR + 255) / 256), 256, 0, st_, St, n, nr32, sk0, sv0);
+        pb200::launch(rec::region_keys_kernel, (unsigned)((NR + 255) / 256), 256, 0, st_, rr_.St, n, nr32, sk0, sv0);
         int key_bits = 1;
         while (((int64_t)1 << key_bits) <= len_[0] && key_bits < 32) ++key_bits;
         const int which = r_sorter_.sort<uint32_t, uint32_t>(sk0, sk1, sv0, sv1, (int64_t)NR, 0, key_bits, st_);
         const uint32_t* perm = which ? sv1 : sv0;
         uint32_t* cnt = which ? sk0 : sk1;                 // (the key buffer that does not hold the sorted keys is free)
-        uint32_t* d_total = reinterpret_cast<uint32_t*>(ctr + 24);
-        pb200::launch(rec::sorted_counts_kernel, (unsigned)((NR + 255) / 256), 256, 0, st_, St, perm, nr32, cnt);
+        uint32_t* d_total = reinterpret_cast<uint32_t*>(rr_.ctr + 24);
+        pb200::launch(rec::sorted_counts_kernel, (unsigned)((NR + 255) / 256), 256, 0, st_, rr_.St, perm, nr32, cnt);
         r_scanner_.scan<prim::OpSum, true>(cnt, cnt, (int64_t)NR, d_total, st_);
         // (capacity of the regrouped candidate arrays = what was produced: read the counter first)
         unsigned long long used = 0;
         std::memcpy(&used, h_ctr + 32, 8);                  // (read back with the level counters: final after the last level)
-        const size_t NCmax = (size_t)std::min<unsigned long long>(used, cand_cap);
-        if (used > cand_cap) r_cand_hint_ = (size_t)used + (size_t)used / 4;          // (the windows that did not fit are searched on demand)
+        const size_t NCmax = (size_t)std::min<unsigned long long>(used, rr_.cand_cap);
+        if (used > rr_.cand_cap) r_cand_hint_ = (size_t)used + (size_t)used / 4;          // (the windows that did not fit are searched on demand)
         // one device block laid out like the pinned block the host reads: coords | slen | hashes | wins | k | lon | sp | fwd
         auto al64 = [](size_t x) { return (x + 63) & ~(size_t)63; };
         size_t off[9];
@@ -360,11 +459,11 @@ public:
         off[7] = off[6] + al64(NCmax * (size_t)nq * 4);
         off[8] = off[7] + al64(NCmax * (size_t)nq);
         uint8_t* d_out = r_out_.ensure(off[8] + 64, false, st_);
-        pb200::launch(rec::gather_sorted_kernel, (unsigned)((NR * 32 + 255) / 256), 256, 0, st_, St, n, perm, cnt, nr32, d_k, d_lon, d_sp, d_fw,
+        pb200::launch(rec::gather_sorted_kernel, (unsigned)((NR * 32 + 255) / 256), 256, 0, st_, rr_.St, n, perm, cnt, nr32, rr_.d_k, rr_.d_lon, rr_.d_sp, rr_.d_fw,
                       (int64_t*)(d_out + off[0]), (int64_t*)(d_out + off[1]), (WindowRec*)(d_out + off[3]), (uint64_t*)(d_out + off[2]),
                       (int32_t*)(d_out + off[4]), (int32_t*)(d_out + off[5]), (int32_t*)(d_out + off[6]), d_out + off[7]);
         PB_CUDA(cudaGetLastError());
-        PB_CUDA(cudaMemcpyAsync(h_ctr, ctr, 32 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
+        PB_CUDA(cudaMemcpyAsync(h_ctr, rr_.ctr, 32 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
         uint8_t* stage = r_pin_stage_.ensure(off[8] + 64);
         PB_CUDA(cudaMemcpyAsync(stage, d_out, off[8], cudaMemcpyDeviceToHost, st_));
         PB_CUDA(cudaStreamSynchronize(st_));
@@ -375,7 +474,7 @@ public:
         out.wins = (const WindowRec*)(stage + off[3]); out.k = (const int32_t*)(stage + off[4]); out.lon = (const int32_t*)(stage + off[5]);
         out.sp = (const int32_t*)(stage + off[6]); out.fwd = stage + off[7];
         const double t2 = wall_s();
-        out.levels = level; out.deferred = h_ctr[17]; out.dropped = h_ctr[18];
+        out.levels = rr_.level; out.deferred = h_ctr[17]; out.dropped = h_ctr[18];
         // statistics: searched windows, their reference / query bases (bench.py's algorithmic-byte model)
         int64_t searched = 0, rb = 0, qb = 0, cands = 0;
         {
@@ -399,11 +498,172 @@ public:
         small_windows += searched; small_ref_bases += rb; small_query_bases += qb;
         if (searched >= 1024) {
             const uint32_t r16 = (uint32_t)std::min<int64_t>(1 << 20, cands * 20 / searched + 16);
-            uint32_t cur = s_cand_per_region_x16.load();
-            while (r16 > cur && !s_cand_per_region_x16.compare_exchange_weak(cur, r16)) {}
+            uint32_t cur = s_cand_per_region_x16_.load();
+            while (r16 > cur && !s_cand_per_region_x16_.compare_exchange_weak(cur, r16)) {}
         }
-        host_rec_device_s += t1 - t0; host_rec_d2h_s += t2 - t1; host_rec_copy_s += wall_s() - t2;
+        host_rec_device_s += t1 - rr_.t0; host_rec_d2h_s += t2 - t1; host_rec_copy_s += wall_s() - t2;
+        rr_.active = false;
         return true;
+    }
+
+    // ---- the anchor stage on the device (cuda/anchors.cuh)
+    int anchor_stage(const AnchorRequest& rq, AnchorResult& out) override {
+        PB_CUDA(cudaSetDevice(device_));
+        const int n = n_, nq = n - 1;
+        if (!rec_supported(rq.n, rq.q) || rq.ntasks <= 0 || getenv("PB200_NO_DEVICE_ANCHORS")) return 0;
+        for (int t = 0; t < rq.ntasks; ++t) if (classify(rq.tasks[t], rq.coords) != 3) return 0;      // (tiny genomes: the batch path)
+        const double t0 = wall_s();
+        // ---- candidates of every reference window, left on the device: k (genome-global), lon, sp, fwd
+        std::vector<uint32_t> wcount((size_t)rq.ntasks, 0);
+        size_t NCA = 0;
+        for (int t = 0; t < rq.ntasks; ++t) {
+            const WindowTask& wt = rq.tasks[t];
+            const int64_t* qs = rq.coords + wt.coord_off;
+            const int64_t* ql = qs + nq;
+            std::vector<big::StrandDesc> sd((size_t)2 * nq);
+            for (int q = 0; q < nq; ++q) {
+                const int g = q + 1;
+                sd[2 * q] = big::StrandDesc{text_.get() + gfwd_[g] + qs[q], (int32_t)ql[q], 0};
+                sd[2 * q + 1] = big::StrandDesc{text_.get() + grc_[g] + (len_[g] - qs[q] - ql[q]), (int32_t)ql[q], 0};
+            }
+            const uint8_t* R = text_.get() + gfwd_[0] + wt.ref_start;
+            big_.build_index(R, (int)wt.ref_len, wt.minsize, st_, window_is_n_free(wt.ref_start, wt.ref_len));
+            big_.scan_events(R, (int)wt.ref_len, nq, sd, wt.minsize, st_);
+            big_.fold(true, st_);
+            big_.emit(st_);
+            const big::BigPath::DeviceCands dc = big_.pass2_device(nullptr, st_);
+            big_windows++;
+            big_ref_bases += wt.ref_len;
+            for (int q = 0; q < nq; ++q) big_query_bases += ql[q];
+            big_events += big_.last_events;
+            index_rounds += big_.last_index.rounds;
+            wcount[(size_t)t] = dc.ncand;
+            if (dc.ncand) {
+                int32_t* ak = a_k_.ensure(NCA + dc.ncand, true, st_);
+                int32_t* al = a_lon_.ensure(NCA + dc.ncand, true, st_);
+                int32_t* as = a_sp_.ensure((NCA + dc.ncand) * (size_t)nq, true, st_);
+                uint8_t* af = a_fwd_.ensure((NCA + dc.ncand) * (size_t)nq, true, st_);
+                pb200::launch(anc::add_offset_kernel, (dc.ncand + 255) / 256, 256, 0, st_, ak + NCA, dc.k, dc.ncand, (int32_t)0);
+                PB_CUDA(cudaMemcpyAsync(al + NCA, dc.lon, (size_t)dc.ncand * 4, cudaMemcpyDeviceToDevice, st_));
+                PB_CUDA(cudaMemcpyAsync(as + NCA * (size_t)nq, dc.sp, (size_t)dc.ncand * nq * 4, cudaMemcpyDeviceToDevice, st_));
+                PB_CUDA(cudaMemcpyAsync(af + NCA * (size_t)nq, dc.fwd, (size_t)dc.ncand * nq, cudaMemcpyDeviceToDevice, st_));
+                NCA += dc.ncand;
+            }
+        }
+        out.ncand = NCA;
+        host_anchor_search_s += wall_s() - t0;
+        if (NCA == 0) { out.status = 1; out.nanchors = 0; out.nregions = 0; rr_.active = false; return 1; }      // (NO MUMS FOUND)
+        // ---- coordinates (k made genome-global per window), collinearity + overlap sweep
+        const unsigned int nca = (unsigned int)NCA;
+        int32_t* ST = a_st_.ensure(2 * NCA * (size_t)n + 64, false, st_);
+        int32_t* STT = ST + NCA * (size_t)n;
+        uint8_t* valid = a_valid_.ensure(NCA + 64, false, st_);
+        anc::Flags* d_flags = reinterpret_cast<anc::Flags*>(a_flags_.ensure(8, false, st_));
+        PB_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(anc::Flags), st_));
+        {
+            size_t base = 0;
+            for (int t = 0; t < rq.ntasks; ++t) {       // window-relative k -> genome position
+                if (wcount[(size_t)t] && rq.tasks[t].ref_start)
+                    pb200::launch(anc::add_offset_kernel, (wcount[(size_t)t] + 255) / 256, 256, 0, st_, a_k_.get() + base, reinterpret_cast<const uint32_t*>(a_k_.get() + base),
+                                  wcount[(size_t)t], (int32_t)rq.tasks[t].ref_start);
+                base += wcount[(size_t)t];
+            }
+        }
+        const int64_t* d_glen = gmeta_.get() + 2 * n_;
+        pb200::launch(anc::anchor_coords_kernel, (unsigned)((NCA * 32 + 255) / 256), 256, 0, st_, n, d_glen, nca, a_k_.get(), a_lon_.get(), a_sp_.get(), a_fwd_.get(),
+                      ST, STT, valid);
+        pb200::launch(anc::anchor_overlap_kernel, n, 1024, 0, st_, nca, STT, a_lon_.get(), valid, d_flags);
+        anc::Flags* h_flags = reinterpret_cast<anc::Flags*>(a_pin_flags_.ensure(8));
+        PB_CUDA(cudaMemcpyAsync(h_flags, d_flags, sizeof(anc::Flags), cudaMemcpyDeviceToHost, st_));
+        PB_CUDA(cudaStreamSynchronize(st_));
+        if (h_flags->noncollinear || h_flags->overlaps) {
+            // the premise of the parallel accept does not hold everywhere: the host gets the candidates (window-relative k, as
+            // search() delivers them) and runs its own accept pass
+            CandBatch& cb = out.cands;
+            cb.clear();
+            cb.nq = nq;
+            cb.off.assign((size_t)rq.ntasks + 1, 0);
+            for (int t = 0; t < rq.ntasks; ++t) cb.off[(size_t)t + 1] = cb.off[(size_t)t] + wcount[(size_t)t];
+            cb.k.resize(NCA); cb.lon.resize(NCA); cb.sp.resize(NCA * (size_t)nq); cb.fwd.resize(NCA * (size_t)nq);
+            PB_CUDA(cudaMemcpyAsync(cb.k.data(), a_k_.get(), NCA * 4, cudaMemcpyDeviceToHost, st_));
+            PB_CUDA(cudaMemcpyAsync(cb.lon.data(), a_lon_.get(), NCA * 4, cudaMemcpyDeviceToHost, st_));
+            PB_CUDA(cudaMemcpyAsync(cb.sp.data(), a_sp_.get(), NCA * (size_t)nq * 4, cudaMemcpyDeviceToHost, st_));
+            PB_CUDA(cudaMemcpyAsync(cb.fwd.data(), a_fwd_.get(), NCA * (size_t)nq, cudaMemcpyDeviceToHost, st_));
+            PB_CUDA(cudaStreamSynchronize(st_));
+            size_t base = 0;
+            for (int t = 0; t < rq.ntasks; ++t) {
+                const int32_t o = (int32_t)rq.tasks[t].ref_start;
+                if (o) for (size_t c = base; c < base + wcount[(size_t)t]; ++c) cb.k[c] -= o;
+                base += wcount[(size_t)t];
+            }
+            out.status = 2;
+            rr_.active = false;
+            return 2;
+        }
+        // ---- accept on the empty layout, regions between the anchors, push rules -> the recursion's store
+        rec_setup(2 * NCA, rq.layout_words, rq.minsize_tab, rq.minsize_n, rq.q, rq.p);
+        unsigned long long* bits = rr_.P.bits;
+        const int64_t* d_bit_off = rr_.P.bit_off;
+        PB_CUDA(cudaMemsetAsync(bits, 0, (size_t)r_bits_words_ * 8, st_));
+        pb200::launch(anc::layout_sentinels_kernel, (n + 127) / 128, 128, 0, st_, n, d_glen, bits, d_bit_off);
+        uint32_t* accepted = a_u32_.ensure(4 * NCA + 4 * 2 * NCA + 256, false, st_);
+        uint32_t* xidx = accepted + NCA;
+        uint32_t* slot = xidx + NCA;                         // [2 * anchors] <= 2 NCA
+        uint32_t* pos = slot + 2 * NCA;
+        uint32_t* d_tot = pos + 2 * NCA;                     // [0] anchors, [1] regions
+        pb200::launch(anc::anchor_accept_kernel, (unsigned)((NCA * 32 + 255) / 256), 256, 0, st_, n, text_.get(), gmeta_.get(), nca, ST, a_lon_.get(), a_fwd_.get(),
+                      valid, bits, d_bit_off, accepted);
+        r_scanner_.scan<prim::OpSum, true>(accepted, xidx, (int64_t)NCA, d_tot, st_);
+        // (anchors <= candidates: everything per anchor is sized by NCA, no synchronisation needed to continue)
+        auto al64 = [](size_t x) { return (x + 63) & ~(size_t)63; };
+        int32_t* REG = a_reg_.ensure(NCA * 4 * (size_t)n + 2 * NCA + 64, false, st_);
+        int32_t* SL = REG + NCA * 4 * (size_t)n;
+        size_t hoff[6];
+        hoff[0] = 0;                                          // anchors' starts
+        hoff[1] = hoff[0] + al64(NCA * (size_t)n * 4);       // lon
+        hoff[2] = hoff[1] + al64(NCA * 4);                   // fwd
+        hoff[3] = hoff[2] + al64(NCA * (size_t)n);           // layout
+        hoff[4] = hoff[3] + al64((size_t)r_bits_words_ * 8); // flags
+        hoff[5] = hoff[4] + 64;
+        uint8_t* d_host = a_out_.ensure(hoff[5] + 64, false, st_);
+        pb200::launch(anc::anchor_regions_kernel, (unsigned)((NCA * 32 + 255) / 256), 256, 0, st_, n, d_glen, nca, accepted, xidx, ST, a_lon_.get(), a_fwd_.get(),
+                      (const unsigned long long*)bits, d_bit_off, REG, SL, (int32_t*)(d_host + hoff[0]), (int32_t*)(d_host + hoff[1]), d_host + hoff[2]);
+        // push flags need the number of anchors: it is on the device; the kernels are launched for NCA and bounded there
+        pb200::launch(anchor_push_flags_bounded, (unsigned)((NCA * 32 + 255) / 256), 256, 0, st_, n, rq.q, (const uint32_t*)d_tot, nca, (const int32_t*)REG, (const int32_t*)SL, slot);
+        r_scanner_.scan<prim::OpSum, true>(slot, pos, (int64_t)(2 * NCA), d_tot + 1, st_);
+        pb200::launch(anchor_push_bounded, (unsigned)((NCA * 32 + 255) / 256), 256, 0, st_, n, (const uint32_t*)d_tot, (const int32_t*)REG, (const int32_t*)SL,
+                      (const uint32_t*)slot, (const uint32_t*)pos, rr_.St, r_pairflag_, rr_.Q.cap);
+        pb200::launch(anc::anchor_finish_kernel, 1, 32, 0, st_, (const uint32_t*)d_tot, (const uint32_t*)(d_tot + 1), d_flags, rr_.Q.nregions, rr_.Q.cap);
+        // ---- what the host needs: the layout BEFORE the recursion scribbles on it, anchors, flags; then the initial regions
+        PB_CUDA(cudaMemcpyAsync(d_host + hoff[3], bits, (size_t)r_bits_words_ * 8, cudaMemcpyDeviceToDevice, st_));
+        PB_CUDA(cudaMemcpyAsync(d_host + hoff[4], d_flags, sizeof(anc::Flags), cudaMemcpyDeviceToDevice, st_));
+        uint8_t* h_host = a_pin_out_.ensure(hoff[5] + 64);
+        PB_CUDA(cudaMemcpyAsync(h_host + hoff[4], d_host + hoff[4], 64, cudaMemcpyDeviceToHost, st_));
+        PB_CUDA(cudaStreamSynchronize(st_));                 // (the counts: how much of the rest to copy)
+        const anc::Flags fl = *reinterpret_cast<const anc::Flags*>(h_host + hoff[4]);
+        const size_t NA = fl.accepted, NR = std::min<size_t>(fl.regions, rr_.cap);
+        if (getenv("PB200_DEBUG_ANCHORS")) fprintf(stderr, "[pb200 anchors] windows %d candidates %zu accepted %u regions %u noncollinear %u overlaps %u\n", rq.ntasks, NCA, fl.accepted, fl.regions, fl.noncollinear, fl.overlaps);
+        if (rq.follow_recursion && NR > 0) {
+            rec_seed(2 * NCA);
+            rec_launch_round();                              // the GPU follows the recursion while the host builds its pools
+        } else rr_.active = false;
+        // copies on a second stream: they overlap the recursion kernels (the store's initial regions are only read by them)
+        if (!st2_) PB_CUDA(cudaStreamCreateWithFlags(&st2_, cudaStreamNonBlocking));
+        int32_t* h_rc = a_pin_rc_.ensure(NR * 2 * (size_t)n + 16);
+        PB_CUDA(cudaMemcpyAsync(h_host + hoff[0], d_host + hoff[0], NA * (size_t)n * 4, cudaMemcpyDeviceToHost, st2_));
+        PB_CUDA(cudaMemcpyAsync(h_host + hoff[1], d_host + hoff[1], NA * 4, cudaMemcpyDeviceToHost, st2_));
+        PB_CUDA(cudaMemcpyAsync(h_host + hoff[2], d_host + hoff[2], NA * (size_t)n, cudaMemcpyDeviceToHost, st2_));
+        PB_CUDA(cudaMemcpyAsync(h_host + hoff[3], d_host + hoff[3], (size_t)r_bits_words_ * 8, cudaMemcpyDeviceToHost, st2_));
+        if (NR) PB_CUDA(cudaMemcpyAsync(h_rc, rr_.St.coords, NR * 2 * (size_t)n * 4, cudaMemcpyDeviceToHost, st2_));
+        PB_CUDA(cudaStreamSynchronize(st2_));
+        out.status = 1;
+        out.nanchors = NA; out.nregions = NR;
+        out.a_start = (const int32_t*)(h_host + hoff[0]); out.a_lon = (const int32_t*)(h_host + hoff[1]); out.a_fwd = h_host + hoff[2];
+        out.layout = (const uint64_t*)(h_host + hoff[3]);
+        out.layout_off = r_bit_off_host_;
+        out.r_coords = h_rc;
+        host_anchor_accept_s += wall_s() - t0;
+        return 1;
     }
 
     // ---- StagedWindowEngine (query-sharded large windows, see host/sharded.h) ----
@@ -515,7 +775,7 @@ public:
     GpuTimers timers;
     int64_t big_windows = 0, small_windows = 0, small_retries = 0, big_events = 0, index_rounds = 0;
     int64_t small_class_tasks[3] = {0, 0, 0};
-    double host_rec_device_s = 0, host_rec_d2h_s = 0, host_rec_copy_s = 0;
+    double host_rec_device_s = 0, host_rec_d2h_s = 0, host_rec_copy_s = 0, host_anchor_search_s = 0, host_anchor_accept_s = 0;
     double host_classify_s = 0, host_upload_s = 0, host_small_wait_s = 0, host_small_d2h_s = 0, host_big_s = 0, host_gather_s = 0;   // wall clock, host side
     int64_t small_ref_bases = 0, small_query_bases = 0, big_ref_bases = 0, big_query_bases = 0;
 
@@ -684,6 +944,17 @@ private:
     rsort::RadixSorter r_sorter_;
     prim::Scanner r_scanner_;
     size_t r_cand_hint_ = 0;
+    // anchor stage on the device (anchor_stage)
+    DevBuf<int32_t> a_k_, a_lon_, a_sp_, a_st_, a_reg_;
+    DevBuf<uint8_t> a_fwd_, a_valid_, a_out_;
+    DevBuf<uint32_t> a_u32_;
+    DevBuf<unsigned int> a_flags_;
+    PinBuf<unsigned int> a_pin_flags_;
+    PinBuf<uint8_t> a_pin_out_;
+    PinBuf<int32_t> a_pin_rc_;
+    cudaStream_t st2_ = nullptr;
+    std::vector<int64_t> r_bit_off_host_;
+    static std::atomic<uint32_t> s_cand_per_region_x16_;
     int64_t r_bits_words_ = -1;
     bool r_attr_set_[8] = {false, false, false, false, false, false, false, false};
     PinBuf<int32_t> pin_k_, pin_lon_, pin_sp_;       // small-window candidates of the current search() call (pinned staging)
@@ -692,6 +963,8 @@ private:
     std::vector<int32_t> bg_k_, bg_lon_, bg_sp_;
     std::vector<uint8_t> bg_fwd_;
 };
+
+std::atomic<uint32_t> CudaEngine::s_cand_per_region_x16_(6 * 16);
 
 }  // namespace pb200
 
@@ -818,6 +1091,7 @@ public:
     void set_genomes(int, const uint8_t* const*, const int64_t*) override {}
     void search(const pb200::WindowTask* t, int nt, const int64_t* c, pb200::CandBatch& out) override { e_->search(t, nt, c, out); }
     bool discover_recursion(const pb200::RecursionRequest& rq, pb200::RecursionResult& out) override { return e_->discover_recursion(rq, out); }
+    int anchor_stage(const pb200::AnchorRequest& rq, pb200::AnchorResult& out) override { return e_->anchor_stage(rq, out); }
 private:
     pb200::CudaEngine* e_;
 };

@@ -395,8 +395,9 @@ __global__ void level_advance_kernel(Queues Q, int level) {
 
 // level 0: classify the initial regions (uploaded into the store by the host) into the first lists.  pair[id] = 1: regions id
 // and id + 1 are the right side of an anchor and the left side of the next one - one entry, the second searched first
-__global__ void seed_lists_kernel(Params P, Store St, Queues Q, int count, const uint8_t* __restrict__ pair) {
+__global__ void seed_lists_kernel(Params P, Store St, Queues Q, const unsigned int* __restrict__ count_ptr, const uint8_t* __restrict__ pair) {
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    const int count = (int)*count_ptr;
     if (id >= count) return;
     const int n = P.n;
     const int32_t* c = St.coords + (size_t)id * 2 * n;

@@ -234,13 +234,10 @@ int Aligner::minsize_cached(CandCache& C, bool anchors, int64_t slength) {
 }
 
 // ------------------------------------------------------------------ batched search (setMums1 up to the emission loop)
-void Aligner::search_regions(CandCache& C, const RegionPool& src, const std::vector<int>& regs, bool anchors) {
-    if (regs.empty()) return;
+void Aligner::make_window_tasks(CandCache& C, const RegionPool& src, const std::vector<int>& regs, bool anchors, std::vector<WindowTask>& tasks,
+                                std::vector<int64_t>& coords, std::vector<int>& first_task) {
     C.rp.n = n_;
-    const double tp0 = now_s();
-    std::vector<WindowTask> tasks;
-    std::vector<int64_t> coords;
-    std::vector<int> first_task(regs.size() + 1, 0);
+    first_task.assign(regs.size() + 1, 0);
     const int nq = n_ - 1;
     tasks.reserve(regs.size());
     coords.reserve(regs.size() * 2 * (size_t)nq);
@@ -275,14 +272,11 @@ void Aligner::search_regions(CandCache& C, const RegionPool& src, const std::vec
         }
     }
     first_task[regs.size()] = (int)tasks.size();
-    const double tp1 = now_s();
-    C.chunks.emplace_back();
-    CandBatch& cb = C.chunks.back();
-    cb.nq = nq;
-    if (!tasks.empty()) {
-        std::lock_guard<std::mutex> lk(backend_mu_);       // one search at a time: the engine owns one stream and one set of buffers
-        be_->search(tasks.data(), (int)tasks.size(), coords.data(), cb);
-    } else cb.off.assign(1, 0);
+}
+
+void Aligner::install_search_result(CandCache& C, const RegionPool& src, const std::vector<int>& regs, const std::vector<WindowTask>& tasks,
+                                    const std::vector<int>& first_task, CandBatch& cb) {
+    const int nq = n_ - 1;
     if (!cb.cnt.empty()) {
         // the engine delivers the windows' candidate blocks in kernel completion order; gather them into window order so that
         // the accept passes (ascending reference order) stream through memory
@@ -309,7 +303,6 @@ void Aligner::search_regions(CandCache& C, const RegionPool& src, const std::vec
         cb.off.swap(noff);
         cb.cnt.clear();
     }
-    const double tp2 = now_s();
     const int32_t chunk = (int32_t)C.chunks.size() - 1;
     C.entries.reserve(C.entries.size() + regs.size());
     C.map.reserve(regs.size());
@@ -331,6 +324,25 @@ void Aligner::search_regions(CandCache& C, const RegionPool& src, const std::vec
         C.map.insert(coords_hash(src.start(regs[ri]), 2 * n_), (int)C.entries.size());
         C.entries.push_back(e);
     }
+}
+
+void Aligner::search_regions(CandCache& C, const RegionPool& src, const std::vector<int>& regs, bool anchors) {
+    if (regs.empty()) return;
+    const double tp0 = now_s();
+    std::vector<WindowTask> tasks;
+    std::vector<int64_t> coords;
+    std::vector<int> first_task;
+    make_window_tasks(C, src, regs, anchors, tasks, coords, first_task);
+    const double tp1 = now_s();
+    C.chunks.emplace_back();
+    CandBatch& cb = C.chunks.back();
+    cb.nq = n_ - 1;
+    if (!tasks.empty()) {
+        std::lock_guard<std::mutex> lk(backend_mu_);       // one search at a time: the engine owns one stream and one set of buffers
+        be_->search(tasks.data(), (int)tasks.size(), coords.data(), cb);
+    } else cb.off.assign(1, 0);
+    const double tp2 = now_s();
+    install_search_result(C, src, regs, tasks, first_task, cb);
     const double tp3 = now_s();
     {
         std::lock_guard<std::mutex> lk(backend_mu_);       // (the statistics are shared between the two producer threads)
@@ -531,12 +543,106 @@ static int64_t det_region(const std::vector<BitRow>& layout, const std::vector<i
     return det_region_impl(acc, len, n, mstart, mlen, left, S, E);
 }
 
+namespace {
+std::shared_ptr<const std::vector<int32_t>> minsize_table(const std::string& expr, int N, int threads);
+}
+
+// the anchor stage as the engine delivered it: anchors into the MUM pool, mumlayout, the regions between the anchors
+void Aligner::install_device_anchors(const AnchorResult& res, int whole) {
+    const size_t NA = res.nanchors, NR = res.nregions, N = (size_t)n_;
+    const int64_t rsl = rp_.slen[(size_t)whole];
+    {   // room for the recursion's MUMs too (about 3x the anchors on divergent genomes)
+        const size_t est = NA * 4 + 1024;
+        mp_.mums.reserve(est);
+        mp_.start.reserve(est * N);
+        mp_.fwd.reserve(est * N);
+    }
+    mp_.mums.resize(NA);
+    mp_.start.resize(NA * N);
+    mp_.fwd.resize(NA * N);
+    all_mums_.resize(NA);
+    const long per = 2048;
+    parallel_chunks(NA > 8192 ? threads_ : 1, ((long)NA + per - 1) / per, [&](long c) {
+        for (size_t x = (size_t)c * per; x < std::min(NA, (size_t)(c + 1) * per); ++x) {
+            MumRec m;
+            m.length = res.a_lon[x];
+            m.slength = rsl;
+            m.off = (int64_t)(x * N);
+            m.alive = true;
+            mp_.mums[x] = m;
+            for (size_t g = 0; g < N; ++g) { mp_.start[x * N + g] = res.a_start[x * N + g]; mp_.fwd[x * N + g] = res.a_fwd[x * N + g]; }
+            all_mums_[x] = (int)x;
+        }
+    });
+    stats_.anchors = (int64_t)NA;
+    if (NA == 0) return;                         // (NO MUMS FOUND: the layout stays as constructed)
+    parallel_chunks(threads_, (long)n_, [&](long g) {
+        BitRow& row = truth_.layout[(size_t)g];
+        std::memcpy(row.words_mut(), res.layout + res.layout_off[(size_t)g], (size_t)row.nwords() * sizeof(uint64_t));
+    });
+    const int base = rp_.size();
+    rp_.coord.resize(rp_.coord.size() + NR * 2 * N);
+    rp_.slen.resize(rp_.slen.size() + NR);
+    initial_regions_.resize(NR);
+    parallel_chunks(NR > 8192 ? threads_ : 1, ((long)NR + per - 1) / per, [&](long c) {
+        for (size_t r = (size_t)c * per; r < std::min(NR, (size_t)(c + 1) * per); ++r) {
+            const int32_t* s = res.r_coords + r * 2 * N;
+            int64_t* d = &rp_.coord[((size_t)base + r) * 2 * N];
+            int64_t sl = 500000000;
+            for (size_t g = 0; g < N; ++g) { d[g] = s[g]; d[N + g] = (int64_t)s[g] + s[N + g]; sl = std::min<int64_t>(sl, s[N + g]); }
+            rp_.slen[(size_t)base + r] = sl;
+            initial_regions_[r] = base + (int)r;
+        }
+    });
+    anchors_on_device_ = true;
+}
+
 // ------------------------------------------------------------------ anchors (src/parsnp.cpp:2121-2174)
 void Aligner::set_initial_clusters() {
     double t0 = now_s();
     std::vector<int64_t> S(n_, 0), E(len_);
     int whole = rp_.add(S.data(), E.data());
-    search_regions(main_cache_, rp_, std::vector<int>(1, whole), true);
+    // The engine can take the whole anchor stage (search + accept on the empty layout + the regions between the anchors:
+    // cuda/anchors.cuh) and start following the recursion from there.  It declines (status 0: tiny genomes, a backend without
+    // it) or hands the candidates back (status 2: overlapping or non-collinear candidates - the accept below is needed).
+    int status = 0;
+    if (speculate_ && pipeline_ && !trace_on_ && n_ > 1) {
+        std::shared_ptr<const std::vector<int32_t>> tab = minsize_table(prm_.mums, 4160, threads_);
+        if (tab) {
+            std::vector<WindowTask> tasks;
+            std::vector<int64_t> coords;
+            std::vector<int> first_task;
+            const std::vector<int> regs(1, whole);
+            make_window_tasks(main_cache_, rp_, regs, true, tasks, coords, first_task);
+            std::vector<int64_t> nwords((size_t)n_);
+            for (int g = 0; g < n_; ++g) nwords[(size_t)g] = truth_.layout[(size_t)g].nwords();
+            AnchorRequest rq;
+            rq.n = n_; rq.tasks = tasks.data(); rq.ntasks = (int)tasks.size(); rq.coords = coords.data(); rq.layout_words = nwords.data();
+            rq.q = prm_.q; rq.p = prm_.p; rq.minsize_tab = tab->data(); rq.minsize_n = (int)tab->size();
+            rq.follow_recursion = !prm_.anchors_only;
+            AnchorResult res;
+            {
+                std::lock_guard<std::mutex> lk(backend_mu_);
+                status = be_->anchor_stage(rq, res);
+            }
+            if (status != 0) {
+                stats_.windows_searched += (int64_t)tasks.size();
+                stats_.regions_searched += 1;
+                stats_.candidates += (int64_t)(status == 1 ? res.ncand : res.cands.k.size());
+            }
+            if (status == 1) {
+                stats_.t_anchor_search = now_s() - t0;
+                install_device_anchors(res, whole);
+                stats_.t_anchor_host = now_s() - t0 - stats_.t_anchor_search;
+                return;
+            }
+            if (status == 2) {
+                main_cache_.chunks.emplace_back(std::move(res.cands));
+                install_search_result(main_cache_, rp_, regs, tasks, first_task, main_cache_.chunks.back());
+            }
+        }
+    }
+    if (status == 0) search_regions(main_cache_, rp_, std::vector<int>(1, whole), true);
     double t1 = now_s();
     stats_.t_anchor_search = t1 - t0;
     std::vector<int> found;
@@ -1324,15 +1430,18 @@ bool Aligner::discover_on_device() {
     const int TABN = 4160;                       // covers every window the shared-memory search kernel takes (<= 4096 bases)
     disc_tab_ = minsize_table(prm_.mums, TABN, threads_);
     if (!disc_tab_) return false;
-    disc_coords_.resize(R * 2 * (size_t)n_);
     const long per = 4096;
-    parallel_chunks(R > 16384 ? threads_ : 1, ((long)R + per - 1) / per, [&](long c) {
-        for (size_t i = (size_t)c * per; i < std::min(R, (size_t)(c + 1) * per); ++i)
-            std::memcpy(&disc_coords_[i * 2 * (size_t)n_], rstart(initial_regions_[i]), sizeof(int64_t) * 2 * (size_t)n_);
-    });
+    if (!anchors_on_device_) {                   // (else the engine already holds them: it made them)
+        disc_coords_.resize(R * 2 * (size_t)n_);
+        parallel_chunks(R > 16384 ? threads_ : 1, ((long)R + per - 1) / per, [&](long c) {
+            for (size_t i = (size_t)c * per; i < std::min(R, (size_t)(c + 1) * per); ++i)
+                std::memcpy(&disc_coords_[i * 2 * (size_t)n_], rstart(initial_regions_[i]), sizeof(int64_t) * 2 * (size_t)n_);
+        });
+    }
     // slices: a small first one (the replay starts as soon as it is there), then growing
     const char* es = getenv("PB200_DISCOVERY_SLICES");
-    size_t K = es ? (size_t)std::max(1, atoi(es)) : 1;       // (measured on configs[1]: slices cost more in launches and syncs than the overlap returns)
+    size_t K = es ? (size_t)std::max(1, atoi(es)) : 1;
+    if (anchors_on_device_) K = 1;               // (the engine is already following the whole recursion)       // (measured on configs[1]: slices cost more in launches and syncs than the overlap returns)
     K = std::min(K, R);
     disc_begin_.assign(K + 1, 0);
     {
@@ -1383,7 +1492,8 @@ bool Aligner::discover_slice(int k) {
     for (int g = 0; g < n_; ++g) { rows[(size_t)g] = truth_.layout[(size_t)g].words(); nwords[(size_t)g] = truth_.layout[(size_t)g].nwords(); }
     RecursionRequest rq;
     rq.n = n_; rq.coords = disc_coords_.data() + i0 * 2 * (size_t)n_; rq.nregions = (int)R; rq.layout = rows.data(); rq.layout_words = nwords.data();
-    rq.upload_layout = k == 0;                   // (later slices run beside the replay, which writes the layout: the engine keeps its scratch copy)
+    rq.upload_layout = k == 0;
+    rq.resume = anchors_on_device_;                   // (later slices run beside the replay, which writes the layout: the engine keeps its scratch copy)
     rq.q = prm_.q; rq.p = prm_.p; rq.minsize_tab = disc_tab_->data(); rq.minsize_n = (int)disc_tab_->size();
     RecursionResult res;
     if (R == 0) return true;

@@ -74,6 +74,7 @@ public:
     int64_t next_set(int64_t i, int64_t limit) const;   // smallest set index in [i,limit), or limit
     int64_t nbits() const { return nbits_; }
     const uint64_t* words() const { return w_.data(); }
+    uint64_t* words_mut() { return w_.data(); }
     int64_t nwords() const { return (int64_t)w_.size(); }
 private:
     std::vector<uint64_t> w_;
@@ -203,6 +204,12 @@ private:
     int minsize_cached(CandCache& C, bool anchors, int64_t slength);
     // batched GPU search of regions `regs` of pool `src`, fills C
     void search_regions(CandCache& C, const RegionPool& src, const std::vector<int>& regs, bool anchors);
+    // its three parts: the reference windows of the regions, (the backend call,) the answer into the cache
+    void make_window_tasks(CandCache& C, const RegionPool& src, const std::vector<int>& regs, bool anchors, std::vector<WindowTask>& tasks,
+                           std::vector<int64_t>& coords, std::vector<int>& first_task);
+    void install_search_result(CandCache& C, const RegionPool& src, const std::vector<int>& regs, const std::vector<WindowTask>& tasks,
+                               const std::vector<int>& first_task, CandBatch& cb);
+    void install_device_anchors(const AnchorResult& res, int whole);
 
     // setMums1 loop D on cached candidates; appends accepted MUMs to `mp`, their indices to `found`
     void accept_candidates(const int64_t* rs, const int64_t* re, int64_t rsl, const CandCache& C, int cache_idx, std::vector<BitRow>& layout,
@@ -283,6 +290,7 @@ private:
     int slices_ready_ = 0;                                  // slices [0, slices_ready_) are published (guarded by slice_mu_)
     std::exception_ptr spec_error_;
     bool pipeline_ = true;
+    bool anchors_on_device_ = false;                        // the engine placed the anchors and is following the recursion (anchor_stage)
     int replay_threads_ = 0;                                // 0 = threads_
     ReplayCtx* replay_ctx_ = nullptr;
     std::thread replay_prep_thread_;
