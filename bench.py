@@ -369,7 +369,8 @@ def main():
                        "anchors": int(st["anchors"]), "regions_searched": int(st["regions_searched"]),
                        "replay_misses": int(st["replay_misses"]), "spec_levels": int(st["spec_levels"]),
                        "replay": {k: int(st[k]) for k in ("replay_tasks", "replay_workers", "replay_foreign_reads", "replay_foreign_writes",
-                                                          "replay_restarts", "replay_fallback", "spec_deferred", "slow_queue_iters") if k in st}},
+                                                          "replay_restarts", "replay_fallback", "spec_deferred", "slow_queue_iters", "replay_gaps", "replay_final_gaps",
+                                                          "replay_final_mums") if k in st}},
             "host_seconds": {k: st[k] for k in st if k.startswith("t_")},
             "engine": {k: timers[k] for k in timers if not k.endswith("_ms") and not k.startswith("n_")},
             "small_class_ms": {"a": timers.get("small_regions_ms", 0.0) / nsteps, "b": timers.get("small_b_ms", 0.0) / nsteps,

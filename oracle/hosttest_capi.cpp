@@ -12,6 +12,7 @@ namespace pb200_oracle {
 pb200::SearchBackend* make_spec_backend();
 pb200::SearchBackend* make_ref_backend();
 pb200::SearchBackend* make_replay_backend();
+pb200::SearchBackend* make_discover_backend();
 pb200::StagedWindowEngine* as_staged(pb200::SearchBackend* b);
 struct SpecCand { int32_t k, lon; std::vector<int32_t> sp; std::vector<uint8_t> fwd; };
 void spec_window(const uint8_t* R, int64_t n, int nq, const uint8_t* const* Q, const int64_t* m, int minsize, std::vector<SpecCand>& out);
@@ -21,9 +22,12 @@ void spec_lrp(const uint8_t* R, int64_t n, std::vector<int32_t>& lrp);
 extern "C" {
 // backend: 0 = brute-force specification (oracle/mumspec.cpp), 1 = real csgmum (oracle/ref_backend.cpp),
 //          2 = csgmum behind the record/replay table (host orchestrator timing, tools/host_bench.py)
+//          3 = 2 + the CPU emulation of the engine's device-resident discovery (oracle/discover_emul.cpp): the host's
+//              "final gaps" path without a GPU
 int pbtest_align(int backend, int n, const uint8_t* const* seqs, const int64_t* lens, const pb200_params* prm, pb200_result** out) {
     try {
-        pb200::SearchBackend* be = backend == 0 ? pb200_oracle::make_spec_backend() : backend == 2 ? pb200_oracle::make_replay_backend() : pb200_oracle::make_ref_backend();
+        pb200::SearchBackend* be = backend == 0 ? pb200_oracle::make_spec_backend() : backend == 2 ? pb200_oracle::make_replay_backend()
+                                  : backend == 3 ? pb200_oracle::make_discover_backend() : pb200_oracle::make_ref_backend();
         pb200::Aligner a(n, seqs, lens, pb200::to_align_params(prm), be);
         a.enable_trace(prm->flags & PB200_FLAG_TRACE_WINDOWS);
         a.set_speculate(!(prm->flags & PB200_FLAG_NO_SPECULATION));

@@ -172,7 +172,17 @@ public:
     struct Entry { std::vector<int32_t> k, lon, sp; std::vector<uint8_t> fwd; };
     void set_genomes(int n, const uint8_t* const* seq, const int64_t* len) override {
         n_ = n; seq_.assign(seq, seq + n); len_.assign(len, len + n);
+        // the table's keys are window coordinates: it belongs to ONE genome set (another set: start afresh)
+        uint64_t h = 1469598103934665603ull;
+        for (int g = 0; g < n; ++g) {
+            h = (h ^ (uint64_t)len[g]) * 1099511628211ull;
+            for (int64_t i = 0; i + 8 <= len[g]; i += 8) { uint64_t w; std::memcpy(&w, seq[g] + i, 8); h = (h ^ w) * 1099511628211ull; }
+            for (int64_t i = len[g] & ~(int64_t)7; i < len[g]; ++i) h = (h ^ seq[g][i]) * 1099511628211ull;
+        }
+        std::lock_guard<std::mutex> lk(mu());
+        if (h != genome_hash()) { table().clear(); genome_hash() = h; }
     }
+    static uint64_t& genome_hash() { static uint64_t h = 0; return h; }
     void search(const pb200::WindowTask* tasks, int ntasks, const int64_t* coords, pb200::CandBatch& out) override {
         const int nq = n_ - 1;
         std::vector<std::string> keys((size_t)ntasks);

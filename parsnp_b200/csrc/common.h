@@ -117,6 +117,7 @@ struct RecursionRequest {
 };
 // All arrays are VIEWS into memory of the backend (pinned staging), valid until its next discover_recursion call; regions are in
 // ascending start[0] order, candidates grouped accordingly.
+constexpr uint32_t REC_ORDER_MASK = 15, REC_SECOND = 16;
 struct RecursionResult {
     size_t nregions = 0, ncands = 0;
     const int64_t* coords = nullptr;     // [nregions * 2n]: start[n] then end[n]
@@ -127,6 +128,19 @@ struct RecursionResult {
     const int32_t* lon = nullptr;
     const int32_t* sp = nullptr;
     const uint8_t* fwd = nullptr;
+    // the engine's own accept decisions (it followed setMums1's loop D on a scratch layout), for callers that can tell where they
+    // cannot depend on the order (host/replay.cpp takes them as final for such gaps): per region flags - a bit of
+    // REC_ORDER_MASK set = the region's pass may depend on the order (a reverse-strand candidate reached the trim loop, the
+    // second region of a gap pair accepted something, its accepted MUMs are not collinear, it was searched outside its pair's
+    // order), REC_SECOND = searched as the second region of a pair - and the sorted position of its parent region (-1:
+    // initial); per candidate the trim shift (-1: not accepted) and the accepted length; and the accepted MUMs that were
+    // written OUTSIDE their region (genome, start, length) - nfw > fw_cap: the list is incomplete.  flags == nullptr: not provided
+    const uint32_t* flags = nullptr;
+    const int32_t* parent = nullptr;
+    const int32_t* acc_shift = nullptr;
+    const int32_t* acc_len = nullptr;
+    const int32_t* fw = nullptr;
+    size_t nfw = 0, fw_cap = 0;
     int64_t levels = 0, deferred = 0, dropped = 0, searched = 0;
 };
 

@@ -308,6 +308,8 @@ public:
         St.minsize = r_minsize_.ensure(cap, false, st_);
         St.ncand = r_ncand_.ensure(cap, false, st_);
         St.cand_base = r_candbase_.ensure(cap, false, st_);
+        St.flags = r_flags_.ensure(cap, false, st_);
+        St.parent = r_parent_.ensure(cap, false, st_);
         int32_t* lists = r_lists_.ensure(cap * (2 * rec::NCLASS + 1), false, st_);
         unsigned int* ctr = r_ctr_.ensure(32, false, st_);
         PB_CUDA(cudaMemsetAsync(ctr, 0, 32 * sizeof(unsigned int), st_));
@@ -315,7 +317,8 @@ public:
         rec::Queues& Q = rr_.Q;
         for (int h = 0; h < 2; ++h) for (int c = 0; c < rec::NCLASS; ++c) Q.list[h][c] = lists + cap * (size_t)(h * rec::NCLASS + c);
         Q.deferred = lists + cap * (size_t)(2 * rec::NCLASS);
-        Q.count = ctr; Q.taken = ctr + 8; Q.nregions = ctr + 16; Q.ndeferred = ctr + 17; Q.dropped = ctr + 18;
+        Q.count = ctr; Q.taken = ctr + 8; Q.nregions = ctr + 16; Q.ndeferred = ctr + 17; Q.dropped = ctr + 18; Q.nfw = ctr + 19;
+        Q.fw = r_fw_.ensure(3 * (size_t)rec::FW_CAP, false, st_);
         Q.cap = (unsigned int)std::min<size_t>(cap, 0x1fffffffu);
         r_pairflag_ = r_pair_.ensure(cap + 16, false, st_);
         // candidate arrays: sized from what earlier alignments of this process needed
@@ -329,6 +332,8 @@ public:
         rr_.d_lon = d_clon_.ensure(cand_cap, false, st_);
         rr_.d_sp = d_csp_.ensure(cand_cap * (size_t)nq, false, st_);
         rr_.d_fw = d_cfwd_.ensure(cand_cap * (size_t)nq, false, st_);
+        St.acc_shift = r_accshift_.ensure(cand_cap, false, st_);
+        St.acc_len = r_acclen_.ensure(cand_cap, false, st_);
         rec::Params& P = rr_.P;
         P.n = n; P.q = q; P.p = p; P.minsize_tab = d_tab; P.minsize_n = tabn; P.bit_off = d_bit_off; P.bits = d_bits;
         for (int c = 0; c < rec::NCLASS; ++c) {
@@ -439,7 +444,8 @@ public:
         const uint32_t* perm = which ? sv1 : sv0;
         uint32_t* cnt = which ? sk0 : sk1;                 // (the key buffer that does not hold the sorted keys is free)
         uint32_t* d_total = reinterpret_cast<uint32_t*>(rr_.ctr + 24);
-        pb200::launch(rec::sorted_counts_kernel, (unsigned)((NR + 255) / 256), 256, 0, st_, rr_.St, perm, nr32, cnt);
+        uint32_t* inv = r_inv_.ensure(NR + 64, false, st_);
+        pb200::launch(rec::sorted_counts_kernel, (unsigned)((NR + 255) / 256), 256, 0, st_, rr_.St, perm, nr32, cnt, inv);
         r_scanner_.scan<prim::OpSum, true>(cnt, cnt, (int64_t)NR, d_total, st_);
         // (capacity of the regrouped candidate arrays = what was produced: read the counter first)
         unsigned long long used = 0;
@@ -448,7 +454,7 @@ public:
         if (used > rr_.cand_cap) r_cand_hint_ = (size_t)used + (size_t)used / 4;          // (the windows that did not fit are searched on demand)
         // one device block laid out like the pinned block the host reads: coords | slen | hashes | wins | k | lon | sp | fwd
         auto al64 = [](size_t x) { return (x + 63) & ~(size_t)63; };
-        size_t off[9];
+        size_t off[14];
         off[0] = 0;
         off[1] = off[0] + al64(NR * 2 * (size_t)n * 8);
         off[2] = off[1] + al64(NR * 8);
@@ -457,15 +463,23 @@ public:
         off[5] = off[4] + al64(NCmax * 4);
         off[6] = off[5] + al64(NCmax * 4);
         off[7] = off[6] + al64(NCmax * (size_t)nq * 4);
-        off[8] = off[7] + al64(NCmax * (size_t)nq);
-        uint8_t* d_out = r_out_.ensure(off[8] + 64, false, st_);
+        off[8] = off[7] + al64(NCmax * (size_t)nq);          // flags
+        off[9] = off[8] + al64(NR * 4);                      // parent
+        off[10] = off[9] + al64(NR * 4);                     // acc_shift
+        off[11] = off[10] + al64(NCmax * 4);                 // acc_len
+        off[12] = off[11] + al64(NCmax * 4);                 // foreign writes
+        const size_t NFW = std::min<size_t>(h_ctr[19], rec::FW_CAP);
+        off[13] = off[12] + al64(NFW * 12);
+        uint8_t* d_out = r_out_.ensure(off[13] + 64, false, st_);
         pb200::launch(rec::gather_sorted_kernel, (unsigned)((NR * 32 + 255) / 256), 256, 0, st_, rr_.St, n, perm, cnt, nr32, rr_.d_k, rr_.d_lon, rr_.d_sp, rr_.d_fw,
                       (int64_t*)(d_out + off[0]), (int64_t*)(d_out + off[1]), (WindowRec*)(d_out + off[3]), (uint64_t*)(d_out + off[2]),
-                      (int32_t*)(d_out + off[4]), (int32_t*)(d_out + off[5]), (int32_t*)(d_out + off[6]), d_out + off[7]);
+                      (int32_t*)(d_out + off[4]), (int32_t*)(d_out + off[5]), (int32_t*)(d_out + off[6]), d_out + off[7],
+                      (const uint32_t*)inv, (uint32_t*)(d_out + off[8]), (int32_t*)(d_out + off[9]), (int32_t*)(d_out + off[10]), (int32_t*)(d_out + off[11]));
+        if (NFW) PB_CUDA(cudaMemcpyAsync(d_out + off[12], rr_.Q.fw, NFW * 12, cudaMemcpyDeviceToDevice, st_));
         PB_CUDA(cudaGetLastError());
         PB_CUDA(cudaMemcpyAsync(h_ctr, rr_.ctr, 32 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
-        uint8_t* stage = r_pin_stage_.ensure(off[8] + 64);
-        PB_CUDA(cudaMemcpyAsync(stage, d_out, off[8], cudaMemcpyDeviceToHost, st_));
+        uint8_t* stage = r_pin_stage_.ensure(off[13] + 64);
+        PB_CUDA(cudaMemcpyAsync(stage, d_out, off[13], cudaMemcpyDeviceToHost, st_));
         PB_CUDA(cudaStreamSynchronize(st_));
         const double t1 = wall_s();
         const size_t NC = std::min<size_t>(h_ctr[24], NCmax);
@@ -473,6 +487,9 @@ public:
         out.coords = (const int64_t*)(stage + off[0]); out.slen = (const int64_t*)(stage + off[1]); out.hashes = (const uint64_t*)(stage + off[2]);
         out.wins = (const WindowRec*)(stage + off[3]); out.k = (const int32_t*)(stage + off[4]); out.lon = (const int32_t*)(stage + off[5]);
         out.sp = (const int32_t*)(stage + off[6]); out.fwd = stage + off[7];
+        out.flags = (const uint32_t*)(stage + off[8]); out.parent = (const int32_t*)(stage + off[9]);
+        out.acc_shift = (const int32_t*)(stage + off[10]); out.acc_len = (const int32_t*)(stage + off[11]);
+        out.fw = (const int32_t*)(stage + off[12]); out.nfw = h_ctr[19]; out.fw_cap = rec::FW_CAP;
         const double t2 = wall_s();
         out.levels = rr_.level; out.deferred = h_ctr[17]; out.dropped = h_ctr[18];
         // statistics: searched windows, their reference / query bases (bench.py's algorithmic-byte model)
@@ -941,6 +958,8 @@ private:
     uint8_t* r_pairflag_ = nullptr;
     DevBuf<uint32_t> r_sortk_, r_sortv_;
     DevBuf<uint8_t> r_out_;
+    DevBuf<uint32_t> r_flags_, r_inv_;
+    DevBuf<int32_t> r_parent_, r_fw_, r_accshift_, r_acclen_;
     rsort::RadixSorter r_sorter_;
     prim::Scanner r_scanner_;
     size_t r_cand_hint_ = 0;

@@ -20,6 +20,7 @@ namespace pb200 {
 namespace rec {
 
 constexpr int NCLASS = 3;
+constexpr unsigned int FW_CAP = 65536;
 // a work-list entry: region id, optionally the PAIR (id, id + 1) = the two regions that cover one gap (the left side of a MUM
 // starts one base before the right side of its predecessor): the reference searches the one with the smaller start first and
 // the second one then sees its bits, so one CTA takes both, in that order
@@ -34,6 +35,8 @@ struct Queues {
     unsigned int* ndeferred;            // regions the device could not take (too large, minsize < 4, ...): left to the host
     unsigned int* dropped;              // children lost to a full store / list (the replay searches them on demand)
     int32_t* deferred;                  // their ids
+    unsigned int* nfw;                  // accepted MUMs written outside their region (reverse-strand genomes): count ...
+    int32_t* fw;                        // ... and (genome, start, length) records, FW_CAP at most (more: the host takes nothing as final)
     unsigned int cap;                   // capacity of the region store and of every list
 };
 
@@ -44,7 +47,23 @@ struct Store {
     int32_t* minsize;
     int32_t* ncand;                     // -1 = not searched (deferred / dropped), else candidates in the global arrays
     int64_t* cand_base;
+    // what the host needs to take the accept decisions made here as FINAL where they cannot depend on the order (host/replay.cpp):
+    uint32_t* flags;                    // F_* below
+    int32_t* parent;                    // the region whose accepted MUM this one lies beside (-1: an initial region)
+    int32_t* acc_shift;                 // per candidate (parallel to the global candidate arrays): -1 = not accepted, else the trim shift
+    int32_t* acc_len;                   //                                                          its accepted length
 };
+// a region's accept pass is order-independent unless ...
+constexpr uint32_t F_FOREIGN = 1;       // ... a candidate that reached the trim loop had a reverse-strand genome (coordinates mirrored on
+                                        //     the whole genome: it read - and, if accepted, wrote - the layout somewhere else)
+constexpr uint32_t F_SECOND = 2;        // ... it is the second region of a gap pair and accepted something (its sub-regions overlap the
+                                        //     first one's)
+constexpr uint32_t F_NONCOLLINEAR = 4;  // ... its accepted MUMs do not ascend in every genome (sub-regions overlap each other)
+constexpr uint32_t F_REQUEUED = 8;      // ... it was one region of a gap pair and overflowed a per-CTA capacity: it is searched again later,
+                                        //     on its own, i.e. not in the pair's order
+constexpr uint32_t F_ORDER_MASK = 15;   // any of the above: the host replays the region's gap itself
+constexpr uint32_t I_SECOND = 16;       // (information) the region was searched as the SECOND one of a gap pair, right after its mate
+static_assert(F_ORDER_MASK == REC_ORDER_MASK && I_SECOND == REC_SECOND, "common.h: RecursionResult::flags");
 
 struct Params {
     int n;                              // genomes
@@ -145,14 +164,14 @@ __device__ inline int region_class(const Params& P, const int64_t (&S)[GPL], con
 }
 template <int GPL>
 __device__ inline void write_region(const Params& P, const Store& St, unsigned int id, const int64_t (&S)[GPL], const int64_t (&E)[GPL], int64_t slength,
-                                    int ms, int lane) {
+                                    int ms, int lane, int parent) {
     const int n = P.n;
     int32_t* c = St.coords + (size_t)id * 2 * n;
     for (int t = 0; t < GPL; ++t) {
         const int g = lane + 32 * t;
         if (g < n) { c[g] = (int32_t)S[t]; c[n + g] = (int32_t)(E[t] - S[t]); }
     }
-    if (lane == 0) { St.slen[id] = (int32_t)slength; St.minsize[id] = ms; St.ncand[id] = -1; St.cand_base[id] = 0; }
+    if (lane == 0) { St.slen[id] = (int32_t)slength; St.minsize[id] = ms; St.ncand[id] = -1; St.cand_base[id] = 0; St.flags[id] = 0; St.parent[id] = parent; }
 }
 __device__ inline void enqueue(const Queues& Q, int next, int cls, int32_t entry) {        // one lane
     if (cls < NCLASS) {
@@ -167,34 +186,34 @@ __device__ inline void enqueue(const Queues& Q, int next, int cls, int32_t entry
 // append region (S[], E[]) to the store and to the next level's list of its class
 template <int GPL>
 __device__ inline void push_region(const Params& P, const Store& St, const Queues& Q, int next, const int64_t (&S)[GPL], const int64_t (&E)[GPL],
-                                   int64_t slength, int lane) {
+                                   int64_t slength, int lane, int parent) {
     int ms;
     const int cls = region_class<GPL>(P, S, E, slength, lane, ms);
     unsigned int id = 0;
     if (lane == 0) id = atomicAdd(Q.nregions, 1u);
     id = __shfl_sync(0xffffffffu, id, 0);
     if (id >= Q.cap) { if (lane == 0) { atomicSub(Q.nregions, 1u); atomicAdd(Q.dropped, 1u); } return; }
-    write_region<GPL>(P, St, id, S, E, slength, ms, lane);
+    write_region<GPL>(P, St, id, S, E, slength, ms, lane, parent);
     if (lane == 0) enqueue(Q, next, cls, (int32_t)id);
 }
 // the two regions of one gap: A (smaller start[0], searched first) and B, as ONE entry when the device can take both
 template <int GPL>
 __device__ inline void push_pair(const Params& P, const Store& St, const Queues& Q, int next, const int64_t (&SA)[GPL], const int64_t (&EA)[GPL],
-                                 int64_t slA, const int64_t (&SB)[GPL], const int64_t (&EB)[GPL], int64_t slB, int lane) {
+                                 int64_t slA, const int64_t (&SB)[GPL], const int64_t (&EB)[GPL], int64_t slB, int lane, int parent) {
     int msA, msB;
     const int clsA = region_class<GPL>(P, SA, EA, slA, lane, msA);
     const int clsB = region_class<GPL>(P, SB, EB, slB, lane, msB);
     if (clsA >= NCLASS || clsB >= NCLASS) {
-        push_region<GPL>(P, St, Q, next, SA, EA, slA, lane);
-        push_region<GPL>(P, St, Q, next, SB, EB, slB, lane);
+        push_region<GPL>(P, St, Q, next, SA, EA, slA, lane, parent);
+        push_region<GPL>(P, St, Q, next, SB, EB, slB, lane, parent);
         return;
     }
     unsigned int id = 0;
     if (lane == 0) id = atomicAdd(Q.nregions, 2u);
     id = __shfl_sync(0xffffffffu, id, 0);
     if (id + 1 >= Q.cap) { if (lane == 0) { atomicSub(Q.nregions, 2u); atomicAdd(Q.dropped, 2u); } return; }
-    write_region<GPL>(P, St, id, SA, EA, slA, msA, lane);
-    write_region<GPL>(P, St, id + 1, SB, EB, slB, msB, lane);
+    write_region<GPL>(P, St, id, SA, EA, slA, msA, lane, parent);
+    write_region<GPL>(P, St, id + 1, SB, EB, slB, msB, lane, parent);
     if (lane == 0) enqueue(Q, next, max(clsA, clsB), (int32_t)id | E_PAIR);
 }
 
@@ -204,9 +223,12 @@ template <int GPL>
 __device__ inline void accept_region(const Params& P, const Store& St, const Queues& Q, int next, const uint8_t* __restrict__ text,
                                      const int64_t* __restrict__ gbase_fwd, const int64_t* __restrict__ glen, int region, int nc, int64_t base,
                                      const int32_t* __restrict__ out_k, const int32_t* __restrict__ out_lon, const int32_t* __restrict__ out_sp,
-                                     const uint8_t* __restrict__ out_fwd, uint16_t* accC, uint16_t* accShift, uint16_t* accLen) {
+                                     const uint8_t* __restrict__ out_fwd, uint16_t* accC, uint16_t* accShift, uint16_t* accLen, bool second) {
     const int lane = threadIdx.x & 31;
     const int n = P.n, nq = n - 1;
+    uint32_t rflags = 0;
+    for (int c = lane; c < nc; c += 32) St.acc_shift[base + c] = -1;
+    __syncwarp();
     const int32_t* rc = St.coords + (size_t)region * 2 * n;
     int64_t rs[GPL], rl[GPL], gl[GPL];
     const unsigned long long* row[GPL];
@@ -238,6 +260,10 @@ __device__ inline void accept_region(const Params& P, const Store& St, const Que
             st[t] = s;
         }
         if (warp_or(fail) || LON < 5) continue;
+        int rev = 0;
+        for (int t = 0; t < GPL; ++t) rev |= (lane + 32 * t < n) && !fw[t];
+        rev = warp_or(rev);
+        if (rev) rflags |= F_FOREIGN;
         // trim (src/parsnp.cpp:1399-1477): genome after genome, every trim shifts ALL genomes.  Only the two ends of an interval
         // are looked at, so when no genome has a set bit at either end (the rule inside a gap) nothing moves.
         int64_t length = LON, shift = 0;
@@ -261,9 +287,8 @@ __device__ inline void accept_region(const Params& P, const Store& St, const Que
         if (length < 2) continue;
         // reverse-strand genomes are verified against the reference substring (src/parsnp.cpp:1800-1825)
         const int64_t s0 = __shfl_sync(0xffffffffu, st[0] + shift, 0);
-        int badmum = 0, anyrev = 0;
-        for (int t = 0; t < GPL; ++t) anyrev |= (lane + 32 * t < n) && !fw[t];
-        for (int g = 1; g < n && warp_or(anyrev); ++g) {
+        int badmum = 0;
+        for (int g = 1; g < n && rev; ++g) {
             const int t = g >> 5, owner = g & 31;
             const int isrev = __shfl_sync(0xffffffffu, (int)!fw[t], owner);
             if (!isrev) continue;
@@ -282,9 +307,37 @@ __device__ inline void accept_region(const Params& P, const Store& St, const Que
             const int g = lane + 32 * t;
             if (g < n) bits_set_range(const_cast<unsigned long long*>(row[t]), st[t] + shift, st[t] + shift + length);
         }
-        if (lane == 0) { accC[nacc] = (uint16_t)c; accShift[nacc] = (uint16_t)shift; accLen[nacc] = (uint16_t)length; }
+        if (rev) {                                              // a write outside the region: the host has to know where
+            for (int t = 0; t < GPL; ++t) {
+                const int g = lane + 32 * t;
+                if (g < n && !fw[t]) {
+                    const unsigned int at = atomicAdd(Q.nfw, 1u);
+                    if (at < FW_CAP) { Q.fw[3 * at] = g; Q.fw[3 * at + 1] = (int32_t)(st[t] + shift); Q.fw[3 * at + 2] = (int32_t)length; }
+                }
+            }
+        }
+        // accepted MUMs must ascend, without overlap, in every genome - else the sub-regions between them overlap
+        if (nacc > 0) {
+            const int pc = accC[nacc - 1];
+            const int64_t pshift = accShift[nacc - 1], plen = accLen[nacc - 1];
+            int bad = 0;
+            for (int t = 0; t < GPL; ++t) {
+                const int g = lane + 32 * t;
+                if (g >= n) continue;
+                const int64_t poff = g == 0 ? out_k[base + pc] : out_sp[(size_t)(base + pc) * nq + (g - 1)];
+                const int64_t pend = rs[t] + poff + pshift + plen;     // (forward: reverse-strand ones are flagged anyway)
+                if (st[t] + shift < pend) bad = 1;
+            }
+            if (warp_or(bad)) rflags |= F_NONCOLLINEAR;
+        }
+        if (lane == 0) {
+            accC[nacc] = (uint16_t)c; accShift[nacc] = (uint16_t)shift; accLen[nacc] = (uint16_t)length;
+            St.acc_shift[base + c] = (int32_t)shift; St.acc_len[base + c] = (int32_t)length;
+        }
         ++nacc;
     }
+    if (second && nacc > 0) rflags |= F_SECOND;
+    if (lane == 0 && rflags) St.flags[region] |= rflags;
     if (nacc == 0) return;
     __threadfence();                                            // (this warp's own atomics are ordered before its reads below)
     __syncwarp();
@@ -319,13 +372,13 @@ __device__ inline void accept_region(const Params& P, const Store& St, const Que
         }
         lsl = warp_min64(lsl);
         rsl = warp_min64(rsl);
-        if (lsl > P.q && psl > P.q) push_pair<GPL>(P, St, Q, next, lS, lE, lsl, pS, pE, psl, lane);
-        else if (lsl > P.q) push_region<GPL>(P, St, Q, next, lS, lE, lsl, lane);
-        else if (psl > P.q) push_region<GPL>(P, St, Q, next, pS, pE, psl, lane);
+        if (lsl > P.q && psl > P.q) push_pair<GPL>(P, St, Q, next, lS, lE, lsl, pS, pE, psl, lane, region);
+        else if (lsl > P.q) push_region<GPL>(P, St, Q, next, lS, lE, lsl, lane, region);
+        else if (psl > P.q) push_region<GPL>(P, St, Q, next, pS, pE, psl, lane, region);
         for (int t = 0; t < GPL; ++t) { pS[t] = rS[t]; pE[t] = rE[t]; }
         psl = rsl;
     }
-    if (psl > P.q) push_region<GPL>(P, St, Q, next, pS, pE, psl, lane);
+    if (psl > P.q) push_region<GPL>(P, St, Q, next, pS, pE, psl, lane, region);
 }
 
 // One level of one size class: CTAs take regions from the level's list until it is empty (dynamic scheduling), search the
@@ -360,7 +413,10 @@ __global__ void __launch_bounds__(small::SM_MAX_THREADS, 4) recursion_level_kern
         for (int half = 0; half < 2; ++half) {
             const int region = half == 0 ? first : second;
             if (region < 0) break;
-            if (half == 1) __syncthreads();                     // (warp 0 has finished the first region's accepts)
+            if (half == 1) {
+                __syncthreads();                                // (warp 0 has finished the first region's accepts)
+                if (threadIdx.x == 0) St.flags[region] |= I_SECOND;
+            }
             const int32_t* rc = St.coords + (size_t)region * 2 * P.n;
             small::TaskDev tk;
             tk.ref_off = gbase_fwd[0] + rc[0];
@@ -374,14 +430,17 @@ __global__ void __launch_bounds__(small::SM_MAX_THREADS, 4) recursion_level_kern
             const int64_t base = *reinterpret_cast<int64_t*>(&sv.s_int[4]);
             if (ovf) {
                 // a per-CTA capacity: this region alone goes to the next class (next level's list); anything else: the host
-                if (threadIdx.x == 0) enqueue(Q, next, ovf == 1 && cls + 1 < NCLASS ? cls + 1 : NCLASS, (int32_t)region);
+                if (threadIdx.x == 0) {
+                    if (entry & E_PAIR) St.flags[region] |= F_REQUEUED;
+                    enqueue(Q, next, ovf == 1 && cls + 1 < NCLASS ? cls + 1 : NCLASS, (int32_t)region);
+                }
                 continue;
             }
             if (threadIdx.x == 0) { St.ncand[region] = nc; St.cand_base[region] = base; }
             if (threadIdx.x < 32 && nc > 0) {
                 // (the candidate rows were written by this CTA before the barrier that ends small_window)
                 accept_region<GPL>(P, St, Q, next, text, gbase_fwd, glen, region, nc, base, out_k, out_lon, out_sp, out_fwd, sv.candK, sv.candM,
-                                   reinterpret_cast<uint16_t*>(sv.HQ));
+                                   reinterpret_cast<uint16_t*>(sv.HQ), half == 1);
             }
         }
     }
@@ -408,6 +467,8 @@ __global__ void seed_lists_kernel(Params P, Store St, Queues Q, const unsigned i
     St.minsize[id] = ms;
     St.ncand[id] = -1;
     St.cand_base[id] = 0;
+    St.flags[id] = 0;
+    St.parent[id] = -1;
     int cls = class_of(P, c[n], mm, ms);
     const bool second = id > 0 && pair[id - 1];
     bool head = pair[id] && id + 1 < count;
@@ -436,11 +497,13 @@ __global__ void region_keys_kernel(Store St, int n, unsigned int nr, uint32_t* _
     keys[i] = (uint32_t)St.coords[(size_t)i * 2 * n];
     vals[i] = i;
 }
-__global__ void sorted_counts_kernel(Store St, const uint32_t* __restrict__ perm, unsigned int nr, uint32_t* __restrict__ cnt) {
+// + the inverse permutation (store id -> sorted position) for the parent links
+__global__ void sorted_counts_kernel(Store St, const uint32_t* __restrict__ perm, unsigned int nr, uint32_t* __restrict__ cnt, uint32_t* __restrict__ inv) {
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nr) return;
     const int c = St.ncand[perm[i]];
     cnt[i] = c > 0 ? (uint32_t)c : 0u;
+    inv[perm[i]] = i;
 }
 // one warp per region: its record in the host's final form (int64 start / end coordinates, slength, window record, coordinate
 // hash) and its candidates, into sorted position
@@ -448,7 +511,9 @@ __global__ void gather_sorted_kernel(Store St, int n, const uint32_t* __restrict
                                      const int32_t* __restrict__ k, const int32_t* __restrict__ lon, const int32_t* __restrict__ sp,
                                      const uint8_t* __restrict__ fwd, int64_t* __restrict__ o_coords, int64_t* __restrict__ o_slen,
                                      WindowRec* __restrict__ o_wins, uint64_t* __restrict__ o_hash, int32_t* __restrict__ o_k,
-                                     int32_t* __restrict__ o_lon, int32_t* __restrict__ o_sp, uint8_t* __restrict__ o_fwd) {
+                                     int32_t* __restrict__ o_lon, int32_t* __restrict__ o_sp, uint8_t* __restrict__ o_fwd,
+                                     const uint32_t* __restrict__ inv, uint32_t* __restrict__ o_flags, int32_t* __restrict__ o_parent,
+                                     int32_t* __restrict__ o_shift, int32_t* __restrict__ o_alen) {
     const unsigned int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (i >= nr) return;
@@ -474,9 +539,15 @@ __global__ void gather_sorted_kernel(Store St, int n, const uint32_t* __restrict
             h ^= h >> 29;
         }
         o_hash[i] = h;
+        o_flags[i] = St.flags[r];
+        const int par = St.parent[r];
+        o_parent[i] = par < 0 ? -1 : (int32_t)inv[par];
     }
     if (nc <= 0) return;
-    for (int x = lane; x < nc; x += 32) { o_k[nb + x] = k[ob + x]; o_lon[nb + x] = lon[ob + x]; }
+    for (int x = lane; x < nc; x += 32) {
+        o_k[nb + x] = k[ob + x]; o_lon[nb + x] = lon[ob + x];
+        o_shift[nb + x] = St.acc_shift[ob + x]; o_alen[nb + x] = St.acc_len[ob + x];
+    }
     const int64_t rows = (int64_t)nc * nq;
     for (int64_t x = lane; x < rows; x += 32) { o_sp[nb * nq + x] = sp[ob * nq + x]; o_fwd[nb * nq + x] = fwd[ob * nq + x]; }
 }

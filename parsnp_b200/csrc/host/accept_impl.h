@@ -4,7 +4,7 @@
 //   TaskAccess     a replay task's view of the shared bitmaps (replay.cpp): its own span directly, everything else through
 //                  the ownership rules that keep the parallel replay identical to the reference's sequential order
 // A policy provides  get / run_up / run_down / prev_set / next_set  per genome and  commit(st, length)  = "set the accepted
-// MUM's bits in every genome".
+// MUM's bits in every genome" (fw: its strand per genome).
 #pragma once
 #include "aligner.h"
 
@@ -28,7 +28,7 @@ struct DirectAccess {
     inline int64_t run_down(int g, int64_t a, int64_t b) { return L[g].run_down(a, b); }
     inline int64_t prev_set(int g, int64_t i) { return L[g].prev_set(i); }
     inline int64_t next_set(int g, int64_t i, int64_t limit) { return L[g].next_set(i, limit); }
-    inline void commit(const int64_t* st, int64_t length, int n) {
+    inline void commit(const int64_t* st, int64_t length, int n, const uint8_t*) {
         for (int k = 0; k < n; ++k) {
             if (atomic) L[k].set_range_atomic(st[k], st[k] + length);
             else L[k].set_range(st[k], st[k] + length);
@@ -129,7 +129,7 @@ void Aligner::accept_candidates_t(const int64_t* rs, const int64_t* re, int64_t 
                     if (comp_base(gk[length - 1 - t]) != g0[t]) { badmum = true; break; }
             }
             if (badmum) continue;
-            acc.commit(st, length, n_);
+            acc.commit(st, length, n_, fw);
             MumRec m;
             m.length = length;
             m.slength = rsl;

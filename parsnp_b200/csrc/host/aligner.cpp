@@ -1524,6 +1524,13 @@ bool Aligner::discover_slice(int k) {
         C.rp.ext_coord = res.coords;
         cb.vk = res.k; cb.vlon = res.lon; cb.vsp = res.sp; cb.vfwd = res.fwd; cb.vcount = NC;
     }
+    dev_ = DeviceDecisions();
+    if (!copy && res.flags && res.parent && res.acc_shift && res.acc_len && res.dropped == 0 && res.nfw <= res.fw_cap && !getenv("PB200_NO_DEVICE_FINAL")) {
+        dev_.valid = true;
+        dev_.nregions = NR; dev_.ncands = NC; dev_.nfw = res.nfw;
+        dev_.coords = res.coords; dev_.slen = res.slen; dev_.wins = res.wins; dev_.k = res.k; dev_.sp = res.sp;
+        dev_.flags = res.flags; dev_.parent = res.parent; dev_.acc_shift = res.acc_shift; dev_.acc_len = res.acc_len; dev_.fw = res.fw;
+    }
     std::vector<uint8_t> valid(NR);
     std::vector<uint64_t> hashes(res.hashes, res.hashes + NR);
     const long nblk = ((long)NR + per - 1) / per;

@@ -125,6 +125,7 @@ struct AlignStats {
     // foreign write hit a running task, 1 = the run fell back to the sequential loop (ties or non-collinear anchors), workers
     int64_t replay_tasks = 0, replay_foreign_reads = 0, replay_foreign_writes = 0, replay_restarts = 0, replay_fallback = 0,
             replay_workers = 1, spec_deferred = 0;
+    int64_t replay_gaps = 0, replay_final_gaps = 0, replay_final_mums = 0;      // gaps whose accept decisions were taken from the engine as final
     double t_replay_merge = 0;
 };
 
@@ -291,6 +292,17 @@ private:
     std::exception_ptr spec_error_;
     bool pipeline_ = true;
     bool anchors_on_device_ = false;                        // the engine placed the anchors and is following the recursion (anchor_stage)
+    // the engine's own accept decisions of its discovery (RecursionResult: views into its pinned memory, valid during the replay),
+    // which the parallel replay takes as final for the gaps where they cannot depend on the order (replay.cpp); valid = false:
+    // every gap is replayed
+    struct DeviceDecisions {
+        bool valid = false;
+        size_t nregions = 0, ncands = 0, nfw = 0;
+        const int64_t* coords = nullptr; const int64_t* slen = nullptr; const WindowRec* wins = nullptr;
+        const int32_t* k = nullptr; const int32_t* sp = nullptr;
+        const uint32_t* flags = nullptr; const int32_t* parent = nullptr; const int32_t* acc_shift = nullptr; const int32_t* acc_len = nullptr;
+        const int32_t* fw = nullptr;
+    } dev_;
     int replay_threads_ = 0;                                // 0 = threads_
     ReplayCtx* replay_ctx_ = nullptr;
     std::thread replay_prep_thread_;

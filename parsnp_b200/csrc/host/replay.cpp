@@ -26,6 +26,18 @@
 //     that are not collinear (rearranged genomes: spans out of order, or initial regions that tie) skip the parallel part.
 //
 // Tasks are handed out in ascending order, so the lowest running task never waits and the scheme cannot deadlock.
+//
+// FINAL GAPS.  When the engine followed the recursion itself (cuda/recursion.cuh) it has already run loop D + determineRegion
+// for every region it discovered, on a scratch layout and level by level instead of in the reference's order.  Inside one gap
+// that difference cannot matter when (a) no candidate that reached the trim loop had a reverse-strand genome (everything read
+// and written lies inside the region), (b) the accepted MUMs of every region ascend in every genome (sibling sub-regions are
+// disjoint: they commute), (c) the two overlapping regions of a gap pair were searched in the reference's order by one CTA and
+// the second one accepted nothing (more bits only trim more: it accepts nothing in the reference's order either), and (d) no
+// MUM of another gap was written into the gap's span - neither on the device (its list of writes outside their region) nor
+// here (every accepted MUM with a reverse-strand genome marks the gaps it touches).  For such a gap the task appends the
+// engine's accepted MUMs - regions in ascending start[0] order, candidates in order: the reference's pop order - and sets
+// their bits, without lookup, trim, determineRegion or queue.  Everything else (the foreign access rules above, restarts) is
+// unchanged: a final gap is just a gap whose replay is cheap.
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -35,6 +47,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <stdexcept>
 #include <thread>
 #include "accept_impl.h"
 #include "parallel.h"
@@ -70,15 +83,15 @@ struct ReplayTask {
     std::atomic<uint32_t> nlog{0};
     std::atomic<bool> log_overflow{false};      // more reads than the log holds: "has read everything"
     std::unique_ptr<Aligner::CandCache> local;  // regions searched on demand (not predicted by the speculation)
-    int64_t n_fread = 0, n_fwrite = 0, misses = 0, regions = 0, slow_iters = 0;
+    int64_t n_fread = 0, n_fwrite = 0, misses = 0, regions = 0, slow_iters = 0, final_gaps = 0, final_mums = 0;
     double t_wait = 0, t_search = 0;
     struct SegCache { int g = -1, owner = -1, gap = -1; int64_t slo = 0, shi = -1; } sc;   // last ownership lookup (run_up and run_down of one candidate hit the same segment)
-    uint64_t pc[6] = {0, 0, 0, 0, 0, 0};          // PB200_PROFILE_HOST: cycles in setup / pop / lookup / accept / det_region / queue
+    uint64_t pc[7] = {0, 0, 0, 0, 0, 0, 0};       // PB200_PROFILE_HOST: cycles in setup / pop / lookup / accept / det_region / queue / final gaps
     void reset() {
         worker = -1; mbegin = mend = 0;
         nlog.store(0, std::memory_order_relaxed); log_overflow.store(false, std::memory_order_relaxed);
         local.reset();
-        n_fread = n_fwrite = misses = regions = slow_iters = 0;
+        n_fread = n_fwrite = misses = regions = slow_iters = final_gaps = final_mums = 0;
         for (auto& x : pc) x = 0;
         sc = SegCache();
     }
@@ -111,6 +124,16 @@ struct ReplayCtx {
     std::vector<int32_t> glo, ghi;
     std::vector<int64_t> gend0;                 // largest end[0] of the gap's regions
     std::unique_ptr<std::atomic<uint8_t>[]> gdone;
+    std::vector<int> gcut;                      // gap j = positions [gcut[j], gcut[j + 1]) of `order`
+    // final gaps (see the head of the file): candidates after classify_gaps(), their regions [gr0, gr1) in the engine's sorted
+    // list; gtouched[j] = a MUM with a reverse-strand genome was (or, by the engine's prediction, would be) written into gap j
+    bool any_final = false;
+    std::vector<uint8_t> gfinal;
+    std::vector<int32_t> gr0, gr1;
+    std::unique_ptr<std::atomic<uint8_t>[]> gtouched;
+    void classify_gaps();
+    void mark_touched(int g, int64_t a, int64_t b);
+    void apply_final_gap(ReplayTask& T, MumPool& MP, int j, const int64_t* lo, const int64_t* hi);
     std::unique_ptr<ReplayTask::FRead[]> log_slab;
     // per worker: an append-only arena for the MUMs of the tasks it ran (a restarted task leaves its first attempt behind as
     // unreferenced garbage) and a region pool that is cleared for every task
@@ -305,7 +328,9 @@ struct TaskAccess {
         }
         return X.f_next_set(T, k, g, i, limit);
     }
-    inline void commit(const int64_t* st, int64_t length, int n) {
+    inline void commit(const int64_t* st, int64_t length, int n, const uint8_t* fw) {
+        if (X.any_final)                          // (before the bits: a gap that is about to be taken as final must see the mark)
+            for (int g = 0; g < n; ++g) if (!fw[g]) X.mark_touched(g, st[g], st[g] + length);
         bool foreign = false;
         for (int g = 0; g < n; ++g) foreign |= !home(g, st[g], st[g] + length);
         if (!foreign) {
@@ -386,8 +411,124 @@ void ReplayCtx::restart_above(int k) {
     cv.notify_all();
 }
 
+// the gaps that [a, b) of genome g touches (gaps ascend in every genome; the bounding anchor bits count: conservative)
+void ReplayCtx::mark_touched(int g, int64_t a, int64_t b) {
+    if (a >= b || ngaps == 0) return;
+    int lo = 0, hi = ngaps;                     // first gap j with ghi[j][g] >= a
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((int64_t)ghi[(size_t)mid * n + g] < a) lo = mid + 1; else hi = mid;
+    }
+    for (int j = lo; j < ngaps && (int64_t)glo[(size_t)j * n + g] <= b - 1; ++j) gtouched[j].store(1, std::memory_order_relaxed);
+}
+
+// which gaps may take the engine's accept decisions as final (conditions (a)-(d) at the head of the file; the dynamic part of
+// (d) is checked again when the gap's turn comes)
+void ReplayCtx::classify_gaps() {
+    gfinal.assign((size_t)ngaps, 0);
+    gr0.assign((size_t)ngaps, 0);
+    gr1.assign((size_t)ngaps, 0);
+    any_final = false;
+    const Aligner::DeviceDecisions& D = A.dev_;
+    if (!D.valid || ngaps < 2) return;
+    const size_t NR = D.nregions, stride = 2 * (size_t)n;
+    for (size_t i = 0; i < D.nfw; ++i) {
+        const int g = D.fw[3 * i];
+        if (g < 0 || g >= n) return;
+        mark_touched(g, D.fw[3 * i + 1], (int64_t)D.fw[3 * i + 1] + D.fw[3 * i + 2]);
+    }
+    struct S0 {                                 // start[0] of the engine's regions as a random-access range
+        const int64_t* c; size_t stride;
+        int64_t operator()(size_t r) const { return c[r * stride]; }
+    } start0{D.coords, stride};
+    auto first_at_least = [&](int64_t v) {
+        size_t a = 0, b = NR;
+        while (a < b) { const size_t mid = (a + b) >> 1; if (start0(mid) < v) a = mid + 1; else b = mid; }
+        return a;
+    };
+    std::atomic<int> some(0);
+    const long per = 512;
+    parallel_chunks(ngaps > 2048 ? A.threads_ : 1, ((long)ngaps + per - 1) / per, [&](long c) {
+        bool mine = false;
+        // (gap 0 stays with the replay: the reference's first pop precedes its first sort, see run_task)
+        for (int j = std::max<int>(1, (int)(c * per)); j < std::min<int>(ngaps, (int)((c + 1) * per)); ++j) {
+            const int p0 = gcut[(size_t)j], p1 = gcut[(size_t)j + 1], ni = p1 - p0;
+            if (ni > 2 || gtouched[j].load(std::memory_order_relaxed)) continue;
+            const size_t r0 = first_at_least(glo[(size_t)j * n]), r1 = first_at_least(ghi[(size_t)j * n]);
+            if (r1 - r0 < (size_t)ni || r1 > (size_t)INT32_MAX) continue;
+            bool ok = true;
+            int ninit = 0, nsecond = 0;
+            int64_t prev = INT64_MIN;
+            for (size_t r = r0; r < r1 && ok; ++r) {
+                const uint32_t f = D.flags[r];
+                const WindowRec& w = D.wins[r];
+                const int64_t* rc = D.coords + r * stride;
+                ok = !(f & REC_ORDER_MASK) && w.ncand >= 0 && (uint64_t)w.cand_off + (uint64_t)w.ncand <= D.ncands && rc[0] > prev;
+                prev = rc[0];
+                const int par = D.parent[r];
+                if (par < 0) {
+                    bool known = false;         // one of the gap's own initial regions
+                    for (int p = p0; p < p1 && !known; ++p)
+                        known = std::memcmp(rc, A.rstart(A.initial_regions_[(size_t)order[(size_t)p]]), sizeof(int64_t) * stride) == 0;
+                    ok = ok && known;
+                    ++ninit;
+                    if (f & REC_SECOND) ++nsecond;
+                } else if ((size_t)par < r0 || (size_t)par >= r1) ok = false;
+            }
+            if (!ok || ninit != ni || (ni == 2 && nsecond != 1)) continue;
+            gfinal[(size_t)j] = 1;
+            gr0[(size_t)j] = (int32_t)r0;
+            gr1[(size_t)j] = (int32_t)r1;
+            mine = true;
+        }
+        if (mine) some.store(1, std::memory_order_relaxed);
+    });
+    any_final = some.load() != 0;
+}
+
+// the engine's accepted MUMs of gap j into the task's output and the layout, in the reference's pop order
+void ReplayCtx::apply_final_gap(ReplayTask& T, MumPool& MP, int j, const int64_t* lo, const int64_t* hi) {
+    const Aligner::DeviceDecisions& D = A.dev_;
+    const size_t stride = 2 * (size_t)n;
+    const int nq = n - 1;
+    int64_t st_buf[64];
+    std::vector<int64_t> st_vec;
+    int64_t* st = st_buf;
+    if (n > 64) { st_vec.resize((size_t)n); st = st_vec.data(); }
+    for (size_t r = (size_t)gr0[(size_t)j]; r < (size_t)gr1[(size_t)j]; ++r) {
+        const WindowRec& w = D.wins[r];
+        const int64_t* rs = D.coords + r * stride;
+        for (int32_t c = 0; c < w.ncand; ++c) {
+            const size_t ci = (size_t)w.cand_off + (size_t)c;
+            const int64_t sh = D.acc_shift[ci];
+            if (sh < 0) continue;
+            const int64_t length = D.acc_len[ci];
+            st[0] = w.ref_start + D.k[ci] + sh;
+            const int32_t* sp = D.sp + ci * (size_t)nq;
+            for (int g = 1; g < n; ++g) st[g] = rs[g] + sp[g - 1] + sh;
+            for (int g = 0; g < n; ++g) {
+                if (st[g] < lo[g] || st[g] + length > hi[g] + 1 || length < 2) throw std::logic_error("parsnp_b200: a MUM of a final gap lies outside its task");
+                truth[(size_t)g].set_range_owned(st[g], st[g] + length, lo[g] >> 6, hi[g] >> 6);
+            }
+            MumRec m;
+            m.length = length;
+            m.slength = D.slen[r];
+            m.off = (int64_t)MP.start.size();
+            m.alive = true;
+            MP.start.insert(MP.start.end(), st, st + n);
+            MP.fwd.insert(MP.fwd.end(), (size_t)n, (uint8_t)1);
+            MP.mums.push_back(m);
+            ++T.final_mums;
+        }
+    }
+    T.mend = MP.mums.size();
+    ++T.final_gaps;
+}
+
 namespace {
-struct QE { int64_t s0; int id; int slice; uint64_t hash; };
+// gap, pos: of an initial region (its gap and its position in `order`), -1 for sub-regions; id < 0: an initial region of a final
+// gap that has not been copied into the task's pool (it will be needed only if the gap has to be replayed after all)
+struct QE { int64_t s0; int id; int slice; uint64_t hash; int gap; int pos; };
 }
 
 // the loop of Aligner::process_queue_exact restricted to one task (its queue is a contiguous piece of the reference's queue:
@@ -417,13 +558,21 @@ void ReplayCtx::run_task(int k, int w, std::vector<int>& found, std::vector<int>
     const size_t cbytes = sizeof(int64_t) * 2 * (size_t)n;
     std::vector<QE> fast;                       // descending start[0]: the back is the front of the reference's vector
     fast.reserve((size_t)(T.last - T.first) + 16);
-    for (int p = T.last - 1; p >= T.first; --p) {
+    for (int p = T.last - 1, j = T.glast - 1; p >= T.first; --p) {
         const int i = order[(size_t)p];
+        while (p < gcut[(size_t)j]) --j;
+        const int slice = (size_t)i < A.slice_of_initial_.size() ? A.slice_of_initial_[(size_t)i] : -1;
+        if (any_final && gfinal[(size_t)j]) { fast.push_back(QE{keys[(size_t)p], -1, slice, 0, j, p}); continue; }
         const int r = A.initial_regions_[(size_t)i];
         const int id = RP.add(A.rp_.start(r), A.rp_.end(r));
-        fast.push_back(QE{RP.start(id)[0], id, (size_t)i < A.slice_of_initial_.size() ? A.slice_of_initial_[(size_t)i] : -1,
-                          Aligner::coords_hash(RP.start(id), 2 * n)});
+        fast.push_back(QE{RP.start(id)[0], id, slice, Aligner::coords_hash(RP.start(id), 2 * n), j, p});
     }
+    auto materialize = [&](QE& e) {
+        if (e.id >= 0) return;
+        const int r = A.initial_regions_[(size_t)order[(size_t)e.pos]];
+        e.id = RP.add(A.rp_.start(r), A.rp_.end(r));
+        e.hash = Aligner::coords_hash(RP.start(e.id), 2 * n);
+    };
     if (k == 0) {
         // the reference takes regions.begin() BEFORE its first sort (src/parsnp.cpp:192-195): the very first region searched is
         // the first one pushed, whatever its key (the right side of the first anchor when its left side was too short, while
@@ -444,6 +593,8 @@ void ReplayCtx::run_task(int k, int w, std::vector<int>& found, std::vector<int>
     unsigned rnd = 12345u + (unsigned)k * 2654435761u;
     // slow mode = the reference's literal vector handling while two DIFFERENT regions share a start[0] (see below)
     bool slow = false, first_pop = true;
+    int applied = -1;                           // the gap whose MUMs were just taken from the engine
+    int pf_gap = T.gfirst - 1;                  // layout rows prefetched up to this gap
     std::vector<QE> lvec;                       // ascending; the front is the front of the reference's vector
     PROF_MARK(0);
     const size_t R = order.size();
@@ -461,7 +612,25 @@ void ReplayCtx::run_task(int k, int w, std::vector<int>& found, std::vector<int>
         // regions come in ascending start[0] order and a sub-region starts at most one base before its parent: every gap that
         // ends before cur.s0 - 1 has nothing left in the queue and never will - its part of the layout is final
         while (gnext < T.glast && gend0[(size_t)gnext] <= cur.s0 - 1) gdone[gnext++].store(1, std::memory_order_release);
+        if (cur.gap > pf_gap) {
+            // the layout rows of the gaps ahead: nine-odd cache lines per gap that nothing else brings in (a gap costs little
+            // more than these misses once its decisions come from the engine)
+            for (int j = std::max(pf_gap + 1, cur.gap) + 1; j <= cur.gap + 3 && j < T.glast; ++j)
+                for (int g = 0; g < n; ++g) __builtin_prefetch(truth[(size_t)g].words() + (glo[(size_t)j * n + g] >> 6), 1);
+            pf_gap = cur.gap + 2;
+        }
         PROF_MARK(1);
+        if (cur.gap >= 0 && any_final) {
+            if (cur.gap == applied) continue;                   // (the gap's other initial region)
+            if (!slow && gfinal[(size_t)cur.gap] && !gtouched[cur.gap].load(std::memory_order_relaxed)) {
+                apply_final_gap(T, MP, cur.gap, lo.data(), hi.data());
+                applied = cur.gap;
+                first_pop = false;
+                PROF_MARK(6);
+                continue;
+            }
+        }
+        materialize(cur);
         const Aligner::CandCache* C = nullptr;
         if (cur.slice >= 0 && cur.slice < (int)A.slice_cache_.size()) {
             if (cur.slice >= ready_upto) {
@@ -510,7 +679,10 @@ void ReplayCtx::run_task(int k, int w, std::vector<int>& found, std::vector<int>
             for (size_t a = 0; a < children.size() && !distinct_tie; ++a) {
                 const int64_t key = RP.start(children[a])[0];
                 const size_t pos = fast_pos(key);
-                if (pos < fast.size() && fast[pos].s0 == key && !req(fast[pos].id, children[a])) distinct_tie = true;
+                if (pos < fast.size() && fast[pos].s0 == key) {
+                    materialize(fast[pos]);
+                    if (!req(fast[pos].id, children[a])) distinct_tie = true;
+                }
                 for (size_t b = 0; b < a && !distinct_tie; ++b)
                     if (key == RP.start(children[b])[0] && !req(children[a], children[b])) distinct_tie = true;
             }
@@ -519,7 +691,7 @@ void ReplayCtx::run_task(int k, int w, std::vector<int>& found, std::vector<int>
                     const int64_t key = RP.start(ch)[0];
                     const size_t pos = fast_pos(key);
                     if (pos < fast.size() && fast[pos].s0 == key) continue;
-                    fast.insert(fast.begin() + (long)pos, QE{key, ch, cur.slice, Aligner::coords_hash(RP.start(ch), 2 * n)});
+                    fast.insert(fast.begin() + (long)pos, QE{key, ch, cur.slice, Aligner::coords_hash(RP.start(ch), 2 * n), -1, -1});
                 }
                 first_pop = false;
                 PROF_MARK(5);
@@ -532,6 +704,7 @@ void ReplayCtx::run_task(int k, int w, std::vector<int>& found, std::vector<int>
             // sort (the reference's vector is still in push order) the run goes back to the sequential loop.
             if (getenv("PB200_REPLAY_DEBUG")) fprintf(stderr, "[pb200 replay] task %d: tie between different regions, literal queue until it is gone\n", k);
             if (k == 0 && first_pop) throw NeedFallback();
+            for (QE& e : fast) materialize(e);
             lvec.assign(fast.rbegin(), fast.rend());
             fast.clear();
             slow = true;
@@ -540,7 +713,7 @@ void ReplayCtx::run_task(int k, int w, std::vector<int>& found, std::vector<int>
         ++T.slow_iters;
         const double tslow0 = prof ? now_s() : 0;
         const size_t before = lvec.size();
-        for (int ch : children) lvec.push_back(QE{RP.start(ch)[0], ch, cur.slice, Aligner::coords_hash(RP.start(ch), 2 * n)});
+        for (int ch : children) lvec.push_back(QE{RP.start(ch)[0], ch, cur.slice, Aligner::coords_hash(RP.start(ch), 2 * n), -1, -1});
         if (!lvec.empty()) {
             std::vector<int64_t> lkeys(lvec.size());
             for (size_t i = 0; i < lvec.size(); ++i) lkeys[i] = lvec[i].s0;
@@ -752,7 +925,8 @@ ReplayCtx* Aligner::replay_prepare() {
     // gaps: runs of regions between cuts (the two regions of one anchor gap, and whatever else overlaps, stay together);
     // tasks: runs of gaps with >= `per` regions
     const size_t per = et ? (size_t)std::max(1, atoi(et)) : std::min<size_t>(128, std::max<size_t>(8, R / ((size_t)W * 24) + 1));
-    std::vector<int> gcut(1, 0);                 // gap j = positions [gcut[j], gcut[j+1])
+    std::vector<int>& gcut = X.gcut;             // gap j = positions [gcut[j], gcut[j+1])
+    gcut.assign(1, 0);
     for (size_t p = 1; p < R; ++p) if (cut[p]) gcut.push_back((int)p);
     gcut.push_back((int)R);
     X.ngaps = (int)gcut.size() - 1;
@@ -760,9 +934,11 @@ ReplayCtx* Aligner::replay_prepare() {
     X.ghi.resize((size_t)X.ngaps * n_);
     X.gend0.resize((size_t)X.ngaps);
     X.gdone.reset(new std::atomic<uint8_t>[(size_t)X.ngaps]);
+    X.gtouched.reset(new std::atomic<uint8_t>[(size_t)X.ngaps]);
     parallel_chunks(X.ngaps > 4096 ? threads_ : 1, ((long)X.ngaps + 1023) / 1024, [&](long c) {
         for (int j = (int)c * 1024; j < std::min(X.ngaps, (int)(c + 1) * 1024); ++j) {
             X.gdone[j].store(0, std::memory_order_relaxed);
+            X.gtouched[j].store(0, std::memory_order_relaxed);
             int64_t e0 = 0;
             for (int g = 0; g < n_; ++g) {
                 int64_t lo = INT64_MAX, hi = -1;
@@ -838,6 +1014,8 @@ bool Aligner::replay_run(ReplayCtx& X) {
         const size_t est = (size_t)stats_.anchors * 4 / (size_t)nw + 1024;       // (about 3 recursion MUMs per anchor on divergent genomes)
         for (auto& m : X.wmp) { m.mums.reserve(est); m.start.reserve(est * (size_t)n_); m.fwd.reserve(est * (size_t)n_); }
     }
+    const double tc0 = now_s();
+    X.classify_gaps();
     const double tr0 = now_s();
     // (the process-wide pool of sleeping threads: no thread is created per alignment.  If the pool is busy - the host's own
     //  level-by-level speculation uses it when the engine does not follow the recursion itself - the workers run one after the
@@ -851,7 +1029,12 @@ bool Aligner::replay_run(ReplayCtx& X) {
         parallel_chunks(nw, (long)nw, [&X](long w) { X.worker((int)w); });
     }
     if (X.error) std::rethrow_exception(X.error);
-    if (getenv("PB200_PROFILE_HOST")) fprintf(stderr, "[pb200 replay ms] setup %.2f tasks %.2f (%d workers, %d tasks, %d gaps)\n", X.t_setup * 1e3, (now_s() - tr0) * 1e3, nw, X.ntasks, X.ngaps);
+    if (getenv("PB200_PROFILE_HOST")) {
+        int64_t fg = 0, fm = 0;
+        for (int k = 0; k < X.ntasks; ++k) { fg += X.tasks[k].final_gaps; fm += X.tasks[k].final_mums; }
+        fprintf(stderr, "[pb200 replay ms] setup %.2f classify %.2f tasks %.2f (%d workers, %d tasks, %d gaps, %lld final with %lld MUMs)\n", X.t_setup * 1e3,
+                (tr0 - tc0) * 1e3, (now_s() - tr0) * 1e3, nw, X.ntasks, X.ngaps, (long long)fg, (long long)fm);
+    }
 
     // ---- the finished tasks' MUMs into the pools, task after task = the reference's push order
     const double tm0 = now_s();
@@ -907,21 +1090,24 @@ bool Aligner::replay_run(ReplayCtx& X) {
                        [&](int x, int y) { return key(x) < key(y); });
         });
     }
-    uint64_t pcs[6] = {0, 0, 0, 0, 0, 0};
+    uint64_t pcs[7] = {0, 0, 0, 0, 0, 0, 0};
     for (int k = 0; k < F; ++k) {
         const ReplayTask& T = X.tasks[k];
         stats_.replay_foreign_reads += T.n_fread;
         stats_.replay_foreign_writes += T.n_fwrite;
         stats_.replay_misses += T.misses;
         stats_.slow_queue_iters += T.slow_iters;
-        for (int i = 0; i < 6; ++i) pcs[i] += T.pc[i];
+        stats_.replay_final_gaps += T.final_gaps;
+        stats_.replay_final_mums += T.final_mums;
+        for (int i = 0; i < 7; ++i) pcs[i] += T.pc[i];
         stats_.t_replay_wait += T.t_wait / nw;
         stats_.t_replay_search += T.t_search;
     }
     if (getenv("PB200_PROFILE_HOST"))
-        fprintf(stderr, "[pb200 replay tasks cycles] setup %llu pop %llu lookup %llu accept %llu det_region %llu queue %llu\n", (unsigned long long)pcs[0],
-                (unsigned long long)pcs[1], (unsigned long long)pcs[2], (unsigned long long)pcs[3], (unsigned long long)pcs[4], (unsigned long long)pcs[5]);
+        fprintf(stderr, "[pb200 replay tasks cycles] setup %llu pop %llu lookup %llu accept %llu det_region %llu queue %llu final gaps %llu\n", (unsigned long long)pcs[0],
+                (unsigned long long)pcs[1], (unsigned long long)pcs[2], (unsigned long long)pcs[3], (unsigned long long)pcs[4], (unsigned long long)pcs[5], (unsigned long long)pcs[6]);
     stats_.replay_tasks = F;
+    stats_.replay_gaps = X.ngaps;
     stats_.replay_restarts = X.restarts;
     stats_.replay_workers = nw;
     stats_.t_replay_merge += now_s() - tm0;

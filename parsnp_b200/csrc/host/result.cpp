@@ -46,7 +46,8 @@ pb200_result* make_result(const Aligner& a, bool unaligned) {
                  s.t_lcb, s.t_total, (double)s.host_threads, s.t_search_prep, s.t_search_backend, s.t_search_cache, s.t_replay_wait,
                  (double)s.spec_slices, (double)s.mums_filtered, (double)s.clusters_filtered,
                  (double)s.replay_tasks, (double)s.replay_foreign_reads, (double)s.replay_foreign_writes, (double)s.replay_restarts,
-                 (double)s.replay_fallback, (double)s.replay_workers, s.t_replay_merge, (double)s.spec_deferred };
+                 (double)s.replay_fallback, (double)s.replay_workers, s.t_replay_merge, (double)s.spec_deferred,
+                 (double)s.replay_gaps, (double)s.replay_final_gaps, (double)s.replay_final_mums };
     return r;
 }
 
@@ -158,7 +159,8 @@ int pb200_result_stats(const pb200_result* r, double* values, int cap) {
 const char* pb200_stats_names(void) {
     return "anchors,regions_searched,spec_regions,replay_misses,spec_levels,windows_searched,candidates,slow_queue_iters,"
            "t_anchor_search,t_anchor_host,t_spec_search,t_spec_host,t_replay,t_replay_search,t_lcb,t_total,host_threads,t_search_prep,t_search_backend,t_search_cache,t_replay_wait,spec_slices,mums_filtered,clusters_filtered,"
-           "replay_tasks,replay_foreign_reads,replay_foreign_writes,replay_restarts,replay_fallback,replay_workers,t_replay_merge,spec_deferred";
+           "replay_tasks,replay_foreign_reads,replay_foreign_writes,replay_restarts,replay_fallback,replay_workers,t_replay_merge,spec_deferred,"
+           "replay_gaps,replay_final_gaps,replay_final_mums";
 }
 void pb200_result_free(pb200_result* r) { delete r; }
 int pb200_minsize(const char* expr, int64_t slength) {

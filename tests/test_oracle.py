@@ -233,6 +233,45 @@ def test_host_fuzz_against_reference_binary():
     assert int(r.stdout.rsplit("mismatches,", 1)[1].split()[0]) <= 2, r.stdout[-2000:]
 
 
+@pytest.mark.parametrize("name", ["indep_20k", "rearr_60k", "pop_30k_x12", "windows_50k"])
+@pytest.mark.parametrize("task,maxlen", [(1, 4096), (7, 120)])
+def test_final_gaps_reproduce_reference(name, task, maxlen, monkeypatch):
+    """the parallel replay takes the accept decisions of the engine's discovery as FINAL for the gaps where they cannot depend on
+    the order (host/replay.cpp "final gaps"); the discovery here is the CPU emulation of the device pass
+    (oracle/discover_emul.cpp: levels, regions of a level in random order, pairs in the reference's order) == golden"""
+    from oracle import hosttest
+    monkeypatch.setenv("PB200_REPLAY_MODE", "par")
+    monkeypatch.setenv("PB200_REPLAY_OWN_THREADS", "1")
+    monkeypatch.setenv("PB200_HOST_THREADS", "3")
+    monkeypatch.setenv("PB200_REPLAY_TASK", str(task))
+    monkeypatch.setenv("PB200_EMUL_MAXLEN", str(maxlen))
+    g, kw, gold = golden_case(name)
+    nfinal = 0
+    for seed in (1, 2, 3):
+        monkeypatch.setenv("PB200_EMUL_SEED", str(seed))
+        res = hosttest.align(g, api.make_params(**kw), backend=3)
+        assert diff_dumps(result_to_dump(res), gold) == []
+        nfinal += res["stats"]["replay_final_gaps"]
+        monkeypatch.setenv("PB200_NO_DEVICE_FINAL", "1")           # the same discovery with every gap replayed
+        res = hosttest.align(g, api.make_params(**kw), backend=3)
+        assert diff_dumps(result_to_dump(res), gold) == [] and res["stats"]["replay_final_gaps"] == 0
+        monkeypatch.delenv("PB200_NO_DEVICE_FINAL")
+    if name == "indep_20k":
+        assert nfinal > 0
+
+
+def test_final_gaps_fuzz():
+    """tools/fuzz_replay.py through the emulated discovery (FUZZ_BACKEND=3): sequential loop == parallel replay with final gaps on
+    random sets with 8-12 base MUMs (chance reverse-strand candidates: foreign reads and writes that touch final gaps)"""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_replay.py"), "9100", "12"], env=dict(os.environ, FUZZ_BACKEND="3"),
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "done 12 cases, 0 mismatches" in r.stdout, r.stdout[-2000:]
+    assert "'replay_final_gaps': 0.0" not in r.stdout.rsplit("totals", 1)[1]
+
+
 def test_window_order_matches_reference_trace():
     """sequence of (window start, length) searched by the exact replay == the reference's setMums1 call sequence"""
     from oracle import hosttest, runner

@@ -9,7 +9,8 @@ x random speculation slicing / anchor-accept mode (FUZZ_WORLD=N: also the N-rank
 orchestrator with the reference's own csgmum as search backend (oracle/hosttest.py) and compares MUM and LCB lists bit for bit.
 MALLOC_PERTURB_=255 makes glibc zero every allocation of the reference binary (tcache off: its hits bypass the fill): wherever
 a reverse-strand match wins, the binary's result otherwise depends on the stale contents of the never-initialised
-MasterRC[].UP."""
+MasterRC[].UP.  FUZZ_BACKEND=3: the same through the CPU emulation of the engine's device-resident
+discovery, parallel replay forced (the "final gaps" path of host/replay.cpp)."""
 import os
 import sys
 import tempfile
@@ -37,7 +38,15 @@ for it in range(ncases):
     if rng.random() < 0.25:                     # the defaults: slices by the number of initial regions, parallel accept by size
         del os.environ["PB200_SPEC_SLICES"], os.environ["PB200_PAR_ANCHORS_MIN"]
     hosttest.runoff_skips()
-    res = hosttest.align(gi, api.make_params(**params_kw(kw)), backend=1)
+    backend = int(os.environ.get("FUZZ_BACKEND", "1"))
+    if backend == 3:                            # the engine's discovery emulated on the CPU: the replay's "final gaps" path (oracle/discover_emul.cpp)
+        os.environ["PB200_REPLAY_MODE"] = "par"
+        os.environ["PB200_REPLAY_OWN_THREADS"] = "1"
+        os.environ["PB200_HOST_THREADS"] = str(int(rng.choice([2, 4])))
+        os.environ["PB200_REPLAY_TASK"] = str(int(rng.choice([1, 3, 40])))
+        os.environ["PB200_EMUL_SEED"] = str(int(rng.integers(1, 10**6)))
+        os.environ["PB200_EMUL_MAXLEN"] = str(int(rng.choice([4096, 4096, 200])))
+    res = hosttest.align(gi, api.make_params(**params_kw(kw)), backend=backend)
     runoff = hosttest.runoff_skips()
     world = int(os.environ.get("FUZZ_WORLD", "0"))
     if world > 1:                               # N>1 host path (thread ranks): every rank must hold the single-rank result

@@ -6,7 +6,11 @@
 Random collinear genome sets with short minimum MUM lengths (many chance reverse-strand candidates inside sub-regions = foreign
 reads and writes of mumlayout), random task sizes down to one gap per task, 2-8 workers, scheduling jitter.  Every case: the
 product's host orchestrator over csgmum (oracle/hosttest.py) once with PB200_REPLAY_MODE=seq and several times with =par; MUM
-and LCB lists must be identical.  tools/fuzz_host.py compares the same code with the reference binary itself."""
+and LCB lists must be identical.  tools/fuzz_host.py compares the same code with the reference binary itself.
+
+FUZZ_BACKEND=3: the parallel runs go through the CPU emulation of the engine's device-resident discovery
+(oracle/discover_emul.cpp), i.e. the replay takes the discovery's accept decisions as final for the gaps where they cannot
+depend on the order ("final gaps", replay.cpp); regions of a level in random order (PB200_EMUL_SEED), random largest window."""
 import os
 import sys
 import time
@@ -17,6 +21,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from parsnp_b200 import api, synth
 from oracle import hosttest
 from tests.refcmp import result_to_dump, diff_dumps
+
+
+BACKEND = int(os.environ.get("FUZZ_BACKEND", "2"))
 
 
 def one_case(seed, verbose=False):
@@ -41,7 +48,7 @@ def one_case(seed, verbose=False):
     ref = hosttest.align(g, prm(), backend=2)
     want = result_to_dump(ref)
     bad = 0
-    tot = dict(replay_tasks=0, replay_foreign_reads=0, replay_foreign_writes=0, replay_restarts=0, replay_fallback=0, slow_queue_iters=0)
+    tot = dict(replay_gaps=0, replay_final_gaps=0, replay_final_mums=0, replay_misses=0, replay_tasks=0, replay_foreign_reads=0, replay_foreign_writes=0, replay_restarts=0, replay_fallback=0, slow_queue_iters=0)
     for rep in range(4):
         os.environ["PB200_REPLAY_MODE"] = "par"
         os.environ["PB200_REPLAY_OWN_THREADS"] = "1"
@@ -49,7 +56,9 @@ def one_case(seed, verbose=False):
         os.environ["PB200_REPLAY_TASK"] = str(int(rng.choice([1, 1, 2, 5, 40])))
         os.environ["PB200_REPLAY_JITTER"] = str(int(rng.choice([0, 3, 20])))
         os.environ["PB200_SPEC_SLICES"] = str(int(rng.choice([1, 4])))
-        got = hosttest.align(g, prm(), backend=2)
+        os.environ["PB200_EMUL_SEED"] = str(int(rng.integers(1, 10**6)))
+        os.environ["PB200_EMUL_MAXLEN"] = str(int(rng.choice([4096, 4096, 300, 80])))
+        got = hosttest.align(g, prm(), backend=BACKEND)
         for k in tot:
             tot[k] += got["stats"][k]
         d = diff_dumps(result_to_dump(got), want)
