@@ -312,8 +312,9 @@ def main():
         return groups.get(name, 0.0) / c, c
     sort_ms, sort_n = per_launch("index_sort")
     seed_ms, seed_n = per_launch("scan_seed")
-    groups["small_regions"] = groups.get("small_regions", 0.0) + groups.pop("small_b", 0.0) + groups.pop("small_c", 0.0)
-    counts["small_regions"] = counts.get("small_regions", 0.0) + counts.pop("small_b", 0.0) + counts.pop("small_c", 0.0)
+    # the recursion = search kernels of the three window classes + the accept kernel of every level
+    groups["small_regions"] = groups.get("small_regions", 0.0) + groups.pop("small_b", 0.0) + groups.pop("small_c", 0.0) + groups.pop("small_accept", 0.0)
+    counts["small_regions"] = counts.get("small_regions", 0.0) + counts.pop("small_b", 0.0) + counts.pop("small_c", 0.0) + counts.pop("small_accept", 0.0)
     small_ms, small_n = per_launch("small_regions")
     rounds = 1.0 + timers.get("index_rounds", 0.0) / max(1.0, timers.get("big_windows", 1.0))
     roof_kernels = {
@@ -374,7 +375,8 @@ def main():
             "host_seconds": {k: st[k] for k in st if k.startswith("t_")},
             "engine": {k: timers[k] for k in timers if not k.endswith("_ms") and not k.startswith("n_")},
             "small_class_ms": {"a": timers.get("small_regions_ms", 0.0) / nsteps, "b": timers.get("small_b_ms", 0.0) / nsteps,
-                               "c": timers.get("small_c_ms", 0.0) / nsteps}}
+                               "c": timers.get("small_c_ms", 0.0) / nsteps,
+                               "accept": timers.get("small_accept_ms", 0.0) / nsteps}}
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         full = None
         try:

@@ -290,7 +290,7 @@ __device__ __forceinline__ bool coop_resolve(unsigned stop, int my, int lm, int 
 // (Measured and dropped: extending two seeds per iteration - registers cost more occupancy than the overlap gained, +15 %;
 //  dropping seeds that continue the previous lane's diagonal from the flank signature alone - the saved left check is an L1
 //  hit, the shuffle is not free, +4 %; loading lrp[] ahead of the extension - chance hits then pay a DRAM sector, +8 %.)
-__global__ void __launch_bounds__(128, 12) seed_extend_kernel(const uint8_t* __restrict__ R, int n, const uint32_t* __restrict__ sa,
+__global__ void __launch_bounds__(128, 16) seed_extend_kernel(const uint8_t* __restrict__ R, int n, const uint32_t* __restrict__ sa,
                                                           const int32_t* __restrict__ lrp, const uint2* __restrict__ table,
                                                           int k, int step, int minsize,
                                                           const StrandDesc* __restrict__ strands, uint64_t* __restrict__ ev_key,

@@ -277,6 +277,11 @@ public:
     RecKernel rec_kernel() const {
         return rr_.gpl == 1 ? rec::recursion_level_kernel<1> : (rr_.gpl == 2 ? rec::recursion_level_kernel<2> : (rr_.gpl == 4 ? rec::recursion_level_kernel<4> : rec::recursion_level_kernel<7>));
     }
+    typedef void (*RecAcceptKernel)(const uint8_t*, const int64_t*, const int64_t*, rec::Params, rec::Store, rec::Queues, int, const int32_t*, const int32_t*,
+                                    const int32_t*, const uint8_t*);
+    RecAcceptKernel rec_accept_kernel() const {
+        return rr_.gpl == 1 ? rec::recursion_accept_kernel<1> : (rr_.gpl == 2 ? rec::recursion_accept_kernel<2> : (rr_.gpl == 4 ? rec::recursion_accept_kernel<4> : rec::recursion_accept_kernel<7>));
+    }
     bool rec_supported(int n, int q) const {
         if (n != n_ || n < 2 || n > 224 || q < 0 || force_big_ || getenv("PB200_NO_DEVICE_RECURSION")) return false;
         for (int g = 0; g < n; ++g) if (len_[g] >= ((int64_t)1 << 31) - 64) return false;
@@ -317,7 +322,7 @@ public:
         rec::Queues& Q = rr_.Q;
         for (int h = 0; h < 2; ++h) for (int c = 0; c < rec::NCLASS; ++c) Q.list[h][c] = lists + cap * (size_t)(h * rec::NCLASS + c);
         Q.deferred = lists + cap * (size_t)(2 * rec::NCLASS);
-        Q.count = ctr; Q.taken = ctr + 8; Q.nregions = ctr + 16; Q.ndeferred = ctr + 17; Q.dropped = ctr + 18; Q.nfw = ctr + 19;
+        Q.count = ctr; Q.taken = ctr + 8; Q.nregions = ctr + 16; Q.ndeferred = ctr + 17; Q.dropped = ctr + 18; Q.nfw = ctr + 19; Q.taken2 = ctr + 26;
         Q.fw = r_fw_.ensure(3 * (size_t)rec::FW_CAP, false, st_);
         Q.cap = (unsigned int)std::min<size_t>(cap, 0x1fffffffu);
         r_pairflag_ = r_pair_.ensure(cap + 16, false, st_);
@@ -364,6 +369,7 @@ public:
     void rec_launch_round() {
         const int nq = n_ - 1;
         RecKernel kern = rec_kernel();
+        RecAcceptKernel akern = rec_accept_kernel();
         for (int l = 0; l < 8; ++l, ++rr_.level) {
             for (int c = 0; c < rec::NCLASS; ++c) {
                 timers.start(GpuTimers::T_SMALL + c, st_);
@@ -371,6 +377,11 @@ public:
                               rr_.P, rr_.St, rr_.Q, rr_.level, c, rr_.cfg[c], rr_.d_cnt, (unsigned long long)rr_.cand_cap, rr_.d_k, rr_.d_lon, rr_.d_sp, rr_.d_fw);
                 timers.stop(GpuTimers::T_SMALL + c, st_);
             }
+            // (one warp per work-list entry; the grid is sized for the first levels, the tail levels leave most of it idle for microseconds)
+            timers.start(GpuTimers::T_SMALL_ACCEPT, st_);
+            pb200::launch(akern, sm_count_ * 8, 128, 0, st_, text_.get(), gmeta_.get(), gmeta_.get() + 2 * n_, rr_.P, rr_.St, rr_.Q, rr_.level,
+                          (const int32_t*)rr_.d_k, (const int32_t*)rr_.d_lon, (const int32_t*)rr_.d_sp, (const uint8_t*)rr_.d_fw);
+            timers.stop(GpuTimers::T_SMALL_ACCEPT, st_);
             pb200::launch(rec::level_advance_kernel, 1, 32, 0, st_, rr_.Q, rr_.level);
         }
         PB_CUDA(cudaGetLastError());

@@ -30,7 +30,8 @@ constexpr int32_t E_PAIR = 1 << 30, E_SECOND_FIRST = 1 << 29, E_ID = (1 << 29) -
 struct Queues {
     int32_t* list[2][NCLASS];           // region ids
     unsigned int* count;                // [2][NCLASS] entries appended
-    unsigned int* taken;                // [2][NCLASS] entries handed out (dynamic scheduling inside a level)
+    unsigned int* taken;                // [2][NCLASS] entries handed out (dynamic scheduling inside a level): search kernels ...
+    unsigned int* taken2;               //                                                                      ... accept kernel
     unsigned int* nregions;             // regions in the store
     unsigned int* ndeferred;            // regions the device could not take (too large, minsize < 4, ...): left to the host
     unsigned int* dropped;              // children lost to a full store / list (the replay searches them on demand)
@@ -223,7 +224,7 @@ template <int GPL>
 __device__ inline void accept_region(const Params& P, const Store& St, const Queues& Q, int next, const uint8_t* __restrict__ text,
                                      const int64_t* __restrict__ gbase_fwd, const int64_t* __restrict__ glen, int region, int nc, int64_t base,
                                      const int32_t* __restrict__ out_k, const int32_t* __restrict__ out_lon, const int32_t* __restrict__ out_sp,
-                                     const uint8_t* __restrict__ out_fwd, uint16_t* accC, uint16_t* accShift, uint16_t* accLen, bool second) {
+                                     const uint8_t* __restrict__ out_fwd, bool second) {
     const int lane = threadIdx.x & 31;
     const int n = P.n, nq = n - 1;
     uint32_t rflags = 0;
@@ -240,6 +241,8 @@ __device__ inline void accept_region(const Params& P, const Store& St, const Que
         row[t] = P.bits + (g < n ? P.bit_off[g] : 0);
     }
     int nacc = 0;
+    int pc = -1;                                                // the previous accepted candidate, its shift and length
+    int64_t pshift = 0, plen = 0;
     for (int c = 0; c < nc; ++c) {
         const int64_t LON = out_lon[base + c];
         const int k = out_k[base + c];
@@ -318,8 +321,6 @@ __device__ inline void accept_region(const Params& P, const Store& St, const Que
         }
         // accepted MUMs must ascend, without overlap, in every genome - else the sub-regions between them overlap
         if (nacc > 0) {
-            const int pc = accC[nacc - 1];
-            const int64_t pshift = accShift[nacc - 1], plen = accLen[nacc - 1];
             int bad = 0;
             for (int t = 0; t < GPL; ++t) {
                 const int g = lane + 32 * t;
@@ -330,10 +331,8 @@ __device__ inline void accept_region(const Params& P, const Store& St, const Que
             }
             if (warp_or(bad)) rflags |= F_NONCOLLINEAR;
         }
-        if (lane == 0) {
-            accC[nacc] = (uint16_t)c; accShift[nacc] = (uint16_t)shift; accLen[nacc] = (uint16_t)length;
-            St.acc_shift[base + c] = (int32_t)shift; St.acc_len[base + c] = (int32_t)length;
-        }
+        if (lane == 0) { St.acc_shift[base + c] = (int32_t)shift; St.acc_len[base + c] = (int32_t)length; }
+        pc = c; pshift = shift; plen = length;
         ++nacc;
     }
     if (second && nacc > 0) rflags |= F_SECOND;
@@ -344,9 +343,10 @@ __device__ inline void accept_region(const Params& P, const Store& St, const Que
     // determineRegion around every accepted MUM, on the layout as it is after ALL accepts of the region (src/parsnp.cpp:251-289).
     // The right side of MUM a-1 and the left side of MUM a are the same gap: pushed as a pair, left side first.
     int64_t pS[GPL], pE[GPL], psl = -1;                         // pending right side of the previous MUM (psl <= q: none)
-    for (int a = 0; a < nacc; ++a) {
-        const int c = accC[a];
-        const int64_t shift = accShift[a], length = accLen[a];
+    for (int c = 0; c < nc; ++c) {
+        const int64_t shift = __ldcg(St.acc_shift + base + c);  // (written by lane 0 above: L2)
+        if (shift < 0) continue;
+        const int64_t length = __ldcg(St.acc_len + base + c);
         const int64_t LON = out_lon[base + c];
         const int k = out_k[base + c];
         int64_t lS[GPL], lE[GPL], rS[GPL], rE[GPL];
@@ -413,10 +413,7 @@ __global__ void __launch_bounds__(small::SM_MAX_THREADS, 4) recursion_level_kern
         for (int half = 0; half < 2; ++half) {
             const int region = half == 0 ? first : second;
             if (region < 0) break;
-            if (half == 1) {
-                __syncthreads();                                // (warp 0 has finished the first region's accepts)
-                if (threadIdx.x == 0) St.flags[region] |= I_SECOND;
-            }
+            if (half == 1) __syncthreads();                     // (every thread has read the first window's counters)
             const int32_t* rc = St.coords + (size_t)region * 2 * P.n;
             small::TaskDev tk;
             tk.ref_off = gbase_fwd[0] + rc[0];
@@ -437,10 +434,38 @@ __global__ void __launch_bounds__(small::SM_MAX_THREADS, 4) recursion_level_kern
                 continue;
             }
             if (threadIdx.x == 0) { St.ncand[region] = nc; St.cand_base[region] = base; }
-            if (threadIdx.x < 32 && nc > 0) {
-                // (the candidate rows were written by this CTA before the barrier that ends small_window)
-                accept_region<GPL>(P, St, Q, next, text, gbase_fwd, glen, region, nc, base, out_k, out_lon, out_sp, out_fwd, sv.candK, sv.candM,
-                                   reinterpret_cast<uint16_t*>(sv.HQ), half == 1);
+        }
+    }
+}
+
+// The accept half of a level: ONE WARP per work-list entry runs loop D + determineRegion (accept_region) on what the search
+// kernels of this level left in the candidate arrays - the two regions of a pair in the reference's order.  Its own kernel
+// because it is a chain of dependent L2 round trips (bit words of the scratch layout): as the tail of the search CTA it
+// left three of four warps waiting at a barrier (ncu: 12 barrier stalls per issue); here every SM keeps 32+ such chains in flight.
+template <int GPL>
+__global__ void __launch_bounds__(128) recursion_accept_kernel(const uint8_t* __restrict__ text, const int64_t* __restrict__ gbase_fwd,
+                                                               const int64_t* __restrict__ glen, Params P, Store St, Queues Q, int level,
+                                                               const int32_t* __restrict__ out_k, const int32_t* __restrict__ out_lon,
+                                                               const int32_t* __restrict__ out_sp, const uint8_t* __restrict__ out_fwd) {
+    const int cur = level & 1, next = cur ^ 1;
+    const int lane = threadIdx.x & 31;
+    for (int cls = 0; cls < NCLASS; ++cls) {
+        const unsigned int total = min(Q.count[cur * NCLASS + cls], Q.cap);
+        for (;;) {
+            unsigned int ti = 0;
+            if (lane == 0) ti = atomicAdd(&Q.taken2[cur * NCLASS + cls], 1u);
+            ti = __shfl_sync(0xffffffffu, ti, 0);
+            if (ti >= total) break;
+            const int32_t entry = Q.list[cur][cls][ti];
+            const int first = (entry & E_ID) + ((entry & E_PAIR) && (entry & E_SECOND_FIRST) ? 1 : 0);
+            const int second = (entry & E_PAIR) ? (entry & E_ID) + ((entry & E_SECOND_FIRST) ? 0 : 1) : -1;
+            for (int half = 0; half < 2; ++half) {
+                const int region = half == 0 ? first : second;
+                if (region < 0) break;
+                if (half == 1 && lane == 0) St.flags[region] |= I_SECOND;
+                const int nc = St.ncand[region];                // (-1: it overflowed a capacity and waits in the next level's list)
+                if (nc > 0) accept_region<GPL>(P, St, Q, next, text, gbase_fwd, glen, region, nc, St.cand_base[region], out_k, out_lon, out_sp, out_fwd, half == 1);
+                __syncwarp();
             }
         }
     }
@@ -449,7 +474,7 @@ __global__ void __launch_bounds__(small::SM_MAX_THREADS, 4) recursion_level_kern
 // between two levels: the finished level's counters are cleared for re-use two levels later
 __global__ void level_advance_kernel(Queues Q, int level) {
     const int cur = level & 1;
-    if (threadIdx.x < NCLASS) { Q.count[cur * NCLASS + threadIdx.x] = 0; Q.taken[cur * NCLASS + threadIdx.x] = 0; }
+    if (threadIdx.x < NCLASS) { Q.count[cur * NCLASS + threadIdx.x] = 0; Q.taken[cur * NCLASS + threadIdx.x] = 0; Q.taken2[cur * NCLASS + threadIdx.x] = 0; }
 }
 
 // level 0: classify the initial regions (uploaded into the store by the host) into the first lists.  pair[id] = 1: regions id

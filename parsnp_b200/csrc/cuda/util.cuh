@@ -116,12 +116,12 @@ private:
 class GpuTimers {
 public:
     enum { T_INDEX_KEYS = 0, T_INDEX_SORT, T_INDEX_DOUBLING, T_INDEX_LCP, T_INDEX_TABLE, T_SCAN_SEED, T_SCAN_EVSORT, T_SCAN_EVSCAN,
-           T_SCAN_FOLD, T_SCAN_EMIT, T_SCAN_PASS2, T_SMALL, T_SMALL_B, T_SMALL_C, T_COUNT };
+           T_SCAN_FOLD, T_SCAN_EMIT, T_SCAN_PASS2, T_SMALL, T_SMALL_B, T_SMALL_C, T_SMALL_ACCEPT, T_COUNT };
     static const char* names() {
         return "index_keys_ms,index_sort_ms,index_doubling_ms,index_lcp_ms,index_table_ms,scan_seed_ms,scan_evsort_ms,scan_evscan_ms,"
-               "scan_fold_ms,scan_emit_ms,scan_pass2_ms,small_regions_ms,small_b_ms,small_c_ms,"
+               "scan_fold_ms,scan_emit_ms,scan_pass2_ms,small_regions_ms,small_b_ms,small_c_ms,small_accept_ms,"
                "n_index_keys,n_index_sort,n_index_doubling,n_index_lcp,n_index_table,n_scan_seed,n_scan_evsort,n_scan_evscan,"
-               "n_scan_fold,n_scan_emit,n_scan_pass2,n_small_regions,n_small_b,n_small_c";
+               "n_scan_fold,n_scan_emit,n_scan_pass2,n_small_regions,n_small_b,n_small_c,n_small_accept";
     }
     GpuTimers() { reset(); }
     ~GpuTimers() { for (auto& e : pool_) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); } }

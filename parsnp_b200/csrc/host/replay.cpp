@@ -847,6 +847,8 @@ ReplayCtx* Aligner::replay_prepare() {
     if (trace_on_ || !pipeline_ || R == 0) return nullptr;
     if (!force && (W < 2 || R < 512)) return nullptr;
     const double tsetup0 = now_s();
+    static const bool profs = getenv("PB200_PROFILE_HOST") != nullptr;
+    double tsec[8] = {tsetup0, 0, 0, 0, 0, 0, 0, 0};
     std::unique_ptr<ReplayCtx> XP(new ReplayCtx(*this));
     ReplayCtx& X = *XP;
     if (const char* ej = getenv("PB200_REPLAY_JITTER")) X.jitter = (unsigned)std::max(0, atoi(ej));
@@ -875,6 +877,7 @@ ReplayCtx* Aligner::replay_prepare() {
             std::stable_sort(X.order.begin(), X.order.end(), [&](int a, int b) { return pushkey[(size_t)a] < pushkey[(size_t)b]; });
         }
     }
+    tsec[1] = now_s();
     X.keys.resize(R);                            // start[0] of the initial regions in ascending order
     for (size_t i = 0; i < R; ++i) X.keys[i] = pushkey[(size_t)X.order[i]];
     for (size_t i = 1; i < R; ++i)
@@ -907,6 +910,7 @@ ReplayCtx* Aligner::replay_prepare() {
             }
         });
         if (bad.load()) return nullptr;
+        tsec[2] = now_s();
         parallel_chunks(threads_, ((long)R + per_blk - 1) / per_blk, [&](long c) {
             for (size_t p = std::max<size_t>(1, (size_t)c * per_blk); p < std::min(R, (size_t)(c + 1) * per_blk); ++p) {
                 bool ok = true;
@@ -922,6 +926,7 @@ ReplayCtx* Aligner::replay_prepare() {
             return nullptr;
         }
     }
+    tsec[3] = now_s();
     // gaps: runs of regions between cuts (the two regions of one anchor gap, and whatever else overlaps, stay together);
     // tasks: runs of gaps with >= `per` regions
     const size_t per = et ? (size_t)std::max(1, atoi(et)) : std::min<size_t>(128, std::max<size_t>(8, R / ((size_t)W * 24) + 1));
@@ -963,6 +968,7 @@ ReplayCtx* Aligner::replay_prepare() {
         if (dbg) fprintf(stderr, "[pb200 replay] gaps not in order in some genome: sequential\n");
         return nullptr;
     }
+    tsec[4] = now_s();
     // the reference's first pop is the first region PUSHED (see run_task): it must belong to the first gap
     if ((int)pos0 >= gcut[1]) {
         if (dbg) fprintf(stderr, "[pb200 replay] the first region pushed is not in the first gap: sequential\n");
@@ -996,12 +1002,16 @@ ReplayCtx* Aligner::replay_prepare() {
             X.hhi[(size_t)g * X.ntasks + k] = X.ghi[(size_t)(T.glast - 1) * n_ + g];
         }
     }
+    tsec[5] = now_s();
     X.S.resize((size_t)n_);
     parallel_chunks(threads_, (long)n_, [&](long g) { X.S[(size_t)g] = truth_.layout[(size_t)g]; });
+    tsec[6] = now_s();
     X.nw = std::max(1, std::min(W, X.ntasks));
     X.log_slab.reset(new ReplayTask::FRead[(size_t)X.ntasks * ReplayTask::LOG_CAP]);
     for (int k = 0; k < X.ntasks; ++k) X.tasks[k].flog = X.log_slab.get() + (size_t)k * ReplayTask::LOG_CAP;
     X.t_setup = now_s() - tsetup0;
+    if (profs) fprintf(stderr, "[pb200 replay setup ms] order %.2f spans %.2f cuts %.2f gaps %.2f tasks %.2f S %.2f logs %.2f\n", (tsec[1] - tsec[0]) * 1e3, (tsec[2] - tsec[1]) * 1e3,
+                       (tsec[3] - tsec[2]) * 1e3, (tsec[4] - tsec[3]) * 1e3, (tsec[5] - tsec[4]) * 1e3, (tsec[6] - tsec[5]) * 1e3, (now_s() - tsec[6]) * 1e3);
     return XP.release();
 }
 

@@ -1,0 +1,7 @@
+export PB200_BACKTRACE=1
+python -m pytest tests/test_gpu_engine.py tests/test_gpu_fullsize.py tests/test_zz_gpu_fuzz.py -m gpu -x -q 2>&1 | tail -6
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_m.json 2> gpurun_out/r02_bench_m.err || echo "bench failed"
+PB200_PROFILE_HOST=1 python bench.py --steps 2 --warmup 1 --no-cpu-baseline 2>&1 >/dev/null | grep pb200 | tail -8 > gpurun_out/r02_prof_m.txt
+PB200_HOST_THREADS=4 taskset -c 0-3 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_m_4thr.json 2> gpurun_out/r02_bench_m_4thr.err || echo "bench failed"
+PB200_PROFILE_HOST=1 PB200_HOST_THREADS=4 taskset -c 0-3 python bench.py --steps 2 --warmup 1 --no-cpu-baseline 2>&1 >/dev/null | grep pb200 | tail -8 > gpurun_out/r02_prof_m_4thr.txt
+python bench.py --workload pop --nq 200 --steps 3 --warmup 1 --no-cpu-baseline > gpurun_out/r02_bench_m_c3.json 2> gpurun_out/r02_bench_m_c3.err || echo failed
