@@ -182,6 +182,7 @@ def main():
                     help="configs1 = G_indep(L, 8 q) [default, BASELINE configs[1]]; pop = G_pop(L, --nq) [configs[2] shape]; "
                          "c4 = configs[3] shape: G_pop(--length [50 Mbp], --nq [64]) as 10 contigs, queries N-padded at contig breaks")
     ap.add_argument("--nq", type=int, default=NQ)
+    ap.add_argument("--seed", type=int, default=SEED, help="genome set of rank 0 (rank r: seed + r); default = the configs[1] set of the goldens")
     ap.add_argument("--no-pin", action="store_true", help="N>1: leave the ranks' host threads unpinned")
     ap.add_argument("--sharded", action="store_true", help="N>1: one alignment sharded over the ranks instead of one partition per rank")
     args = ap.parse_args()
@@ -218,7 +219,7 @@ def main():
 
     L = args.length
     sharded = args.sharded and world > 1
-    seed = SEED if sharded else SEED + rank
+    seed = args.seed if sharded else args.seed + rank
     if args.workload == "c4":
         genomes = synth.g_pop(L, args.nq, DIV, seed)
         genomes = [genomes[0]] + [synth.with_contig_padding(g, 10) for g in genomes[1:]]
@@ -353,8 +354,8 @@ def main():
     line = {"metric": "genome_bases_per_sec_mum_lcb", "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": ("configs[1]: G_indep(%d bp reference + %d queries, 1%% independent divergence, seed 1+rank), "
-                                    "ini = template defaults (c=21 d=300 q=30 p=15000000 diagdiff=0.12)" % (L, NQ)) if args.workload == "configs1"
+            "config": {"workload": ("configs[1]: G_indep(%d bp reference + %d queries, 1%% independent divergence, seed %d+rank), "
+                                    "ini = template defaults (c=21 d=300 q=30 p=15000000 diagdiff=0.12)" % (L, NQ, args.seed)) if args.workload == "configs1"
                        else (("configs[2] shape: G_pop(%d bp reference + %d queries, 1%% divergence, seed 1), ini = template defaults" % (L, args.nq))
                              if args.workload == "pop" else
                              ("configs[3] shape: G_pop(%d bp reference in 10 contigs + %d queries of 10 contigs with 310-N padding, 1%% divergence), "

@@ -3,7 +3,10 @@
 // exercise the host logic (queue order, trim, LCB chaining) without a GPU.  Never linked into libparsnp_b200.so.
 #include "../parsnp_b200/csrc/host/result.h"
 #include "../parsnp_b200/csrc/host/sharded.h"
+#include <algorithm>
 #include <memory>
+#include <vector>
+#include "../parsnp_b200/csrc/host/parallel.h"
 #include <stdexcept>
 #include <cstdlib>
 #include <cstring>
@@ -78,6 +81,16 @@ int pbtest_search_windows(int backend, int n, const uint8_t* const* seqs, const 
     *lon = (int32_t*)dup(cb.lon.data(), cb.lon.size() * 4);
     *sp = (int32_t*)dup(cb.sp.data(), cb.sp.size() * 4);
     *fwd = (uint8_t*)dup(cb.fwd.data(), cb.fwd.size());
+    return 0;
+}
+// parallel.h's literal_std_sort_by_first against the call it replaces: 0 = same permutation
+int pbtest_literal_sort_check(const int64_t* keys, int64_t n, int threads) {
+    std::vector<std::pair<int64_t, int>> a((size_t)n), b;
+    for (int64_t i = 0; i < n; ++i) a[(size_t)i] = std::make_pair(keys[i], (int)i);
+    b = a;
+    std::sort(a.begin(), a.end(), [](const std::pair<int64_t, int>& x, const std::pair<int64_t, int>& y) { return x.first < y.first; });
+    pb200::literal_std_sort_by_first(b.data(), (size_t)n, threads);
+    for (int64_t i = 0; i < n; ++i) if (a[(size_t)i] != b[(size_t)i]) return 1;
     return 0;
 }
 int pbtest_lrp(const uint8_t* R, int64_t n, int32_t* out) {

@@ -1020,6 +1020,10 @@ void Aligner::do_work_exact() {
 void Aligner::sort_final_mums() {
     const size_t M = final_mums_.size();
     if (final_sorted_) return;                  // (removals keep the order; only `final_mums_ = all_mums_` resets the flag)
+    const double ts0 = now_s();
+    struct Report { double t0; size_t* d; ~Report() { if (getenv("PB200_PROFILE_HOST")) fprintf(stderr, "[pb200 sort_final_mums ms] %.2f descents %zu\n", (now_s() - t0) * 1e3, *d); } };
+    size_t descents = 0;
+    Report rep{ts0, &descents};
     if (sorted_hint_.size() == M && M > 0) {
         // the parallel replay delivered the ascending order with its MUMs (every task's MUMs sorted by its worker, tasks in
         // reference order, merged with the anchors): verify it in parallel; ties still go through the literal std::sort below
@@ -1051,6 +1055,20 @@ void Aligner::sort_final_mums() {
             return;
         }
         sorted_hint_.clear();                   // (ties or an unexpected order: the general path)
+        if (!bad) {
+            // ascending with ties: only the literal call on the initial order can say how the reference orders them
+            std::vector<std::pair<int64_t, int>> kv0(M);
+            parallel_chunks(M > 32768 ? threads_ : 1, nch, [&](long c) {
+                for (size_t i = (size_t)c * per; i < std::min(M, (size_t)(c + 1) * per); ++i) kv0[i] = std::make_pair(mum_start_[mums_[final_mums_[i]].off], final_mums_[i]);
+            });
+            literal_std_sort_by_first(kv0.data(), M, threads_);
+            parallel_chunks(M > 32768 ? threads_ : 1, nch, [&](long c) {
+                for (size_t i = (size_t)c * per; i < std::min(M, (size_t)(c + 1) * per); ++i) final_mums_[i] = kv0[i].second;
+            });
+            final_min_length_ = ml;
+            final_sorted_ = false;              // the next call sorts again, like the reference
+            return;
+        }
     }
     std::vector<std::pair<int64_t, int>> kv(M);
     // gather the keys (random reads into the MUM pools) in parallel; per chunk: descents inside, first/last key, min length
@@ -1072,7 +1090,7 @@ void Aligner::sort_final_mums() {
         }
         ch_desc[c] = d; ch_split[c] = sp; ch_max[c] = mx; ch_minlen[c] = ml;
     });
-    size_t descents = 0, split = 0;
+    size_t split = 0;
     int64_t maxkey = 0;
     final_min_length_ = INT64_MAX;
     for (long c = 0; c < nch; ++c) {
@@ -1085,11 +1103,19 @@ void Aligner::sort_final_mums() {
     // later MUM) make the order implementation-defined: the reference calls std::sort (libstdc++ introsort, unstable) with
     // operator< on start[0] (src/TMum.cpp:151) at every one of these calls.  The same algorithm on (start0, id) records in the
     // same initial order makes the same comparisons and moves, hence the same permutation - whatever the element type.
+    bool kv_initial = true;                             // kv = the records in the initial order (as gathered above)
+    static const bool prof_sort = getenv("PB200_PROFILE_HOST") != nullptr;
     auto literal_sort = [&]() {
-        for (size_t i = 0; i < M; ++i) kv[i] = std::make_pair(mum_start_[mums_[final_mums_[i]].off], final_mums_[i]);   // (final_mums_ still holds the initial order)
-        std::sort(kv.begin(), kv.end(), [](const std::pair<int64_t, int>& x, const std::pair<int64_t, int>& y) { return x.first < y.first; });
+        const double tl0 = now_s();
+        if (!kv_initial)                                // (final_mums_ still holds the initial order)
+            parallel_chunks(M > 32768 ? threads_ : 1, nch, [&](long c) {
+                for (size_t i = (size_t)c * per; i < std::min(M, (size_t)(c + 1) * per); ++i) kv[i] = std::make_pair(mum_start_[mums_[final_mums_[i]].off], final_mums_[i]);
+            });
+        literal_std_sort_by_first(kv.data(), M, threads_);     // = std::sort(kv.begin(), kv.end(), by .first), on several threads (parallel.h)
+        const double tl1 = now_s();
         for (size_t i = 0; i < M; ++i) final_mums_[i] = kv[i].second;
         final_sorted_ = false;                         // the next call sorts again, like the reference
+        if (prof_sort) fprintf(stderr, "[pb200 literal sort ms] %.2f (+ %.2f)\n", (tl1 - tl0) * 1e3, (now_s() - tl1) * 1e3);
     };
     auto has_ties = [&]() {
         for (size_t i = 1; i < M; ++i) if (kv[i].first == kv[i - 1].first) return true;
@@ -1101,6 +1127,7 @@ void Aligner::sort_final_mums() {
         return;
     }
     std::vector<std::pair<int64_t, int>> tmp(M);
+    kv_initial = false;
     if (descents == 1) {
         // the usual shape: the anchors (ascending) followed by the recursion's MUMs (ascending): one merge
         std::merge(kv.begin(), kv.begin() + (long)split, kv.begin() + (long)split, kv.end(), tmp.begin(),

@@ -6,7 +6,10 @@
 // never starved).  A pass hands out chunk indices through an atomic counter; the caller works too.  Calls from a second
 // thread while the pool is busy, and nested calls, simply run their chunks inline.
 #pragma once
+#include <cstddef>
+#include <cstdint>
 #include <functional>
+#include <utility>
 
 namespace pb200 {
 
@@ -18,5 +21,15 @@ inline void parallel_chunks(int nthreads, long nchunks, F&& fn) {
     const std::function<void(long)> f(std::ref(fn));
     parallel_run(nthreads, nchunks, f);
 }
+
+// std::sort(v, v + n, by .first) - the SAME permutation as that call, ties included - on several threads.
+// The reference orders its MUM list with std::sort on start[0] (src/TMum.cpp:151, src/parsnp.cpp:331, 2566); when two MUMs
+// share a start the outcome is whatever libstdc++'s introsort does with them, so the host replays that call literally on
+// (start0, id) records (aligner.cpp: sort_final_mums) - 17 ms for the 195 405 MUMs of configs[1] on one thread, three times
+// per alignment.  Here the library's own steps are driven in parallel: the two sides of every partition are independent
+// (std::__unguarded_partition_pivot per range, level by level, same depth budget), small ranges finish with the library's
+// std::__introsort_loop, and the final insertion pass runs per range (every range starts at a partition cut: nothing moves
+// across it).  Same comparisons on the same data in every range, hence the same permutation.
+void literal_std_sort_by_first(std::pair<int64_t, int>* v, size_t n, int threads);
 
 }  // namespace pb200

@@ -33,6 +33,9 @@ def cases():
     return {
         # configs[1]: the benched workload
         "c2_indep_5m_8q": dict(kind="indep", L=5_000_000, nq=8, div=0.01, seed=1, contigs=1, ini={}),
+        # the same shape with seed 3 = the genome set of rank 2 in `bench.py --gpus N` (N >= 3): its final MUM list has two MUMs
+        # with the same start[0], i.e. the literal replay of the reference's unstable std::sort decides their order
+        "c2_indep_5m_8q_seed3": dict(kind="indep", L=5_000_000, nq=8, div=0.01, seed=3, contigs=1, ini={}),
         # configs[2] shape at 32 and at the full 200 queries
         "c3_pop_5m_32q": dict(kind="pop", L=5_000_000, nq=32, div=0.01, seed=1, contigs=1, ini={}),
         "c3_pop_5m_200q": dict(kind="pop", L=5_000_000, nq=200, div=0.01, seed=1, contigs=1, ini={}),

@@ -272,6 +272,24 @@ def test_final_gaps_fuzz():
     assert "'replay_final_gaps': 0.0" not in r.stdout.rsplit("totals", 1)[1]
 
 
+def test_parallel_literal_sort_equals_std_sort():
+    """host/parallel.cpp: literal_std_sort_by_first == std::sort on (key, id) records, position by position, on inputs full of
+    ties (the only case where the permutation is not determined by the keys): random, few distinct keys, sorted, reversed,
+    ascending runs (the MUM list's shape: anchors, then the recursion's MUMs), constant"""
+    from oracle import hosttest
+    lib = hosttest.load()
+    lib.pbtest_literal_sort_check.argtypes = [C.c_void_p, C.c_int64, C.c_int]
+    rng = np.random.default_rng(77)
+    for n in (40000, 100003, 262144, 300001):
+        shapes = [rng.integers(0, n // 3, n), rng.integers(0, 7, n), np.sort(rng.integers(0, n // 2, n)),
+                  np.sort(rng.integers(0, n // 2, n))[::-1].copy(), np.concatenate([np.sort(rng.integers(0, n, n // 4)), np.sort(rng.integers(0, n, n - n // 4))]),
+                  np.zeros(n, np.int64), np.arange(n) // 2]
+        for keys in shapes:
+            keys = np.ascontiguousarray(keys, np.int64)
+            for threads in (2, 3, 8):
+                assert lib.pbtest_literal_sort_check(keys.ctypes.data, len(keys), threads) == 0
+
+
 def test_window_order_matches_reference_trace():
     """sequence of (window start, length) searched by the exact replay == the reference's setMums1 call sequence"""
     from oracle import hosttest, runner

@@ -39,6 +39,44 @@ def test_cuda_search_fuzz_against_csgmum(seed0):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not have_ref, reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed0", [91000, 91008])
+def test_cuda_final_gaps_fuzz(seed0, monkeypatch):
+    """the device's own accept decisions taken as final by the parallel replay (host/replay.cpp "final gaps") on random sets with
+    8-12 base MUMs - chance reverse-strand candidates inside sub-regions, i.e. gaps that must NOT be taken as final, foreign
+    writes that touch final gaps, restarts - against the sequential loop over csgmum (tools/fuzz_replay.py's generator; the CPU
+    suite runs the same host code over the emulated discovery, oracle/discover_emul.cpp)"""
+    import numpy as np
+    from oracle import hosttest
+    from parsnp_b200 import api, synth
+    nfinal, bad = 0, []
+    for seed in range(seed0, seed0 + 8):
+        rng = np.random.default_rng(seed)
+        L = int(rng.choice([30000, 80000, 200000]))
+        nq = int(rng.integers(1, 7))
+        div = float(rng.choice([0.01, 0.03, 0.05]))
+        g = (synth.g_indep if rng.random() < 0.6 else synth.g_pop)(L, nq, div, int(rng.integers(1, 10**6)))
+        if rng.random() < 0.3:
+            a = int(rng.integers(0, L - 400)); ln = int(rng.integers(30, 300))
+            for x in g:
+                x[a + ln:a + 2 * ln] = synth.revcomp(x[a:a + ln])
+        kw = dict(mums=str(rng.choice(["8", "10", "12", "1.1*(Log(S))", "0.7*(Log(S))"])), q=int(rng.choice([10, 30])))
+        monkeypatch.setenv("PB200_REPLAY_MODE", "seq")
+        want = result_to_dump(hosttest.align(g, api.make_params(**kw), backend=1))
+        for rep in range(2):
+            monkeypatch.setenv("PB200_REPLAY_MODE", "par")
+            monkeypatch.setenv("PB200_REPLAY_TASK", str(int(rng.choice([1, 2, 5, 40]))))
+            monkeypatch.setenv("PB200_REPLAY_THREADS", str(int(rng.choice([2, 4, 8]))))
+            got = api.align(g, api.make_params(**kw))
+            nfinal += got["stats"]["replay_final_gaps"]
+            d = diff_dumps(result_to_dump(got), want)
+            if d:
+                bad.append((seed, rep, kw, d[:2]))
+    assert bad == []
+    assert nfinal > 100
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not have_ref, reason="oracle/_ref not built")
 @pytest.mark.parametrize("force_big", [False, True])
 def test_cuda_window_fuzz_wide_regimes(force_big):
     """single windows far from the comfortable regime - homopolymers and two-letter alphabets (everything repeats), N runs in

@@ -48,6 +48,10 @@ def make_case(seed):
         kw["mums"] = str(rng.choice(["1.1*(Log(S))", "0.9*(Log(S))", "14", "1.1*(Log(S))"]))
     if rng.random() < 0.15:
         kw["filter"] = 0
+    if os.environ.get("FUZZ_FILTERS") != "0" and rng.random() < 0.12:
+        # ini [MUM] filter > 1 (src/parsnp.cpp:327-425, filterRandom1): drawn from its own stream so that the cases of earlier
+        # campaigns keep their seeds
+        kw["filter"] = int(np.random.default_rng(seed + 7919).choice([2, 5, 30]))
     if rng.random() < 0.12:                     # many queries: mutated copies of the first ones
         for _ in range(int(rng.integers(3, 9))):
             x = g[int(rng.integers(0, len(g)))].copy()
