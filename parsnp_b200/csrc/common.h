@@ -168,6 +168,7 @@ struct AnchorResult {
     const int32_t* a_lon = nullptr;      // [nanchors]
     const uint8_t* a_fwd = nullptr;      // [nanchors * n]
     const int32_t* r_coords = nullptr;   // [nregions * 2n]: start[n] then LENGTH[n], in push order
+    const int32_t* r_lo = nullptr;       // [nregions * n] (optional): the set bit of mumlayout that bounds the region on the left, per genome (0: none)
     const uint64_t* layout = nullptr;    // all rows of mumlayout after the anchors, row g at layout_off[g] words
     std::vector<int64_t> layout_off;
     CandBatch cands;

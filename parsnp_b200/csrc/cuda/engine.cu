@@ -70,7 +70,8 @@ __global__ void anchor_push_flags_bounded(int n, int q, const uint32_t* __restri
 }
 __global__ void anchor_push_bounded(int n, const uint32_t* __restrict__ nanchors, const int32_t* __restrict__ REG, const int32_t* __restrict__ SL,
                                     const uint32_t* __restrict__ slot, const uint32_t* __restrict__ pos, rec::Store St, uint8_t* __restrict__ pair,
-                                    unsigned int cap) {
+                                    unsigned int cap, const unsigned long long* __restrict__ bits, const int64_t* __restrict__ bit_off,
+                                    int32_t* __restrict__ LO) {
     const unsigned int x = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const unsigned int na = *nanchors;
@@ -82,7 +83,13 @@ __global__ void anchor_push_bounded(int n, const uint32_t* __restrict__ nanchors
         if (id >= cap) continue;
         const int32_t* S = me + 2 * n * side;
         int32_t* c = St.coords + (size_t)id * 2 * n;
-        for (int g = lane; g < n; g += 32) { c[g] = S[g]; c[n + g] = S[n + g] - S[g]; }
+        for (int g = lane; g < n; g += 32) {
+            c[g] = S[g]; c[n + g] = S[n + g] - S[g];
+            // the set bit that bounds the region on the left (the replay's ownership spans, host/replay.cpp): a left side starts
+            // right behind one; a right side starts two bases behind the anchor's last base, or one if the skipped base is set
+            const int32_t b = S[g] - 1;
+            LO[(size_t)id * n + g] = b <= 0 ? 0 : (rec::bit_get(bits + bit_off[g], b) ? b : b - 1);
+        }
         if (lane == 0) {
             int p = 0;
             if (side == 1 && x + 1 < na && slot[2 * x + 2]) {
@@ -656,11 +663,12 @@ public:
         uint8_t* d_host = a_out_.ensure(hoff[5] + 64, false, st_);
         pb200::launch(anc::anchor_regions_kernel, (unsigned)((NCA * 32 + 255) / 256), 256, 0, st_, n, d_glen, nca, accepted, xidx, ST, a_lon_.get(), a_fwd_.get(),
                       (const unsigned long long*)bits, d_bit_off, REG, SL, (int32_t*)(d_host + hoff[0]), (int32_t*)(d_host + hoff[1]), d_host + hoff[2]);
+        int32_t* d_lo = a_lo_.ensure((size_t)rr_.cap * (size_t)n + 64, false, st_);
         // push flags need the number of anchors: it is on the device; the kernels are launched for NCA and bounded there
         pb200::launch(anchor_push_flags_bounded, (unsigned)((NCA * 32 + 255) / 256), 256, 0, st_, n, rq.q, (const uint32_t*)d_tot, nca, (const int32_t*)REG, (const int32_t*)SL, slot);
         r_scanner_.scan<prim::OpSum, true>(slot, pos, (int64_t)(2 * NCA), d_tot + 1, st_);
         pb200::launch(anchor_push_bounded, (unsigned)((NCA * 32 + 255) / 256), 256, 0, st_, n, (const uint32_t*)d_tot, (const int32_t*)REG, (const int32_t*)SL,
-                      (const uint32_t*)slot, (const uint32_t*)pos, rr_.St, r_pairflag_, rr_.Q.cap);
+                      (const uint32_t*)slot, (const uint32_t*)pos, rr_.St, r_pairflag_, rr_.Q.cap, (const unsigned long long*)bits, d_bit_off, d_lo);
         pb200::launch(anc::anchor_finish_kernel, 1, 32, 0, st_, (const uint32_t*)d_tot, (const uint32_t*)(d_tot + 1), d_flags, rr_.Q.nregions, rr_.Q.cap);
         // ---- what the host needs: the layout BEFORE the recursion scribbles on it, anchors, flags; then the initial regions
         PB_CUDA(cudaMemcpyAsync(d_host + hoff[3], bits, (size_t)r_bits_words_ * 8, cudaMemcpyDeviceToDevice, st_));
@@ -682,7 +690,9 @@ public:
         PB_CUDA(cudaMemcpyAsync(h_host + hoff[1], d_host + hoff[1], NA * 4, cudaMemcpyDeviceToHost, st2_));
         PB_CUDA(cudaMemcpyAsync(h_host + hoff[2], d_host + hoff[2], NA * (size_t)n, cudaMemcpyDeviceToHost, st2_));
         PB_CUDA(cudaMemcpyAsync(h_host + hoff[3], d_host + hoff[3], (size_t)r_bits_words_ * 8, cudaMemcpyDeviceToHost, st2_));
+        int32_t* h_lo = a_pin_lo_.ensure(NR * (size_t)n + 16);
         if (NR) PB_CUDA(cudaMemcpyAsync(h_rc, rr_.St.coords, NR * 2 * (size_t)n * 4, cudaMemcpyDeviceToHost, st2_));
+        if (NR) PB_CUDA(cudaMemcpyAsync(h_lo, d_lo, NR * (size_t)n * 4, cudaMemcpyDeviceToHost, st2_));
         PB_CUDA(cudaStreamSynchronize(st2_));
         out.status = 1;
         out.nanchors = NA; out.nregions = NR;
@@ -690,6 +700,7 @@ public:
         out.layout = (const uint64_t*)(h_host + hoff[3]);
         out.layout_off = r_bit_off_host_;
         out.r_coords = h_rc;
+        out.r_lo = h_lo;
         host_anchor_accept_s += wall_s() - t0;
         return 1;
     }
@@ -975,13 +986,13 @@ private:
     prim::Scanner r_scanner_;
     size_t r_cand_hint_ = 0;
     // anchor stage on the device (anchor_stage)
-    DevBuf<int32_t> a_k_, a_lon_, a_sp_, a_st_, a_reg_;
+    DevBuf<int32_t> a_k_, a_lon_, a_sp_, a_st_, a_reg_, a_lo_;
     DevBuf<uint8_t> a_fwd_, a_valid_, a_out_;
     DevBuf<uint32_t> a_u32_;
     DevBuf<unsigned int> a_flags_;
     PinBuf<unsigned int> a_pin_flags_;
     PinBuf<uint8_t> a_pin_out_;
-    PinBuf<int32_t> a_pin_rc_;
+    PinBuf<int32_t> a_pin_rc_, a_pin_lo_;
     cudaStream_t st2_ = nullptr;
     std::vector<int64_t> r_bit_off_host_;
     static std::atomic<uint32_t> s_cand_per_region_x16_;

@@ -584,8 +584,11 @@ void Aligner::install_device_anchors(const AnchorResult& res, int whole) {
     rp_.coord.resize(rp_.coord.size() + NR * 2 * N);
     rp_.slen.resize(rp_.slen.size() + NR);
     initial_regions_.resize(NR);
+    initial_lo_.clear();
+    if (res.r_lo) initial_lo_.resize(NR * N);
     parallel_chunks(NR > 8192 ? threads_ : 1, ((long)NR + per - 1) / per, [&](long c) {
         for (size_t r = (size_t)c * per; r < std::min(NR, (size_t)(c + 1) * per); ++r) {
+            if (res.r_lo) std::memcpy(&initial_lo_[r * N], res.r_lo + r * N, N * sizeof(int32_t));
             const int32_t* s = res.r_coords + r * 2 * N;
             int64_t* d = &rp_.coord[((size_t)base + r) * 2 * N];
             int64_t sl = 500000000;

@@ -275,6 +275,7 @@ private:
 
     World truth_;
     std::vector<int> initial_regions_;
+    pod_vector<int32_t> initial_lo_;         // per initial region and genome: the bounding set bit on its left, when the engine delivered it (else empty)
 
     CandCache main_cache_;                                  // anchors + regions the speculation did not predict
     std::vector<std::unique_ptr<CandCache>> slice_cache_;   // one per speculation slice

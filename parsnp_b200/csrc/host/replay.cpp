@@ -890,17 +890,34 @@ ReplayCtx* Aligner::replay_prepare() {
     // spans of the initial regions: between the anchor bits that bound them, per genome (the layout holds exactly the anchors);
     // cut[p] = region p starts behind everything before it in every genome.  Collinear anchors make the span ends ascend with p,
     // so "everything before" is the previous region; anything else declines.
-    std::vector<int64_t> rlo(R * (size_t)n_), rhi(R * (size_t)n_);
+    pod_vector<int64_t> rlo(R * (size_t)n_), rhi(R * (size_t)n_);       // (filled in parallel below: the workers touch the new pages)
     std::vector<uint8_t> cut(R, 0);
     std::atomic<int> bad(0);
+    const bool have_lo = anchors_on_device_ && initial_lo_.size() == R * (size_t)n_;
+    const bool check_spans = have_lo && getenv("PB200_CHECK_SPANS") != nullptr;
     {
         const long per_blk = 512;
         parallel_chunks(threads_, ((long)R + per_blk - 1) / per_blk, [&](long c) {
             for (size_t p = (size_t)c * per_blk; p < std::min(R, (size_t)(c + 1) * per_blk); ++p) {
                 const int r = initial_regions_[(size_t)X.order[p]];
+                const int32_t* dlo = have_lo ? &initial_lo_[(size_t)X.order[p] * (size_t)n_] : nullptr;
                 for (int g = 0; g < n_; ++g) {
                     const int64_t s = rstart(r)[g], e = rend(r)[g];
                     if (s < 0 || e > len_[g] || e < s) { bad.store(1); continue; }
+                    if (dlo) {
+                        // the engine made these regions (determineRegion on the anchors' layout): it knows the set bit on their left;
+                        // on the right a non-empty region [s, e] ends one base before one (an anchor's start, the next set bit, or
+                        // the sentinel) - no walk over nine bitmap rows per region
+                        rlo[p * (size_t)n_ + g] = dlo[g];
+                        rhi[p * (size_t)n_ + g] = std::min(e + 1, len_[g]);
+                        if (check_spans) {
+                            int64_t a = truth_.layout[g].prev_set(s > 0 ? s - 1 : 0);
+                            if (a < 0) a = 0;
+                            const int64_t b = std::min(truth_.layout[g].next_set(e, len_[g] + 1), len_[g]);
+                            if (a != dlo[g] || b != rhi[p * (size_t)n_ + g]) bad.store(2);
+                        }
+                        continue;
+                    }
                     int64_t a = truth_.layout[g].prev_set(s > 0 ? s - 1 : 0);
                     if (a < 0) a = 0;
                     const int64_t b = truth_.layout[g].next_set(e, len_[g] + 1);   // (the sentinel bit at len ends every scan)
@@ -909,6 +926,7 @@ ReplayCtx* Aligner::replay_prepare() {
                 }
             }
         });
+        if (bad.load() == 2) throw std::logic_error("parsnp_b200: the engine's region bounds differ from the layout (PB200_CHECK_SPANS)");
         if (bad.load()) return nullptr;
         tsec[2] = now_s();
         parallel_chunks(threads_, ((long)R + per_blk - 1) / per_blk, [&](long c) {
