@@ -325,26 +325,35 @@ def main():
         # A_scan = 20 B per query base (both strands)
         "mum_scan(seed_extend_kernel)": {"bytes": 20.0 * timers.get("big_query_bases", 0.0) / seed_n, "ms": seed_ms},
         # SURVEY 8(d) "recursion: same formulas applied to the sum of region lengths": A_sa(r=1) = 221 B per window base + 20 B per query base
-        "recursion(small_region_kernel)": {"bytes": (221.0 * timers.get("small_ref_bases", 0.0) + 20.0 * timers.get("small_query_bases", 0.0)) / small_n,
+        "recursion(recursion_level_kernel+recursion_accept_kernel)": {"bytes": (221.0 * timers.get("small_ref_bases", 0.0) + 20.0 * timers.get("small_query_bases", 0.0)) / small_n,
                                            "ms": small_ms},
     }
     dom_total = {"sa_build_radix_sort(tile_hist+digit_scan+scatter_kernel passes)": groups.get("index_sort", 0.0), "mum_scan(seed_extend_kernel)": groups.get("scan_seed", 0.0),
-                 "recursion(small_region_kernel)": groups.get("small_regions", 0.0)}
+                 "recursion(recursion_level_kernel+recursion_accept_kernel)": groups.get("small_regions", 0.0)}
     dom = max(dom_total, key=lambda k: dom_total[k])
     rk = roof_kernels[dom]
     ach = rk["bytes"] / (rk["ms"] / 1000.0) / 1e9 if rk["ms"] > 0 else 0.0
     # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this workload (tools/ncu_traffic.py)
-    traffic, traffic_src = None, None
+    traffic, traffic_src, issue = None, None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        kname = {"recursion(small_region_kernel)": "small_region_kernel", "mum_scan(seed_extend_kernel)": "seed_extend_kernel"}.get(dom)
-        if args.workload == "configs1" and L == L_FULL and kname in tj["kernels"]:
-            traffic = tj["kernels"][kname]["dram_bytes_per_launch"]
+        knames = {"recursion(recursion_level_kernel+recursion_accept_kernel)": ["recursion_level_kernel", "recursion_accept_kernel"],
+                  "mum_scan(seed_extend_kernel)": ["seed_extend_kernel"],
+                  "sa_build_radix_sort(tile_hist+digit_scan+scatter_kernel passes)": ["tile_hist_kernel", "digit_scan_kernel", "scatter_kernel"]}.get(dom, [])
+        have = [tj["kernels"][k] for k in knames if k in tj["kernels"]]
+        if args.workload == "configs1" and L == L_FULL and have and len(have) == len(knames):
+            # per launch like `achieved`: the group's DRAM bytes over one step / its launches in that step
+            traffic = sum(k["dram_bytes"] for k in have) / max(1, sum(k["launches"] for k in have))
             traffic_src = "profiles/ncu_traffic.json (" + tj["source"] + ")"
+            if "issue_active_pct" in tj and dom in tj["issue_active_pct"]:
+                issue = tj["issue_active_pct"][dom]
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "traffic_source": traffic_src, "peak_source": peak_src,
+                # the recursion kernels are instruction / shared-memory bound by construction (DRAM < 1 %): beside the byte ruler of
+                # SURVEY 8(d), the issue-slot utilisation of their main launches from the committed `ncu --set full` capture
+                "issue_slot_utilisation": issue,
                 "algorithmic_bytes_per_launch": rk["bytes"], "ms_per_launch": rk["ms"],
                 "share_of_gpu_time": dom_total[dom] / gpu_ms_total if gpu_ms_total else 0.0,
                 "other": {k: {"GBps": (v["bytes"] / (v["ms"] / 1000.0) / 1e9 if v["ms"] > 0 else 0.0), "ms": v["ms"]}

@@ -42,9 +42,9 @@ struct Job {
 
 class WorkerPool {
 public:
-    static WorkerPool& get() {
-        static WorkerPool p;
-        return p;
+    static WorkerPool& get(int which) {
+        static WorkerPool p[2];
+        return p[which ? 1 : 0];
     }
     void run(int nthreads, long nchunks, const std::function<void(long)>& fn) {
         bool expected = false;
@@ -110,7 +110,9 @@ private:
 
 }  // namespace
 
-void parallel_run(int nthreads, long nchunks, const std::function<void(long)>& fn) { WorkerPool::get().run(nthreads, nchunks, fn); }
+namespace { thread_local int tl_pool = 0; }
+void parallel_use_second_pool(bool on) { tl_pool = on ? 1 : 0; }
+void parallel_run(int nthreads, long nchunks, const std::function<void(long)>& fn) { WorkerPool::get(tl_pool).run(nthreads, nchunks, fn); }
 
 namespace {
 // std::sort's steps (libstdc++ __sort: __introsort_loop with depth 2 lg n, then __final_insertion_sort) on [v, v + n), driven

@@ -14,6 +14,10 @@
 namespace pb200 {
 
 void parallel_run(int nthreads, long nchunks, const std::function<void(long)>& fn);
+// A thread that works BESIDE the orchestrator's main thread for a while (the replay's task structure is built while the main
+// thread waits for the engine and indexes its answer) takes its helpers from a second pool: on the first one its passes would
+// run inline whenever the main thread is inside one of its own.  Per calling thread.
+void parallel_use_second_pool(bool on);
 
 template <class F>
 inline void parallel_chunks(int nthreads, long nchunks, F&& fn) {

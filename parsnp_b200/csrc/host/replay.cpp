@@ -819,6 +819,7 @@ Aligner::~Aligner() {
 // second thread while the host would otherwise wait for the GPU.
 void Aligner::replay_prepare_async() {
     replay_prep_thread_ = std::thread([this] {
+        parallel_use_second_pool(true);
         try { replay_ctx_ = replay_prepare(); } catch (...) { replay_prep_error_ = std::current_exception(); }
         replay_prepared_ = true;
     });
