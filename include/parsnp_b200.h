@@ -118,7 +118,8 @@ int pb200_result_n(const pb200_result* r);                 /* number of genomes 
 int64_t pb200_result_num_mums(const pb200_result* r);
 /* length[m], slength[m], start[m*n], end[m*n], fwd[m*n] - any pointer may be NULL */
 int pb200_result_mums(const pb200_result* r, int64_t* length, int64_t* slength, int64_t* start, int64_t* end, uint8_t* fwd);
-/* the same arrays without a copy: pointers into the result, valid until pb200_result_free (any pointer argument may be NULL) */
+/* the same arrays without a copy: pointers into the result, valid until pb200_result_free (any pointer argument may be NULL).
+ * end[] = start[] + length (TMum::end) is not stored: it is materialised by the first call that asks for it. */
 int pb200_result_mums_view(const pb200_result* r, const int64_t** length, const int64_t** slength, const int64_t** start,
                            const int64_t** end, const uint8_t** fwd);
 int64_t pb200_result_num_clusters(const pb200_result* r);

@@ -181,6 +181,16 @@ def _view(owner, addr, shape, dtype):
     return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
 
+class _Result(dict):
+    """result dictionary; "mum_end" (= start + length, TMum::end) is computed when somebody asks for it"""
+
+    def __missing__(self, key):
+        if key == "mum_end":
+            self[key] = self["mum_start"] + self["mum_length"][:, None]
+            return self[key]
+        raise KeyError(key)
+
+
 def unpack_result(lib, h):
     """pb200_result* -> dict of numpy arrays.  The MUM arrays are views of the result's own memory (pb200_result_mums_view);
     the handle is freed when the last of them is garbage collected."""
@@ -188,9 +198,9 @@ def unpack_result(lib, h):
     M = lib.pb200_result_num_mums(h)
     owner = _ResultOwner(lib, h)
     p = [C.c_void_p() for _ in range(5)]
-    lib.pb200_result_mums_view(h, *[C.byref(x) for x in p])
+    lib.pb200_result_mums_view(h, C.byref(p[0]), C.byref(p[1]), C.byref(p[2]), None, C.byref(p[4]))
     length = _view(owner, p[0].value, (M,), np.int64); slength = _view(owner, p[1].value, (M,), np.int64)
-    start = _view(owner, p[2].value, (M, n), np.int64); end = _view(owner, p[3].value, (M, n), np.int64)
+    start = _view(owner, p[2].value, (M, n), np.int64)
     fwd = _view(owner, p[4].value, (M, n), np.uint8)
     K = lib.pb200_result_num_clusters(h)
     ctype = np.zeros(K, np.int32); cn = np.zeros(K, np.int64); cl = np.zeros(K, np.int64)
@@ -211,7 +221,7 @@ def unpack_result(lib, h):
     sv = np.zeros(len(names), np.float64)
     lib.pb200_result_stats(h, _ptr(sv), len(names))
     del owner                      # the views hold the remaining references
-    return dict(n=n, mum_length=length, mum_slength=slength, mum_start=start, mum_end=end, mum_fwd=fwd,
+    return _Result(n=n, mum_length=length, mum_slength=slength, mum_start=start, mum_fwd=fwd,
                 cluster_type=ctype, cluster_nmums=cn, cluster_length=cl, cluster_start=cs, cluster_end=ce,
                 cluster_mum_off=cmo, cluster_mum_idx=cmi[:nidx], trace=tr, unaligned=np.stack([ug.astype(np.int64), us, ue], axis=1), stats=dict(zip(names, sv.tolist())))
 

@@ -364,8 +364,21 @@ __global__ void __launch_bounds__(128, 16) seed_extend_kernel(const uint8_t* __r
                 }
                 c = min(c, cmax);
                 if (c < step) {                           // else: an earlier sampled seed lies inside the same match
-                    pend = true;
                     lim = min(m - (j + k), n - (l + k));
+                    // An event needs c + k + ext >= minsize.  Suffixes of a seed bucket that are not the match (every bucket of
+                    // more than one suffix has them, and they carry no flank signature) end within a base or two: 8 bytes to the
+                    // right of the seed settle that here, instead of a whole cooperative step of the warp per such pair (they
+                    // were most of the pending seeds: ~40 % of the kernel's instructions went into their extensions)
+                    const int need = minsize - k - c;     // bases still missing on the right
+                    pend = true;
+                    if (need > 0) {
+                        if (lim < need) pend = false;
+                        else {
+                            const uint64_t x = load8u(Q + j + k) ^ load8u(R + l + k);
+                            const int e8 = x ? ((__ffsll((long long)x) - 1) >> 3) : 8;
+                            if (e8 < 8 && min(e8, lim) < need) pend = false;
+                        }
+                    }
                 }
             }
         }

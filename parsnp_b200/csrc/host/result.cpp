@@ -19,14 +19,15 @@ pb200_result* make_result(const Aligner& a, bool unaligned) {
     r->n = n;
     const int64_t M = a.num_mums();
     r->m_length.resize(M); r->m_slength.resize(M);
-    r->m_start.resize(M * n); r->m_end.resize(M * n); r->m_fwd.resize(M * n);
+    r->m_start.resize(M * n); r->m_fwd.resize(M * n);        // (m_end = start + length: filled when somebody asks for it)
     const long per = 4096;
     parallel_chunks(M > 32768 ? default_host_threads() : 1, ((long)M + per - 1) / per, [&](long c) {
         for (int64_t i = c * per; i < std::min<int64_t>(M, (c + 1) * per); ++i) {
             const MumRec& m = a.mum(i);
             r->m_length[i] = m.length; r->m_slength[i] = m.slength;
             const int64_t* s = a.mum_start(i); const uint8_t* f = a.mum_fwd(i);
-            for (int k = 0; k < n; ++k) { r->m_start[i * n + k] = s[k]; r->m_end[i * n + k] = s[k] + m.length; r->m_fwd[i * n + k] = f[k]; }
+            std::memcpy(&r->m_start[i * n], s, sizeof(int64_t) * (size_t)n);
+            std::memcpy(&r->m_fwd[i * n], f, (size_t)n);
         }
     });
     r->c_mum_off.push_back(0);
@@ -112,11 +113,23 @@ void pb200_params_default(pb200_params* p) {
 const char* pb200_last_error(void) { return pb200::g_last_error.c_str(); }
 int pb200_result_n(const pb200_result* r) { return r->n; }
 int64_t pb200_result_num_mums(const pb200_result* r) { return (int64_t)r->m_length.size(); }
+namespace {
+// end[i][k] = start[i][k] + length[i] (TMum::end, src/TMum.cpp:13-72) into `dst` (M * n entries)
+void fill_mum_ends(const pb200_result* r, int64_t* dst) {
+    const int64_t M = (int64_t)r->m_length.size();
+    const int n = r->n;
+    const long per = 4096;
+    pb200::parallel_chunks(M > 32768 ? pb200::default_host_threads() : 1, ((long)M + per - 1) / per, [&](long c) {
+        for (int64_t i = c * per; i < std::min<int64_t>(M, (c + 1) * per); ++i)
+            for (int k = 0; k < n; ++k) dst[i * n + k] = r->m_start[i * n + k] + r->m_length[i];
+    });
+}
+}  // namespace
 int pb200_result_mums(const pb200_result* r, int64_t* length, int64_t* slength, int64_t* start, int64_t* end, uint8_t* fwd) {
     if (length) std::memcpy(length, r->m_length.data(), r->m_length.size() * 8);
     if (slength) std::memcpy(slength, r->m_slength.data(), r->m_slength.size() * 8);
     if (start) std::memcpy(start, r->m_start.data(), r->m_start.size() * 8);
-    if (end) std::memcpy(end, r->m_end.data(), r->m_end.size() * 8);
+    if (end) fill_mum_ends(r, end);
     if (fwd) std::memcpy(fwd, r->m_fwd.data(), r->m_fwd.size());
     return 0;
 }
@@ -125,7 +138,11 @@ int pb200_result_mums_view(const pb200_result* r, const int64_t** length, const 
     if (length) *length = r->m_length.data();
     if (slength) *slength = r->m_slength.data();
     if (start) *start = r->m_start.data();
-    if (end) *end = r->m_end.data();
+    if (end) {                                   // (materialised on the first request; callers that only need starts and lengths pass NULL)
+        pb200_result* w = const_cast<pb200_result*>(r);
+        if (w->m_end.size() != w->m_start.size()) { w->m_end.resize(w->m_start.size()); fill_mum_ends(r, w->m_end.data()); }
+        *end = r->m_end.data();
+    }
     if (fwd) *fwd = r->m_fwd.data();
     return 0;
 }
