@@ -171,14 +171,15 @@ inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
     kernel<<<grid, block, smem, st>>>(static_cast<KArgs>(args)...);
 }
 
-// unaligned 8-byte load (two aligned loads + funnel shift); may read up to 15 bytes past p: every text buffer is padded
+// unaligned 8-byte load: three aligned 32-bit words + two funnel shifts (SHF); may read up to 11 bytes past p: every text buffer is
+// padded.  (The first form - two aligned 64-bit loads and a 64-bit shift pair - was ~14 instructions of 32-bit arithmetic per
+// call and a quarter of seed_extend_kernel's instruction stream.)
 __device__ __forceinline__ uint64_t load8u(const uint8_t* p) {
-    const uint64_t* a = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)7);
-    const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(p) & 7) * 8;
-    uint64_t lo = a[0];
-    if (sh == 0) return lo;
-    uint64_t hi = a[1];
-    return (lo >> sh) | (hi << (64 - sh));
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const unsigned sh = (unsigned)(a & 3) * 8;
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    return ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
 }
 // four 2-bit base codes (one per byte, first base in byte 0) -> 8 bits, first base most significant
 __device__ __forceinline__ uint32_t pack4x2(uint32_t w) { return ((w & 0x03030303u) * 0x40100401u) >> 24; }
