@@ -221,8 +221,17 @@ int Aligner::CandCache::lookup(const int64_t* coords) const {
 int Aligner::CandCache::lookup(const int64_t* coords, uint64_t hash) const {
     const int n = rp.n;
     const size_t bytes = sizeof(int64_t) * 2 * n;
-    return map.find(hash,
-                    [&](int e) { return std::memcmp(rp.start(entries[e].region), coords, bytes) == 0; });
+    const int hit = map.find(hash, [&](int e) { return std::memcmp(rp.start(entries[e].region), coords, bytes) == 0; });
+    if (hit >= 0 || !sorted_valid) return hit;
+    // entries in ascending start[0] order that the index may not hold (the engine's discovery: regions of gaps that were
+    // expected to need no lookup, build_region_index): a binary search instead
+    const size_t N = entries.size(), stride = 2 * (size_t)n;
+    const int64_t* base = rp.start(0);
+    size_t a = 0, b = N;
+    while (a < b) { const size_t mid = (a + b) >> 1; if (base[mid * stride] < coords[0]) a = mid + 1; else b = mid; }
+    for (; a < N && base[a * stride] == coords[0]; ++a)
+        if ((*sorted_valid)[a] && std::memcmp(base + a * stride, coords, bytes) == 0) return (int)a;
+    return -1;
 }
 
 int Aligner::minsize_cached(CandCache& C, bool anchors, int64_t slength) {
@@ -1008,9 +1017,26 @@ void Aligner::process_queue_exact(const std::vector<int>& initial, RegionPool& r
 #undef PROF_MARK
 }
 
+// the deferred index of the discovery's regions (discover_slice): over all searched regions, or without those of `skip`
+void Aligner::build_region_index(const std::vector<uint8_t>* skip) {
+    if (!disc_index_deferred_ || slice_cache_.empty()) return;
+    if (skip) {
+        const long per = 8192, N = (long)disc_valid_.size();
+        std::vector<uint8_t> v(disc_valid_);
+        parallel_chunks(N > 32768 ? threads_ : 1, (N + per - 1) / per, [&](long c) {
+            for (long r = c * per; r < std::min(N, (c + 1) * per); ++r) if ((*skip)[(size_t)r]) v[(size_t)r] = 0;
+        });
+        slice_cache_[0]->map.build_parallel(disc_hashes_, v, threads_);
+        return;                                 // (stays "deferred": a fallback to the sequential loop asks for the full index)
+    }
+    slice_cache_[0]->map.build_parallel(disc_hashes_, disc_valid_, threads_);
+    disc_index_deferred_ = false;
+}
+
 void Aligner::do_work_exact() {
     double t0 = now_s();
     if (!do_work_parallel()) {                 // replay.cpp: independent gaps on several threads when the anchors allow it
+        build_region_index(nullptr);
         std::vector<int> out;
         process_queue_exact(initial_regions_, rp_, truth_.layout, mp_, out);
         all_mums_.insert(all_mums_.end(), out.begin(), out.end());
@@ -1562,8 +1588,15 @@ bool Aligner::discover_slice(int k) {
         dev_.coords = res.coords; dev_.slen = res.slen; dev_.wins = res.wins; dev_.k = res.k; dev_.sp = res.sp;
         dev_.flags = res.flags; dev_.parent = res.parent; dev_.acc_shift = res.acc_shift; dev_.acc_len = res.acc_len; dev_.fw = res.fw;
     }
-    std::vector<uint8_t> valid(NR);
-    std::vector<uint64_t> hashes(res.hashes, res.hashes + NR);
+    // (the index over the regions' coordinates: built right away, or - when the replay may take most gaps from the engine as final -
+    //  after the gaps have been classified, over the regions it will really look up: build_region_index)
+    std::vector<uint8_t> valid_local;
+    std::vector<uint64_t> hashes_local;
+    const bool defer_index = dev_.valid && k == 0;
+    std::vector<uint8_t>& valid = defer_index ? disc_valid_ : valid_local;
+    std::vector<uint64_t>& hashes = defer_index ? disc_hashes_ : hashes_local;
+    valid.assign(NR, 0);
+    hashes.assign(res.hashes, res.hashes + NR);
     const long nblk = ((long)NR + per - 1) / per;
     std::vector<int64_t> blk_searched((size_t)nblk + 1, 0), blk_cands((size_t)nblk + 1, 0);
     parallel_chunks(NR > 16384 ? threads_ : 1, nblk, [&](long c) {
@@ -1582,7 +1615,9 @@ bool Aligner::discover_slice(int k) {
     });
     int64_t searched = 0, cands = 0;
     for (long c = 0; c < nblk; ++c) { searched += blk_searched[(size_t)c]; cands += blk_cands[(size_t)c]; }
-    C.map.build_parallel(hashes, valid, threads_);
+    disc_index_deferred_ = defer_index;
+    C.sorted_valid = defer_index ? &disc_valid_ : nullptr;  // (entry r = region r of the engine's list, ascending start[0])
+    if (!defer_index) C.map.build_parallel(hashes, valid, threads_);
     std::lock_guard<std::mutex> lk(backend_mu_);           // (the statistics are shared with the replay's on-demand searches)
     stats_.spec_regions += searched;
     stats_.regions_searched += searched;

@@ -199,6 +199,7 @@ private:
         std::vector<WinRec> wins;
         std::vector<CandBatch> chunks;         // one per search call; candidates stay where the backend delivered them
         std::unordered_map<int64_t, int> minsize[2];
+        const std::vector<uint8_t>* sorted_valid = nullptr;   // set: entry r is region r of `rp`, ascending start[0]; [r] = it was searched
         int lookup(const int64_t* coords) const;    // -> index into entries or -1
         int lookup(const int64_t* coords, uint64_t hash) const;      // hash = coords_hash(coords) computed by the caller
     };
@@ -246,6 +247,7 @@ private:
     void speculation_thread_main();
     bool discover_on_device();           // the engine follows the recursion itself (SearchBackend::discover_recursion)
     bool discover_slice(int k);
+    void build_region_index(const std::vector<uint8_t>* skip);
     const CandCache* wait_slice(int slice);
     void wait_slice_quiet(int slice);
     void do_work_exact();
@@ -285,6 +287,9 @@ private:
     World spec_world_;                                      // scratch copy of mumlayout for the speculation
     std::shared_ptr<const std::vector<int32_t>> disc_tab_;  // device discovery: minsize table, initial coordinates, slice bounds
     pod_vector<int64_t> disc_coords_;
+    std::vector<uint64_t> disc_hashes_;                     // the discovery's regions: coordinate hashes and "was searched", kept while the
+    std::vector<uint8_t> disc_valid_;                       // index over them is deferred (build_region_index)
+    bool disc_index_deferred_ = false;
     std::vector<size_t> disc_begin_;
     std::thread spec_thread_;
     std::mutex slice_mu_, backend_mu_;

@@ -1045,6 +1045,17 @@ bool Aligner::replay_run(ReplayCtx& X) {
     }
     const double tc0 = now_s();
     X.classify_gaps();
+    if (disc_index_deferred_) {
+        // the tasks look regions up by their coordinates - but not those of final gaps: the index is built without them (a final
+        // gap that has to be replayed after all, because a foreign write touched it, searches its regions on demand)
+        std::vector<uint8_t> skip(dev_.nregions, 0);
+        if (X.any_final)
+            parallel_chunks(X.ngaps > 4096 ? threads_ : 1, ((long)X.ngaps + 1023) / 1024, [&](long c) {
+                for (int j = (int)c * 1024; j < std::min(X.ngaps, (int)(c + 1) * 1024); ++j)
+                    if (X.gfinal[(size_t)j]) std::memset(&skip[(size_t)X.gr0[(size_t)j]], 1, (size_t)(X.gr1[(size_t)j] - X.gr0[(size_t)j]));
+            });
+        build_region_index(&skip);
+    }
     const double tr0 = now_s();
     // (the process-wide pool of sleeping threads: no thread is created per alignment.  If the pool is busy - the host's own
     //  level-by-level speculation uses it when the engine does not follow the recursion itself - the workers run one after the
@@ -1144,6 +1155,7 @@ bool Aligner::replay_run(ReplayCtx& X) {
         // a tie inside task F: rebuild the layout as the reference has it when it reaches that task (anchors + the MUMs of
         // everything before), then its own loop from there
         stats_.replay_fallback = 1;
+        build_region_index(nullptr);
         parallel_chunks(threads_, (long)n_, [&](long g) {
             BitRow& row = truth_.layout[(size_t)g];
             row.init(len_[(size_t)g] + 1);
