@@ -91,6 +91,12 @@ int pbtest_literal_sort_check(const int64_t* keys, int64_t n, int threads) {
     std::sort(a.begin(), a.end(), [](const std::pair<int64_t, int>& x, const std::pair<int64_t, int>& y) { return x.first < y.first; });
     pb200::literal_std_sort_by_first(b.data(), (size_t)n, threads);
     for (int64_t i = 0; i < n; ++i) if (a[(size_t)i] != b[(size_t)i]) return 1;
+    // the same with the tied keys given (ranges without equal keys are then sorted by other means)
+    std::vector<int64_t> tk;
+    for (int64_t i = 1; i < n; ++i) if (a[(size_t)i].first == a[(size_t)i - 1].first && (tk.empty() || tk.back() != a[(size_t)i].first)) tk.push_back(a[(size_t)i].first);
+    for (int64_t i = 0; i < n; ++i) b[(size_t)i] = std::make_pair(keys[i], (int)i);
+    pb200::literal_std_sort_by_first(b.data(), (size_t)n, threads, tk.data(), tk.size());
+    for (int64_t i = 0; i < n; ++i) if (a[(size_t)i] != b[(size_t)i]) return 2;
     return 0;
 }
 int pbtest_lrp(const uint8_t* R, int64_t n, int32_t* out) {

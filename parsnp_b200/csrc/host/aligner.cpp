@@ -1061,6 +1061,7 @@ void Aligner::sort_final_mums() {
         const long nch = ((long)M + per - 1) / per;
         std::vector<uint8_t> ch_bad((size_t)nch, 0), ch_tie((size_t)nch, 0);
         std::vector<int64_t> ch_minlen((size_t)nch, INT64_MAX);
+        std::vector<std::vector<int64_t>> ch_tkeys((size_t)nch);       // the keys that occur more than once (ascending)
         parallel_chunks(M > 32768 ? threads_ : 1, nch, [&](long c) {
             const size_t i0 = (size_t)c * per, i1 = std::min(M, (size_t)(c + 1) * per);
             int64_t prev = i0 ? mum_start_[mums_[sorted_hint_[i0 - 1]].off] : INT64_MIN, ml = INT64_MAX;
@@ -1068,7 +1069,7 @@ void Aligner::sort_final_mums() {
                 const MumRec& m = mums_[sorted_hint_[i]];
                 const int64_t s0 = mum_start_[m.off];
                 if (s0 < prev) ch_bad[c] = 1;
-                if (s0 == prev) ch_tie[c] = 1;
+                if (s0 == prev) { ch_tie[c] = 1; ch_tkeys[(size_t)c].push_back(s0); }
                 prev = s0;
                 ml = std::min(ml, m.length);
             }
@@ -1091,7 +1092,12 @@ void Aligner::sort_final_mums() {
             parallel_chunks(M > 32768 ? threads_ : 1, nch, [&](long c) {
                 for (size_t i = (size_t)c * per; i < std::min(M, (size_t)(c + 1) * per); ++i) kv0[i] = std::make_pair(mum_start_[mums_[final_mums_[i]].off], final_mums_[i]);
             });
-            literal_std_sort_by_first(kv0.data(), M, threads_);
+            std::vector<int64_t> tkeys;
+            for (const auto& t : ch_tkeys) tkeys.insert(tkeys.end(), t.begin(), t.end());
+            tkeys.erase(std::unique(tkeys.begin(), tkeys.end()), tkeys.end());
+            const double tl0 = now_s();
+            literal_std_sort_by_first(kv0.data(), M, threads_, tkeys.data(), tkeys.size());
+            if (getenv("PB200_PROFILE_HOST")) fprintf(stderr, "[pb200 literal sort ms] %.2f (%zu tied keys)\n", (now_s() - tl0) * 1e3, tkeys.size());
             parallel_chunks(M > 32768 ? threads_ : 1, nch, [&](long c) {
                 for (size_t i = (size_t)c * per; i < std::min(M, (size_t)(c + 1) * per); ++i) final_mums_[i] = kv0[i].second;
             });
@@ -1134,6 +1140,7 @@ void Aligner::sort_final_mums() {
     // operator< on start[0] (src/TMum.cpp:151) at every one of these calls.  The same algorithm on (start0, id) records in the
     // same initial order makes the same comparisons and moves, hence the same permutation - whatever the element type.
     bool kv_initial = true;                             // kv = the records in the initial order (as gathered above)
+    std::vector<int64_t> tkeys;
     static const bool prof_sort = getenv("PB200_PROFILE_HOST") != nullptr;
     auto literal_sort = [&]() {
         const double tl0 = now_s();
@@ -1141,15 +1148,16 @@ void Aligner::sort_final_mums() {
             parallel_chunks(M > 32768 ? threads_ : 1, nch, [&](long c) {
                 for (size_t i = (size_t)c * per; i < std::min(M, (size_t)(c + 1) * per); ++i) kv[i] = std::make_pair(mum_start_[mums_[final_mums_[i]].off], final_mums_[i]);
             });
-        literal_std_sort_by_first(kv.data(), M, threads_);     // = std::sort(kv.begin(), kv.end(), by .first), on several threads (parallel.h)
+        literal_std_sort_by_first(kv.data(), M, threads_, tkeys.data(), tkeys.size());     // = std::sort(kv.begin(), kv.end(), by .first) (parallel.h)
         const double tl1 = now_s();
         for (size_t i = 0; i < M; ++i) final_mums_[i] = kv[i].second;
         final_sorted_ = false;                         // the next call sorts again, like the reference
         if (prof_sort) fprintf(stderr, "[pb200 literal sort ms] %.2f (+ %.2f)\n", (tl1 - tl0) * 1e3, (now_s() - tl1) * 1e3);
     };
-    auto has_ties = [&]() {
-        for (size_t i = 1; i < M; ++i) if (kv[i].first == kv[i - 1].first) return true;
-        return false;
+    auto has_ties = [&]() {                             // (kv ascending here) + the tied keys for the literal call
+        tkeys.clear();
+        for (size_t i = 1; i < M; ++i) if (kv[i].first == kv[i - 1].first && (tkeys.empty() || tkeys.back() != kv[i].first)) tkeys.push_back(kv[i].first);
+        return !tkeys.empty();
     };
     final_sorted_ = true;
     if (descents == 0) {

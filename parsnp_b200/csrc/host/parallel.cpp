@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
+#include <cstring>
 #include <exception>
 #include <memory>
 #include <mutex>
@@ -115,57 +116,165 @@ void parallel_use_second_pool(bool on) { tl_pool = on ? 1 : 0; }
 void parallel_run(int nthreads, long nchunks, const std::function<void(long)>& fn) { WorkerPool::get(tl_pool).run(nthreads, nchunks, fn); }
 
 namespace {
-// std::sort's steps (libstdc++ __sort: __introsort_loop with depth 2 lg n, then __final_insertion_sort) on [v, v + n), driven
-// range by range; T = element type, less = the comparison the caller's std::sort call would have used
+// ---- std::sort(v, v + n, less), the same permutation, ties included (libstdc++ __sort: __introsort_loop with depth 2 lg n,
+// then __final_insertion_sort), driven range by range:
+//   * the two sides of a partition are independent: ranges are partitioned level by level, the rest of every range is left
+//     to the library's own std::__introsort_loop / std::__insertion_sort (the final insertion pass never moves anything
+//     across a partition cut: elements left of a cut are not greater than elements right of it);
+//   * `tie_keys` given (the keys that occur more than once): only a range that still holds two elements with the same key
+//     has to be followed literally - everywhere else the ascending order is unique, so any sort will do.  After a partition
+//     around pivot key P a tied key < P is in the left part, > P in the right part (== P: both parts are looked at);
+//   * the literal partition is restated here (std::__unguarded_partition_pivot = median of first+1 / mid / last-1 moved to
+//     first, then the two-pointer loop) so that a LONG scan of one pointer - on the MUM list's shape the down scan crosses
+//     the whole range for 34 rounds in a row - becomes a parallel search for the same position.
 template <class T, class Less>
-void literal_sort_impl(T* v, size_t n, int threads, Less less) {
+T* find_up(T* lo, T* end, const T& pivot, Less less, int threads) {          // first p >= lo with !less(*p, pivot); exists before `end`
+    for (int i = 0; i < 256; ++i, ++lo) if (!less(*lo, pivot)) return lo;
+    const long n = end - lo, per = 16384, nch = (n + per - 1) / per;
+    if (threads <= 1 || nch < 4) { while (less(*lo, pivot)) ++lo; return lo; }
+    std::atomic<long> best(n);
+    parallel_chunks(threads, nch, [&](long c) {
+        if (c * per >= best.load(std::memory_order_relaxed)) return;
+        for (long i = c * per; i < std::min(n, (c + 1) * per); ++i)
+            if (!less(lo[i], pivot)) { long b = best.load(); while (i < b && !best.compare_exchange_weak(b, i)) {} return; }
+    });
+    return lo + best.load();
+}
+template <class T, class Less>
+T* find_down(T* hi, T* begin, const T& pivot, Less less, int threads) {       // last p <= hi with !less(pivot, *p); exists at or after `begin`
+    for (int i = 0; i < 256; ++i, --hi) if (!less(pivot, *hi)) return hi;
+    const long n = hi - begin + 1, per = 16384, nch = (n + per - 1) / per;
+    if (threads <= 1 || nch < 4) { while (less(pivot, *hi)) --hi; return hi; }
+    std::atomic<long> best(-1);                                              // index from `begin`
+    parallel_chunks(threads, nch, [&](long c) {
+        const long c0 = nch - 1 - c;                                         // (high chunks first)
+        if ((c0 + 1) * per <= best.load(std::memory_order_relaxed)) return;
+        for (long i = std::min(n, (c0 + 1) * per) - 1; i >= c0 * per; --i)
+            if (!less(pivot, begin[i])) { long b = best.load(); while (i > b && !best.compare_exchange_weak(b, i)) {} return; }
+    });
+    return begin + best.load();
+}
+template <class T, class Less>
+T* partition_pivot_literal(T* first, T* last, Less less, int threads) {
+    T* mid = first + (last - first) / 2;
+    T *a = first + 1, *b = mid, *c = last - 1;                               // std::__move_median_to_first(first, a, b, c)
+    if (less(*a, *b)) {
+        if (less(*b, *c)) std::iter_swap(first, b);
+        else if (less(*a, *c)) std::iter_swap(first, c);
+        else std::iter_swap(first, a);
+    } else if (less(*a, *c)) std::iter_swap(first, a);
+    else if (less(*b, *c)) std::iter_swap(first, c);
+    else std::iter_swap(first, b);
+    T* lo = first + 1;                                                       // std::__unguarded_partition(first + 1, last, first)
+    T* hi = last;
+    const T& pivot = *first;
+    for (;;) {
+        lo = find_up(lo, last, pivot, less, threads);
+        --hi;
+        hi = find_down(hi, first, pivot, less, threads);
+        if (!(lo < hi)) return lo;
+        std::iter_swap(lo, hi);
+        ++lo;
+    }
+}
+// any-order sort of a range without equal keys: 32-bit keys in the upper half of a word -> LSD byte radix; else std::sort
+template <class T, class Less> void unique_order_sort(T* first, T* last, Less less, std::vector<T>&) { std::sort(first, last, less); }
+template <class Less> void unique_order_sort(uint64_t* first, uint64_t* last, Less less, std::vector<uint64_t>& tmp) {
+    const size_t n = (size_t)(last - first);
+    if (n < 2048) { std::sort(first, last, less); return; }
+    tmp.resize(n);
+    uint64_t* src = first;
+    uint64_t* dst = tmp.data();
+    uint64_t all_or = 0, all_and = ~0ull;
+    for (size_t i = 0; i < n; ++i) { all_or |= first[i]; all_and &= first[i]; }
+    for (int shift = 32; shift < 64; shift += 8) {
+        if ((((all_or ^ all_and) >> shift) & 0xff) == 0) continue;            // the byte is the same everywhere
+        size_t cnt[257] = {0};
+        for (size_t i = 0; i < n; ++i) cnt[((src[i] >> shift) & 0xff) + 1]++;
+        for (int d = 0; d < 256; ++d) cnt[d + 1] += cnt[d];
+        for (size_t i = 0; i < n; ++i) dst[cnt[(src[i] >> shift) & 0xff]++] = src[i];
+        std::swap(src, dst);
+    }
+    if (src != first) std::memcpy(first, src, n * sizeof(uint64_t));
+}
+
+template <class T, class Less, class KeyOf>
+void literal_sort_impl(T* v, size_t n, int threads, Less less, KeyOf key_of, const int64_t* tie_keys, size_t ntie) {
 #if defined(__GLIBCXX__)
-    if (threads > 1 && n >= 32768) {
+    if (n >= 32768 && (threads > 1 || tie_keys)) {
         auto cmp = __gnu_cxx::__ops::__iter_comp_iter(less);
-        struct Range { T* first; T* last; long depth; };
-        std::vector<Range> ranges(1, Range{v, v + n, (long)std::__lg((long)n) * 2}), next;
-        const long leaf = (long)std::max<size_t>(4096, n / ((size_t)threads * 8));
+        struct Range { T* first; T* last; long depth; std::vector<int64_t> ties; bool literal; };
+        std::vector<Range> ranges, next;
+        ranges.push_back(Range{v, v + n, (long)std::__lg((long)n) * 2, std::vector<int64_t>(), true});
+        if (tie_keys) ranges[0].ties.assign(tie_keys, tie_keys + ntie);
+        const long leaf = (long)std::max<size_t>(4096, n / ((size_t)std::max(1, threads) * 8));
         std::vector<size_t> big;
         std::vector<T*> cuts;
+        auto count_key = [&](const T* f, const T* l, int64_t k) { long c = 0; for (; f != l; ++f) c += key_of(*f) == k; return c; };
         for (;;) {
-            // one step of __introsort_loop for every range that is still large: partition; both sides go on with depth - 1
+            // one step of __introsort_loop for every range that must be followed and is still large
             big.clear();
-            for (size_t i = 0; i < ranges.size(); ++i)
-                if (ranges[i].last - ranges[i].first > leaf && ranges[i].depth > 0) big.push_back(i);
+            for (size_t i = 0; i < ranges.size(); ++i) {
+                const Range& r = ranges[i];
+                if (r.literal && r.depth > 0 && (tie_keys ? r.last - r.first > 16 : r.last - r.first > leaf)) big.push_back(i);
+            }
             if (big.empty()) break;
             cuts.assign(big.size(), nullptr);
-            parallel_chunks(threads, (long)big.size(), [&](long b) {
-                const Range& r = ranges[big[(size_t)b]];
-                cuts[(size_t)b] = std::__unguarded_partition_pivot(r.first, r.last, cmp);
-            });
+            if (tie_keys) {
+                // (few ranges, possibly long ones: one after the other, each with the pool for its long scans)
+                for (size_t b = 0; b < big.size(); ++b) cuts[b] = partition_pivot_literal(ranges[big[b]].first, ranges[big[b]].last, less, threads);
+            } else {
+                parallel_chunks(threads, (long)big.size(), [&](long b) {
+                    const Range& r = ranges[big[(size_t)b]];
+                    cuts[(size_t)b] = std::__unguarded_partition_pivot(r.first, r.last, cmp);
+                });
+            }
             next.clear();
             size_t bi = 0;
             for (size_t i = 0; i < ranges.size(); ++i) {
-                const Range& r = ranges[i];
-                if (bi < big.size() && big[bi] == i) {
-                    next.push_back(Range{r.first, cuts[bi], r.depth - 1});
-                    next.push_back(Range{cuts[bi], r.last, r.depth - 1});
-                    ++bi;
-                } else next.push_back(r);
+                Range& r = ranges[i];
+                if (!(bi < big.size() && big[bi] == i)) { next.push_back(std::move(r)); continue; }
+                T* cut = cuts[bi++];
+                Range L{r.first, cut, r.depth - 1, std::vector<int64_t>(), true}, R{cut, r.last, r.depth - 1, std::vector<int64_t>(), true};
+                if (tie_keys) {
+                    const int64_t P = key_of(*r.first);                       // (the pivot stays at `first`)
+                    for (int64_t k : r.ties) {
+                        if (k < P) L.ties.push_back(k);
+                        else if (k > P) R.ties.push_back(k);
+                        else {
+                            if (count_key(L.first, L.last, k) >= 2) L.ties.push_back(k);
+                            if (count_key(R.first, R.last, k) >= 2) R.ties.push_back(k);
+                        }
+                    }
+                    L.literal = !L.ties.empty();
+                    R.literal = !R.ties.empty();
+                }
+                next.push_back(std::move(L));
+                next.push_back(std::move(R));
             }
             ranges.swap(next);
         }
-        // the rest of every range with the library's own loop (heap sort when the depth budget is spent), then its share of the
-        // final insertion pass: elements left of a partition cut are never greater than elements right of it, so the global
-        // (unguarded) insertion would stop at the cut where the guarded one stops at the range's first element
+        // the rest: literal ranges with the library's own loop (heap sort when the depth budget is spent) and their share of the
+        // final insertion pass; ranges without equal keys by any sort
         parallel_chunks(threads, (long)ranges.size(), [&](long i) {
             const Range& r = ranges[(size_t)i];
-            std::__introsort_loop(r.first, r.last, r.depth, cmp);
-            std::__insertion_sort(r.first, r.last, cmp);
+            if (r.literal) {
+                std::__introsort_loop(r.first, r.last, r.depth, cmp);
+                std::__insertion_sort(r.first, r.last, cmp);
+            } else {
+                std::vector<T> tmp;
+                unique_order_sort(r.first, r.last, less, tmp);
+            }
         });
         return;
     }
 #endif
+    (void)key_of; (void)tie_keys; (void)ntie;
     std::sort(v, v + n, less);
 }
 }  // namespace
 
-void literal_std_sort_by_first(std::pair<int64_t, int>* v, size_t n, int threads) {
+void literal_std_sort_by_first(std::pair<int64_t, int>* v, size_t n, int threads, const int64_t* tie_keys, size_t ntie) {
     typedef std::pair<int64_t, int> P;
     // keys and ids that fit 32 bits each travel as one 64-bit word compared on its upper half: the algorithm sees the same
     // outcome of every comparison and makes the same moves on elements half the size
@@ -181,14 +290,15 @@ void literal_std_sort_by_first(std::pair<int64_t, int>* v, size_t n, int threads
             }
         });
         if (!wide.load()) {
-            literal_sort_impl(w.data(), n, threads, [](uint64_t x, uint64_t y) { return (x >> 32) < (y >> 32); });
+            literal_sort_impl(w.data(), n, threads, [](uint64_t x, uint64_t y) { return (x >> 32) < (y >> 32); },
+                              [](uint64_t x) { return (int64_t)(x >> 32); }, tie_keys, ntie);
             parallel_chunks(n >= 65536 ? threads : 1, nch, [&](long c) {
                 for (size_t i = (size_t)c * per; i < std::min(n, (size_t)(c + 1) * per); ++i) v[i] = P((int64_t)(w[i] >> 32), (int)(uint32_t)w[i]);
             });
             return;
         }
     }
-    literal_sort_impl(v, n, threads, [](const P& x, const P& y) { return x.first < y.first; });
+    literal_sort_impl(v, n, threads, [](const P& x, const P& y) { return x.first < y.first; }, [](const P& x) { return x.first; }, tie_keys, ntie);
 }
 
 }  // namespace pb200

@@ -34,6 +34,8 @@ inline void parallel_chunks(int nthreads, long nchunks, F&& fn) {
 // (std::__unguarded_partition_pivot per range, level by level, same depth budget), small ranges finish with the library's
 // std::__introsort_loop, and the final insertion pass runs per range (every range starts at a partition cut: nothing moves
 // across it).  Same comparisons on the same data in every range, hence the same permutation.
-void literal_std_sort_by_first(std::pair<int64_t, int>* v, size_t n, int threads);
+// tie_keys (optional): the keys that occur more than once, ascending - then only the ranges that still hold two elements with
+// the same key are followed literally; every other range has ONE ascending order and is sorted by the fastest means.
+void literal_std_sort_by_first(std::pair<int64_t, int>* v, size_t n, int threads, const int64_t* tie_keys = nullptr, size_t ntie = 0);
 
 }  // namespace pb200

@@ -284,9 +284,20 @@ def test_parallel_literal_sort_equals_std_sort():
         shapes = [rng.integers(0, n // 3, n), rng.integers(0, 7, n), np.sort(rng.integers(0, n // 2, n)),
                   np.sort(rng.integers(0, n // 2, n))[::-1].copy(), np.concatenate([np.sort(rng.integers(0, n, n // 4)), np.sort(rng.integers(0, n, n - n // 4))]),
                   np.zeros(n, np.int64), np.arange(n) // 2]
+        # + the MUM list's own shape with ONE tied pair at a random place (what the alignments really produce): two ascending
+        # runs, a few local descents in the second, distinct keys except one
+        for rep in range(6):
+            ks = rng.permutation(4 * n)[:n]
+            a, b = np.sort(ks[:n // 4]), np.sort(ks[n // 4:])
+            for i in range(0, len(b) - 1, 120):
+                b[i], b[i + 1] = b[i + 1], b[i]
+            keys = np.concatenate([a, b])
+            i, j = rng.integers(0, n, 2)
+            keys[i] = keys[j]
+            shapes.append(keys)
         for keys in shapes:
             keys = np.ascontiguousarray(keys, np.int64)
-            for threads in (2, 3, 8):
+            for threads in (1, 2, 3, 8):
                 assert lib.pbtest_literal_sort_check(keys.ctypes.data, len(keys), threads) == 0
 
 
