@@ -97,6 +97,12 @@ int pbtest_literal_sort_check(const int64_t* keys, int64_t n, int threads) {
     for (int64_t i = 0; i < n; ++i) b[(size_t)i] = std::make_pair(keys[i], (int)i);
     pb200::literal_std_sort_by_first(b.data(), (size_t)n, threads, tk.data(), tk.size());
     for (int64_t i = 0; i < n; ++i) if (a[(size_t)i] != b[(size_t)i]) return 2;
+    // ... and with the ascending list as a hint, its tied records in the OTHER order
+    std::vector<std::pair<int64_t, int>> h(a);
+    for (int64_t i = 1; i < n; ++i) if (h[(size_t)i].first == h[(size_t)i - 1].first) { std::swap(h[(size_t)i], h[(size_t)i - 1]); ++i; }
+    for (int64_t i = 0; i < n; ++i) b[(size_t)i] = std::make_pair(keys[i], (int)i);
+    pb200::literal_std_sort_by_first(b.data(), (size_t)n, threads, tk.data(), tk.size(), h.data());
+    for (int64_t i = 0; i < n; ++i) if (a[(size_t)i] != b[(size_t)i]) return 3;
     return 0;
 }
 int pbtest_lrp(const uint8_t* R, int64_t n, int32_t* out) {

@@ -1085,18 +1085,23 @@ void Aligner::sort_final_mums() {
             final_sorted_ = true;
             return;
         }
-        sorted_hint_.clear();                   // (ties or an unexpected order: the general path)
+        if (bad) sorted_hint_.clear();          // (an unexpected order: the general path)
         if (!bad) {
             // ascending with ties: only the literal call on the initial order can say how the reference orders them
-            std::vector<std::pair<int64_t, int>> kv0(M);
+            std::vector<std::pair<int64_t, int>> kv0(M), kvh(M);        // the records in the initial order / in the hint's ascending order
+            const std::vector<int> hint_ids(std::move(sorted_hint_));
+            sorted_hint_.clear();
             parallel_chunks(M > 32768 ? threads_ : 1, nch, [&](long c) {
-                for (size_t i = (size_t)c * per; i < std::min(M, (size_t)(c + 1) * per); ++i) kv0[i] = std::make_pair(mum_start_[mums_[final_mums_[i]].off], final_mums_[i]);
+                for (size_t i = (size_t)c * per; i < std::min(M, (size_t)(c + 1) * per); ++i) {
+                    kv0[i] = std::make_pair(mum_start_[mums_[final_mums_[i]].off], final_mums_[i]);
+                    kvh[i] = std::make_pair(mum_start_[mums_[hint_ids[i]].off], hint_ids[i]);
+                }
             });
             std::vector<int64_t> tkeys;
             for (const auto& t : ch_tkeys) tkeys.insert(tkeys.end(), t.begin(), t.end());
             tkeys.erase(std::unique(tkeys.begin(), tkeys.end()), tkeys.end());
             const double tl0 = now_s();
-            literal_std_sort_by_first(kv0.data(), M, threads_, tkeys.data(), tkeys.size());
+            literal_std_sort_by_first(kv0.data(), M, threads_, tkeys.data(), tkeys.size(), kvh.data());
             if (getenv("PB200_PROFILE_HOST")) fprintf(stderr, "[pb200 literal sort ms] %.2f (%zu tied keys)\n", (now_s() - tl0) * 1e3, tkeys.size());
             parallel_chunks(M > 32768 ? threads_ : 1, nch, [&](long c) {
                 for (size_t i = (size_t)c * per; i < std::min(M, (size_t)(c + 1) * per); ++i) final_mums_[i] = kv0[i].second;
@@ -1150,7 +1155,9 @@ void Aligner::sort_final_mums() {
             });
         literal_std_sort_by_first(kv.data(), M, threads_, tkeys.data(), tkeys.size());     // = std::sort(kv.begin(), kv.end(), by .first) (parallel.h)
         const double tl1 = now_s();
-        for (size_t i = 0; i < M; ++i) final_mums_[i] = kv[i].second;
+        parallel_chunks(M > 32768 ? threads_ : 1, nch, [&](long c) {
+            for (size_t i = (size_t)c * per; i < std::min(M, (size_t)(c + 1) * per); ++i) final_mums_[i] = kv[i].second;
+        });
         final_sorted_ = false;                         // the next call sorts again, like the reference
         if (prof_sort) fprintf(stderr, "[pb200 literal sort ms] %.2f (+ %.2f)\n", (tl1 - tl0) * 1e3, (now_s() - tl1) * 1e3);
     };

@@ -199,7 +199,7 @@ template <class Less> void unique_order_sort(uint64_t* first, uint64_t* last, Le
 }
 
 template <class T, class Less, class KeyOf>
-void literal_sort_impl(T* v, size_t n, int threads, Less less, KeyOf key_of, const int64_t* tie_keys, size_t ntie) {
+void literal_sort_impl(T* v, size_t n, int threads, Less less, KeyOf key_of, const int64_t* tie_keys, size_t ntie, const T* hint) {
 #if defined(__GLIBCXX__)
     if (n >= 32768 && (threads > 1 || tie_keys)) {
         auto cmp = __gnu_cxx::__ops::__iter_comp_iter(less);
@@ -262,6 +262,14 @@ void literal_sort_impl(T* v, size_t n, int threads, Less less, KeyOf key_of, con
                 std::__introsort_loop(r.first, r.last, r.depth, cmp);
                 std::__insertion_sort(r.first, r.last, cmp);
             } else {
+                // one possible order: the caller's ascending list says which (unless a tied pair straddles the range's border:
+                // then the range holds ONE of the two, and only sorting tells which); else already sorted?; else a radix sort
+                const size_t f = (size_t)(r.first - v), l = (size_t)(r.last - v);
+                if (hint && l > f && !(f > 0 && key_of(hint[f - 1]) == key_of(hint[f])) && !(l < n && key_of(hint[l - 1]) == key_of(hint[l]))) {
+                    std::memcpy((void*)r.first, (const void*)(hint + f), (l - f) * sizeof(T));
+                    return;
+                }
+                if (std::is_sorted(r.first, r.last, less)) return;
                 std::vector<T> tmp;
                 unique_order_sort(r.first, r.last, less, tmp);
             }
@@ -269,12 +277,14 @@ void literal_sort_impl(T* v, size_t n, int threads, Less less, KeyOf key_of, con
         return;
     }
 #endif
-    (void)key_of; (void)tie_keys; (void)ntie;
+    (void)key_of; (void)tie_keys; (void)ntie; (void)hint;
     std::sort(v, v + n, less);
 }
 }  // namespace
 
-void literal_std_sort_by_first(std::pair<int64_t, int>* v, size_t n, int threads, const int64_t* tie_keys, size_t ntie) {
+void literal_std_sort_by_first(std::pair<int64_t, int>* v, size_t n, int threads, const int64_t* tie_keys, size_t ntie,
+                               const std::pair<int64_t, int>* hint) {
+    if (!tie_keys) hint = nullptr;
     typedef std::pair<int64_t, int> P;
     // keys and ids that fit 32 bits each travel as one 64-bit word compared on its upper half: the algorithm sees the same
     // outcome of every comparison and makes the same moves on elements half the size
@@ -282,23 +292,24 @@ void literal_std_sort_by_first(std::pair<int64_t, int>* v, size_t n, int threads
     if (narrow) {
         const long per = 16384, nch = ((long)n + per - 1) / per;
         std::atomic<int> wide(0);
-        std::vector<uint64_t> w(n);
+        std::vector<uint64_t> w(n), wh(hint ? n : 0);
         parallel_chunks(n >= 65536 ? threads : 1, nch, [&](long c) {
             for (size_t i = (size_t)c * per; i < std::min(n, (size_t)(c + 1) * per); ++i) {
                 if ((uint64_t)v[i].first >> 32 || v[i].second < 0) { wide.store(1, std::memory_order_relaxed); break; }
                 w[i] = ((uint64_t)v[i].first << 32) | (uint32_t)v[i].second;
+                if (hint) wh[i] = ((uint64_t)hint[i].first << 32) | (uint32_t)hint[i].second;       // (the same records in another order)
             }
         });
         if (!wide.load()) {
             literal_sort_impl(w.data(), n, threads, [](uint64_t x, uint64_t y) { return (x >> 32) < (y >> 32); },
-                              [](uint64_t x) { return (int64_t)(x >> 32); }, tie_keys, ntie);
+                              [](uint64_t x) { return (int64_t)(x >> 32); }, tie_keys, ntie, hint ? wh.data() : (const uint64_t*)nullptr);
             parallel_chunks(n >= 65536 ? threads : 1, nch, [&](long c) {
                 for (size_t i = (size_t)c * per; i < std::min(n, (size_t)(c + 1) * per); ++i) v[i] = P((int64_t)(w[i] >> 32), (int)(uint32_t)w[i]);
             });
             return;
         }
     }
-    literal_sort_impl(v, n, threads, [](const P& x, const P& y) { return x.first < y.first; }, [](const P& x) { return x.first; }, tie_keys, ntie);
+    literal_sort_impl(v, n, threads, [](const P& x, const P& y) { return x.first < y.first; }, [](const P& x) { return x.first; }, tie_keys, ntie, hint);
 }
 
 }  // namespace pb200

@@ -36,6 +36,8 @@ inline void parallel_chunks(int nthreads, long nchunks, F&& fn) {
 // across it).  Same comparisons on the same data in every range, hence the same permutation.
 // tie_keys (optional): the keys that occur more than once, ascending - then only the ranges that still hold two elements with
 // the same key are followed literally; every other range has ONE ascending order and is sorted by the fastest means.
-void literal_std_sort_by_first(std::pair<int64_t, int>* v, size_t n, int threads, const int64_t* tie_keys = nullptr, size_t ntie = 0);
+// hint (optional, with tie_keys): the same records in ascending key order (tied ones in any order) - such a range is then copied.
+void literal_std_sort_by_first(std::pair<int64_t, int>* v, size_t n, int threads, const int64_t* tie_keys = nullptr, size_t ntie = 0,
+                               const std::pair<int64_t, int>* hint = nullptr);
 
 }  // namespace pb200
