@@ -819,7 +819,9 @@ Aligner::~Aligner() {
 // second thread while the host would otherwise wait for the GPU.
 void Aligner::replay_prepare_async() {
     replay_prep_thread_ = std::thread([this] {
-        parallel_use_second_pool(true);
+        // (with few cores per rank a second set of helpers only competes with the main thread's own passes: at 4 threads per
+        //  rank, 8 ranks on 32 cores, the replay then waited longer for this structure than the helpers saved)
+        parallel_use_second_pool(threads_ >= 8);
         try { replay_ctx_ = replay_prepare(); } catch (...) { replay_prep_error_ = std::current_exception(); }
         replay_prepared_ = true;
     });
