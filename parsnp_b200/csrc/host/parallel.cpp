@@ -1,7 +1,9 @@
 #include "parallel.h"
 #include <algorithm>
 #include <atomic>
+#include <climits>
 #include <condition_variable>
+#include <cstdint>
 #include <cstring>
 #include <exception>
 #include <memory>
@@ -126,54 +128,83 @@ namespace {
 //     around pivot key P a tied key < P is in the left part, > P in the right part (== P: both parts are looked at);
 //   * the literal partition is restated here (std::__unguarded_partition_pivot = median of first+1 / mid / last-1 moved to
 //     first, then the two-pointer loop) so that a LONG scan of one pointer - on the MUM list's shape the down scan crosses
-//     the whole range for 34 rounds in a row - becomes a parallel search for the same position.
-template <class T, class Less>
-T* find_up(T* lo, T* end, const T& pivot, Less less, int threads) {          // first p >= lo with !less(*p, pivot); exists before `end`
+//     the whole range for 34 rounds in a row - can skip the blocks that hold no candidate (BlockIndex below).
+// Conservative block summaries of the array being sorted (blocks of 1024 records): lo[b] <= every key in block b <= hi[b].
+// A long pointer scan of the partition ("the next record that is not less / not greater than the pivot") skips the blocks
+// that cannot hold one; swaps only widen the summaries, so a skipped block never held a candidate - the scan stops at the
+// same record as the plain loop.  (On the MUM list's shape the down scan crosses ~130 000 records that are all greater than
+// the pivot, 34 rounds in a row.)
+template <class T, class KeyOf>
+struct BlockIndex {
+    static constexpr int SHIFT = 10;
+    const T* base = nullptr;
+    KeyOf key_of;
+    std::vector<int64_t> lo, hi;
+    BlockIndex(const T* v, size_t n, KeyOf k, int threads) : base(v), key_of(k) {
+        const long nb = (long)((n + (1u << SHIFT) - 1) >> SHIFT);
+        lo.assign((size_t)nb, INT64_MAX);
+        hi.assign((size_t)nb, INT64_MIN);
+        parallel_chunks(nb >= 64 ? threads : 1, nb, [&](long b) {
+            int64_t mn = INT64_MAX, mx = INT64_MIN;
+            for (size_t i = (size_t)b << SHIFT; i < std::min(n, ((size_t)b + 1) << SHIFT); ++i) { const int64_t k2 = key_of(v[i]); mn = std::min(mn, k2); mx = std::max(mx, k2); }
+            lo[(size_t)b] = mn; hi[(size_t)b] = mx;
+        });
+    }
+    inline void wrote(const T* p) {                                          // *p has just been overwritten
+        const size_t b = (size_t)(p - base) >> SHIFT;
+        const int64_t k2 = key_of(*p);
+        if (k2 < lo[b]) lo[b] = k2;
+        if (k2 > hi[b]) hi[b] = k2;
+    }
+};
+template <class T, class Less, class BI>
+T* find_up(T* lo, const T& pivot, Less less, BI* bi) {                        // first p >= lo with !less(*p, pivot) (exists)
     for (int i = 0; i < 256; ++i, ++lo) if (!less(*lo, pivot)) return lo;
-    const long n = end - lo, per = 16384, nch = (n + per - 1) / per;
-    if (threads <= 1 || nch < 4) { while (less(*lo, pivot)) ++lo; return lo; }
-    std::atomic<long> best(n);
-    parallel_chunks(threads, nch, [&](long c) {
-        if (c * per >= best.load(std::memory_order_relaxed)) return;
-        for (long i = c * per; i < std::min(n, (c + 1) * per); ++i)
-            if (!less(lo[i], pivot)) { long b = best.load(); while (i < b && !best.compare_exchange_weak(b, i)) {} return; }
-    });
-    return lo + best.load();
+    if (!bi) { while (less(*lo, pivot)) ++lo; return lo; }
+    const int64_t pk = bi->key_of(pivot);
+    for (;;) {
+        const size_t b = (size_t)(lo - bi->base) >> BI::SHIFT;
+        T* bend = const_cast<T*>(bi->base) + ((b + 1) << BI::SHIFT);          // (the scan ends before the array does)
+        if (bi->hi[b] >= pk) { for (; lo < bend; ++lo) if (!less(*lo, pivot)) return lo; }
+        lo = bend;
+    }
 }
-template <class T, class Less>
-T* find_down(T* hi, T* begin, const T& pivot, Less less, int threads) {       // last p <= hi with !less(pivot, *p); exists at or after `begin`
+template <class T, class Less, class BI>
+T* find_down(T* hi, const T& pivot, Less less, BI* bi) {                      // last p <= hi with !less(pivot, *p) (exists)
     for (int i = 0; i < 256; ++i, --hi) if (!less(pivot, *hi)) return hi;
-    const long n = hi - begin + 1, per = 16384, nch = (n + per - 1) / per;
-    if (threads <= 1 || nch < 4) { while (less(pivot, *hi)) --hi; return hi; }
-    std::atomic<long> best(-1);                                              // index from `begin`
-    parallel_chunks(threads, nch, [&](long c) {
-        const long c0 = nch - 1 - c;                                         // (high chunks first)
-        if ((c0 + 1) * per <= best.load(std::memory_order_relaxed)) return;
-        for (long i = std::min(n, (c0 + 1) * per) - 1; i >= c0 * per; --i)
-            if (!less(pivot, begin[i])) { long b = best.load(); while (i > b && !best.compare_exchange_weak(b, i)) {} return; }
-    });
-    return begin + best.load();
+    if (!bi) { while (less(pivot, *hi)) --hi; return hi; }
+    const int64_t pk = bi->key_of(pivot);
+    for (;;) {
+        const size_t b = (size_t)(hi - bi->base) >> BI::SHIFT;
+        T* bbeg = const_cast<T*>(bi->base) + (b << BI::SHIFT);
+        if (bi->lo[b] <= pk) { for (; hi >= bbeg; --hi) if (!less(pivot, *hi)) return hi; }
+        hi = bbeg - 1;
+    }
 }
-template <class T, class Less>
-T* partition_pivot_literal(T* first, T* last, Less less, int threads) {
+template <class T, class Less, class BI>
+T* partition_pivot_literal(T* first, T* last, Less less, BI* bi) {
     T* mid = first + (last - first) / 2;
     T *a = first + 1, *b = mid, *c = last - 1;                               // std::__move_median_to_first(first, a, b, c)
+    T* m = nullptr;
     if (less(*a, *b)) {
-        if (less(*b, *c)) std::iter_swap(first, b);
-        else if (less(*a, *c)) std::iter_swap(first, c);
-        else std::iter_swap(first, a);
-    } else if (less(*a, *c)) std::iter_swap(first, a);
-    else if (less(*b, *c)) std::iter_swap(first, c);
-    else std::iter_swap(first, b);
+        if (less(*b, *c)) m = b;
+        else if (less(*a, *c)) m = c;
+        else m = a;
+    } else if (less(*a, *c)) m = a;
+    else if (less(*b, *c)) m = c;
+    else m = b;
+    std::iter_swap(first, m);
+    if (bi) { bi->wrote(first); bi->wrote(m); }
     T* lo = first + 1;                                                       // std::__unguarded_partition(first + 1, last, first)
     T* hi = last;
     const T& pivot = *first;
     for (;;) {
-        lo = find_up(lo, last, pivot, less, threads);
+        lo = find_up(lo, pivot, less, bi);
         --hi;
-        hi = find_down(hi, first, pivot, less, threads);
+        hi = find_down(hi, pivot, less, bi);
         if (!(lo < hi)) return lo;
         std::iter_swap(lo, hi);
+        if (bi) { bi->wrote(lo); bi->wrote(hi); }
         ++lo;
     }
 }
@@ -208,6 +239,8 @@ void literal_sort_impl(T* v, size_t n, int threads, Less less, KeyOf key_of, con
         ranges.push_back(Range{v, v + n, (long)std::__lg((long)n) * 2, std::vector<int64_t>(), true});
         if (tie_keys) ranges[0].ties.assign(tie_keys, tie_keys + ntie);
         const long leaf = (long)std::max<size_t>(4096, n / ((size_t)std::max(1, threads) * 8));
+        std::unique_ptr<BlockIndex<T, KeyOf>> blocks;
+        if (tie_keys) blocks.reset(new BlockIndex<T, KeyOf>(v, n, key_of, threads));
         std::vector<size_t> big;
         std::vector<T*> cuts;
         auto count_key = [&](const T* f, const T* l, int64_t k) { long c = 0; for (; f != l; ++f) c += key_of(*f) == k; return c; };
@@ -221,8 +254,8 @@ void literal_sort_impl(T* v, size_t n, int threads, Less less, KeyOf key_of, con
             if (big.empty()) break;
             cuts.assign(big.size(), nullptr);
             if (tie_keys) {
-                // (few ranges, possibly long ones: one after the other, each with the pool for its long scans)
-                for (size_t b = 0; b < big.size(); ++b) cuts[b] = partition_pivot_literal(ranges[big[b]].first, ranges[big[b]].last, less, threads);
+                // (few ranges, possibly long ones: one after the other, long pointer scans skip through the block summaries)
+                for (size_t b = 0; b < big.size(); ++b) cuts[b] = partition_pivot_literal(ranges[big[b]].first, ranges[big[b]].last, less, blocks.get());
             } else {
                 parallel_chunks(threads, (long)big.size(), [&](long b) {
                     const Range& r = ranges[big[(size_t)b]];
