@@ -325,7 +325,9 @@ void literal_std_sort_by_first(std::pair<int64_t, int>* v, size_t n, int threads
     if (narrow) {
         const long per = 16384, nch = ((long)n + per - 1) / per;
         std::atomic<int> wide(0);
-        std::vector<uint64_t> w(n), wh(hint ? n : 0);
+        std::unique_ptr<uint64_t[]> w_(new uint64_t[n]), wh_(hint ? new uint64_t[n] : nullptr);      // (uninitialised: filled in parallel)
+        uint64_t* const w = w_.get();
+        uint64_t* const wh = wh_.get();
         parallel_chunks(n >= 65536 ? threads : 1, nch, [&](long c) {
             for (size_t i = (size_t)c * per; i < std::min(n, (size_t)(c + 1) * per); ++i) {
                 if ((uint64_t)v[i].first >> 32 || v[i].second < 0) { wide.store(1, std::memory_order_relaxed); break; }
@@ -334,8 +336,8 @@ void literal_std_sort_by_first(std::pair<int64_t, int>* v, size_t n, int threads
             }
         });
         if (!wide.load()) {
-            literal_sort_impl(w.data(), n, threads, [](uint64_t x, uint64_t y) { return (x >> 32) < (y >> 32); },
-                              [](uint64_t x) { return (int64_t)(x >> 32); }, tie_keys, ntie, hint ? wh.data() : (const uint64_t*)nullptr);
+            literal_sort_impl(w, n, threads, [](uint64_t x, uint64_t y) { return (x >> 32) < (y >> 32); },
+                              [](uint64_t x) { return (int64_t)(x >> 32); }, tie_keys, ntie, (const uint64_t*)wh);
             parallel_chunks(n >= 65536 ? threads : 1, nch, [&](long c) {
                 for (size_t i = (size_t)c * per; i < std::min(n, (size_t)(c + 1) * per); ++i) v[i] = P((int64_t)(w[i] >> 32), (int)(uint32_t)w[i]);
             });
