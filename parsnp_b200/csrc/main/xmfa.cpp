@@ -1,4 +1,5 @@
 #include "xmfa.h"
+#include <atomic>
 #include <sstream>
 #include <sys/stat.h>
 #include <sys/types.h>
@@ -44,7 +45,7 @@ bool write_xmfa(const XmfaInput& in, const std::string& path) {
     auto MF = [&](int64_t m, int i) { return in.mfwd[(size_t)m * n + i] != 0; };
 
     // ---- alignment assembly per LCB (src/parsnp.cpp:646-919); MUSCLE runs on the inter-MUM regions
-    bool muscle_failed = false;
+    std::atomic<bool> muscle_failed(false);          // (set from the OpenMP threads of the loop below)
 #pragma omp parallel for schedule(dynamic) num_threads(in.cores > 0 ? in.cores : 1)
     for (int64_t z = 0; z < K; z++) {
         const int64_t m0 = in.cmum_off[z], m1 = in.cmum_off[z + 1];
@@ -85,7 +86,7 @@ bool write_xmfa(const XmfaInput& in, const std::string& path) {
                         for (int j = 0; j < n; j++) T[j].append(reg[j]);       // total_skipped (0) >= nnum-1 only when nnum == 1
                     } else {
                         std::vector<std::string> res;
-                        if (!muscle_align(reg, res)) muscle_failed = true;
+                        if (!muscle_align(reg, res)) muscle_failed.store(true, std::memory_order_relaxed);
                         for (size_t i = 0; i < res.size() && i < (size_t)n; i++) T[i].append(res[i]);
                     }
                 } else if (maxl > 0) {
@@ -103,7 +104,7 @@ bool write_xmfa(const XmfaInput& in, const std::string& path) {
             }
         }
     }
-    if (muscle_failed) return false;
+    if (muscle_failed.load()) return false;
 
     // ---- recombfilter: blocks/ and one directory per LCB that has MUMs (src/parsnp.cpp:538-543, 605-644)
     const std::string lcbprefix = in.outdir + "/blocks/b";
