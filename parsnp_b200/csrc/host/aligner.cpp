@@ -188,8 +188,10 @@ void Aligner::CoordIndex::reserve(size_t entries) {
 }
 void Aligner::CoordIndex::build_parallel(const std::vector<uint64_t>& hashes, const std::vector<uint8_t>& valid, int threads) {
     const size_t N = hashes.size();
+    size_t nvalid = 0;
+    for (size_t r = 0; r < N; ++r) nvalid += valid[r] != 0;       // (the table is sized by what goes in: the replay indexes a tenth of the regions)
     size_t need = 1024;
-    while (need < N * 2 + 2) need *= 2;
+    while (need < nvalid * 2 + 2) need *= 2;
     s.resize(need);
     const long per = 8192;
     parallel_chunks(need > 65536 ? threads : 1, ((long)need + per - 1) / per, [&](long c) {

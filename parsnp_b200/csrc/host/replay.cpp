@@ -489,15 +489,30 @@ void ReplayCtx::classify_gaps() {
 // the engine's accepted MUMs of gap j into the task's output and the layout, in the reference's pop order
 void ReplayCtx::apply_final_gap(ReplayTask& T, MumPool& MP, int j, const int64_t* lo, const int64_t* hi) {
     const Aligner::DeviceDecisions& D = A.dev_;
-    const size_t stride = 2 * (size_t)n;
+    const size_t stride = 2 * (size_t)n, N = (size_t)n;
     const int nq = n - 1;
-    int64_t st_buf[64];
-    std::vector<int64_t> st_vec;
-    int64_t* st = st_buf;
-    if (n > 64) { st_vec.resize((size_t)n); st = st_vec.data(); }
-    for (size_t r = (size_t)gr0[(size_t)j]; r < (size_t)gr1[(size_t)j]; ++r) {
+    const size_t r0 = (size_t)gr0[(size_t)j], r1 = (size_t)gr1[(size_t)j];
+    // room for the gap's MUMs first (their number is known), then filled through plain pointers
+    size_t cnt = 0;
+    for (size_t r = r0; r < r1; ++r) {
+        const WindowRec& w = D.wins[r];
+        const int32_t* sh = D.acc_shift + w.cand_off;
+        for (int32_t c = 0; c < w.ncand; ++c) cnt += sh[c] >= 0;
+    }
+    ++T.final_gaps;
+    if (!cnt) return;
+    const size_t m0 = MP.mums.size(), s0 = MP.start.size();
+    MP.mums.resize(m0 + cnt);
+    MP.start.resize(s0 + cnt * N);
+    MP.fwd.resize(s0 + cnt * N);
+    std::memset(&MP.fwd[s0], 1, cnt * N);
+    MumRec* mrec = &MP.mums[m0];
+    int64_t* st = &MP.start[s0];
+    int64_t off = (int64_t)s0;
+    for (size_t r = r0; r < r1; ++r) {
         const WindowRec& w = D.wins[r];
         const int64_t* rs = D.coords + r * stride;
+        const int64_t rsl = D.slen[r];
         for (int32_t c = 0; c < w.ncand; ++c) {
             const size_t ci = (size_t)w.cand_off + (size_t)c;
             const int64_t sh = D.acc_shift[ci];
@@ -507,22 +522,26 @@ void ReplayCtx::apply_final_gap(ReplayTask& T, MumPool& MP, int j, const int64_t
             const int32_t* sp = D.sp + ci * (size_t)nq;
             for (int g = 1; g < n; ++g) st[g] = rs[g] + sp[g - 1] + sh;
             for (int g = 0; g < n; ++g) {
-                if (st[g] < lo[g] || st[g] + length > hi[g] + 1 || length < 2) throw std::logic_error("parsnp_b200: a MUM of a final gap lies outside its task");
-                truth[(size_t)g].set_range_owned(st[g], st[g] + length, lo[g] >> 6, hi[g] >> 6);
+                const int64_t a = st[g], b = a + length;
+                if (a < lo[g] || b > hi[g] + 1 || length < 2) throw std::logic_error("parsnp_b200: a MUM of a final gap lies outside its task");
+                const int64_t wa = a >> 6, wb = (b - 1) >> 6;
+                if (wa == wb && wa > (lo[g] >> 6) && wa < (hi[g] >> 6)) {
+                    // (one word strictly inside the task's span - the rule: this task is its only writer)
+                    uint64_t* word = truth[(size_t)g].words_mut() + wa;
+                    __atomic_store_n(word, __atomic_load_n(word, __ATOMIC_RELAXED) | ((~0ull << (a & 63)) & (~0ull >> (63 - ((b - 1) & 63)))), __ATOMIC_RELAXED);
+                } else truth[(size_t)g].set_range_owned(a, b, lo[g] >> 6, hi[g] >> 6);
             }
-            MumRec m;
-            m.length = length;
-            m.slength = D.slen[r];
-            m.off = (int64_t)MP.start.size();
-            m.alive = true;
-            MP.start.insert(MP.start.end(), st, st + n);
-            MP.fwd.insert(MP.fwd.end(), (size_t)n, (uint8_t)1);
-            MP.mums.push_back(m);
-            ++T.final_mums;
+            mrec->length = length;
+            mrec->slength = rsl;
+            mrec->off = off;
+            mrec->alive = true;
+            ++mrec;
+            st += N;
+            off += (int64_t)N;
         }
     }
+    T.final_mums += (int64_t)cnt;
     T.mend = MP.mums.size();
-    ++T.final_gaps;
 }
 
 namespace {
