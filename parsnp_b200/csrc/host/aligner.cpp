@@ -1602,7 +1602,7 @@ bool Aligner::discover_slice(int k) {
     if (!copy && res.flags && res.parent && res.acc_shift && res.acc_len && res.dropped == 0 && res.nfw <= res.fw_cap && !getenv("PB200_NO_DEVICE_FINAL")) {
         dev_.valid = true;
         dev_.nregions = NR; dev_.ncands = NC; dev_.nfw = res.nfw;
-        dev_.coords = res.coords; dev_.slen = res.slen; dev_.wins = res.wins; dev_.k = res.k; dev_.sp = res.sp;
+        dev_.coords = res.coords; dev_.slen = res.slen; dev_.wins = res.wins; dev_.k = res.k; dev_.lon = res.lon; dev_.sp = res.sp; dev_.fwd = res.fwd;
         dev_.flags = res.flags; dev_.parent = res.parent; dev_.acc_shift = res.acc_shift; dev_.acc_len = res.acc_len; dev_.fw = res.fw;
     }
     // (the index over the regions' coordinates: built right away, or - when the replay may take most gaps from the engine as final -

@@ -305,7 +305,7 @@ private:
         bool valid = false;
         size_t nregions = 0, ncands = 0, nfw = 0;
         const int64_t* coords = nullptr; const int64_t* slen = nullptr; const WindowRec* wins = nullptr;
-        const int32_t* k = nullptr; const int32_t* sp = nullptr;
+        const int32_t* k = nullptr; const int32_t* lon = nullptr; const int32_t* sp = nullptr; const uint8_t* fwd = nullptr;
         const uint32_t* flags = nullptr; const int32_t* parent = nullptr; const int32_t* acc_shift = nullptr; const int32_t* acc_len = nullptr;
         const int32_t* fw = nullptr;
     } dev_;

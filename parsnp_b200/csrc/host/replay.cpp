@@ -30,7 +30,7 @@
 // FINAL GAPS.  When the engine followed the recursion itself (cuda/recursion.cuh) it has already run loop D + determineRegion
 // for every region it discovered, on a scratch layout and level by level instead of in the reference's order.  Inside one gap
 // that difference cannot matter when (a) no candidate that reached the trim loop had a reverse-strand genome (everything read
-// and written lies inside the region), (b) the accepted MUMs of every region ascend in every genome (sibling sub-regions are
+// and written lies inside the region) - or every such candidate dies on the anchors alone (foreign_harmless below) -, (b) the accepted MUMs of every region ascend in every genome (sibling sub-regions are
 // disjoint: they commute), (c) the two overlapping regions of a gap pair were searched in the reference's order by one CTA and
 // the second one accepted nothing (more bits only trim more: it accepts nothing in the reference's order either), and (d) no
 // MUM of another gap was written into the gap's span - neither on the device (its list of writes outside their region) nor
@@ -132,6 +132,7 @@ struct ReplayCtx {
     std::vector<int32_t> gr0, gr1;
     std::unique_ptr<std::atomic<uint8_t>[]> gtouched;
     void classify_gaps();
+    bool foreign_harmless(size_t r) const;
     void mark_touched(int g, int64_t a, int64_t b);
     void apply_final_gap(ReplayTask& T, MumPool& MP, int j, const int64_t* lo, const int64_t* hi);
     std::unique_ptr<ReplayTask::FRead[]> log_slab;
@@ -422,6 +423,59 @@ void ReplayCtx::mark_touched(int g, int64_t a, int64_t b) {
     for (int j = lo; j < ngaps && (int64_t)glo[(size_t)j * n + g] <= b - 1; ++j) gtouched[j].store(1, std::memory_order_relaxed);
 }
 
+// A region the engine flagged because a candidate with a reverse-strand genome reached its trim loop: harmless if every such
+// candidate trims to nothing already on the layout that holds ONLY the anchors (= `truth` before the first task runs).  Bits
+// are only ever added during the recursion, and the interval that survives the trim loop on a layout with more bits lies
+// inside the one that survives with fewer (start and end only move inwards, genome after genome): such a candidate is
+// rejected on the engine's scratch layout and on the reference's layout alike, whatever they hold at that moment - it read
+// foreign positions, but nothing depends on what it saw, and it wrote nothing.
+bool ReplayCtx::foreign_harmless(size_t r) const {
+    const Aligner::DeviceDecisions& D = A.dev_;
+    if (!D.lon || !D.fwd) return false;
+    const int nq = n - 1;
+    const WindowRec& w = D.wins[r];
+    const int64_t* rs = D.coords + r * 2 * (size_t)n;
+    const int64_t* re = rs + n;
+    int64_t st_buf[64];
+    std::vector<int64_t> st_vec;
+    int64_t* st = st_buf;
+    if (n > 64) { st_vec.resize((size_t)n); st = st_vec.data(); }
+    for (int32_t c = 0; c < w.ncand; ++c) {
+        const size_t ci = (size_t)w.cand_off + (size_t)c;
+        const uint8_t* fwj = D.fwd + ci * (size_t)nq;
+        bool rev = false;
+        for (int j = 0; j < nq; ++j) rev |= !fwj[j];
+        if (!rev) continue;
+        // the checks that precede the trim loop (accept_impl.h; src/parsnp.cpp:1723, src/TMum.cpp:13-72)
+        const int64_t LON = D.lon[ci];
+        const uint64_t dsp0 = (uint64_t)((int64_t)D.k[ci] + 1 + w.ref_start);
+        bool bad = (uint64_t)(dsp0 - (uint64_t)rs[0]) > (uint64_t)(uint32_t)(re[0] - rs[0]);
+        st[0] = (int64_t)dsp0 - 1;
+        bool any_fail = st[0] + LON > A.len_[0] || st[0] < 0;
+        const int32_t* spj = D.sp + ci * (size_t)nq;
+        for (int j = 1; j < n; ++j) {
+            const uint64_t dsp = (uint64_t)((int64_t)spj[j - 1] + 1 + rs[j]);
+            bad |= (uint64_t)(dsp - (uint64_t)rs[j]) > (uint64_t)(uint32_t)(re[j] - rs[j]);
+            int64_t s2 = (int64_t)dsp - 1;
+            if (!fwj[j - 1]) s2 = A.len_[(size_t)j] - (s2 + LON);
+            any_fail |= (s2 + LON > A.len_[(size_t)j]) | (s2 < 0);
+            st[j] = s2;
+        }
+        if (bad || any_fail || LON < 5) continue;            // never reaches the trim loop
+        if (D.acc_shift[ci] >= 0) return false;              // the engine accepted it: where it was placed depends on what it saw
+        int64_t length = LON;
+        for (int j = 0; j < n; ++j) {
+            const int64_t t1 = truth[(size_t)j].run_up(st[j], st[j] + length);
+            if (t1) { for (int i = 0; i < n; ++i) st[i] += t1; length -= t1; }
+            const int64_t t2 = truth[(size_t)j].run_down(st[j], st[j] + length);
+            length -= t2;
+            if (length <= 0) break;
+        }
+        if (length >= 2) return false;                       // survives on the anchors alone: later bits decide
+    }
+    return true;
+}
+
 // which gaps may take the engine's accept decisions as final (conditions (a)-(d) at the head of the file; the dynamic part of
 // (d) is checked again when the gap's turn comes)
 void ReplayCtx::classify_gaps() {
@@ -447,13 +501,20 @@ void ReplayCtx::classify_gaps() {
         return a;
     };
     std::atomic<int> some(0);
+    static const bool why = getenv("PB200_REPLAY_DEBUG") != nullptr;
+    std::atomic<long> reason[8];
+    for (auto& x : reason) x.store(0);
+    // (opt-in: on configs[1] it turns 778 of the 3 270 replayed gaps into final ones - the anchors cover less than half of the
+    //  genomes there, so most mirrored candidates do survive on them - and the check costs the classification more (+0.9 ms on
+    //  4 threads) than the tasks gain (0.1 ms))
+    const bool harmless_ok = getenv("PB200_HARMLESS_FOREIGN") != nullptr;
     const long per = 512;
     parallel_chunks(ngaps > 2048 ? A.threads_ : 1, ((long)ngaps + per - 1) / per, [&](long c) {
         bool mine = false;
         // (gap 0 stays with the replay: the reference's first pop precedes its first sort, see run_task)
         for (int j = std::max<int>(1, (int)(c * per)); j < std::min<int>(ngaps, (int)((c + 1) * per)); ++j) {
             const int p0 = gcut[(size_t)j], p1 = gcut[(size_t)j + 1], ni = p1 - p0;
-            if (ni > 2 || gtouched[j].load(std::memory_order_relaxed)) continue;
+            if (ni > 2 || gtouched[j].load(std::memory_order_relaxed)) { if (why) reason[ni > 2 ? 0 : 1]++; continue; }
             const size_t r0 = first_at_least(glo[(size_t)j * n]), r1 = first_at_least(ghi[(size_t)j * n]);
             if (r1 - r0 < (size_t)ni || r1 > (size_t)INT32_MAX) continue;
             bool ok = true;
@@ -463,7 +524,8 @@ void ReplayCtx::classify_gaps() {
                 const uint32_t f = D.flags[r];
                 const WindowRec& w = D.wins[r];
                 const int64_t* rc = D.coords + r * stride;
-                ok = !(f & REC_ORDER_MASK) && w.ncand >= 0 && (uint64_t)w.cand_off + (uint64_t)w.ncand <= D.ncands && rc[0] > prev;
+                ok = w.ncand >= 0 && (uint64_t)w.cand_off + (uint64_t)w.ncand <= D.ncands && rc[0] > prev;
+                if (ok && (f & REC_ORDER_MASK)) ok = (f & REC_ORDER_MASK) == 1u && harmless_ok && foreign_harmless(r);      // (1 = only "a reverse-strand candidate reached the trim loop")
                 prev = rc[0];
                 const int par = D.parent[r];
                 if (par < 0) {
@@ -475,7 +537,15 @@ void ReplayCtx::classify_gaps() {
                     if (f & REC_SECOND) ++nsecond;
                 } else if ((size_t)par < r0 || (size_t)par >= r1) ok = false;
             }
-            if (!ok || ninit != ni || (ni == 2 && nsecond != 1)) continue;
+            if (!ok || ninit != ni || (ni == 2 && nsecond != 1)) {
+                if (why) {
+                    uint32_t fl = 0;
+                    bool unsearched = false;
+                    for (size_t r = r0; r < r1; ++r) { fl |= D.flags[r] & REC_ORDER_MASK; unsearched |= D.wins[r].ncand < 0; }
+                    reason[unsearched ? 2 : (fl & 1) ? 3 : (fl & 2) ? 4 : (fl & 4) ? 5 : (fl & 8) ? 6 : 7]++;
+                }
+                continue;
+            }
             gfinal[(size_t)j] = 1;
             gr0[(size_t)j] = (int32_t)r0;
             gr1[(size_t)j] = (int32_t)r1;
@@ -484,6 +554,9 @@ void ReplayCtx::classify_gaps() {
         if (mine) some.store(1, std::memory_order_relaxed);
     });
     any_final = some.load() != 0;
+    if (why) fprintf(stderr, "[pb200 replay] gaps kept for the replay: >2 initial regions %ld, touched by a foreign write %ld, unsearched region %ld, "
+                             "reverse-strand candidate %ld, second of a pair accepted %ld, accepts not collinear %ld, requeued %ld, other %ld\n",
+                     reason[0].load(), reason[1].load(), reason[2].load(), reason[3].load(), reason[4].load(), reason[5].load(), reason[6].load(), reason[7].load());
 }
 
 // the engine's accepted MUMs of gap j into the task's output and the layout, in the reference's pop order

@@ -56,7 +56,7 @@ def test_cuda_final_gaps_fuzz(seed0, monkeypatch):
         div = float(rng.choice([0.01, 0.03, 0.05]))
         g = (synth.g_indep if rng.random() < 0.6 else synth.g_pop)(L, nq, div, int(rng.integers(1, 10**6)))
         if rng.random() < 0.3:
-            a = int(rng.integers(0, L - 400)); ln = int(rng.integers(30, 300))
+            a = int(rng.integers(0, L - 400)); ln = int(rng.integers(30, 300)); a = min(a, L - 2 * ln)
             for x in g:
                 x[a + ln:a + 2 * ln] = synth.revcomp(x[a:a + ln])
         kw = dict(mums=str(rng.choice(["8", "10", "12", "1.1*(Log(S))", "0.7*(Log(S))"])), q=int(rng.choice([10, 30])))

@@ -23,7 +23,7 @@ for seed in range(s0, s0 + nc):
     div = float(rng.choice([0.01, 0.03, 0.05]))
     g = (synth.g_indep if rng.random() < 0.6 else synth.g_pop)(L, nq, div, int(rng.integers(1, 10**6)))
     if rng.random() < 0.3:
-        a = int(rng.integers(0, L - 400)); ln = int(rng.integers(30, 300))
+        a = int(rng.integers(0, L - 400)); ln = int(rng.integers(30, 300)); a = min(a, L - 2 * ln)
         for x in g:
             x[a + ln:a + 2 * ln] = synth.revcomp(x[a:a + ln])
     if rng.random() < 0.2:
